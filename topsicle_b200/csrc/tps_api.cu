@@ -1,0 +1,459 @@
+/*
+ * tps_api.cu -- C-ABI (include/topsicle_b200.h) over the sm_100a kernels.
+ *
+ * One tps_ctx owns `n_slots` independent batch slots, each with its own CUDA stream,
+ * device buffers and pinned result staging, so that H2D of batch i+1 overlaps the kernels
+ * of batch i and the D2H of batch i-1 (async H2D / compute / D2H pipeline per device).
+ * There is no CPU fallback: without a CUDA device tps_create fails with TPS_ENODEVICE.
+ */
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+
+#include "tps_kernels.cuh"
+
+namespace {
+
+thread_local char g_create_error[512] = "";
+
+struct Slot {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr;
+  uint8_t *d_bases = nullptr;
+  uint32_t *d_codes = nullptr;
+  uint32_t *d_flags = nullptr;
+  uint16_t *d_masks = nullptr;
+  uint64_t *d_off = nullptr;
+  tps_row *d_rows = nullptr;
+  uint32_t *d_pass = nullptr;
+  uint32_t *d_counters = nullptr;
+  uint8_t *d_raw = nullptr;
+  uint32_t *d_cw_scratch = nullptr;
+  tps_row *h_rows = nullptr;        /* pinned */
+  uint32_t *h_counters = nullptr;   /* pinned */
+  uint64_t batch_id = 0;
+  uint32_t n_reads = 0;
+  bool busy = false;
+};
+
+}  // namespace
+
+struct tps_ctx {
+  int device = 0;
+  tps_params p;
+  TpsPatTable pt;
+  int n_sms = 0;
+  uint32_t k2_lin_words = 0, k2_nq_max = 0, k2_smem = 0;
+  uint32_t k3_lin_words = 0, k3_tile_words = 0, k3_smem = 0, k3_grid = 0;
+  uint32_t cw_stride = 0, cw_in_smem = 0;
+  int k1_grid = 0;
+  uint64_t cap_tiles = 0;
+  Slot slots[4];
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool ev_valid = false;
+  uint64_t launches = 0;
+  char err[512] = "";
+};
+
+namespace {
+
+int fail(tps_ctx *ctx, int code, const char *fmt, ...) {
+  char *dst = ctx ? ctx->err : g_create_error;
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(dst, 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define TPS_CUDA(ctx, call)                                                                     \
+  do {                                                                                          \
+    cudaError_t e_ = (call);                                                                    \
+    if (e_ != cudaSuccess)                                                                      \
+      return fail(ctx, e_ == cudaErrorMemoryAllocation ? TPS_ENOMEM : TPS_ECUDA, "%s: %s", #call, \
+                  cudaGetErrorString(e_));                                                      \
+  } while (0)
+
+uint32_t lin_words_for(uint64_t n_max) {
+  uint64_t ng = (n_max + 30) / 16 + 1;
+  return (uint32_t)((2 + ng + 1) / 2 + 2);
+}
+
+int build_pattern_table(const tps_params *p, TpsPatTable *pt) {
+  memset(pt, 0, sizeof(*pt));
+  if (p->n_patterns < 1 || p->n_patterns > TPS_MAX_PATTERNS)
+    return fail(nullptr, TPS_EINVAL, "n_patterns must be in 1..%d", TPS_MAX_PATTERNS);
+  pt->n = p->n_patterns;
+  for (uint32_t i = 0; i < p->n_patterns; ++i) {
+    uint32_t k = p->pattern_len[i];
+    if (k < 1 || k > TPS_MAX_PATTERN_LEN)
+      return fail(nullptr, TPS_EINVAL, "pattern %u: length %u not in 1..%d", i, k, TPS_MAX_PATTERN_LEN);
+    pt->len[i] = (uint8_t)k;
+    for (uint32_t j = 0; j < k; ++j) {
+      uint32_t c = tps_ascii_code((uint8_t)p->patterns[i][j]);
+      if (c == 0xFFu)
+        return fail(nullptr, TPS_EINVAL, "pattern %u has a non-ACGT character (regex metacharacters and "
+                                         "'|' patterns are undefined in the reference)", i);
+      pt->lo[i] |= (c & 1u) << j;
+      pt->hi[i] |= ((c >> 1) & 1u) << j;
+    }
+    /* proper border <=> two occurrences can overlap <=> greedy != count of all occurrences */
+    bool bordered = false;
+    for (uint32_t b = 1; b < k && !bordered; ++b) {
+      bool eq = true;
+      for (uint32_t j = 0; j < b && eq; ++j)
+        eq = tps_ascii_code((uint8_t)p->patterns[i][j]) == tps_ascii_code((uint8_t)p->patterns[i][k - b + j]);
+      bordered = eq;
+    }
+    pt->bordered[i] = bordered;
+    if (bordered) pt->brow[i] = (uint8_t)pt->n_bordered++;
+  }
+  return TPS_OK;
+}
+
+int log2_ceil(uint64_t v) {
+  int b = 0;
+  while (b < 64 && (1ull << b) < v) ++b;
+  return b;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tps_abi_version(void) { return TPS_ABI_VERSION; }
+
+const char *tps_build_info(void) {
+  return "topsicle_b200 sm_100a; kernels: tps_pack_kernel, tps_trc_kernel, tps_window_kernel; " __DATE__;
+}
+
+const char *tps_last_error(const tps_ctx *ctx) { return ctx ? ctx->err : g_create_error; }
+
+void *tps_alloc_pinned(size_t bytes) {
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+
+void tps_free_pinned(void *p) {
+  if (p) cudaFreeHost(p);
+}
+
+void tps_destroy(tps_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  for (int i = 0; i < 4; ++i) {
+    Slot &s = ctx->slots[i];
+    if (s.stream) cudaStreamSynchronize(s.stream);
+    cudaFree(s.d_bases); cudaFree(s.d_codes); cudaFree(s.d_flags); cudaFree(s.d_masks);
+    cudaFree(s.d_off); cudaFree(s.d_rows); cudaFree(s.d_pass); cudaFree(s.d_counters);
+    cudaFree(s.d_raw); cudaFree(s.d_cw_scratch);
+    if (s.h_rows) cudaFreeHost(s.h_rows);
+    if (s.h_counters) cudaFreeHost(s.h_counters);
+    if (s.done) cudaEventDestroy(s.done);
+    if (s.stream) cudaStreamDestroy(s.stream);
+  }
+  for (int i = 0; i < 4; ++i)
+    if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  delete ctx;
+}
+
+int tps_create(tps_ctx **out, int device, const tps_params *params) {
+  if (!out || !params) return fail(nullptr, TPS_EINVAL, "null argument");
+  *out = nullptr;
+  if (params->struct_size != sizeof(tps_params))
+    return fail(nullptr, TPS_EINVAL, "tps_params.struct_size %u != %zu (ABI mismatch)", params->struct_size,
+                sizeof(tps_params));
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(nullptr, TPS_ENODEVICE, "no CUDA device visible; topsicle_b200 has no CPU fallback");
+  }
+  if (device < 0 || device >= ndev) return fail(nullptr, TPS_EINVAL, "device %d out of range (0..%d)", device, ndev - 1);
+  const tps_params &p = *params;
+  if (p.window_size < 1 || p.window_size > 8192) return fail(nullptr, TPS_EINVAL, "window_size must be in 1..8192");
+  if (p.slide < 1) return fail(nullptr, TPS_EINVAL, "slide must be >= 1");
+  if (p.no_bp < 1 || p.no_bp > 32768) return fail(nullptr, TPS_EINVAL, "no_bp must be in 1..32768");
+  if (p.n_slots < 1 || p.n_slots > 4) return fail(nullptr, TPS_EINVAL, "n_slots must be in 1..4");
+  if (p.max_batch_reads < 1 || p.max_batch_bases < 1) return fail(nullptr, TPS_EINVAL, "batch capacities must be >= 1");
+  TpsPatTable pt;
+  int rc = build_pattern_table(&p, &pt);
+  if (rc) return rc;
+  uint32_t kmin = 255;
+  for (uint32_t i = 0; i < pt.n; ++i) kmin = pt.len[i] < kmin ? pt.len[i] : kmin;
+  const uint32_t cnt_max = (p.window_size - 1) / kmin > 0 ? (p.window_size - 1) / kmin : 1;
+  if (p.want_rawcount && cnt_max > 255)
+    return fail(nullptr, TPS_EINVAL, "want_rawcount needs (window_size-1)/min(pattern_len) <= 255");
+  /* windows of the longest possible region */
+  const uint64_t reg_max = p.maxlengthtelo > p.trimfirst ? (uint64_t)p.maxlengthtelo - p.trimfirst : 0;
+  const uint64_t nw_max = reg_max >= p.window_size ? (reg_max - p.window_size) / p.slide + 1 : 0;
+  if (nw_max > 0xFFFFFFF0ull / 4) return fail(nullptr, TPS_EINVAL, "too many windows per read");
+  /* exact change-point compare needs n^6 * cmax^2 < 2^128 (see tps_bitops.h) */
+  if (6 * log2_ceil(nw_max ? nw_max : 1) + 2 * log2_ceil((uint64_t)cnt_max * pt.n) >= 128)
+    return fail(nullptr, TPS_EINVAL, "maxlengthtelo/slide/windowSize combination exceeds the exact "
+                                     "128-bit change-point range (%llu windows)", (unsigned long long)nw_max);
+
+  tps_ctx *ctx = new (std::nothrow) tps_ctx();
+  if (!ctx) return fail(nullptr, TPS_ENOMEM, "out of host memory");
+  ctx->device = device;
+  ctx->p = p;
+  ctx->pt = pt;
+#define TPS_CC(call)                                                               \
+  do {                                                                             \
+    cudaError_t e_ = (call);                                                       \
+    if (e_ != cudaSuccess) {                                                       \
+      int c_ = fail(nullptr, e_ == cudaErrorMemoryAllocation ? TPS_ENOMEM : TPS_ECUDA, "%s: %s", #call, \
+                    cudaGetErrorString(e_));                                       \
+      tps_destroy(ctx);                                                            \
+      return c_;                                                                   \
+    }                                                                              \
+  } while (0)
+  TPS_CC(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  TPS_CC(cudaGetDeviceProperties(&prop, device));
+  ctx->n_sms = prop.multiProcessorCount;
+
+  /* K2 geometry */
+  ctx->k2_lin_words = lin_words_for(p.no_bp);
+  ctx->k2_nq_max = (p.no_bp + 31) / 32;
+  ctx->k2_smem = TPS_K2_WARPS * (3 * ctx->k2_lin_words + pt.n_bordered * ctx->k2_nq_max + TPS_MAX_PATTERNS) * 4;
+  /* K3 geometry */
+  const uint32_t tile_n = TPS_K3_TILE_BASES + p.window_size;
+  ctx->k3_lin_words = lin_words_for(tile_n);
+  ctx->k3_tile_words = (tile_n + 31) / 32 + 1;
+  uint32_t k3_words = 3 * ctx->k3_lin_words + 3 * ctx->k3_tile_words + pt.n * ctx->k3_tile_words;
+  ctx->cw_stride = (uint32_t)(nw_max ? nw_max : 1);
+  const uint32_t smem_limit = (uint32_t)prop.sharedMemPerBlockOptin;
+  ctx->cw_in_smem = ((uint64_t)(k3_words + ctx->cw_stride) * 4 <= 96 * 1024) ? 1u : 0u;
+  if (ctx->cw_in_smem) k3_words += ctx->cw_stride;
+  ctx->k3_smem = k3_words * 4;
+  if (ctx->k2_smem > smem_limit || ctx->k3_smem > smem_limit) {
+    int c_ = fail(nullptr, TPS_EINVAL, "parameters need %u / %u bytes of shared memory (limit %u)", ctx->k2_smem,
+                  ctx->k3_smem, smem_limit);
+    tps_destroy(ctx);
+    return c_;
+  }
+  TPS_CC(cudaFuncSetAttribute(tps_trc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->k2_smem));
+  TPS_CC(cudaFuncSetAttribute(tps_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->k3_smem));
+  int occ1 = 0, occ3 = 0;
+  TPS_CC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, tps_pack_kernel, TPS_K1_THREADS, 0));
+  TPS_CC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3, tps_window_kernel, TPS_K3_THREADS, ctx->k3_smem));
+  ctx->k1_grid = ctx->n_sms * (occ1 > 0 ? occ1 : 1);
+  ctx->k3_grid = (uint32_t)(ctx->n_sms * (occ3 > 0 ? occ3 : 1));
+
+  ctx->cap_tiles = (p.max_batch_bases + 511) / 512;
+  const uint64_t cap_pad = ((p.max_batch_bases + 2047) / 2048) * 2048;
+  for (uint32_t i = 0; i < p.n_slots; ++i) {
+    Slot &s = ctx->slots[i];
+    TPS_CC(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    TPS_CC(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    TPS_CC(cudaMalloc(&s.d_bases, cap_pad));
+    TPS_CC(cudaMemset(s.d_bases, 'N', cap_pad));
+    TPS_CC(cudaMalloc(&s.d_codes, ctx->cap_tiles * 32 * sizeof(uint32_t)));
+    TPS_CC(cudaMalloc(&s.d_flags, ctx->cap_tiles * sizeof(uint32_t)));
+    TPS_CC(cudaMalloc(&s.d_masks, ctx->cap_tiles * 32 * sizeof(uint16_t)));
+    TPS_CC(cudaMalloc(&s.d_off, ((uint64_t)p.max_batch_reads + 1) * sizeof(uint64_t)));
+    TPS_CC(cudaMalloc(&s.d_rows, (uint64_t)p.max_batch_reads * sizeof(tps_row)));
+    TPS_CC(cudaMalloc(&s.d_pass, (uint64_t)p.max_batch_reads * sizeof(uint32_t)));
+    TPS_CC(cudaMalloc(&s.d_counters, 8 * sizeof(uint32_t)));
+    if (p.want_rawcount) TPS_CC(cudaMalloc(&s.d_raw, p.rawcount_capacity ? p.rawcount_capacity : 1));
+    if (!ctx->cw_in_smem)
+      TPS_CC(cudaMalloc(&s.d_cw_scratch, (uint64_t)ctx->k3_grid * ctx->cw_stride * sizeof(uint32_t)));
+    TPS_CC(cudaHostAlloc(&s.h_rows, (uint64_t)p.max_batch_reads * sizeof(tps_row), cudaHostAllocDefault));
+    TPS_CC(cudaHostAlloc(&s.h_counters, 8 * sizeof(uint32_t), cudaHostAllocDefault));
+  }
+  for (int i = 0; i < 4; ++i) TPS_CC(cudaEventCreate(&ctx->ev[i]));
+#undef TPS_CC
+  *out = ctx;
+  return TPS_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+/* Enqueue K1..K4 for one batch on `st`.  d_bases/d_off may be slot- or caller-owned. */
+int enqueue_scan(tps_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t *d_bases, const uint64_t *d_off,
+                 uint32_t n_reads, uint64_t n_bases, tps_row *d_rows, bool timed) {
+  const tps_params &p = ctx->p;
+  TPS_CUDA(ctx, cudaMemsetAsync(s.d_counters, 0, 8 * sizeof(uint32_t), st));
+  if (timed) TPS_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
+  const uint64_t n_tiles = (n_bases + 511) / 512;
+  if (n_tiles) {
+    uint64_t want = (n_tiles + (TPS_K1_THREADS / 32) * TPS_K1_UNROLL - 1) / ((TPS_K1_THREADS / 32) * TPS_K1_UNROLL);
+    int grid = (int)(want < (uint64_t)ctx->k1_grid ? want : (uint64_t)ctx->k1_grid);
+    tps_pack_kernel<<<grid, TPS_K1_THREADS, 0, st>>>(reinterpret_cast<const uint4 *>(d_bases), s.d_codes, s.d_flags,
+                                                     s.d_masks, n_tiles);
+    ctx->launches++;
+  }
+  if (timed) TPS_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
+  TpsScanArgs a;
+  memset(&a, 0, sizeof(a));
+  a.pk.codes = s.d_codes;
+  a.pk.flags = s.d_flags;
+  a.pk.masks = s.d_masks;
+  a.offsets = d_off;
+  a.n_reads = n_reads;
+  a.rows = d_rows;
+  a.pass_list = s.d_pass;
+  a.counters = s.d_counters;
+  a.min_seq_length = p.min_seq_length;
+  a.no_bp = p.no_bp;
+  a.count_threshold = p.count_threshold;
+  a.W = p.window_size;
+  a.slide = p.slide;
+  a.trimfirst = p.trimfirst;
+  a.maxlengthtelo = p.maxlengthtelo;
+  a.want_rawcount = p.want_rawcount;
+  a.raw = s.d_raw;
+  a.raw_capacity = p.want_rawcount ? p.rawcount_capacity : 0;
+  a.cw_scratch = s.d_cw_scratch;
+  a.cw_stride = ctx->cw_stride;
+  a.cw_in_smem = ctx->cw_in_smem;
+  a.nq_max = ctx->k2_nq_max;
+  if (n_reads) {
+    a.lin_words = ctx->k2_lin_words;
+    tps_trc_kernel<<<(n_reads + TPS_K2_WARPS - 1) / TPS_K2_WARPS, TPS_K2_WARPS * 32, ctx->k2_smem, st>>>(a, ctx->pt);
+    ctx->launches++;
+  }
+  if (timed) TPS_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
+  if (n_reads) {
+    a.lin_words = ctx->k3_lin_words;
+    a.tile_words = ctx->k3_tile_words;
+    uint32_t grid = ctx->k3_grid < n_reads ? ctx->k3_grid : n_reads;
+    tps_window_kernel<<<grid, TPS_K3_THREADS, ctx->k3_smem, st>>>(a, ctx->pt);
+    ctx->launches++;
+  }
+  if (timed) {
+    TPS_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
+    ctx->ev_valid = true;
+  }
+  TPS_CUDA(ctx, cudaGetLastError());
+  return TPS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tps_submit(tps_ctx *ctx, const uint8_t *bases, const uint64_t *offsets, uint32_t n_reads, uint64_t batch_id) {
+  if (!ctx || !offsets || (!bases && n_reads)) return fail(ctx, TPS_EINVAL, "null argument");
+  const tps_params &p = ctx->p;
+  if (n_reads > p.max_batch_reads) return fail(ctx, TPS_ECAPACITY, "batch has %u reads, capacity %u", n_reads, p.max_batch_reads);
+  const uint64_t n_bases = offsets[n_reads];
+  if (offsets[0] != 0) return fail(ctx, TPS_EINVAL, "offsets[0] must be 0");
+  if (n_bases > p.max_batch_bases) return fail(ctx, TPS_ECAPACITY, "batch has %llu bases, capacity %llu",
+                                               (unsigned long long)n_bases, (unsigned long long)p.max_batch_bases);
+  Slot *sl = nullptr;
+  for (uint32_t i = 0; i < p.n_slots; ++i) {
+    if (ctx->slots[i].busy && ctx->slots[i].batch_id == batch_id) return fail(ctx, TPS_ESTATE, "batch id already in flight");
+    if (!ctx->slots[i].busy && !sl) sl = &ctx->slots[i];
+  }
+  if (!sl) return fail(ctx, TPS_ESTATE, "all %u slots busy: call tps_wait first", p.n_slots);
+  TPS_CUDA(ctx, cudaSetDevice(ctx->device));
+  Slot &s = *sl;
+  cudaStream_t st = s.stream;
+  TPS_CUDA(ctx, cudaMemcpyAsync(s.d_off, offsets, ((uint64_t)n_reads + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+  if (n_bases) TPS_CUDA(ctx, cudaMemcpyAsync(s.d_bases, bases, n_bases, cudaMemcpyHostToDevice, st));
+  int rc = enqueue_scan(ctx, s, st, s.d_bases, s.d_off, n_reads, n_bases, s.d_rows, false);
+  if (rc) return rc;
+  if (n_reads)
+    TPS_CUDA(ctx, cudaMemcpyAsync(s.h_rows, s.d_rows, (uint64_t)n_reads * sizeof(tps_row), cudaMemcpyDeviceToHost, st));
+  TPS_CUDA(ctx, cudaMemcpyAsync(s.h_counters, s.d_counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  TPS_CUDA(ctx, cudaEventRecord(s.done, st));
+  s.busy = true;
+  s.batch_id = batch_id;
+  s.n_reads = n_reads;
+  return TPS_OK;
+}
+
+int tps_wait(tps_ctx *ctx, uint64_t batch_id, tps_row *rows_out, uint32_t *n_pass_out, uint8_t *rawcounts_out,
+             uint64_t rawcount_cap, uint64_t *rawcount_elems) {
+  if (!ctx) return TPS_EINVAL;
+  Slot *sl = nullptr;
+  for (uint32_t i = 0; i < ctx->p.n_slots; ++i)
+    if (ctx->slots[i].busy && ctx->slots[i].batch_id == batch_id) sl = &ctx->slots[i];
+  if (!sl) return fail(ctx, TPS_ESTATE, "batch %llu is not in flight", (unsigned long long)batch_id);
+  Slot &s = *sl;
+  TPS_CUDA(ctx, cudaSetDevice(ctx->device));
+  TPS_CUDA(ctx, cudaEventSynchronize(s.done));
+  if (rows_out && s.n_reads) memcpy(rows_out, s.h_rows, (uint64_t)s.n_reads * sizeof(tps_row));
+  if (n_pass_out) *n_pass_out = s.h_counters[0];
+  uint64_t elems = 0;
+  memcpy(&elems, s.h_counters + 2, sizeof(uint64_t));
+  if (rawcount_elems) *rawcount_elems = elems;
+  if (ctx->p.want_rawcount) {
+    if (s.h_counters[4]) {
+      s.busy = false;
+      return fail(ctx, TPS_ECAPACITY, "rawcount_capacity %llu too small: batch needs %llu elements",
+                  (unsigned long long)ctx->p.rawcount_capacity, (unsigned long long)elems);
+    }
+    if (rawcounts_out) {
+      if (elems > rawcount_cap)
+        return fail(ctx, TPS_ECAPACITY, "rawcounts_out holds %llu elements, batch has %llu (slot kept; call again)",
+                    (unsigned long long)rawcount_cap, (unsigned long long)elems);
+      if (elems) TPS_CUDA(ctx, cudaMemcpy(rawcounts_out, s.d_raw, elems, cudaMemcpyDeviceToHost));
+    }
+  }
+  s.busy = false;
+  return TPS_OK;
+}
+
+int tps_scan_device(tps_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_offsets, uint32_t n_reads,
+                    uint64_t n_bases, tps_row *d_rows_out) {
+  if (!ctx || !d_offsets || !d_rows_out || (!d_bases && n_bases)) return fail(ctx, TPS_EINVAL, "null argument");
+  if (n_reads > ctx->p.max_batch_reads || n_bases > ctx->p.max_batch_bases)
+    return fail(ctx, TPS_ECAPACITY, "batch (%u reads, %llu bases) exceeds context capacity", n_reads,
+                (unsigned long long)n_bases);
+  if ((uintptr_t)d_bases & 15u) return fail(ctx, TPS_EINVAL, "d_bases must be 16-byte aligned");
+  TPS_CUDA(ctx, cudaSetDevice(ctx->device));
+  Slot &s = ctx->slots[0];
+  if (s.busy) return fail(ctx, TPS_ESTATE, "slot 0 busy with a submitted batch");
+  return enqueue_scan(ctx, s, s.stream, d_bases, d_offsets, n_reads, n_bases, d_rows_out, true);
+}
+
+int tps_sync(tps_ctx *ctx) {
+  if (!ctx) return TPS_EINVAL;
+  TPS_CUDA(ctx, cudaSetDevice(ctx->device));
+  for (uint32_t i = 0; i < ctx->p.n_slots; ++i) TPS_CUDA(ctx, cudaStreamSynchronize(ctx->slots[i].stream));
+  return TPS_OK;
+}
+
+int tps_get_timings(tps_ctx *ctx, float ms[TPS_N_TIMINGS]) {
+  if (!ctx || !ms) return TPS_EINVAL;
+  if (!ctx->ev_valid) return fail(ctx, TPS_ESTATE, "no timed scan recorded");
+  TPS_CUDA(ctx, cudaEventSynchronize(ctx->ev[3]));
+  for (int i = 0; i < 3; ++i) TPS_CUDA(ctx, cudaEventElapsedTime(&ms[i], ctx->ev[i], ctx->ev[i + 1]));
+  TPS_CUDA(ctx, cudaEventElapsedTime(&ms[3], ctx->ev[0], ctx->ev[3]));
+  return TPS_OK;
+}
+
+uint64_t tps_kernel_launches(const tps_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int tps_debug_copy(tps_ctx *ctx, int what, void *dst, size_t bytes) {
+  if (!ctx || !dst) return TPS_EINVAL;
+  Slot &s = ctx->slots[0];
+  TPS_CUDA(ctx, cudaSetDevice(ctx->device));
+  TPS_CUDA(ctx, cudaStreamSynchronize(s.stream));
+  const void *src = nullptr;
+  size_t cap = 0;
+  switch (what) {
+    case 0: src = s.d_codes; cap = ctx->cap_tiles * 32 * sizeof(uint32_t); break;
+    case 1: src = s.d_flags; cap = ctx->cap_tiles * sizeof(uint32_t); break;
+    case 2: src = s.d_masks; cap = ctx->cap_tiles * 32 * sizeof(uint16_t); break;
+    case 3: src = s.d_pass; cap = (size_t)ctx->p.max_batch_reads * sizeof(uint32_t); break;
+    default: return fail(ctx, TPS_EINVAL, "unknown debug array %d", what);
+  }
+  if (bytes > cap) return fail(ctx, TPS_EINVAL, "debug copy of %zu bytes exceeds array size %zu", bytes, cap);
+  TPS_CUDA(ctx, cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+  return TPS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,178 @@
+/*
+ * tps_bitops.h -- bit-level building blocks shared by the CUDA kernels (device) and
+ * the host unit tests (tests/csrc).  Pure integer code, no CUDA intrinsics.
+ *
+ * Packed read format produced by K1 (tps_pack_kernel), per group of 16 consecutive
+ * bases (= 4 little-endian 32-bit words w0..w3 of ASCII):
+ *
+ *   code word (uint32): base g = 4*i + m (word i, byte m) has its 2-bit code at bits
+ *       8*m + 2*i (+1).  code = (ascii >> 1) & 3  ->  A=0 C=1 T=2 G=3, case-insensitive
+ *       (this is what `.upper()` + literal matching needs: allsteps.py:176-177,267-271).
+ *       complement(code) = code ^ 2.
+ *   flag bit: 1 iff any of the 16 bytes is not in {A,C,G,T,a,c,g,t}; such bytes can never
+ *       be part of a match (the reference's regex literals contain only ACGT).
+ *   exact mask (uint16, only written for flagged groups): bit g = 1 iff base g is valid.
+ */
+#ifndef TPS_BITOPS_H
+#define TPS_BITOPS_H
+
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define TPS_HD __host__ __device__ __forceinline__
+#else
+#define TPS_HD static inline
+#endif
+
+/* ---- K1: 16 ASCII bytes -> code word, and "group has an invalid byte" flag ---------- */
+TPS_HD uint32_t tps_pack16(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t *bad_out) {
+  /* bits 1,2 of every byte -> 2-bit fields at 8m+2i */
+  uint32_t u = ((w0 >> 1) & 0x03030303u) | ((w1 << 1) & 0x0C0C0C0Cu) | ((w2 << 3) & 0x30303030u) |
+               ((w3 << 5) & 0xC0C0C0C0u);
+  /* bit 0 and bit 4 of every byte -> even bit positions 8m+2i (same layout as the low code bit) */
+  uint32_t u0 = (w0 & 0x01010101u) | ((w1 << 2) & 0x04040404u) | ((w2 << 4) & 0x10101010u) |
+                ((w3 << 6) & 0x40404040u);
+  uint32_t u4 = ((w0 >> 4) & 0x01010101u) | ((w1 >> 2) & 0x04040404u) | (w2 & 0x10101010u) |
+                ((w3 << 2) & 0x40404040u);
+  /* z = ascii bit2 & ~bit1 : 1 only for T/t among the valid letters */
+  uint32_t z = (u >> 1) & ~u;
+  /* valid letter <=> bit7=0, bit6=1, bit3=0, bit4 == z, bit0 == !z  (bit5 = case, ignored) */
+  uint32_t bad = ((u4 ^ z) | ~(u0 ^ z)) & 0x55555555u;
+  uint32_t o = w0 | w1 | w2 | w3;
+  uint32_t a = w0 & w1 & w2 & w3;
+  bad |= (o & 0x88888888u) | (~a & 0x40404040u);
+  *bad_out = bad;
+  return u;
+}
+
+TPS_HD int tps_byte_is_acgt(uint32_t c) {
+  c &= 0xDFu;
+  return c == 0x41u || c == 0x43u || c == 0x47u || c == 0x54u;
+}
+
+/* exact validity bits of a 16-base group (slow path, only for flagged groups) */
+TPS_HD uint32_t tps_exact_mask16(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+  uint32_t w[4] = {w0, w1, w2, w3};
+  uint32_t m = 0;
+  for (int g = 0; g < 16; ++g) {
+    uint32_t c = (w[g >> 2] >> (8 * (g & 3))) & 0xFFu;
+    m |= (uint32_t)tps_byte_is_acgt(c) << g;
+  }
+  return m;
+}
+
+/* 2-bit code of base g (0..15) inside a code word */
+TPS_HD uint32_t tps_code_at(uint32_t u, uint32_t g) { return (u >> (8 * (g & 3) + 2 * (g >> 2))) & 3u; }
+
+/* code word -> linear bit planes: low 16 bits = plane0 (code bit 0) of bases 0..15 in order,
+ * high 16 bits = plane1 (code bit 1). */
+TPS_HD uint32_t tps_linear_planes(uint32_t u) {
+  uint32_t x0 = u & 0x55555555u, x1 = (u >> 1) & 0x55555555u;
+  /* compress the 4 even bits of every byte into its low nibble: nibble bit i <- bit 2i */
+  x0 = (x0 | (x0 >> 1)) & 0x33333333u;
+  x1 = (x1 | (x1 >> 1)) & 0x33333333u;
+  x0 = (x0 | (x0 >> 2)) & 0x0F0F0F0Fu;
+  x1 = (x1 | (x1 >> 2)) & 0x0F0F0F0Fu;
+  /* gather the 4 nibbles into 16 bits: bit 4m+i */
+  x0 = (x0 | (x0 >> 4)) & 0x00FF00FFu;
+  x1 = (x1 | (x1 >> 4)) & 0x00FF00FFu;
+  x0 = (x0 | (x0 >> 8)) & 0x0000FFFFu;
+  x1 = (x1 | (x1 >> 8)) & 0x0000FFFFu;
+  uint32_t y = x0 | (x1 << 16);
+  /* 4x4 bit-matrix transpose in each half: bit 4m+i -> bit 4i+m */
+  uint32_t t = (y ^ (y >> 3)) & 0x0A0A0A0Au;
+  y ^= t ^ (t << 3);
+  t = (y ^ (y >> 6)) & 0x00CC00CCu;
+  y ^= t ^ (t << 6);
+  return y;
+}
+
+/* ---- pattern properties ------------------------------------------------------------- */
+/* ASCII base -> code, or 0xFF if not ACGT (upper or lower case) */
+TPS_HD uint32_t tps_ascii_code(uint32_t c) { return tps_byte_is_acgt(c) ? ((c >> 1) & 3u) : 0xFFu; }
+
+/* ---- greedy (leftmost, non-overlapping) count over a match bitmask -------------------
+ * mask bit j = literal of length k matches at position j.  Counts matches with start in
+ * [from, to] (inclusive), restarting the greedy scan at `from` -- exactly
+ * len(list(re.finditer(literal, text))) for text = s[from : to + k]
+ * (allsteps.py:182-183, 281, 288). */
+TPS_HD uint32_t tps_greedy_count(const uint32_t *mask, int32_t from, int32_t to, uint32_t k) {
+  uint32_t cnt = 0;
+  int32_t pos = from;
+  while (pos <= to) {
+    int32_t wi = pos >> 5;
+    uint32_t w = mask[wi] & (0xFFFFFFFFu << (pos & 31));
+    const int32_t wlast = to >> 5;
+    while (w == 0u) {
+      if (++wi > wlast) return cnt;
+      w = mask[wi];
+    }
+    /* index of lowest set bit */
+    uint32_t low = w & (0u - w);
+    int32_t b = 0;
+#if defined(__CUDA_ARCH__)
+    b = __ffs((int)w) - 1;
+    (void)low;
+#else
+    while (!((low >> b) & 1u)) ++b;
+#endif
+    int32_t at = (wi << 5) + b;
+    if (at > to) return cnt;
+    ++cnt;
+    pos = at + (int32_t)k;
+  }
+  return cnt;
+}
+
+/* popcount of mask bits with index in [from, to] (inclusive); for border-free literals this
+ * equals the greedy count */
+TPS_HD uint32_t tps_popc32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+  return (uint32_t)__popc(v);
+#else
+  return (uint32_t)__builtin_popcount(v);
+#endif
+}
+
+TPS_HD uint32_t tps_range_popcount(const uint32_t *mask, int32_t from, int32_t to) {
+  if (to < from) return 0;
+  int32_t w0 = from >> 5, w1 = to >> 5;
+  uint32_t first = 0xFFFFFFFFu << (from & 31);
+  uint32_t last = 0xFFFFFFFFu >> (31 - (to & 31));
+  if (w0 == w1) return tps_popc32(mask[w0] & first & last);
+  uint32_t c = tps_popc32(mask[w0] & first) + tps_popc32(mask[w1] & last);
+  for (int32_t w = w0 + 1; w < w1; ++w) c += tps_popc32(mask[w]);
+  return c;
+}
+
+/* ---- change point: exact comparison of two candidate gains --------------------------
+ * gain(b) is proportional to  num/den  with num = (n*S_b - b*T)^2, den = b*(n-b)
+ * (equivalent to ruptures' C(0,n) - C(0,b) - C(b,n) with CostL2; the common factor 1/(n*P^2)
+ * cancels).  Returns 1 if candidate B is better than A under ruptures' `max((gain, bkp))`
+ * rule: larger gain, ties -> larger b. */
+typedef struct tps_cand {
+  unsigned __int128 num;
+  uint64_t den;
+  int32_t b;
+} tps_cand;
+
+TPS_HD int tps_cand_better(const tps_cand *A, const tps_cand *B) {
+  if (A->b < 0) return B->b >= 0;
+  if (B->b < 0) return 0;
+  unsigned __int128 l = B->num * (unsigned __int128)A->den;
+  unsigned __int128 r = A->num * (unsigned __int128)B->den;
+  if (l != r) return l > r;
+  return B->b > A->b;
+}
+
+TPS_HD tps_cand tps_make_cand(uint32_t n, uint64_t S_b, uint64_t T, uint32_t b) {
+  tps_cand c;
+  __int128 d = (__int128)n * (__int128)S_b - (__int128)b * (__int128)T;
+  if (d < 0) d = -d;
+  c.num = (unsigned __int128)d * (unsigned __int128)d;
+  c.den = (uint64_t)b * (uint64_t)(n - b);
+  c.b = (int32_t)b;
+  return c;
+}
+
+#endif /* TPS_BITOPS_H */

@@ -1,0 +1,289 @@
+"""ctypes binding of the C-ABI in include/topsicle_b200.h plus a small batch engine.
+
+The CUDA library is the only implementation of the scan: if `libtopsicle_b200.so`
+is missing or no CUDA device is visible this module raises -- there is no CPU
+fallback (nothing under `oracle/` is ever imported from here).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Iterable, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtopsicle_b200.so")
+
+TPS_MAX_PATTERNS = 64
+TPS_MAX_PATTERN_LEN = 32
+
+ST_FILTERED, ST_BELOW, ST_PASS, ST_BADSEG = 0, 1, 2, 3
+TAIL_NAMES = ("forward", "reverse")
+NO_RAWCOUNT = 0xFFFFFFFFFFFFFFFF
+
+
+class TpsError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"topsicle_b200 error {code}: {msg}")
+        self.code = code
+
+
+class TpsParams(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32),
+        ("n_patterns", C.c_uint32),
+        ("pattern_len", C.c_uint8 * TPS_MAX_PATTERNS),
+        ("patterns", (C.c_char * TPS_MAX_PATTERN_LEN) * TPS_MAX_PATTERNS),
+        ("min_seq_length", C.c_uint32),
+        ("no_bp", C.c_uint32),
+        ("count_threshold", C.c_uint32),
+        ("window_size", C.c_uint32),
+        ("slide", C.c_uint32),
+        ("trimfirst", C.c_uint32),
+        ("maxlengthtelo", C.c_uint32),
+        ("want_rawcount", C.c_uint32),
+        ("n_slots", C.c_uint32),
+        ("max_batch_reads", C.c_uint32),
+        ("max_batch_bases", C.c_uint64),
+        ("rawcount_capacity", C.c_uint64),
+    ]
+
+
+ROW_DTYPE = np.dtype([
+    ("length", "<u4"), ("status", "u1"), ("tail", "u1"), ("best_pattern", "u1"), ("reserved0", "u1"),
+    ("match_count", "<u2"), ("head_max", "<u2"), ("tail_max", "<u2"), ("reserved1", "<u2"),
+    ("n_windows", "<u4"), ("bkp", "<i4"), ("telo_length", "<i4"), ("reserved2", "<u4"),
+    ("rawcount_offset", "<u8"),
+])
+assert ROW_DTYPE.itemsize == 40
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Load libtopsicle_b200.so (built in-tree by `__graft_entry__.build()`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise TpsError(-100, f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; "
+                             "g.build()'` (there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    vp, u8p, u64p, u32p = C.c_void_p, C.POINTER(C.c_uint8), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)
+    lib.tps_abi_version.restype = C.c_int
+    lib.tps_build_info.restype = C.c_char_p
+    lib.tps_last_error.restype = C.c_char_p
+    lib.tps_last_error.argtypes = [vp]
+    lib.tps_create.restype = C.c_int
+    lib.tps_create.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(TpsParams)]
+    lib.tps_destroy.restype = None
+    lib.tps_destroy.argtypes = [vp]
+    lib.tps_alloc_pinned.restype = vp
+    lib.tps_alloc_pinned.argtypes = [C.c_size_t]
+    lib.tps_free_pinned.restype = None
+    lib.tps_free_pinned.argtypes = [vp]
+    lib.tps_submit.restype = C.c_int
+    lib.tps_submit.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint64]
+    lib.tps_wait.restype = C.c_int
+    lib.tps_wait.argtypes = [vp, C.c_uint64, vp, u32p, vp, C.c_uint64, u64p]
+    lib.tps_scan_device.restype = C.c_int
+    lib.tps_scan_device.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint64, vp]
+    lib.tps_sync.restype = C.c_int
+    lib.tps_sync.argtypes = [vp]
+    lib.tps_get_timings.restype = C.c_int
+    lib.tps_get_timings.argtypes = [vp, C.POINTER(C.c_float * 4)]
+    lib.tps_kernel_launches.restype = C.c_uint64
+    lib.tps_kernel_launches.argtypes = [vp]
+    lib.tps_debug_copy.restype = C.c_int
+    lib.tps_debug_copy.argtypes = [vp, C.c_int, vp, C.c_size_t]
+    if lib.tps_abi_version() != 1:
+        raise TpsError(-101, "ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def count_threshold(cutoff: float, len_telopattern: int, no_bp: int = 1000) -> int:
+    """Smallest integer count c with `c / (no_bp / len(telopattern)) > cutoff` evaluated in
+    float64 exactly as the reference does (allsteps.py:178,185-186,194,197).  The quotient
+    is monotone in c, so the reference's float test equals `count >= threshold`."""
+    ratio = no_bp / len_telopattern
+    for c in range(0, no_bp + 2):
+        if c / ratio > cutoff:
+            return c
+    return 0xFFFFFFFF
+
+
+def trc_value(count: int, len_telopattern: int, no_bp: int = 1000) -> float:
+    """The reference's TRC float: matches / (no_bp / len(telopattern)) (allsteps.py:178,185)."""
+    return int(count) / (no_bp / len_telopattern)
+
+
+def pack_reads(seqs: Iterable) -> tuple[np.ndarray, np.ndarray]:
+    """Concatenate reads (str / bytes) back to back -> (uint8 bases, uint64 offsets[n+1])."""
+    bufs = [s.encode("ascii", "replace") if isinstance(s, str) else bytes(s) for s in seqs]
+    offsets = np.zeros(len(bufs) + 1, dtype=np.uint64)
+    if bufs:
+        offsets[1:] = np.cumsum([len(b) for b in bufs], dtype=np.uint64)
+    bases = np.frombuffer(b"".join(bufs), dtype=np.uint8)
+    return bases, offsets
+
+
+class PinnedBuffer:
+    """Page-locked host memory from the library, exposed as a numpy uint8 array."""
+
+    def __init__(self, nbytes: int):
+        self._lib = load_library()
+        self.nbytes = int(nbytes)
+        self.ptr = self._lib.tps_alloc_pinned(max(self.nbytes, 1))
+        if not self.ptr:
+            raise TpsError(-3, f"cannot pin {nbytes} bytes of host memory")
+        self.array = np.ctypeslib.as_array((C.c_uint8 * max(self.nbytes, 1)).from_address(self.ptr))
+
+    def free(self):
+        if self.ptr:
+            self._lib.tps_free_pinned(self.ptr)
+            self.ptr = None
+            self.array = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class ScanContext:
+    """One GPU scan context == the arguments of one process_file call (main.py:52-150)."""
+
+    def __init__(self, patterns: Sequence[str], *, len_telopattern: int | None = None, cutoff: float = 0.7,
+                 min_seq_length: int = 9000, no_bp: int = 1000, window_size: int = 100, slide: int = 6,
+                 trimfirst: int = 100, maxlengthtelo: int = 20000, want_rawcount: bool = False,
+                 device: int = 0, n_slots: int = 2, max_batch_reads: int = 1 << 16,
+                 max_batch_bases: int = 1 << 28, rawcount_capacity: int = 0,
+                 count_threshold_override: int | None = None):
+        self.lib = load_library()
+        self.patterns = [p.upper() for p in patterns]
+        self.len_telopattern = len_telopattern if len_telopattern is not None else len(self.patterns[0])
+        self.no_bp = no_bp
+        p = TpsParams()
+        p.struct_size = C.sizeof(TpsParams)
+        if len(self.patterns) > TPS_MAX_PATTERNS:
+            raise TpsError(-1, f"at most {TPS_MAX_PATTERNS} literals are supported")
+        p.n_patterns = len(self.patterns)
+        for i, lit in enumerate(self.patterns):
+            b = lit.encode("ascii")
+            if not 1 <= len(b) <= TPS_MAX_PATTERN_LEN:
+                raise TpsError(-1, f"literal {lit!r}: length must be in 1..{TPS_MAX_PATTERN_LEN}")
+            p.pattern_len[i] = len(b)
+            C.memmove(C.addressof(p.patterns[i]), b, len(b))
+        p.min_seq_length = min_seq_length
+        p.no_bp = no_bp
+        p.count_threshold = (count_threshold_override if count_threshold_override is not None
+                             else count_threshold(cutoff, self.len_telopattern, no_bp))
+        p.window_size, p.slide, p.trimfirst, p.maxlengthtelo = window_size, slide, trimfirst, maxlengthtelo
+        p.want_rawcount = 1 if want_rawcount else 0
+        p.n_slots = n_slots
+        p.max_batch_reads = max_batch_reads
+        p.max_batch_bases = max_batch_bases
+        if want_rawcount and not rawcount_capacity:
+            nreg = max(0, maxlengthtelo - trimfirst)
+            nw = (nreg - window_size) // slide + 1 if nreg >= window_size else 0
+            rawcount_capacity = max(1, min(max_batch_reads, 4096) * nw * len(self.patterns))
+        p.rawcount_capacity = rawcount_capacity
+        self.params = p
+        self.max_batch_reads = max_batch_reads
+        self.max_batch_bases = max_batch_bases
+        self.want_rawcount = bool(want_rawcount)
+        self._h = C.c_void_p()
+        rc = self.lib.tps_create(C.byref(self._h), device, C.byref(p))
+        if rc != 0:
+            raise TpsError(rc, self.lib.tps_last_error(None).decode())
+        self._next_id = 1
+        self._inflight = {}
+
+    # -- lifetime
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self.lib.tps_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise TpsError(rc, self.lib.tps_last_error(self._h).decode())
+
+    # -- host-buffer path (reference-facing: H2D and D2H inside)
+    def submit(self, bases: np.ndarray, offsets: np.ndarray) -> int:
+        assert bases.dtype == np.uint8 and offsets.dtype == np.uint64
+        assert bases.flags.c_contiguous and offsets.flags.c_contiguous
+        n_reads = len(offsets) - 1
+        bid = self._next_id
+        self._next_id += 1
+        self._check(self.lib.tps_submit(self._h, bases.ctypes.data, offsets.ctypes.data, n_reads, bid))
+        self._inflight[bid] = (bases, offsets, n_reads)  # keep buffers alive
+        return bid
+
+    def wait(self, bid: int):
+        bases, offsets, n_reads = self._inflight[bid]
+        rows = np.empty(n_reads, dtype=ROW_DTYPE)
+        n_pass = C.c_uint32(0)
+        elems = C.c_uint64(0)
+        raw = None
+        if self.want_rawcount:
+            raw = np.empty(int(self.params.rawcount_capacity), dtype=np.uint8)
+            self._check(self.lib.tps_wait(self._h, bid, rows.ctypes.data, C.byref(n_pass), raw.ctypes.data,
+                                          raw.size, C.byref(elems)))
+            raw = raw[:elems.value]
+        else:
+            self._check(self.lib.tps_wait(self._h, bid, rows.ctypes.data, C.byref(n_pass), None, 0,
+                                          C.byref(elems)))
+        del self._inflight[bid]
+        return rows, raw
+
+    def scan(self, bases: np.ndarray, offsets: np.ndarray):
+        """Synchronous scan of one host batch -> (rows, rawcounts or None)."""
+        return self.wait(self.submit(bases, offsets))
+
+    def scan_reads(self, seqs: Iterable):
+        bases, offsets = pack_reads(seqs)
+        return self.scan(bases, offsets)
+
+    def rawcount_table(self, rows, raw, i) -> np.ndarray:
+        """counts[w][p] (uint8) of read i, or None."""
+        off = int(rows["rawcount_offset"][i])
+        if raw is None or off == NO_RAWCOUNT:
+            return None
+        nw, npat = int(rows["n_windows"][i]), len(self.patterns)
+        return raw[off:off + nw * npat].reshape(nw, npat)
+
+    # -- device-resident path (kernel-only timing)
+    def scan_device(self, d_bases_ptr: int, d_offsets_ptr: int, n_reads: int, n_bases: int, d_rows_ptr: int):
+        self._check(self.lib.tps_scan_device(self._h, d_bases_ptr, d_offsets_ptr, n_reads, n_bases, d_rows_ptr))
+
+    def sync(self):
+        self._check(self.lib.tps_sync(self._h))
+
+    def timings(self):
+        ms = (C.c_float * 4)()
+        self._check(self.lib.tps_get_timings(self._h, C.byref(ms)))
+        return dict(k1_pack=ms[0], k2_trc=ms[1], k3_windows_cp=ms[2], total=ms[3])
+
+    def kernel_launches(self) -> int:
+        return int(self.lib.tps_kernel_launches(self._h))
+
+    def debug_copy(self, what: int, nbytes: int) -> np.ndarray:
+        out = np.empty(nbytes, dtype=np.uint8)
+        self._check(self.lib.tps_debug_copy(self._h, what, out.ctypes.data, nbytes))
+        return out

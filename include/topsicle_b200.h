@@ -130,10 +130,13 @@ int tps_scan_device(tps_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_offs
                     uint32_t n_reads, uint64_t n_bases, tps_row *d_rows_out);
 int tps_sync(tps_ctx *ctx);
 
-/* CUDA-event timings (ms) of the most recent completed tps_scan_device on this context:
- * ms[0] = K1 pack, ms[1] = K2 TRC, ms[2] = K3+K4 windows/change point, ms[3] = whole scan. */
+/* CUDA-event timings (ms), recorded on the scan's own stream, of the tps_scan_device call
+ * `back` calls ago (0 = most recent; a ring of TPS_TIMING_RING calls is kept):
+ * ms[0] = K1 pack, ms[1] = K2 TRC, ms[2] = K3+K4 windows/change point, ms[3] = whole scan.
+ * Blocks until that scan has finished. */
 #define TPS_N_TIMINGS 4
-int tps_get_timings(tps_ctx *ctx, float ms[TPS_N_TIMINGS]);
+#define TPS_TIMING_RING 256
+int tps_get_timings(tps_ctx *ctx, uint32_t back, float ms[TPS_N_TIMINGS]);
 /* Number of kernels this context has launched so far. */
 uint64_t tps_kernel_launches(const tps_ctx *ctx);
 

@@ -1,0 +1,159 @@
+#!/usr/bin/env python
+"""TEST / MEASUREMENT INFRASTRUCTURE ONLY -- the reference's CPU path, timed.
+
+A port of what `Topsicle/main.py:process_file` makes the CPU do for one file, operation
+for operation, on reads already in memory (so the reference's Biopython parsing and its
+O(p^2) temp-file re-scans, main.py:83-86 / allsteps.py:252-259, are NOT charged -- this
+favours the reference):
+
+  step 1  allsteps.py:175-198  `re.finditer` of every literal over seq[:1000] and the
+          reversed seq[-1000:]
+  step 2  allsteps.py:263-297  windows of BOTH orientations, `len(finditer) or 1` per
+          literal, mean (one orientation is then discarded, exactly as upstream)
+          allsteps.py:310-311  ruptures Binseg(l2).fit(y).predict(pen=4, n_bkps=1)
+          (restated 1.1.9, oracle/shims/ruptures)
+
+Parallelism: the reference runs one process per input FILE (main.py:232-235); here the
+sample is dealt into `cores` equal-base shards, one worker process each, i.e. the best
+case for the reference.  Used by `bench.py` (cpu_baseline leg and `--impl reference`).
+Run as a script it prints one JSON object.
+"""
+import argparse
+import json
+import os
+import re
+import sys
+import time
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+for p in (REPO, os.path.join(HERE, "shims")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+
+def _windows(s, window_size, step):
+    """allsteps.py:207-225."""
+    out = []
+    for i in range(0, len(s) - window_size + 1, step):
+        end = i + window_size - 1
+        if end > len(s):
+            end = len(s)
+        out.append((i, s[i:end]))
+    return out
+
+
+def scan_shard(args):
+    """Reference-style scan of a list of read strings -> (n_scanned, n_pass, [telo_lengths])."""
+    import ruptures as rpt  # restated 1.1.9 (oracle/shims)
+    from oracle.topsicle_oracle import patterns_to_search
+    seqs, pattern, phrase, cutoff, min_len, W, slide, trim, maxlen = args
+    literals = patterns_to_search(pattern, phrase)
+    compiled = [re.compile(p) for p in literals]
+    ratio = 1000 / len(pattern)
+    passing = []
+    n_scanned = 0
+    for seq in seqs:                                   # ---- step 1, allsteps.py:174-198
+        if len(seq) > min_len:
+            n_scanned += 1
+            head = seq[:1000].upper()
+            tail = seq[-1000:][::-1].upper()
+            rows = []
+            for pat in compiled:
+                ms = len([m.start() for m in pat.finditer(head)])
+                me = len([m.start() for m in pat.finditer(tail)])
+                rows.append((ms / ratio, me / ratio))
+            best_s = max(r[0] for r in rows)
+            best_e = max(r[1] for r in rows)
+            if best_s > best_e:
+                if best_s > cutoff:
+                    passing.append((seq, "forward"))
+            elif best_e > cutoff:
+                passing.append((seq, "reverse"))
+    telo = []
+    for seq, tail in passing:                          # ---- step 2, allsteps.py:263-315
+        m = min(maxlen, len(seq))
+        s_fwd = seq[trim:m].upper()
+        s_rev = seq[::-1].upper()[trim:m]
+        mean_s, mean_e = [], []
+        for start, cut in _windows(s_fwd, W, slide):
+            c = [len([mm.start() for mm in pat.finditer(cut)]) or 1 for pat in compiled]
+            mean_s.append((start, sum(c) / len(c)))
+        for start, cut in _windows(s_rev, W, slide):
+            c = [len([mm.start() for mm in pat.finditer(cut)]) or 1 for pat in compiled]
+            mean_e.append((start, sum(c) / len(c)))
+        mean = mean_s if tail == "forward" else mean_e
+        x = [a + trim for a, _ in mean]
+        y = [b for _, b in mean]
+        if len(y) < 7:
+            telo.append(-1)
+            continue
+        res = rpt.Binseg(model="l2").fit(np.array(y)).predict(pen=4, n_bkps=1)
+        telo.append(int(x[res[0]]))
+    return n_scanned, len(passing), telo
+
+
+def deal_shards(seqs, n):
+    """n shards of (nearly) equal bases, reads kept in order inside a shard."""
+    shards = [[] for _ in range(n)]
+    load = [0] * n
+    for s in seqs:
+        i = load.index(min(load))
+        shards[i].append(s)
+        load[i] += len(s)
+    return shards
+
+
+def time_sample(seqs, scan_kw, cores, steps=1, warmup=0):
+    """Wall time per pass over `seqs` on `cores` worker processes."""
+    import multiprocessing as mp
+    shards = deal_shards(seqs, cores)
+    argl = [(sh, scan_kw["pattern"], scan_kw["phrase"], scan_kw["cutoff"], scan_kw["min_len"], scan_kw["W"],
+             scan_kw["slide"], scan_kw["trim"], scan_kw["maxlen"]) for sh in shards]
+    times, last = [], None
+    ctx = mp.get_context("fork")
+    with ctx.Pool(processes=cores) as pool:
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            last = pool.map(scan_shard, argl)
+            dt = time.perf_counter() - t0
+            if it >= warmup:
+                times.append(dt)
+    n_pass = sum(r[1] for r in last)
+    return times, n_pass
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", type=int, default=2)
+    ap.add_argument("--reads", type=int, default=4000)
+    ap.add_argument("--first-read", type=int, default=0)
+    ap.add_argument("--steps", type=int, default=1)
+    ap.add_argument("--warmup", type=int, default=0)
+    ap.add_argument("--cores", type=int, default=0)
+    a = ap.parse_args()
+    from topsicle_b200 import synth
+    spec = synth.CONFIGS[a.config]
+    cli = spec["cli"]
+    bases, off, _ = synth.generate(spec, a.first_read, a.reads)
+    buf = bases.tobytes().decode("ascii")
+    seqs = [buf[int(off[i]):int(off[i + 1])] for i in range(a.reads)]
+    cores = a.cores or len(os.sched_getaffinity(0))
+    pattern = cli["pattern"]
+    phrases = cli.get("telophrase") or [len(pattern) - 2]
+    cut = cli.get("cutoff", 0.7)
+    kw = dict(pattern=pattern, phrase=phrases[0], cutoff=min(cut) if isinstance(cut, list) else cut,
+              min_len=cli.get("minSeqLength", 9000), W=cli.get("windowSize", 100),
+              slide=cli.get("slide") or len(pattern), trim=cli.get("trimfirst", 100),
+              maxlen=cli.get("maxlengthtelo", 20000))
+    times, n_pass = time_sample(seqs, kw, cores, a.steps, a.warmup)
+    n_bases = int(off[-1])
+    print(json.dumps(dict(config=a.config, reads=a.reads, bases=n_bases, cores=cores, n_pass=n_pass,
+                          seconds=times, gbases_per_s=[n_bases / t / 1e9 for t in times],
+                          reads_per_s=[a.reads / t for t in times])))
+
+
+if __name__ == "__main__":
+    main()

@@ -53,8 +53,8 @@ struct tps_ctx {
   int k1_grid = 0;
   uint64_t cap_tiles = 0;
   Slot slots[4];
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-  bool ev_valid = false;
+  cudaEvent_t ev[TPS_TIMING_RING][4]; /* CUDA-event ring: one set of 4 events per timed scan */
+  uint64_t scan_seq = 0;               /* number of timed scans enqueued so far */
   uint64_t launches = 0;
   char err[512] = "";
 };
@@ -160,8 +160,9 @@ void tps_destroy(tps_ctx *ctx) {
     if (s.done) cudaEventDestroy(s.done);
     if (s.stream) cudaStreamDestroy(s.stream);
   }
-  for (int i = 0; i < 4; ++i)
-    if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  for (int r = 0; r < TPS_TIMING_RING; ++r)
+    for (int i = 0; i < 4; ++i)
+      if (ctx->ev[r][i]) cudaEventDestroy(ctx->ev[r][i]);
   delete ctx;
 }
 
@@ -202,6 +203,7 @@ int tps_create(tps_ctx **out, int device, const tps_params *params) {
 
   tps_ctx *ctx = new (std::nothrow) tps_ctx();
   if (!ctx) return fail(nullptr, TPS_ENOMEM, "out of host memory");
+  memset(ctx->ev, 0, sizeof(ctx->ev));
   ctx->device = device;
   ctx->p = p;
   ctx->pt = pt;
@@ -269,7 +271,8 @@ int tps_create(tps_ctx **out, int device, const tps_params *params) {
     TPS_CC(cudaHostAlloc(&s.h_rows, (uint64_t)p.max_batch_reads * sizeof(tps_row), cudaHostAllocDefault));
     TPS_CC(cudaHostAlloc(&s.h_counters, 8 * sizeof(uint32_t), cudaHostAllocDefault));
   }
-  for (int i = 0; i < 4; ++i) TPS_CC(cudaEventCreate(&ctx->ev[i]));
+  for (int r = 0; r < TPS_TIMING_RING; ++r)
+    for (int i = 0; i < 4; ++i) TPS_CC(cudaEventCreate(&ctx->ev[r][i]));
 #undef TPS_CC
   *out = ctx;
   return TPS_OK;
@@ -283,8 +286,9 @@ namespace {
 int enqueue_scan(tps_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t *d_bases, const uint64_t *d_off,
                  uint32_t n_reads, uint64_t n_bases, tps_row *d_rows, bool timed) {
   const tps_params &p = ctx->p;
+  cudaEvent_t *ev = ctx->ev[ctx->scan_seq % TPS_TIMING_RING];
   TPS_CUDA(ctx, cudaMemsetAsync(s.d_counters, 0, 8 * sizeof(uint32_t), st));
-  if (timed) TPS_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
+  if (timed) TPS_CUDA(ctx, cudaEventRecord(ev[0], st));
   const uint64_t n_tiles = (n_bases + 511) / 512;
   if (n_tiles) {
     uint64_t want = (n_tiles + (TPS_K1_THREADS / 32) * TPS_K1_UNROLL - 1) / ((TPS_K1_THREADS / 32) * TPS_K1_UNROLL);
@@ -293,7 +297,7 @@ int enqueue_scan(tps_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t *d_bases,
                                                      s.d_masks, n_tiles);
     ctx->launches++;
   }
-  if (timed) TPS_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
+  if (timed) TPS_CUDA(ctx, cudaEventRecord(ev[1], st));
   TpsScanArgs a;
   memset(&a, 0, sizeof(a));
   a.pk.codes = s.d_codes;
@@ -323,7 +327,7 @@ int enqueue_scan(tps_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t *d_bases,
     tps_trc_kernel<<<(n_reads + TPS_K2_WARPS - 1) / TPS_K2_WARPS, TPS_K2_WARPS * 32, ctx->k2_smem, st>>>(a, ctx->pt);
     ctx->launches++;
   }
-  if (timed) TPS_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
+  if (timed) TPS_CUDA(ctx, cudaEventRecord(ev[2], st));
   if (n_reads) {
     a.lin_words = ctx->k3_lin_words;
     a.tile_words = ctx->k3_tile_words;
@@ -332,8 +336,8 @@ int enqueue_scan(tps_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t *d_bases,
     ctx->launches++;
   }
   if (timed) {
-    TPS_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
-    ctx->ev_valid = true;
+    TPS_CUDA(ctx, cudaEventRecord(ev[3], st));
+    ctx->scan_seq++;
   }
   TPS_CUDA(ctx, cudaGetLastError());
   return TPS_OK;
@@ -426,12 +430,14 @@ int tps_sync(tps_ctx *ctx) {
   return TPS_OK;
 }
 
-int tps_get_timings(tps_ctx *ctx, float ms[TPS_N_TIMINGS]) {
+int tps_get_timings(tps_ctx *ctx, uint32_t back, float ms[TPS_N_TIMINGS]) {
   if (!ctx || !ms) return TPS_EINVAL;
-  if (!ctx->ev_valid) return fail(ctx, TPS_ESTATE, "no timed scan recorded");
-  TPS_CUDA(ctx, cudaEventSynchronize(ctx->ev[3]));
-  for (int i = 0; i < 3; ++i) TPS_CUDA(ctx, cudaEventElapsedTime(&ms[i], ctx->ev[i], ctx->ev[i + 1]));
-  TPS_CUDA(ctx, cudaEventElapsedTime(&ms[3], ctx->ev[0], ctx->ev[3]));
+  if (back >= TPS_TIMING_RING || back >= ctx->scan_seq)
+    return fail(ctx, TPS_ESTATE, "timed scan %u steps back is not recorded (ring of %d)", back, TPS_TIMING_RING);
+  cudaEvent_t *ev = ctx->ev[(ctx->scan_seq - 1 - back) % TPS_TIMING_RING];
+  TPS_CUDA(ctx, cudaEventSynchronize(ev[3]));
+  for (int i = 0; i < 3; ++i) TPS_CUDA(ctx, cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
+  TPS_CUDA(ctx, cudaEventElapsedTime(&ms[3], ev[0], ev[3]));
   return TPS_OK;
 }
 

@@ -92,7 +92,7 @@ def load_library() -> C.CDLL:
     lib.tps_sync.restype = C.c_int
     lib.tps_sync.argtypes = [vp]
     lib.tps_get_timings.restype = C.c_int
-    lib.tps_get_timings.argtypes = [vp, C.POINTER(C.c_float * 4)]
+    lib.tps_get_timings.argtypes = [vp, C.c_uint32, C.POINTER(C.c_float * 4)]
     lib.tps_kernel_launches.restype = C.c_uint64
     lib.tps_kernel_launches.argtypes = [vp]
     lib.tps_debug_copy.restype = C.c_int
@@ -275,9 +275,10 @@ class ScanContext:
     def sync(self):
         self._check(self.lib.tps_sync(self._h))
 
-    def timings(self):
+    def timings(self, back: int = 0):
+        """CUDA-event stage times (ms) of the scan_device call `back` calls ago."""
         ms = (C.c_float * 4)()
-        self._check(self.lib.tps_get_timings(self._h, C.byref(ms)))
+        self._check(self.lib.tps_get_timings(self._h, back, C.byref(ms)))
         return dict(k1_pack=ms[0], k2_trc=ms[1], k3_windows_cp=ms[2], total=ms[3])
 
     def kernel_launches(self) -> int:

@@ -70,6 +70,9 @@ typedef struct tps_params {
   uint32_t want_rawcount;   /* also return counts[w][p]                     (allsteps.py:401-416) */
   uint32_t n_slots;         /* batches in flight (1..4), async pipeline depth */
   uint32_t max_batch_reads; /* capacity per batch */
+  uint32_t max_pass_reads;  /* capacity for TRC-pass reads per batch (0 = max_batch_reads); each costs
+                               4 bytes x windows-per-read of device memory */
+  uint32_t reserved;
   uint64_t max_batch_bases; /* capacity per batch (bytes of sequence) */
   uint64_t rawcount_capacity; /* per batch, in count elements (uint8 each); 0 if !want_rawcount */
 } tps_params;

@@ -298,3 +298,36 @@ def test_empty_and_capacity(eng):
         _ctx(eng, ["CCNTA"])
     with pytest.raises(eng.TpsError):
         _ctx(eng, ["CC|TA"])
+
+
+def test_generic_literal_lists(eng, edge_records, demo_records):
+    """Literal lists of mixed lengths / longer than 8 (the reference accepts a list for pattern_telo,
+    allsteps.py:122-123) take the generic (non-templated) matching path."""
+    lists = [["CCCTAA", "TTAGGGTTA", "AA", "CCCTAACCCTAA", "G"], ["CCCTAAACCCTAAACCCTAAACCCTAAACCC", "AAACCCT"],
+             ["CCCTAAACC", "GGGATTTGG", "TTTAGGGTT"]]
+    records = edge_records + demo_records[:8]
+    for pats in lists:
+        W, s, t, M = 100, 6, 50, 4000
+        with _ctx(eng, pats, len_telopattern=7, min_seq_length=0, count_threshold_override=0, window_size=W,
+                  slide=s, trimfirst=t, maxlengthtelo=M, want_rawcount=True, rawcount_capacity=1 << 26) as ctx:
+            rows, raw = ctx.scan_reads([sq for _, sq in records])
+            for i, ((rid, seq), row) in enumerate(zip(records, rows)):
+                tail, bi, cnt, ms, me, _, _ = orc.trc_read(seq, pats, 7)
+                assert (eng.TAIL_NAMES[row["tail"]], int(row["best_pattern"]), int(row["match_count"]),
+                        int(row["head_max"]), int(row["tail_max"])) == (tail, bi, cnt, ms, me), (rid, pats)
+                counts = orc.window_counts(orc.oriented_region(seq, tail, t, M), pats, W, s)
+                assert row["n_windows"] == counts.shape[0]
+                if counts.shape[0]:
+                    assert np.array_equal(ctx.rawcount_table(rows, raw, i).astype(np.int64), counts), rid
+                if counts.shape[0] >= 7:
+                    assert row["telo_length"] == t + s * orc.change_point_exact(counts.sum(axis=1))
+
+
+def test_max_pass_overflow_is_loud(eng, demo_records):
+    pats = orc.patterns_to_search("CCCTAAA", 5)
+    with _ctx(eng, pats, len_telopattern=7, cutoff=0.7, slide=6, max_pass_reads=4) as ctx:
+        with pytest.raises(eng.TpsError):
+            ctx.scan_reads([s for _, s in demo_records])
+    with _ctx(eng, pats, len_telopattern=7, cutoff=0.7, slide=6, max_pass_reads=17) as ctx:
+        rows, _ = ctx.scan_reads([s for _, s in demo_records])
+        assert int((rows["status"] == eng.ST_PASS).sum()) == 17

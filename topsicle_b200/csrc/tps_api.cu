@@ -32,7 +32,7 @@ struct Slot {
   uint32_t *d_pass = nullptr;
   uint32_t *d_counters = nullptr;
   uint8_t *d_raw = nullptr;
-  uint32_t *d_cw_scratch = nullptr;
+  uint32_t *d_cw = nullptr;         /* c_w rows of passing reads */
   tps_row *h_rows = nullptr;        /* pinned */
   uint32_t *h_counters = nullptr;   /* pinned */
   uint64_t batch_id = 0;
@@ -48,8 +48,12 @@ struct tps_ctx {
   TpsPatTable pt;
   int n_sms = 0;
   uint32_t k2_lin_words = 0, k2_nq_max = 0, k2_smem = 0;
-  uint32_t k3_lin_words = 0, k3_tile_words = 0, k3_smem = 0, k3_grid = 0;
-  uint32_t cw_stride = 0, cw_in_smem = 0;
+  uint32_t k3_lin_words = 0, k3_tile_words = 0, k3_tile_bases = 0, k3_tiles_max = 0, k3_smem = 0, k3_grid = 0;
+  uint32_t k4_grid = 0;
+  uint32_t cw_stride = 0, max_pass = 0;
+  int kt = 0; /* template K of the K2/K3 instantiation in use (0 = generic) */
+  void (*k2_fn)(const TpsScanArgs, const TpsPatTable) = nullptr;
+  void (*k3_fn)(const TpsScanArgs, const TpsPatTable) = nullptr;
   int k1_grid = 0;
   uint64_t cap_tiles = 0;
   Slot slots[4];
@@ -128,7 +132,7 @@ extern "C" {
 int tps_abi_version(void) { return TPS_ABI_VERSION; }
 
 const char *tps_build_info(void) {
-  return "topsicle_b200 sm_100a; kernels: tps_pack_kernel, tps_trc_kernel, tps_window_kernel; " __DATE__;
+  return "topsicle_b200 sm_100a; kernels: tps_pack_kernel, tps_trc_kernel<K>, tps_window_kernel<K>, tps_changepoint_kernel; " __DATE__;
 }
 
 const char *tps_last_error(const tps_ctx *ctx) { return ctx ? ctx->err : g_create_error; }
@@ -154,7 +158,7 @@ void tps_destroy(tps_ctx *ctx) {
     if (s.stream) cudaStreamSynchronize(s.stream);
     cudaFree(s.d_bases); cudaFree(s.d_codes); cudaFree(s.d_flags); cudaFree(s.d_masks);
     cudaFree(s.d_off); cudaFree(s.d_rows); cudaFree(s.d_pass); cudaFree(s.d_counters);
-    cudaFree(s.d_raw); cudaFree(s.d_cw_scratch);
+    cudaFree(s.d_raw); cudaFree(s.d_cw);
     if (s.h_rows) cudaFreeHost(s.h_rows);
     if (s.h_counters) cudaFreeHost(s.h_counters);
     if (s.done) cudaEventDestroy(s.done);
@@ -222,33 +226,54 @@ int tps_create(tps_ctx **out, int device, const tps_params *params) {
   TPS_CC(cudaGetDeviceProperties(&prop, device));
   ctx->n_sms = prop.multiProcessorCount;
 
+  /* pick the K2/K3 instantiation: K = common literal length if all literals share one <= 8 */
+  uint32_t kmax = 0;
+  for (uint32_t i = 0; i < pt.n; ++i) kmax = pt.len[i] > kmax ? pt.len[i] : kmax;
+  ctx->kt = (kmin == kmax && kmax <= 8) ? (int)kmax : 0;
+  switch (ctx->kt) {
+#define TPS_PICK(KK) case KK: ctx->k2_fn = tps_trc_kernel<KK>; ctx->k3_fn = tps_window_kernel<KK>; break;
+    TPS_PICK(1) TPS_PICK(2) TPS_PICK(3) TPS_PICK(4) TPS_PICK(5) TPS_PICK(6) TPS_PICK(7) TPS_PICK(8)
+#undef TPS_PICK
+    default: ctx->k2_fn = tps_trc_kernel<0>; ctx->k3_fn = tps_window_kernel<0>; break;
+  }
+  const uint32_t pm_words = 2 * pt.n * (ctx->kt > 0 ? (uint32_t)ctx->kt : 1u);
   /* K2 geometry */
   ctx->k2_lin_words = lin_words_for(p.no_bp);
   ctx->k2_nq_max = (p.no_bp + 31) / 32;
-  ctx->k2_smem = TPS_K2_WARPS * (3 * ctx->k2_lin_words + pt.n_bordered * ctx->k2_nq_max + TPS_MAX_PATTERNS) * 4;
-  /* K3 geometry */
-  const uint32_t tile_n = TPS_K3_TILE_BASES + p.window_size;
+  ctx->k2_smem = (pm_words + TPS_K2_WARPS * (3 * ctx->k2_lin_words + pt.n_bordered * ctx->k2_nq_max + TPS_MAX_PATTERNS)) * 4;
+  /* K3 geometry: a tile stages tile_bases + W positions; keep that <= 4096 (128 words) when W allows */
+  const uint32_t w32 = (p.window_size + 31) / 32 * 32;
+  ctx->k3_tile_bases = w32 + 1024 <= 4096 ? 4096 - w32 : 1024;
+  const uint32_t tile_n = ctx->k3_tile_bases + p.window_size;
   ctx->k3_lin_words = lin_words_for(tile_n);
   ctx->k3_tile_words = (tile_n + 31) / 32 + 1;
-  uint32_t k3_words = 3 * ctx->k3_lin_words + 3 * ctx->k3_tile_words + pt.n * ctx->k3_tile_words;
+  ctx->k3_tiles_max = (uint32_t)((reg_max + ctx->k3_tile_bases - 1) / ctx->k3_tile_bases);
+  if (ctx->k3_tiles_max == 0) ctx->k3_tiles_max = 1;
+  ctx->k3_smem = (pm_words + 3 * ctx->k3_lin_words + 3 * ctx->k3_tile_words + pt.n * ctx->k3_tile_words) * 4;
   ctx->cw_stride = (uint32_t)(nw_max ? nw_max : 1);
+  ctx->max_pass = p.max_pass_reads ? p.max_pass_reads : p.max_batch_reads;
+  if (ctx->max_pass > p.max_batch_reads) ctx->max_pass = p.max_batch_reads;
+  if ((uint64_t)ctx->max_pass * ctx->k3_tiles_max > 0xFFFFFFF0ull) {
+    int c_ = fail(nullptr, TPS_EINVAL, "max_pass_reads * tiles per read overflows the work counter");
+    tps_destroy(ctx);
+    return c_;
+  }
   const uint32_t smem_limit = (uint32_t)prop.sharedMemPerBlockOptin;
-  ctx->cw_in_smem = ((uint64_t)(k3_words + ctx->cw_stride) * 4 <= 96 * 1024) ? 1u : 0u;
-  if (ctx->cw_in_smem) k3_words += ctx->cw_stride;
-  ctx->k3_smem = k3_words * 4;
   if (ctx->k2_smem > smem_limit || ctx->k3_smem > smem_limit) {
     int c_ = fail(nullptr, TPS_EINVAL, "parameters need %u / %u bytes of shared memory (limit %u)", ctx->k2_smem,
                   ctx->k3_smem, smem_limit);
     tps_destroy(ctx);
     return c_;
   }
-  TPS_CC(cudaFuncSetAttribute(tps_trc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->k2_smem));
-  TPS_CC(cudaFuncSetAttribute(tps_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->k3_smem));
-  int occ1 = 0, occ3 = 0;
+  TPS_CC(cudaFuncSetAttribute(ctx->k2_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->k2_smem));
+  TPS_CC(cudaFuncSetAttribute(ctx->k3_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->k3_smem));
+  int occ1 = 0, occ3 = 0, occ4 = 0;
   TPS_CC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, tps_pack_kernel, TPS_K1_THREADS, 0));
-  TPS_CC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3, tps_window_kernel, TPS_K3_THREADS, ctx->k3_smem));
+  TPS_CC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3, ctx->k3_fn, TPS_K3_THREADS, ctx->k3_smem));
+  TPS_CC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ4, tps_changepoint_kernel, TPS_K4_THREADS, 0));
   ctx->k1_grid = ctx->n_sms * (occ1 > 0 ? occ1 : 1);
   ctx->k3_grid = (uint32_t)(ctx->n_sms * (occ3 > 0 ? occ3 : 1));
+  ctx->k4_grid = (uint32_t)(ctx->n_sms * (occ4 > 0 ? (occ4 > 4 ? 4 : occ4) : 1));
 
   ctx->cap_tiles = (p.max_batch_bases + 511) / 512;
   const uint64_t cap_pad = ((p.max_batch_bases + 2047) / 2048) * 2048;
@@ -263,11 +288,10 @@ int tps_create(tps_ctx **out, int device, const tps_params *params) {
     TPS_CC(cudaMalloc(&s.d_masks, ctx->cap_tiles * 32 * sizeof(uint16_t)));
     TPS_CC(cudaMalloc(&s.d_off, ((uint64_t)p.max_batch_reads + 1) * sizeof(uint64_t)));
     TPS_CC(cudaMalloc(&s.d_rows, (uint64_t)p.max_batch_reads * sizeof(tps_row)));
-    TPS_CC(cudaMalloc(&s.d_pass, (uint64_t)p.max_batch_reads * sizeof(uint32_t)));
+    TPS_CC(cudaMalloc(&s.d_pass, (uint64_t)ctx->max_pass * sizeof(uint32_t)));
     TPS_CC(cudaMalloc(&s.d_counters, 8 * sizeof(uint32_t)));
     if (p.want_rawcount) TPS_CC(cudaMalloc(&s.d_raw, p.rawcount_capacity ? p.rawcount_capacity : 1));
-    if (!ctx->cw_in_smem)
-      TPS_CC(cudaMalloc(&s.d_cw_scratch, (uint64_t)ctx->k3_grid * ctx->cw_stride * sizeof(uint32_t)));
+    TPS_CC(cudaMalloc(&s.d_cw, (uint64_t)ctx->max_pass * ctx->cw_stride * sizeof(uint32_t)));
     TPS_CC(cudaHostAlloc(&s.h_rows, (uint64_t)p.max_batch_reads * sizeof(tps_row), cudaHostAllocDefault));
     TPS_CC(cudaHostAlloc(&s.h_counters, 8 * sizeof(uint32_t), cudaHostAllocDefault));
   }
@@ -318,22 +342,24 @@ int enqueue_scan(tps_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t *d_bases,
   a.want_rawcount = p.want_rawcount;
   a.raw = s.d_raw;
   a.raw_capacity = p.want_rawcount ? p.rawcount_capacity : 0;
-  a.cw_scratch = s.d_cw_scratch;
+  a.cw = s.d_cw;
   a.cw_stride = ctx->cw_stride;
-  a.cw_in_smem = ctx->cw_in_smem;
+  a.max_pass = ctx->max_pass;
+  a.tile_bases = ctx->k3_tile_bases;
+  a.tiles_max = ctx->k3_tiles_max;
   a.nq_max = ctx->k2_nq_max;
   if (n_reads) {
     a.lin_words = ctx->k2_lin_words;
-    tps_trc_kernel<<<(n_reads + TPS_K2_WARPS - 1) / TPS_K2_WARPS, TPS_K2_WARPS * 32, ctx->k2_smem, st>>>(a, ctx->pt);
+    ctx->k2_fn<<<(n_reads + TPS_K2_WARPS - 1) / TPS_K2_WARPS, TPS_K2_WARPS * 32, ctx->k2_smem, st>>>(a, ctx->pt);
     ctx->launches++;
   }
   if (timed) TPS_CUDA(ctx, cudaEventRecord(ev[2], st));
   if (n_reads) {
     a.lin_words = ctx->k3_lin_words;
     a.tile_words = ctx->k3_tile_words;
-    uint32_t grid = ctx->k3_grid < n_reads ? ctx->k3_grid : n_reads;
-    tps_window_kernel<<<grid, TPS_K3_THREADS, ctx->k3_smem, st>>>(a, ctx->pt);
-    ctx->launches++;
+    ctx->k3_fn<<<ctx->k3_grid, TPS_K3_THREADS, ctx->k3_smem, st>>>(a, ctx->pt);
+    tps_changepoint_kernel<<<ctx->k4_grid, TPS_K4_THREADS, 0, st>>>(a);
+    ctx->launches += 2;
   }
   if (timed) {
     TPS_CUDA(ctx, cudaEventRecord(ev[3], st));
@@ -390,11 +416,16 @@ int tps_wait(tps_ctx *ctx, uint64_t batch_id, tps_row *rows_out, uint32_t *n_pas
   TPS_CUDA(ctx, cudaEventSynchronize(s.done));
   if (rows_out && s.n_reads) memcpy(rows_out, s.h_rows, (uint64_t)s.n_reads * sizeof(tps_row));
   if (n_pass_out) *n_pass_out = s.h_counters[0];
+  if (s.h_counters[4] & TPS_OVF_PASS) {
+    s.busy = false;
+    return fail(ctx, TPS_ECAPACITY, "%u reads passed the TRC cutoff but max_pass_reads is %u", s.h_counters[0],
+                ctx->max_pass);
+  }
   uint64_t elems = 0;
   memcpy(&elems, s.h_counters + 2, sizeof(uint64_t));
   if (rawcount_elems) *rawcount_elems = elems;
   if (ctx->p.want_rawcount) {
-    if (s.h_counters[4]) {
+    if (s.h_counters[4] & TPS_OVF_RAWCOUNT) {
       s.busy = false;
       return fail(ctx, TPS_ECAPACITY, "rawcount_capacity %llu too small: batch needs %llu elements",
                   (unsigned long long)ctx->p.rawcount_capacity, (unsigned long long)elems);
@@ -454,7 +485,7 @@ int tps_debug_copy(tps_ctx *ctx, int what, void *dst, size_t bytes) {
     case 0: src = s.d_codes; cap = ctx->cap_tiles * 32 * sizeof(uint32_t); break;
     case 1: src = s.d_flags; cap = ctx->cap_tiles * sizeof(uint32_t); break;
     case 2: src = s.d_masks; cap = ctx->cap_tiles * 32 * sizeof(uint16_t); break;
-    case 3: src = s.d_pass; cap = (size_t)ctx->p.max_batch_reads * sizeof(uint32_t); break;
+    case 3: src = s.d_pass; cap = (size_t)ctx->max_pass * sizeof(uint32_t); break;
     default: return fail(ctx, TPS_EINVAL, "unknown debug array %d", what);
   }
   if (bytes > cap) return fail(ctx, TPS_EINVAL, "debug copy of %zu bytes exceeds array size %zu", bytes, cap);

@@ -1,15 +1,20 @@
 /*
  * tps_kernels.cuh -- sm_100a kernels of the per-read telomere scan.
  *
- *   K1  tps_pack_kernel      ASCII -> 2-bit codes (+ invalid-group flags, sparse exact masks)
- *   K2  tps_trc_kernel       per read: head/tail greedy counts, TRC decision, pass list
- *   K3+K4 tps_window_kernel  per passing read: window counts (+raw counts), change point
+ *   K1  tps_pack_kernel         ASCII -> 2-bit codes (+ invalid-group flags, sparse exact masks)
+ *   K2  tps_trc_kernel<K>       per read: head/tail greedy counts, TRC decision, pass list
+ *   K3  tps_window_kernel<K>    per (passing read, tile): window counts c_w (+ raw counts)
+ *   K4  tps_changepoint_kernel  per passing read: exact single change point
  *
  * Reference semantics: /root/reference/Topsicle/allsteps.py:152-204 (step 1),
  * :207-225 + :227-338 (step 2), :359-464 (step 3), ruptures 1.1.9 Binseg/CostL2.
  * Nothing here is a dense contraction; the path is HBM-bound integer/bit work, so no
  * tensor cores: coalesced 128-bit loads (K1), shared-memory staging of read tiles with a
  * window halo (K3), warp ballot/redux reductions (K2), exact 128-bit rational argmax (K4).
+ *
+ * K2/K3 are templated on K = the common literal length (1..8) so the per-position match is a
+ * fully unrolled chain of LOP3 over register-resident shifted bit planes; K = 0 is the
+ * generic path (mixed lengths or literals longer than 8).
  */
 #pragma once
 #include <cuda_runtime.h>
@@ -36,23 +41,30 @@ struct TpsPacked {
   const uint16_t *masks; /* exact validity, defined where flag bit set */
 };
 
+/* counters[]: [0] n_pass, [1] K3 work cursor, [2,3] rawcount cursor (u64), [4] overflow flags,
+ * [5] K4 work cursor */
+#define TPS_OVF_RAWCOUNT 1u
+#define TPS_OVF_PASS 2u
+
 struct TpsScanArgs {
   TpsPacked pk;
   const uint64_t *offsets;
   uint32_t n_reads;
   tps_row *rows;
   uint32_t *pass_list;
-  uint32_t *counters; /* [0] n_pass, [1] work cursor, [2,3] rawcount cursor (u64), [4] overflow */
+  uint32_t *counters;
   uint32_t min_seq_length, no_bp, count_threshold;
   uint32_t W, slide, trimfirst, maxlengthtelo, want_rawcount;
   uint8_t *raw;
   uint64_t raw_capacity;
-  uint32_t *cw_scratch; /* per-CTA c_w scratch (global) when nW does not fit in shared memory */
+  uint32_t *cw;        /* c_w of passing read i at cw + i * cw_stride */
   uint32_t cw_stride;
-  uint32_t cw_in_smem;
-  uint32_t lin_words;   /* words per linear plane buffer */
-  uint32_t tile_words;  /* K3: oriented words per tile incl. halo (+1) */
-  uint32_t nq_max;      /* K2: ceil(no_bp/32) */
+  uint32_t max_pass;   /* capacity of pass_list / cw */
+  uint32_t lin_words;  /* words per linear plane buffer */
+  uint32_t tile_words; /* K3: oriented words per tile incl. halo (+1) */
+  uint32_t tile_bases; /* K3: window-start positions per tile */
+  uint32_t tiles_max;  /* K3: tiles per read at the longest region */
+  uint32_t nq_max;     /* K2: ceil(no_bp/32) */
 };
 
 /* ------------------------------------------------------------------------------------ K1 */
@@ -67,6 +79,25 @@ __device__ __forceinline__ uint4 tps_ldg_stream(const uint4 *p) {
 #define TPS_K1_THREADS 256
 #define TPS_K1_UNROLL 4
 
+/* Rare path (a group holds a non-ACGT byte): kept out of line so that the hot loop does not
+ * carry its 16 x 4 byte compares as predicated code. */
+__device__ __noinline__ void tps_store_exact_mask(uint16_t *dst, uint32_t w0, uint32_t w1, uint32_t w2,
+                                                  uint32_t w3) {
+  *dst = (uint16_t)tps_exact_mask16(w0, w1, w2, w3);
+}
+
+__device__ __forceinline__ void tps_pack_tile(const uint4 &v, uint32_t *__restrict__ codes,
+                                              uint32_t *__restrict__ flags, uint16_t *__restrict__ masks,
+                                              uint64_t tile, uint32_t lane) {
+  uint32_t bad;
+  const uint32_t code = tps_pack16(v.x, v.y, v.z, v.w, &bad);
+  const uint64_t g = tile * 32 + lane;
+  codes[g] = code;
+  const uint32_t fl = __ballot_sync(TPS_FULL, bad != 0u);
+  if (lane == 0) flags[tile] = fl;
+  if (bad != 0u) tps_store_exact_mask(masks + g, v.x, v.y, v.z, v.w);
+}
+
 /* One warp converts 512 consecutive bases per tile: lane l loads bytes [16l,16l+16) as one
  * 128-bit load (512 B coalesced per warp instruction), emits one code word (128 B coalesced
  * store per warp), and the warp emits one flag word by ballot.  TPS_K1_UNROLL tiles are
@@ -76,26 +107,20 @@ tps_pack_kernel(const uint4 *__restrict__ bases, uint32_t *__restrict__ codes,
                 uint32_t *__restrict__ flags, uint16_t *__restrict__ masks, uint64_t n_tiles) {
   const uint32_t lane = threadIdx.x & 31u;
   const uint64_t warp = (uint64_t)blockIdx.x * (TPS_K1_THREADS / 32) + (threadIdx.x >> 5);
-  const uint64_t nwarps = (uint64_t)gridDim.x * (TPS_K1_THREADS / 32);
-  for (uint64_t t0 = warp * TPS_K1_UNROLL; t0 < n_tiles; t0 += nwarps * TPS_K1_UNROLL) {
+  const uint64_t stride = (uint64_t)gridDim.x * (TPS_K1_THREADS / 32) * TPS_K1_UNROLL;
+  const uint64_t n_main = n_tiles / TPS_K1_UNROLL * TPS_K1_UNROLL;
+  for (uint64_t t0 = warp * TPS_K1_UNROLL; t0 < n_main; t0 += stride) {
     uint4 v[TPS_K1_UNROLL];
+    const uint4 *src = bases + t0 * 32 + lane;
 #pragma unroll
-    for (int u = 0; u < TPS_K1_UNROLL; ++u) {
-      v[u] = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
-      if (t0 + u < n_tiles) v[u] = tps_ldg_stream(bases + (t0 + u) * 32 + lane);
-    }
+    for (int u = 0; u < TPS_K1_UNROLL; ++u) v[u] = tps_ldg_stream(src + u * 32);
 #pragma unroll
-    for (int u = 0; u < TPS_K1_UNROLL; ++u) {
-      if (t0 + u < n_tiles) { /* warp-uniform */
-        uint32_t bad;
-        uint32_t code = tps_pack16(v[u].x, v[u].y, v[u].z, v[u].w, &bad);
-        const uint64_t g = (t0 + u) * 32 + lane;
-        codes[g] = code;
-        uint32_t fl = __ballot_sync(TPS_FULL, bad != 0u);
-        if (lane == 0) flags[t0 + u] = fl;
-        if (bad != 0u) masks[g] = (uint16_t)tps_exact_mask16(v[u].x, v[u].y, v[u].z, v[u].w);
-      }
-    }
+    for (int u = 0; u < TPS_K1_UNROLL; ++u) tps_pack_tile(v[u], codes, flags, masks, t0 + u, lane);
+  }
+  const uint64_t tt = n_main + warp; /* at most UNROLL-1 trailing tiles, one warp each */
+  if (tt < n_tiles) {
+    const uint4 v = tps_ldg_stream(bases + tt * 32 + lane);
+    tps_pack_tile(v, codes, flags, masks, tt, lane);
   }
 }
 
@@ -153,45 +178,64 @@ __device__ __forceinline__ void tps_oriented_word(const uint32_t *lin, uint32_t 
   }
 }
 
-/* Match words of every literal for 32 consecutive positions.  (a*, b*) are the oriented
- * words q and q+1 of plane0 / plane1 / valid.  Calls emit(p, M). */
-struct TpsShifted {
-  uint32_t X[8], Y[8], VA[8]; /* planes shifted by j; VA[j] = AND_{i<=j} valid >> i */
-  uint32_t a0, b0, a1, b1, av, bv;
-};
-
-__device__ __forceinline__ void tps_shifted_init(TpsShifted &s, uint32_t a0, uint32_t b0, uint32_t a1,
-                                                 uint32_t b1, uint32_t av, uint32_t bv) {
-  s.a0 = a0; s.b0 = b0; s.a1 = a1; s.b1 = b1; s.av = av; s.bv = bv;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    s.X[j] = __funnelshift_r(a0, b0, j);
-    s.Y[j] = __funnelshift_r(a1, b1, j);
-    uint32_t v = __funnelshift_r(av, bv, j);
-    s.VA[j] = j ? (s.VA[j - 1] & v) : v;
+/* ------------------------------------------------------------------ per-position matching */
+/* Shared-memory literal masks: pm[p * KS + j] = (x, y) with x = all-ones iff code bit 0 of
+ * base j of literal p is 1, y likewise for code bit 1.  KS = max(K, 1). */
+__device__ __forceinline__ void tps_build_pattern_masks(uint2 *pm, const TpsPatTable &pt, uint32_t ks,
+                                                        uint32_t tid, uint32_t nthreads) {
+  for (uint32_t i = tid; i < pt.n * ks; i += nthreads) {
+    const uint32_t p = i / ks, j = i - p * ks;
+    pm[i] = make_uint2(0u - ((pt.lo[p] >> j) & 1u), 0u - ((pt.hi[p] >> j) & 1u));
   }
 }
 
-__device__ __forceinline__ uint32_t tps_match_word(const TpsShifted &s, uint32_t lo, uint32_t hi,
-                                                   uint32_t k) {
-  uint32_t M = TPS_FULL;
+/* Planes of 32 consecutive positions shifted by 0..K-1, valid = all K bases valid. */
+template <int K>
+struct TpsWin {
+  uint32_t X[K > 0 ? K : 1], Y[K > 0 ? K : 1], V;
+  uint32_t a0, b0, a1, b1, av, bv;
+};
+
+template <int K>
+__device__ __forceinline__ void tps_win_init(TpsWin<K> &w, uint32_t a0, uint32_t b0, uint32_t a1, uint32_t b1,
+                                             uint32_t av, uint32_t bv) {
+  if constexpr (K > 0) {
+    w.V = av;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    if ((uint32_t)j < k) {
-      const uint32_t cx = 0u - ((lo >> j) & 1u), cy = 0u - ((hi >> j) & 1u);
-      M &= ~(s.X[j] ^ cx) & ~(s.Y[j] ^ cy);
-      if ((uint32_t)j == k - 1u) M &= s.VA[j];
+    for (int j = 0; j < K; ++j) {
+      w.X[j] = __funnelshift_r(a0, b0, j);
+      w.Y[j] = __funnelshift_r(a1, b1, j);
+      if (j) w.V &= __funnelshift_r(av, bv, j);
     }
+  } else {
+    w.a0 = a0; w.b0 = b0; w.a1 = a1; w.b1 = b1; w.av = av; w.bv = bv;
   }
-  if (k > 8u) {
-    M &= s.VA[7];
-    for (uint32_t j = 8; j < k; ++j) {
-      const uint32_t cx = 0u - ((lo >> j) & 1u), cy = 0u - ((hi >> j) & 1u);
-      M &= ~(__funnelshift_r(s.a0, s.b0, j) ^ cx) & ~(__funnelshift_r(s.a1, s.b1, j) ^ cy) &
-           __funnelshift_r(s.av, s.bv, j);
+}
+
+/* Match word of literal p: bit i = literal occurs at position 32q+i (all bases valid). */
+template <int K>
+__device__ __forceinline__ uint32_t tps_win_match(const TpsWin<K> &w, const uint2 *pm, const TpsPatTable &pt,
+                                                  uint32_t p) {
+  if constexpr (K > 0) {
+    uint32_t M = w.V;
+    const uint2 *c = pm + p * K;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      const uint2 m = c[j];
+      M &= ~(w.X[j] ^ m.x);
+      M &= ~(w.Y[j] ^ m.y);
     }
+    return M;
+  } else {
+    uint32_t M = TPS_FULL;
+    const uint32_t lo = pt.lo[p], hi = pt.hi[p], k = pt.len[p];
+    for (uint32_t j = 0; j < k; ++j) {
+      const uint32_t cx = 0u - ((lo >> j) & 1u), cy = 0u - ((hi >> j) & 1u);
+      M &= ~(__funnelshift_r(w.a0, w.b0, j) ^ cx) & ~(__funnelshift_r(w.a1, w.b1, j) ^ cy) &
+           __funnelshift_r(w.av, w.bv, j);
+    }
+    return M;
   }
-  return M;
 }
 
 /* ------------------------------------------------------------------------------------ K2 */
@@ -199,10 +243,10 @@ __device__ __forceinline__ uint32_t tps_match_word(const TpsShifted &s, uint32_t
 
 /* Greedy counts of every literal over one oriented slice (head or reversed tail), one warp.
  * Returns (max count, first-max literal index) -- allsteps.py:181-191. */
-__device__ __forceinline__ void tps_trc_end(const TpsScanArgs &a, const TpsPatTable &pt, uint64_t g0,
-                                            uint32_t n, bool rev, uint32_t *lin, uint32_t *mrows,
-                                            uint32_t *cnts, uint32_t lane, uint32_t &best,
-                                            uint32_t &bestp) {
+template <int K>
+__device__ __forceinline__ void tps_trc_end(const TpsScanArgs &a, const TpsPatTable &pt, const uint2 *pm,
+                                            uint64_t g0, uint32_t n, bool rev, uint32_t *lin, uint32_t *mrows,
+                                            uint32_t *cnts, uint32_t lane, uint32_t &best, uint32_t &bestp) {
   const uint32_t lw = a.lin_words;
   const uint32_t phase = (uint32_t)(g0 & 15u);
   const uint32_t nq = (n + 31u) >> 5;
@@ -214,11 +258,11 @@ __device__ __forceinline__ void tps_trc_end(const TpsScanArgs &a, const TpsPatTa
     uint32_t a0, a1, av, b0, b1, bv;
     tps_oriented_word(lin, lw, phase, n, rev, q, a0, a1, av);
     tps_oriented_word(lin, lw, phase, n, rev, q + 1u, b0, b1, bv);
-    TpsShifted sh;
-    tps_shifted_init(sh, a0, b0, a1, b1, av, bv);
+    TpsWin<K> win;
+    tps_win_init<K>(win, a0, b0, a1, b1, av, bv);
     for (uint32_t p = 0; p < pt.n; ++p) {
-      const uint32_t M = tps_match_word(sh, pt.lo[p], pt.hi[p], pt.len[p]);
-      if (pt.bordered[p]) {
+      const uint32_t M = tps_win_match<K>(win, pm, pt, p);
+      if (pt.bordered[p]) { /* warp-uniform */
         if (q < nq) mrows[pt.brow[p] * a.nq_max + q] = M;
       } else {
         const uint32_t c = __reduce_add_sync(TPS_FULL, tps_popc32(M));
@@ -247,19 +291,25 @@ __device__ __forceinline__ void tps_trc_end(const TpsScanArgs &a, const TpsPatTa
   __syncwarp();
 }
 
+/* dynamic shared memory (words): pm[2 * P * max(K,1)] | per warp: lin[3*lin_words] |
+ * mrows[n_bordered * nq_max] | cnts[TPS_MAX_PATTERNS] */
+template <int K>
 __global__ void __launch_bounds__(TPS_K2_WARPS * 32)
 tps_trc_kernel(const TpsScanArgs a, const TpsPatTable pt) {
   extern __shared__ uint32_t smem[];
+  constexpr uint32_t KS = K > 0 ? K : 1;
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  uint2 *pm = reinterpret_cast<uint2 *>(smem);
+  tps_build_pattern_masks(pm, pt, KS, threadIdx.x, TPS_K2_WARPS * 32);
+  __syncthreads();
   const uint32_t per_warp = 3u * a.lin_words + pt.n_bordered * a.nq_max + TPS_MAX_PATTERNS;
-  uint32_t *lin = smem + warp * per_warp;
+  uint32_t *lin = smem + 2u * pt.n * KS + warp * per_warp;
   uint32_t *mrows = lin + 3u * a.lin_words;
   uint32_t *cnts = mrows + pt.n_bordered * a.nq_max;
   const uint32_t r = blockIdx.x * TPS_K2_WARPS + warp;
   if (r >= a.n_reads) return;
   const uint64_t off = a.offsets[r];
-  const uint64_t len64 = a.offsets[r + 1] - off;
-  const uint32_t L = (uint32_t)len64;
+  const uint32_t L = (uint32_t)(a.offsets[r + 1] - off);
   tps_row row;
   row.length = L;
   row.status = TPS_ST_FILTERED;
@@ -270,8 +320,8 @@ tps_trc_kernel(const TpsScanArgs a, const TpsPatTable pt) {
   if (L > a.min_seq_length) { /* strict, allsteps.py:175 */
     const uint32_t n = L < a.no_bp ? L : a.no_bp;
     uint32_t ms, ps, me, pe;
-    tps_trc_end(a, pt, off, n, false, lin, mrows, cnts, lane, ms, ps);          /* seq[:no_bp] */
-    tps_trc_end(a, pt, off + L - n, n, true, lin, mrows, cnts, lane, me, pe);   /* seq[-no_bp:][::-1] */
+    tps_trc_end<K>(a, pt, pm, off, n, false, lin, mrows, cnts, lane, ms, ps);         /* seq[:no_bp] */
+    tps_trc_end<K>(a, pt, pm, off + L - n, n, true, lin, mrows, cnts, lane, me, pe);  /* seq[-no_bp:][::-1] */
     const bool fwd = ms > me; /* tie -> reverse, allsteps.py:193-198 */
     const uint32_t cnt = fwd ? ms : me;
     row.tail = fwd ? TPS_TAIL_FORWARD : TPS_TAIL_REVERSE;
@@ -285,37 +335,48 @@ tps_trc_kernel(const TpsScanArgs a, const TpsPatTable pt) {
       const uint32_t nreg = M > a.trimfirst ? M - a.trimfirst : 0u;
       const uint32_t nW = nreg >= a.W ? (nreg - a.W) / a.slide + 1u : 0u;
       row.n_windows = nW;
-      if (a.want_rawcount && nW) {
-        const unsigned long long elems = (unsigned long long)nW * pt.n;
-        const unsigned long long at =
-            atomicAdd(reinterpret_cast<unsigned long long *>(a.counters + 2), elems);
-        if (at + elems <= a.raw_capacity) row.rawcount_offset = at;
-        else atomicExch(a.counters + 4, 1u);
-      }
       const uint32_t slot = atomicAdd(a.counters + 0, 1u);
-      a.pass_list[slot] = r;
+      if (slot < a.max_pass) {
+        a.pass_list[slot] = r;
+        if (a.want_rawcount && nW) {
+          const unsigned long long elems = (unsigned long long)nW * pt.n;
+          const unsigned long long at =
+              atomicAdd(reinterpret_cast<unsigned long long *>(a.counters + 2), elems);
+          if (at + elems <= a.raw_capacity) row.rawcount_offset = at;
+          else atomicOr(a.counters + 4, TPS_OVF_RAWCOUNT);
+        }
+      } else {
+        atomicOr(a.counters + 4, TPS_OVF_PASS);
+      }
     }
   }
   if (lane == 0) a.rows[r] = row;
 }
 
-/* --------------------------------------------------------------------------------- K3+K4 */
+/* ------------------------------------------------------------------------------------ K3 */
 #define TPS_K3_THREADS 256
-#define TPS_K3_TILE_BASES 4096u /* window starts handled per tile; multiple of 32 */
+#define TPS_K3_PSPLIT 2 /* literals of one 32-position word are split over this many threads */
 
-/* shared-memory layout (words): lin[3*lin_words] | ori[3*tile_words] | rows[P*tile_words] |
- * cw[cw_in_smem ? cw_stride : 0] */
+/* One work item = one tile of one passing read: window starts in [tb0, tb0 + tile_bases) of
+ * the oriented region z = oriented[trimfirst : min(L, maxlengthtelo)].
+ * dynamic shared memory (words): pm[2*P*max(K,1)] | lin[3*lin_words] | ori[3*tile_words] |
+ * mrows[P*tile_words] */
+template <int K>
 __global__ void __launch_bounds__(TPS_K3_THREADS)
 tps_window_kernel(const TpsScanArgs a, const TpsPatTable pt) {
   extern __shared__ uint32_t smem[];
   __shared__ uint32_t s_item;
-  const uint32_t tid = threadIdx.x, lane = tid & 31u;
+  constexpr uint32_t KS = K > 0 ? K : 1;
+  const uint32_t tid = threadIdx.x;
   const uint32_t lw = a.lin_words, tw = a.tile_words;
-  uint32_t *lin = smem;
+  uint2 *pm = reinterpret_cast<uint2 *>(smem);
+  uint32_t *lin = smem + 2u * pt.n * KS;
   uint32_t *ori = lin + 3u * lw;
   uint32_t *mrows = ori + 3u * tw;
-  uint32_t *cw = a.cw_in_smem ? (mrows + pt.n * tw) : (a.cw_scratch + (size_t)blockIdx.x * a.cw_stride);
-  const uint32_t n_pass = a.counters[0];
+  tps_build_pattern_masks(pm, pt, KS, tid, TPS_K3_THREADS);
+  uint32_t n_pass = a.counters[0];
+  if (n_pass > a.max_pass) n_pass = a.max_pass;
+  const uint32_t n_items = n_pass * a.tiles_max;
   const uint32_t W = a.W, s = a.slide, t = a.trimfirst;
 
   for (;;) {
@@ -323,123 +384,139 @@ tps_window_kernel(const TpsScanArgs a, const TpsPatTable pt) {
     if (tid == 0) s_item = atomicAdd(a.counters + 1, 1u);
     __syncthreads();
     const uint32_t item = s_item;
-    if (item >= n_pass) break;
-    const uint32_t r = a.pass_list[item];
+    if (item >= n_items) break;
+    const uint32_t pi = item / a.tiles_max;
+    const uint32_t tb0 = (item - pi * a.tiles_max) * a.tile_bases;
+    const uint32_t r = a.pass_list[pi];
     const uint64_t off = a.offsets[r];
     const uint32_t L = (uint32_t)(a.offsets[r + 1] - off);
-    const bool rev = a.rows[r].tail == TPS_TAIL_REVERSE;
-    const uint64_t raw_off = a.rows[r].rawcount_offset;
     const uint32_t M = L < a.maxlengthtelo ? L : a.maxlengthtelo; /* allsteps.py:263-264 */
     const uint32_t nreg = M > t ? M - t : 0u;                      /* |z|, allsteps.py:267-271 */
     const uint32_t nW = nreg >= W ? (nreg - W) / s + 1u : 0u;      /* allsteps.py:219 */
-
-    for (uint32_t tb0 = 0; tb0 < nreg && nW; tb0 += TPS_K3_TILE_BASES) {
-      /* windows whose start lies in [tb0, tb0 + TILE) */
-      const uint32_t wlo = (tb0 + s - 1u) / s;
-      uint32_t whi = (tb0 + TPS_K3_TILE_BASES + s - 1u) / s;
-      if (whi > nW) whi = nW;
-      if (wlo >= whi) continue;
-      /* oriented positions [tb0, tb0 + tn) of the region are staged */
-      uint32_t tn = TPS_K3_TILE_BASES + W; /* halo: a window reaches W-2 past its start */
-      if (tn > nreg - tb0) tn = nreg - tb0;
-      /* forward: read bases [off+t+tb0, +tn); reverse: region position j is read index
-       * L-1-(t+j), so the slice is read bases [off+L-t-tb0-tn, off+L-t-tb0) reversed */
-      const uint64_t g0 = rev ? (off + L - t - tb0 - tn) : (off + t + tb0);
-      const uint32_t phase = (uint32_t)(g0 & 15u);
-      __syncthreads();
-      tps_stage_linear(a.pk, g0, tn, lin, lw, tid, TPS_K3_THREADS);
-      __syncthreads();
-      const uint32_t nq = (tn + 31u) >> 5;
-      for (uint32_t q = tid; q < tw; q += TPS_K3_THREADS) {
-        uint32_t p0, p1, v;
-        tps_oriented_word(lin, lw, phase, tn, rev, q, p0, p1, v);
-        ori[q] = p0;
-        ori[tw + q] = p1;
-        ori[2u * tw + q] = v;
-      }
-      __syncthreads();
-      for (uint32_t q = tid; q < nq; q += TPS_K3_THREADS) {
-        TpsShifted sh;
-        tps_shifted_init(sh, ori[q], ori[q + 1], ori[tw + q], ori[tw + q + 1], ori[2u * tw + q],
-                         ori[2u * tw + q + 1]);
-        for (uint32_t p = 0; p < pt.n; ++p)
-          mrows[p * tw + q] = tps_match_word(sh, pt.lo[p], pt.hi[p], pt.len[p]);
-      }
-      __syncthreads();
-      for (uint32_t w = wlo + tid; w < whi; w += TPS_K3_THREADS) {
-        const int32_t ls = (int32_t)(w * s - tb0);
-        uint32_t c = 0;
-        for (uint32_t p = 0; p < pt.n; ++p) {
-          const uint32_t k = pt.len[p];
-          uint32_t cnt = 0;
-          if (W - 1u >= k) {
-            const int32_t to = ls + (int32_t)(W - 1u - k);
-            cnt = pt.bordered[p] ? tps_greedy_count(mrows + p * tw, ls, to, k)
-                                 : tps_range_popcount(mrows + p * tw, ls, to);
-          }
-          if (cnt == 0u) cnt = 1u; /* `... or 1`, allsteps.py:281,288 */
-          c += cnt;
-          if (raw_off != ~0ull) a.raw[raw_off + (uint64_t)w * pt.n + p] = (uint8_t)cnt;
-        }
-        cw[w] = c;
-      }
+    if (tb0 >= nreg || nW == 0u) continue;
+    /* windows whose start lies in [tb0, tb0 + tile_bases) */
+    const uint32_t wlo = (tb0 + s - 1u) / s;
+    uint32_t whi = (tb0 + a.tile_bases + s - 1u) / s;
+    if (whi > nW) whi = nW;
+    if (wlo >= whi) continue;
+    const bool rev = a.rows[r].tail == TPS_TAIL_REVERSE;
+    const uint64_t raw_off = a.rows[r].rawcount_offset;
+    uint32_t *cw = a.cw + (size_t)pi * a.cw_stride;
+    /* oriented positions [tb0, tb0 + tn) are staged; a window reaches W-2 past its start */
+    uint32_t tn = a.tile_bases + W;
+    if (tn > nreg - tb0) tn = nreg - tb0;
+    /* forward: read bases [off+t+tb0, +tn); reverse: region position j is read index
+     * L-1-(t+j), so the slice is read bases [off+L-t-tb0-tn, off+L-t-tb0) reversed */
+    const uint64_t g0 = rev ? (off + L - t - tb0 - tn) : (off + t + tb0);
+    const uint32_t phase = (uint32_t)(g0 & 15u);
+    tps_stage_linear(a.pk, g0, tn, lin, lw, tid, TPS_K3_THREADS);
+    __syncthreads();
+    const uint32_t nq = (tn + 31u) >> 5;
+    for (uint32_t q = tid; q < tw; q += TPS_K3_THREADS) {
+      uint32_t p0, p1, v;
+      tps_oriented_word(lin, lw, phase, tn, rev, q, p0, p1, v);
+      ori[q] = p0;
+      ori[tw + q] = p1;
+      ori[2u * tw + q] = v;
     }
     __syncthreads();
-
-    /* K4: single change point, exact form of ruptures Binseg(l2, jump=5, min_size=2) */
-    if (tid < 32u) {
-      int32_t best_b = -1;
-      if (nW >= 7u) {
-        uint64_t T = 0;
-        for (uint32_t w = lane; w < nW; w += 32u) T += cw[w];
-#pragma unroll
-        for (int o = 16; o; o >>= 1) T += __shfl_xor_sync(TPS_FULL, T, o);
-        tps_cand best;
-        best.b = -1; best.num = 0; best.den = 1;
-        uint64_t carry = 0; /* sum of c_w over windows before this chunk */
-        for (uint32_t base = 0; base < nW; base += 160u) {
-          /* lane handles the 5 windows [base+5*lane, +5): candidate b = base+5*lane */
-          const uint32_t b = base + 5u * lane;
-          uint64_t g = 0;
-#pragma unroll
-          for (uint32_t i = 0; i < 5u; ++i)
-            if (b + i < nW) g += cw[b + i];
-          uint64_t inc = g;
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            uint64_t up = __shfl_up_sync(TPS_FULL, inc, o);
-            if ((int)lane >= o) inc += up;
-          }
-          const uint64_t S_b = carry + inc - g; /* exclusive prefix = sum_{w<b} c_w */
-          if (b >= 2u && b < nW && nW - b >= 2u) {
-            tps_cand c = tps_make_cand(nW, S_b, T, b);
-            if (tps_cand_better(&best, &c)) best = c;
-          }
-          carry += __shfl_sync(TPS_FULL, inc, 31);
+    for (uint32_t i = tid; i < nq * TPS_K3_PSPLIT; i += TPS_K3_THREADS) {
+      const uint32_t h = i / nq, q = i - h * nq;
+      TpsWin<K> win;
+      tps_win_init<K>(win, ori[q], ori[q + 1], ori[tw + q], ori[tw + q + 1], ori[2u * tw + q],
+                      ori[2u * tw + q + 1]);
+      for (uint32_t p = h; p < pt.n; p += TPS_K3_PSPLIT) mrows[p * tw + q] = tps_win_match<K>(win, pm, pt, p);
+    }
+    __syncthreads();
+    for (uint32_t w = wlo + tid; w < whi; w += TPS_K3_THREADS) {
+      const int32_t ls = (int32_t)(w * s - tb0);
+      uint32_t c = 0;
+      for (uint32_t p = 0; p < pt.n; ++p) {
+        const uint32_t k = pt.len[p];
+        uint32_t cnt = 0;
+        if (W - 1u >= k) {
+          const int32_t to = ls + (int32_t)(W - 1u - k);
+          cnt = pt.bordered[p] ? tps_greedy_count(mrows + p * tw, ls, to, k)
+                               : tps_range_popcount(mrows + p * tw, ls, to);
         }
-        /* warp argmax with the exact comparator (ties -> larger b) */
-#pragma unroll
-        for (int o = 16; o; o >>= 1) {
-          tps_cand oth;
-          uint64_t nlo = (uint64_t)best.num, nhi = (uint64_t)(best.num >> 64);
-          nlo = __shfl_xor_sync(TPS_FULL, nlo, o);
-          nhi = __shfl_xor_sync(TPS_FULL, nhi, o);
-          oth.num = ((unsigned __int128)nhi << 64) | nlo;
-          oth.den = __shfl_xor_sync(TPS_FULL, best.den, o);
-          oth.b = __shfl_xor_sync(TPS_FULL, best.b, o);
-          if (tps_cand_better(&best, &oth)) best = oth;
-        }
-        best_b = best.b;
+        if (cnt == 0u) cnt = 1u; /* `... or 1`, allsteps.py:281,288 */
+        c += cnt;
+        if (raw_off != ~0ull) a.raw[raw_off + (uint64_t)w * pt.n + p] = (uint8_t)cnt;
       }
-      if (lane == 0) {
-        tps_row *row = a.rows + r;
-        row->n_windows = nW;
-        if (best_b >= 0) {
-          row->bkp = best_b;
-          row->telo_length = (int32_t)(t + s * (uint32_t)best_b); /* x[bkp], allsteps.py:304,312 */
-        } else {
-          row->status = TPS_ST_BADSEG;
+      cw[w] = c;
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------------------ K4 */
+#define TPS_K4_THREADS 128
+
+/* One warp per passing read: single change point of c_w, the exact form of ruptures
+ * Binseg(model="l2", jump=5, min_size=2).predict(n_bkps=1):
+ * argmax over b in {5,10,...}, 2 <= b <= n-2 of (n*S_b - b*T)^2 / (b*(n-b)), ties -> larger b. */
+__global__ void __launch_bounds__(TPS_K4_THREADS)
+tps_changepoint_kernel(const TpsScanArgs a) {
+  const uint32_t lane = threadIdx.x & 31u;
+  uint32_t n_pass = a.counters[0];
+  if (n_pass > a.max_pass) n_pass = a.max_pass;
+  for (;;) {
+    uint32_t pi = 0;
+    if (lane == 0) pi = atomicAdd(a.counters + 5, 1u);
+    pi = __shfl_sync(TPS_FULL, pi, 0);
+    if (pi >= n_pass) break;
+    const uint32_t r = a.pass_list[pi];
+    const uint32_t nW = a.rows[r].n_windows;
+    const uint32_t *cw = a.cw + (size_t)pi * a.cw_stride;
+    int32_t best_b = -1;
+    if (nW >= 7u) { /* ruptures sanity_check: n >= 7 for jump 5, min_size 2, one breakpoint */
+      uint64_t T = 0;
+      for (uint32_t w = lane; w < nW; w += 32u) T += cw[w];
+#pragma unroll
+      for (int o = 16; o; o >>= 1) T += __shfl_xor_sync(TPS_FULL, T, o);
+      tps_cand best;
+      best.b = -1; best.num = 0; best.den = 1;
+      uint64_t carry = 0; /* sum of c_w over windows before this chunk */
+      for (uint32_t base = 0; base < nW; base += 160u) {
+        /* lane handles the 5 windows [base+5*lane, +5): candidate b = base+5*lane */
+        const uint32_t b = base + 5u * lane;
+        uint64_t g = 0;
+#pragma unroll
+        for (uint32_t i = 0; i < 5u; ++i)
+          if (b + i < nW) g += cw[b + i];
+        uint64_t inc = g;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          uint64_t up = __shfl_up_sync(TPS_FULL, inc, o);
+          if ((int)lane >= o) inc += up;
         }
+        const uint64_t S_b = carry + inc - g; /* exclusive prefix = sum_{w<b} c_w */
+        if (b >= 2u && b < nW && nW - b >= 2u) {
+          tps_cand c = tps_make_cand(nW, S_b, T, b);
+          if (tps_cand_better(&best, &c)) best = c;
+        }
+        carry += __shfl_sync(TPS_FULL, inc, 31);
+      }
+      /* warp argmax with the exact comparator (ties -> larger b) */
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        tps_cand oth;
+        uint64_t nlo = (uint64_t)best.num, nhi = (uint64_t)(best.num >> 64);
+        nlo = __shfl_xor_sync(TPS_FULL, nlo, o);
+        nhi = __shfl_xor_sync(TPS_FULL, nhi, o);
+        oth.num = ((unsigned __int128)nhi << 64) | nlo;
+        oth.den = __shfl_xor_sync(TPS_FULL, best.den, o);
+        oth.b = __shfl_xor_sync(TPS_FULL, best.b, o);
+        if (tps_cand_better(&best, &oth)) best = oth;
+      }
+      best_b = best.b;
+    }
+    if (lane == 0) {
+      tps_row *row = a.rows + r;
+      if (best_b >= 0) {
+        row->bkp = best_b;
+        row->telo_length = (int32_t)(a.trimfirst + a.slide * (uint32_t)best_b); /* x[bkp], allsteps.py:304,312 */
+      } else {
+        row->status = TPS_ST_BADSEG;
       }
     }
   }

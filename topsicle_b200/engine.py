@@ -45,6 +45,8 @@ class TpsParams(C.Structure):
         ("want_rawcount", C.c_uint32),
         ("n_slots", C.c_uint32),
         ("max_batch_reads", C.c_uint32),
+        ("max_pass_reads", C.c_uint32),
+        ("reserved", C.c_uint32),
         ("max_batch_bases", C.c_uint64),
         ("rawcount_capacity", C.c_uint64),
     ]
@@ -160,7 +162,7 @@ class ScanContext:
                  min_seq_length: int = 9000, no_bp: int = 1000, window_size: int = 100, slide: int = 6,
                  trimfirst: int = 100, maxlengthtelo: int = 20000, want_rawcount: bool = False,
                  device: int = 0, n_slots: int = 2, max_batch_reads: int = 1 << 16,
-                 max_batch_bases: int = 1 << 28, rawcount_capacity: int = 0,
+                 max_batch_bases: int = 1 << 28, max_pass_reads: int = 0, rawcount_capacity: int = 0,
                  count_threshold_override: int | None = None):
         self.lib = load_library()
         self.patterns = [p.upper() for p in patterns]
@@ -186,6 +188,7 @@ class ScanContext:
         p.n_slots = n_slots
         p.max_batch_reads = max_batch_reads
         p.max_batch_bases = max_batch_bases
+        p.max_pass_reads = max_pass_reads
         if want_rawcount and not rawcount_capacity:
             nreg = max(0, maxlengthtelo - trimfirst)
             nw = (nreg - window_size) // slide + 1 if nreg >= window_size else 0

@@ -21,7 +21,7 @@ def lib():
     src = os.path.join(HERE, "csrc", "bitops_host.cpp")
     subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-o", so, src])
     L = C.CDLL(so)
-    for f in ("t_pack16", "t_exact_mask16", "t_code_at", "t_linear_planes", "t_ascii_code", "t_greedy_count",
+    for f in ("t_pack16", "t_exact_mask16", "t_exact_mask16_simd", "t_code_at", "t_linear_planes", "t_ascii_code", "t_greedy_count",
               "t_range_popcount"):
         getattr(L, f).restype = C.c_uint32
     L.t_change_point.restype = C.c_int32
@@ -47,6 +47,7 @@ def test_pack16_all_bytes(lib):
         want_bad = any(x not in valid for x in b)
         assert (bad.value != 0) == want_bad, b
         mask = lib.t_exact_mask16(b)
+        assert lib.t_exact_mask16_simd(b) == mask, b
         for g in range(16):
             assert ((mask >> g) & 1) == (b[g] in valid)
             if b[g] in valid:

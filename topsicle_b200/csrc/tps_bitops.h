@@ -25,7 +25,9 @@
 #endif
 
 /* ---- K1: 16 ASCII bytes -> code word, and "group has an invalid byte" flag ---------- */
-TPS_HD uint32_t tps_pack16(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t *bad_out) {
+/* Field layout: base g = 4*i + m (word i, byte m) owns bits 8m+2i, 8m+2i+1. */
+TPS_HD uint32_t tps_pack16(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t *bad_out,
+                           uint32_t *rel_out) {
   /* bits 1,2 of every byte -> 2-bit fields at 8m+2i */
   uint32_t u = ((w0 >> 1) & 0x03030303u) | ((w1 << 1) & 0x0C0C0C0Cu) | ((w2 << 3) & 0x30303030u) |
                ((w3 << 5) & 0xC0C0C0C0u);
@@ -37,12 +39,39 @@ TPS_HD uint32_t tps_pack16(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, u
   /* z = ascii bit2 & ~bit1 : 1 only for T/t among the valid letters */
   uint32_t z = (u >> 1) & ~u;
   /* valid letter <=> bit7=0, bit6=1, bit3=0, bit4 == z, bit0 == !z  (bit5 = case, ignored) */
-  uint32_t bad = ((u4 ^ z) | ~(u0 ^ z)) & 0x55555555u;
-  uint32_t o = w0 | w1 | w2 | w3;
-  uint32_t a = w0 & w1 & w2 & w3;
-  bad |= (o & 0x88888888u) | (~a & 0x40404040u);
-  *bad_out = bad;
+  uint32_t rel = ((u4 ^ z) | ~(u0 ^ z)) & 0x55555555u;
+  /* bits 7,6,3 must read 0,1,0 in every byte: OR of (w ^ 0x40) over the four words */
+  uint32_t hi = ((w0 ^ 0x40404040u) | (w1 ^ 0x40404040u)) | ((w2 ^ 0x40404040u) | (w3 ^ 0x40404040u));
+  *bad_out = rel | (hi & 0xC8C8C8C8u);
+  *rel_out = rel;
   return u;
+}
+
+/* even-bit field word (bit 8m+2i for base 4i+m) -> 16 bits in linear base order */
+TPS_HD uint32_t tps_fields_to_linear16(uint32_t x) {
+  x &= 0x55555555u;
+  x = (x | (x >> 1)) & 0x33333333u;
+  x = (x | (x >> 2)) & 0x0F0F0F0Fu;
+  x = (x | (x >> 4)) & 0x00FF00FFu;
+  x = (x | (x >> 8)) & 0x0000FFFFu;
+  uint32_t t = (x ^ (x >> 3)) & 0x0A0Au;
+  x ^= t ^ (t << 3);
+  t = (x ^ (x >> 6)) & 0x00CCu;
+  x ^= t ^ (t << 6);
+  return x;
+}
+
+/* exact validity bits (bit g = base g is ACGTacgt) of a flagged group, branch-free;
+ * `rel` is the relational part already computed by tps_pack16 */
+TPS_HD uint32_t tps_exact_mask16_simd(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t rel) {
+  uint32_t u7 = ((w0 >> 7) & 0x01010101u) | ((w1 >> 5) & 0x04040404u) | ((w2 >> 3) & 0x10101010u) |
+                ((w3 >> 1) & 0x40404040u);
+  uint32_t u6 = ((w0 >> 6) & 0x01010101u) | ((w1 >> 4) & 0x04040404u) | ((w2 >> 2) & 0x10101010u) |
+                (w3 & 0x40404040u);
+  uint32_t u3 = ((w0 >> 3) & 0x01010101u) | ((w1 >> 1) & 0x04040404u) | ((w2 << 1) & 0x10101010u) |
+                ((w3 << 3) & 0x40404040u);
+  uint32_t inv = rel | u7 | u3 | (~u6 & 0x55555555u);
+  return (~tps_fields_to_linear16(inv)) & 0xFFFFu;
 }
 
 TPS_HD int tps_byte_is_acgt(uint32_t c) {

@@ -79,23 +79,19 @@ __device__ __forceinline__ uint4 tps_ldg_stream(const uint4 *p) {
 #define TPS_K1_THREADS 256
 #define TPS_K1_UNROLL 4
 
-/* Rare path (a group holds a non-ACGT byte): kept out of line so that the hot loop does not
- * carry its 16 x 4 byte compares as predicated code. */
-__device__ __noinline__ void tps_store_exact_mask(uint16_t *dst, uint32_t w0, uint32_t w1, uint32_t w2,
-                                                  uint32_t w3) {
-  *dst = (uint16_t)tps_exact_mask16(w0, w1, w2, w3);
-}
-
 __device__ __forceinline__ void tps_pack_tile(const uint4 &v, uint32_t *__restrict__ codes,
                                               uint32_t *__restrict__ flags, uint16_t *__restrict__ masks,
                                               uint64_t tile, uint32_t lane) {
-  uint32_t bad;
-  const uint32_t code = tps_pack16(v.x, v.y, v.z, v.w, &bad);
+  uint32_t bad, rel;
+  const uint32_t code = tps_pack16(v.x, v.y, v.z, v.w, &bad, &rel);
   const uint64_t g = tile * 32 + lane;
   codes[g] = code;
   const uint32_t fl = __ballot_sync(TPS_FULL, bad != 0u);
   if (lane == 0) flags[tile] = fl;
-  if (bad != 0u) tps_store_exact_mask(masks + g, v.x, v.y, v.z, v.w);
+  if (fl != 0u) { /* warp-uniform; ~20 % of tiles at 0.05 % N: exact per-base validity, branch-free */
+    const uint32_t m = tps_exact_mask16_simd(v.x, v.y, v.z, v.w, rel);
+    if (bad != 0u) masks[g] = (uint16_t)m;
+  }
 }
 
 /* One warp converts 512 consecutive bases per tile: lane l loads bytes [16l,16l+16) as one

@@ -150,7 +150,7 @@ def reference_arm(a):
     from topsicle_b200 import synth
     spec = synth.CONFIGS[a.config]
     cores = len(os.sched_getaffinity(0))
-    reads = a.cpu_sample_reads or min(2500 * cores, 60000)
+    reads = a.cpu_sample_reads or min(4000 * cores, 100000)
     r = run_cpu_baseline(a.config, reads, steps=a.steps, warmup=a.warmup)
     t = sum(r["seconds"])
     value = r["bases"] * a.steps / t / 1e9
@@ -195,7 +195,7 @@ def main():
     cpu = None
     if world == 1 and not a.no_cpu_baseline:
         cores = len(os.sched_getaffinity(0))
-        sample_reads = a.cpu_sample_reads or min(2500 * cores, 60000)
+        sample_reads = a.cpu_sample_reads or min(10000 * cores, 200000)
         r = run_cpu_baseline(a.config, sample_reads)
         cpu = {"value": r["gbases_per_s"][0], "unit": UNIT, "cores": r["cores"], "kind": "port",
                "reads_per_s": r["reads_per_s"][0],

@@ -7,15 +7,13 @@ uint32_t t_pack16(const uint8_t *b, uint32_t *bad) {
   uint32_t w[4];
   for (int i = 0; i < 4; ++i)
     w[i] = (uint32_t)b[4 * i] | ((uint32_t)b[4 * i + 1] << 8) | ((uint32_t)b[4 * i + 2] << 16) | ((uint32_t)b[4 * i + 3] << 24);
-  uint32_t rel;
-  return tps_pack16(w[0], w[1], w[2], w[3], bad, &rel);
+  return tps_pack16(w[0], w[1], w[2], w[3], bad);
 }
 uint32_t t_exact_mask16_simd(const uint8_t *b) {
-  uint32_t w[4], bad, rel;
+  uint32_t w[4];
   for (int i = 0; i < 4; ++i)
     w[i] = (uint32_t)b[4 * i] | ((uint32_t)b[4 * i + 1] << 8) | ((uint32_t)b[4 * i + 2] << 16) | ((uint32_t)b[4 * i + 3] << 24);
-  tps_pack16(w[0], w[1], w[2], w[3], &bad, &rel);
-  return tps_exact_mask16_simd(w[0], w[1], w[2], w[3], rel);
+  return tps_exact_mask16_simd(w[0], w[1], w[2], w[3]);
 }
 uint32_t t_exact_mask16(const uint8_t *b) {
   uint32_t w[4];

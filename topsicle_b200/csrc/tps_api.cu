@@ -54,7 +54,8 @@ struct tps_ctx {
   int kt = 0; /* template K of the K2/K3 instantiation in use (0 = generic) */
   void (*k2_fn)(const TpsScanArgs, const TpsPatTable) = nullptr;
   void (*k3_fn)(const TpsScanArgs, const TpsPatTable) = nullptr;
-  int k1_grid = 0;
+  int k1_grid = 0, k1_unroll = 4;
+  void (*k1_fn)(const uint4 *, uint32_t *, uint32_t *, uint16_t *, uint64_t) = nullptr;
   uint64_t cap_tiles = 0;
   Slot slots[4];
   cudaEvent_t ev[TPS_TIMING_RING][4]; /* CUDA-event ring: one set of 4 events per timed scan */
@@ -268,7 +269,21 @@ int tps_create(tps_ctx **out, int device, const tps_params *params) {
   TPS_CC(cudaFuncSetAttribute(ctx->k2_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->k2_smem));
   TPS_CC(cudaFuncSetAttribute(ctx->k3_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->k3_smem));
   int occ1 = 0, occ3 = 0, occ4 = 0;
-  TPS_CC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, tps_pack_kernel, TPS_K1_THREADS, 0));
+  {
+    const char *e = getenv("TPS_K1_UNROLL"); /* tuning knob: 2, 4 (default) or 8 tiles in flight per warp */
+    ctx->k1_unroll = e ? atoi(e) : 4;
+    if (ctx->k1_unroll == 8) ctx->k1_fn = tps_pack_kernel<8>;
+    else { ctx->k1_unroll = 4; ctx->k1_fn = tps_pack_kernel<4>; }
+#ifdef TPS_TUNING
+    const char *pv = getenv("TPS_K1_PROBE");
+    if (pv && atoi(pv) == 1) { ctx->k1_unroll = 4; ctx->k1_fn = tps_pack_probe<4, 1>; }
+    if (pv && atoi(pv) == 2) { ctx->k1_unroll = 4; ctx->k1_fn = tps_pack_probe<4, 2>; }
+    if (pv && atoi(pv) == 3) { ctx->k1_unroll = 8; ctx->k1_fn = tps_pack_probe<8, 2>; }
+    if (pv && atoi(pv) == 4) { ctx->k1_unroll = 4; ctx->k1_fn = tps_pack_probe<4, 4>; }
+    if (pv && atoi(pv) == 5) { ctx->k1_unroll = 4; ctx->k1_fn = tps_pack_probe<4, 5>; }
+#endif
+  }
+  TPS_CC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, ctx->k1_fn, TPS_K1_THREADS, 0));
   TPS_CC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3, ctx->k3_fn, TPS_K3_THREADS, ctx->k3_smem));
   TPS_CC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ4, tps_changepoint_kernel, TPS_K4_THREADS, 0));
   ctx->k1_grid = ctx->n_sms * (occ1 > 0 ? occ1 : 1);
@@ -315,9 +330,10 @@ int enqueue_scan(tps_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t *d_bases,
   if (timed) TPS_CUDA(ctx, cudaEventRecord(ev[0], st));
   const uint64_t n_tiles = (n_bases + 511) / 512;
   if (n_tiles) {
-    uint64_t want = (n_tiles + (TPS_K1_THREADS / 32) * TPS_K1_UNROLL - 1) / ((TPS_K1_THREADS / 32) * TPS_K1_UNROLL);
+    const uint64_t per_cta = (uint64_t)(TPS_K1_THREADS / 32) * ctx->k1_unroll;
+    uint64_t want = (n_tiles + per_cta - 1) / per_cta;
     int grid = (int)(want < (uint64_t)ctx->k1_grid ? want : (uint64_t)ctx->k1_grid);
-    tps_pack_kernel<<<grid, TPS_K1_THREADS, 0, st>>>(reinterpret_cast<const uint4 *>(d_bases), s.d_codes, s.d_flags,
+    ctx->k1_fn<<<grid, TPS_K1_THREADS, 0, st>>>(reinterpret_cast<const uint4 *>(d_bases), s.d_codes, s.d_flags,
                                                      s.d_masks, n_tiles);
     ctx->launches++;
   }

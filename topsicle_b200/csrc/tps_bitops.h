@@ -26,24 +26,20 @@
 
 /* ---- K1: 16 ASCII bytes -> code word, and "group has an invalid byte" flag ---------- */
 /* Field layout: base g = 4*i + m (word i, byte m) owns bits 8m+2i, 8m+2i+1. */
-TPS_HD uint32_t tps_pack16(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t *bad_out,
-                           uint32_t *rel_out) {
+TPS_HD uint32_t tps_pack16(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t *bad_out) {
   /* bits 1,2 of every byte -> 2-bit fields at 8m+2i */
   uint32_t u = ((w0 >> 1) & 0x03030303u) | ((w1 << 1) & 0x0C0C0C0Cu) | ((w2 << 3) & 0x30303030u) |
                ((w3 << 5) & 0xC0C0C0C0u);
-  /* bit 0 and bit 4 of every byte -> even bit positions 8m+2i (same layout as the low code bit) */
-  uint32_t u0 = (w0 & 0x01010101u) | ((w1 << 2) & 0x04040404u) | ((w2 << 4) & 0x10101010u) |
-                ((w3 << 6) & 0x40404040u);
-  uint32_t u4 = ((w0 >> 4) & 0x01010101u) | ((w1 >> 2) & 0x04040404u) | (w2 & 0x10101010u) |
-                ((w3 << 2) & 0x40404040u);
-  /* z = ascii bit2 & ~bit1 : 1 only for T/t among the valid letters */
-  uint32_t z = (u >> 1) & ~u;
-  /* valid letter <=> bit7=0, bit6=1, bit3=0, bit4 == z, bit0 == !z  (bit5 = case, ignored) */
-  uint32_t rel = ((u4 ^ z) | ~(u0 ^ z)) & 0x55555555u;
+  /* A byte is one of ACGTacgt <=> bit7=0, bit6=1, bit3=0, bit4 == z, bit0 == !z with
+   * z = bit2 & ~bit1 (1 only for T/t); bit5 is the case bit and is ignored.  The relational
+   * part is evaluated per word at bit position 4 using left shifts only (they run on the FMA
+   * pipe as IMAD.SHL, keeping the ALU pipe for the LOP3s). */
+#define TPS_REL4(w) ((((w) ^ (((w) << 2) & ~((w) << 3))) | ~((((w) << 4)) ^ (((w) << 2) & ~((w) << 3)))))
+  uint32_t inv = (TPS_REL4(w0) | TPS_REL4(w1)) | (TPS_REL4(w2) | TPS_REL4(w3));
+#undef TPS_REL4
   /* bits 7,6,3 must read 0,1,0 in every byte: OR of (w ^ 0x40) over the four words */
   uint32_t hi = ((w0 ^ 0x40404040u) | (w1 ^ 0x40404040u)) | ((w2 ^ 0x40404040u) | (w3 ^ 0x40404040u));
-  *bad_out = rel | (hi & 0xC8C8C8C8u);
-  *rel_out = rel;
+  *bad_out = (inv & 0x10101010u) | (hi & 0xC8C8C8C8u);
   return u;
 }
 
@@ -61,16 +57,25 @@ TPS_HD uint32_t tps_fields_to_linear16(uint32_t x) {
   return x;
 }
 
-/* exact validity bits (bit g = base g is ACGTacgt) of a flagged group, branch-free;
- * `rel` is the relational part already computed by tps_pack16 */
-TPS_HD uint32_t tps_exact_mask16_simd(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t rel) {
+/* exact validity bits (bit g = base g is ACGTacgt) of a flagged group, branch-free */
+TPS_HD uint32_t tps_exact_mask16_simd(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+  /* every tested ASCII bit gathered to the even field positions 8m+2i */
+  uint32_t u1 = ((w0 >> 1) & 0x01010101u) | ((w1 << 1) & 0x04040404u) | ((w2 << 3) & 0x10101010u) |
+                ((w3 << 5) & 0x40404040u);
+  uint32_t u2 = ((w0 >> 2) & 0x01010101u) | (w1 & 0x04040404u) | ((w2 << 2) & 0x10101010u) |
+                ((w3 << 4) & 0x40404040u);
+  uint32_t u0 = (w0 & 0x01010101u) | ((w1 << 2) & 0x04040404u) | ((w2 << 4) & 0x10101010u) |
+                ((w3 << 6) & 0x40404040u);
+  uint32_t u4 = ((w0 >> 4) & 0x01010101u) | ((w1 >> 2) & 0x04040404u) | (w2 & 0x10101010u) |
+                ((w3 << 2) & 0x40404040u);
   uint32_t u7 = ((w0 >> 7) & 0x01010101u) | ((w1 >> 5) & 0x04040404u) | ((w2 >> 3) & 0x10101010u) |
                 ((w3 >> 1) & 0x40404040u);
   uint32_t u6 = ((w0 >> 6) & 0x01010101u) | ((w1 >> 4) & 0x04040404u) | ((w2 >> 2) & 0x10101010u) |
                 (w3 & 0x40404040u);
   uint32_t u3 = ((w0 >> 3) & 0x01010101u) | ((w1 >> 1) & 0x04040404u) | ((w2 << 1) & 0x10101010u) |
                 ((w3 << 3) & 0x40404040u);
-  uint32_t inv = rel | u7 | u3 | (~u6 & 0x55555555u);
+  uint32_t z = u2 & ~u1;
+  uint32_t inv = (u4 ^ z) | ~(u0 ^ z) | u7 | u3 | ~u6;
   return (~tps_fields_to_linear16(inv)) & 0xFFFFu;
 }
 

@@ -77,46 +77,101 @@ __device__ __forceinline__ uint4 tps_ldg_stream(const uint4 *p) {
 }
 
 #define TPS_K1_THREADS 256
-#define TPS_K1_UNROLL 4
 
-__device__ __forceinline__ void tps_pack_tile(const uint4 &v, uint32_t *__restrict__ codes,
-                                              uint32_t *__restrict__ flags, uint16_t *__restrict__ masks,
-                                              uint64_t tile, uint32_t lane) {
-  uint32_t bad, rel;
-  const uint32_t code = tps_pack16(v.x, v.y, v.z, v.w, &bad, &rel);
-  const uint64_t g = tile * 32 + lane;
-  codes[g] = code;
-  const uint32_t fl = __ballot_sync(TPS_FULL, bad != 0u);
-  if (lane == 0) flags[tile] = fl;
-  if (fl != 0u) { /* warp-uniform; ~20 % of tiles at 0.05 % N: exact per-base validity, branch-free */
-    const uint32_t m = tps_exact_mask16_simd(v.x, v.y, v.z, v.w, rel);
-    if (bad != 0u) masks[g] = (uint16_t)m;
+/* Exact validity of a flagged tile: every lane stores its group's 16-bit mask, so the tile's
+ * 64 bytes of masks are written as two full 32-byte sectors (sparse 2-byte stores by the bad
+ * lanes alone cost more than they save: partial-sector writes). */
+__device__ __forceinline__ void tps_store_tile_masks(const uint4 &v, uint16_t *__restrict__ mp) {
+  *mp = (uint16_t)tps_exact_mask16_simd(v.x, v.y, v.z, v.w);
+}
+
+#ifdef TPS_TUNING
+/* tuning probes (not used by the product): V=1 codes only, V=2 load + trivial store */
+template <int U, int V>
+__global__ void __launch_bounds__(TPS_K1_THREADS)
+tps_pack_probe(const uint4 *__restrict__ bases, uint32_t *__restrict__ codes, uint32_t *__restrict__ flags,
+               uint16_t *__restrict__ masks, uint64_t n_tiles) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint64_t warp = (uint64_t)blockIdx.x * (TPS_K1_THREADS / 32) + (threadIdx.x >> 5);
+  const uint64_t stride = (uint64_t)gridDim.x * (TPS_K1_THREADS / 32) * U;
+  const uint64_t n_main = n_tiles / U * U;
+  for (uint64_t t0 = warp * U; t0 < n_main; t0 += stride) {
+    uint4 v[U];
+    const uint64_t g0 = t0 * 32 + lane;
+    const uint4 *src = bases + g0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u] = tps_ldg_stream(src + u * 32);
+    uint32_t *cp = codes + g0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (V == 1) {
+        uint32_t w0 = v[u].x, w1 = v[u].y, w2 = v[u].z, w3 = v[u].w;
+        cp[u * 32] = ((w0 >> 1) & 0x03030303u) | ((w1 << 1) & 0x0C0C0C0Cu) | ((w2 << 3) & 0x30303030u) |
+                     ((w3 << 5) & 0xC0C0C0C0u);
+      } else if (V == 4) { /* codes + flags, no exact-mask path */
+        uint32_t bad;
+        cp[u * 32] = tps_pack16(v[u].x, v[u].y, v[u].z, v[u].w, &bad);
+        const uint32_t fl = __ballot_sync(TPS_FULL, bad != 0u);
+        if (lane == 0) flags[t0 + u] = fl;
+      } else if (V == 5) { /* codes + per-lane bad OR-ed into one store, no ballot */
+        uint32_t bad;
+        cp[u * 32] = tps_pack16(v[u].x, v[u].y, v[u].z, v[u].w, &bad);
+        if (bad) masks[g0 + u * 32] = 1;
+      } else {
+        cp[u * 32] = v[u].x ^ v[u].y ^ v[u].z ^ v[u].w;
+      }
+    }
   }
 }
+#endif
 
 /* One warp converts 512 consecutive bases per tile: lane l loads bytes [16l,16l+16) as one
  * 128-bit load (512 B coalesced per warp instruction), emits one code word (128 B coalesced
- * store per warp), and the warp emits one flag word by ballot.  TPS_K1_UNROLL tiles are
- * loaded before any is converted so each thread keeps 4 x 16 B in flight. */
+ * store per warp), and the warp emits one flag word per tile by ballot (lane 0 stores the U
+ * flag words of its U consecutive tiles as 128-bit vectors).  U tiles are loaded before any is
+ * converted so each thread keeps U x 16 B in flight.  U must be a multiple of 4. */
+template <int U>
 __global__ void __launch_bounds__(TPS_K1_THREADS)
 tps_pack_kernel(const uint4 *__restrict__ bases, uint32_t *__restrict__ codes,
                 uint32_t *__restrict__ flags, uint16_t *__restrict__ masks, uint64_t n_tiles) {
+  static_assert(U % 4 == 0, "U must be a multiple of 4 (vector flag stores)");
   const uint32_t lane = threadIdx.x & 31u;
   const uint64_t warp = (uint64_t)blockIdx.x * (TPS_K1_THREADS / 32) + (threadIdx.x >> 5);
-  const uint64_t stride = (uint64_t)gridDim.x * (TPS_K1_THREADS / 32) * TPS_K1_UNROLL;
-  const uint64_t n_main = n_tiles / TPS_K1_UNROLL * TPS_K1_UNROLL;
-  for (uint64_t t0 = warp * TPS_K1_UNROLL; t0 < n_main; t0 += stride) {
-    uint4 v[TPS_K1_UNROLL];
-    const uint4 *src = bases + t0 * 32 + lane;
+  const uint64_t stride = (uint64_t)gridDim.x * (TPS_K1_THREADS / 32) * U;
+  const uint64_t n_main = n_tiles / U * U;
+  for (uint64_t t0 = warp * U; t0 < n_main; t0 += stride) {
+    uint4 v[U];
+    uint32_t fl[U];
+    const uint64_t g0 = t0 * 32 + lane;
+    const uint4 *src = bases + g0;
 #pragma unroll
-    for (int u = 0; u < TPS_K1_UNROLL; ++u) v[u] = tps_ldg_stream(src + u * 32);
+    for (int u = 0; u < U; ++u) v[u] = tps_ldg_stream(src + u * 32);
+    uint32_t *cp = codes + g0;
 #pragma unroll
-    for (int u = 0; u < TPS_K1_UNROLL; ++u) tps_pack_tile(v[u], codes, flags, masks, t0 + u, lane);
+    for (int u = 0; u < U; ++u) {
+      uint32_t bad;
+      cp[u * 32] = tps_pack16(v[u].x, v[u].y, v[u].z, v[u].w, &bad);
+      fl[u] = __ballot_sync(TPS_FULL, bad != 0u);
+    }
+    if (lane == 0) {
+      uint4 *fp = reinterpret_cast<uint4 *>(flags + t0); /* t0 is a multiple of U: 16-byte aligned */
+#pragma unroll
+      for (int u = 0; u < U; u += 4) fp[u / 4] = make_uint4(fl[u], fl[u + 1], fl[u + 2], fl[u + 3]);
+    }
+    uint16_t *mp = masks + g0;
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (fl[u] != 0u) tps_store_tile_masks(v[u], mp + u * 32); /* warp-uniform, ~20 % of tiles at 0.05 % N */
   }
-  const uint64_t tt = n_main + warp; /* at most UNROLL-1 trailing tiles, one warp each */
+  const uint64_t tt = n_main + warp; /* at most U-1 trailing tiles, one warp each */
   if (tt < n_tiles) {
-    const uint4 v = tps_ldg_stream(bases + tt * 32 + lane);
-    tps_pack_tile(v, codes, flags, masks, tt, lane);
+    const uint64_t g = tt * 32 + lane;
+    const uint4 v = tps_ldg_stream(bases + g);
+    uint32_t bad;
+    codes[g] = tps_pack16(v.x, v.y, v.z, v.w, &bad);
+    const uint32_t f = __ballot_sync(TPS_FULL, bad != 0u);
+    if (lane == 0) flags[tt] = f;
+    if (f != 0u) tps_store_tile_masks(v, masks + g);
   }
 }
 

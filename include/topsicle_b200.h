@@ -48,6 +48,12 @@ extern "C" {
 #define TPS_ST_BADSEG 3   /* TRC > cutoff but fewer than 7 windows: the reference raises
                              ruptures.BadSegmentationParameters (n>=1) or IndexError (n==0) */
 
+/* tps_params.flags */
+#define TPS_FLAG_STEP1_ONLY 1u    /* patternTRC_count alone: no windows / change point (allsteps.py:152-204) */
+#define TPS_FLAG_FORCE_FORWARD 2u /* bound_detect / rawCountPattern called with tail='forward': the caller,
+                                     not step 1, picks the end (allsteps.py:294-297, 413-416) */
+#define TPS_FLAG_FORCE_REVERSE 4u /* ... tail='reverse' */
+
 /* tps_row.tail */
 #define TPS_TAIL_FORWARD 0
 #define TPS_TAIL_REVERSE 1
@@ -72,7 +78,7 @@ typedef struct tps_params {
   uint32_t max_batch_reads; /* capacity per batch */
   uint32_t max_pass_reads;  /* capacity for TRC-pass reads per batch (0 = max_batch_reads); each costs
                                4 bytes x windows-per-read of device memory */
-  uint32_t reserved;
+  uint32_t flags;           /* TPS_FLAG_* */
   uint64_t max_batch_bases; /* capacity per batch (bytes of sequence) */
   uint64_t rawcount_capacity; /* per batch, in count elements (uint8 each); 0 if !want_rawcount */
 } tps_params;
@@ -125,6 +131,11 @@ int tps_submit(tps_ctx *ctx, const uint8_t *bases, const uint64_t *offsets, uint
  * in elements is rawcount_cap (TPS_ECAPACITY if too small; call again with a larger one). */
 int tps_wait(tps_ctx *ctx, uint64_t batch_id, tps_row *rows_out, uint32_t *n_pass_out,
              uint8_t *rawcounts_out, uint64_t rawcount_cap, uint64_t *rawcount_elems);
+
+/* Block until batch `batch_id` is done and report its sizes WITHOUT releasing it, so that the
+ * caller can size rawcounts_out for tps_wait: *n_pass_out = reads that passed the TRC cutoff,
+ * *rawcount_elems = count elements the batch produced. */
+int tps_batch_info(tps_ctx *ctx, uint64_t batch_id, uint32_t *n_pass_out, uint64_t *rawcount_elems);
 
 /* Scan a batch already resident in DEVICE memory (d_bases must be readable up to
  * n_bases rounded up to a multiple of 2048 bytes); rows are written to d_rows_out (device).

@@ -1,0 +1,116 @@
+"""TEST INFRASTRUCTURE ONLY -- an oracle-backed stand-in for `engine.ScanContext`.
+
+Lets the CPU test tier (`-m "not gpu"`) drive the host-side logic (reader -> pipeline ->
+CLI writers, sharding, gathering) without a GPU: batches are answered by the CPU oracle in
+the `tps_row` layout the CUDA library produces.  It is injected by monkeypatching
+`pipeline.make_context` / `engine.PinnedBuffer`; the product never imports it.
+"""
+import numpy as np
+
+from oracle import topsicle_oracle as orc
+from topsicle_b200 import engine
+
+
+class NumpyPinned:
+    """PinnedBuffer stand-in (plain host memory)."""
+
+    def __init__(self, nbytes):
+        self.nbytes = int(nbytes)
+        self.array = np.zeros(max(self.nbytes, 1), dtype=np.uint8)
+        self.ptr = self.array.ctypes.data
+
+    def free(self):
+        self.array = None
+
+
+class OracleContext:
+    def __init__(self, cfg, device, max_batch_reads, max_batch_bases, n_slots, max_pass_reads=0,
+                 rawcount_capacity=0):
+        self.cfg = cfg
+        self.patterns = [p.upper() for p in cfg.patterns]
+        self.max_pass = max_pass_reads or max_batch_reads
+        self.max_batch_reads, self.max_batch_bases = max_batch_reads, max_batch_bases
+        self.rawcount_capacity = rawcount_capacity
+        self.want_rawcount = cfg.want_rawcount
+        self.thr = (cfg.count_threshold_override if cfg.count_threshold_override is not None
+                    else engine.count_threshold(cfg.cutoff, cfg.len_telopattern, cfg.no_bp))
+        self._pending = {}
+        self._next = 1
+        self.closed = False
+
+    def submit(self, bases, offsets):
+        bid = self._next
+        self._next += 1
+        assert len(offsets) - 1 <= self.max_batch_reads and int(offsets[-1]) <= self.max_batch_bases
+        self._pending[bid] = (bases.tobytes(), np.array(offsets, dtype=np.uint64))
+        return bid
+
+    def wait(self, bid):
+        buf, off = self._pending.pop(bid)
+        cfg = self.cfg
+        n = len(off) - 1
+        rows = np.zeros(n, dtype=engine.ROW_DTYPE)
+        rows["bkp"] = -1
+        rows["telo_length"] = -1
+        rows["rawcount_offset"] = engine.NO_RAWCOUNT
+        raw_parts, raw_at, n_pass = [], 0, 0
+        for i in range(n):
+            seq = buf[int(off[i]):int(off[i + 1])].decode("latin-1")
+            rows["length"][i] = len(seq)
+            if not len(seq) > cfg.min_seq_length:
+                continue
+            tail, bi, cnt, ms, me, hc, tc = orc.trc_read(seq, self.patterns, cfg.len_telopattern, cfg.no_bp)
+            if cfg.force_tail:
+                tail = cfg.force_tail
+                cs = hc if tail == "forward" else tc
+                cnt = max(cs)
+                bi = cs.index(cnt)
+            rows["tail"][i] = 0 if tail == "forward" else 1
+            rows["best_pattern"][i] = bi
+            rows["match_count"][i], rows["head_max"][i], rows["tail_max"][i] = cnt, ms, me
+            if cnt < self.thr:
+                rows["status"][i] = engine.ST_BELOW
+                continue
+            rows["status"][i] = engine.ST_PASS
+            if cfg.step1_only:
+                continue
+            n_pass += 1
+            if n_pass > self.max_pass:
+                raise engine.TpsError(-4, "max_pass_reads exceeded")
+            region = orc.oriented_region(seq, tail, cfg.trimfirst, cfg.maxlengthtelo)
+            counts = orc.window_counts(region, self.patterns, cfg.window_size, cfg.slide)
+            rows["n_windows"][i] = counts.shape[0]
+            if cfg.want_rawcount and counts.shape[0]:
+                rows["rawcount_offset"][i] = raw_at
+                raw_parts.append(counts.astype(np.uint8).reshape(-1))
+                raw_at += counts.size
+                if raw_at > self.rawcount_capacity:
+                    raise engine.TpsError(-4, "rawcount_capacity exceeded")
+            if counts.shape[0] < 7:
+                rows["status"][i] = engine.ST_BADSEG
+                continue
+            b = orc.change_point_exact(counts.sum(axis=1))
+            rows["bkp"][i] = b
+            rows["telo_length"][i] = cfg.trimfirst + cfg.slide * b
+        raw = np.concatenate(raw_parts) if raw_parts else (np.zeros(0, np.uint8) if cfg.want_rawcount else None)
+        return rows, raw
+
+    def scan(self, bases, offsets):
+        return self.wait(self.submit(bases, offsets))
+
+    def rawcount_table(self, rows, raw, i):
+        off = int(rows["rawcount_offset"][i])
+        if raw is None or off == engine.NO_RAWCOUNT:
+            return None
+        nw, npat = int(rows["n_windows"][i]), len(self.patterns)
+        return raw[off:off + nw * npat].reshape(nw, npat)
+
+    def close(self):
+        self.closed = True
+
+
+def install(monkeypatch):
+    """Route pipeline contexts / pinned buffers to the CPU stand-ins."""
+    from topsicle_b200 import pipeline
+    monkeypatch.setattr(pipeline, "make_context", OracleContext)
+    monkeypatch.setattr(engine, "PinnedBuffer", NumpyPinned)

@@ -1,0 +1,60 @@
+"""CPU tier: the host side of the drop-in (reader -> batch pipeline -> CLI writers) with the GPU
+answered by the oracle stand-in (tests/fake_engine.py).  The real-kernel version of the same
+checks is tests/test_gpu_cli.py."""
+import os
+
+import numpy as np
+import pytest
+
+from tests import fake_engine
+from tests.cli_cases import golden_cases, run_case
+from tests.conftest import GOLD
+
+
+@pytest.mark.parametrize("case", golden_cases(), ids=lambda c: c["name"])
+def test_cli_matches_reference_outputs(case, tmp_path, monkeypatch):
+    fake_engine.install(monkeypatch)
+    run_case(case, tmp_path)
+
+
+def test_cli_small_batches_and_two_devices(tmp_path, monkeypatch):
+    """Tiny batches dealt over two (stand-in) devices: same bytes out, file order restored."""
+    fake_engine.install(monkeypatch)
+    monkeypatch.setenv("TOPSICLE_BATCH_READS", "3")
+    case = [c for c in golden_cases() if c["name"] == "CCCTAA_sweep_456_cut04_07"][0]
+    run_case(case, tmp_path, extra_argv=["--devices", "0", "1"])
+
+
+def test_cli_refuses_to_overwrite(tmp_path, monkeypatch):
+    fake_engine.install(monkeypatch)
+    case = golden_cases()[0]
+    run_case(case, tmp_path)
+    from topsicle_b200 import main as tmain
+    argv = ["--inputDir", str(tmp_path / "in"), "--outputDir", str(tmp_path / "out"), "--pattern", "CCCTAAA"]
+    with pytest.raises(SystemExit) as e:
+        tmain.main(argv)
+    assert e.value.code == 1
+    tmain.main(argv + ["--override", "--slide", "6"])
+    assert open(tmp_path / "out" / "telolengths_all.csv", newline="").read() == case["csv"]
+
+
+def test_cli_phrase_longer_than_pattern_exits(tmp_path, monkeypatch):
+    fake_engine.install(monkeypatch)
+    from topsicle_b200 import main as tmain
+    with pytest.raises(SystemExit):
+        tmain.main(["--inputDir", os.path.join(GOLD, "demo.fastq.gz"), "--outputDir", str(tmp_path / "o"),
+                    "--pattern", "CCCTAA", "--telophrase", "7"])
+
+
+def test_pass_capacity_overflow_is_split_not_lost(tmp_path, monkeypatch):
+    """More TRC-pass reads in a batch than the context can hold -> the batch is re-scanned in halves."""
+    fake_engine.install(monkeypatch)
+    from topsicle_b200 import pipeline
+    from topsicle_b200.patterns import patterns_to_search
+    cfg = pipeline.ScanConfig(patterns=patterns_to_search("CCCTAAA", 5), len_telopattern=7, phrase=5, slide=6)
+    path = os.path.join(GOLD, "demo.fastq.gz")
+    _, big = pipeline.collect_file(path, [cfg], max_pass_reads=1 << 10)
+    _, small = pipeline.collect_file(path, [cfg], max_pass_reads=2, max_batch_reads=1 << 10)
+    assert len(big[0]) == 17
+    assert [(p.index, p.read_id, p.telo_length) for p in small[0]] == [(p.index, p.read_id, p.telo_length)
+                                                                      for p in big[0]]

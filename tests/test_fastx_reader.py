@@ -1,0 +1,121 @@
+"""CPU tier: the C FASTQ/FASTA reader (csrc/tps_fastx.c) against the oracle's parser and against
+Biopython's record conventions as the reference relies on them."""
+import gzip
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from oracle import topsicle_oracle as orc
+from tests.conftest import GOLD
+from topsicle_b200 import fastx
+
+
+def read_all(path, max_reads=1 << 12, max_bases=1 << 22, window=None, threads=4):
+    out = []
+    with fastx.FastxFile(path, threads=threads) as fx:
+        if window:
+            fx.set_window(window)
+        bases = np.empty(max_bases, np.uint8)
+        offs = np.empty(max_reads + 1, np.uint64)
+        while True:
+            b = fx.next_batch(bases, offs)
+            if b is None:
+                break
+            assert b.first_read == len(out)
+            for i in range(b.n_reads):
+                out.append((b.read_id(i), b.sequence(i).decode(), b.title(i), b.record_text(i)))
+            b.release()
+    return out
+
+
+@pytest.mark.parametrize("name", ["demo.fastq.gz", "edge.fastq", "edge.fasta"])
+@pytest.mark.parametrize("caps", [(1 << 12, 1 << 22, None), (3, 1 << 20, 5000), (1, 1 << 20, 4096)])
+def test_reader_matches_oracle_parser(name, caps):
+    path = os.path.join(GOLD, name)
+    got = read_all(path, *caps)
+    assert [(a, b) for a, b, _, _ in got] == list(orc.read_fastx(path))
+
+
+def test_subset_text_is_seqio_write_format(tmp_path):
+    """record_text == what SeqIO.write emits: the reference's golden subset FASTQ is reproduced from the
+    ids of the golden CSV (md5 of Topsicle_demo/result_justone/..._trc_over_0.7.fastq)."""
+    path = os.path.join(GOLD, "demo.fastq.gz")
+    import json
+    case = json.load(open(os.path.join(GOLD, "demo_cli.json")))["cases"][0]
+    ids = {ln.split(",")[3] for ln in case["csv"].split("\r\n")[1:] if ln}
+    text = b"".join(r[3] for r in read_all(path) if r[0] in ids)
+    assert hashlib.md5(text).hexdigest() == case["files"]["demo.fastq_trc_over_0.7.fastq"]
+
+
+def test_fasta_conventions(tmp_path):
+    p = tmp_path / "x.fasta"
+    p.write_bytes(b">r1 desc here  \nACGT\r\nAC GT\n\nTT\n>r2\n>  r3\tz\nNNNN")
+    got = read_all(str(p))
+    assert [(g[0], g[1], g[2]) for g in got] == [("r1", "ACGTACGTTT", "r1 desc here"), ("r2", "", "r2"),
+                                                ("r3", "NNNN", "  r3\tz")]
+    assert got[0][3] == b">r1 desc here\nACGTACGTTT\n"
+    long = tmp_path / "long.fa"
+    seq = "ACGT" * 40
+    long.write_text(">a\n" + seq + "\n")
+    assert read_all(str(long))[0][3] == (">a\n" + seq[:60] + "\n" + seq[60:120] + "\n" + seq[120:] + "\n").encode()
+
+
+def test_fastq_conventions_and_errors(tmp_path):
+    p = tmp_path / "x.fq"
+    p.write_bytes(b"@a b c\r\nACGT\r\n+a b c\r\n@@@@\r\n\n@b\nAC\n+\n!!")      # '@' quality, CRLF, no final newline
+    got = read_all(str(p))
+    assert [(g[0], g[1]) for g in got] == [("a", "ACGT"), ("b", "AC")]
+    assert got[0][3] == b"@a b c\nACGT\n+\n@@@@\n"
+    bad = tmp_path / "bad.fq"
+    bad.write_bytes(b"@a\nACGT\n+\n!!!\n")
+    with pytest.raises(fastx.FastxError):
+        read_all(str(bad))
+    multi = tmp_path / "multi.fq"
+    multi.write_bytes(b"@a\nACGT\nACGT\n+\n!!!!!!!!\n")
+    with pytest.raises(fastx.FastxError):
+        read_all(str(multi))
+    other = tmp_path / "x.txt"
+    other.write_text("hello\n")
+    with pytest.raises(fastx.FastxError):
+        fastx.FastxFile(str(other))
+    assert fastx.sniff_format(str(other)) == 0
+    with pytest.raises(fastx.FastxError):
+        read_all(str(p), max_bases=3)                                        # read longer than the batch
+
+
+def test_parallel_index_equals_sequential(tmp_path):
+    """Big synthetic FASTQ (qualities full of '@' and '+'), plain and gzip: 8-thread segmented
+    indexing, small windows and the sequential path all give the same records."""
+    rng = np.random.default_rng(5)
+    p = tmp_path / "big.fastq"
+    want = []
+    with open(p, "wb") as fh:
+        for i in range(3000):
+            L = int(rng.integers(1, 4000))
+            seq = bytes(rng.choice(np.frombuffer(b"ACGTN", np.uint8), L))
+            qual = bytes(rng.choice(np.frombuffer(b"@+I!5", np.uint8), L))
+            fh.write(b"@r%d extra\n%s\n+\n%s\n" % (i, seq, qual))
+            want.append((f"r{i}", seq.decode()))
+    for threads, window in [(1, None), (8, None), (8, 3 << 20), (3, 1 << 20)]:
+        got = read_all(str(p), 1 << 12, 1 << 24, window, threads)
+        assert [(a, b) for a, b, _, _ in got] == want, (threads, window)
+    gz = tmp_path / "big.fastq.gz"
+    with open(p, "rb") as src, gzip.open(gz, "wb", compresslevel=1) as dst:
+        dst.write(src.read())
+    got = read_all(str(gz), 500, 1 << 20, 1 << 20, 4)
+    assert [(a, b) for a, b, _, _ in got] == want
+
+
+def test_rawcount_csv_text_equals_pandas():
+    import pandas as pd
+    rng = np.random.default_rng(1)
+    pats = ["AACC", "ACCC", "TTGG"]
+    counts = rng.integers(1, 15, (57, 3)).astype(np.uint8)
+    text = fastx.format_rawcount_csv(counts, 6, "reverse", pats)
+    rows = [("reverse", w * 6, pats[p], int(counts[w, p])) for w in range(57) for p in range(3)]
+    want = pd.DataFrame(rows, columns=["tail", "position", "pattern", "count"]).to_csv()
+    assert text.decode() == want
+    from topsicle_b200.allsteps import rawcount_frame
+    assert rawcount_frame(counts, "reverse", 6, pats).to_csv() == want

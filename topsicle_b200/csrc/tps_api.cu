@@ -189,6 +189,10 @@ int tps_create(tps_ctx **out, int device, const tps_params *params) {
   if (p.no_bp < 1 || p.no_bp > 32768) return fail(nullptr, TPS_EINVAL, "no_bp must be in 1..32768");
   if (p.n_slots < 1 || p.n_slots > 4) return fail(nullptr, TPS_EINVAL, "n_slots must be in 1..4");
   if (p.max_batch_reads < 1 || p.max_batch_bases < 1) return fail(nullptr, TPS_EINVAL, "batch capacities must be >= 1");
+  if (p.flags & ~(TPS_FLAG_STEP1_ONLY | TPS_FLAG_FORCE_FORWARD | TPS_FLAG_FORCE_REVERSE))
+    return fail(nullptr, TPS_EINVAL, "unknown bits in tps_params.flags");
+  if ((p.flags & TPS_FLAG_FORCE_FORWARD) && (p.flags & TPS_FLAG_FORCE_REVERSE))
+    return fail(nullptr, TPS_EINVAL, "FORCE_FORWARD and FORCE_REVERSE are exclusive");
   TpsPatTable pt;
   int rc = build_pattern_table(&p, &pt);
   if (rc) return rc;
@@ -356,6 +360,7 @@ int enqueue_scan(tps_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t *d_bases,
   a.trimfirst = p.trimfirst;
   a.maxlengthtelo = p.maxlengthtelo;
   a.want_rawcount = p.want_rawcount;
+  a.flags = p.flags;
   a.raw = s.d_raw;
   a.raw_capacity = p.want_rawcount ? p.rawcount_capacity : 0;
   a.cw = s.d_cw;
@@ -370,7 +375,7 @@ int enqueue_scan(tps_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t *d_bases,
     ctx->launches++;
   }
   if (timed) TPS_CUDA(ctx, cudaEventRecord(ev[2], st));
-  if (n_reads) {
+  if (n_reads && !(p.flags & TPS_FLAG_STEP1_ONLY)) {
     a.lin_words = ctx->k3_lin_words;
     a.tile_words = ctx->k3_tile_words;
     ctx->k3_fn<<<ctx->k3_grid, TPS_K3_THREADS, ctx->k3_smem, st>>>(a, ctx->pt);
@@ -454,6 +459,19 @@ int tps_wait(tps_ctx *ctx, uint64_t batch_id, tps_row *rows_out, uint32_t *n_pas
     }
   }
   s.busy = false;
+  return TPS_OK;
+}
+
+int tps_batch_info(tps_ctx *ctx, uint64_t batch_id, uint32_t *n_pass_out, uint64_t *rawcount_elems) {
+  if (!ctx) return TPS_EINVAL;
+  Slot *sl = nullptr;
+  for (uint32_t i = 0; i < ctx->p.n_slots; ++i)
+    if (ctx->slots[i].busy && ctx->slots[i].batch_id == batch_id) sl = &ctx->slots[i];
+  if (!sl) return fail(ctx, TPS_ESTATE, "batch %llu is not in flight", (unsigned long long)batch_id);
+  TPS_CUDA(ctx, cudaSetDevice(ctx->device));
+  TPS_CUDA(ctx, cudaEventSynchronize(sl->done));
+  if (n_pass_out) *n_pass_out = sl->h_counters[0];
+  if (rawcount_elems) memcpy(rawcount_elems, sl->h_counters + 2, sizeof(uint64_t));
   return TPS_OK;
 }
 

@@ -1,0 +1,688 @@
+/*
+ * tps_fastx.c -- streaming FASTQ / FASTA (.gz) reader that fills scan batches.
+ *
+ * Replaces, for the hot path, the reference's input side: check_file_type / unzip_file
+ * (Topsicle/allsteps.py:36-50, 127-149, Bio.SeqIO.parse records) and the re-parse that
+ * writes the `_trc_over_` subset (Topsicle/main.py:68-86).  The reference hands every read
+ * to Python as a SeqRecord; here records are only *indexed* (title / sequence / quality
+ * byte ranges inside the raw text) and their bases are gathered back to back into the
+ * caller's (pinned) batch buffer, ready for tps_submit.  Titles and qualities are touched
+ * again only for the few reads that pass the TRC cutoff.
+ *
+ * Record semantics follow Biopython as the reference sees it:
+ *   id          = title.split(None, 1)[0]  (first whitespace-delimited token, "" if none)
+ *   description = title line after '@' / '>' with trailing whitespace stripped
+ *   FASTQ       = 4-line records; sequence / quality lines right-stripped; lengths must agree
+ *   FASTA       = '>' title, sequence = lines right-stripped and joined, ' ' and '\r' removed
+ * Unlike the reference (which logs a parse error and silently stops, allsteps.py:147-149)
+ * malformed input is an error.
+ *
+ * Plain files are mmap-ed and indexed by several threads (a window is cut into segments,
+ * every segment finds its first record start on its own; the pieces must chain exactly or
+ * the window is re-indexed sequentially).  `.gz` files are inflated with zlib by the calling
+ * thread into chunk buffers that the batch then owns.
+ */
+#define _GNU_SOURCE
+#include <errno.h>
+#include <fcntl.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <zlib.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define TPS_FX_FASTQ 1
+#define TPS_FX_FASTA 2
+
+#define TPS_FX_OK 0
+#define TPS_FX_EIO (-1)
+#define TPS_FX_EFORMAT (-2)
+#define TPS_FX_ENOMEM (-3)
+#define TPS_FX_ECAPACITY (-4)
+#define TPS_FX_EINVAL (-5)
+
+typedef struct tps_fastx_rec { /* 48 bytes; offsets are relative to the batch's raw base */
+  uint64_t title_off;   /* first title byte (after '@' / '>') */
+  uint64_t seq_off;     /* first byte of the first sequence line */
+  uint64_t qual_off;    /* FASTQ: first byte of the quality line; FASTA: 0 */
+  uint32_t title_len;   /* right-stripped */
+  uint32_t id_off;      /* id = title[id_off : id_off + id_len] */
+  uint32_t id_len;
+  uint32_t seq_len;     /* bases after stripping */
+  uint32_t seq_raw_len; /* raw bytes spanned by the sequence lines (FASTA: incl. newlines) */
+  uint32_t flags;       /* bit 0: sequence needs the filtered copy (multi-line or inner blanks) */
+} tps_fastx_rec;
+
+typedef struct rec_vec {
+  tps_fastx_rec *v;
+  size_t n, cap;
+  uint64_t first, end; /* first record start / end of the last complete record (abs. in window) */
+  int status;          /* 0 ok, <0 error */
+  uint64_t err_at;
+} rec_vec;
+
+typedef struct tps_fastx {
+  int format;
+  int is_gz;
+  int fd;
+  gzFile gz;
+  const uint8_t *map;
+  uint64_t map_len, pos;
+  /* gz streaming */
+  uint8_t *carry;
+  uint64_t carry_len;
+  int gz_eof;
+  uint64_t window_bytes;
+  int threads;
+  uint64_t n_records; /* records delivered so far */
+  char err[256];
+} tps_fastx;
+
+static __thread char g_open_err[256];
+
+static int fx_fail(tps_fastx *fx, int code, const char *fmt, ...) {
+  char *dst = fx ? fx->err : g_open_err;
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(dst, 256, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+const char *tps_fastx_last_error(const tps_fastx *fx) { return fx ? fx->err : g_open_err; }
+
+static inline int is_ws(uint8_t c) { return c == ' ' || (c >= 9 && c <= 13); }
+
+/* length of [p, p+n) without trailing whitespace */
+static inline uint64_t rstrip_len(const uint8_t *p, uint64_t n) {
+  while (n && is_ws(p[n - 1])) --n;
+  return n;
+}
+
+static int vec_push(rec_vec *rv, const tps_fastx_rec *r) {
+  if (rv->n == rv->cap) {
+    size_t nc = rv->cap ? rv->cap * 2 : 1024;
+    tps_fastx_rec *nv = (tps_fastx_rec *)realloc(rv->v, nc * sizeof(*nv));
+    if (!nv) return -1;
+    rv->v = nv;
+    rv->cap = nc;
+  }
+  rv->v[rv->n++] = *r;
+  return 0;
+}
+
+static void set_title(tps_fastx_rec *r, const uint8_t *w, uint64_t t0, uint64_t tl) {
+  r->title_off = t0;
+  r->title_len = (uint32_t)rstrip_len(w + t0, tl);
+  uint32_t i = 0;
+  while (i < r->title_len && is_ws(w[t0 + i])) ++i;
+  uint32_t j = i;
+  while (j < r->title_len && !is_ws(w[t0 + j])) ++j;
+  r->id_off = i;
+  r->id_len = j - i;
+}
+
+/* end of the line starting at `at`: index of '\n' or `end` when none (sets *has_nl) */
+static inline uint64_t line_end(const uint8_t *w, uint64_t at, uint64_t end, int *has_nl) {
+  const uint8_t *q = (const uint8_t *)memchr(w + at, '\n', end - at);
+  *has_nl = q != NULL;
+  return q ? (uint64_t)(q - w) : end;
+}
+
+/* ---- FASTQ: parse records starting in [from, seg_end); a record may run up to win_end.
+ * `final` = the window ends at end of file (a last line without '\n' is complete). */
+static void index_fastq(const uint8_t *w, uint64_t from, uint64_t seg_end, uint64_t win_end, int final,
+                        rec_vec *rv) {
+  uint64_t p = from;
+  rv->first = from;
+  rv->end = from;
+  while (p < seg_end) {
+    if (w[p] == '\n' || w[p] == '\r') { /* blank line between records */
+      ++p;
+      rv->end = p;
+      continue;
+    }
+    if (w[p] != '@') {
+      rv->status = TPS_FX_EFORMAT;
+      rv->err_at = p;
+      return;
+    }
+    int nl;
+    uint64_t e1 = line_end(w, p, win_end, &nl);
+    if (!nl) break; /* title incomplete */
+    uint64_t s0 = e1 + 1;
+    if (s0 >= win_end) break;
+    uint64_t e2 = line_end(w, s0, win_end, &nl);
+    if (!nl) break;
+    uint64_t p0 = e2 + 1;
+    if (p0 >= win_end) break;
+    if (w[p0] != '+') { /* multi-line FASTQ is undefined in the reference's use; rejected */
+      rv->status = TPS_FX_EFORMAT;
+      rv->err_at = p0;
+      return;
+    }
+    uint64_t e3 = line_end(w, p0, win_end, &nl);
+    if (!nl) break;
+    uint64_t q0 = e3 + 1;
+    uint64_t e4 = q0 <= win_end ? line_end(w, q0, win_end, &nl) : win_end;
+    if (!nl && !final) break; /* quality line may continue in the next window */
+    tps_fastx_rec r;
+    memset(&r, 0, sizeof(r));
+    set_title(&r, w, p + 1, e1 - (p + 1));
+    r.seq_off = s0;
+    r.seq_len = (uint32_t)rstrip_len(w + s0, e2 - s0);
+    r.seq_raw_len = (uint32_t)(e2 - s0);
+    r.qual_off = q0;
+    if (rstrip_len(w + q0, e4 - q0) != r.seq_len) {
+      rv->status = TPS_FX_EFORMAT;
+      rv->err_at = q0;
+      return;
+    }
+    if (vec_push(rv, &r)) {
+      rv->status = TPS_FX_ENOMEM;
+      return;
+    }
+    p = nl ? e4 + 1 : e4;
+    rv->end = p;
+  }
+}
+
+/* first FASTQ record start at or after `a` (a > window start): a line that begins with '@'
+ * and whose second-next line begins with '+' (a quality line may begin with '@', but then
+ * the second-next line is a sequence line, which never begins with '+'). */
+static uint64_t find_fastq_start(const uint8_t *w, uint64_t a, uint64_t win_end) {
+  int nl;
+  uint64_t p = line_end(w, a - 1, win_end, &nl); /* a-1: `a` itself may be a line start */
+  if (!nl) return win_end;
+  ++p;
+  while (p < win_end) {
+    if (w[p] == '@') {
+      uint64_t e1 = line_end(w, p, win_end, &nl);
+      if (!nl) return win_end;
+      uint64_t e2 = e1 + 1 < win_end ? line_end(w, e1 + 1, win_end, &nl) : win_end;
+      if (e2 >= win_end || !nl) return win_end;
+      if (e2 + 1 < win_end && w[e2 + 1] == '+') return p;
+      if (e2 + 1 >= win_end) return win_end;
+    }
+    uint64_t e = line_end(w, p, win_end, &nl);
+    if (!nl) return win_end;
+    p = e + 1;
+  }
+  return win_end;
+}
+
+/* ---- FASTA */
+static void index_fasta(const uint8_t *w, uint64_t from, uint64_t seg_end, uint64_t win_end, int final,
+                        rec_vec *rv) {
+  uint64_t p = from;
+  rv->first = from;
+  rv->end = from;
+  while (p < seg_end) {
+    int nl;
+    if (w[p] != '>') { /* text before the first record / blank lines: skipped */
+      uint64_t e = line_end(w, p, win_end, &nl);
+      if (!nl && !final) return;
+      p = nl ? e + 1 : e;
+      rv->end = p;
+      continue;
+    }
+    uint64_t e1 = line_end(w, p, win_end, &nl);
+    if (!nl && !final) return;
+    tps_fastx_rec r;
+    memset(&r, 0, sizeof(r));
+    set_title(&r, w, p + 1, e1 - (p + 1));
+    uint64_t q = nl ? e1 + 1 : e1;
+    r.seq_off = q;
+    uint64_t bases = 0;
+    uint32_t lines = 0, special = 0;
+    int complete = 0;
+    while (1) {
+      if (q >= win_end) {
+        complete = final;
+        break;
+      }
+      if (w[q] == '>') {
+        complete = 1;
+        break;
+      }
+      uint64_t e = line_end(w, q, win_end, &nl);
+      if (!nl && !final) break;
+      uint64_t n = rstrip_len(w + q, e - q);
+      uint64_t blanks = 0;
+      for (uint64_t j = 0; j < n; ++j) blanks += (w[q + j] == ' ') | (w[q + j] == '\r');
+      bases += n - blanks;
+      special |= blanks != 0;
+      if (n) ++lines;
+      q = nl ? e + 1 : e;
+    }
+    if (!complete) return;
+    if (bases > 0xFFFFFFFFull || q - r.seq_off > 0xFFFFFFFFull) {
+      rv->status = TPS_FX_ECAPACITY;
+      rv->err_at = p;
+      return;
+    }
+    r.seq_len = (uint32_t)bases;
+    r.seq_raw_len = (uint32_t)(q - r.seq_off);
+    r.flags = (lines > 1 || special || r.seq_raw_len != r.seq_len + 1u) ? 1u : 0u;
+    if (vec_push(rv, &r)) {
+      rv->status = TPS_FX_ENOMEM;
+      return;
+    }
+    p = q;
+    rv->end = p;
+  }
+}
+
+static uint64_t find_fasta_start(const uint8_t *w, uint64_t a, uint64_t win_end) {
+  int nl;
+  uint64_t p = line_end(w, a - 1, win_end, &nl);
+  if (!nl) return win_end;
+  ++p;
+  while (p < win_end) {
+    if (w[p] == '>') return p;
+    uint64_t e = line_end(w, p, win_end, &nl);
+    if (!nl) return win_end;
+    p = e + 1;
+  }
+  return win_end;
+}
+
+/* copy the bases of record r to dst (r->seq_len bytes) */
+static void gather_seq(const uint8_t *w, const tps_fastx_rec *r, uint8_t *dst) {
+  if (!(r->flags & 1u)) {
+    memcpy(dst, w + r->seq_off, r->seq_len);
+    return;
+  }
+  uint64_t q = r->seq_off, end = r->seq_off + r->seq_raw_len, o = 0;
+  while (q < end) {
+    int nl;
+    uint64_t e = line_end(w, q, end, &nl);
+    uint64_t n = rstrip_len(w + q, e - q);
+    for (uint64_t j = 0; j < n; ++j) {
+      uint8_t c = w[q + j];
+      if (c != ' ' && c != '\r') dst[o++] = c;
+    }
+    q = nl ? e + 1 : e;
+  }
+}
+
+/* Index [0, win_end) of w with `threads` segments.  Returns the merged record list in *out
+ * (caller frees out->v); out->end = bytes consumed. */
+static int index_window(tps_fastx *fx, const uint8_t *w, uint64_t win_end, int final, rec_vec *out) {
+  memset(out, 0, sizeof(*out));
+  int T = fx->threads;
+  if (T < 1) T = 1;
+  if (win_end < (uint64_t)T * (1u << 20)) T = 1; /* small windows: not worth splitting */
+  void (*index_fn)(const uint8_t *, uint64_t, uint64_t, uint64_t, int, rec_vec *) =
+      fx->format == TPS_FX_FASTQ ? index_fastq : index_fasta;
+  if (T > 1) {
+    rec_vec *parts = (rec_vec *)calloc((size_t)T, sizeof(rec_vec));
+    uint64_t *starts = (uint64_t *)calloc((size_t)T + 1, sizeof(uint64_t));
+    if (!parts || !starts) {
+      free(parts);
+      free(starts);
+      return fx_fail(fx, TPS_FX_ENOMEM, "out of memory");
+    }
+#pragma omp parallel for num_threads(T) schedule(static, 1)
+    for (int i = 0; i < T; ++i) {
+      uint64_t a = win_end / (uint64_t)T * (uint64_t)i;
+      starts[i] = i == 0 ? 0
+                         : (fx->format == TPS_FX_FASTQ ? find_fastq_start(w, a, win_end)
+                                                       : find_fasta_start(w, a, win_end));
+    }
+    starts[T] = win_end;
+    for (int i = T - 1; i >= 0; --i) /* segments that found nothing inherit the next start */
+      if (starts[i] > starts[i + 1]) starts[i] = starts[i + 1];
+#pragma omp parallel for num_threads(T) schedule(static, 1)
+    for (int i = 0; i < T; ++i) {
+      if (starts[i] < starts[i + 1]) index_fn(w, starts[i], starts[i + 1], win_end, final, &parts[i]);
+      else parts[i].first = parts[i].end = starts[i];
+    }
+    /* the pieces must chain: piece i ends where piece i+1 begins (or piece i stopped early) */
+    int ok = 1;
+    size_t total = 0;
+    int last = -1;
+    for (int i = 0; i < T && ok; ++i) {
+      if (parts[i].status) ok = 0;
+      else if (starts[i] < starts[i + 1]) {
+        if (last >= 0 && parts[last].end != parts[i].first) ok = 0;
+        last = i;
+        total += parts[i].n;
+        if (parts[i].end < starts[i + 1]) { /* incomplete record: nothing after it counts */
+          for (int j = i + 1; j < T; ++j) parts[j].n = 0;
+          break;
+        }
+      }
+    }
+    if (ok) {
+      out->v = (tps_fastx_rec *)malloc((total ? total : 1) * sizeof(tps_fastx_rec));
+      if (!out->v) ok = 0;
+    }
+    if (ok) {
+      out->end = 0;
+      for (int i = 0; i < T; ++i) {
+        if (starts[i] >= starts[i + 1]) continue;
+        memcpy(out->v + out->n, parts[i].v, parts[i].n * sizeof(tps_fastx_rec));
+        out->n += parts[i].n;
+        if (parts[i].end > out->end) out->end = parts[i].end;
+        if (parts[i].end < starts[i + 1]) break;
+      }
+      out->cap = out->n;
+    }
+    for (int i = 0; i < T; ++i) free(parts[i].v);
+    free(parts);
+    free(starts);
+    if (ok) return TPS_FX_OK;
+    free(out->v);
+    memset(out, 0, sizeof(*out)); /* fall through to the sequential index (also reports errors) */
+  }
+  index_fn(w, 0, win_end, win_end, final, out);
+  if (out->status == TPS_FX_EFORMAT) {
+    free(out->v);
+    out->v = NULL;
+    return fx_fail(fx, TPS_FX_EFORMAT,
+                   "malformed %s record #%llu near byte %llu of the current window (4-line FASTQ / FASTA expected; "
+                   "sequence and quality lengths must agree)",
+                   fx->format == TPS_FX_FASTQ ? "FASTQ" : "FASTA",
+                   (unsigned long long)(fx->n_records + out->n + 1), (unsigned long long)out->err_at);
+  }
+  if (out->status) {
+    int st = out->status;
+    free(out->v);
+    out->v = NULL;
+    return fx_fail(fx, st, st == TPS_FX_ENOMEM ? "out of memory" : "record longer than 4 Gbases");
+  }
+  return TPS_FX_OK;
+}
+
+/* ------------------------------------------------------------------------------ public API */
+int tps_fastx_open(tps_fastx **out, const char *path, int threads) {
+  if (!out || !path) return fx_fail(NULL, TPS_FX_EINVAL, "null argument");
+  *out = NULL;
+  tps_fastx *fx = (tps_fastx *)calloc(1, sizeof(*fx));
+  if (!fx) return fx_fail(NULL, TPS_FX_ENOMEM, "out of memory");
+  fx->fd = -1;
+  fx->threads = threads > 0 ? threads : 1;
+  fx->window_bytes = 4ull << 30;
+  size_t pl = strlen(path);
+  fx->is_gz = pl >= 3 && strcmp(path + pl - 3, ".gz") == 0; /* by suffix, allsteps.py:37,141 */
+  uint8_t first = 0;
+  if (fx->is_gz) {
+    fx->gz = gzopen(path, "rb");
+    if (!fx->gz) {
+      int rc = fx_fail(NULL, TPS_FX_EIO, "cannot open %s: %s", path, strerror(errno));
+      free(fx);
+      return rc;
+    }
+    gzbuffer(fx->gz, 1u << 20);
+    fx->carry = (uint8_t *)malloc(1u << 16);
+    int n = fx->carry ? gzread(fx->gz, fx->carry, 1u << 16) : -1;
+    if (n < 0) {
+      int rc = fx_fail(NULL, TPS_FX_EIO, "cannot read %s (not a gzip stream?)", path);
+      gzclose(fx->gz);
+      free(fx->carry);
+      free(fx);
+      return rc;
+    }
+    fx->carry_len = (uint64_t)n;
+    if (n < (1 << 16)) fx->gz_eof = 1;
+    uint64_t i = 0; /* check_file_type: first line, stripped (allsteps.py:40) */
+    while (i < fx->carry_len && is_ws(fx->carry[i]) && fx->carry[i] != '\n') ++i;
+    first = i < fx->carry_len ? fx->carry[i] : 0;
+  } else {
+    fx->fd = open(path, O_RDONLY);
+    struct stat st;
+    if (fx->fd < 0 || fstat(fx->fd, &st) != 0) {
+      int rc = fx_fail(NULL, TPS_FX_EIO, "cannot open %s: %s", path, strerror(errno));
+      if (fx->fd >= 0) close(fx->fd);
+      free(fx);
+      return rc;
+    }
+    fx->map_len = (uint64_t)st.st_size;
+    if (fx->map_len) {
+      void *m = mmap(NULL, fx->map_len, PROT_READ, MAP_PRIVATE, fx->fd, 0);
+      if (m == MAP_FAILED) {
+        int rc = fx_fail(NULL, TPS_FX_EIO, "cannot mmap %s: %s", path, strerror(errno));
+        close(fx->fd);
+        free(fx);
+        return rc;
+      }
+      fx->map = (const uint8_t *)m;
+      madvise(m, fx->map_len, MADV_SEQUENTIAL);
+      uint64_t i = 0;
+      while (i < fx->map_len && is_ws(fx->map[i]) && fx->map[i] != '\n') ++i;
+      first = i < fx->map_len ? fx->map[i] : 0;
+    }
+  }
+  if (first == '@') fx->format = TPS_FX_FASTQ;
+  else if (first == '>') fx->format = TPS_FX_FASTA;
+  else {
+    int rc = fx_fail(NULL, TPS_FX_EFORMAT, "%s: format cannot be identified (first line starts with neither '@' nor '>')",
+                     path);
+    if (fx->gz) gzclose(fx->gz);
+    if (fx->map) munmap((void *)fx->map, fx->map_len);
+    if (fx->fd >= 0) close(fx->fd);
+    free(fx->carry);
+    free(fx);
+    return rc;
+  }
+  *out = fx;
+  return TPS_FX_OK;
+}
+
+void tps_fastx_close(tps_fastx *fx) {
+  if (!fx) return;
+  if (fx->gz) gzclose(fx->gz);
+  if (fx->map) munmap((void *)fx->map, fx->map_len);
+  if (fx->fd >= 0) close(fx->fd);
+  free(fx->carry);
+  free(fx);
+}
+
+int tps_fastx_format(const tps_fastx *fx) { return fx ? fx->format : 0; }
+void tps_fastx_set_window(tps_fastx *fx, uint64_t bytes) {
+  if (fx && bytes >= 4096) fx->window_bytes = bytes;
+}
+void tps_fastx_release(void *owner) { free(owner); }
+
+/* Next batch: at most reads_cap records and bases_cap bases, in file order.
+ *   bases_out[offsets_out[i] .. offsets_out[i+1]) = bases of record i; recs_out[i] indexes its text
+ *   relative to *raw_base, which stays valid until tps_fastx_release(*raw_owner) (gz input) or
+ *   tps_fastx_close (plain input, *raw_owner == NULL).
+ * *n_reads == 0 means end of file. */
+int tps_fastx_next(tps_fastx *fx, uint64_t bases_cap, uint32_t reads_cap, uint8_t *bases_out,
+                   uint64_t *offsets_out, tps_fastx_rec *recs_out, uint32_t *n_reads,
+                   const uint8_t **raw_base, void **raw_owner) {
+  if (!fx || !bases_out || !offsets_out || !recs_out || !n_reads || !raw_base || !raw_owner)
+    return fx_fail(fx, TPS_FX_EINVAL, "null argument");
+  *n_reads = 0;
+  *raw_base = NULL;
+  *raw_owner = NULL;
+  offsets_out[0] = 0;
+  if (reads_cap == 0 || bases_cap == 0) return fx_fail(fx, TPS_FX_EINVAL, "zero capacity");
+  /* raw bytes that can hold a full batch: FASTQ carries the quality line too */
+  uint64_t want = (fx->format == TPS_FX_FASTQ ? 2 : 1) * bases_cap + bases_cap / 32 + (uint64_t)reads_cap * 128 + 4096;
+  if (want > fx->window_bytes) want = fx->window_bytes;
+  const uint8_t *w = NULL;
+  uint8_t *chunk = NULL;
+  uint64_t win = 0;
+  int final = 0;
+  rec_vec rv;
+  memset(&rv, 0, sizeof(rv));
+  for (;;) {
+    if (!fx->is_gz) {
+      if (fx->pos >= fx->map_len) return TPS_FX_OK;
+      w = fx->map + fx->pos;
+      win = fx->map_len - fx->pos;
+      if (win > want) win = want;
+      final = fx->pos + win == fx->map_len;
+    } else {
+      if (fx->carry_len == 0 && fx->gz_eof) return TPS_FX_OK;
+      uint64_t cap = fx->carry_len > want ? fx->carry_len : want;
+      if (!chunk) {
+        chunk = (uint8_t *)malloc(cap + 1);
+        if (!chunk) return fx_fail(fx, TPS_FX_ENOMEM, "out of memory for a %llu-byte chunk", (unsigned long long)cap);
+        memcpy(chunk, fx->carry, fx->carry_len);
+        win = fx->carry_len;
+      } else {
+        uint8_t *nc = (uint8_t *)realloc(chunk, cap + 1);
+        if (!nc) {
+          free(chunk);
+          return fx_fail(fx, TPS_FX_ENOMEM, "out of memory for a %llu-byte chunk", (unsigned long long)cap);
+        }
+        chunk = nc;
+      }
+      while (win < cap && !fx->gz_eof) {
+        uint64_t ask = cap - win;
+        if (ask > (1u << 30)) ask = 1u << 30;
+        int n = gzread(fx->gz, chunk + win, (unsigned)ask);
+        if (n < 0) {
+          free(chunk);
+          return fx_fail(fx, TPS_FX_EIO, "gzip read error");
+        }
+        if (n == 0) fx->gz_eof = 1;
+        win += (uint64_t)n;
+      }
+      w = chunk;
+      final = fx->gz_eof;
+    }
+    int rc = index_window(fx, w, win, final, &rv);
+    if (rc) {
+      free(chunk);
+      return rc;
+    }
+    if (rv.n > 0 || final) break;
+    /* not one complete record in the window: widen it */
+    free(rv.v);
+    memset(&rv, 0, sizeof(rv));
+    if (want >= (1ull << 40)) {
+      free(chunk);
+      return fx_fail(fx, TPS_FX_ECAPACITY, "record larger than 1 TiB");
+    }
+    want *= 2;
+  }
+  /* longest prefix within the caps */
+  uint32_t n = 0;
+  uint64_t nb = 0;
+  while (n < rv.n && n < reads_cap && nb + rv.v[n].seq_len <= bases_cap) {
+    nb += rv.v[n].seq_len;
+    offsets_out[n + 1] = nb;
+    ++n;
+  }
+  if (n == 0 && rv.n > 0) {
+    uint32_t L = rv.v[0].seq_len;
+    free(rv.v);
+    free(chunk);
+    return fx_fail(fx, TPS_FX_ECAPACITY, "read #%llu has %u bases, more than the batch capacity of %llu",
+                   (unsigned long long)(fx->n_records + 1), L, (unsigned long long)bases_cap);
+  }
+  uint64_t consumed;
+  if (n == rv.n) consumed = rv.end;
+  else consumed = rv.v[n].title_off - 1; /* start of the first record left for the next call */
+  if (n) memcpy(recs_out, rv.v, (size_t)n * sizeof(tps_fastx_rec));
+  int T = fx->threads;
+#pragma omp parallel for num_threads(T) schedule(dynamic, 16) if (nb > (8u << 20))
+  for (int64_t i = 0; i < (int64_t)n; ++i) gather_seq(w, &rv.v[i], bases_out + offsets_out[i]);
+  free(rv.v);
+  if (!fx->is_gz) {
+    *raw_base = w;
+    fx->pos += consumed;
+    if (n == 0) fx->pos = fx->map_len; /* only blank / skipped text was left */
+  } else {
+    uint64_t left = win - consumed;
+    if (n == 0) left = 0;
+    uint8_t *nc = (uint8_t *)realloc(fx->carry, left ? left : 1);
+    if (!nc) {
+      free(chunk);
+      return fx_fail(fx, TPS_FX_ENOMEM, "out of memory");
+    }
+    fx->carry = nc;
+    memcpy(fx->carry, chunk + consumed, left);
+    fx->carry_len = left;
+    if (n) {
+      *raw_base = chunk;
+      *raw_owner = chunk;
+    } else {
+      free(chunk);
+    }
+  }
+  fx->n_records += n;
+  *n_reads = n;
+  return TPS_FX_OK;
+}
+
+/* ---------------------------------------------------------------- rawcount CSV formatter
+ * Text of `DataFrame(rows, columns=['tail','position','pattern','count']).to_csv()` as
+ * rawCountPattern + main.py:150 produce it (allsteps.py:401-416, 464): header
+ * ",tail,position,pattern,count", then one line "{row},{tail},{w*slide},{literal},{count}" per
+ * window (major) and literal (minor), '\n' line ends.  counts = uint8[n_windows][n_patterns].
+ * Returns the number of bytes written, or -(bytes needed) if cap is too small. */
+static inline char *put_u64(char *p, uint64_t v) {
+  char tmp[24];
+  int n = 0;
+  do {
+    tmp[n++] = (char)('0' + v % 10);
+    v /= 10;
+  } while (v);
+  while (n) *p++ = tmp[--n];
+  return p;
+}
+
+int64_t tps_format_rawcount(const uint8_t *counts, uint32_t n_windows, uint32_t n_patterns, uint32_t slide,
+                            const char *tail, const char *const *patterns, char *out, uint64_t cap) {
+  static const char header[] = ",tail,position,pattern,count\n";
+  size_t tl = strlen(tail), maxpat = 0;
+  for (uint32_t p = 0; p < n_patterns; ++p) {
+    size_t l = strlen(patterns[p]);
+    if (l > maxpat) maxpat = l;
+  }
+  uint64_t need = sizeof(header) - 1 + (uint64_t)n_windows * n_patterns * (20 + tl + 10 + maxpat + 3 + 5);
+  if (need > cap) return -(int64_t)need;
+  char *p = out;
+  memcpy(p, header, sizeof(header) - 1);
+  p += sizeof(header) - 1;
+  uint64_t row = 0;
+  for (uint32_t w = 0; w < n_windows; ++w) {
+    char pos[24];
+    char *pe = put_u64(pos, (uint64_t)w * slide);
+    size_t pl = (size_t)(pe - pos);
+    for (uint32_t q = 0; q < n_patterns; ++q, ++row) {
+      p = put_u64(p, row);
+      *p++ = ',';
+      memcpy(p, tail, tl);
+      p += tl;
+      *p++ = ',';
+      memcpy(p, pos, pl);
+      p += pl;
+      *p++ = ',';
+      size_t l = strlen(patterns[q]);
+      memcpy(p, patterns[q], l);
+      p += l;
+      *p++ = ',';
+      p = put_u64(p, counts[(uint64_t)w * n_patterns + q]);
+      *p++ = '\n';
+    }
+  }
+  return (int64_t)(p - out);
+}
+
+/* Indices of the records of a batch whose id equals `id` (`seq.id != read`, allsteps.py:258, 381).
+ * Returns the number of matches (at most `cap` indices are stored). */
+uint32_t tps_fastx_find_id(const uint8_t *raw_base, const tps_fastx_rec *recs, uint32_t n_reads, const char *id,
+                           uint32_t id_len, uint32_t *out_idx, uint32_t cap) {
+  uint32_t found = 0;
+  for (uint32_t i = 0; i < n_reads; ++i) {
+    if (recs[i].id_len != id_len) continue;
+    if (memcmp(raw_base + recs[i].title_off + recs[i].id_off, id, id_len) != 0) continue;
+    if (found < cap) out_idx[found] = i;
+    ++found;
+  }
+  return found;
+}

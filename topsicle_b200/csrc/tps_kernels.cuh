@@ -54,7 +54,7 @@ struct TpsScanArgs {
   uint32_t *pass_list;
   uint32_t *counters;
   uint32_t min_seq_length, no_bp, count_threshold;
-  uint32_t W, slide, trimfirst, maxlengthtelo, want_rawcount;
+  uint32_t W, slide, trimfirst, maxlengthtelo, want_rawcount, flags;
   uint8_t *raw;
   uint64_t raw_capacity;
   uint32_t *cw;        /* c_w of passing read i at cw + i * cw_stride */
@@ -373,7 +373,9 @@ tps_trc_kernel(const TpsScanArgs a, const TpsPatTable pt) {
     uint32_t ms, ps, me, pe;
     tps_trc_end<K>(a, pt, pm, off, n, false, lin, mrows, cnts, lane, ms, ps);         /* seq[:no_bp] */
     tps_trc_end<K>(a, pt, pm, off + L - n, n, true, lin, mrows, cnts, lane, me, pe);  /* seq[-no_bp:][::-1] */
-    const bool fwd = ms > me; /* tie -> reverse, allsteps.py:193-198 */
+    bool fwd = ms > me; /* tie -> reverse, allsteps.py:193-198 */
+    if (a.flags & TPS_FLAG_FORCE_FORWARD) fwd = true; /* caller-chosen tail, allsteps.py:294-297 */
+    if (a.flags & TPS_FLAG_FORCE_REVERSE) fwd = false;
     const uint32_t cnt = fwd ? ms : me;
     row.tail = fwd ? TPS_TAIL_FORWARD : TPS_TAIL_REVERSE;
     row.best_pattern = (uint8_t)(fwd ? ps : pe);
@@ -381,7 +383,7 @@ tps_trc_kernel(const TpsScanArgs a, const TpsPatTable pt) {
     row.head_max = (uint16_t)ms;
     row.tail_max = (uint16_t)me;
     row.status = cnt >= a.count_threshold ? TPS_ST_PASS : TPS_ST_BELOW;
-    if (row.status == TPS_ST_PASS && lane == 0) {
+    if (row.status == TPS_ST_PASS && lane == 0 && !(a.flags & TPS_FLAG_STEP1_ONLY)) {
       const uint32_t M = L < a.maxlengthtelo ? L : a.maxlengthtelo;
       const uint32_t nreg = M > a.trimfirst ? M - a.trimfirst : 0u;
       const uint32_t nW = nreg >= a.W ? (nreg - a.W) / a.slide + 1u : 0u;

@@ -19,6 +19,7 @@ TPS_MAX_PATTERNS = 64
 TPS_MAX_PATTERN_LEN = 32
 
 ST_FILTERED, ST_BELOW, ST_PASS, ST_BADSEG = 0, 1, 2, 3
+FLAG_STEP1_ONLY, FLAG_FORCE_FORWARD, FLAG_FORCE_REVERSE = 1, 2, 4
 TAIL_NAMES = ("forward", "reverse")
 NO_RAWCOUNT = 0xFFFFFFFFFFFFFFFF
 
@@ -46,7 +47,7 @@ class TpsParams(C.Structure):
         ("n_slots", C.c_uint32),
         ("max_batch_reads", C.c_uint32),
         ("max_pass_reads", C.c_uint32),
-        ("reserved", C.c_uint32),
+        ("flags", C.c_uint32),
         ("max_batch_bases", C.c_uint64),
         ("rawcount_capacity", C.c_uint64),
     ]
@@ -89,6 +90,8 @@ def load_library() -> C.CDLL:
     lib.tps_submit.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint64]
     lib.tps_wait.restype = C.c_int
     lib.tps_wait.argtypes = [vp, C.c_uint64, vp, u32p, vp, C.c_uint64, u64p]
+    lib.tps_batch_info.restype = C.c_int
+    lib.tps_batch_info.argtypes = [vp, C.c_uint64, u32p, u64p]
     lib.tps_scan_device.restype = C.c_int
     lib.tps_scan_device.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint64, vp]
     lib.tps_sync.restype = C.c_int
@@ -163,7 +166,8 @@ class ScanContext:
                  trimfirst: int = 100, maxlengthtelo: int = 20000, want_rawcount: bool = False,
                  device: int = 0, n_slots: int = 2, max_batch_reads: int = 1 << 16,
                  max_batch_bases: int = 1 << 28, max_pass_reads: int = 0, rawcount_capacity: int = 0,
-                 count_threshold_override: int | None = None):
+                 count_threshold_override: int | None = None, step1_only: bool = False,
+                 force_tail: str | None = None):
         self.lib = load_library()
         self.patterns = [p.upper() for p in patterns]
         self.len_telopattern = len_telopattern if len_telopattern is not None else len(self.patterns[0])
@@ -185,6 +189,8 @@ class ScanContext:
                              else count_threshold(cutoff, self.len_telopattern, no_bp))
         p.window_size, p.slide, p.trimfirst, p.maxlengthtelo = window_size, slide, trimfirst, maxlengthtelo
         p.want_rawcount = 1 if want_rawcount else 0
+        p.flags = (FLAG_STEP1_ONLY if step1_only else 0) | {None: 0, "forward": FLAG_FORCE_FORWARD,
+                                                             "reverse": FLAG_FORCE_REVERSE}[force_tail]
         p.n_slots = n_slots
         p.max_batch_reads = max_batch_reads
         p.max_batch_bases = max_batch_bases
@@ -244,15 +250,18 @@ class ScanContext:
         n_pass = C.c_uint32(0)
         elems = C.c_uint64(0)
         raw = None
-        if self.want_rawcount:
-            raw = np.empty(int(self.params.rawcount_capacity), dtype=np.uint8)
-            self._check(self.lib.tps_wait(self._h, bid, rows.ctypes.data, C.byref(n_pass), raw.ctypes.data,
-                                          raw.size, C.byref(elems)))
-            raw = raw[:elems.value]
-        else:
-            self._check(self.lib.tps_wait(self._h, bid, rows.ctypes.data, C.byref(n_pass), None, 0,
-                                          C.byref(elems)))
-        del self._inflight[bid]
+        try:
+            if self.want_rawcount:
+                self._check(self.lib.tps_batch_info(self._h, bid, C.byref(n_pass), C.byref(elems)))
+                raw = np.empty(min(int(elems.value), int(self.params.rawcount_capacity)), dtype=np.uint8)
+                self._check(self.lib.tps_wait(self._h, bid, rows.ctypes.data, C.byref(n_pass), raw.ctypes.data,
+                                              raw.size, C.byref(elems)))
+                raw = raw[:elems.value]
+            else:
+                self._check(self.lib.tps_wait(self._h, bid, rows.ctypes.data, C.byref(n_pass), None, 0,
+                                              C.byref(elems)))
+        finally:
+            del self._inflight[bid]
         return rows, raw
 
     def scan(self, bases: np.ndarray, offsets: np.ndarray):

@@ -1,0 +1,212 @@
+"""Streaming FASTQ / FASTA (.gz) input -- ctypes wrapper over csrc/tps_fastx.c.
+
+Takes the place of `check_file_type` / `unzip_file` + `Bio.SeqIO.parse`
+(Topsicle/allsteps.py:36-50, 127-149) on the scan path: records are indexed in C (several
+threads on plain files, zlib on `.gz`) and their bases land back to back in a pinned batch
+buffer that `tps_submit` uploads as is.  Python never materialises a per-read object;
+ids / titles / qualities are sliced out of the raw text only for the reads that need them
+(the TRC-pass reads written to the `_trc_over_` subset, Topsicle/main.py:68-86).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+HOST_LIB_PATH = os.path.join(_HERE, "libtps_host.so")
+
+FASTQ, FASTA = 1, 2
+FORMAT_NAMES = {FASTQ: "fastq", FASTA: "fasta"}
+
+REC_DTYPE = np.dtype([
+    ("title_off", "<u8"), ("seq_off", "<u8"), ("qual_off", "<u8"), ("title_len", "<u4"), ("id_off", "<u4"),
+    ("id_len", "<u4"), ("seq_len", "<u4"), ("seq_raw_len", "<u4"), ("flags", "<u4"),
+])
+assert REC_DTYPE.itemsize == 48
+
+
+class FastxError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"fastx error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def host_library() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(HOST_LIB_PATH):
+            raise RuntimeError(f"{HOST_LIB_PATH} not found: run __graft_entry__.build()")
+        lib = C.CDLL(HOST_LIB_PATH)
+        vp = C.c_void_p
+        lib.tps_fastx_open.restype = C.c_int
+        lib.tps_fastx_open.argtypes = [C.POINTER(vp), C.c_char_p, C.c_int]
+        lib.tps_fastx_close.restype = None
+        lib.tps_fastx_close.argtypes = [vp]
+        lib.tps_fastx_format.restype = C.c_int
+        lib.tps_fastx_format.argtypes = [vp]
+        lib.tps_fastx_set_window.restype = None
+        lib.tps_fastx_set_window.argtypes = [vp, C.c_uint64]
+        lib.tps_fastx_release.restype = None
+        lib.tps_fastx_release.argtypes = [vp]
+        lib.tps_fastx_last_error.restype = C.c_char_p
+        lib.tps_fastx_last_error.argtypes = [vp]
+        lib.tps_fastx_next.restype = C.c_int
+        lib.tps_fastx_next.argtypes = [vp, C.c_uint64, C.c_uint32, vp, vp, vp, C.POINTER(C.c_uint32),
+                                       C.POINTER(vp), C.POINTER(vp)]
+        lib.tps_fastx_find_id.restype = C.c_uint32
+        lib.tps_fastx_find_id.argtypes = [vp, vp, C.c_uint32, C.c_char_p, C.c_uint32, vp, C.c_uint32]
+        lib.tps_format_rawcount.restype = C.c_int64
+        lib.tps_format_rawcount.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_char_p,
+                                            C.POINTER(C.c_char_p), vp, C.c_uint64]
+        _lib = lib
+    return _lib
+
+
+class Batch:
+    """One batch of reads: `bases[offsets[i]:offsets[i+1]]` is read i; `recs[i]` indexes its raw
+    text.  `first_read` = index of read 0 within its file.  Keep the batch (and its FastxFile)
+    alive while slicing raw text; call `release()` when done."""
+
+    def __init__(self, lib, n_reads, bases, offsets, recs, raw_base, raw_owner, first_read, fmt):
+        self._lib = lib
+        self.n_reads = n_reads
+        self.bases = bases
+        self.offsets = offsets
+        self.recs = recs
+        self._raw = raw_base
+        self._owner = raw_owner
+        self.first_read = first_read
+        self.format = fmt
+
+    @property
+    def n_bases(self) -> int:
+        return int(self.offsets[self.n_reads])
+
+    def _text(self, off, n) -> bytes:
+        return C.string_at(self._raw + int(off), int(n))
+
+    def title(self, i) -> str:
+        r = self.recs[i]
+        return self._text(r["title_off"], r["title_len"]).decode("utf-8", "replace")
+
+    def read_id(self, i) -> str:
+        r = self.recs[i]
+        return self._text(int(r["title_off"]) + int(r["id_off"]), r["id_len"]).decode("utf-8", "replace")
+
+    def sequence(self, i) -> bytes:
+        return self.bases[int(self.offsets[i]):int(self.offsets[i + 1])].tobytes()
+
+    def quality(self, i) -> bytes:
+        r = self.recs[i]
+        return self._text(r["qual_off"], r["seq_len"])
+
+    def record_text(self, i) -> bytes:
+        """The record as `SeqIO.write(record, handle, fmt)` emits it (main.py:86): FASTQ
+        `@title\\nseq\\n+\\nqual\\n`; FASTA `>title\\n` + sequence wrapped at 60 columns."""
+        title = self._text(self.recs[i]["title_off"], self.recs[i]["title_len"])
+        seq = self.sequence(i)
+        if self.format == FASTQ:
+            return b"@" + title + b"\n" + seq + b"\n+\n" + self.quality(i) + b"\n"
+        lines = [seq[j:j + 60] for j in range(0, len(seq), 60)]
+        return b">" + title + b"\n" + b"".join(ln + b"\n" for ln in lines)
+
+    def find_id(self, read_id: str) -> list:
+        """Indices of the records whose id equals `read_id` (the reference's `seq.id != read` test)."""
+        key = read_id.encode("utf-8")
+        recs = np.ascontiguousarray(self.recs)
+        out = np.empty(max(1, self.n_reads), dtype=np.uint32)
+        n = self._lib.tps_fastx_find_id(self._raw, recs.ctypes.data, self.n_reads, key, len(key), out.ctypes.data,
+                                        out.size)
+        return [int(i) for i in out[:n]]
+
+    def release(self):
+        if self._owner:
+            self._lib.tps_fastx_release(self._owner)
+            self._owner = None
+        self._raw = None
+
+
+class FastxFile:
+    """An open FASTQ / FASTA file (gzip if the name ends in `.gz`, as the reference decides)."""
+
+    def __init__(self, path: str, threads: int = 0):
+        self._lib = host_library()
+        self.path = path
+        self._h = C.c_void_p()
+        threads = threads or len(os.sched_getaffinity(0))
+        rc = self._lib.tps_fastx_open(C.byref(self._h), os.fsencode(path), threads)
+        if rc != 0:
+            raise FastxError(rc, self._lib.tps_fastx_last_error(None).decode())
+        self.format = self._lib.tps_fastx_format(self._h)
+        self.format_name = FORMAT_NAMES[self.format]
+        self.reads_delivered = 0
+
+    def set_window(self, nbytes: int):
+        self._lib.tps_fastx_set_window(self._h, nbytes)
+
+    def next_batch(self, bases: np.ndarray, offsets: np.ndarray, max_reads: int | None = None,
+                   max_bases: int | None = None) -> Batch | None:
+        """Fill `bases` (uint8) / `offsets` (uint64, >= max_reads + 1) with the next reads of the
+        file; returns None at end of file."""
+        assert bases.dtype == np.uint8 and offsets.dtype == np.uint64
+        reads_cap = min(len(offsets) - 1, max_reads if max_reads is not None else 1 << 31)
+        bases_cap = min(bases.size, max_bases if max_bases is not None else 1 << 62)
+        recs = np.empty(reads_cap, dtype=REC_DTYPE)
+        n = C.c_uint32(0)
+        raw, owner = C.c_void_p(), C.c_void_p()
+        rc = self._lib.tps_fastx_next(self._h, bases_cap, reads_cap, bases.ctypes.data, offsets.ctypes.data,
+                                      recs.ctypes.data, C.byref(n), C.byref(raw), C.byref(owner))
+        if rc != 0:
+            raise FastxError(rc, self._lib.tps_fastx_last_error(self._h).decode())
+        if n.value == 0:
+            return None
+        b = Batch(self._lib, n.value, bases, offsets, recs[:n.value], raw.value, owner.value,
+                  self.reads_delivered, self.format)
+        self.reads_delivered += n.value
+        return b
+
+    def close(self):
+        if self._h and self._h.value:
+            self._lib.tps_fastx_close(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def sniff_format(path: str) -> str | int:
+    """`check_file_type` (allsteps.py:36-50): 'fastq' / 'fasta', or 0 if it cannot be told."""
+    try:
+        with FastxFile(path, threads=1) as fx:
+            return fx.format_name
+    except (FastxError, OSError):
+        return 0
+
+
+def format_rawcount_csv(counts: np.ndarray, slide: int, tail: str, patterns) -> bytes:
+    """`rawCountPattern(...).to_csv()` text (allsteps.py:401-416,464; main.py:150) from a
+    uint8 [n_windows][n_patterns] count table."""
+    lib = host_library()
+    counts = np.ascontiguousarray(counts, dtype=np.uint8)
+    nw, npat = (counts.shape if counts.ndim == 2 else (0, len(patterns)))
+    pats = (C.c_char_p * len(patterns))(*[p.encode() for p in patterns])
+    cap = 64 + nw * npat * (48 + len(tail) + max((len(p) for p in patterns), default=0))
+    out = C.create_string_buffer(cap)
+    n = lib.tps_format_rawcount(counts.ctypes.data, nw, npat, slide, tail.encode(), pats, out, cap)
+    if n < 0:
+        raise FastxError(-4, f"rawcount buffer too small ({cap} < {-n})")
+    return out.raw[:n]

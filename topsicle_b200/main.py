@@ -1,0 +1,360 @@
+"""`topsicle` command line -- drop-in for Topsicle/main.py on a B200 box.
+
+Same flags, defaults and types as the reference parser (main.py:319-334), same outputs in
+`--outputDir`: `telolengths_all.csv` (header + CRLF rows `file,phrase,trc,readID,telo_length`,
+main.py:198-200,136-138), `{stem}_trc_over_{cutoff}.fastq|fasta` (main.py:64-87),
+`topsicle_run.log` (main.py:31-45), optional `rawcount_{phrase}_{i}.csv` (main.py:146-150),
+`plot_{phrase}_{i}.png`, `quadfit_{phrase}mer_{pattern}.png`, and the same log sentences
+including the final "All telomere found, have a nice day." (main.py:309).
+
+What differs is how the work is done: the reference forks one process per input FILE and
+re-parses the file once per telophrase and once per TRC-pass read; here every file is parsed
+once, all telophrases are scanned from that one pass, and the batches of reads are dealt to
+all visible GPUs (`--devices`, default: every CUDA device).  `--threads` sets the host
+parser threads.  Rows of one file are always in file order (the reference interleaves files
+nondeterministically).
+"""
+from __future__ import annotations
+
+import argparse
+import csv
+import datetime
+import os
+import sys
+import time
+from collections import defaultdict
+
+import numpy as np
+
+from . import engine, fastx, pipeline
+from .allsteps import _plot_boundary, fit_quadratic_and_find_vertex
+from .patterns import patterns_to_search, validate_literals
+
+version_number = "1.0.0"
+Topsicle_output_prefix = "Topsicle"
+
+
+def get_log_path(args):
+    log_dir = getattr(args, "outputDir", ".")
+    os.makedirs(log_dir, exist_ok=True)
+    return os.path.join(log_dir, "topsicle_run.log")
+
+
+def tprint(*args, **kwargs):
+    """Timestamped line to stdout and to topsicle_run.log (main.py:37-45)."""
+    msg = " ".join(str(a) for a in args)
+    now = datetime.datetime.now().strftime("%Y-%m-%d %H:%M:%S")
+    line = f"[{now}] {msg}"
+    print(line)
+    if hasattr(tprint, "logfile"):
+        with open(tprint.logfile, "a") as f:
+            f.write(line + "\n")
+
+
+def visible_devices():
+    """CUDA devices to use: TOPSICLE_DEVICES, else all devices the runtime reports."""
+    env = os.environ.get("TOPSICLE_DEVICES")
+    if env:
+        return [int(x) for x in env.split(",") if x.strip() != ""]
+    try:
+        import torch
+        n = torch.cuda.device_count()
+    except Exception:  # noqa: BLE001
+        n = 0
+    return list(range(n)) if n > 0 else [0]
+
+
+def subset_path(args, seq_loc, min_cutoff):
+    """Name and format of the TRC subset file (main.py:53-80): `.fastq` for .fastq/.fq(.gz)
+    inputs, `.fasta` otherwise; an existing `.fasta`-named file is reused."""
+    file_name = os.path.splitext(os.path.basename(seq_loc))[0]
+    fasta_temp = os.path.join(args.outputDir, f"{file_name}_trc_over_{min_cutoff}.fasta")
+    if os.path.exists(fasta_temp):
+        return file_name, fasta_temp, True
+    name = seq_loc[:-3] if seq_loc.endswith(".gz") else seq_loc
+    if name.endswith(".fastq") or name.endswith(".fq"):
+        fasta_temp = os.path.join(args.outputDir, f"{file_name}_trc_over_{min_cutoff}.fastq")
+    return file_name, fasta_temp, False
+
+
+class _FileWriter:
+    """Ordered sink of one input file: subset records, CSV rows, rawcount tables, plots."""
+
+    def __init__(self, args, seq_loc, cfgs, phrases, min_cutoff, sliding_val, csv_path):
+        self.args = args
+        self.cfgs = cfgs
+        self.phrases = phrases
+        self.sliding_val = sliding_val
+        self.csv_path = csv_path
+        self.file_name, self.subset, self.subset_exists = subset_path(args, seq_loc, min_cutoff)
+        name = seq_loc[:-3] if seq_loc.endswith(".gz") else seq_loc
+        # the subset holds the reads passing ONE phrase: with FASTQ input the reference rewrites it for
+        # every phrase (last one stays), with FASTA input the first phrase's file is reused (main.py:64-66)
+        is_fastq_name = name.endswith(".fastq") or name.endswith(".fq")
+        self.records_cfg = None if self.subset_exists else (len(cfgs) - 1 if is_fastq_name else 0)
+        self.subset_handle = None if self.subset_exists else open(self.subset, "wb")
+        self.rows = [[] for _ in cfgs]          # per phrase: CSV rows (held: the CSV is phrase-major)
+        self.results = [[] for _ in cfgs]       # per phrase: (telolen, trc)
+        self.image_num = [1 for _ in cfgs]
+        self.n_badseg = 0
+        self.stats_scanned = 0
+
+    def __call__(self, res: pipeline.BatchResult):
+        args = self.args
+        self.stats_scanned += res.n_scanned
+        new_first = []   # rows of the first phrase go to the CSV as they are found (main.py:136: "real time")
+        for k, passes in enumerate(res.passes):
+            cfg, phrase = self.cfgs[k], self.phrases[k]
+            for p in passes:
+                if self.records_cfg == k and p.record is not None:
+                    self.subset_handle.write(p.record)
+                if args.read_check and p.read_id != args.read_check:
+                    continue
+                if p.status != engine.ST_PASS:
+                    # the reference dies here: ruptures.BadSegmentationParameters (1..6 windows) or
+                    # IndexError on an empty boundary list (0 windows), main.py:133
+                    self.n_badseg += 1
+                    tprint(f"WARNING: read {p.read_id} passes TRC but has only {p.n_windows} windows "
+                           f"(needs >= 7 for a change point); skipped")
+                    continue
+                m = min(args.maxlengthtelo, p.length)
+                telolen = p.telo_length if (p.telo_length <= m and p.telo_length != 0) else 0
+                row = [self.file_name, phrase, f"{p.trc:.3f}", p.read_id, telolen]
+                (new_first if k == 0 else self.rows[k]).append(row)
+                self.results[k].append((float(telolen), float(p.trc)))
+                i = self.image_num[k]
+                if args.plot and p.counts is not None:
+                    _plot_boundary(p.read_id, p, len(cfg.patterns), args.trimfirst, self.sliding_val, m, telolen,
+                                   args.rangecp)
+                    try:
+                        import matplotlib.pyplot as plt
+                        plt.savefig(f"{args.outputDir}/plot_{phrase}_{i}.png", format="png", dpi=300)
+                        plt.close()
+                    except ImportError:
+                        pass
+                if args.rawcountpattern and p.counts is not None:
+                    text = fastx.format_rawcount_csv(p.counts, self.sliding_val, p.tail, cfg.patterns)
+                    with open(f"{args.outputDir}/rawcount_{phrase}_{i}.csv", "wb") as fh:
+                        fh.write(text)
+                self.image_num[k] += 1
+        if new_first:
+            with open(self.csv_path, mode="a", newline="") as file:
+                csv.writer(file).writerows(new_first)
+
+    def close(self):
+        if self.subset_handle is not None:
+            self.subset_handle.close()
+
+
+def process_file(args, seq_loc, telo_phrases, patterns, sliding_val, devices, csv_rows_out):
+    """One input file, every telophrase, one pass (reference: main.py:52-154, once per phrase).
+    Returns per phrase the list of (telomere length, TRC)."""
+    tprint("subsetting raw dataset based on TRC cutoff")
+    min_cutoff = min(args.cutoff) if isinstance(args.cutoff, (list, tuple)) else args.cutoff
+    want_counts = bool(args.rawcountpattern or args.plot)
+    cfgs = [pipeline.ScanConfig(patterns=pats, len_telopattern=len(args.pattern), phrase=k, cutoff=min_cutoff,
+                                min_seq_length=args.minSeqLength, no_bp=1000, window_size=args.windowSize,
+                                slide=sliding_val, trimfirst=args.trimfirst, maxlengthtelo=args.maxlengthtelo,
+                                want_rawcount=want_counts)
+            for k, pats in zip(telo_phrases, patterns)]
+    w = _FileWriter(args, seq_loc, cfgs, telo_phrases, min_cutoff, sliding_val,
+                    f"{args.outputDir}/telolengths_all.csv")
+    if w.subset_exists:
+        tprint(f"Temporary fasta file already exists: {w.subset}. Using existing file.")
+    if args.read_check:
+        tprint("checking specific read:", args.read_check)
+    try:
+        stats = pipeline.scan_file(seq_loc, cfgs, w, devices=devices, threads=args.threads or 0,
+                                   records_cfg=w.records_cfg,
+                                   max_batch_bases=int(os.environ.get("TOPSICLE_BATCH_BASES", 1 << 28)),
+                                   max_batch_reads=int(os.environ.get("TOPSICLE_BATCH_READS", 1 << 17)))
+    finally:
+        w.close()
+    if not w.subset_exists:
+        tprint(f"Temporary fasta file with TRC more than {min_cutoff}:", w.subset)
+    for k in range(1, len(cfgs)):
+        csv_rows_out[k].extend(w.rows[k])
+    process_file.last_stats = stats
+    return w.results
+
+
+def analysis_run(args):
+    print("---- Topsicle run parameters ---")
+    for k, v in vars(args).items():
+        tprint(f"{k}: {v}")
+    print("---------------------")
+
+    tprint("Starting Topsicle analysis")
+    os.makedirs(args.outputDir, exist_ok=True)
+
+    if args.threads is not None:
+        num_cores = args.threads
+        tprint(f"Specified number of cores are/is: {num_cores}")
+    else:
+        num_cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
+        tprint(f"By default, Topsicle allocates nmber of cores: {num_cores}")
+    devices = args.devices if getattr(args, "devices", None) else visible_devices()
+    tprint(f"CUDA devices used for the scan: {devices} ({engine.load_library().tps_build_info().decode()})")
+
+    output_csv = f"{args.outputDir}/telolengths_all.csv"
+    tprint(f"Output will be here: {output_csv}")
+    if os.path.exists(output_csv) and os.path.getsize(output_csv) > 0:
+        if args.override:
+            tprint(f"Output file {output_csv} already exists and will be overridden becuz having --override flag.")
+            os.remove(output_csv)
+        else:
+            tprint(f"Output file {output_csv} already exists and is not empty. Exiting to avoid overwrite. "
+                   "Use --override to force overwrite.")
+            sys.exit(1)
+
+    if args.telophrase is None:
+        telo_phrases = [len(args.pattern) - 2]
+        tprint(f"No telophrase provided, use kmer: {telo_phrases}")
+    else:
+        telo_phrases = args.telophrase if isinstance(args.telophrase, list) else [args.telophrase]
+
+    print("---------------------")
+
+    with open(output_csv, mode="w", newline="") as file:
+        csv.writer(file).writerow(["file_number", "phrase", "trc", "readID", "telo_length"])
+
+    for telo_phrase in telo_phrases:
+        if telo_phrase > len(args.pattern):
+            tprint("Cannot have length of subset larger than length of pattern")
+            tprint(f"Cannot get {telo_phrase}-bp cut from {len(args.pattern)}-bp pattern")
+            sys.exit()
+    sliding_val = args.slide if args.slide else len(args.pattern)
+
+    patterns = []
+    for telo_phrase in telo_phrases:
+        pats = patterns_to_search(telopattern=args.pattern, cut_length=telo_phrase)
+        validate_literals(pats)
+        patterns.append(pats)
+        tprint("patterns to search:", pats)
+
+    filenames = []
+    if os.path.isdir(args.inputDir):
+        for root, dirs, files in os.walk(args.inputDir):
+            for filename in files:
+                filenames.append(os.path.join(root, filename))
+    else:
+        filenames.append(args.inputDir)
+
+    tprint("begin processing reads")
+    phrase_to_telo = defaultdict(list)
+    phrase_to_trc = defaultdict(list)
+    csv_rows = [[] for _ in telo_phrases]
+    t0 = time.time()
+    total_bases = total_reads = 0
+    for seq_loc in filenames:
+        results = process_file(args, seq_loc, telo_phrases, patterns, sliding_val, devices, csv_rows)
+        st = process_file.last_stats
+        total_bases += st.n_bases
+        total_reads += st.n_reads
+        for k, telo_phrase in enumerate(telo_phrases):
+            for telolen, trc_val in results[k]:
+                phrase_to_telo[telo_phrase].append(telolen)
+                phrase_to_trc[telo_phrase].append(trc_val)
+    # the CSV is phrase-major (the reference's outer loop is over telo_phrases, main.py:206-235): rows of
+    # the first phrase were appended as they were found, those of the other phrases follow here
+    with open(output_csv, mode="a", newline="") as file:
+        writer = csv.writer(file)
+        for rows in csv_rows[1:]:
+            writer.writerows(rows)
+    dt = max(time.time() - t0, 1e-9)
+    tprint("finished processing all reads")
+    tprint(f"scanned {total_reads} reads / {total_bases} bases x {len(telo_phrases)} phrase(s) in {dt:.2f} s "
+           f"({total_bases * len(telo_phrases) / dt / 1e9:.3f} Gbases/s)")
+    print("---------------------")
+
+    inputtrc = args.cutoff[0] if isinstance(args.cutoff, (list, tuple)) else args.cutoff
+    for phrase in sorted(phrase_to_telo):
+        median_telo = np.median(phrase_to_telo[phrase])
+        median_trc = np.median(phrase_to_trc[phrase])
+        tprint(f"k-mer: {phrase}, with TRC >= {inputtrc}, median telomere length is {median_telo:.2f} bp")
+
+        if len(phrase_to_telo[phrase]) >= 3:
+            max_trc = max(phrase_to_trc[phrase])
+            plot_path = os.path.join(args.outputDir, f"quadfit_{phrase}mer_{args.pattern}.png")
+            vertex_x, vertex_y, coeffs = fit_quadratic_and_find_vertex(
+                phrase_to_trc[phrase], phrase_to_telo[phrase], inputtrc=inputtrc, median_trc=median_trc,
+                save_path=plot_path)
+            if vertex_x > max_trc:
+                tprint(f"Asymptotic TRC {vertex_x:.3f} is greater than max TRC, which is not expected. See plot.")
+                if median_trc < 1.0:
+                    tprint(f"Using median TRC value ({median_trc:.3f}) as asymptotic TRC instead.")
+                    vertex_x = median_trc
+                else:
+                    tprint("Using 0.9 as asymptotic TRC instead, since asymptotic is greater than 1.0.")
+                    vertex_x = 0.9
+            if vertex_x < 0.4:
+                tprint("Quadratic fit suggests asymptotic TRC less than 0.4. See plot with fit line")
+                if max_trc < 0.4:
+                    tprint(f"Maximum TRC value in data is {max_trc:.3f}, which is less than 0.4, indicating low "
+                           "confidence in telomere detection.")
+                if vertex_x < inputtrc:
+                    tprint(f"Asymptotic TRC {vertex_x:.3f} is less than input cutoff {inputtrc:.3f}. Topsicle "
+                           f"declares input TRC (={inputtrc}) as asymptotic TRC.")
+                    vertex_x = inputtrc
+            tprint(f"asymptotic TRC, or recommended cutoff: {vertex_x:.3f}")
+            filtered_telolen = [telo for trc, telo in zip(phrase_to_trc[phrase], phrase_to_telo[phrase])
+                                if trc >= vertex_x]
+            if filtered_telolen:
+                tprint(f"Median telomere length for reads with TRC cutoff >= {vertex_x:.3f}: "
+                       f"{np.median(filtered_telolen):.2f} bp")
+            else:
+                tprint(f"No read has TRC >= {vertex_x:.3f}, please double check the data or submit log to GitHub.")
+        else:
+            tprint("Not enough data points to recommend TRC cutoff.")
+
+    return tprint("All telomere found, have a nice day.")
+
+
+def build_parser():
+    p = argparse.ArgumentParser(description="Topsicle - Telomere length estimation from long reads",
+                                formatter_class=argparse.ArgumentDefaultsHelpFormatter)
+    p.add_argument("--inputDir", "-i", type=str, metavar="FILE/FOLDER",
+                   help="Required, Path to the input file or directory", required=True)
+    p.add_argument("--outputDir", "-o", type=str, metavar="FOLDER", help="Required, Path to the output directory",
+                   required=True)
+    p.add_argument("--pattern", metavar="CHAR", type=str,
+                   help="Required, Telomere repeat sequence (in 5' to 3' orientation). For e.g., in human use CCCTAA",
+                   required=True)
+    p.add_argument("--minSeqLength", metavar="INT", type=int,
+                   help="Minimum length of a long read sequence that will be analyzed", default=9000)
+    p.add_argument("--rawcountpattern", action="store_true", help="Output raw count of the k-mer for each window")
+    p.add_argument("--telophrase", nargs="+", metavar="INT", type=int,
+                   help="Length of telomere k-mer to search. By default will use telomere k-mer length minus 2")
+    p.add_argument("--cutoff", nargs="+", metavar="FLOAT", type=float, help="TRC statistics threshold", default=0.7)
+    p.add_argument("--windowSize", metavar="INT", type=int, help="Sliding window size", default=100)
+    p.add_argument("--slide", metavar="INT", type=int, help="Window sliding step. Default is telomere k-mer length")
+    p.add_argument("--trimfirst", metavar="INT", type=int, help="Length of intial number of base pairs to trim",
+                   default=100)
+    p.add_argument("--maxlengthtelo", metavar="INT", type=int,
+                   help="Longest possible length of telomere for any given read", default=20000)
+    p.add_argument("--plot", action="store_true",
+                   help="Optional, generate plot showing for each telomere read the abundance across the sequencing "
+                        "reead and the changepoint")
+    p.add_argument("--rangecp", metavar="INT", type=int,
+                   help="Optional, set range of changepoint plot for visualization, default is maxlengthtelo")
+    p.add_argument("--read_check", metavar="STR", type=str, help="Optional, get telomere of a specific read")
+    p.add_argument("--override", "-ov", action="store_true",
+                   help="Override telolengths_all.csv file but keep subset fastq")
+    p.add_argument("--threads", "-t", metavar="INT", type=int,
+                   help="Number of CPU cores to use (by default, all available cores)", default=None)
+    p.add_argument("--devices", nargs="+", metavar="INT", type=int,
+                   help="(B200 build) CUDA devices to scan on; default: all visible devices")
+    return p
+
+
+def main(argv=None):
+    start_time = time.time()
+    args = build_parser().parse_args(argv)
+    tprint.logfile = get_log_path(args)
+    analysis_run(args)
+    elapsed = time.time() - start_time
+    print(f"Elapsed time(s): {elapsed:.2f} seconds")
+
+
+if __name__ == "__main__":
+    main()

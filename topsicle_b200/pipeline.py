@@ -1,0 +1,374 @@
+"""Batched per-file scan driver: FASTQ/FASTA reader -> pinned batches -> GPU(s) -> ordered results.
+
+This is what `process_file` (Topsicle/main.py:52-154) becomes on a B200 box.  The reference
+parses the file (at least) twice plus once per TRC-pass read and runs step 1 / step 2 read
+by read in one Python process per *file*; here one pass over the file feeds fixed-size
+batches of reads to every visible GPU:
+
+    reader (C, threads) --> pinned batch --tps_submit--> [H2D | K1 K2 K3 K4 | D2H] --tps_wait-->
+    harvest TRC-pass reads --> ordered sink (file order restored across devices)
+
+One host thread per device owns a `ScanContext` per telophrase and a ring of pinned batch
+buffers; batches are dealt to whichever device asks next (reads are independent units, no
+collective).  Several phrases (`--telophrase 4 5 6`) are scanned from ONE parse of the file.
+Results are handed to the caller's sink strictly in file order, whatever order the devices
+finish in, so CSV rows, `rawcount_{phrase}_{i}.csv` numbering and the subset file come out
+exactly as the reference writes them.
+"""
+from __future__ import annotations
+
+import threading
+from dataclasses import dataclass, field
+from typing import Callable, Sequence
+
+import numpy as np
+
+from . import engine, fastx
+
+
+@dataclass
+class ScanConfig:
+    """The arguments main.py:process_file passes down for one telophrase (main.py:57,129-130,147-148)."""
+    patterns: Sequence[str]
+    len_telopattern: int
+    phrase: int = 0
+    cutoff: float = 0.7
+    min_seq_length: int = 9000
+    no_bp: int = 1000
+    window_size: int = 100
+    slide: int = 6
+    trimfirst: int = 100
+    maxlengthtelo: int = 20000
+    want_rawcount: bool = False
+    step1_only: bool = False
+    force_tail: str | None = None
+    count_threshold_override: int | None = None
+
+
+@dataclass
+class PassRead:
+    """One TRC-pass read (a row of telolengths_all.csv)."""
+    index: int            # position of the read in its file
+    read_id: str
+    literal: str          # first-max literal (allsteps.py:190-191)
+    tail: str             # 'forward' | 'reverse'
+    count: int
+    trc: float            # count / (no_bp / len(pattern))
+    status: int           # engine.ST_PASS or engine.ST_BADSEG
+    n_windows: int
+    telo_length: int      # trimfirst + slide * bkp, -1 if BADSEG
+    length: int
+    counts: np.ndarray | None = None   # uint8 [n_windows][n_patterns] when want_rawcount
+    record: bytes | None = None        # SeqIO.write text when want_records
+
+
+@dataclass
+class BatchResult:
+    seq: int
+    first_read: int
+    n_reads: int
+    n_bases: int
+    n_scanned: int                     # reads with L > minSeqLength
+    passes: list = field(default_factory=list)   # per config: list[PassRead]
+
+
+@dataclass
+class FileStats:
+    n_reads: int = 0
+    n_bases: int = 0
+    n_scanned: int = 0
+    n_batches: int = 0
+    format_name: str = ""
+
+
+class _OrderedSink:
+    """Delivers BatchResults to `fn` in batch order."""
+
+    def __init__(self, fn):
+        self.fn = fn
+        self.lock = threading.Lock()
+        self.next_seq = 0
+        self.held = {}
+
+    def put(self, res: BatchResult):
+        with self.lock:
+            self.held[res.seq] = res
+            while self.next_seq in self.held:
+                self.fn(self.held.pop(self.next_seq))
+                self.next_seq += 1
+
+
+class _Slot:
+    def __init__(self, max_bases, max_reads):
+        self.bases = engine.PinnedBuffer(max_bases)
+        self.offsets = engine.PinnedBuffer((max_reads + 1) * 8)
+
+    def free(self):
+        self.bases.free()
+        self.offsets.free()
+
+
+def make_context(cfg: ScanConfig, device: int, max_batch_reads: int, max_batch_bases: int, n_slots: int,
+                 max_pass_reads: int = 0, rawcount_capacity: int = 0) -> engine.ScanContext:
+    return engine.ScanContext(
+        cfg.patterns, len_telopattern=cfg.len_telopattern, cutoff=cfg.cutoff, min_seq_length=cfg.min_seq_length,
+        no_bp=cfg.no_bp, window_size=cfg.window_size, slide=cfg.slide, trimfirst=cfg.trimfirst,
+        maxlengthtelo=cfg.maxlengthtelo, want_rawcount=cfg.want_rawcount, device=device, n_slots=n_slots,
+        max_batch_reads=max_batch_reads, max_batch_bases=max_batch_bases, max_pass_reads=max_pass_reads,
+        rawcount_capacity=rawcount_capacity, count_threshold_override=cfg.count_threshold_override,
+        step1_only=cfg.step1_only, force_tail=cfg.force_tail)
+
+
+def windows_per_read(cfg: ScanConfig) -> int:
+    reg = max(0, cfg.maxlengthtelo - cfg.trimfirst)
+    return (reg - cfg.window_size) // cfg.slide + 1 if reg >= cfg.window_size else 0
+
+
+def harvest(cfg: ScanConfig, ctx, batch, rows, raw, want_records: bool, keep=None) -> list:  # noqa: D401
+    """TRC-pass reads of one finished batch, in read order."""
+    out = []
+    idx = np.nonzero(rows["status"] >= engine.ST_PASS)[0]
+    for i in idx:
+        i = int(i)
+        r = rows[i]
+        rid = batch.read_id(i)
+        if keep is not None and rid not in keep:
+            continue
+        cnt = int(r["match_count"])
+        pr = PassRead(index=batch.first_read + i, read_id=rid, literal=ctx.patterns[int(r["best_pattern"])],
+                      tail=engine.TAIL_NAMES[int(r["tail"])], count=cnt,
+                      trc=engine.trc_value(cnt, cfg.len_telopattern, cfg.no_bp), status=int(r["status"]),
+                      n_windows=int(r["n_windows"]), telo_length=int(r["telo_length"]), length=int(r["length"]))
+        if cfg.want_rawcount and raw is not None:
+            tab = ctx.rawcount_table(rows, raw, i)
+            pr.counts = None if tab is None else tab.copy()
+        if want_records:
+            pr.record = batch.record_text(i)
+        out.append(pr)
+    return out
+
+
+class _DeviceWorker:
+    """One device: a context per config, a ring of pinned batch slots."""
+
+    def __init__(self, device, cfgs, max_batch_reads, max_batch_bases, depth, max_pass_reads, rawcount_capacity,
+                 context_factory):
+        self.device = device
+        self.cfgs = cfgs
+        self.max_batch_reads = max_batch_reads
+        self.max_batch_bases = max_batch_bases
+        self.ctxs = [context_factory(c, device, max_batch_reads, max_batch_bases, depth, max_pass_reads,
+                                     rawcount_capacity if c.want_rawcount else 0) for c in cfgs]
+        self.slots = [_Slot(max_batch_bases, max_batch_reads) for _ in range(depth)]
+
+    def close(self):
+        for c in self.ctxs:
+            c.close()
+        for s in self.slots:
+            s.free()
+
+    def _scan_sub(self, ci, bases, offsets, lo, hi):
+        """Synchronous scan of reads [lo, hi) of a batch, splitting again on capacity overflow
+        (more TRC-pass reads or raw counts than the context's per-batch capacity)."""
+        ctx = self.ctxs[ci]
+        base0 = int(offsets[lo])
+        sub_off = (offsets[lo:hi + 1] - offsets[lo]).astype(np.uint64)
+        sub_bases = bases[base0:int(offsets[hi])]
+        try:
+            rows, raw = ctx.scan(np.ascontiguousarray(sub_bases), sub_off)
+            return [(lo, hi, rows, raw)]
+        except engine.TpsError as e:
+            if e.code != -4 or hi - lo <= 1:
+                raise
+            mid = (lo + hi) // 2
+            return self._scan_sub(ci, bases, offsets, lo, mid) + self._scan_sub(ci, bases, offsets, mid, hi)
+
+    def finish(self, item, records_cfg, keep):
+        slot, batch, bids, seq = item
+        res = BatchResult(seq=seq, first_read=batch.first_read, n_reads=batch.n_reads, n_bases=batch.n_bases,
+                          n_scanned=0)
+        n = batch.n_reads
+        for ci, (cfg, ctx, bid) in enumerate(zip(self.cfgs, self.ctxs, bids)):
+            try:
+                parts = [(0, n, *ctx.wait(bid))]
+            except engine.TpsError as e:
+                if e.code != -4:
+                    raise
+                mid = n // 2
+                if n <= 1:
+                    raise
+                parts = (self._scan_sub(ci, slot.bases.array, batch.offsets, 0, mid)
+                         + self._scan_sub(ci, slot.bases.array, batch.offsets, mid, n))
+            passes = []
+            scanned = 0
+            for lo, hi, rows, raw in parts:
+                scanned += int((rows["status"] != engine.ST_FILTERED).sum())
+                view = _BatchView(batch, lo)
+                passes += harvest(cfg, ctx, view, rows, raw, records_cfg == ci, keep)
+            res.passes.append(passes)
+            if ci == 0:
+                res.n_scanned = scanned
+        batch.release()
+        return res
+
+
+class _BatchView:
+    """Reads [lo, ...) of a batch addressed from 0 (for split re-scans)."""
+
+    def __init__(self, batch, lo):
+        self.b = batch
+        self.lo = lo
+        self.first_read = batch.first_read + lo
+
+    def read_id(self, i):
+        return self.b.read_id(self.lo + i)
+
+    def record_text(self, i):
+        return self.b.record_text(self.lo + i)
+
+
+def scan_file(path: str, cfgs: Sequence[ScanConfig], sink: Callable[[BatchResult], None], *,
+              devices: Sequence[int] = (0,), threads: int = 0, max_batch_bases: int = 1 << 28,
+              max_batch_reads: int = 1 << 17, depth: int = 3, max_pass_reads: int = 0,
+              rawcount_capacity: int = 0, records_cfg: int | None = None, keep_ids=None,
+              context_factory=None) -> FileStats:
+    """Scan every read of `path` under each config in `cfgs` (one parse, one pass).
+
+    `sink(BatchResult)` is called in file order; BatchResult.passes[k] holds the TRC-pass
+    reads under cfgs[k].  `records_cfg=k` attaches the SeqIO.write text of the reads passing
+    cfgs[k].  `keep_ids` restricts the harvest to those read ids (`--read_check`)."""
+    context_factory = context_factory or make_context
+    if not max_pass_reads:
+        max_pass_reads = max(1024, max_batch_reads // 8)
+    if not rawcount_capacity and any(c.want_rawcount for c in cfgs):
+        per_read = max(windows_per_read(c) * len(c.patterns) for c in cfgs if c.want_rawcount)
+        rawcount_capacity = max(1 << 20, min(1 << 30, per_read * max_pass_reads))
+    stats = FileStats()
+    ordered = _OrderedSink(sink)
+    fx = fastx.FastxFile(path, threads=threads)
+    stats.format_name = fx.format_name
+    reader_lock = threading.Lock()
+    seq_counter = [0]
+    errors = []
+    workers = []
+    try:
+        for d in devices:
+            workers.append(_DeviceWorker(d, cfgs, max_batch_reads, max_batch_bases, depth, max_pass_reads,
+                                         rawcount_capacity, context_factory))
+
+        def run(w: _DeviceWorker):
+            inflight = []
+            free = list(w.slots)
+            try:
+                while not errors:
+                    if not free:
+                        item = inflight.pop(0)
+                        ordered.put(w.finish(item, records_cfg, keep_ids))
+                        free.append(item[0])
+                    slot = free.pop()
+                    with reader_lock:
+                        batch = fx.next_batch(slot.bases.array, slot.offsets.array.view(np.uint64),
+                                              max_reads=w.max_batch_reads, max_bases=w.max_batch_bases)
+                        if batch is not None:
+                            seq = seq_counter[0]
+                            seq_counter[0] += 1
+                            stats.n_reads += batch.n_reads
+                            stats.n_bases += batch.n_bases
+                            stats.n_batches += 1
+                    if batch is None:
+                        free.append(slot)
+                        break
+                    nb = batch.n_bases
+                    off = batch.offsets[:batch.n_reads + 1]
+                    bids = [c.submit(slot.bases.array[:nb], off) for c in w.ctxs]
+                    inflight.append((slot, batch, bids, seq))
+                while inflight and not errors:
+                    ordered.put(w.finish(inflight.pop(0), records_cfg, keep_ids))
+            except BaseException as e:  # noqa: BLE001 - reported to the caller below
+                errors.append(e)
+
+        if len(workers) == 1:
+            run(workers[0])
+        else:
+            ths = [threading.Thread(target=run, args=(w,), name=f"tps-dev{w.device}") for w in workers]
+            for t in ths:
+                t.start()
+            for t in ths:
+                t.join()
+        if errors:
+            raise errors[0]
+    finally:
+        for w in workers:
+            w.close()
+        fx.close()
+    return stats
+
+
+def collect_file(path: str, cfgs: Sequence[ScanConfig], **kw):
+    """scan_file with an in-memory sink -> (stats, per-config list[PassRead], scanned counts)."""
+    per_cfg = [[] for _ in cfgs]
+    scanned = [0]
+
+    def sink(res: BatchResult):
+        for k, ps in enumerate(res.passes):
+            per_cfg[k].extend(ps)
+        scanned[0] += res.n_scanned
+
+    stats = scan_file(path, cfgs, sink, **kw)
+    stats.n_scanned = scanned[0]
+    return stats, per_cfg
+
+
+def scan_named_read(path: str, cfgs: Sequence[ScanConfig], read_id: str, *, device: int = 0, threads: int = 0,
+                    context_factory=None):
+    """Per-read entry (bound_detect / rawCountPattern, allsteps.py:252-259, 375-382): find the record(s)
+    whose id is `read_id`, scan only those under every config.  Returns per-config list[PassRead]."""
+    context_factory = context_factory or make_context
+    picked, lengths, indices = [], [], []
+    fx = fastx.FastxFile(path, threads=threads)
+    try:
+        bases = np.empty(1 << 27, dtype=np.uint8)
+        offsets = np.empty((1 << 17) + 1, dtype=np.uint64)
+        while True:
+            try:
+                b = fx.next_batch(bases, offsets)
+            except fastx.FastxError as e:
+                if e.code != -4:
+                    raise
+                bases = np.empty(bases.size * 4, dtype=np.uint8)
+                continue
+            if b is None:
+                break
+            for i in b.find_id(read_id):
+                picked.append(b.sequence(i))
+                lengths.append(len(picked[-1]))
+                indices.append(b.first_read + i)
+            b.release()
+    finally:
+        fx.close()
+    per_cfg = [[] for _ in cfgs]
+    if not picked:
+        return per_cfg
+    sel_bases, sel_off = engine.pack_reads(picked)
+    for k, cfg in enumerate(cfgs):
+        ctx = context_factory(cfg, device, len(picked), max(1, int(sel_off[-1])), 1, len(picked),
+                              max(1, windows_per_read(cfg) * len(cfg.patterns) * len(picked))
+                              if cfg.want_rawcount else 0)
+        try:
+            rows, raw = ctx.scan(sel_bases, sel_off)
+            for i, r in enumerate(rows):
+                if r["status"] < engine.ST_PASS:
+                    continue
+                cnt = int(r["match_count"])
+                pr = PassRead(index=indices[i], read_id=read_id, literal=ctx.patterns[int(r["best_pattern"])],
+                              tail=engine.TAIL_NAMES[int(r["tail"])], count=cnt,
+                              trc=engine.trc_value(cnt, cfg.len_telopattern, cfg.no_bp), status=int(r["status"]),
+                              n_windows=int(r["n_windows"]), telo_length=int(r["telo_length"]),
+                              length=int(r["length"]))
+                if cfg.want_rawcount and raw is not None:
+                    tab = ctx.rawcount_table(rows, raw, i)
+                    pr.counts = None if tab is None else tab.copy()
+                per_cfg[k].append(pr)
+        finally:
+            ctx.close()
+    return per_cfg

@@ -1,0 +1,82 @@
+"""CPU tier: the C-ABI library loads, exports every function `include/topsicle_b200.h` declares,
+agrees with the ctypes mirror on struct sizes, and refuses to run without a GPU (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from tests.conftest import REPO
+from topsicle_b200 import engine, fastx
+
+
+def declared_functions():
+    text = open(os.path.join(REPO, "include", "topsicle_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = re.findall(r"^\s*(?:const\s+)?[A-Za-z_][\w\s\*]*?\b(tps_\w+)\s*\(", text, flags=re.M)
+    return sorted(set(names))
+
+
+def test_header_declares_the_expected_entry_points():
+    names = declared_functions()
+    for must in ("tps_create", "tps_destroy", "tps_submit", "tps_wait", "tps_batch_info", "tps_scan_device",
+                 "tps_sync", "tps_get_timings", "tps_last_error", "tps_alloc_pinned", "tps_free_pinned",
+                 "tps_abi_version", "tps_build_info", "tps_kernel_launches", "tps_debug_copy"):
+        assert must in names, must
+
+
+def test_library_exports_every_declared_symbol():
+    lib = engine.load_library()
+    for name in declared_functions():
+        assert getattr(lib, name) is not None, name
+    assert lib.tps_abi_version() == 1
+    assert b"sm_100a" in lib.tps_build_info()
+
+
+def test_struct_layout_matches_header(tmp_path):
+    """sizeof / offsetof as gcc sees the header == the ctypes / numpy mirrors."""
+    import subprocess
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "topsicle_b200.h"\n'
+                   'int main(void){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(tps_params), sizeof(tps_row),'
+                   'offsetof(tps_params, flags), offsetof(tps_params, max_batch_bases),'
+                   'offsetof(tps_row, telo_length), offsetof(tps_row, rawcount_offset));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(REPO, "include"), "-o", str(exe), str(src)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    P = engine.TpsParams
+    want = [C.sizeof(P), engine.ROW_DTYPE.itemsize, P.flags.offset, P.max_batch_bases.offset,
+            engine.ROW_DTYPE.fields["telo_length"][1], engine.ROW_DTYPE.fields["rawcount_offset"][1]]
+    assert got == want
+    assert fastx.REC_DTYPE.itemsize == 48
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product fails loudly; with one, a bad struct_size is rejected."""
+    import torch
+    lib = engine.load_library()
+    p = engine.TpsParams()
+    h = C.c_void_p()
+    if not torch.cuda.is_available():
+        with pytest.raises(engine.TpsError) as e:
+            engine.ScanContext(["CCCTA"])
+        assert e.value.code == -6 and "no CPU fallback" in str(e.value)
+    p.struct_size = 1
+    assert lib.tps_create(C.byref(h), 0, C.byref(p)) == -1
+    assert b"ABI mismatch" in lib.tps_last_error(None)
+
+
+def test_host_library_symbols():
+    lib = fastx.host_library()
+    for name in ("tps_fastx_open", "tps_fastx_next", "tps_fastx_release", "tps_fastx_close", "tps_fastx_find_id",
+                 "tps_format_rawcount", "tps_synth_fill", "tps_synth_lengths"):
+        assert getattr(lib, name) is not None
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(REPO, "topsicle_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".c", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(root, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f

@@ -66,7 +66,7 @@ def test_bound_detect_both_tails_and_errors(tmp_path):
     assert bound_detect(DEMO, "no_such_read", pats, 100, 6, 100, 20000, 5, tail="forward") == []
     assert bound_detect(DEMO, 7, pats, 100, 6, 100, 20000, 5) is None
     short = tmp_path / "short.fasta"
-    short.write_text(">s1\n" + "CCCTAAA" * 20 + "\n")
+    short.write_text(">s1\n" + "CCCTAAA" * 17 + "\n")          # 119 bases -> 4 windows
     with pytest.raises(ValueError):
         bound_detect(str(short), "s1", pats, 100, 6, 0, 20000, 5, tail="forward")   # 7 windows needed
 

@@ -43,6 +43,8 @@ def parse_args():
     ap.add_argument("--cpu-sample-reads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parse", action="store_true", help="skip the FASTQ-file end-to-end leg")
+    ap.add_argument("--parse-passes", type=int, default=2)
     return ap.parse_args()
 
 
@@ -309,6 +311,43 @@ def main():
                "ms_per_step": e_wall / a.steps * 1e3, "slots_in_flight": depth}
     clocks = sampler.stop(t0, time.perf_counter())
 
+    # ---- end to end from a FASTQ file: C reader (host threads) -> pinned batches -> H2D -> kernels -> D2H
+    # -> harvest of the TRC-pass reads, through the same Scanner the `topsicle` CLI uses
+    e2e_file = None
+    if not a.no_parse:
+        from topsicle_b200 import pipeline
+        ctx.close()
+        shm = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else "/tmp"
+        path = os.path.join(shm, f"tps_bench_{os.getpid()}_r{rank}.fastq")
+        try:
+            synth.write_fastq(path, host_bases[0].array[:nbases[0]], host_off[0].array.view(np.uint64),
+                              prefix=f"syn{a.config}", first_read=rank * nb * reads_per_step)
+            fsize = os.path.getsize(path)
+            cfg = pipeline.ScanConfig(patterns=pats, len_telopattern=len(kw["pattern"]), phrase=kw["phrase"],
+                                      cutoff=kw["cutoff"], min_seq_length=kw["min_len"], window_size=kw["W"],
+                                      slide=kw["slide"], trimfirst=kw["trim"], maxlengthtelo=kw["maxlen"])
+            got = []
+            with pipeline.Scanner([cfg], devices=[local_rank], max_batch_bases=1 << 28, max_batch_reads=1 << 17,
+                                  depth=3) as sc:
+                sc.scan_file(path, lambda res: None)           # warm-up pass (page cache, first launches)
+                barrier()
+                t4 = time.perf_counter()
+                for _ in range(a.parse_passes):
+                    got.clear()
+                    st = sc.scan_file(path, lambda res: got.extend(res.passes[0]))
+                barrier()
+                t5 = time.perf_counter()
+            p_wall = max_over_ranks(t5 - t4)
+            p_bases = sum_over_ranks(float(st.n_bases * a.parse_passes))
+            assert st.n_reads == reads_per_step and st.n_bases == nbases[0]
+            e2e_file = {"value": p_bases / p_wall / 1e9, "unit": UNIT, "file_bytes": fsize, "passes": a.parse_passes,
+                        "ms_per_pass": p_wall / a.parse_passes * 1e3, "host_threads": len(os.sched_getaffinity(0)),
+                        "trc_pass_reads": len(got),
+                        "what": "uncompressed FASTQ in page cache -> telomere rows (parse + PCIe + kernels + harvest)"}
+        finally:
+            if os.path.exists(path):
+                os.remove(path)
+
     n_pass = int((rows_dev["status"] >= engine.ST_PASS).sum())
     peak, peak_src = hbm_peak()
     alg_bytes = ALG_BYTES_PER_BASE * (bases_timed / a.steps)
@@ -334,10 +373,13 @@ def main():
                              "algorithmic_bytes_per_base": ALG_BYTES_PER_BASE,
                              "traffic": (tpb * bases_timed / a.steps) if tpb else None,
                              "whole_scan_frac": alg_bytes / (dev_ms * 1e-3) / 1e9 / peak},
-                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                "cpu_baseline": cpu, "e2e": e2e, "e2e_from_fastq": e2e_file, "gpu_launches": int(launches),
+                "clocks": clocks,
                 "generate_s": t_gen}
         print(json.dumps(line))
     ctx.close()
+    for hb in host_bases + host_off:
+        hb.free()
     if world > 1:
         dist.destroy_process_group()
 

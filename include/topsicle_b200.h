@@ -125,6 +125,13 @@ void tps_free_pinned(void *p);
  * Replaces: process_file's step 1 + per-read step 2/3 loop (main.py:57, 125-150). */
 int tps_submit(tps_ctx *ctx, const uint8_t *bases, const uint64_t *offsets, uint32_t n_reads,
                uint64_t batch_id);
+/* Scan, under the parameters of `ctx`, the batch that `owner` has in flight as `batch_id`, without a
+ * second upload or a second K1: ctx's K2..K4 are enqueued on the owner's stream and read the owner's
+ * packed reads.  Same device; collect with tps_wait(ctx, batch_id, ...).  This is how several
+ * telophrases are scanned from one pass over the input.
+ * Replaces: the reference's outer loop over telo_phrases, which re-parses and re-scans the whole
+ * dataset once per phrase (main.py:206-235). */
+int tps_submit_shared(tps_ctx *ctx, tps_ctx *owner, uint64_t batch_id);
 /* Block until batch `batch_id` is done; copies n_reads rows to rows_out.  If the context
  * was created with want_rawcount, copies *rawcount_elems count elements (uint8,
  * [n_windows][P] per PASS read at tps_row.rawcount_offset) to rawcounts_out, whose capacity

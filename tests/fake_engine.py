@@ -35,14 +35,16 @@ class OracleContext:
         self.thr = (cfg.count_threshold_override if cfg.count_threshold_override is not None
                     else engine.count_threshold(cfg.cutoff, cfg.len_telopattern, cfg.no_bp))
         self._pending = {}
-        self._next = 1
         self.closed = False
 
     def submit(self, bases, offsets):
-        bid = self._next
-        self._next += 1
+        bid = next(engine._batch_ids)
         assert len(offsets) - 1 <= self.max_batch_reads and int(offsets[-1]) <= self.max_batch_bases
         self._pending[bid] = (bases.tobytes(), np.array(offsets, dtype=np.uint64))
+        return bid
+
+    def submit_shared(self, owner, bid):
+        self._pending[bid] = owner._pending[bid]
         return bid
 
     def wait(self, bid):

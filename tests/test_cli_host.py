@@ -58,3 +58,21 @@ def test_pass_capacity_overflow_is_split_not_lost(tmp_path, monkeypatch):
     assert len(big[0]) == 17
     assert [(p.index, p.read_id, p.telo_length) for p in small[0]] == [(p.index, p.read_id, p.telo_length)
                                                                       for p in big[0]]
+
+
+def test_read_check_only_that_read(tmp_path, monkeypatch):
+    """--read_check: one CSV row, but the subset file still holds every TRC-pass read (main.py:64-87
+    runs before the read_check branch)."""
+    fake_engine.install(monkeypatch)
+    import hashlib
+    from topsicle_b200 import main as tmain
+    case = golden_cases()[0]
+    out = tmp_path / "o"
+    if hasattr(tmain.tprint, "logfile"):
+        del tmain.tprint.logfile
+    tmain.main(["--inputDir", os.path.join(GOLD, "demo.fastq.gz"), "--outputDir", str(out), "--pattern", "CCCTAAA",
+                "--slide", "6", "--read_check", "ERR11436636.163616"])
+    rows = open(out / "telolengths_all.csv", newline="").read().split("\r\n")
+    assert rows[1:] == ["demo.fastq,5,0.791,ERR11436636.163616,3010", ""]
+    sub = hashlib.md5(open(out / "demo.fastq_trc_over_0.7.fastq", "rb").read()).hexdigest()
+    assert sub == case["files"]["demo.fastq_trc_over_0.7.fastq"]

@@ -325,15 +325,17 @@ int tps_create(tps_ctx **out, int device, const tps_params *params) {
 
 namespace {
 
-/* Enqueue K1..K4 for one batch on `st`.  d_bases/d_off may be slot- or caller-owned. */
+/* Enqueue K1..K4 for one batch on `st`.  d_bases/d_off may be slot- or caller-owned.  With
+ * `packed_by` the batch was already packed (K1) into that slot's code/flag/mask buffers by another
+ * context: only K2..K4 run, reading them. */
 int enqueue_scan(tps_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t *d_bases, const uint64_t *d_off,
-                 uint32_t n_reads, uint64_t n_bases, tps_row *d_rows, bool timed) {
+                 uint32_t n_reads, uint64_t n_bases, tps_row *d_rows, bool timed, const Slot *packed_by = nullptr) {
   const tps_params &p = ctx->p;
   cudaEvent_t *ev = ctx->ev[ctx->scan_seq % TPS_TIMING_RING];
   TPS_CUDA(ctx, cudaMemsetAsync(s.d_counters, 0, 8 * sizeof(uint32_t), st));
   if (timed) TPS_CUDA(ctx, cudaEventRecord(ev[0], st));
   const uint64_t n_tiles = (n_bases + 511) / 512;
-  if (n_tiles) {
+  if (n_tiles && !packed_by) {
     const uint64_t per_cta = (uint64_t)(TPS_K1_THREADS / 32) * ctx->k1_unroll;
     uint64_t want = (n_tiles + per_cta - 1) / per_cta;
     int grid = (int)(want < (uint64_t)ctx->k1_grid ? want : (uint64_t)ctx->k1_grid);
@@ -344,9 +346,10 @@ int enqueue_scan(tps_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t *d_bases,
   if (timed) TPS_CUDA(ctx, cudaEventRecord(ev[1], st));
   TpsScanArgs a;
   memset(&a, 0, sizeof(a));
-  a.pk.codes = s.d_codes;
-  a.pk.flags = s.d_flags;
-  a.pk.masks = s.d_masks;
+  const Slot &src = packed_by ? *packed_by : s;
+  a.pk.codes = src.d_codes;
+  a.pk.flags = src.d_flags;
+  a.pk.masks = src.d_masks;
   a.offsets = d_off;
   a.n_reads = n_reads;
   a.rows = d_rows;
@@ -422,6 +425,36 @@ int tps_submit(tps_ctx *ctx, const uint8_t *bases, const uint64_t *offsets, uint
   s.busy = true;
   s.batch_id = batch_id;
   s.n_reads = n_reads;
+  return TPS_OK;
+}
+
+int tps_submit_shared(tps_ctx *ctx, tps_ctx *owner, uint64_t batch_id) {
+  if (!ctx || !owner || ctx == owner) return fail(ctx, TPS_EINVAL, "tps_submit_shared needs two distinct contexts");
+  if (ctx->device != owner->device) return fail(ctx, TPS_EINVAL, "contexts are on different devices");
+  Slot *so = nullptr, *sl = nullptr;
+  for (uint32_t i = 0; i < owner->p.n_slots; ++i)
+    if (owner->slots[i].busy && owner->slots[i].batch_id == batch_id) so = &owner->slots[i];
+  if (!so) return fail(ctx, TPS_ESTATE, "batch %llu is not in flight in the owner context", (unsigned long long)batch_id);
+  const tps_params &p = ctx->p;
+  if (so->n_reads > p.max_batch_reads)
+    return fail(ctx, TPS_ECAPACITY, "batch has %u reads, capacity %u", so->n_reads, p.max_batch_reads);
+  for (uint32_t i = 0; i < p.n_slots; ++i) {
+    if (ctx->slots[i].busy && ctx->slots[i].batch_id == batch_id) return fail(ctx, TPS_ESTATE, "batch id already in flight");
+    if (!ctx->slots[i].busy && !sl) sl = &ctx->slots[i];
+  }
+  if (!sl) return fail(ctx, TPS_ESTATE, "all %u slots busy: call tps_wait first", p.n_slots);
+  TPS_CUDA(ctx, cudaSetDevice(ctx->device));
+  Slot &s = *sl;
+  cudaStream_t st = so->stream; /* owner's stream: ordered after its H2D + K1 and before its slot is reused */
+  int rc = enqueue_scan(ctx, s, st, so->d_bases, so->d_off, so->n_reads, 0, s.d_rows, false, so);
+  if (rc) return rc;
+  if (so->n_reads)
+    TPS_CUDA(ctx, cudaMemcpyAsync(s.h_rows, s.d_rows, (uint64_t)so->n_reads * sizeof(tps_row), cudaMemcpyDeviceToHost, st));
+  TPS_CUDA(ctx, cudaMemcpyAsync(s.h_counters, s.d_counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  TPS_CUDA(ctx, cudaEventRecord(s.done, st));
+  s.busy = true;
+  s.batch_id = batch_id;
+  s.n_reads = so->n_reads;
   return TPS_OK;
 }
 

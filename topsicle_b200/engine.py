@@ -7,6 +7,7 @@ fallback (nothing under `oracle/` is ever imported from here).
 from __future__ import annotations
 
 import ctypes as C
+import itertools
 import os
 from typing import Iterable, Sequence
 
@@ -62,6 +63,7 @@ ROW_DTYPE = np.dtype([
 assert ROW_DTYPE.itemsize == 40
 
 _lib = None
+_batch_ids = itertools.count(1)   # batch ids are unique across contexts (shared batches keep their owner's id)
 
 
 def load_library() -> C.CDLL:
@@ -88,6 +90,8 @@ def load_library() -> C.CDLL:
     lib.tps_free_pinned.argtypes = [vp]
     lib.tps_submit.restype = C.c_int
     lib.tps_submit.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint64]
+    lib.tps_submit_shared.restype = C.c_int
+    lib.tps_submit_shared.argtypes = [vp, vp, C.c_uint64]
     lib.tps_wait.restype = C.c_int
     lib.tps_wait.argtypes = [vp, C.c_uint64, vp, u32p, vp, C.c_uint64, u64p]
     lib.tps_batch_info.restype = C.c_int
@@ -208,7 +212,6 @@ class ScanContext:
         rc = self.lib.tps_create(C.byref(self._h), device, C.byref(p))
         if rc != 0:
             raise TpsError(rc, self.lib.tps_last_error(None).decode())
-        self._next_id = 1
         self._inflight = {}
 
     # -- lifetime
@@ -238,10 +241,16 @@ class ScanContext:
         assert bases.dtype == np.uint8 and offsets.dtype == np.uint64
         assert bases.flags.c_contiguous and offsets.flags.c_contiguous
         n_reads = len(offsets) - 1
-        bid = self._next_id
-        self._next_id += 1
+        bid = next(_batch_ids)
         self._check(self.lib.tps_submit(self._h, bases.ctypes.data, offsets.ctypes.data, n_reads, bid))
         self._inflight[bid] = (bases, offsets, n_reads)  # keep buffers alive
+        return bid
+
+    def submit_shared(self, owner: "ScanContext", bid: int) -> int:
+        """Scan the batch `owner` has in flight as `bid` under this context's parameters, reusing the
+        owner's upload and packed reads (no second H2D / K1)."""
+        self._check(self.lib.tps_submit_shared(self._h, owner._h, bid))
+        self._inflight[bid] = owner._inflight[bid]
         return bid
 
     def wait(self, bid: int):

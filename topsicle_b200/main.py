@@ -146,17 +146,23 @@ class _FileWriter:
             self.subset_handle.close()
 
 
-def process_file(args, seq_loc, telo_phrases, patterns, sliding_val, devices, csv_rows_out):
-    """One input file, every telophrase, one pass (reference: main.py:52-154, once per phrase).
-    Returns per phrase the list of (telomere length, TRC)."""
-    tprint("subsetting raw dataset based on TRC cutoff")
+def scan_configs(args, telo_phrases, patterns, sliding_val):
+    """One ScanConfig per telophrase == the arguments the reference passes down (main.py:57,129-130,147-148)."""
     min_cutoff = min(args.cutoff) if isinstance(args.cutoff, (list, tuple)) else args.cutoff
     want_counts = bool(args.rawcountpattern or args.plot)
-    cfgs = [pipeline.ScanConfig(patterns=pats, len_telopattern=len(args.pattern), phrase=k, cutoff=min_cutoff,
+    return [pipeline.ScanConfig(patterns=pats, len_telopattern=len(args.pattern), phrase=k, cutoff=min_cutoff,
                                 min_seq_length=args.minSeqLength, no_bp=1000, window_size=args.windowSize,
                                 slide=sliding_val, trimfirst=args.trimfirst, maxlengthtelo=args.maxlengthtelo,
                                 want_rawcount=want_counts)
             for k, pats in zip(telo_phrases, patterns)]
+
+
+def process_file(args, seq_loc, telo_phrases, scanner, sliding_val, csv_rows_out):
+    """One input file, every telophrase, one pass (reference: main.py:52-154, once per phrase).
+    Returns per phrase the list of (telomere length, TRC)."""
+    tprint("subsetting raw dataset based on TRC cutoff")
+    min_cutoff = min(args.cutoff) if isinstance(args.cutoff, (list, tuple)) else args.cutoff
+    cfgs = scanner.cfgs
     w = _FileWriter(args, seq_loc, cfgs, telo_phrases, min_cutoff, sliding_val,
                     f"{args.outputDir}/telolengths_all.csv")
     if w.subset_exists:
@@ -164,10 +170,7 @@ def process_file(args, seq_loc, telo_phrases, patterns, sliding_val, devices, cs
     if args.read_check:
         tprint("checking specific read:", args.read_check)
     try:
-        stats = pipeline.scan_file(seq_loc, cfgs, w, devices=devices, threads=args.threads or 0,
-                                   records_cfg=w.records_cfg,
-                                   max_batch_bases=int(os.environ.get("TOPSICLE_BATCH_BASES", 1 << 28)),
-                                   max_batch_reads=int(os.environ.get("TOPSICLE_BATCH_READS", 1 << 17)))
+        stats = scanner.scan_file(seq_loc, w, records_cfg=w.records_cfg)
     finally:
         w.close()
     if not w.subset_exists:
@@ -246,15 +249,22 @@ def analysis_run(args):
     csv_rows = [[] for _ in telo_phrases]
     t0 = time.time()
     total_bases = total_reads = 0
-    for seq_loc in filenames:
-        results = process_file(args, seq_loc, telo_phrases, patterns, sliding_val, devices, csv_rows)
-        st = process_file.last_stats
-        total_bases += st.n_bases
-        total_reads += st.n_reads
-        for k, telo_phrase in enumerate(telo_phrases):
-            for telolen, trc_val in results[k]:
-                phrase_to_telo[telo_phrase].append(telolen)
-                phrase_to_trc[telo_phrase].append(trc_val)
+    scanner = pipeline.Scanner(scan_configs(args, telo_phrases, patterns, sliding_val), devices=devices,
+                               threads=args.threads or 0,
+                               max_batch_bases=int(os.environ.get("TOPSICLE_BATCH_BASES", 1 << 28)),
+                               max_batch_reads=int(os.environ.get("TOPSICLE_BATCH_READS", 1 << 17)))
+    try:
+        for seq_loc in filenames:
+            results = process_file(args, seq_loc, telo_phrases, scanner, sliding_val, csv_rows)
+            st = process_file.last_stats
+            total_bases += st.n_bases
+            total_reads += st.n_reads
+            for k, telo_phrase in enumerate(telo_phrases):
+                for telolen, trc_val in results[k]:
+                    phrase_to_telo[telo_phrase].append(telolen)
+                    phrase_to_trc[telo_phrase].append(trc_val)
+    finally:
+        scanner.close()
     # the CSV is phrase-major (the reference's outer loop is over telo_phrases, main.py:206-235): rows of
     # the first phrase were appended as they were found, those of the other phrases follow here
     with open(output_csv, mode="a", newline="") as file:

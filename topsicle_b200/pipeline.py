@@ -149,7 +149,8 @@ def harvest(cfg: ScanConfig, ctx, batch, rows, raw, want_records: bool, keep=Non
 
 
 class _DeviceWorker:
-    """One device: a context per config, a ring of pinned batch slots."""
+    """One device: a context per config, a ring of pinned batch slots.  The first context uploads and
+    packs each batch; the others scan the same device-resident batch (tps_submit_shared)."""
 
     def __init__(self, device, cfgs, max_batch_reads, max_batch_bases, depth, max_pass_reads, rawcount_capacity,
                  context_factory):
@@ -157,8 +158,11 @@ class _DeviceWorker:
         self.cfgs = cfgs
         self.max_batch_reads = max_batch_reads
         self.max_batch_bases = max_batch_bases
-        self.ctxs = [context_factory(c, device, max_batch_reads, max_batch_bases, depth, max_pass_reads,
-                                     rawcount_capacity if c.want_rawcount else 0) for c in cfgs]
+        self.ctxs = []
+        for k, c in enumerate(cfgs):
+            # followers never upload: they need no base / code buffers of their own
+            self.ctxs.append(context_factory(c, device, max_batch_reads, max_batch_bases if k == 0 else 1, depth,
+                                             max_pass_reads, rawcount_capacity if c.want_rawcount else 0))
         self.slots = [_Slot(max_batch_bases, max_batch_reads) for _ in range(depth)]
 
     def close(self):
@@ -167,15 +171,30 @@ class _DeviceWorker:
         for s in self.slots:
             s.free()
 
+    def submit(self, bases, offsets):
+        bid = self.ctxs[0].submit(bases, offsets)
+        for c in self.ctxs[1:]:
+            c.submit_shared(self.ctxs[0], bid)
+        return bid
+
     def _scan_sub(self, ci, bases, offsets, lo, hi):
-        """Synchronous scan of reads [lo, hi) of a batch, splitting again on capacity overflow
-        (more TRC-pass reads or raw counts than the context's per-batch capacity)."""
-        ctx = self.ctxs[ci]
+        """Synchronous scan of reads [lo, hi) of a batch under config ci, splitting again on capacity
+        overflow (more TRC-pass reads or raw counts than the context's per-batch capacity)."""
         base0 = int(offsets[lo])
         sub_off = (offsets[lo:hi + 1] - offsets[lo]).astype(np.uint64)
-        sub_bases = bases[base0:int(offsets[hi])]
+        sub_bases = np.ascontiguousarray(bases[base0:int(offsets[hi])])
         try:
-            rows, raw = ctx.scan(np.ascontiguousarray(sub_bases), sub_off)
+            bid = self.ctxs[0].submit(sub_bases, sub_off)
+            if ci == 0:
+                rows, raw = self.ctxs[0].wait(bid)
+            else:
+                self.ctxs[ci].submit_shared(self.ctxs[0], bid)
+                try:
+                    self.ctxs[0].wait(bid)
+                except engine.TpsError as e:       # the leader's own overflow is irrelevant here
+                    if e.code != -4:
+                        raise
+                rows, raw = self.ctxs[ci].wait(bid)
             return [(lo, hi, rows, raw)]
         except engine.TpsError as e:
             if e.code != -4 or hi - lo <= 1:
@@ -184,19 +203,23 @@ class _DeviceWorker:
             return self._scan_sub(ci, bases, offsets, lo, mid) + self._scan_sub(ci, bases, offsets, mid, hi)
 
     def finish(self, item, records_cfg, keep):
-        slot, batch, bids, seq = item
+        slot, batch, bid, seq = item
         res = BatchResult(seq=seq, first_read=batch.first_read, n_reads=batch.n_reads, n_bases=batch.n_bases,
                           n_scanned=0)
         n = batch.n_reads
-        for ci, (cfg, ctx, bid) in enumerate(zip(self.cfgs, self.ctxs, bids)):
+        waited = []
+        for ctx in self.ctxs:                      # release every context's slot before any re-scan
             try:
-                parts = [(0, n, *ctx.wait(bid))]
+                waited.append(ctx.wait(bid))
             except engine.TpsError as e:
-                if e.code != -4:
+                if e.code != -4 or n <= 1:
                     raise
+                waited.append(None)
+        for ci, (cfg, ctx) in enumerate(zip(self.cfgs, self.ctxs)):
+            if waited[ci] is not None:
+                parts = [(0, n, *waited[ci])]
+            else:
                 mid = n // 2
-                if n <= 1:
-                    raise
                 parts = (self._scan_sub(ci, slot.bases.array, batch.offsets, 0, mid)
                          + self._scan_sub(ci, slot.bases.array, batch.offsets, mid, n))
             passes = []
@@ -227,34 +250,55 @@ class _BatchView:
         return self.b.record_text(self.lo + i)
 
 
-def scan_file(path: str, cfgs: Sequence[ScanConfig], sink: Callable[[BatchResult], None], *,
-              devices: Sequence[int] = (0,), threads: int = 0, max_batch_bases: int = 1 << 28,
-              max_batch_reads: int = 1 << 17, depth: int = 3, max_pass_reads: int = 0,
-              rawcount_capacity: int = 0, records_cfg: int | None = None, keep_ids=None,
-              context_factory=None) -> FileStats:
-    """Scan every read of `path` under each config in `cfgs` (one parse, one pass).
+class Scanner:
+    """Contexts + pinned batch rings on a set of devices, reusable across files (creating them costs
+    far more than scanning a small file).  `scan_file` may be called any number of times."""
 
-    `sink(BatchResult)` is called in file order; BatchResult.passes[k] holds the TRC-pass
-    reads under cfgs[k].  `records_cfg=k` attaches the SeqIO.write text of the reads passing
-    cfgs[k].  `keep_ids` restricts the harvest to those read ids (`--read_check`)."""
-    context_factory = context_factory or make_context
-    if not max_pass_reads:
-        max_pass_reads = max(1024, max_batch_reads // 8)
-    if not rawcount_capacity and any(c.want_rawcount for c in cfgs):
-        per_read = max(windows_per_read(c) * len(c.patterns) for c in cfgs if c.want_rawcount)
-        rawcount_capacity = max(1 << 20, min(1 << 30, per_read * max_pass_reads))
-    stats = FileStats()
-    ordered = _OrderedSink(sink)
-    fx = fastx.FastxFile(path, threads=threads)
-    stats.format_name = fx.format_name
-    reader_lock = threading.Lock()
-    seq_counter = [0]
-    errors = []
-    workers = []
-    try:
-        for d in devices:
-            workers.append(_DeviceWorker(d, cfgs, max_batch_reads, max_batch_bases, depth, max_pass_reads,
-                                         rawcount_capacity, context_factory))
+    def __init__(self, cfgs: Sequence[ScanConfig], *, devices: Sequence[int] = (0,), threads: int = 0,
+                 max_batch_bases: int = 1 << 28, max_batch_reads: int = 1 << 17, depth: int = 3,
+                 max_pass_reads: int = 0, rawcount_capacity: int = 0, context_factory=None):
+        context_factory = context_factory or make_context
+        if not max_pass_reads:
+            max_pass_reads = max(1024, max_batch_reads // 8)
+        if not rawcount_capacity and any(c.want_rawcount for c in cfgs):
+            per_read = max(windows_per_read(c) * len(c.patterns) for c in cfgs if c.want_rawcount)
+            rawcount_capacity = max(1 << 20, min(1 << 30, per_read * max_pass_reads))
+        self.cfgs = list(cfgs)
+        self.threads = threads
+        self.workers = []
+        try:
+            for d in devices:
+                self.workers.append(_DeviceWorker(d, self.cfgs, max_batch_reads, max_batch_bases, depth,
+                                                  max_pass_reads, rawcount_capacity, context_factory))
+        except BaseException:
+            self.close()
+            raise
+
+    def close(self):
+        for w in self.workers:
+            w.close()
+        self.workers = []
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def scan_file(self, path: str, sink: Callable[[BatchResult], None], *, records_cfg: int | None = None,
+                  keep_ids=None) -> FileStats:
+        """Scan every read of `path` under each config (one parse, one pass).
+
+        `sink(BatchResult)` is called in file order; BatchResult.passes[k] holds the TRC-pass reads
+        under cfgs[k].  `records_cfg=k` attaches the SeqIO.write text of the reads passing cfgs[k].
+        `keep_ids` restricts the harvest to those read ids (`--read_check`)."""
+        stats = FileStats()
+        ordered = _OrderedSink(sink)
+        fx = fastx.FastxFile(path, threads=self.threads)
+        stats.format_name = fx.format_name
+        reader_lock = threading.Lock()
+        seq_counter = [0]
+        errors = []
 
         def run(w: _DeviceWorker):
             inflight = []
@@ -280,28 +324,34 @@ def scan_file(path: str, cfgs: Sequence[ScanConfig], sink: Callable[[BatchResult
                         break
                     nb = batch.n_bases
                     off = batch.offsets[:batch.n_reads + 1]
-                    bids = [c.submit(slot.bases.array[:nb], off) for c in w.ctxs]
-                    inflight.append((slot, batch, bids, seq))
+                    bid = w.submit(slot.bases.array[:nb], off)
+                    inflight.append((slot, batch, bid, seq))
                 while inflight and not errors:
                     ordered.put(w.finish(inflight.pop(0), records_cfg, keep_ids))
             except BaseException as e:  # noqa: BLE001 - reported to the caller below
                 errors.append(e)
 
-        if len(workers) == 1:
-            run(workers[0])
-        else:
-            ths = [threading.Thread(target=run, args=(w,), name=f"tps-dev{w.device}") for w in workers]
-            for t in ths:
-                t.start()
-            for t in ths:
-                t.join()
-        if errors:
-            raise errors[0]
-    finally:
-        for w in workers:
-            w.close()
-        fx.close()
-    return stats
+        try:
+            if len(self.workers) == 1:
+                run(self.workers[0])
+            else:
+                ths = [threading.Thread(target=run, args=(w,), name=f"tps-dev{w.device}") for w in self.workers]
+                for t in ths:
+                    t.start()
+                for t in ths:
+                    t.join()
+            if errors:
+                raise errors[0]
+        finally:
+            fx.close()
+        return stats
+
+
+def scan_file(path: str, cfgs: Sequence[ScanConfig], sink: Callable[[BatchResult], None], *,
+              records_cfg: int | None = None, keep_ids=None, **scanner_kw) -> FileStats:
+    """One-shot convenience: Scanner(cfgs, **scanner_kw).scan_file(path, sink, ...)."""
+    with Scanner(cfgs, **scanner_kw) as sc:
+        return sc.scan_file(path, sink, records_cfg=records_cfg, keep_ids=keep_ids)
 
 
 def collect_file(path: str, cfgs: Sequence[ScanConfig], **kw):

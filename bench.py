@@ -342,7 +342,7 @@ def main():
             assert st.n_reads == reads_per_step and st.n_bases == nbases[0]
             e2e_file = {"value": p_bases / p_wall / 1e9, "unit": UNIT, "file_bytes": fsize, "passes": a.parse_passes,
                         "ms_per_pass": p_wall / a.parse_passes * 1e3, "host_threads": len(os.sched_getaffinity(0)),
-                        "trc_pass_reads": len(got),
+                        "trc_pass_reads": len(got), "host_seconds_last_pass": {k: round(v, 4) for k, v in st.timing.items()},
                         "what": "uncompressed FASTQ in page cache -> telomere rows (parse + PCIe + kernels + harvest)"}
         finally:
             if os.path.exists(path):

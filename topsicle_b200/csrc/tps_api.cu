@@ -140,7 +140,7 @@ const char *tps_last_error(const tps_ctx *ctx) { return ctx ? ctx->err : g_creat
 
 void *tps_alloc_pinned(size_t bytes) {
   void *p = nullptr;
-  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
     cudaGetLastError();
     return nullptr;
   }

@@ -87,6 +87,13 @@ typedef struct tps_fastx {
 
 static __thread char g_open_err[256];
 
+#include <time.h>
+static double dbg_now(void) {
+  struct timespec t;
+  clock_gettime(CLOCK_MONOTONIC, &t);
+  return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec;
+}
+
 static int fx_fail(tps_fastx *fx, int code, const char *fmt, ...) {
   char *dst = fx ? fx->err : g_open_err;
   va_list ap;
@@ -171,8 +178,18 @@ static void index_fastq(const uint8_t *w, uint64_t from, uint64_t seg_end, uint6
     uint64_t e3 = line_end(w, p0, win_end, &nl);
     if (!nl) break;
     uint64_t q0 = e3 + 1;
-    uint64_t e4 = q0 <= win_end ? line_end(w, q0, win_end, &nl) : win_end;
-    if (!nl && !final) break; /* quality line may continue in the next window */
+    uint64_t e4;
+    /* The quality line is as long as the sequence line: jump over it instead of scanning it (half of
+     * a FASTQ file is quality text).  Accepted only if a newline sits exactly there and the next line
+     * starts a record (or the window ends); anything else takes the scanning path, which validates. */
+    const uint64_t j = q0 + (e2 - s0);
+    if (j < win_end && w[j] == '\n' && (j + 1 == win_end || w[j + 1] == '@' || w[j + 1] == '\n')) {
+      e4 = j;
+      nl = 1;
+    } else {
+      e4 = q0 <= win_end ? line_end(w, q0, win_end, &nl) : win_end;
+      if (!nl && !final) break; /* quality line may continue in the next window */
+    }
     tps_fastx_rec r;
     memset(&r, 0, sizeof(r));
     set_title(&r, w, p + 1, e1 - (p + 1));
@@ -294,10 +311,48 @@ static uint64_t find_fasta_start(const uint8_t *w, uint64_t a, uint64_t win_end)
   return win_end;
 }
 
+/* Copy with non-temporal stores: the destination (a pinned batch buffer, GBs per batch) is only read
+ * back by the DMA engine, so it should not displace the file text from the caches nor cost a
+ * read-for-ownership of every line. */
+#if defined(__x86_64__)
+#include <immintrin.h>
+__attribute__((target("avx2"))) static void copy_stream_avx2(uint8_t *dst, const uint8_t *src, size_t n) {
+  size_t head = (32u - ((uintptr_t)dst & 31u)) & 31u;
+  if (head > n) head = n;
+  memcpy(dst, src, head);
+  dst += head;
+  src += head;
+  n -= head;
+  size_t i = 0;
+  for (; i + 128 <= n; i += 128) {
+    __m256i a = _mm256_loadu_si256((const __m256i *)(src + i));
+    __m256i b = _mm256_loadu_si256((const __m256i *)(src + i + 32));
+    __m256i c = _mm256_loadu_si256((const __m256i *)(src + i + 64));
+    __m256i d = _mm256_loadu_si256((const __m256i *)(src + i + 96));
+    _mm256_stream_si256((__m256i *)(dst + i), a);
+    _mm256_stream_si256((__m256i *)(dst + i + 32), b);
+    _mm256_stream_si256((__m256i *)(dst + i + 64), c);
+    _mm256_stream_si256((__m256i *)(dst + i + 96), d);
+  }
+  for (; i + 32 <= n; i += 32) _mm256_stream_si256((__m256i *)(dst + i), _mm256_loadu_si256((const __m256i *)(src + i)));
+  memcpy(dst + i, src + i, n - i);
+}
+static int g_have_avx2 = -1;
+static inline void copy_stream(uint8_t *dst, const uint8_t *src, size_t n) {
+  if (g_have_avx2 < 0) g_have_avx2 = __builtin_cpu_supports("avx2") ? 1 : 0;
+  if (g_have_avx2 && n >= 256) copy_stream_avx2(dst, src, n);
+  else memcpy(dst, src, n);
+}
+static inline void copy_fence(void) { _mm_sfence(); }
+#else
+static inline void copy_stream(uint8_t *dst, const uint8_t *src, size_t n) { memcpy(dst, src, n); }
+static inline void copy_fence(void) {}
+#endif
+
 /* copy the bases of record r to dst (r->seq_len bytes) */
 static void gather_seq(const uint8_t *w, const tps_fastx_rec *r, uint8_t *dst) {
   if (!(r->flags & 1u)) {
-    memcpy(dst, w + r->seq_off, r->seq_len);
+    copy_stream(dst, w + r->seq_off, r->seq_len);
     return;
   }
   uint64_t q = r->seq_off, end = r->seq_off + r->seq_raw_len, o = 0;
@@ -477,10 +532,26 @@ int tps_fastx_open(tps_fastx **out, const char *path, int threads) {
   return TPS_FX_OK;
 }
 
+/* Dropping the page-table entries of a multi-GB mapping is the expensive part of munmap and runs on
+ * one thread under the exclusive mm lock; madvise(MADV_DONTNEED) does the same work under the shared
+ * lock, so it can be spread over the parser threads first (the page cache itself is untouched). */
+static void unmap_parallel(const uint8_t *map, uint64_t len, int threads) {
+  const uint64_t chunk = 32ull << 20;
+  const int64_t n = (int64_t)((len + chunk - 1) / chunk);
+  if (threads > 1 && n > 1) {
+#pragma omp parallel for num_threads(threads) schedule(dynamic, 1)
+    for (int64_t i = 0; i < n; ++i) {
+      uint64_t a = (uint64_t)i * chunk, b = a + chunk < len ? a + chunk : len;
+      madvise((void *)(map + a), b - a, MADV_DONTNEED);
+    }
+  }
+  munmap((void *)map, len);
+}
+
 void tps_fastx_close(tps_fastx *fx) {
   if (!fx) return;
   if (fx->gz) gzclose(fx->gz);
-  if (fx->map) munmap((void *)fx->map, fx->map_len);
+  if (fx->map) unmap_parallel(fx->map, fx->map_len, fx->threads);
   if (fx->fd >= 0) close(fx->fd);
   free(fx->carry);
   free(fx);
@@ -553,7 +624,9 @@ int tps_fastx_next(tps_fastx *fx, uint64_t bases_cap, uint32_t reads_cap, uint8_
       w = chunk;
       final = fx->gz_eof;
     }
+    double t_ix = dbg_now();
     int rc = index_window(fx, w, win, final, &rv);
+    if (getenv("TPS_FX_DEBUG")) fprintf(stderr, "[fastx] index %.1f MB in %.4f s, %zu records\n", win / 1e6, dbg_now() - t_ix, rv.n);
     if (rc) {
       free(chunk);
       return rc;
@@ -588,8 +661,14 @@ int tps_fastx_next(tps_fastx *fx, uint64_t bases_cap, uint32_t reads_cap, uint8_
   else consumed = rv.v[n].title_off - 1; /* start of the first record left for the next call */
   if (n) memcpy(recs_out, rv.v, (size_t)n * sizeof(tps_fastx_rec));
   int T = fx->threads;
-#pragma omp parallel for num_threads(T) schedule(dynamic, 16) if (nb > (8u << 20))
-  for (int64_t i = 0; i < (int64_t)n; ++i) gather_seq(w, &rv.v[i], bases_out + offsets_out[i]);
+  double t_g = dbg_now();
+#pragma omp parallel num_threads(T) if (nb > (8u << 20))
+  {
+#pragma omp for schedule(dynamic, 16)
+    for (int64_t i = 0; i < (int64_t)n; ++i) gather_seq(w, &rv.v[i], bases_out + offsets_out[i]);
+    copy_fence(); /* non-temporal stores are visible before the batch is handed to the DMA engine */
+  }
+  if (getenv("TPS_FX_DEBUG")) fprintf(stderr, "[fastx] gather %.1f MB in %.4f s\n", nb / 1e6, dbg_now() - t_g);
   free(rv.v);
   if (!fx->is_gz) {
     *raw_base = w;

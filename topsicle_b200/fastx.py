@@ -150,13 +150,16 @@ class FastxFile:
         self._lib.tps_fastx_set_window(self._h, nbytes)
 
     def next_batch(self, bases: np.ndarray, offsets: np.ndarray, max_reads: int | None = None,
-                   max_bases: int | None = None) -> Batch | None:
+                   max_bases: int | None = None, recs: np.ndarray | None = None) -> Batch | None:
         """Fill `bases` (uint8) / `offsets` (uint64, >= max_reads + 1) with the next reads of the
         file; returns None at end of file."""
         assert bases.dtype == np.uint8 and offsets.dtype == np.uint64
         reads_cap = min(len(offsets) - 1, max_reads if max_reads is not None else 1 << 31)
         bases_cap = min(bases.size, max_bases if max_bases is not None else 1 << 62)
-        recs = np.empty(reads_cap, dtype=REC_DTYPE)
+        if recs is None:
+            recs = np.empty(reads_cap, dtype=REC_DTYPE)
+        else:
+            reads_cap = min(reads_cap, len(recs))
         n = C.c_uint32(0)
         raw, owner = C.c_void_p(), C.c_void_p()
         rc = self._lib.tps_fastx_next(self._h, bases_cap, reads_cap, bases.ctypes.data, offsets.ctypes.data,

@@ -17,7 +17,9 @@ exactly as the reference writes them.
 """
 from __future__ import annotations
 
+import queue
 import threading
+import time
 from dataclasses import dataclass, field
 from typing import Callable, Sequence
 
@@ -79,6 +81,7 @@ class FileStats:
     n_scanned: int = 0
     n_batches: int = 0
     format_name: str = ""
+    timing: dict = field(default_factory=dict)   # seconds: open, parse (reader thread), submit, wait, harvest, close
 
 
 class _OrderedSink:
@@ -102,6 +105,7 @@ class _Slot:
     def __init__(self, max_bases, max_reads):
         self.bases = engine.PinnedBuffer(max_bases)
         self.offsets = engine.PinnedBuffer((max_reads + 1) * 8)
+        self.recs = np.empty(max_reads, dtype=fastx.REC_DTYPE)
 
     def free(self):
         self.bases.free()
@@ -291,59 +295,100 @@ class Scanner:
 
         `sink(BatchResult)` is called in file order; BatchResult.passes[k] holds the TRC-pass reads
         under cfgs[k].  `records_cfg=k` attaches the SeqIO.write text of the reads passing cfgs[k].
-        `keep_ids` restricts the harvest to those read ids (`--read_check`)."""
+        `keep_ids` restricts the harvest to those read ids.
+
+        Threads: one reader (the C parser, itself multi-threaded, fills free pinned slots) and one
+        worker per device (submit / wait / harvest), so parsing, PCIe and the kernels overlap."""
         stats = FileStats()
         ordered = _OrderedSink(sink)
+        tm = stats.timing
+        for k in ("open", "parse", "submit", "finish", "close"):
+            tm[k] = 0.0
+        t_open = time.perf_counter()
         fx = fastx.FastxFile(path, threads=self.threads)
+        tm["open"] = time.perf_counter() - t_open
         stats.format_name = fx.format_name
-        reader_lock = threading.Lock()
-        seq_counter = [0]
         errors = []
+        ready = queue.Queue()
+        free = queue.Queue()
+        for w in self.workers:
+            for slot in w.slots:
+                free.put(slot)
+        n_workers = len(self.workers)
+        w0 = self.workers[0]
 
-        def run(w: _DeviceWorker):
-            inflight = []
-            free = list(w.slots)
+        def read_loop():
+            seq = 0
             try:
                 while not errors:
-                    if not free:
-                        item = inflight.pop(0)
-                        ordered.put(w.finish(item, records_cfg, keep_ids))
-                        free.append(item[0])
-                    slot = free.pop()
-                    with reader_lock:
-                        batch = fx.next_batch(slot.bases.array, slot.offsets.array.view(np.uint64),
-                                              max_reads=w.max_batch_reads, max_bases=w.max_batch_bases)
-                        if batch is not None:
-                            seq = seq_counter[0]
-                            seq_counter[0] += 1
-                            stats.n_reads += batch.n_reads
-                            stats.n_bases += batch.n_bases
-                            stats.n_batches += 1
-                    if batch is None:
-                        free.append(slot)
+                    slot = free.get()
+                    if slot is None:
                         break
-                    nb = batch.n_bases
-                    off = batch.offsets[:batch.n_reads + 1]
-                    bid = w.submit(slot.bases.array[:nb], off)
-                    inflight.append((slot, batch, bid, seq))
-                while inflight and not errors:
-                    ordered.put(w.finish(inflight.pop(0), records_cfg, keep_ids))
+                    t = time.perf_counter()
+                    batch = fx.next_batch(slot.bases.array, slot.offsets.array.view(np.uint64),
+                                          max_reads=w0.max_batch_reads, max_bases=w0.max_batch_bases,
+                                          recs=slot.recs)
+                    tm["parse"] += time.perf_counter() - t
+                    if batch is None:
+                        break
+                    stats.n_reads += batch.n_reads
+                    stats.n_bases += batch.n_bases
+                    stats.n_batches += 1
+                    ready.put((slot, batch, seq))
+                    seq += 1
             except BaseException as e:  # noqa: BLE001 - reported to the caller below
                 errors.append(e)
+            finally:
+                for _ in range(n_workers):
+                    ready.put(None)
 
+        def work_loop(w: _DeviceWorker):
+            inflight = []
+            depth = len(w.slots)
+            try:
+                while not errors:
+                    if inflight and (len(inflight) >= depth or ready.empty()):
+                        item = inflight.pop(0)
+                        t = time.perf_counter()
+                        ordered.put(w.finish(item, records_cfg, keep_ids))
+                        tm["finish"] += time.perf_counter() - t
+                        free.put(item[0])
+                        continue
+                    got = ready.get()
+                    if got is None:
+                        break
+                    slot, batch, seq = got
+                    nb = batch.n_bases
+                    t = time.perf_counter()
+                    bid = w.submit(slot.bases.array[:nb], batch.offsets[:batch.n_reads + 1])
+                    tm["submit"] += time.perf_counter() - t
+                    inflight.append((slot, batch, bid, seq))
+                while inflight and not errors:
+                    item = inflight.pop(0)
+                    t = time.perf_counter()
+                    ordered.put(w.finish(item, records_cfg, keep_ids))
+                    tm["finish"] += time.perf_counter() - t
+                    free.put(item[0])
+            except BaseException as e:  # noqa: BLE001
+                errors.append(e)
+                free.put(None)   # unblock the reader
+
+        reader = threading.Thread(target=read_loop, name="tps-reader")
+        ths = [threading.Thread(target=work_loop, args=(w,), name=f"tps-dev{w.device}") for w in self.workers]
         try:
-            if len(self.workers) == 1:
-                run(self.workers[0])
-            else:
-                ths = [threading.Thread(target=run, args=(w,), name=f"tps-dev{w.device}") for w in self.workers]
-                for t in ths:
-                    t.start()
-                for t in ths:
-                    t.join()
+            reader.start()
+            for t in ths:
+                t.start()
+            for t in ths:
+                t.join()
+            free.put(None)
+            reader.join()
             if errors:
                 raise errors[0]
         finally:
+            t_close = time.perf_counter()
             fx.close()
+            tm["close"] = time.perf_counter() - t_close
         return stats
 
 

@@ -53,6 +53,9 @@ struct tps_ctx {
   uint32_t cw_stride = 0, max_pass = 0;
   int kt = 0; /* template K of the K2/K3 instantiation in use (0 = generic) */
   void (*k2_fn)(const TpsScanArgs, const TpsPatTable) = nullptr;
+  void (*k2r_fn)(const TpsScanArgs, const TpsPatTable) = nullptr; /* register-staged K2 (no_bp <= 1000, P <= 32) */
+  bool k2_reg = false;
+  uint32_t k2r_smem = 0;
   void (*k3_fn)(const TpsScanArgs, const TpsPatTable) = nullptr;
   int k1_grid = 0, k1_unroll = 4;
   void (*k1_fn)(const uint4 *, uint32_t *, uint32_t *, uint16_t *, uint64_t) = nullptr;
@@ -133,7 +136,7 @@ extern "C" {
 int tps_abi_version(void) { return TPS_ABI_VERSION; }
 
 const char *tps_build_info(void) {
-  return "topsicle_b200 sm_100a; kernels: tps_pack_kernel, tps_trc_kernel<K>, tps_window_kernel<K>, tps_changepoint_kernel; " __DATE__;
+  return "topsicle_b200 sm_100a; kernels: tps_pack_kernel, tps_trc_reg_kernel<K>, tps_trc_kernel<K>, tps_window_kernel<K>, tps_changepoint_kernel; " __DATE__;
 }
 
 const char *tps_last_error(const tps_ctx *ctx) { return ctx ? ctx->err : g_create_error; }
@@ -236,16 +239,18 @@ int tps_create(tps_ctx **out, int device, const tps_params *params) {
   for (uint32_t i = 0; i < pt.n; ++i) kmax = pt.len[i] > kmax ? pt.len[i] : kmax;
   ctx->kt = (kmin == kmax && kmax <= 8) ? (int)kmax : 0;
   switch (ctx->kt) {
-#define TPS_PICK(KK) case KK: ctx->k2_fn = tps_trc_kernel<KK>; ctx->k3_fn = tps_window_kernel<KK>; break;
+#define TPS_PICK(KK) case KK: ctx->k2_fn = tps_trc_kernel<KK>; ctx->k2r_fn = tps_trc_reg_kernel<KK>; ctx->k3_fn = tps_window_kernel<KK>; break;
     TPS_PICK(1) TPS_PICK(2) TPS_PICK(3) TPS_PICK(4) TPS_PICK(5) TPS_PICK(6) TPS_PICK(7) TPS_PICK(8)
 #undef TPS_PICK
-    default: ctx->k2_fn = tps_trc_kernel<0>; ctx->k3_fn = tps_window_kernel<0>; break;
+    default: ctx->k2_fn = tps_trc_kernel<0>; ctx->k2r_fn = tps_trc_reg_kernel<0>; ctx->k3_fn = tps_window_kernel<0>; break;
   }
   const uint32_t pm_words = 2 * pt.n * (ctx->kt > 0 ? (uint32_t)ctx->kt : 1u);
   /* K2 geometry */
   ctx->k2_lin_words = lin_words_for(p.no_bp);
   ctx->k2_nq_max = (p.no_bp + 31) / 32;
   ctx->k2_smem = (pm_words + TPS_K2_WARPS * (3 * ctx->k2_lin_words + pt.n_bordered * ctx->k2_nq_max + TPS_MAX_PATTERNS)) * 4;
+  ctx->k2_reg = p.no_bp <= 1000 && pt.n <= 32 && !getenv("TPS_K2_SMEM_PATH");
+  ctx->k2r_smem = (pm_words + TPS_K2R_WARPS * pt.n_bordered * 32) * 4;
   /* K3 geometry: a tile stages tile_bases + W positions; keep that <= 4096 (128 words) when W allows */
   const uint32_t w32 = (p.window_size + 31) / 32 * 32;
   ctx->k3_tile_bases = w32 + 1024 <= 4096 ? 4096 - w32 : 1024;
@@ -254,7 +259,8 @@ int tps_create(tps_ctx **out, int device, const tps_params *params) {
   ctx->k3_tile_words = (tile_n + 31) / 32 + 1;
   ctx->k3_tiles_max = (uint32_t)((reg_max + ctx->k3_tile_bases - 1) / ctx->k3_tile_bases);
   if (ctx->k3_tiles_max == 0) ctx->k3_tiles_max = 1;
-  ctx->k3_smem = (pm_words + 3 * ctx->k3_lin_words + 3 * ctx->k3_tile_words + pt.n * ctx->k3_tile_words) * 4;
+  ctx->k3_smem = (pm_words + 3 * ctx->k3_lin_words + 3 * ctx->k3_tile_words + 1 + 2 * pt.n * ctx->k3_tile_words +
+                  pt.n_bordered * ctx->k3_tile_words) * 4;
   ctx->cw_stride = (uint32_t)(nw_max ? nw_max : 1);
   ctx->max_pass = p.max_pass_reads ? p.max_pass_reads : p.max_batch_reads;
   if (ctx->max_pass > p.max_batch_reads) ctx->max_pass = p.max_batch_reads;
@@ -272,6 +278,8 @@ int tps_create(tps_ctx **out, int device, const tps_params *params) {
   }
   TPS_CC(cudaFuncSetAttribute(ctx->k2_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->k2_smem));
   TPS_CC(cudaFuncSetAttribute(ctx->k3_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->k3_smem));
+  if (ctx->k2r_smem > 48 * 1024)
+    TPS_CC(cudaFuncSetAttribute(ctx->k2r_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->k2r_smem));
   int occ1 = 0, occ3 = 0, occ4 = 0;
   {
     const char *e = getenv("TPS_K1_UNROLL"); /* tuning knob: 2, 4 (default) or 8 tiles in flight per warp */
@@ -374,7 +382,10 @@ int enqueue_scan(tps_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t *d_bases,
   a.nq_max = ctx->k2_nq_max;
   if (n_reads) {
     a.lin_words = ctx->k2_lin_words;
-    ctx->k2_fn<<<(n_reads + TPS_K2_WARPS - 1) / TPS_K2_WARPS, TPS_K2_WARPS * 32, ctx->k2_smem, st>>>(a, ctx->pt);
+    if (ctx->k2_reg)
+      ctx->k2r_fn<<<(n_reads + TPS_K2R_WARPS - 1) / TPS_K2R_WARPS, TPS_K2R_WARPS * 32, ctx->k2r_smem, st>>>(a, ctx->pt);
+    else
+      ctx->k2_fn<<<(n_reads + TPS_K2_WARPS - 1) / TPS_K2_WARPS, TPS_K2_WARPS * 32, ctx->k2_smem, st>>>(a, ctx->pt);
     ctx->launches++;
   }
   if (timed) TPS_CUDA(ctx, cudaEventRecord(ev[2], st));

@@ -406,26 +406,190 @@ tps_trc_kernel(const TpsScanArgs a, const TpsPatTable pt) {
   if (lane == 0) a.rows[r] = row;
 }
 
+/* ---------------------------------------------------------------------- K2, register-staged
+ * Fast path of step 1 for no_bp <= 1000 and <= 32 literals (every CLI run: no_bp is 1000,
+ * main.py:57).  The slice of one read end (<= 1000 bases + <= 15 bases of group misalignment
+ * <= 1024) fits one 32-bit word of each bit plane per lane, so staging needs no shared memory:
+ * lane l converts groups 2l, 2l+1 to linear planes in registers, the oriented words come from
+ * warp shuffles, every literal costs one LOP3 chain + POPC + REDUX, the first maximum is one
+ * REDUX.MAX over (count << 8 | 255 - index).  Only self-overlapping literals still write their
+ * match row to shared memory for the greedy walk. */
+template <int K>
+__device__ __forceinline__ void tps_trc_end_reg(const TpsScanArgs &a, const TpsPatTable &pt, const uint2 *pm,
+                                                uint64_t g0, uint32_t n, bool rev, uint32_t *mrows,
+                                                uint32_t lane, uint32_t &best, uint32_t &bestp) {
+  const uint32_t phase = (uint32_t)(g0 & 15u);
+  const uint64_t gfirst = g0 >> 4;
+  const uint32_t ng = n ? (uint32_t)(((g0 + n + 15) >> 4) - gfirst) : 0u; /* <= 64 */
+  /* linear planes of bases [16*gfirst + 32*lane, +32): bit x of the slice is linear bit phase + x */
+  uint32_t L0 = 0u, L1 = 0u, LV = 0u;
+#pragma unroll
+  for (uint32_t h = 0; h < 2u; ++h) {
+    const uint32_t gi = 2u * lane + h;
+    if (gi < ng) {
+      const uint64_t g = gfirst + gi;
+      const uint32_t y = tps_linear_planes(__ldg(a.pk.codes + g));
+      const uint32_t fw = __ldg(a.pk.flags + (g >> 5));
+      const uint32_t v = ((fw >> (g & 31)) & 1u) ? (uint32_t)__ldg(a.pk.masks + g) : 0xFFFFu;
+      L0 |= (y & 0xFFFFu) << (16u * h);
+      L1 |= (y >> 16) << (16u * h);
+      LV |= v << (16u * h);
+    }
+  }
+  /* oriented word `lane`: positions 32*lane .. 32*lane+31 of the (reversed) slice */
+  uint32_t a0, a1, av;
+  if (!rev) {
+    uint32_t n0 = __shfl_down_sync(TPS_FULL, L0, 1), n1 = __shfl_down_sync(TPS_FULL, L1, 1),
+             nv = __shfl_down_sync(TPS_FULL, LV, 1);
+    if (lane == 31u) n0 = n1 = nv = 0u;
+    a0 = __funnelshift_r(L0, n0, phase);
+    a1 = __funnelshift_r(L1, n1, phase);
+    av = __funnelshift_r(LV, nv, phase);
+  } else {
+    /* reversed position j is slice base n-1-j: word `lane` is the bit-reversal of the 32 linear bits
+     * starting at o = phase + n - 32*lane - 32 (o < 0: the part below bit 0 is masked out below) */
+    const int32_t o = (int32_t)(phase + n) - 32 * (int32_t)lane - 32;
+    const int32_t idx = o >> 5; /* floor; >= -1 for every word that holds slice bases */
+    const uint32_t sh = (uint32_t)o & 31u;
+    const int lo_src = idx & 31, hi_src = (idx + 1) & 31;
+    uint32_t l0 = __shfl_sync(TPS_FULL, L0, lo_src), l1 = __shfl_sync(TPS_FULL, L1, lo_src),
+             lv = __shfl_sync(TPS_FULL, LV, lo_src);
+    uint32_t h0 = __shfl_sync(TPS_FULL, L0, hi_src), h1 = __shfl_sync(TPS_FULL, L1, hi_src),
+             hv = __shfl_sync(TPS_FULL, LV, hi_src);
+    if (idx < 0) l0 = l1 = lv = 0u;
+    if (idx + 1 < 0 || idx + 1 > 31) h0 = h1 = hv = 0u;
+    a0 = __brev(__funnelshift_r(l0, h0, sh));
+    a1 = __brev(__funnelshift_r(l1, h1, sh));
+    av = __brev(__funnelshift_r(lv, hv, sh));
+  }
+  {
+    const uint32_t done = 32u * lane;
+    const uint32_t rem = n > done ? n - done : 0u;
+    av &= rem >= 32u ? TPS_FULL : ((1u << rem) - 1u);
+  }
+  uint32_t b0 = __shfl_down_sync(TPS_FULL, a0, 1), b1 = __shfl_down_sync(TPS_FULL, a1, 1),
+           bv = __shfl_down_sync(TPS_FULL, av, 1);
+  if (lane == 31u) b0 = b1 = bv = 0u;
+  TpsWin<K> win;
+  tps_win_init<K>(win, a0, b0, a1, b1, av, bv);
+  const uint32_t nq = (n + 31u) >> 5;
+  uint32_t mine = 0u; /* count of literal `lane` */
+  for (uint32_t p = 0; p < pt.n; ++p) {
+    const uint32_t M = tps_win_match<K>(win, pm, pt, p);
+    if (pt.bordered[p]) { /* warp-uniform */
+      if (lane < nq) mrows[pt.brow[p] * 32u + lane] = M;
+    } else {
+      const uint32_t c = __reduce_add_sync(TPS_FULL, tps_popc32(M));
+      if (lane == p) mine = c;
+    }
+  }
+  if (pt.n_bordered) {
+    __syncwarp();
+    if (lane < pt.n && pt.bordered[lane]) {
+      const uint32_t k = pt.len[lane];
+      mine = (n >= k) ? tps_greedy_count(mrows + pt.brow[lane] * 32u, 0, (int32_t)(n - k), k) : 0u;
+    }
+    __syncwarp();
+  }
+  /* first maximum in literal order (allsteps.py:190-191): max over (count, -index) */
+  const uint32_t key = lane < pt.n ? ((mine << 8) | (255u - lane)) : 0u;
+  const uint32_t kmax = __reduce_max_sync(TPS_FULL, key);
+  best = kmax >> 8;
+  bestp = best ? 255u - (kmax & 255u) : 0u;
+}
+
+#define TPS_K2R_WARPS 8
+
+/* dynamic shared memory (words): pm[2 * P * max(K,1)] | per warp: mrows[n_bordered * 32] */
+template <int K>
+__global__ void __launch_bounds__(TPS_K2R_WARPS * 32)
+tps_trc_reg_kernel(const TpsScanArgs a, const TpsPatTable pt) {
+  extern __shared__ uint32_t smem[];
+  constexpr uint32_t KS = K > 0 ? K : 1;
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  uint2 *pm = reinterpret_cast<uint2 *>(smem);
+  tps_build_pattern_masks(pm, pt, KS, threadIdx.x, TPS_K2R_WARPS * 32);
+  __syncthreads();
+  uint32_t *mrows = smem + 2u * pt.n * KS + warp * (pt.n_bordered * 32u);
+  const uint32_t r = blockIdx.x * TPS_K2R_WARPS + warp;
+  if (r >= a.n_reads) return;
+  const uint64_t off = a.offsets[r];
+  const uint32_t L = (uint32_t)(a.offsets[r + 1] - off);
+  tps_row row;
+  row.length = L;
+  row.status = TPS_ST_FILTERED;
+  row.tail = 0; row.best_pattern = 0; row.reserved0 = 0;
+  row.match_count = 0; row.head_max = 0; row.tail_max = 0; row.reserved1 = 0;
+  row.n_windows = 0; row.bkp = -1; row.telo_length = -1; row.reserved2 = 0;
+  row.rawcount_offset = ~0ull;
+  if (L > a.min_seq_length) { /* strict, allsteps.py:175 */
+    const uint32_t n = L < a.no_bp ? L : a.no_bp;
+    uint32_t ms, ps, me, pe;
+    tps_trc_end_reg<K>(a, pt, pm, off, n, false, mrows, lane, ms, ps);         /* seq[:no_bp] */
+    tps_trc_end_reg<K>(a, pt, pm, off + L - n, n, true, mrows, lane, me, pe);  /* seq[-no_bp:][::-1] */
+    bool fwd = ms > me; /* tie -> reverse, allsteps.py:193-198 */
+    if (a.flags & TPS_FLAG_FORCE_FORWARD) fwd = true;
+    if (a.flags & TPS_FLAG_FORCE_REVERSE) fwd = false;
+    const uint32_t cnt = fwd ? ms : me;
+    row.tail = fwd ? TPS_TAIL_FORWARD : TPS_TAIL_REVERSE;
+    row.best_pattern = (uint8_t)(fwd ? ps : pe);
+    row.match_count = (uint16_t)cnt;
+    row.head_max = (uint16_t)ms;
+    row.tail_max = (uint16_t)me;
+    row.status = cnt >= a.count_threshold ? TPS_ST_PASS : TPS_ST_BELOW;
+    if (row.status == TPS_ST_PASS && lane == 0 && !(a.flags & TPS_FLAG_STEP1_ONLY)) {
+      const uint32_t M = L < a.maxlengthtelo ? L : a.maxlengthtelo;
+      const uint32_t nreg = M > a.trimfirst ? M - a.trimfirst : 0u;
+      const uint32_t nW = nreg >= a.W ? (nreg - a.W) / a.slide + 1u : 0u;
+      row.n_windows = nW;
+      const uint32_t slot = atomicAdd(a.counters + 0, 1u);
+      if (slot < a.max_pass) {
+        a.pass_list[slot] = r;
+        if (a.want_rawcount && nW) {
+          const unsigned long long elems = (unsigned long long)nW * pt.n;
+          const unsigned long long at =
+              atomicAdd(reinterpret_cast<unsigned long long *>(a.counters + 2), elems);
+          if (at + elems <= a.raw_capacity) row.rawcount_offset = at;
+          else atomicOr(a.counters + 4, TPS_OVF_RAWCOUNT);
+        }
+      } else {
+        atomicOr(a.counters + 4, TPS_OVF_PASS);
+      }
+    }
+  }
+  if (lane == 0) a.rows[r] = row;
+}
+
 /* ------------------------------------------------------------------------------------ K3 */
 #define TPS_K3_THREADS 256
 #define TPS_K3_PSPLIT 2 /* literals of one 32-position word are split over this many threads */
 
 /* One work item = one tile of one passing read: window starts in [tb0, tb0 + tile_bases) of
  * the oriented region z = oriented[trimfirst : min(L, maxlengthtelo)].
+ *
+ * Per tile: (1) stage the tile + W-base halo as oriented bit planes, (2) one match word per
+ * (literal, 32 positions), stored next to (3) the running popcount of the literal's row up to
+ * that word, so that (4) a window's count of a border-free literal is two 64-bit shared-memory
+ * loads, two masked POPCs and a subtraction:
+ *     cnt = pre[qe] + popc(row[qe] & below(be)) - pre[q0] - popc(row[q0] & below(b0))
+ * with [ls, to] the window's start positions and e = to + 1.  Self-overlapping literals keep a
+ * plain copy of their row for the greedy walk (exactly re.finditer's non-overlapping count).
+ *
  * dynamic shared memory (words): pm[2*P*max(K,1)] | lin[3*lin_words] | ori[3*tile_words] |
- * mrows[P*tile_words] */
+ * rp[2*P*tile_words] (uint2 {row, prefix}) | brows[n_bordered*tile_words] */
 template <int K>
 __global__ void __launch_bounds__(TPS_K3_THREADS)
 tps_window_kernel(const TpsScanArgs a, const TpsPatTable pt) {
   extern __shared__ uint32_t smem[];
   __shared__ uint32_t s_item;
   constexpr uint32_t KS = K > 0 ? K : 1;
-  const uint32_t tid = threadIdx.x;
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const uint32_t lw = a.lin_words, tw = a.tile_words;
   uint2 *pm = reinterpret_cast<uint2 *>(smem);
   uint32_t *lin = smem + 2u * pt.n * KS;
   uint32_t *ori = lin + 3u * lw;
-  uint32_t *mrows = ori + 3u * tw;
+  uint2 *rp = reinterpret_cast<uint2 *>(ori + 3u * tw + ((3u * lw + 3u * tw) & 1u)); /* 8-byte aligned */
+  uint32_t *brows = reinterpret_cast<uint32_t *>(rp + (size_t)pt.n * tw);
   tps_build_pattern_masks(pm, pt, KS, tid, TPS_K3_THREADS);
   uint32_t n_pass = a.counters[0];
   if (n_pass > a.max_pass) n_pass = a.max_pass;
@@ -473,28 +637,87 @@ tps_window_kernel(const TpsScanArgs a, const TpsPatTable pt) {
       ori[2u * tw + q] = v;
     }
     __syncthreads();
-    for (uint32_t i = tid; i < nq * TPS_K3_PSPLIT; i += TPS_K3_THREADS) {
-      const uint32_t h = i / nq, q = i - h * nq;
-      TpsWin<K> win;
-      tps_win_init<K>(win, ori[q], ori[q + 1], ori[tw + q], ori[tw + q + 1], ori[2u * tw + q],
-                      ori[2u * tw + q + 1]);
-      for (uint32_t p = h; p < pt.n; p += TPS_K3_PSPLIT) mrows[p * tw + q] = tps_win_match<K>(win, pm, pt, p);
+    /* (2) match words; words past the staged slice are zero */
+    for (uint32_t i = tid; i < tw * TPS_K3_PSPLIT; i += TPS_K3_THREADS) {
+      const uint32_t h = i / tw, q = i - h * tw;
+      if (q < nq) {
+        TpsWin<K> win;
+        tps_win_init<K>(win, ori[q], ori[q + 1], ori[tw + q], ori[tw + q + 1], ori[2u * tw + q],
+                        ori[2u * tw + q + 1]);
+        for (uint32_t p = h; p < pt.n; p += TPS_K3_PSPLIT) {
+          const uint32_t Mw = tps_win_match<K>(win, pm, pt, p);
+          rp[p * tw + q].x = Mw;
+          if (pt.bordered[p]) brows[pt.brow[p] * tw + q] = Mw;
+        }
+      } else {
+        for (uint32_t p = h; p < pt.n; p += TPS_K3_PSPLIT) {
+          rp[p * tw + q].x = 0u;
+          if (pt.bordered[p]) brows[pt.brow[p] * tw + q] = 0u;
+        }
+      }
     }
     __syncthreads();
-    for (uint32_t w = wlo + tid; w < whi; w += TPS_K3_THREADS) {
-      const int32_t ls = (int32_t)(w * s - tb0);
-      uint32_t c = 0;
-      for (uint32_t p = 0; p < pt.n; ++p) {
-        const uint32_t k = pt.len[p];
-        uint32_t cnt = 0;
-        if (W - 1u >= k) {
-          const int32_t to = ls + (int32_t)(W - 1u - k);
-          cnt = pt.bordered[p] ? tps_greedy_count(mrows + p * tw, ls, to, k)
-                               : tps_range_popcount(mrows + p * tw, ls, to);
+    /* (3) exclusive running popcount per literal row: one warp per literal */
+    for (uint32_t p = warp; p < pt.n; p += TPS_K3_THREADS / 32) {
+      uint32_t carry = 0u;
+      for (uint32_t qb = 0; qb < tw; qb += 32u) {
+        const uint32_t q = qb + lane;
+        const uint32_t c = q < tw ? tps_popc32(rp[p * tw + q].x) : 0u;
+        uint32_t inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t up = __shfl_up_sync(TPS_FULL, inc, o);
+          if ((int)lane >= o) inc += up;
         }
-        if (cnt == 0u) cnt = 1u; /* `... or 1`, allsteps.py:281,288 */
-        c += cnt;
-        if (raw_off != ~0ull) a.raw[raw_off + (uint64_t)w * pt.n + p] = (uint8_t)cnt;
+        if (q < tw) rp[p * tw + q].y = carry + inc - c;
+        carry += __shfl_sync(TPS_FULL, inc, 31);
+      }
+    }
+    __syncthreads();
+    /* (4) windows */
+    for (uint32_t w = wlo + tid; w < whi; w += TPS_K3_THREADS) {
+      const uint32_t ls = w * s - tb0;
+      uint32_t c = 0;
+      if constexpr (K > 0) {
+        if (W - 1u >= (uint32_t)K) {
+          const uint32_t e = ls + (W - (uint32_t)K); /* one past the last start position */
+          const uint32_t q0 = ls >> 5, qe = e >> 5;
+          const uint32_t m0 = (1u << (ls & 31u)) - 1u, me = (1u << (e & 31u)) - 1u;
+          for (uint32_t p = 0; p < pt.n; ++p) {
+            uint32_t cnt;
+            if (pt.bordered[p]) {
+              cnt = tps_greedy_count(brows + pt.brow[p] * tw, (int32_t)ls, (int32_t)e - 1, (uint32_t)K);
+            } else {
+              const uint2 r0 = rp[p * tw + q0], re = rp[p * tw + qe];
+              cnt = re.y + tps_popc32(re.x & me) - r0.y - tps_popc32(r0.x & m0);
+            }
+            if (cnt == 0u) cnt = 1u; /* `... or 1`, allsteps.py:281,288 */
+            c += cnt;
+            if (raw_off != ~0ull) a.raw[raw_off + (uint64_t)w * pt.n + p] = (uint8_t)cnt;
+          }
+        } else {
+          c = pt.n; /* window text shorter than the literals: every count is floored to 1 */
+          if (raw_off != ~0ull)
+            for (uint32_t p = 0; p < pt.n; ++p) a.raw[raw_off + (uint64_t)w * pt.n + p] = 1u;
+        }
+      } else {
+        for (uint32_t p = 0; p < pt.n; ++p) {
+          const uint32_t k = pt.len[p];
+          uint32_t cnt = 0;
+          if (W - 1u >= k) {
+            const uint32_t e = ls + (W - k);
+            if (pt.bordered[p]) {
+              cnt = tps_greedy_count(brows + pt.brow[p] * tw, (int32_t)ls, (int32_t)e - 1, k);
+            } else {
+              const uint2 r0 = rp[p * tw + (ls >> 5)], re = rp[p * tw + (e >> 5)];
+              cnt = re.y + tps_popc32(re.x & ((1u << (e & 31u)) - 1u)) - r0.y -
+                    tps_popc32(r0.x & ((1u << (ls & 31u)) - 1u));
+            }
+          }
+          if (cnt == 0u) cnt = 1u;
+          c += cnt;
+          if (raw_off != ~0ull) a.raw[raw_off + (uint64_t)w * pt.n + p] = (uint8_t)cnt;
+        }
       }
       cw[w] = c;
     }

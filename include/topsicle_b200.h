@@ -149,6 +149,10 @@ int tps_batch_info(tps_ctx *ctx, uint64_t batch_id, uint32_t *n_pass_out, uint64
  * Enqueued on the context's stream 0; returns without synchronising. */
 int tps_scan_device(tps_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_offsets,
                     uint32_t n_reads, uint64_t n_bases, tps_row *d_rows_out);
+/* Same, on batch slot `slot` (0 .. n_slots-1): every slot has its own stream and scratch buffers, so
+ * scans of independent device-resident batches issued on different slots may overlap on the GPU. */
+int tps_scan_device_slot(tps_ctx *ctx, uint32_t slot, const uint8_t *d_bases, const uint64_t *d_offsets,
+                         uint32_t n_reads, uint64_t n_bases, tps_row *d_rows_out);
 int tps_sync(tps_ctx *ctx);
 
 /* CUDA-event timings (ms), recorded on the scan's own stream, of the tps_scan_device call

@@ -46,7 +46,7 @@ def _windows(s, window_size, step):
 
 
 def scan_shard(args):
-    """Reference-style scan of a list of read strings -> (n_scanned, n_pass, [telo_lengths])."""
+    """Reference-style scan of a list of (index, read string) -> (n_scanned, n_pass, [(index, tail, count, telo)])."""
     import ruptures as rpt  # restated 1.1.9 (oracle/shims)
     from oracle.topsicle_oracle import patterns_to_search
     seqs, pattern, phrase, cutoff, min_len, W, slide, trim, maxlen = args
@@ -55,7 +55,7 @@ def scan_shard(args):
     ratio = 1000 / len(pattern)
     passing = []
     n_scanned = 0
-    for seq in seqs:                                   # ---- step 1, allsteps.py:174-198
+    for gi, seq in seqs:                               # ---- step 1, allsteps.py:174-198
         if len(seq) > min_len:
             n_scanned += 1
             head = seq[:1000].upper()
@@ -69,11 +69,11 @@ def scan_shard(args):
             best_e = max(r[1] for r in rows)
             if best_s > best_e:
                 if best_s > cutoff:
-                    passing.append((seq, "forward"))
+                    passing.append((gi, seq, "forward", best_s))
             elif best_e > cutoff:
-                passing.append((seq, "reverse"))
+                passing.append((gi, seq, "reverse", best_e))
     telo = []
-    for seq, tail in passing:                          # ---- step 2, allsteps.py:263-315
+    for gi, seq, tail, trc in passing:                 # ---- step 2, allsteps.py:263-315
         m = min(maxlen, len(seq))
         s_fwd = seq[trim:m].upper()
         s_rev = seq[::-1].upper()[trim:m]
@@ -88,10 +88,10 @@ def scan_shard(args):
         x = [a + trim for a, _ in mean]
         y = [b for _, b in mean]
         if len(y) < 7:
-            telo.append(-1)
+            telo.append((gi, tail, trc, -1))
             continue
         res = rpt.Binseg(model="l2").fit(np.array(y)).predict(pen=4, n_bkps=1)
-        telo.append(int(x[res[0]]))
+        telo.append((gi, tail, trc, int(x[res[0]])))
     return n_scanned, len(passing), telo
 
 
@@ -99,9 +99,9 @@ def deal_shards(seqs, n):
     """n shards of (nearly) equal bases, reads kept in order inside a shard."""
     shards = [[] for _ in range(n)]
     load = [0] * n
-    for s in seqs:
+    for gi, s in enumerate(seqs):
         i = load.index(min(load))
-        shards[i].append(s)
+        shards[i].append((gi, s))
         load[i] += len(s)
     return shards
 
@@ -122,7 +122,8 @@ def time_sample(seqs, scan_kw, cores, steps=1, warmup=0):
             if it >= warmup:
                 times.append(dt)
     n_pass = sum(r[1] for r in last)
-    return times, n_pass
+    rows = sorted(t for r in last for t in r[2])
+    return times, n_pass, rows
 
 
 def main():
@@ -148,11 +149,12 @@ def main():
               min_len=cli.get("minSeqLength", 9000), W=cli.get("windowSize", 100),
               slide=cli.get("slide") or len(pattern), trim=cli.get("trimfirst", 100),
               maxlen=cli.get("maxlengthtelo", 20000))
-    times, n_pass = time_sample(seqs, kw, cores, a.steps, a.warmup)
+    times, n_pass, rows = time_sample(seqs, kw, cores, a.steps, a.warmup)
     n_bases = int(off[-1])
     print(json.dumps(dict(config=a.config, reads=a.reads, bases=n_bases, cores=cores, n_pass=n_pass,
                           seconds=times, gbases_per_s=[n_bases / t / 1e9 for t in times],
-                          reads_per_s=[a.reads / t for t in times])))
+                          reads_per_s=[a.reads / t for t in times],
+                          pass_rows=[[gi + a.first_read, tail, trc, telo] for gi, tail, trc, telo in rows])))
 
 
 if __name__ == "__main__":

@@ -118,7 +118,10 @@ int build_pattern_table(const tps_params *p, TpsPatTable *pt) {
       bordered = eq;
     }
     pt->bordered[i] = bordered;
-    if (bordered) pt->brow[i] = (uint8_t)pt->n_bordered++;
+    if (bordered) {
+      pt->brow[i] = (uint8_t)pt->n_bordered++;
+      pt->bordered_mask |= 1ull << i;
+    }
   }
   return TPS_OK;
 }
@@ -299,6 +302,10 @@ int tps_create(tps_ctx **out, int device, const tps_params *params) {
   TPS_CC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3, ctx->k3_fn, TPS_K3_THREADS, ctx->k3_smem));
   TPS_CC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ4, tps_changepoint_kernel, TPS_K4_THREADS, 0));
   ctx->k1_grid = ctx->n_sms * (occ1 > 0 ? occ1 : 1);
+  if (const char *e = getenv("TPS_K1_CTAS_PER_SM")) { /* tuning knob: leave room for other streams' kernels */
+    int v = atoi(e);
+    if (v >= 1 && v <= occ1) ctx->k1_grid = ctx->n_sms * v;
+  }
   ctx->k3_grid = (uint32_t)(ctx->n_sms * (occ3 > 0 ? occ3 : 1));
   ctx->k4_grid = (uint32_t)(ctx->n_sms * (occ4 > 0 ? (occ4 > 4 ? 4 : occ4) : 1));
 
@@ -521,14 +528,20 @@ int tps_batch_info(tps_ctx *ctx, uint64_t batch_id, uint32_t *n_pass_out, uint64
 
 int tps_scan_device(tps_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_offsets, uint32_t n_reads,
                     uint64_t n_bases, tps_row *d_rows_out) {
+  return tps_scan_device_slot(ctx, 0, d_bases, d_offsets, n_reads, n_bases, d_rows_out);
+}
+
+int tps_scan_device_slot(tps_ctx *ctx, uint32_t slot, const uint8_t *d_bases, const uint64_t *d_offsets,
+                         uint32_t n_reads, uint64_t n_bases, tps_row *d_rows_out) {
   if (!ctx || !d_offsets || !d_rows_out || (!d_bases && n_bases)) return fail(ctx, TPS_EINVAL, "null argument");
+  if (slot >= ctx->p.n_slots) return fail(ctx, TPS_EINVAL, "slot %u out of range (context has %u)", slot, ctx->p.n_slots);
   if (n_reads > ctx->p.max_batch_reads || n_bases > ctx->p.max_batch_bases)
     return fail(ctx, TPS_ECAPACITY, "batch (%u reads, %llu bases) exceeds context capacity", n_reads,
                 (unsigned long long)n_bases);
   if ((uintptr_t)d_bases & 15u) return fail(ctx, TPS_EINVAL, "d_bases must be 16-byte aligned");
   TPS_CUDA(ctx, cudaSetDevice(ctx->device));
-  Slot &s = ctx->slots[0];
-  if (s.busy) return fail(ctx, TPS_ESTATE, "slot 0 busy with a submitted batch");
+  Slot &s = ctx->slots[slot];
+  if (s.busy) return fail(ctx, TPS_ESTATE, "slot %u busy with a submitted batch", slot);
   return enqueue_scan(ctx, s, s.stream, d_bases, d_offsets, n_reads, n_bases, d_rows_out, true);
 }
 

@@ -33,6 +33,7 @@ struct TpsPatTable {
   uint8_t brow[TPS_MAX_PATTERNS];     /* row index among bordered literals */
   uint32_t n;
   uint32_t n_bordered;
+  uint64_t bordered_mask; /* bit p = literal p overlaps itself */
 };
 
 struct TpsPacked {
@@ -474,16 +475,18 @@ __device__ __forceinline__ void tps_trc_end_reg(const TpsScanArgs &a, const TpsP
   tps_win_init<K>(win, a0, b0, a1, b1, av, bv);
   const uint32_t nq = (n + 31u) >> 5;
   uint32_t mine = 0u; /* count of literal `lane` */
-  for (uint32_t p = 0; p < pt.n; ++p) {
+#pragma unroll 4
+  for (uint32_t p = 0; p < pt.n; ++p) { /* branch-free: occurrences of every literal */
     const uint32_t M = tps_win_match<K>(win, pm, pt, p);
-    if (pt.bordered[p]) { /* warp-uniform */
-      if (lane < nq) mrows[pt.brow[p] * 32u + lane] = M;
-    } else {
-      const uint32_t c = __reduce_add_sync(TPS_FULL, tps_popc32(M));
-      if (lane == p) mine = c;
-    }
+    const uint32_t c = __reduce_add_sync(TPS_FULL, tps_popc32(M));
+    if (lane == p) mine = c;
   }
-  if (pt.n_bordered) {
+  if (pt.n_bordered) { /* self-overlapping literals: occurrences != greedy count, redo those exactly */
+    for (uint64_t bm = pt.bordered_mask; bm; bm &= bm - 1) {
+      const uint32_t p = (uint32_t)__ffsll((long long)bm) - 1u;
+      const uint32_t M = tps_win_match<K>(win, pm, pt, p);
+      if (lane < nq) mrows[pt.brow[p] * 32u + lane] = M;
+    }
     __syncwarp();
     if (lane < pt.n && pt.bordered[lane]) {
       const uint32_t k = pt.len[lane];
@@ -727,34 +730,50 @@ tps_window_kernel(const TpsScanArgs a, const TpsPatTable pt) {
 /* ------------------------------------------------------------------------------------ K4 */
 #define TPS_K4_THREADS 128
 
-/* One warp per passing read: single change point of c_w, the exact form of ruptures
+/* One CTA per passing read: single change point of c_w, the exact form of ruptures
  * Binseg(model="l2", jump=5, min_size=2).predict(n_bkps=1):
- * argmax over b in {5,10,...}, 2 <= b <= n-2 of (n*S_b - b*T)^2 / (b*(n-b)), ties -> larger b. */
+ * argmax over b in {5,10,...}, 2 <= b <= n-2 of (n*S_b - b*T)^2 / (b*(n-b)), ties -> larger b.
+ * Thread i of a 640-window chunk owns the candidate b = chunk + 5i and the five windows behind it;
+ * S_b comes from a block-wide exclusive scan of those group sums, the argmax from the exact
+ * 128-bit comparator (warp shuffles, then one shared-memory round across the four warps). */
 __global__ void __launch_bounds__(TPS_K4_THREADS)
 tps_changepoint_kernel(const TpsScanArgs a) {
-  const uint32_t lane = threadIdx.x & 31u;
+  __shared__ uint64_t s_warp[TPS_K4_THREADS / 32];
+  __shared__ uint64_t s_num[TPS_K4_THREADS / 32][2];
+  __shared__ uint64_t s_den[TPS_K4_THREADS / 32];
+  __shared__ int32_t s_b[TPS_K4_THREADS / 32];
+  __shared__ uint32_t s_pi;
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  constexpr uint32_t NWARP = TPS_K4_THREADS / 32;
   uint32_t n_pass = a.counters[0];
   if (n_pass > a.max_pass) n_pass = a.max_pass;
   for (;;) {
-    uint32_t pi = 0;
-    if (lane == 0) pi = atomicAdd(a.counters + 5, 1u);
-    pi = __shfl_sync(TPS_FULL, pi, 0);
+    __syncthreads();
+    if (tid == 0) s_pi = atomicAdd(a.counters + 5, 1u);
+    __syncthreads();
+    const uint32_t pi = s_pi;
     if (pi >= n_pass) break;
     const uint32_t r = a.pass_list[pi];
     const uint32_t nW = a.rows[r].n_windows;
     const uint32_t *cw = a.cw + (size_t)pi * a.cw_stride;
     int32_t best_b = -1;
     if (nW >= 7u) { /* ruptures sanity_check: n >= 7 for jump 5, min_size 2, one breakpoint */
+      /* T = sum of all c_w */
       uint64_t T = 0;
-      for (uint32_t w = lane; w < nW; w += 32u) T += cw[w];
+      for (uint32_t w = tid; w < nW; w += TPS_K4_THREADS) T += cw[w];
 #pragma unroll
       for (int o = 16; o; o >>= 1) T += __shfl_xor_sync(TPS_FULL, T, o);
+      if (lane == 0) s_warp[warp] = T;
+      __syncthreads();
+      T = 0;
+#pragma unroll
+      for (uint32_t i = 0; i < NWARP; ++i) T += s_warp[i];
+      __syncthreads();
       tps_cand best;
       best.b = -1; best.num = 0; best.den = 1;
-      uint64_t carry = 0; /* sum of c_w over windows before this chunk */
-      for (uint32_t base = 0; base < nW; base += 160u) {
-        /* lane handles the 5 windows [base+5*lane, +5): candidate b = base+5*lane */
-        const uint32_t b = base + 5u * lane;
+      uint64_t carry = 0; /* sum of c_w over the windows before this chunk */
+      for (uint32_t base = 0; base < nW; base += 5u * TPS_K4_THREADS) {
+        const uint32_t b = base + 5u * tid;
         uint64_t g = 0;
 #pragma unroll
         for (uint32_t i = 0; i < 5u; ++i)
@@ -762,15 +781,24 @@ tps_changepoint_kernel(const TpsScanArgs a) {
         uint64_t inc = g;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-          uint64_t up = __shfl_up_sync(TPS_FULL, inc, o);
+          const uint64_t up = __shfl_up_sync(TPS_FULL, inc, o);
           if ((int)lane >= o) inc += up;
         }
-        const uint64_t S_b = carry + inc - g; /* exclusive prefix = sum_{w<b} c_w */
+        if (lane == 31u) s_warp[warp] = inc;
+        __syncthreads();
+        uint64_t before = carry, chunk = 0;
+#pragma unroll
+        for (uint32_t i = 0; i < NWARP; ++i) {
+          if (i < warp) before += s_warp[i];
+          chunk += s_warp[i];
+        }
+        __syncthreads();
+        const uint64_t S_b = before + inc - g; /* exclusive prefix = sum_{w<b} c_w */
         if (b >= 2u && b < nW && nW - b >= 2u) {
-          tps_cand c = tps_make_cand(nW, S_b, T, b);
+          const tps_cand c = tps_make_cand(nW, S_b, T, b);
           if (tps_cand_better(&best, &c)) best = c;
         }
-        carry += __shfl_sync(TPS_FULL, inc, 31);
+        carry += chunk;
       }
       /* warp argmax with the exact comparator (ties -> larger b) */
 #pragma unroll
@@ -784,9 +812,25 @@ tps_changepoint_kernel(const TpsScanArgs a) {
         oth.b = __shfl_xor_sync(TPS_FULL, best.b, o);
         if (tps_cand_better(&best, &oth)) best = oth;
       }
-      best_b = best.b;
+      if (lane == 0) {
+        s_num[warp][0] = (uint64_t)best.num;
+        s_num[warp][1] = (uint64_t)(best.num >> 64);
+        s_den[warp] = best.den;
+        s_b[warp] = best.b;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        for (uint32_t i = 1; i < NWARP; ++i) {
+          tps_cand oth;
+          oth.num = ((unsigned __int128)s_num[i][1] << 64) | s_num[i][0];
+          oth.den = s_den[i];
+          oth.b = s_b[i];
+          if (tps_cand_better(&best, &oth)) best = oth;
+        }
+        best_b = best.b;
+      }
     }
-    if (lane == 0) {
+    if (tid == 0) {
       tps_row *row = a.rows + r;
       if (best_b >= 0) {
         row->bkp = best_b;

@@ -98,6 +98,8 @@ def load_library() -> C.CDLL:
     lib.tps_batch_info.argtypes = [vp, C.c_uint64, u32p, u64p]
     lib.tps_scan_device.restype = C.c_int
     lib.tps_scan_device.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint64, vp]
+    lib.tps_scan_device_slot.restype = C.c_int
+    lib.tps_scan_device_slot.argtypes = [vp, C.c_uint32, vp, vp, C.c_uint32, C.c_uint64, vp]
     lib.tps_sync.restype = C.c_int
     lib.tps_sync.argtypes = [vp]
     lib.tps_get_timings.restype = C.c_int
@@ -290,8 +292,10 @@ class ScanContext:
         return raw[off:off + nw * npat].reshape(nw, npat)
 
     # -- device-resident path (kernel-only timing)
-    def scan_device(self, d_bases_ptr: int, d_offsets_ptr: int, n_reads: int, n_bases: int, d_rows_ptr: int):
-        self._check(self.lib.tps_scan_device(self._h, d_bases_ptr, d_offsets_ptr, n_reads, n_bases, d_rows_ptr))
+    def scan_device(self, d_bases_ptr: int, d_offsets_ptr: int, n_reads: int, n_bases: int, d_rows_ptr: int,
+                    slot: int = 0):
+        self._check(self.lib.tps_scan_device_slot(self._h, slot, d_bases_ptr, d_offsets_ptr, n_reads, n_bases,
+                                                  d_rows_ptr))
 
     def sync(self):
         self._check(self.lib.tps_sync(self._h))

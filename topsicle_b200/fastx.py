@@ -95,8 +95,8 @@ class Batch:
         return self._text(r["title_off"], r["title_len"]).decode("utf-8", "replace")
 
     def read_id(self, i) -> str:
-        r = self.recs[i]
-        return self._text(int(r["title_off"]) + int(r["id_off"]), r["id_len"]).decode("utf-8", "replace")
+        r = self.recs[i].item()   # (title_off, seq_off, qual_off, title_len, id_off, id_len, ...)
+        return C.string_at(self._raw + r[0] + r[4], r[5]).decode("utf-8", "replace")
 
     def sequence(self, i) -> bytes:
         return self.bases[int(self.offsets[i]):int(self.offsets[i + 1])].tobytes()

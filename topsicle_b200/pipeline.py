@@ -18,6 +18,7 @@ exactly as the reference writes them.
 from __future__ import annotations
 
 import queue
+import sys
 import threading
 import time
 from dataclasses import dataclass, field
@@ -132,17 +133,19 @@ def harvest(cfg: ScanConfig, ctx, batch, rows, raw, want_records: bool, keep=Non
     """TRC-pass reads of one finished batch, in read order."""
     out = []
     idx = np.nonzero(rows["status"] >= engine.ST_PASS)[0]
-    for i in idx:
-        i = int(i)
-        r = rows[i]
+    if len(idx) == 0:
+        return out
+    sel = rows[idx]
+    cols = [sel[f].tolist() for f in ("match_count", "best_pattern", "tail", "status", "n_windows", "telo_length",
+                                      "length")]
+    ratio = cfg.no_bp / cfg.len_telopattern            # allsteps.py:178
+    for i, cnt, bp, tl, st, nw, telo, length in zip(idx.tolist(), *cols):
         rid = batch.read_id(i)
         if keep is not None and rid not in keep:
             continue
-        cnt = int(r["match_count"])
-        pr = PassRead(index=batch.first_read + i, read_id=rid, literal=ctx.patterns[int(r["best_pattern"])],
-                      tail=engine.TAIL_NAMES[int(r["tail"])], count=cnt,
-                      trc=engine.trc_value(cnt, cfg.len_telopattern, cfg.no_bp), status=int(r["status"]),
-                      n_windows=int(r["n_windows"]), telo_length=int(r["telo_length"]), length=int(r["length"]))
+        pr = PassRead(index=batch.first_read + i, read_id=rid, literal=ctx.patterns[bp],
+                      tail=engine.TAIL_NAMES[tl], count=cnt, trc=cnt / ratio, status=st,
+                      n_windows=nw, telo_length=telo, length=length)
         if cfg.want_rawcount and raw is not None:
             tab = ctx.rawcount_table(rows, raw, i)
             pr.counts = None if tab is None else tab.copy()
@@ -373,6 +376,10 @@ class Scanner:
                 errors.append(e)
                 free.put(None)   # unblock the reader
 
+        # the reader thread re-acquires the GIL between two C parser calls while the workers harvest in
+        # Python: with the default 5 ms switch interval that wait would dominate the parse of a batch
+        old_switch = sys.getswitchinterval()
+        sys.setswitchinterval(1e-4)
         reader = threading.Thread(target=read_loop, name="tps-reader")
         ths = [threading.Thread(target=work_loop, args=(w,), name=f"tps-dev{w.device}") for w in self.workers]
         try:
@@ -386,6 +393,7 @@ class Scanner:
             if errors:
                 raise errors[0]
         finally:
+            sys.setswitchinterval(old_switch)
             t_close = time.perf_counter()
             fx.close()
             tm["close"] = time.perf_counter() - t_close

@@ -26,7 +26,8 @@ def synth_file(tmp_path_factory):
 
 
 def _cfgs(phrases, **kw):
-    return [pipeline.ScanConfig(patterns=patterns_to_search("CCCTAA", k), len_telopattern=6, phrase=k, slide=6, **kw)
+    kw.setdefault("slide", 6)
+    return [pipeline.ScanConfig(patterns=patterns_to_search("CCCTAA", k), len_telopattern=6, phrase=k, **kw)
             for k in phrases]
 
 
@@ -58,7 +59,6 @@ def test_rawcount_and_capacity_split(synth_file):
     """Raw count tables through the pipeline; a tiny pass / rawcount capacity forces the split re-scan."""
     path, recs = synth_file
     cfgs = _cfgs([4], cutoff=0.6, want_rawcount=True, window_size=50, slide=3)
-    cfgs[0].slide = 3
     stats, per = pipeline.collect_file(path, cfgs, devices=[0], max_batch_bases=16 << 20, max_batch_reads=1024,
                                        max_pass_reads=8, rawcount_capacity=6617 * 12 * 3)
     assert _check(per[0], recs, 4, 0.6, W=50, s=3, counts=True) > 40

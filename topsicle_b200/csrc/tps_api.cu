@@ -262,7 +262,7 @@ int tps_create(tps_ctx **out, int device, const tps_params *params) {
   ctx->k3_tile_words = (tile_n + 31) / 32 + 1;
   ctx->k3_tiles_max = (uint32_t)((reg_max + ctx->k3_tile_bases - 1) / ctx->k3_tile_bases);
   if (ctx->k3_tiles_max == 0) ctx->k3_tiles_max = 1;
-  ctx->k3_smem = (pm_words + 3 * ctx->k3_lin_words + 3 * ctx->k3_tile_words + 1 + 2 * pt.n * ctx->k3_tile_words +
+  ctx->k3_smem = (pm_words + 3 * ctx->k3_lin_words + 3 * ctx->k3_tile_words + 3 + 2 * pt.n * ctx->k3_tile_words +
                   pt.n_bordered * ctx->k3_tile_words) * 4;
   ctx->cw_stride = (uint32_t)(nw_max ? nw_max : 1);
   ctx->max_pass = p.max_pass_reads ? p.max_pass_reads : p.max_batch_reads;

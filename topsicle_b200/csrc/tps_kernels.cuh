@@ -348,7 +348,7 @@ __device__ __forceinline__ void tps_trc_end(const TpsScanArgs &a, const TpsPatTa
 template <int K>
 __global__ void __launch_bounds__(TPS_K2_WARPS * 32)
 tps_trc_kernel(const TpsScanArgs a, const TpsPatTable pt) {
-  extern __shared__ uint32_t smem[];
+  extern __shared__ __align__(16) uint32_t smem[];
   constexpr uint32_t KS = K > 0 ? K : 1;
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
   uint2 *pm = reinterpret_cast<uint2 *>(smem);
@@ -507,7 +507,7 @@ __device__ __forceinline__ void tps_trc_end_reg(const TpsScanArgs &a, const TpsP
 template <int K>
 __global__ void __launch_bounds__(TPS_K2R_WARPS * 32)
 tps_trc_reg_kernel(const TpsScanArgs a, const TpsPatTable pt) {
-  extern __shared__ uint32_t smem[];
+  extern __shared__ __align__(16) uint32_t smem[];
   constexpr uint32_t KS = K > 0 ? K : 1;
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
   uint2 *pm = reinterpret_cast<uint2 *>(smem);
@@ -578,12 +578,12 @@ tps_trc_reg_kernel(const TpsScanArgs a, const TpsPatTable pt) {
  * with [ls, to] the window's start positions and e = to + 1.  Self-overlapping literals keep a
  * plain copy of their row for the greedy walk (exactly re.finditer's non-overlapping count).
  *
- * dynamic shared memory (words): pm[2*P*max(K,1)] | lin[3*lin_words] | ori[3*tile_words] |
- * rp[2*P*tile_words] (uint2 {row, prefix}) | brows[n_bordered*tile_words] */
+ * dynamic shared memory (words): pm[2*P*max(K,1)] | lin[3*lin_words] | ori[3*tile_words] | pad to 16 B |
+ * rp[tile_words][P] (uint2 {row word, running popcount}) | brows[n_bordered*tile_words] */
 template <int K>
 __global__ void __launch_bounds__(TPS_K3_THREADS)
 tps_window_kernel(const TpsScanArgs a, const TpsPatTable pt) {
-  extern __shared__ uint32_t smem[];
+  extern __shared__ __align__(16) uint32_t smem[];
   __shared__ uint32_t s_item;
   constexpr uint32_t KS = K > 0 ? K : 1;
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -591,7 +591,7 @@ tps_window_kernel(const TpsScanArgs a, const TpsPatTable pt) {
   uint2 *pm = reinterpret_cast<uint2 *>(smem);
   uint32_t *lin = smem + 2u * pt.n * KS;
   uint32_t *ori = lin + 3u * lw;
-  uint2 *rp = reinterpret_cast<uint2 *>(ori + 3u * tw + ((3u * lw + 3u * tw) & 1u)); /* 8-byte aligned */
+  uint2 *rp = reinterpret_cast<uint2 *>(ori + 3u * tw + ((4u - ((3u * lw + 3u * tw) & 3u)) & 3u)); /* 16-byte aligned */
   uint32_t *brows = reinterpret_cast<uint32_t *>(rp + (size_t)pt.n * tw);
   tps_build_pattern_masks(pm, pt, KS, tid, TPS_K3_THREADS);
   uint32_t n_pass = a.counters[0];
@@ -640,71 +640,106 @@ tps_window_kernel(const TpsScanArgs a, const TpsPatTable pt) {
       ori[2u * tw + q] = v;
     }
     __syncthreads();
-    /* (2) match words; words past the staged slice are zero */
+    /* (2) match words; words past the staged slice are zero.  rp is word-major: rp[q * P + p] */
+    const uint32_t P = pt.n;
     for (uint32_t i = tid; i < tw * TPS_K3_PSPLIT; i += TPS_K3_THREADS) {
       const uint32_t h = i / tw, q = i - h * tw;
       if (q < nq) {
         TpsWin<K> win;
         tps_win_init<K>(win, ori[q], ori[q + 1], ori[tw + q], ori[tw + q + 1], ori[2u * tw + q],
                         ori[2u * tw + q + 1]);
-        for (uint32_t p = h; p < pt.n; p += TPS_K3_PSPLIT) {
-          const uint32_t Mw = tps_win_match<K>(win, pm, pt, p);
-          rp[p * tw + q].x = Mw;
-          if (pt.bordered[p]) brows[pt.brow[p] * tw + q] = Mw;
-        }
+        for (uint32_t p = h; p < P; p += TPS_K3_PSPLIT) rp[q * P + p].x = tps_win_match<K>(win, pm, pt, p);
       } else {
-        for (uint32_t p = h; p < pt.n; p += TPS_K3_PSPLIT) {
-          rp[p * tw + q].x = 0u;
-          if (pt.bordered[p]) brows[pt.brow[p] * tw + q] = 0u;
-        }
+        for (uint32_t p = h; p < P; p += TPS_K3_PSPLIT) rp[q * P + p].x = 0u;
       }
     }
     __syncthreads();
-    /* (3) exclusive running popcount per literal row: one warp per literal */
-    for (uint32_t p = warp; p < pt.n; p += TPS_K3_THREADS / 32) {
-      uint32_t carry = 0u;
-      for (uint32_t qb = 0; qb < tw; qb += 32u) {
-        const uint32_t q = qb + lane;
-        const uint32_t c = q < tw ? tps_popc32(rp[p * tw + q].x) : 0u;
-        uint32_t inc = c;
+    /* plain copies of the rows of self-overlapping literals for the greedy walk */
+    for (uint64_t bm = pt.bordered_mask; bm; bm &= bm - 1) {
+      const uint32_t p = (uint32_t)__ffsll((long long)bm) - 1u;
+      for (uint32_t q = tid; q < tw; q += TPS_K3_THREADS) brows[pt.brow[p] * tw + q] = rp[q * P + p].x;
+    }
+    /* (3) exclusive running popcount per literal row: one warp per literal, each lane sums a run of
+     * consecutive words, one warp scan joins the runs */
+    {
+      const uint32_t per = (tw + 31u) / 32u; /* words per lane */
+      for (uint32_t p = warp; p < P; p += TPS_K3_THREADS / 32) {
+        const uint32_t qa = lane * per;
+        uint32_t run = 0u;
+        for (uint32_t j = 0; j < per; ++j) {
+          const uint32_t q = qa + j;
+          if (q < tw) run += tps_popc32(rp[q * P + p].x);
+        }
+        uint32_t inc = run;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
           const uint32_t up = __shfl_up_sync(TPS_FULL, inc, o);
           if ((int)lane >= o) inc += up;
         }
-        if (q < tw) rp[p * tw + q].y = carry + inc - c;
-        carry += __shfl_sync(TPS_FULL, inc, 31);
+        uint32_t acc = inc - run;
+        for (uint32_t j = 0; j < per; ++j) {
+          const uint32_t q = qa + j;
+          if (q < tw) {
+            uint2 *e = rp + q * P + p;
+            const uint32_t x = e->x;
+            e->y = acc;
+            acc += tps_popc32(x);
+          }
+        }
       }
     }
     __syncthreads();
     /* (4) windows */
+    const bool want_raw = raw_off != ~0ull;
     for (uint32_t w = wlo + tid; w < whi; w += TPS_K3_THREADS) {
       const uint32_t ls = w * s - tb0;
       uint32_t c = 0;
+      uint8_t *rawp = want_raw ? a.raw + raw_off + (uint64_t)w * P : nullptr;
       if constexpr (K > 0) {
         if (W - 1u >= (uint32_t)K) {
           const uint32_t e = ls + (W - (uint32_t)K); /* one past the last start position */
-          const uint32_t q0 = ls >> 5, qe = e >> 5;
+          const uint2 *r0 = rp + (ls >> 5) * P, *re = rp + (e >> 5) * P;
           const uint32_t m0 = (1u << (ls & 31u)) - 1u, me = (1u << (e & 31u)) - 1u;
-          for (uint32_t p = 0; p < pt.n; ++p) {
-            uint32_t cnt;
-            if (pt.bordered[p]) {
-              cnt = tps_greedy_count(brows + pt.brow[p] * tw, (int32_t)ls, (int32_t)e - 1, (uint32_t)K);
-            } else {
-              const uint2 r0 = rp[p * tw + q0], re = rp[p * tw + qe];
-              cnt = re.y + tps_popc32(re.x & me) - r0.y - tps_popc32(r0.x & m0);
+          /* occurrences of every literal (branch-free); P even: two literals per 128-bit load */
+          if ((P & 3u) == 0u) {
+            const uint4 *v0 = reinterpret_cast<const uint4 *>(r0), *ve = reinterpret_cast<const uint4 *>(re);
+            for (uint32_t p = 0; p < P; p += 4u) {
+              const uint4 a0 = v0[p >> 1], ae = ve[p >> 1], b0 = v0[(p >> 1) + 1u], be = ve[(p >> 1) + 1u];
+              uint32_t c0 = ae.y + tps_popc32(ae.x & me) - a0.y - tps_popc32(a0.x & m0);
+              uint32_t c1 = ae.w + tps_popc32(ae.z & me) - a0.w - tps_popc32(a0.z & m0);
+              uint32_t c2 = be.y + tps_popc32(be.x & me) - b0.y - tps_popc32(b0.x & m0);
+              uint32_t c3 = be.w + tps_popc32(be.z & me) - b0.w - tps_popc32(b0.z & m0);
+              c0 = c0 ? c0 : 1u; c1 = c1 ? c1 : 1u; c2 = c2 ? c2 : 1u; c3 = c3 ? c3 : 1u; /* `... or 1` */
+              c += (c0 + c1) + (c2 + c3);
+              if (want_raw) *reinterpret_cast<uint32_t *>(rawp + p) = c0 | (c1 << 8) | (c2 << 16) | (c3 << 24);
             }
-            if (cnt == 0u) cnt = 1u; /* `... or 1`, allsteps.py:281,288 */
-            c += cnt;
-            if (raw_off != ~0ull) a.raw[raw_off + (uint64_t)w * pt.n + p] = (uint8_t)cnt;
+          } else {
+            for (uint32_t p = 0; p < P; ++p) {
+              const uint2 x0 = r0[p], xe = re[p];
+              uint32_t cnt = xe.y + tps_popc32(xe.x & me) - x0.y - tps_popc32(x0.x & m0);
+              cnt = cnt ? cnt : 1u;
+              c += cnt;
+              if (want_raw) rawp[p] = (uint8_t)cnt;
+            }
+          }
+          /* self-overlapping literals: replace the occurrence count by the greedy one */
+          for (uint64_t bm = pt.bordered_mask; bm; bm &= bm - 1) {
+            const uint32_t p = (uint32_t)__ffsll((long long)bm) - 1u;
+            const uint2 x0 = r0[p], xe = re[p];
+            uint32_t occ = xe.y + tps_popc32(xe.x & me) - x0.y - tps_popc32(x0.x & m0);
+            uint32_t g = tps_greedy_count(brows + pt.brow[p] * tw, (int32_t)ls, (int32_t)e - 1, (uint32_t)K);
+            occ = occ ? occ : 1u;
+            g = g ? g : 1u;
+            c = c - occ + g;
+            if (want_raw) rawp[p] = (uint8_t)g;
           }
         } else {
-          c = pt.n; /* window text shorter than the literals: every count is floored to 1 */
-          if (raw_off != ~0ull)
-            for (uint32_t p = 0; p < pt.n; ++p) a.raw[raw_off + (uint64_t)w * pt.n + p] = 1u;
+          c = P; /* window text shorter than the literals: every count is floored to 1 */
+          if (want_raw)
+            for (uint32_t p = 0; p < P; ++p) rawp[p] = 1u;
         }
       } else {
-        for (uint32_t p = 0; p < pt.n; ++p) {
+        for (uint32_t p = 0; p < P; ++p) {
           const uint32_t k = pt.len[p];
           uint32_t cnt = 0;
           if (W - 1u >= k) {
@@ -712,14 +747,14 @@ tps_window_kernel(const TpsScanArgs a, const TpsPatTable pt) {
             if (pt.bordered[p]) {
               cnt = tps_greedy_count(brows + pt.brow[p] * tw, (int32_t)ls, (int32_t)e - 1, k);
             } else {
-              const uint2 r0 = rp[p * tw + (ls >> 5)], re = rp[p * tw + (e >> 5)];
-              cnt = re.y + tps_popc32(re.x & ((1u << (e & 31u)) - 1u)) - r0.y -
-                    tps_popc32(r0.x & ((1u << (ls & 31u)) - 1u));
+              const uint2 x0 = rp[(ls >> 5) * P + p], xe = rp[(e >> 5) * P + p];
+              cnt = xe.y + tps_popc32(xe.x & ((1u << (e & 31u)) - 1u)) - x0.y -
+                    tps_popc32(x0.x & ((1u << (ls & 31u)) - 1u));
             }
           }
-          if (cnt == 0u) cnt = 1u;
+          cnt = cnt ? cnt : 1u;
           c += cnt;
-          if (raw_off != ~0ull) a.raw[raw_off + (uint64_t)w * pt.n + p] = (uint8_t)cnt;
+          if (want_raw) rawp[p] = (uint8_t)cnt;
         }
       }
       cw[w] = c;

@@ -31,7 +31,7 @@ int32_t t_change_point(const uint32_t *cw, uint32_t n) {
   if (n < 7) return -1;
   uint64_t T = 0, S = 0;
   for (uint32_t i = 0; i < n; ++i) T += cw[i];
-  tps_cand best; best.b = -1; best.num = 0; best.den = 1;
+  tps_cand best; best.b = -1; best.d = 0; best.den = 1; best.num_f = 0.0; best.den_f = 1.0;
   uint32_t pos = 0;
   for (uint32_t b = 0; b < n; b += 5) {
     while (pos < b) S += cw[pos++];

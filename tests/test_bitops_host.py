@@ -113,3 +113,21 @@ def test_change_point_exact(lib):
                 orc.change_point_exact(cw)
         else:
             assert got == orc.change_point_exact(cw)
+
+
+def test_change_point_exact_long_signals(lib):
+    """Full-size signals (nW up to 6617 at W50/s3, c_w up to 14*24) incl. piecewise-constant ones with
+    many exactly tied gains: the float64-filtered comparator must still return the exact argmax."""
+    rnd = np.random.default_rng(9)
+    for trial in range(12):
+        n = int(rnd.integers(2500, 6700))
+        if trial % 3 == 0:
+            b = int(rnd.integers(100, n - 100))
+            cw = np.concatenate([np.full(b, 168), np.full(n - b, 14)])           # ideal telomere step
+        elif trial % 3 == 1:
+            cw = np.repeat(rnd.integers(12, 336, n // 50 + 1), 50)[:n]             # plateaus: tied gains
+        else:
+            cw = rnd.integers(12, 336, n)
+        cw = cw.astype(np.uint32)
+        got = lib.t_change_point(cw.ctypes.data_as(C.POINTER(C.c_uint32)), n)
+        assert got == orc.change_point_exact(cw), (trial, n)

@@ -180,31 +180,42 @@ TPS_HD uint32_t tps_range_popcount(const uint32_t *mask, int32_t from, int32_t t
 }
 
 /* ---- change point: exact comparison of two candidate gains --------------------------
- * gain(b) is proportional to  num/den  with num = (n*S_b - b*T)^2, den = b*(n-b)
+ * gain(b) is proportional to  d^2/den  with d = n*S_b - b*T, den = b*(n-b)
  * (equivalent to ruptures' C(0,n) - C(0,b) - C(b,n) with CostL2; the common factor 1/(n*P^2)
- * cancels).  Returns 1 if candidate B is better than A under ruptures' `max((gain, bkp))`
- * rule: larger gain, ties -> larger b. */
+ * cancels).  tps_cand_better returns 1 if candidate B is better than A under ruptures'
+ * `max((gain, bkp))` rule: larger gain, ties -> larger b.
+ * The decision is exact: a float64 cross-multiplication settles every pair whose gains differ by
+ * more than 1e-9 relative (the float64 evaluation is good to ~1e-15), anything closer -- ties and
+ * near-ties -- is compared as 128-bit integers (d^2 * den fits: checked at tps_create). */
 typedef struct tps_cand {
-  unsigned __int128 num;
+  int64_t d;
   uint64_t den;
+  double num_f; /* (double)d * (double)d */
+  double den_f;
   int32_t b;
 } tps_cand;
 
 TPS_HD int tps_cand_better(const tps_cand *A, const tps_cand *B) {
   if (A->b < 0) return B->b >= 0;
   if (B->b < 0) return 0;
-  unsigned __int128 l = B->num * (unsigned __int128)A->den;
-  unsigned __int128 r = A->num * (unsigned __int128)B->den;
-  if (l != r) return l > r;
+  const double l = B->num_f * A->den_f, r = A->num_f * B->den_f;
+  const double diff = l - r, big = l > r ? l : r;
+  if (diff > 1e-9 * big) return 1;
+  if (-diff > 1e-9 * big) return 0;
+  const uint64_t da = (uint64_t)(A->d < 0 ? -A->d : A->d), db = (uint64_t)(B->d < 0 ? -B->d : B->d);
+  const unsigned __int128 le = (unsigned __int128)db * db * (unsigned __int128)A->den;
+  const unsigned __int128 re = (unsigned __int128)da * da * (unsigned __int128)B->den;
+  if (le != re) return le > re;
   return B->b > A->b;
 }
 
 TPS_HD tps_cand tps_make_cand(uint32_t n, uint64_t S_b, uint64_t T, uint32_t b) {
   tps_cand c;
-  __int128 d = (__int128)n * (__int128)S_b - (__int128)b * (__int128)T;
-  if (d < 0) d = -d;
-  c.num = (unsigned __int128)d * (unsigned __int128)d;
+  c.d = (int64_t)((uint64_t)n * S_b) - (int64_t)((uint64_t)b * T);
   c.den = (uint64_t)b * (uint64_t)(n - b);
+  const double df = (double)c.d;
+  c.num_f = df * df;
+  c.den_f = (double)c.den;
   c.b = (int32_t)b;
   return c;
 }

@@ -564,7 +564,9 @@ tps_trc_reg_kernel(const TpsScanArgs a, const TpsPatTable pt) {
 }
 
 /* ------------------------------------------------------------------------------------ K3 */
-#define TPS_K3_THREADS 256
+#ifndef TPS_K3_THREADS
+#define TPS_K3_THREADS 128
+#endif
 #define TPS_K3_PSPLIT 2 /* literals of one 32-position word are split over this many threads */
 
 /* One work item = one tile of one passing read: window starts in [tb0, tb0 + tile_bases) of
@@ -774,9 +776,7 @@ tps_window_kernel(const TpsScanArgs a, const TpsPatTable pt) {
 __global__ void __launch_bounds__(TPS_K4_THREADS)
 tps_changepoint_kernel(const TpsScanArgs a) {
   __shared__ uint64_t s_warp[TPS_K4_THREADS / 32];
-  __shared__ uint64_t s_num[TPS_K4_THREADS / 32][2];
-  __shared__ uint64_t s_den[TPS_K4_THREADS / 32];
-  __shared__ int32_t s_b[TPS_K4_THREADS / 32];
+  __shared__ tps_cand s_cand[TPS_K4_THREADS / 32];
   __shared__ uint32_t s_pi;
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   constexpr uint32_t NWARP = TPS_K4_THREADS / 32;
@@ -805,7 +805,7 @@ tps_changepoint_kernel(const TpsScanArgs a) {
       for (uint32_t i = 0; i < NWARP; ++i) T += s_warp[i];
       __syncthreads();
       tps_cand best;
-      best.b = -1; best.num = 0; best.den = 1;
+      best.b = -1; best.d = 0; best.den = 1; best.num_f = 0.0; best.den_f = 1.0;
       uint64_t carry = 0; /* sum of c_w over the windows before this chunk */
       for (uint32_t base = 0; base < nW; base += 5u * TPS_K4_THREADS) {
         const uint32_t b = base + 5u * tid;
@@ -839,27 +839,18 @@ tps_changepoint_kernel(const TpsScanArgs a) {
 #pragma unroll
       for (int o = 16; o; o >>= 1) {
         tps_cand oth;
-        uint64_t nlo = (uint64_t)best.num, nhi = (uint64_t)(best.num >> 64);
-        nlo = __shfl_xor_sync(TPS_FULL, nlo, o);
-        nhi = __shfl_xor_sync(TPS_FULL, nhi, o);
-        oth.num = ((unsigned __int128)nhi << 64) | nlo;
+        oth.d = __shfl_xor_sync(TPS_FULL, best.d, o);
         oth.den = __shfl_xor_sync(TPS_FULL, best.den, o);
+        oth.num_f = __shfl_xor_sync(TPS_FULL, best.num_f, o);
+        oth.den_f = __shfl_xor_sync(TPS_FULL, best.den_f, o);
         oth.b = __shfl_xor_sync(TPS_FULL, best.b, o);
         if (tps_cand_better(&best, &oth)) best = oth;
       }
-      if (lane == 0) {
-        s_num[warp][0] = (uint64_t)best.num;
-        s_num[warp][1] = (uint64_t)(best.num >> 64);
-        s_den[warp] = best.den;
-        s_b[warp] = best.b;
-      }
+      if (lane == 0) s_cand[warp] = best;
       __syncthreads();
       if (tid == 0) {
         for (uint32_t i = 1; i < NWARP; ++i) {
-          tps_cand oth;
-          oth.num = ((unsigned __int128)s_num[i][1] << 64) | s_num[i][0];
-          oth.den = s_den[i];
-          oth.b = s_b[i];
+          const tps_cand oth = s_cand[i];
           if (tps_cand_better(&best, &oth)) best = oth;
         }
         best_b = best.b;

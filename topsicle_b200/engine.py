@@ -14,7 +14,7 @@ from typing import Iterable, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtopsicle_b200.so")
+LIB_PATH = os.environ.get("TOPSICLE_B200_LIB") or os.path.join(_HERE, "libtopsicle_b200.so")  # override: tuning builds
 
 TPS_MAX_PATTERNS = 64
 TPS_MAX_PATTERN_LEN = 32

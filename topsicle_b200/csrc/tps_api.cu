@@ -290,6 +290,17 @@ int tps_create(tps_ctx **out, int device, const tps_params *params) {
     if (ctx->k1_unroll == 8) ctx->k1_fn = tps_pack_kernel<8>;
     else { ctx->k1_unroll = 4; ctx->k1_fn = tps_pack_kernel<4>; }
 #ifdef TPS_TUNING
+    if (const char *mb = getenv("TPS_K1_MINB")) { /* register-capped builds: more resident CTAs */
+      ctx->k1_unroll = 4;
+      switch (atoi(mb)) {
+        case 5: ctx->k1_fn = tps_pack_kernel<4, 5>; break;
+        case 6: ctx->k1_fn = tps_pack_kernel<4, 6>; break;
+        case 8: ctx->k1_fn = tps_pack_kernel<4, 8>; break;
+        default: break;
+      }
+    }
+#endif
+#ifdef TPS_TUNING
     const char *pv = getenv("TPS_K1_PROBE");
     if (pv && atoi(pv) == 1) { ctx->k1_unroll = 4; ctx->k1_fn = tps_pack_probe<4, 1>; }
     if (pv && atoi(pv) == 2) { ctx->k1_unroll = 4; ctx->k1_fn = tps_pack_probe<4, 2>; }

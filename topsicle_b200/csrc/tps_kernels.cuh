@@ -131,8 +131,8 @@ tps_pack_probe(const uint4 *__restrict__ bases, uint32_t *__restrict__ codes, ui
  * store per warp), and the warp emits one flag word per tile by ballot (lane 0 stores the U
  * flag words of its U consecutive tiles as 128-bit vectors).  U tiles are loaded before any is
  * converted so each thread keeps U x 16 B in flight.  U must be a multiple of 4. */
-template <int U>
-__global__ void __launch_bounds__(TPS_K1_THREADS)
+template <int U, int MINB = 4>
+__global__ void __launch_bounds__(TPS_K1_THREADS, MINB)
 tps_pack_kernel(const uint4 *__restrict__ bases, uint32_t *__restrict__ codes,
                 uint32_t *__restrict__ flags, uint16_t *__restrict__ masks, uint64_t n_tiles) {
   static_assert(U % 4 == 0, "U must be a multiple of 4 (vector flag stores)");

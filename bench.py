@@ -209,6 +209,12 @@ def main():
                          f"workload, {r['seconds'][0]:.1f} s; in-memory reads (parsing not charged)"}
 
     # ---- synthetic batches: rank r owns reads [r*nb*R + b*R, ...) -> pinned host + device copies
+    # host placement: this rank's pinned buffers and parser threads on the CPUs local to its GPU
+    from topsicle_b200 import numa
+    cores_before = len(os.sched_getaffinity(0))
+    near = None if os.environ.get("TOPSICLE_NO_NUMA") else numa.cpus_near_device(local_rank)
+    if near and world > 1:
+        os.sched_setaffinity(0, near)
     t_gen = time.perf_counter()
     host_bases, host_off, dev_bases, dev_off, nbases = [], [], [], [], []
     for b in range(nb):
@@ -376,7 +382,8 @@ def main():
                                         want_rawcount=bool(spec["cli"].get("rawcountpattern")))
                     for k in phrases]
             got = []
-            host_threads = max(1, len(os.sched_getaffinity(0)) // world)   # ranks share the host cores
+            # ranks share the host cores (a rank bound to its GPU's CPUs already has its share)
+            host_threads = max(1, cores_before // world)
             with pipeline.Scanner(cfgs, devices=[local_rank], max_batch_bases=1 << 28, max_batch_reads=1 << 17,
                                   depth=3, threads=host_threads) as sc:
                 sc.scan_file(path, lambda res: None)           # warm-up pass (page cache, first launches)
@@ -426,7 +433,8 @@ def main():
                              "whole_scan_frac": alg_bytes / (dev_ms * 1e-3) / 1e9 / peak},
                 "cpu_baseline": cpu, "parity_sample": parity, "e2e": e2e, "e2e_from_fastq": e2e_file, "gpu_launches": int(launches),
                 "clocks": clocks,
-                "generate_s": t_gen}
+                "generate_s": t_gen,
+                "host_placement": {"cpus_local_to_gpu0": near, "bound": bool(near and world > 1)}}
         print(json.dumps(line))
     ctx.close()
     for hb in host_bases + host_off:

@@ -26,7 +26,7 @@ from typing import Callable, Sequence
 
 import numpy as np
 
-from . import engine, fastx
+from . import engine, fastx, numa
 
 
 @dataclass
@@ -170,7 +170,8 @@ class _DeviceWorker:
             # followers never upload: they need no base / code buffers of their own
             self.ctxs.append(context_factory(c, device, max_batch_reads, max_batch_bases if k == 0 else 1, depth,
                                              max_pass_reads, rawcount_capacity if c.want_rawcount else 0))
-        self.slots = [_Slot(max_batch_bases, max_batch_reads) for _ in range(depth)]
+        with numa.near_device(device):      # pinned staging on the GPU's own NUMA node
+            self.slots = [_Slot(max_batch_bases, max_batch_reads) for _ in range(depth)]
 
     def close(self):
         for c in self.ctxs:

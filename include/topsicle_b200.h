@@ -125,6 +125,12 @@ void tps_free_pinned(void *p);
  * Replaces: process_file's step 1 + per-read step 2/3 loop (main.py:57, 125-150). */
 int tps_submit(tps_ctx *ctx, const uint8_t *bases, const uint64_t *offsets, uint32_t n_reads,
                uint64_t batch_id);
+/* Same for a batch whose reads are NOT packed back to back: read i is bases[starts[i] .. starts[i] +
+ * lengths[i]); reads do not overlap, anything between them is ignored, `n_span` bytes of `bases` are
+ * uploaded.  This is what a one-pass parser produces (it can place every read without first knowing the
+ * lengths of all reads before it, see csrc/tps_fastx.c).  Same lifetime rules as tps_submit. */
+int tps_submit_spans(tps_ctx *ctx, const uint8_t *bases, uint64_t n_span, const uint64_t *starts,
+                     const uint32_t *lengths, uint32_t n_reads, uint64_t batch_id);
 /* Scan, under the parameters of `ctx`, the batch that `owner` has in flight as `batch_id`, without a
  * second upload or a second K1: ctx's K2..K4 are enqueued on the owner's stream and read the owner's
  * packed reads.  Same device; collect with tps_wait(ctx, batch_id, ...).  This is how several

@@ -43,6 +43,17 @@ class OracleContext:
         self._pending[bid] = (bases.tobytes(), np.array(offsets, dtype=np.uint64))
         return bid
 
+    def submit_spans(self, bases, starts, lens, n_reads):
+        """Span batch -> the same back-to-back form the oracle loop below reads."""
+        bid = next(engine._batch_ids)
+        assert n_reads <= self.max_batch_reads and bases.size <= self.max_batch_bases
+        parts = [bases[int(starts[i]):int(starts[i]) + int(lens[i])].tobytes() for i in range(n_reads)]
+        assert all(int(starts[i]) + int(lens[i]) <= int(starts[i + 1]) for i in range(n_reads - 1)), "reads overlap"
+        off = np.zeros(n_reads + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([len(p) for p in parts], dtype=np.uint64)
+        self._pending[bid] = (b"".join(parts), off)
+        return bid
+
     def submit_shared(self, owner, bid):
         self._pending[bid] = owner._pending[bid]
         return bid

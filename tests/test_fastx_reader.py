@@ -119,3 +119,68 @@ def test_rawcount_csv_text_equals_pandas():
     assert text.decode() == want
     from topsicle_b200.allsteps import rawcount_frame
     assert rawcount_frame(counts, "reverse", 6, pats).to_csv() == want
+
+
+# ----------------------------------------------------------------------------- span batches (one-pass reader)
+def read_all_spans(path, max_reads=1 << 12, max_span=1 << 22, window=None, threads=4, two_pass=False):
+    out = []
+    with fastx.FastxFile(path, threads=threads) as fx:
+        if window:
+            fx.set_window(window)
+        if two_pass:
+            fx.set_two_pass()
+        bases = np.full(max_span, ord("!"), np.uint8)
+        starts = np.zeros(max_reads + 1, np.uint64)
+        lens = np.zeros(max_reads, np.uint32)
+        while True:
+            b = fx.next_spans(bases, starts, lens)
+            if b is None:
+                break
+            ends = starts[:b.n_reads] + lens[:b.n_reads]
+            assert (ends[:-1] <= starts[1:b.n_reads]).all() and int(ends[-1]) <= b.span <= max_span
+            assert b.n_bases == int(lens[:b.n_reads].sum())
+            for i in range(b.n_reads):
+                out.append((b.read_id(i), b.sequence(i).decode(), b.title(i), b.record_text(i)))
+            b.release()
+    return out
+
+
+@pytest.mark.parametrize("name", ["demo.fastq.gz", "edge.fastq", "edge.fasta"])
+@pytest.mark.parametrize("caps", [(1 << 12, 1 << 22, None), (3, 1 << 20, 5000), (1, 1 << 20, 4096)])
+def test_span_reader_matches_oracle_parser(name, caps):
+    path = os.path.join(GOLD, name)
+    got = read_all_spans(path, *caps)
+    assert [(a, b) for a, b, _, _ in got] == list(orc.read_fastx(path))
+    assert got == read_all(path, *caps)
+
+
+def test_one_pass_equals_two_pass_on_awkward_fastq(tmp_path):
+    """CRLF, '@'/'+' in qualities, blank lines, trailing blanks (forces the validating fallback), a record
+    bigger than the first window, no final newline -- plain and gzip, several thread counts."""
+    rng = np.random.default_rng(17)
+    p = tmp_path / "awk.fastq"
+    want = []
+    with open(p, "wb") as fh:
+        for i in range(1500):
+            L = int(rng.integers(0, 3000)) if i != 700 else 300000
+            seq = bytes(rng.choice(np.frombuffer(b"ACGTNacgt", np.uint8), L))
+            qual = bytes(rng.choice(np.frombuffer(b"@+I!5", np.uint8), L))
+            eol = b"\r\n" if i % 7 == 0 else b"\n"
+            pad = b"      " if i % 97 == 0 else b""           # > 4 trailing blanks: two-pass path
+            fh.write(b"@r%d some text%s%s%s%s+%s%s%s" % (i, eol, seq, pad, eol, eol, qual, eol if i < 1499 else b""))
+            if i % 50 == 0:
+                fh.write(b"\n")
+            want.append((f"r{i}", seq.decode()))
+    for threads, window in [(1, None), (8, None), (8, 2 << 20), (3, 1 << 20)]:
+        got = read_all_spans(str(p), 1 << 12, 1 << 24, window, threads)
+        assert [(a, b) for a, b, _, _ in got] == want, (threads, window)
+        assert got == read_all_spans(str(p), 1 << 12, 1 << 24, window, threads, two_pass=True)
+    gz = tmp_path / "awk.fastq.gz"
+    with open(p, "rb") as src, gzip.open(gz, "wb", compresslevel=1) as dst:
+        dst.write(src.read())
+    got = read_all_spans(str(gz), 700, 1 << 20, None, 4)
+    assert [(a, b) for a, b, _, _ in got] == want
+    bad = tmp_path / "bad.fq"
+    bad.write_bytes(b"@a\nACGT\n+\n!!!!\n@b\nACGT\n+\n!!!\n")
+    with pytest.raises(fastx.FastxError):
+        read_all_spans(str(bad))

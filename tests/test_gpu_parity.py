@@ -331,3 +331,40 @@ def test_max_pass_overflow_is_loud(eng, demo_records):
     with _ctx(eng, pats, len_telopattern=7, cutoff=0.7, slide=6, max_pass_reads=17) as ctx:
         rows, _ = ctx.scan_reads([s for _, s in demo_records])
         assert int((rows["status"] == eng.ST_PASS).sum()) == 17
+
+
+def test_span_batch_equals_back_to_back(eng, edge_records, demo_records):
+    """tps_submit_spans: reads separated by gaps of junk give the same rows as the packed batch, also for a
+    second context sharing the upload (tps_submit_shared)."""
+    rng = np.random.default_rng(4)
+    records = edge_records + demo_records[:10]
+    seqs = [s.encode() for _, s in records]
+    starts, lens, chunks, at = [], [], [], 0
+    for s in seqs:
+        gap = bytes(rng.choice(np.frombuffer(b"ACGTN@+\n", np.uint8), int(rng.integers(0, 40))))
+        chunks.append(gap)
+        at += len(gap)
+        starts.append(at)
+        lens.append(len(s))
+        chunks.append(s)
+        at += len(s)
+    chunks.append(b"CCCTAA" * 7)
+    buf = np.frombuffer(b"".join(chunks), dtype=np.uint8)
+    starts = np.array(starts, dtype=np.uint64)
+    lens = np.array(lens, dtype=np.uint32)
+    p4, p5 = orc.patterns_to_search("CCCTAA", 4), orc.patterns_to_search("CCCTAA", 5)
+    kw = dict(len_telopattern=6, min_seq_length=0, cutoff=0.3, slide=6, want_rawcount=True, rawcount_capacity=1 << 26)
+    with _ctx(eng, p4, **kw) as a, _ctx(eng, p5, max_batch_bases=1, **kw) as b:
+        want4 = a.scan_reads(seqs)
+        bid = a.submit_spans(buf, starts, lens, len(seqs))
+        b.submit_shared(a, bid)
+        got4, got5 = a.wait(bid), b.wait(bid)
+        with _ctx(eng, p5, **kw) as c:
+            want5 = c.scan_reads(seqs)
+    for got, want in ((got4, want4), (got5, want5)):
+        assert got[0].tobytes() == want[0].tobytes()
+        assert got[1].tobytes() == want[1].tobytes()
+    assert int((got4[0]["status"] == eng.ST_PASS).sum()) > 20
+    with _ctx(eng, p4, **kw) as a:
+        with pytest.raises(eng.TpsError):
+            a.submit_spans(buf[:100], starts, lens, len(seqs))     # last read ends beyond the uploaded bytes

@@ -28,6 +28,8 @@ struct Slot {
   uint32_t *d_flags = nullptr;
   uint16_t *d_masks = nullptr;
   uint64_t *d_off = nullptr;
+  uint32_t *d_len = nullptr;        /* read lengths of a span batch */
+  bool has_lens = false;
   tps_row *d_rows = nullptr;
   uint32_t *d_pass = nullptr;
   uint32_t *d_counters = nullptr;
@@ -164,7 +166,7 @@ void tps_destroy(tps_ctx *ctx) {
     Slot &s = ctx->slots[i];
     if (s.stream) cudaStreamSynchronize(s.stream);
     cudaFree(s.d_bases); cudaFree(s.d_codes); cudaFree(s.d_flags); cudaFree(s.d_masks);
-    cudaFree(s.d_off); cudaFree(s.d_rows); cudaFree(s.d_pass); cudaFree(s.d_counters);
+    cudaFree(s.d_off); cudaFree(s.d_len); cudaFree(s.d_rows); cudaFree(s.d_pass); cudaFree(s.d_counters);
     cudaFree(s.d_raw); cudaFree(s.d_cw);
     if (s.h_rows) cudaFreeHost(s.h_rows);
     if (s.h_counters) cudaFreeHost(s.h_counters);
@@ -332,6 +334,7 @@ int tps_create(tps_ctx **out, int device, const tps_params *params) {
     TPS_CC(cudaMalloc(&s.d_flags, ctx->cap_tiles * sizeof(uint32_t)));
     TPS_CC(cudaMalloc(&s.d_masks, ctx->cap_tiles * 32 * sizeof(uint16_t)));
     TPS_CC(cudaMalloc(&s.d_off, ((uint64_t)p.max_batch_reads + 1) * sizeof(uint64_t)));
+    TPS_CC(cudaMalloc(&s.d_len, (uint64_t)p.max_batch_reads * sizeof(uint32_t)));
     TPS_CC(cudaMalloc(&s.d_rows, (uint64_t)p.max_batch_reads * sizeof(tps_row)));
     TPS_CC(cudaMalloc(&s.d_pass, (uint64_t)ctx->max_pass * sizeof(uint32_t)));
     TPS_CC(cudaMalloc(&s.d_counters, 8 * sizeof(uint32_t)));
@@ -355,7 +358,8 @@ namespace {
  * `packed_by` the batch was already packed (K1) into that slot's code/flag/mask buffers by another
  * context: only K2..K4 run, reading them. */
 int enqueue_scan(tps_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t *d_bases, const uint64_t *d_off,
-                 uint32_t n_reads, uint64_t n_bases, tps_row *d_rows, bool timed, const Slot *packed_by = nullptr) {
+                 uint32_t n_reads, uint64_t n_bases, tps_row *d_rows, bool timed, const Slot *packed_by = nullptr,
+                 const uint32_t *d_len = nullptr) {
   const tps_params &p = ctx->p;
   cudaEvent_t *ev = ctx->ev[ctx->scan_seq % TPS_TIMING_RING];
   TPS_CUDA(ctx, cudaMemsetAsync(s.d_counters, 0, 8 * sizeof(uint32_t), st));
@@ -377,6 +381,7 @@ int enqueue_scan(tps_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t *d_bases,
   a.pk.flags = src.d_flags;
   a.pk.masks = src.d_masks;
   a.offsets = d_off;
+  a.lens = d_len;
   a.n_reads = n_reads;
   a.rows = d_rows;
   a.pass_list = s.d_pass;
@@ -426,12 +431,10 @@ int enqueue_scan(tps_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t *d_bases,
 
 extern "C" {
 
-int tps_submit(tps_ctx *ctx, const uint8_t *bases, const uint64_t *offsets, uint32_t n_reads, uint64_t batch_id) {
-  if (!ctx || !offsets || (!bases && n_reads)) return fail(ctx, TPS_EINVAL, "null argument");
+static int submit_common(tps_ctx *ctx, const uint8_t *bases, uint64_t n_bases, const uint64_t *starts,
+                         const uint32_t *lengths, uint32_t n_reads, uint64_t batch_id) {
   const tps_params &p = ctx->p;
   if (n_reads > p.max_batch_reads) return fail(ctx, TPS_ECAPACITY, "batch has %u reads, capacity %u", n_reads, p.max_batch_reads);
-  const uint64_t n_bases = offsets[n_reads];
-  if (offsets[0] != 0) return fail(ctx, TPS_EINVAL, "offsets[0] must be 0");
   if (n_bases > p.max_batch_bases) return fail(ctx, TPS_ECAPACITY, "batch has %llu bases, capacity %llu",
                                                (unsigned long long)n_bases, (unsigned long long)p.max_batch_bases);
   Slot *sl = nullptr;
@@ -443,9 +446,15 @@ int tps_submit(tps_ctx *ctx, const uint8_t *bases, const uint64_t *offsets, uint
   TPS_CUDA(ctx, cudaSetDevice(ctx->device));
   Slot &s = *sl;
   cudaStream_t st = s.stream;
-  TPS_CUDA(ctx, cudaMemcpyAsync(s.d_off, offsets, ((uint64_t)n_reads + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+  /* span batches carry n starts + n lengths, back-to-back batches n+1 offsets */
+  TPS_CUDA(ctx, cudaMemcpyAsync(s.d_off, starts, ((uint64_t)n_reads + (lengths ? 0 : 1)) * sizeof(uint64_t),
+                                cudaMemcpyHostToDevice, st));
+  if (lengths && n_reads)
+    TPS_CUDA(ctx, cudaMemcpyAsync(s.d_len, lengths, (uint64_t)n_reads * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
   if (n_bases) TPS_CUDA(ctx, cudaMemcpyAsync(s.d_bases, bases, n_bases, cudaMemcpyHostToDevice, st));
-  int rc = enqueue_scan(ctx, s, st, s.d_bases, s.d_off, n_reads, n_bases, s.d_rows, false);
+  s.has_lens = lengths != nullptr;
+  int rc = enqueue_scan(ctx, s, st, s.d_bases, s.d_off, n_reads, n_bases, s.d_rows, false, nullptr,
+                        lengths ? s.d_len : nullptr);
   if (rc) return rc;
   if (n_reads)
     TPS_CUDA(ctx, cudaMemcpyAsync(s.h_rows, s.d_rows, (uint64_t)n_reads * sizeof(tps_row), cudaMemcpyDeviceToHost, st));
@@ -455,6 +464,22 @@ int tps_submit(tps_ctx *ctx, const uint8_t *bases, const uint64_t *offsets, uint
   s.batch_id = batch_id;
   s.n_reads = n_reads;
   return TPS_OK;
+}
+
+int tps_submit(tps_ctx *ctx, const uint8_t *bases, const uint64_t *offsets, uint32_t n_reads, uint64_t batch_id) {
+  if (!ctx || !offsets || (!bases && n_reads)) return fail(ctx, TPS_EINVAL, "null argument");
+  if (offsets[0] != 0) return fail(ctx, TPS_EINVAL, "offsets[0] must be 0");
+  return submit_common(ctx, bases, offsets[n_reads], offsets, nullptr, n_reads, batch_id);
+}
+
+int tps_submit_spans(tps_ctx *ctx, const uint8_t *bases, uint64_t n_span, const uint64_t *starts,
+                     const uint32_t *lengths, uint32_t n_reads, uint64_t batch_id) {
+  if (!ctx || (n_reads && (!starts || !lengths)) || (!bases && n_span)) return fail(ctx, TPS_EINVAL, "null argument");
+  if (n_reads && starts[n_reads - 1] + lengths[n_reads - 1] > n_span)
+    return fail(ctx, TPS_EINVAL, "last read ends at %llu, beyond the %llu uploaded bytes",
+                (unsigned long long)(starts[n_reads - 1] + lengths[n_reads - 1]), (unsigned long long)n_span);
+  static const uint64_t zero = 0;
+  return submit_common(ctx, bases, n_span, n_reads ? starts : &zero, n_reads ? lengths : nullptr, n_reads, batch_id);
 }
 
 int tps_submit_shared(tps_ctx *ctx, tps_ctx *owner, uint64_t batch_id) {
@@ -475,7 +500,8 @@ int tps_submit_shared(tps_ctx *ctx, tps_ctx *owner, uint64_t batch_id) {
   TPS_CUDA(ctx, cudaSetDevice(ctx->device));
   Slot &s = *sl;
   cudaStream_t st = so->stream; /* owner's stream: ordered after its H2D + K1 and before its slot is reused */
-  int rc = enqueue_scan(ctx, s, st, so->d_bases, so->d_off, so->n_reads, 0, s.d_rows, false, so);
+  int rc = enqueue_scan(ctx, s, st, so->d_bases, so->d_off, so->n_reads, 0, s.d_rows, false, so,
+                        so->has_lens ? so->d_len : nullptr);
   if (rc) return rc;
   if (so->n_reads)
     TPS_CUDA(ctx, cudaMemcpyAsync(s.h_rows, s.d_rows, (uint64_t)so->n_reads * sizeof(tps_row), cudaMemcpyDeviceToHost, st));

@@ -81,6 +81,7 @@ typedef struct tps_fastx {
   int gz_eof;
   uint64_t window_bytes;
   int threads;
+  int slow_only;      /* never use the one-pass FASTQ reader (tests / tuning) */
   uint64_t n_records; /* records delivered so far */
   char err[256];
 } tps_fastx;
@@ -562,6 +563,9 @@ void tps_fastx_set_window(tps_fastx *fx, uint64_t bytes) {
   if (fx && bytes >= 4096) fx->window_bytes = bytes;
 }
 void tps_fastx_release(void *owner) { free(owner); }
+void tps_fastx_set_two_pass(tps_fastx *fx, int on) {
+  if (fx) fx->slow_only = on;
+}
 
 /* Next batch: at most reads_cap records and bases_cap bases, in file order.
  *   bases_out[offsets_out[i] .. offsets_out[i+1]) = bases of record i; recs_out[i] indexes its text
@@ -694,6 +698,307 @@ int tps_fastx_next(tps_fastx *fx, uint64_t bases_cap, uint32_t reads_cap, uint8_
   }
   fx->n_records += n;
   *n_reads = n;
+  return TPS_FX_OK;
+}
+
+/* ------------------------------------------------------------------ one-pass FASTQ -> span batch
+ * In a 4-line FASTQ record the quality line is as long as the sequence line, so a record that starts
+ * at byte x of the window owns at least 2*L + 6 bytes of text.  Placing its L bases at x/2 of the batch
+ * buffer therefore never collides with the next record -- and needs no knowledge of the records before
+ * it.  Every parser thread can then copy the sequence line WHILE it looks for its end (one pass over
+ * the text, streaming stores), instead of indexing first and gathering after a global prefix sum.  The
+ * batch is a "span batch": reads separated by small gaps (tps_submit_spans). */
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) static int64_t copy_line_avx2(uint8_t *dst, const uint8_t *src, uint64_t n) {
+  const __m256i nl = _mm256_set1_epi8('\n');
+  uint64_t i = 0;
+  if (n >= 32) {
+    const __m256i v = _mm256_loadu_si256((const __m256i *)src);
+    const uint32_t m = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(v, nl));
+    if (m) {
+      const uint32_t k = (uint32_t)__builtin_ctz(m);
+      memcpy(dst, src, k);
+      return (int64_t)k;
+    }
+    _mm256_storeu_si256((__m256i *)dst, v);
+    i = 32u - ((uintptr_t)dst & 31u); /* 1..32: from here dst + i is 32-byte aligned */
+  }
+  for (; i + 32 <= n; i += 32) {
+    const __m256i v = _mm256_loadu_si256((const __m256i *)(src + i));
+    const uint32_t m = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(v, nl));
+    if (m) {
+      const uint32_t k = (uint32_t)__builtin_ctz(m);
+      memcpy(dst + i, src + i, k);
+      return (int64_t)(i + k);
+    }
+    if (((uintptr_t)(dst + i) & 31u) == 0) _mm256_stream_si256((__m256i *)(dst + i), v);
+    else _mm256_storeu_si256((__m256i *)(dst + i), v);
+  }
+  const uint8_t *q = (const uint8_t *)memchr(src + i, '\n', n - i);
+  if (q) {
+    memcpy(dst + i, src + i, (size_t)(q - (src + i)));
+    return (int64_t)(q - src);
+  }
+  memcpy(dst + i, src + i, n - i);
+  return -1;
+}
+#endif
+
+/* copy src[0..] to dst up to (not including) the first '\n' within n bytes; returns the line length or
+ * -1 when there is no newline (n bytes were then copied) */
+static int64_t copy_line(uint8_t *dst, const uint8_t *src, uint64_t n) {
+#if defined(__x86_64__)
+  if (g_have_avx2 < 0) g_have_avx2 = __builtin_cpu_supports("avx2") ? 1 : 0;
+  if (g_have_avx2) return copy_line_avx2(dst, src, n);
+#endif
+  const uint8_t *q = (const uint8_t *)memchr(src, '\n', n);
+  memcpy(dst, src, q ? (size_t)(q - src) : n);
+  return q ? (int64_t)(q - src) : -1;
+}
+
+#define TPS_FX_NEED_SLOW (-100) /* internal: this window must take the two-pass path */
+
+/* records starting in [from, seg_end): parse + copy bases to dst[(record start) >> 1 ...] */
+static void scan_fastq_fused(const uint8_t *w, uint64_t from, uint64_t seg_end, uint64_t win_end, int final,
+                             uint8_t *dst, rec_vec *rv) {
+  uint64_t p = from;
+  rv->first = from;
+  rv->end = from;
+  while (p < seg_end) {
+    if (w[p] == '\n' || w[p] == '\r') {
+      ++p;
+      rv->end = p;
+      continue;
+    }
+    if (w[p] != '@') {
+      rv->status = TPS_FX_EFORMAT;
+      rv->err_at = p;
+      return;
+    }
+    int nl;
+    const uint64_t e1 = line_end(w, p, win_end, &nl);
+    if (!nl) break;
+    const uint64_t s0 = e1 + 1;
+    if (s0 >= win_end) break;
+    /* a complete record needs 2 * line bytes: a longer line cannot end inside this window, and
+     * copying more than (win_end - p) / 2 bytes would leave the first win/2 bytes of the batch buffer */
+    uint64_t lim = (win_end - p) / 2;
+    if (lim > win_end - s0) lim = win_end - s0;
+    const int64_t ll = copy_line(dst + (p >> 1), w + s0, lim);
+    if (ll < 0) break; /* sequence line runs past the window */
+    const uint64_t e2 = s0 + (uint64_t)ll;
+    const uint64_t p0 = e2 + 1;
+    if (p0 >= win_end) break;
+    if (w[p0] != '+') {
+      rv->status = TPS_FX_EFORMAT;
+      rv->err_at = p0;
+      return;
+    }
+    const uint64_t e3 = line_end(w, p0, win_end, &nl);
+    if (!nl) break;
+    const uint64_t q0 = e3 + 1;
+    uint64_t e4;
+    const uint64_t j = q0 + (e2 - s0);
+    if (j < win_end && w[j] == '\n' && (j + 1 == win_end || w[j + 1] == '@' || w[j + 1] == '\n')) {
+      e4 = j;
+      nl = 1;
+    } else {
+      e4 = q0 <= win_end ? line_end(w, q0, win_end, &nl) : win_end;
+      if (!nl && !final) break;
+    }
+    tps_fastx_rec r;
+    memset(&r, 0, sizeof(r));
+    set_title(&r, w, p + 1, e1 - (p + 1));
+    r.seq_off = s0;
+    r.seq_len = (uint32_t)rstrip_len(w + s0, e2 - s0);
+    r.seq_raw_len = (uint32_t)(e2 - s0);
+    r.qual_off = q0;
+    if (rstrip_len(w + q0, e4 - q0) != r.seq_len) {
+      rv->status = TPS_FX_EFORMAT;
+      rv->err_at = q0;
+      return;
+    }
+    /* the x/2 placement needs record bytes >= 2 * (copied bytes): only odd trailing blanks break it */
+    if ((e2 - s0) - r.seq_len > 4 || (nl ? e4 + 1 : e4) - p < 2 * (e2 - s0) + 2) {
+      rv->status = TPS_FX_NEED_SLOW;
+      return;
+    }
+    if (vec_push(rv, &r)) {
+      rv->status = TPS_FX_ENOMEM;
+      return;
+    }
+    p = nl ? e4 + 1 : e4;
+    rv->end = p;
+  }
+}
+
+static int next_spans_contiguous(tps_fastx *fx, uint64_t span_cap, uint32_t reads_cap, uint8_t *bases_out,
+                                 uint64_t *starts_out, uint32_t *lens_out, tps_fastx_rec *recs_out, uint32_t *n_reads,
+                                 uint64_t *span_used, const uint8_t **raw_base, void **raw_owner);
+
+/* Next batch as a span batch: read i = bases_out[starts_out[i] .. + lens_out[i]); *span_used bytes of
+ * bases_out are meaningful.  starts_out must hold reads_cap + 1 entries.  Otherwise like tps_fastx_next. */
+int tps_fastx_next_spans(tps_fastx *fx, uint64_t span_cap, uint32_t reads_cap, uint8_t *bases_out,
+                         uint64_t *starts_out, uint32_t *lens_out, tps_fastx_rec *recs_out, uint32_t *n_reads,
+                         uint64_t *span_used, const uint8_t **raw_base, void **raw_owner) {
+  if (!fx || !bases_out || !starts_out || !lens_out || !recs_out || !n_reads || !span_used || !raw_base || !raw_owner)
+    return fx_fail(fx, TPS_FX_EINVAL, "null argument");
+  *n_reads = 0;
+  *span_used = 0;
+  *raw_base = NULL;
+  *raw_owner = NULL;
+  if (reads_cap == 0 || span_cap < 64) return fx_fail(fx, TPS_FX_EINVAL, "zero capacity");
+  if (fx->format != TPS_FX_FASTQ || fx->slow_only)
+    return next_spans_contiguous(fx, span_cap, reads_cap, bases_out, starts_out, lens_out, recs_out, n_reads, span_used,
+                                 raw_base, raw_owner);
+  uint64_t want = 2 * span_cap; /* a record at window byte x lands at x/2 */
+  if (want > fx->window_bytes) want = fx->window_bytes;
+  const uint8_t *w = NULL;
+  uint8_t *chunk = NULL;
+  uint64_t win = 0;
+  int final = 0;
+  if (!fx->is_gz) {
+    if (fx->pos >= fx->map_len) return TPS_FX_OK;
+    w = fx->map + fx->pos;
+    win = fx->map_len - fx->pos;
+    if (win > want) win = want;
+    final = fx->pos + win == fx->map_len;
+  } else {
+    if (fx->carry_len == 0 && fx->gz_eof) return TPS_FX_OK;
+    if (fx->carry_len >= want) /* a carried record as large as the batch: the two-pass path reports it */
+      return next_spans_contiguous(fx, span_cap, reads_cap, bases_out, starts_out, lens_out, recs_out, n_reads,
+                                   span_used, raw_base, raw_owner);
+    chunk = (uint8_t *)malloc(want + 1);
+    if (!chunk) return fx_fail(fx, TPS_FX_ENOMEM, "out of memory for a %llu-byte chunk", (unsigned long long)want);
+    memcpy(chunk, fx->carry, fx->carry_len);
+    win = fx->carry_len;
+    while (win < want && !fx->gz_eof) {
+      uint64_t ask = want - win;
+      if (ask > (1u << 30)) ask = 1u << 30;
+      int n = gzread(fx->gz, chunk + win, (unsigned)ask);
+      if (n < 0) {
+        free(chunk);
+        return fx_fail(fx, TPS_FX_EIO, "gzip read error");
+      }
+      if (n == 0) fx->gz_eof = 1;
+      win += (uint64_t)n;
+    }
+    w = chunk;
+    final = fx->gz_eof;
+  }
+  int T = fx->threads;
+  if (T < 1) T = 1;
+  if (win < (uint64_t)T * (1u << 20)) T = 1;
+  rec_vec *parts = (rec_vec *)calloc((size_t)T, sizeof(rec_vec));
+  uint64_t *sst = (uint64_t *)calloc((size_t)T + 1, sizeof(uint64_t));
+  if (!parts || !sst) {
+    free(parts);
+    free(sst);
+    free(chunk);
+    return fx_fail(fx, TPS_FX_ENOMEM, "out of memory");
+  }
+  double t_ix = dbg_now();
+#pragma omp parallel for num_threads(T) schedule(static, 1)
+  for (int i = 0; i < T; ++i) sst[i] = i == 0 ? 0 : find_fastq_start(w, win / (uint64_t)T * (uint64_t)i, win);
+  sst[T] = win;
+  for (int i = T - 1; i >= 0; --i)
+    if (sst[i] > sst[i + 1]) sst[i] = sst[i + 1];
+#pragma omp parallel num_threads(T)
+  {
+#pragma omp for schedule(static, 1)
+    for (int i = 0; i < T; ++i) {
+      if (sst[i] < sst[i + 1]) scan_fastq_fused(w, sst[i], sst[i + 1], win, final, bases_out, &parts[i]);
+      else parts[i].first = parts[i].end = sst[i];
+    }
+    copy_fence();
+  }
+  /* the pieces must chain exactly; anything odd (format error, pathological blanks, a segment start
+   * guessed wrong) sends this window through the validating two-pass path */
+  int ok = 1, last = -1;
+  size_t total = 0;
+  uint64_t end = 0;
+  for (int i = 0; i < T && ok; ++i) {
+    if (parts[i].status) ok = 0;
+    else if (sst[i] < sst[i + 1]) {
+      if (last >= 0 && parts[last].end != parts[i].first) ok = 0;
+      last = i;
+      total += parts[i].n;
+      end = parts[i].end;
+      if (parts[i].end < sst[i + 1]) { /* incomplete record: nothing after it counts */
+        for (int j = i + 1; j < T; ++j) parts[j].n = 0;
+        break;
+      }
+    }
+  }
+  if (getenv("TPS_FX_DEBUG"))
+    fprintf(stderr, "[fastx] one-pass %.1f MB in %.4f s, %zu records, ok=%d\n", win / 1e6, dbg_now() - t_ix, total, ok);
+  if (!ok || (total == 0 && !final)) {
+    for (int i = 0; i < T; ++i) free(parts[i].v);
+    free(parts);
+    free(sst);
+    if (chunk) { /* gz: the bytes already inflated become the carry of the two-pass path */
+      free(fx->carry);
+      fx->carry = chunk;
+      fx->carry_len = win;
+    }
+    return next_spans_contiguous(fx, span_cap, reads_cap, bases_out, starts_out, lens_out, recs_out, n_reads, span_used,
+                                 raw_base, raw_owner);
+  }
+  uint32_t n = 0;
+  uint64_t consumed = end;
+  for (int i = 0; i < T; ++i) {
+    for (size_t k = 0; k < parts[i].n; ++k) {
+      if (n == reads_cap) {
+        consumed = parts[i].v[k].title_off - 1;
+        goto capped;
+      }
+      const tps_fastx_rec *r = &parts[i].v[k];
+      recs_out[n] = *r;
+      starts_out[n] = (r->title_off - 1) >> 1;
+      lens_out[n] = r->seq_len;
+      ++n;
+    }
+  }
+capped:
+  for (int i = 0; i < T; ++i) free(parts[i].v);
+  free(parts);
+  free(sst);
+  *span_used = n ? starts_out[n - 1] + lens_out[n - 1] : 0;
+  if (!fx->is_gz) {
+    *raw_base = w;
+    fx->pos += consumed;
+    if (n == 0) fx->pos = fx->map_len;
+  } else {
+    uint64_t left = n ? win - consumed : 0;
+    uint8_t *nc = (uint8_t *)realloc(fx->carry, left ? left : 1);
+    if (!nc) {
+      free(chunk);
+      return fx_fail(fx, TPS_FX_ENOMEM, "out of memory");
+    }
+    fx->carry = nc;
+    memcpy(fx->carry, chunk + consumed, left);
+    fx->carry_len = left;
+    if (n) {
+      *raw_base = chunk;
+      *raw_owner = chunk;
+    } else {
+      free(chunk);
+    }
+  }
+  fx->n_records += n;
+  *n_reads = n;
+  return TPS_FX_OK;
+}
+
+/* two-pass reader presented as a span batch (FASTA, and the fallback of the one-pass FASTQ reader) */
+static int next_spans_contiguous(tps_fastx *fx, uint64_t span_cap, uint32_t reads_cap, uint8_t *bases_out,
+                                 uint64_t *starts_out, uint32_t *lens_out, tps_fastx_rec *recs_out, uint32_t *n_reads,
+                                 uint64_t *span_used, const uint8_t **raw_base, void **raw_owner) {
+  int rc = tps_fastx_next(fx, span_cap, reads_cap, bases_out, starts_out, recs_out, n_reads, raw_base, raw_owner);
+  if (rc) return rc;
+  const uint32_t n = *n_reads;
+  *span_used = n ? starts_out[n] : 0;
+  for (uint32_t i = 0; i < n; ++i) lens_out[i] = (uint32_t)(starts_out[i + 1] - starts_out[i]);
   return TPS_FX_OK;
 }
 

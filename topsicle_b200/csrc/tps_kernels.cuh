@@ -49,7 +49,8 @@ struct TpsPacked {
 
 struct TpsScanArgs {
   TpsPacked pk;
-  const uint64_t *offsets;
+  const uint64_t *offsets; /* read starts; without `lens`, offsets[r+1] ends read r (back-to-back batch) */
+  const uint32_t *lens;    /* read lengths of a span batch (reads separated by gaps), or null */
   uint32_t n_reads;
   tps_row *rows;
   uint32_t *pass_list;
@@ -361,7 +362,7 @@ tps_trc_kernel(const TpsScanArgs a, const TpsPatTable pt) {
   const uint32_t r = blockIdx.x * TPS_K2_WARPS + warp;
   if (r >= a.n_reads) return;
   const uint64_t off = a.offsets[r];
-  const uint32_t L = (uint32_t)(a.offsets[r + 1] - off);
+  const uint32_t L = a.lens ? a.lens[r] : (uint32_t)(a.offsets[r + 1] - off);
   tps_row row;
   row.length = L;
   row.status = TPS_ST_FILTERED;
@@ -517,7 +518,7 @@ tps_trc_reg_kernel(const TpsScanArgs a, const TpsPatTable pt) {
   const uint32_t r = blockIdx.x * TPS_K2R_WARPS + warp;
   if (r >= a.n_reads) return;
   const uint64_t off = a.offsets[r];
-  const uint32_t L = (uint32_t)(a.offsets[r + 1] - off);
+  const uint32_t L = a.lens ? a.lens[r] : (uint32_t)(a.offsets[r + 1] - off);
   tps_row row;
   row.length = L;
   row.status = TPS_ST_FILTERED;
@@ -611,7 +612,7 @@ tps_window_kernel(const TpsScanArgs a, const TpsPatTable pt) {
     const uint32_t tb0 = (item - pi * a.tiles_max) * a.tile_bases;
     const uint32_t r = a.pass_list[pi];
     const uint64_t off = a.offsets[r];
-    const uint32_t L = (uint32_t)(a.offsets[r + 1] - off);
+    const uint32_t L = a.lens ? a.lens[r] : (uint32_t)(a.offsets[r + 1] - off);
     const uint32_t M = L < a.maxlengthtelo ? L : a.maxlengthtelo; /* allsteps.py:263-264 */
     const uint32_t nreg = M > t ? M - t : 0u;                      /* |z|, allsteps.py:267-271 */
     const uint32_t nW = nreg >= W ? (nreg - W) / s + 1u : 0u;      /* allsteps.py:219 */

@@ -90,6 +90,8 @@ def load_library() -> C.CDLL:
     lib.tps_free_pinned.argtypes = [vp]
     lib.tps_submit.restype = C.c_int
     lib.tps_submit.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint64]
+    lib.tps_submit_spans.restype = C.c_int
+    lib.tps_submit_spans.argtypes = [vp, vp, C.c_uint64, vp, vp, C.c_uint32, C.c_uint64]
     lib.tps_submit_shared.restype = C.c_int
     lib.tps_submit_shared.argtypes = [vp, vp, C.c_uint64]
     lib.tps_wait.restype = C.c_int
@@ -246,6 +248,16 @@ class ScanContext:
         bid = next(_batch_ids)
         self._check(self.lib.tps_submit(self._h, bases.ctypes.data, offsets.ctypes.data, n_reads, bid))
         self._inflight[bid] = (bases, offsets, n_reads)  # keep buffers alive
+        return bid
+
+    def submit_spans(self, bases: np.ndarray, starts: np.ndarray, lens: np.ndarray, n_reads: int) -> int:
+        """Submit a span batch: read i = bases[starts[i] : starts[i] + lens[i]] (gaps in between are ignored)."""
+        assert bases.dtype == np.uint8 and starts.dtype == np.uint64 and lens.dtype == np.uint32
+        assert bases.flags.c_contiguous and starts.flags.c_contiguous and lens.flags.c_contiguous
+        bid = next(_batch_ids)
+        self._check(self.lib.tps_submit_spans(self._h, bases.ctypes.data, bases.size, starts.ctypes.data,
+                                              lens.ctypes.data, n_reads, bid))
+        self._inflight[bid] = (bases, (starts, lens), n_reads)  # keep buffers alive
         return bid
 
     def submit_shared(self, owner: "ScanContext", bid: int) -> int:

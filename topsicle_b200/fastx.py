@@ -58,6 +58,11 @@ def host_library() -> C.CDLL:
         lib.tps_fastx_next.restype = C.c_int
         lib.tps_fastx_next.argtypes = [vp, C.c_uint64, C.c_uint32, vp, vp, vp, C.POINTER(C.c_uint32),
                                        C.POINTER(vp), C.POINTER(vp)]
+        lib.tps_fastx_next_spans.restype = C.c_int
+        lib.tps_fastx_next_spans.argtypes = [vp, C.c_uint64, C.c_uint32, vp, vp, vp, vp, C.POINTER(C.c_uint32),
+                                             C.POINTER(C.c_uint64), C.POINTER(vp), C.POINTER(vp)]
+        lib.tps_fastx_set_two_pass.restype = None
+        lib.tps_fastx_set_two_pass.argtypes = [vp, C.c_int]
         lib.tps_fastx_find_id.restype = C.c_uint32
         lib.tps_fastx_find_id.argtypes = [vp, vp, C.c_uint32, C.c_char_p, C.c_uint32, vp, C.c_uint32]
         lib.tps_format_rawcount.restype = C.c_int64
@@ -72,11 +77,14 @@ class Batch:
     text.  `first_read` = index of read 0 within its file.  Keep the batch (and its FastxFile)
     alive while slicing raw text; call `release()` when done."""
 
-    def __init__(self, lib, n_reads, bases, offsets, recs, raw_base, raw_owner, first_read, fmt):
+    def __init__(self, lib, n_reads, bases, offsets, recs, raw_base, raw_owner, first_read, fmt, lens=None,
+                 span=None):
         self._lib = lib
         self.n_reads = n_reads
         self.bases = bases
-        self.offsets = offsets
+        self.offsets = offsets          # read starts (n_reads + 1 entries when the reads are back to back)
+        self.lens = lens                # uint32 read lengths of a span batch, None for a back-to-back batch
+        self.span = span if span is not None else int(offsets[n_reads])   # bytes of `bases` in use
         self.recs = recs
         self._raw = raw_base
         self._owner = raw_owner
@@ -85,7 +93,13 @@ class Batch:
 
     @property
     def n_bases(self) -> int:
+        if self.lens is not None:
+            return int(self.lens[:self.n_reads].sum(dtype=np.uint64))
         return int(self.offsets[self.n_reads])
+
+    def bounds(self, i):
+        a = int(self.offsets[i])
+        return (a, a + int(self.lens[i])) if self.lens is not None else (a, int(self.offsets[i + 1]))
 
     def _text(self, off, n) -> bytes:
         return C.string_at(self._raw + int(off), int(n))
@@ -99,7 +113,8 @@ class Batch:
         return C.string_at(self._raw + r[0] + r[4], r[5]).decode("utf-8", "replace")
 
     def sequence(self, i) -> bytes:
-        return self.bases[int(self.offsets[i]):int(self.offsets[i + 1])].tobytes()
+        a, b = self.bounds(i)
+        return self.bases[a:b].tobytes()
 
     def quality(self, i) -> bytes:
         r = self.recs[i]
@@ -172,6 +187,36 @@ class FastxFile:
                   self.reads_delivered, self.format)
         self.reads_delivered += n.value
         return b
+
+    def next_spans(self, bases: np.ndarray, starts: np.ndarray, lens: np.ndarray, max_reads: int | None = None,
+                   max_span: int | None = None, recs: np.ndarray | None = None) -> Batch | None:
+        """Next batch as a span batch (`tps_submit_spans`): read i = bases[starts[i] : starts[i] + lens[i]].
+        FASTQ takes the one-pass reader (reads land at half their file offset, small gaps in between);
+        FASTA falls back to back-to-back packing.  `starts` needs max_reads + 1 entries."""
+        assert bases.dtype == np.uint8 and starts.dtype == np.uint64 and lens.dtype == np.uint32
+        reads_cap = min(len(starts) - 1, len(lens), max_reads if max_reads is not None else 1 << 31)
+        span_cap = min(bases.size, max_span if max_span is not None else 1 << 62)
+        if recs is None:
+            recs = np.empty(reads_cap, dtype=REC_DTYPE)
+        else:
+            reads_cap = min(reads_cap, len(recs))
+        n, span = C.c_uint32(0), C.c_uint64(0)
+        raw, owner = C.c_void_p(), C.c_void_p()
+        rc = self._lib.tps_fastx_next_spans(self._h, span_cap, reads_cap, bases.ctypes.data, starts.ctypes.data,
+                                            lens.ctypes.data, recs.ctypes.data, C.byref(n), C.byref(span),
+                                            C.byref(raw), C.byref(owner))
+        if rc != 0:
+            raise FastxError(rc, self._lib.tps_fastx_last_error(self._h).decode())
+        if n.value == 0:
+            return None
+        b = Batch(self._lib, n.value, bases, starts, recs[:n.value], raw.value, owner.value, self.reads_delivered,
+                  self.format, lens=lens, span=span.value)
+        self.reads_delivered += n.value
+        return b
+
+    def set_two_pass(self, on: bool = True):
+        """Force the index-then-gather reader (the one-pass FASTQ reader's validating fallback)."""
+        self._lib.tps_fastx_set_two_pass(self._h, 1 if on else 0)
 
     def close(self):
         if self._h and self._h.value:

@@ -105,12 +105,14 @@ class _OrderedSink:
 class _Slot:
     def __init__(self, max_bases, max_reads):
         self.bases = engine.PinnedBuffer(max_bases)
-        self.offsets = engine.PinnedBuffer((max_reads + 1) * 8)
+        self.offsets = engine.PinnedBuffer((max_reads + 1) * 8)     # read starts (uint64)
+        self.lens = engine.PinnedBuffer(max_reads * 4)              # read lengths (uint32)
         self.recs = np.empty(max_reads, dtype=fastx.REC_DTYPE)
 
     def free(self):
         self.bases.free()
         self.offsets.free()
+        self.lens.free()
 
 
 def make_context(cfg: ScanConfig, device: int, max_batch_reads: int, max_batch_bases: int, n_slots: int,
@@ -179,20 +181,21 @@ class _DeviceWorker:
         for s in self.slots:
             s.free()
 
-    def submit(self, bases, offsets):
-        bid = self.ctxs[0].submit(bases, offsets)
+    def submit(self, bases, starts, lens, n_reads):
+        bid = self.ctxs[0].submit_spans(bases, starts, lens, n_reads)
         for c in self.ctxs[1:]:
             c.submit_shared(self.ctxs[0], bid)
         return bid
 
-    def _scan_sub(self, ci, bases, offsets, lo, hi):
+    def _scan_sub(self, ci, bases, starts, lens, lo, hi):
         """Synchronous scan of reads [lo, hi) of a batch under config ci, splitting again on capacity
         overflow (more TRC-pass reads or raw counts than the context's per-batch capacity)."""
-        base0 = int(offsets[lo])
-        sub_off = (offsets[lo:hi + 1] - offsets[lo]).astype(np.uint64)
-        sub_bases = np.ascontiguousarray(bases[base0:int(offsets[hi])])
+        base0 = int(starts[lo])
+        sub_starts = (starts[lo:hi] - starts[lo]).astype(np.uint64)
+        sub_lens = np.ascontiguousarray(lens[lo:hi])
+        sub_bases = np.ascontiguousarray(bases[base0:int(starts[hi - 1]) + int(lens[hi - 1])])
         try:
-            bid = self.ctxs[0].submit(sub_bases, sub_off)
+            bid = self.ctxs[0].submit_spans(sub_bases, sub_starts, sub_lens, hi - lo)
             if ci == 0:
                 rows, raw = self.ctxs[0].wait(bid)
             else:
@@ -208,7 +211,8 @@ class _DeviceWorker:
             if e.code != -4 or hi - lo <= 1:
                 raise
             mid = (lo + hi) // 2
-            return self._scan_sub(ci, bases, offsets, lo, mid) + self._scan_sub(ci, bases, offsets, mid, hi)
+            return (self._scan_sub(ci, bases, starts, lens, lo, mid)
+                    + self._scan_sub(ci, bases, starts, lens, mid, hi))
 
     def finish(self, item, records_cfg, keep):
         slot, batch, bid, seq = item
@@ -228,8 +232,8 @@ class _DeviceWorker:
                 parts = [(0, n, *waited[ci])]
             else:
                 mid = n // 2
-                parts = (self._scan_sub(ci, slot.bases.array, batch.offsets, 0, mid)
-                         + self._scan_sub(ci, slot.bases.array, batch.offsets, mid, n))
+                parts = (self._scan_sub(ci, slot.bases.array, batch.offsets, batch.lens, 0, mid)
+                         + self._scan_sub(ci, slot.bases.array, batch.offsets, batch.lens, mid, n))
             passes = []
             scanned = 0
             for lo, hi, rows, raw in parts:
@@ -329,9 +333,9 @@ class Scanner:
                     if slot is None:
                         break
                     t = time.perf_counter()
-                    batch = fx.next_batch(slot.bases.array, slot.offsets.array.view(np.uint64),
-                                          max_reads=w0.max_batch_reads, max_bases=w0.max_batch_bases,
-                                          recs=slot.recs)
+                    batch = fx.next_spans(slot.bases.array, slot.offsets.array.view(np.uint64),
+                                          slot.lens.array.view(np.uint32), max_reads=w0.max_batch_reads,
+                                          max_span=w0.max_batch_bases, recs=slot.recs)
                     tm["parse"] += time.perf_counter() - t
                     if batch is None:
                         break
@@ -362,9 +366,9 @@ class Scanner:
                     if got is None:
                         break
                     slot, batch, seq = got
-                    nb = batch.n_bases
                     t = time.perf_counter()
-                    bid = w.submit(slot.bases.array[:nb], batch.offsets[:batch.n_reads + 1])
+                    bid = w.submit(slot.bases.array[:batch.span], batch.offsets[:batch.n_reads],
+                                   batch.lens[:batch.n_reads], batch.n_reads)
                     tm["submit"] += time.perf_counter() - t
                     inflight.append((slot, batch, bid, seq))
                 while inflight and not errors:

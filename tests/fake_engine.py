@@ -58,7 +58,7 @@ class OracleContext:
         self._pending[bid] = owner._pending[bid]
         return bid
 
-    def wait(self, bid):
+    def wait(self, bid, raw_view=False):
         buf, off = self._pending.pop(bid)
         cfg = self.cfg
         n = len(off) - 1

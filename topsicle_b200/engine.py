@@ -217,9 +217,13 @@ class ScanContext:
         if rc != 0:
             raise TpsError(rc, self.lib.tps_last_error(None).decode())
         self._inflight = {}
+        self._raw_pin = None
 
     # -- lifetime
     def close(self):
+        if getattr(self, "_raw_pin", None) is not None:
+            self._raw_pin.free()
+            self._raw_pin = None
         if getattr(self, "_h", None) and self._h.value:
             self.lib.tps_destroy(self._h)
             self._h = C.c_void_p()
@@ -267,7 +271,9 @@ class ScanContext:
         self._inflight[bid] = owner._inflight[bid]
         return bid
 
-    def wait(self, bid: int):
+    def wait(self, bid: int, raw_view: bool = False):
+        """Rows (and raw count tables) of a finished batch.  With `raw_view` the tables are returned as a view
+        of this context's page-locked landing buffer, valid until its next wait()."""
         bases, offsets, n_reads = self._inflight[bid]
         rows = np.empty(n_reads, dtype=ROW_DTYPE)
         n_pass = C.c_uint32(0)
@@ -276,10 +282,15 @@ class ScanContext:
         try:
             if self.want_rawcount:
                 self._check(self.lib.tps_batch_info(self._h, bid, C.byref(n_pass), C.byref(elems)))
-                raw = np.empty(min(int(elems.value), int(self.params.rawcount_capacity)), dtype=np.uint8)
+                need = min(int(elems.value), int(self.params.rawcount_capacity))
+                if self._raw_pin is None or self._raw_pin.nbytes < need:      # page-locked landing zone for the
+                    if self._raw_pin is not None:                             # count tables (D2H at PCIe speed)
+                        self._raw_pin.free()
+                    self._raw_pin = PinnedBuffer(max(need * 5 // 4, 1 << 20))
+                raw = self._raw_pin.array[:need]
                 self._check(self.lib.tps_wait(self._h, bid, rows.ctypes.data, C.byref(n_pass), raw.ctypes.data,
                                               raw.size, C.byref(elems)))
-                raw = raw[:elems.value]
+                raw = raw[:elems.value] if raw_view else raw[:elems.value].copy()
             else:
                 self._check(self.lib.tps_wait(self._h, bid, rows.ctypes.data, C.byref(n_pass), None, 0,
                                               C.byref(elems)))

@@ -222,7 +222,7 @@ class _DeviceWorker:
         waited = []
         for ctx in self.ctxs:                      # release every context's slot before any re-scan
             try:
-                waited.append(ctx.wait(bid))
+                waited.append(ctx.wait(bid, True))  # tables are copied out per read by harvest()
             except engine.TpsError as e:
                 if e.code != -4 or n <= 1:
                     raise

@@ -108,6 +108,9 @@ typedef struct tps_ctx tps_ctx;
 int tps_abi_version(void);
 const char *tps_build_info(void);
 
+/* Number of CUDA devices visible to the library (0 if none / no driver). */
+int tps_device_count(void);
+
 /* Create / destroy a scan context on CUDA device `device`.
  * Replaces: the per-call setup in patternTRC_count / bound_detect
  * (re.compile of every literal, allsteps.py:167-168, 240-241). */

@@ -146,6 +146,15 @@ const char *tps_build_info(void) {
 
 const char *tps_last_error(const tps_ctx *ctx) { return ctx ? ctx->err : g_create_error; }
 
+int tps_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
 void *tps_alloc_pinned(size_t bytes) {
   void *p = nullptr;
   if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {

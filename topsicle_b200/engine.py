@@ -78,6 +78,7 @@ def load_library() -> C.CDLL:
     vp, u8p, u64p, u32p = C.c_void_p, C.POINTER(C.c_uint8), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)
     lib.tps_abi_version.restype = C.c_int
     lib.tps_build_info.restype = C.c_char_p
+    lib.tps_device_count.restype = C.c_int
     lib.tps_last_error.restype = C.c_char_p
     lib.tps_last_error.argtypes = [vp]
     lib.tps_create.restype = C.c_int
@@ -114,6 +115,11 @@ def load_library() -> C.CDLL:
         raise TpsError(-101, "ABI version mismatch")
     _lib = lib
     return lib
+
+
+def device_count() -> int:
+    """CUDA devices visible to the library."""
+    return int(load_library().tps_device_count())
 
 
 def count_threshold(cutoff: float, len_telopattern: int, no_bp: int = 1000) -> int:

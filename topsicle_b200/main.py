@@ -56,11 +56,7 @@ def visible_devices():
     env = os.environ.get("TOPSICLE_DEVICES")
     if env:
         return [int(x) for x in env.split(",") if x.strip() != ""]
-    try:
-        import torch
-        n = torch.cuda.device_count()
-    except Exception:  # noqa: BLE001
-        n = 0
+    n = engine.device_count()
     return list(range(n)) if n > 0 else [0]
 
 
@@ -249,9 +245,16 @@ def analysis_run(args):
     csv_rows = [[] for _ in telo_phrases]
     t0 = time.time()
     total_bases = total_reads = 0
+    # batch size: 256 MiB of bases by default, less when the whole input is small (page-locking and
+    # zeroing GBs of staging memory would then cost more than the scan itself)
+    try:
+        total_bytes = sum(os.path.getsize(f) * (4 if f.endswith(".gz") else 1) for f in filenames)
+    except OSError:
+        total_bytes = 1 << 40
+    auto_bases = min(1 << 28, max(1 << 24, 1 << max(0, (total_bytes // 4).bit_length())))
     scanner = pipeline.Scanner(scan_configs(args, telo_phrases, patterns, sliding_val), devices=devices,
                                threads=args.threads or 0,
-                               max_batch_bases=int(os.environ.get("TOPSICLE_BATCH_BASES", 1 << 28)),
+                               max_batch_bases=int(os.environ.get("TOPSICLE_BATCH_BASES", auto_bases)),
                                max_batch_reads=int(os.environ.get("TOPSICLE_BATCH_READS", 1 << 17)))
     try:
         for seq_loc in filenames:

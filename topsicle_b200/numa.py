@@ -13,11 +13,14 @@ def cpus_near_device(device: int):
     or None if that cannot be determined."""
     try:
         import pynvml
-        import torch
         pynvml.nvmlInit()
-        p = torch.cuda.get_device_properties(device)
-        bus_id = f"{getattr(p, 'pci_domain_id', 0):08x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
-        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus_id.encode())
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:                                   # CUDA ordinal -> NVML index / UUID
+            tok = [t.strip() for t in vis.split(",") if t.strip()][device]
+            h = pynvml.nvmlDeviceGetHandleByUUID(tok.encode()) if tok.startswith("GPU-") else \
+                pynvml.nvmlDeviceGetHandleByIndex(int(tok))
+        else:
+            h = pynvml.nvmlDeviceGetHandleByIndex(device)
         words = (os.cpu_count() + 63) // 64
         mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
         cpus = {i * 64 + b for i, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}

@@ -76,3 +76,40 @@ def test_read_check_only_that_read(tmp_path, monkeypatch):
     assert rows[1:] == ["demo.fastq,5,0.791,ERR11436636.163616,3010", ""]
     sub = hashlib.md5(open(out / "demo.fastq_trc_over_0.7.fastq", "rb").read()).hexdigest()
     assert sub == case["files"]["demo.fastq_trc_over_0.7.fastq"]
+
+
+def test_directory_of_files_scanned_concurrently(tmp_path, monkeypatch):
+    """--inputDir with several files (.fastq.gz, .fastq, .fasta): files are read concurrently, every
+    file's rows stay in file order, subset files are per file with the reference's naming rule."""
+    fake_engine.install(monkeypatch)
+    import gzip
+    import shutil
+    from oracle import topsicle_oracle as orc
+    from topsicle_b200 import main as tmain
+    recs = list(orc.read_fastx(os.path.join(GOLD, "demo.fastq.gz")))
+    indir, out = tmp_path / "in", tmp_path / "out"
+    indir.mkdir()
+    shutil.copy(os.path.join(GOLD, "demo.fastq.gz"), indir / "a.fastq.gz")
+    with open(indir / "b.fq", "w") as fh:
+        for rid, s in recs[10:40]:
+            fh.write(f"@{rid} x\n{s}\n+\n{'I' * len(s)}\n")
+    with open(indir / "c.fasta", "w") as fh:
+        for rid, s in recs[:25]:
+            fh.write(f">{rid}\n" + "\n".join(s[i:i + 70] for i in range(0, len(s), 70)) + "\n")
+    if hasattr(tmain.tprint, "logfile"):
+        del tmain.tprint.logfile
+    monkeypatch.setenv("TOPSICLE_BATCH_READS", "7")
+    tmain.main(["-i", str(indir), "-o", str(out), "--pattern", "CCCTAAA", "--slide", "6", "--devices", "0", "1"])
+    rows = [ln.split(",") for ln in open(out / "telolengths_all.csv", newline="").read().split("\r\n")[1:] if ln]
+    want = {}
+    for stem, sub in (("a.fastq", recs), ("b", recs[10:40]), ("c", recs[:25])):
+        want[stem] = [[stem, "5", f"{r['trc']:.3f}", r["id"], str(r["telo_length"])]
+                      for r in orc.scan_records(sub, "CCCTAAA", 5, 0.7, 9000, 100, 6, 100, 20000, exact=True)]
+    for stem in want:
+        assert [r for r in rows if r[0] == stem] == want[stem], stem
+    assert len(rows) == sum(len(v) for v in want.values())
+    names = set(os.listdir(out))
+    assert {"a.fastq_trc_over_0.7.fastq", "b_trc_over_0.7.fastq", "c_trc_over_0.7.fasta"} <= names
+    sub_c = open(out / "c_trc_over_0.7.fasta").read()
+    assert [ln[1:] for ln in sub_c.split("\n") if ln.startswith(">")] == [r[3] for r in want["c"]]
+    assert all(len(ln) <= 60 for ln in sub_c.split("\n"))

@@ -21,6 +21,7 @@ import csv
 import datetime
 import os
 import sys
+import threading
 import time
 from collections import defaultdict
 
@@ -32,6 +33,7 @@ from .patterns import patterns_to_search, validate_literals
 
 version_number = "1.0.0"
 Topsicle_output_prefix = "Topsicle"
+_csv_lock = threading.Lock()
 
 
 def get_log_path(args):
@@ -134,12 +136,13 @@ class _FileWriter:
                         fh.write(text)
                 self.image_num[k] += 1
         if new_first:
-            with open(self.csv_path, mode="a", newline="") as file:
+            with _csv_lock, open(self.csv_path, mode="a", newline="") as file:   # files are scanned concurrently
                 csv.writer(file).writerows(new_first)
 
     def close(self):
         if self.subset_handle is not None:
             self.subset_handle.close()
+            self.subset_handle = None
 
 
 def scan_configs(args, telo_phrases, patterns, sliding_val):
@@ -153,28 +156,23 @@ def scan_configs(args, telo_phrases, patterns, sliding_val):
             for k, pats in zip(telo_phrases, patterns)]
 
 
-def process_file(args, seq_loc, telo_phrases, scanner, sliding_val, csv_rows_out):
-    """One input file, every telophrase, one pass (reference: main.py:52-154, once per phrase).
-    Returns per phrase the list of (telomere length, TRC)."""
+def file_job(args, seq_loc, telo_phrases, scanner, sliding_val):
+    """Writer + scan job of one input file, every telophrase in one pass (reference: process_file,
+    main.py:52-154, once per phrase and per file).  Returns (writer, FileJob)."""
     tprint("subsetting raw dataset based on TRC cutoff")
     min_cutoff = min(args.cutoff) if isinstance(args.cutoff, (list, tuple)) else args.cutoff
-    cfgs = scanner.cfgs
-    w = _FileWriter(args, seq_loc, cfgs, telo_phrases, min_cutoff, sliding_val,
+    w = _FileWriter(args, seq_loc, scanner.cfgs, telo_phrases, min_cutoff, sliding_val,
                     f"{args.outputDir}/telolengths_all.csv")
     if w.subset_exists:
         tprint(f"Temporary fasta file already exists: {w.subset}. Using existing file.")
-    if args.read_check:
-        tprint("checking specific read:", args.read_check)
-    try:
-        stats = scanner.scan_file(seq_loc, w, records_cfg=w.records_cfg)
-    finally:
+
+    def on_done(stats):
         w.close()
-    if not w.subset_exists:
-        tprint(f"Temporary fasta file with TRC more than {min_cutoff}:", w.subset)
-    for k in range(1, len(cfgs)):
-        csv_rows_out[k].extend(w.rows[k])
-    process_file.last_stats = stats
-    return w.results
+        w.stats = stats
+        if not w.subset_exists:
+            tprint(f"Temporary fasta file with TRC more than {min_cutoff}:", w.subset)
+
+    return w, pipeline.FileJob(seq_loc, w, records_cfg=w.records_cfg, on_done=on_done)
 
 
 def analysis_run(args):
@@ -256,17 +254,30 @@ def analysis_run(args):
                                threads=args.threads or 0,
                                max_batch_bases=int(os.environ.get("TOPSICLE_BATCH_BASES", auto_bases)),
                                max_batch_reads=int(os.environ.get("TOPSICLE_BATCH_READS", 1 << 17)))
+    writers = []
     try:
+        if args.read_check:
+            tprint("checking specific read:", args.read_check)
+        jobs = []
         for seq_loc in filenames:
-            results = process_file(args, seq_loc, telo_phrases, scanner, sliding_val, csv_rows)
-            st = process_file.last_stats
+            w, job = file_job(args, seq_loc, telo_phrases, scanner, sliding_val)
+            writers.append(w)
+            jobs.append(job)
+        # files are scanned concurrently (the reference's Pool is over files, main.py:232-235): one reader
+        # thread per file in flight, every GPU takes batches of any file
+        for st in scanner.scan_files(jobs):
             total_bases += st.n_bases
             total_reads += st.n_reads
+        for w in writers:
             for k, telo_phrase in enumerate(telo_phrases):
-                for telolen, trc_val in results[k]:
+                for telolen, trc_val in w.results[k]:
                     phrase_to_telo[telo_phrase].append(telolen)
                     phrase_to_trc[telo_phrase].append(trc_val)
+                if k:
+                    csv_rows[k].extend(w.rows[k])
     finally:
+        for w in writers:
+            w.close()
         scanner.close()
     # the CSV is phrase-major (the reference's outer loop is over telo_phrases, main.py:206-235): rows of
     # the first phrase were appended as they were found, those of the other phrases follow here

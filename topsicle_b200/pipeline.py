@@ -17,6 +17,7 @@ exactly as the reference writes them.
 """
 from __future__ import annotations
 
+import os
 import queue
 import sys
 import threading
@@ -303,106 +304,173 @@ class Scanner:
 
         `sink(BatchResult)` is called in file order; BatchResult.passes[k] holds the TRC-pass reads
         under cfgs[k].  `records_cfg=k` attaches the SeqIO.write text of the reads passing cfgs[k].
-        `keep_ids` restricts the harvest to those read ids.
+        `keep_ids` restricts the harvest to those read ids."""
+        return self.scan_files([FileJob(path, sink, records_cfg=records_cfg, keep_ids=keep_ids)], readers=1)[0]
 
-        Threads: one reader (the C parser, itself multi-threaded, fills free pinned slots) and one
-        worker per device (submit / wait / harvest), so parsing, PCIe and the kernels overlap."""
-        stats = FileStats()
-        ordered = _OrderedSink(sink)
-        tm = stats.timing
-        for k in ("open", "parse", "submit", "finish", "close"):
-            tm[k] = 0.0
-        t_open = time.perf_counter()
-        fx = fastx.FastxFile(path, threads=self.threads)
-        tm["open"] = time.perf_counter() - t_open
-        stats.format_name = fx.format_name
+    def scan_files(self, jobs: Sequence["FileJob"], *, readers: int = 0) -> list:
+        """Scan several files concurrently (the reference's unit of parallelism is the input file,
+        main.py:232-235): `readers` reader threads each parse one file at a time into the shared pool of
+        pinned slots, one worker per device scans whatever is ready.  Every job's sink still sees its
+        batches in file order; `job.on_done(stats)` fires after its last batch.  Returns the FileStats
+        in job order.
+
+        Threads: the C parser is itself multi-threaded on plain files; `.gz` files are inflated by one
+        thread each, which is why several readers matter for directories of compressed files."""
+        jobs = list(jobs)
+        n_workers = len(self.workers)
+        n_threads = self.threads or len(os.sched_getaffinity(0))
+        if readers <= 0:
+            readers = min(len(jobs), max(1, n_threads // 2), 8)
+        readers = max(1, min(readers, len(jobs)))
+        fx_threads = max(1, n_threads // readers)
         errors = []
         ready = queue.Queue()
         free = queue.Queue()
         for w in self.workers:
             for slot in w.slots:
                 free.put(slot)
-        n_workers = len(self.workers)
         w0 = self.workers[0]
+        todo = queue.Queue()
+        for j in jobs:
+            j._reset()
+            todo.put(j)
+        lock = threading.Lock()
+        tm_parse = [0.0]
+
+        def finalize(job):
+            t = time.perf_counter()
+            if job.fx is not None:
+                job.fx.close()
+                job.fx = None
+            job.stats.timing["close"] = time.perf_counter() - t
+            if job.on_done is not None:
+                job.on_done(job.stats)
+
+        def delivered(job, res):
+            """Called by a worker after it finished one batch of `job`."""
+            job.ordered.put(res)
+            with lock:
+                job.n_delivered += 1
+                done = job.eof and job.n_delivered == job.stats.n_batches
+            if done:
+                finalize(job)
 
         def read_loop():
-            seq = 0
             try:
                 while not errors:
-                    slot = free.get()
-                    if slot is None:
-                        break
+                    try:
+                        job = todo.get_nowait()
+                    except queue.Empty:
+                        return
                     t = time.perf_counter()
-                    batch = fx.next_spans(slot.bases.array, slot.offsets.array.view(np.uint64),
-                                          slot.lens.array.view(np.uint32), max_reads=w0.max_batch_reads,
-                                          max_span=w0.max_batch_bases, recs=slot.recs)
-                    tm["parse"] += time.perf_counter() - t
-                    if batch is None:
-                        break
-                    stats.n_reads += batch.n_reads
-                    stats.n_bases += batch.n_bases
-                    stats.n_batches += 1
-                    ready.put((slot, batch, seq))
-                    seq += 1
+                    job.fx = fastx.FastxFile(job.path, threads=fx_threads)
+                    job.stats.timing["open"] = time.perf_counter() - t
+                    job.stats.format_name = job.fx.format_name
+                    seq = 0
+                    while not errors:
+                        slot = free.get()
+                        if slot is None:
+                            free.put(None)      # let the other readers see the stop signal too
+                            return
+                        t = time.perf_counter()
+                        batch = job.fx.next_spans(slot.bases.array, slot.offsets.array.view(np.uint64),
+                                                  slot.lens.array.view(np.uint32), max_reads=w0.max_batch_reads,
+                                                  max_span=w0.max_batch_bases, recs=slot.recs)
+                        job.stats.timing["parse"] += time.perf_counter() - t
+                        if batch is None:
+                            free.put(slot)
+                            break
+                        job.stats.n_reads += batch.n_reads
+                        job.stats.n_bases += batch.n_bases
+                        job.stats.n_batches += 1
+                        ready.put((job, slot, batch, seq))
+                        seq += 1
+                    with lock:
+                        job.eof = True
+                        done = job.n_delivered == job.stats.n_batches
+                    if done:
+                        finalize(job)
             except BaseException as e:  # noqa: BLE001 - reported to the caller below
                 errors.append(e)
-            finally:
-                for _ in range(n_workers):
-                    ready.put(None)
 
         def work_loop(w: _DeviceWorker):
             inflight = []
             depth = len(w.slots)
+
+            def finish_oldest():
+                job, item = inflight.pop(0)
+                t = time.perf_counter()
+                res = w.finish(item, job.records_cfg, job.keep_ids)
+                job.stats.timing["finish"] += time.perf_counter() - t
+                free.put(item[0])
+                delivered(job, res)
+
             try:
                 while not errors:
                     if inflight and (len(inflight) >= depth or ready.empty()):
-                        item = inflight.pop(0)
-                        t = time.perf_counter()
-                        ordered.put(w.finish(item, records_cfg, keep_ids))
-                        tm["finish"] += time.perf_counter() - t
-                        free.put(item[0])
+                        finish_oldest()
                         continue
                     got = ready.get()
                     if got is None:
                         break
-                    slot, batch, seq = got
+                    job, slot, batch, seq = got
                     t = time.perf_counter()
                     bid = w.submit(slot.bases.array[:batch.span], batch.offsets[:batch.n_reads],
                                    batch.lens[:batch.n_reads], batch.n_reads)
-                    tm["submit"] += time.perf_counter() - t
-                    inflight.append((slot, batch, bid, seq))
+                    job.stats.timing["submit"] += time.perf_counter() - t
+                    inflight.append((job, (slot, batch, bid, seq)))
                 while inflight and not errors:
-                    item = inflight.pop(0)
-                    t = time.perf_counter()
-                    ordered.put(w.finish(item, records_cfg, keep_ids))
-                    tm["finish"] += time.perf_counter() - t
-                    free.put(item[0])
+                    finish_oldest()
             except BaseException as e:  # noqa: BLE001
                 errors.append(e)
-                free.put(None)   # unblock the reader
+                free.put(None)   # unblock the readers
 
-        # the reader thread re-acquires the GIL between two C parser calls while the workers harvest in
+        # the reader threads re-acquire the GIL between two C parser calls while the workers harvest in
         # Python: with the default 5 ms switch interval that wait would dominate the parse of a batch
         old_switch = sys.getswitchinterval()
         sys.setswitchinterval(1e-4)
-        reader = threading.Thread(target=read_loop, name="tps-reader")
-        ths = [threading.Thread(target=work_loop, args=(w,), name=f"tps-dev{w.device}") for w in self.workers]
+        rthreads = [threading.Thread(target=read_loop, name=f"tps-reader{i}") for i in range(readers)]
+        wthreads = [threading.Thread(target=work_loop, args=(w,), name=f"tps-dev{w.device}") for w in self.workers]
         try:
-            reader.start()
-            for t in ths:
+            for t in rthreads + wthreads:
                 t.start()
-            for t in ths:
+            for t in rthreads:
                 t.join()
-            free.put(None)
-            reader.join()
+            for _ in range(n_workers):
+                ready.put(None)
+            for t in wthreads:
+                t.join()
             if errors:
                 raise errors[0]
         finally:
             sys.setswitchinterval(old_switch)
-            t_close = time.perf_counter()
-            fx.close()
-            tm["close"] = time.perf_counter() - t_close
-        return stats
+            for j in jobs:
+                if j.fx is not None:
+                    j.fx.close()
+                    j.fx = None
+        return [j.stats for j in jobs]
+
+
+class FileJob:
+    """One input file of a `Scanner.scan_files` call."""
+
+    def __init__(self, path: str, sink: Callable[[BatchResult], None], *, records_cfg: int | None = None,
+                 keep_ids=None, on_done: Callable[[FileStats], None] | None = None):
+        self.path = path
+        self.sink = sink
+        self.records_cfg = records_cfg
+        self.keep_ids = keep_ids
+        self.on_done = on_done
+        self._reset()
+
+    def _reset(self):
+        self.stats = FileStats()
+        for k in ("open", "parse", "submit", "finish", "close"):
+            self.stats.timing[k] = 0.0
+        self.ordered = _OrderedSink(self.sink)
+        self.fx = None
+        self.eof = False
+        self.n_delivered = 0
 
 
 def scan_file(path: str, cfgs: Sequence[ScanConfig], sink: Callable[[BatchResult], None], *,

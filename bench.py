@@ -29,6 +29,8 @@ import numpy as np  # noqa: E402
 METRIC = "telomere_scan_throughput"
 UNIT = "Gbases/s"
 ALG_BYTES_PER_BASE = 1.25  # K1: 1 B ASCII read + 0.25 B 2-bit code written
+# the dominant kernel: bulk-copy (TMA) staged pack kernel unless the register-staged one is forced
+K1_KERNEL = "tps_pack_kernel" if os.environ.get("TPS_K1_TMA") == "0" else "tps_pack_tma_kernel"
 
 
 def parse_args():
@@ -43,7 +45,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-reads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--streams", type=int, default=2,
+    ap.add_argument("--streams", type=int, default=3,
                     help="kernel-only leg: issue consecutive (independent) batches on this many batch slots/streams")
     ap.add_argument("--no-parse", action="store_true", help="skip the FASTQ-file end-to-end leg")
     ap.add_argument("--parse-passes", type=int, default=2)
@@ -130,7 +132,7 @@ def hbm_peak():
 
 
 def ncu_traffic_per_base():
-    """dram bytes per base of tps_pack_kernel from the committed ncu --set full capture."""
+    """dram bytes per base of the pack kernel (K1) from the committed ncu --set full capture."""
     try:
         with open(os.path.join(REPO, "profiles", "k1_traffic.json")) as fh:
             return float(json.load(fh)["dram_bytes_per_base"])
@@ -426,11 +428,12 @@ def main():
                 "trc_pass_reads_per_step": n_pass,
                 "device_ms_per_step": {"k1_pack": k1_ms, "k2_trc": k2_ms, "k3k4_windows_changepoint": k3_ms,
                                        "scan_total": dev_ms},
-                "roofline": {"bound": "hbm", "kernel": "tps_pack_kernel", "achieved": achieved, "peak": peak,
+                "roofline": {"bound": "hbm", "kernel": K1_KERNEL, "achieved": achieved, "peak": peak,
                              "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                              "algorithmic_bytes_per_base": ALG_BYTES_PER_BASE,
                              "traffic": (tpb * bases_timed / a.steps) if tpb else None,
-                             "whole_scan_frac": alg_bytes / (dev_ms * 1e-3) / 1e9 / peak},
+                             "whole_scan_frac": alg_bytes / (dev_ms * 1e-3) / 1e9 / peak,
+                             "pipelined_scan_frac": ALG_BYTES_PER_BASE * value / peak / world},
                 "cpu_baseline": cpu, "parity_sample": parity, "e2e": e2e, "e2e_from_fastq": e2e_file, "gpu_launches": int(launches),
                 "clocks": clocks,
                 "generate_s": t_gen,

@@ -171,6 +171,9 @@ int tps_sync(tps_ctx *ctx);
 #define TPS_N_TIMINGS 4
 #define TPS_TIMING_RING 256
 int tps_get_timings(tps_ctx *ctx, uint32_t back, float ms[TPS_N_TIMINGS]);
+/* Timeline of overlapping scans: ms[i] = time from the start of the timed scan `base_back` calls ago to
+ * event i of the scan `back` calls ago (0 = K1 start, 1 = K1 end, 2 = K2 end, 3 = K4 end). */
+int tps_get_timeline(tps_ctx *ctx, uint32_t back, uint32_t base_back, float ms[TPS_N_TIMINGS]);
 /* Number of kernels this context has launched so far. */
 uint64_t tps_kernel_launches(const tps_ctx *ctx);
 

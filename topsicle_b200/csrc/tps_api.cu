@@ -22,6 +22,7 @@ thread_local char g_create_error[512] = "";
 
 struct Slot {
   cudaStream_t stream = nullptr;
+  cudaEvent_t e_in = nullptr, e_k1 = nullptr, e_tail = nullptr; /* split mode: slot -> pack -> tail -> slot */
   cudaEvent_t done = nullptr;
   uint8_t *d_bases = nullptr;
   uint32_t *d_codes = nullptr;
@@ -60,6 +61,16 @@ struct tps_ctx {
   uint32_t k2r_smem = 0;
   void (*k3_fn)(const TpsScanArgs, const TpsPatTable) = nullptr;
   int k1_grid = 0, k1_unroll = 4;
+  /* split mode (default): every K1 of the context runs on `pack_stream` (low priority), every K2..K4 on
+   * `tail_stream` (high priority), so the tail kernels of batch i run under the K1 of batch i+1 -- the
+   * HBM-bound pack kernel leaves issue slots and registers free, the issue-bound tail kernels use them --
+   * and never more than one K1 is resident.  The slot streams keep the copies and the ordering. */
+  bool split = false;
+  cudaStream_t pack_stream = nullptr, tail_stream = nullptr;
+  bool k1_tma = false;          /* K1 through the bulk-copy engine (tps_pack_tma_kernel) */
+  uint32_t k1t_stages = 0, k1t_smem = 0, k1t_unroll = 4; /* stage = 4 * k1t_unroll KiB */
+  int k1t_grid = 0;
+  void (*k1t_fn)(const uint4 *, uint32_t *, uint32_t *, uint16_t *, uint64_t, uint32_t) = nullptr;
   void (*k1_fn)(const uint4 *, uint32_t *, uint32_t *, uint16_t *, uint64_t) = nullptr;
   uint64_t cap_tiles = 0;
   Slot slots[4];
@@ -141,7 +152,7 @@ extern "C" {
 int tps_abi_version(void) { return TPS_ABI_VERSION; }
 
 const char *tps_build_info(void) {
-  return "topsicle_b200 sm_100a; kernels: tps_pack_kernel, tps_trc_reg_kernel<K>, tps_trc_kernel<K>, tps_window_kernel<K>, tps_changepoint_kernel; " __DATE__;
+  return "topsicle_b200 sm_100a; kernels: tps_pack_tma_kernel, tps_pack_kernel, tps_trc_reg_kernel<K>, tps_trc_kernel<K>, tps_window_kernel<K>, tps_changepoint_kernel; " __DATE__;
 }
 
 const char *tps_last_error(const tps_ctx *ctx) { return ctx ? ctx->err : g_create_error; }
@@ -180,8 +191,13 @@ void tps_destroy(tps_ctx *ctx) {
     if (s.h_rows) cudaFreeHost(s.h_rows);
     if (s.h_counters) cudaFreeHost(s.h_counters);
     if (s.done) cudaEventDestroy(s.done);
+    if (s.e_in) cudaEventDestroy(s.e_in);
+    if (s.e_k1) cudaEventDestroy(s.e_k1);
+    if (s.e_tail) cudaEventDestroy(s.e_tail);
     if (s.stream) cudaStreamDestroy(s.stream);
   }
+  if (ctx->pack_stream) { cudaStreamSynchronize(ctx->pack_stream); cudaStreamDestroy(ctx->pack_stream); }
+  if (ctx->tail_stream) { cudaStreamSynchronize(ctx->tail_stream); cudaStreamDestroy(ctx->tail_stream); }
   for (int r = 0; r < TPS_TIMING_RING; ++r)
     for (int i = 0; i < 4; ++i)
       if (ctx->ev[r][i]) cudaEventDestroy(ctx->ev[r][i]);
@@ -328,14 +344,53 @@ int tps_create(tps_ctx **out, int device, const tps_params *params) {
     int v = atoi(e);
     if (v >= 1 && v <= occ1) ctx->k1_grid = ctx->n_sms * v;
   }
+  {
+    /* K1 variant: bulk-copy (TMA) staged, TPS_K1_STAGES x 16 KiB per CTA (default), or register-staged
+     * (TPS_K1_TMA=0, kept for A/B measurements) */
+    const char *e = getenv("TPS_K1_TMA");
+    ctx->k1_tma = !(e && atoi(e) == 0);
+    if (ctx->k1_tma) {
+      const char *se = getenv("TPS_K1_STAGES");
+      int stages = se ? atoi(se) : 4;
+      if (stages < 2) stages = 2;
+      if (stages > 12) stages = 12;
+      ctx->k1t_stages = (uint32_t)stages;
+      if (const char *ke = getenv("TPS_K1_STAGE_KB")) ctx->k1t_unroll = atoi(ke) <= 8 ? 2u : 4u;
+      ctx->k1t_smem = ctx->k1t_stages * (TPS_K1T_STAGE_BYTES(ctx->k1t_unroll) + 16u);
+      int want_per_sm = 2; /* 2 CTAs x 4 stages x 16 KiB in flight per SM measured best (profiles/README.md) */
+      if (const char *ce = getenv("TPS_K1_CTAS_PER_SM")) want_per_sm = atoi(ce);
+      if (want_per_sm < 1) want_per_sm = 1;
+      if (want_per_sm > 6) want_per_sm = 6;
+      ctx->k1t_fn = ctx->k1t_unroll == 2 ? tps_pack_tma_kernel<2> : tps_pack_tma_kernel<4>;
+      TPS_CC(cudaFuncSetAttribute(ctx->k1t_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->k1t_smem));
+      int occt = 0;
+      TPS_CC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occt, ctx->k1t_fn, TPS_K1T_THREADS, ctx->k1t_smem));
+      if (occt < 1) occt = 1;
+      const int per_sm = want_per_sm < occt ? want_per_sm : occt;
+      ctx->k1t_grid = ctx->n_sms * per_sm;
+    }
+  }
   ctx->k3_grid = (uint32_t)(ctx->n_sms * (occ3 > 0 ? occ3 : 1));
   ctx->k4_grid = (uint32_t)(ctx->n_sms * (occ4 > 0 ? (occ4 > 4 ? 4 : occ4) : 1));
 
+  {
+    const char *e = getenv("TPS_SPLIT_STREAMS"); /* 0 = everything of a batch on its slot's stream */
+    ctx->split = !(e && atoi(e) == 0);
+    if (ctx->split) {
+      int pr_lo = 0, pr_hi = 0;
+      TPS_CC(cudaDeviceGetStreamPriorityRange(&pr_lo, &pr_hi));
+      TPS_CC(cudaStreamCreateWithPriority(&ctx->pack_stream, cudaStreamNonBlocking, pr_lo));
+      TPS_CC(cudaStreamCreateWithPriority(&ctx->tail_stream, cudaStreamNonBlocking, pr_hi));
+    }
+  }
   ctx->cap_tiles = (p.max_batch_bases + 511) / 512;
   const uint64_t cap_pad = ((p.max_batch_bases + 2047) / 2048) * 2048;
   for (uint32_t i = 0; i < p.n_slots; ++i) {
     Slot &s = ctx->slots[i];
     TPS_CC(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    TPS_CC(cudaEventCreateWithFlags(&s.e_in, cudaEventDisableTiming));
+    TPS_CC(cudaEventCreateWithFlags(&s.e_k1, cudaEventDisableTiming));
+    TPS_CC(cudaEventCreateWithFlags(&s.e_tail, cudaEventDisableTiming));
     TPS_CC(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
     TPS_CC(cudaMalloc(&s.d_bases, cap_pad));
     TPS_CC(cudaMemset(s.d_bases, 'N', cap_pad));
@@ -368,21 +423,46 @@ namespace {
  * context: only K2..K4 run, reading them. */
 int enqueue_scan(tps_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t *d_bases, const uint64_t *d_off,
                  uint32_t n_reads, uint64_t n_bases, tps_row *d_rows, bool timed, const Slot *packed_by = nullptr,
-                 const uint32_t *d_len = nullptr) {
+                 const uint32_t *d_len = nullptr, tps_ctx *stream_owner = nullptr) {
   const tps_params &p = ctx->p;
   cudaEvent_t *ev = ctx->ev[ctx->scan_seq % TPS_TIMING_RING];
-  TPS_CUDA(ctx, cudaMemsetAsync(s.d_counters, 0, 8 * sizeof(uint32_t), st));
-  if (timed) TPS_CUDA(ctx, cudaEventRecord(ev[0], st));
+  /* split mode: `st` (the slot's stream) orders the batch against its copies; K1 goes to the context's
+   * pack stream, K2..K4 to its tail stream.  A follower context (packed_by) runs on the owner's streams. */
+  tps_ctx *so = stream_owner ? stream_owner : ctx;
+  const bool split = so->split;
+  cudaStream_t sp = split ? so->pack_stream : st; /* K1 */
+  cudaStream_t sh = split ? so->tail_stream : st; /* K2..K4 */
+  if (split) {
+    TPS_CUDA(ctx, cudaEventRecord(s.e_in, st));
+    TPS_CUDA(ctx, cudaStreamWaitEvent(packed_by ? sh : sp, s.e_in, 0));
+  } else {
+    TPS_CUDA(ctx, cudaMemsetAsync(s.d_counters, 0, 8 * sizeof(uint32_t), st));
+  }
+  if (timed) TPS_CUDA(ctx, cudaEventRecord(ev[0], sp));
   const uint64_t n_tiles = (n_bases + 511) / 512;
-  if (n_tiles && !packed_by) {
+  if (n_tiles && !packed_by && ctx->k1_tma) {
+    const uint64_t st_tiles = TPS_K1T_STAGE_TILES(ctx->k1t_unroll);
+    const uint64_t want = (n_tiles + st_tiles - 1) / st_tiles;
+    int grid = (int)(want < (uint64_t)ctx->k1t_grid ? want : (uint64_t)ctx->k1t_grid);
+    ctx->k1t_fn<<<grid, TPS_K1T_THREADS, ctx->k1t_smem, sp>>>(
+        reinterpret_cast<const uint4 *>(d_bases), s.d_codes, s.d_flags, s.d_masks, n_tiles, ctx->k1t_stages);
+    ctx->launches++;
+  } else if (n_tiles && !packed_by) {
     const uint64_t per_cta = (uint64_t)(TPS_K1_THREADS / 32) * ctx->k1_unroll;
     uint64_t want = (n_tiles + per_cta - 1) / per_cta;
     int grid = (int)(want < (uint64_t)ctx->k1_grid ? want : (uint64_t)ctx->k1_grid);
-    ctx->k1_fn<<<grid, TPS_K1_THREADS, 0, st>>>(reinterpret_cast<const uint4 *>(d_bases), s.d_codes, s.d_flags,
+    ctx->k1_fn<<<grid, TPS_K1_THREADS, 0, sp>>>(reinterpret_cast<const uint4 *>(d_bases), s.d_codes, s.d_flags,
                                                      s.d_masks, n_tiles);
     ctx->launches++;
   }
-  if (timed) TPS_CUDA(ctx, cudaEventRecord(ev[1], st));
+  if (timed) TPS_CUDA(ctx, cudaEventRecord(ev[1], sp));
+  if (split) {
+    if (!packed_by) {
+      TPS_CUDA(ctx, cudaEventRecord(s.e_k1, sp));
+      TPS_CUDA(ctx, cudaStreamWaitEvent(sh, s.e_k1, 0));
+    }
+    TPS_CUDA(ctx, cudaMemsetAsync(s.d_counters, 0, 8 * sizeof(uint32_t), sh));
+  }
   TpsScanArgs a;
   memset(&a, 0, sizeof(a));
   const Slot &src = packed_by ? *packed_by : s;
@@ -415,22 +495,26 @@ int enqueue_scan(tps_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t *d_bases,
   if (n_reads) {
     a.lin_words = ctx->k2_lin_words;
     if (ctx->k2_reg)
-      ctx->k2r_fn<<<(n_reads + TPS_K2R_WARPS - 1) / TPS_K2R_WARPS, TPS_K2R_WARPS * 32, ctx->k2r_smem, st>>>(a, ctx->pt);
+      ctx->k2r_fn<<<(n_reads + TPS_K2R_WARPS - 1) / TPS_K2R_WARPS, TPS_K2R_WARPS * 32, ctx->k2r_smem, sh>>>(a, ctx->pt);
     else
-      ctx->k2_fn<<<(n_reads + TPS_K2_WARPS - 1) / TPS_K2_WARPS, TPS_K2_WARPS * 32, ctx->k2_smem, st>>>(a, ctx->pt);
+      ctx->k2_fn<<<(n_reads + TPS_K2_WARPS - 1) / TPS_K2_WARPS, TPS_K2_WARPS * 32, ctx->k2_smem, sh>>>(a, ctx->pt);
     ctx->launches++;
   }
-  if (timed) TPS_CUDA(ctx, cudaEventRecord(ev[2], st));
+  if (timed) TPS_CUDA(ctx, cudaEventRecord(ev[2], sh));
   if (n_reads && !(p.flags & TPS_FLAG_STEP1_ONLY)) {
     a.lin_words = ctx->k3_lin_words;
     a.tile_words = ctx->k3_tile_words;
-    ctx->k3_fn<<<ctx->k3_grid, TPS_K3_THREADS, ctx->k3_smem, st>>>(a, ctx->pt);
-    tps_changepoint_kernel<<<ctx->k4_grid, TPS_K4_THREADS, 0, st>>>(a);
+    ctx->k3_fn<<<ctx->k3_grid, TPS_K3_THREADS, ctx->k3_smem, sh>>>(a, ctx->pt);
+    tps_changepoint_kernel<<<ctx->k4_grid, TPS_K4_THREADS, 0, sh>>>(a);
     ctx->launches += 2;
   }
   if (timed) {
-    TPS_CUDA(ctx, cudaEventRecord(ev[3], st));
+    TPS_CUDA(ctx, cudaEventRecord(ev[3], sh));
     ctx->scan_seq++;
+  }
+  if (split) { /* the slot's stream continues (D2H, next batch) only after the tail kernels */
+    TPS_CUDA(ctx, cudaEventRecord(s.e_tail, sh));
+    TPS_CUDA(ctx, cudaStreamWaitEvent(st, s.e_tail, 0));
   }
   TPS_CUDA(ctx, cudaGetLastError());
   return TPS_OK;
@@ -510,7 +594,7 @@ int tps_submit_shared(tps_ctx *ctx, tps_ctx *owner, uint64_t batch_id) {
   Slot &s = *sl;
   cudaStream_t st = so->stream; /* owner's stream: ordered after its H2D + K1 and before its slot is reused */
   int rc = enqueue_scan(ctx, s, st, so->d_bases, so->d_off, so->n_reads, 0, s.d_rows, false, so,
-                        so->has_lens ? so->d_len : nullptr);
+                        so->has_lens ? so->d_len : nullptr, owner);
   if (rc) return rc;
   if (so->n_reads)
     TPS_CUDA(ctx, cudaMemcpyAsync(s.h_rows, s.d_rows, (uint64_t)so->n_reads * sizeof(tps_row), cudaMemcpyDeviceToHost, st));
@@ -606,6 +690,19 @@ int tps_get_timings(tps_ctx *ctx, uint32_t back, float ms[TPS_N_TIMINGS]) {
   TPS_CUDA(ctx, cudaEventSynchronize(ev[3]));
   for (int i = 0; i < 3; ++i) TPS_CUDA(ctx, cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
   TPS_CUDA(ctx, cudaEventElapsedTime(&ms[3], ev[0], ev[3]));
+  return TPS_OK;
+}
+
+int tps_get_timeline(tps_ctx *ctx, uint32_t back, uint32_t base_back, float ms[TPS_N_TIMINGS]) {
+  if (!ctx || !ms) return TPS_EINVAL;
+  if (back >= TPS_TIMING_RING || back >= ctx->scan_seq || base_back >= TPS_TIMING_RING || base_back >= ctx->scan_seq)
+    return fail(ctx, TPS_ESTATE, "timed scan %u / %u steps back is not recorded (ring of %d)", back, base_back,
+                TPS_TIMING_RING);
+  cudaEvent_t *ev = ctx->ev[(ctx->scan_seq - 1 - back) % TPS_TIMING_RING];
+  cudaEvent_t *e0 = ctx->ev[(ctx->scan_seq - 1 - base_back) % TPS_TIMING_RING];
+  TPS_CUDA(ctx, cudaEventSynchronize(ev[3]));
+  TPS_CUDA(ctx, cudaEventSynchronize(e0[3]));
+  for (int i = 0; i < 4; ++i) TPS_CUDA(ctx, cudaEventElapsedTime(&ms[i], e0[0], ev[i]));
   return TPS_OK;
 }
 

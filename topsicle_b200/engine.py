@@ -107,6 +107,8 @@ def load_library() -> C.CDLL:
     lib.tps_sync.argtypes = [vp]
     lib.tps_get_timings.restype = C.c_int
     lib.tps_get_timings.argtypes = [vp, C.c_uint32, C.POINTER(C.c_float * 4)]
+    lib.tps_get_timeline.restype = C.c_int
+    lib.tps_get_timeline.argtypes = [vp, C.c_uint32, C.c_uint32, C.POINTER(C.c_float * 4)]
     lib.tps_kernel_launches.restype = C.c_uint64
     lib.tps_kernel_launches.argtypes = [vp]
     lib.tps_debug_copy.restype = C.c_int
@@ -334,6 +336,13 @@ class ScanContext:
         ms = (C.c_float * 4)()
         self._check(self.lib.tps_get_timings(self._h, back, C.byref(ms)))
         return dict(k1_pack=ms[0], k2_trc=ms[1], k3_windows_cp=ms[2], total=ms[3])
+
+    def timeline(self, back: int, base_back: int):
+        """Event times (ms) of the scan `back` calls ago relative to the start of the scan `base_back` calls ago:
+        (K1 start, K1 end, K2 end, K4 end)."""
+        ms = (C.c_float * 4)()
+        self._check(self.lib.tps_get_timeline(self._h, back, base_back, C.byref(ms)))
+        return tuple(float(x) for x in ms)
 
     def kernel_launches(self) -> int:
         return int(self.lib.tps_kernel_launches(self._h))

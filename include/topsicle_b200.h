@@ -179,8 +179,8 @@ uint64_t tps_kernel_launches(const tps_ctx *ctx);
 
 /* Test hooks: copy internal device arrays of slot 0 to the host after a scan.
  * what: 0 = 2-bit code words (uint32 per 16 bases), 1 = invalid-group flag words
- * (uint32 per 512 bases), 2 = exact validity masks (uint16 per 16 bases, defined only
- * for the groups of 512-base tiles whose flag word is non-zero), 3 = pass list (uint32 read indices, unordered). */
+ * (uint32 per 512 bases), 2 = validity masks as K2/K3 see them (uint16 per 16 bases: 0xFFFF for an
+ * unflagged group, else rebuilt from the group's ASCII bytes), 3 = pass list (uint32 read indices, unordered). */
 int tps_debug_copy(tps_ctx *ctx, int what, void *dst, size_t bytes);
 
 #ifdef __cplusplus

@@ -54,9 +54,8 @@ def test_k1_pack_matches_numpy(eng):
     got_flag = ((flags[np.arange(ng) >> 5] >> (np.arange(ng) & 31).astype(np.uint32)) & 1).astype(bool)
     assert np.array_equal(got_flag[:full], want_flag[:full])
     want_mask = (valid.astype(np.uint32) << g.astype(np.uint32)).sum(axis=1).astype(np.uint16)
-    idx = np.nonzero(want_flag[:full])[0]
-    assert len(idx) > 50
-    assert np.array_equal(masks[idx], want_mask[idx])
+    assert want_flag[:full].sum() > 50
+    assert np.array_equal(masks[:full], want_mask[:full])
 
 
 # ------------------------------------------------------------------------------- step 1

@@ -27,7 +27,7 @@ struct Slot {
   uint8_t *d_bases = nullptr;
   uint32_t *d_codes = nullptr;
   uint32_t *d_flags = nullptr;
-  uint16_t *d_masks = nullptr;
+  const uint8_t *last_bases = nullptr; /* ASCII batch of the last scan (slot- or caller-owned) */
   uint64_t *d_off = nullptr;
   uint32_t *d_len = nullptr;        /* read lengths of a span batch */
   bool has_lens = false;
@@ -70,8 +70,8 @@ struct tps_ctx {
   bool k1_tma = false;          /* K1 through the bulk-copy engine (tps_pack_tma_kernel) */
   uint32_t k1t_stages = 0, k1t_smem = 0, k1t_unroll = 4; /* stage = 4 * k1t_unroll KiB */
   int k1t_grid = 0;
-  void (*k1t_fn)(const uint4 *, uint32_t *, uint32_t *, uint16_t *, uint64_t, uint32_t) = nullptr;
-  void (*k1_fn)(const uint4 *, uint32_t *, uint32_t *, uint16_t *, uint64_t) = nullptr;
+  void (*k1t_fn)(const uint4 *, uint32_t *, uint32_t *, uint64_t, uint32_t) = nullptr;
+  void (*k1_fn)(const uint4 *, uint32_t *, uint32_t *, uint64_t) = nullptr;
   uint64_t cap_tiles = 0;
   Slot slots[4];
   cudaEvent_t ev[TPS_TIMING_RING][4]; /* CUDA-event ring: one set of 4 events per timed scan */
@@ -185,7 +185,7 @@ void tps_destroy(tps_ctx *ctx) {
   for (int i = 0; i < 4; ++i) {
     Slot &s = ctx->slots[i];
     if (s.stream) cudaStreamSynchronize(s.stream);
-    cudaFree(s.d_bases); cudaFree(s.d_codes); cudaFree(s.d_flags); cudaFree(s.d_masks);
+    cudaFree(s.d_bases); cudaFree(s.d_codes); cudaFree(s.d_flags);
     cudaFree(s.d_off); cudaFree(s.d_len); cudaFree(s.d_rows); cudaFree(s.d_pass); cudaFree(s.d_counters);
     cudaFree(s.d_raw); cudaFree(s.d_cw);
     if (s.h_rows) cudaFreeHost(s.h_rows);
@@ -396,7 +396,6 @@ int tps_create(tps_ctx **out, int device, const tps_params *params) {
     TPS_CC(cudaMemset(s.d_bases, 'N', cap_pad));
     TPS_CC(cudaMalloc(&s.d_codes, ctx->cap_tiles * 32 * sizeof(uint32_t)));
     TPS_CC(cudaMalloc(&s.d_flags, ctx->cap_tiles * sizeof(uint32_t)));
-    TPS_CC(cudaMalloc(&s.d_masks, ctx->cap_tiles * 32 * sizeof(uint16_t)));
     TPS_CC(cudaMalloc(&s.d_off, ((uint64_t)p.max_batch_reads + 1) * sizeof(uint64_t)));
     TPS_CC(cudaMalloc(&s.d_len, (uint64_t)p.max_batch_reads * sizeof(uint32_t)));
     TPS_CC(cudaMalloc(&s.d_rows, (uint64_t)p.max_batch_reads * sizeof(tps_row)));
@@ -445,14 +444,14 @@ int enqueue_scan(tps_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t *d_bases,
     const uint64_t want = (n_tiles + st_tiles - 1) / st_tiles;
     int grid = (int)(want < (uint64_t)ctx->k1t_grid ? want : (uint64_t)ctx->k1t_grid);
     ctx->k1t_fn<<<grid, TPS_K1T_THREADS, ctx->k1t_smem, sp>>>(
-        reinterpret_cast<const uint4 *>(d_bases), s.d_codes, s.d_flags, s.d_masks, n_tiles, ctx->k1t_stages);
+        reinterpret_cast<const uint4 *>(d_bases), s.d_codes, s.d_flags, n_tiles, ctx->k1t_stages);
     ctx->launches++;
   } else if (n_tiles && !packed_by) {
     const uint64_t per_cta = (uint64_t)(TPS_K1_THREADS / 32) * ctx->k1_unroll;
     uint64_t want = (n_tiles + per_cta - 1) / per_cta;
     int grid = (int)(want < (uint64_t)ctx->k1_grid ? want : (uint64_t)ctx->k1_grid);
     ctx->k1_fn<<<grid, TPS_K1_THREADS, 0, sp>>>(reinterpret_cast<const uint4 *>(d_bases), s.d_codes, s.d_flags,
-                                                     s.d_masks, n_tiles);
+                                                     n_tiles);
     ctx->launches++;
   }
   if (timed) TPS_CUDA(ctx, cudaEventRecord(ev[1], sp));
@@ -468,7 +467,8 @@ int enqueue_scan(tps_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t *d_bases,
   const Slot &src = packed_by ? *packed_by : s;
   a.pk.codes = src.d_codes;
   a.pk.flags = src.d_flags;
-  a.pk.masks = src.d_masks;
+  a.pk.bases = d_bases;
+  s.last_bases = d_bases;
   a.offsets = d_off;
   a.lens = d_len;
   a.n_reads = n_reads;
@@ -718,7 +718,18 @@ int tps_debug_copy(tps_ctx *ctx, int what, void *dst, size_t bytes) {
   switch (what) {
     case 0: src = s.d_codes; cap = ctx->cap_tiles * 32 * sizeof(uint32_t); break;
     case 1: src = s.d_flags; cap = ctx->cap_tiles * sizeof(uint32_t); break;
-    case 2: src = s.d_masks; cap = ctx->cap_tiles * 32 * sizeof(uint16_t); break;
+    case 2: { /* validity masks as K2/K3 derive them (flag word + ASCII bytes of flagged groups) */
+      const uint64_t ng = bytes / sizeof(uint16_t);
+      if (!s.last_bases || ng > ctx->cap_tiles * 32) return fail(ctx, TPS_EINVAL, "no scanned batch / too many groups");
+      uint16_t *tmp = nullptr;
+      TPS_CUDA(ctx, cudaMalloc(&tmp, ng * sizeof(uint16_t) + 2));
+      tps_debug_valid_kernel<<<(unsigned)((ng + 255) / 256), 256, 0, s.stream>>>(s.d_flags, s.last_bases, tmp, ng);
+      cudaError_t e = cudaMemcpyAsync(dst, tmp, ng * sizeof(uint16_t), cudaMemcpyDeviceToHost, s.stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
+      cudaFree(tmp);
+      if (e != cudaSuccess) return fail(ctx, TPS_ECUDA, "debug validity copy: %s", cudaGetErrorString(e));
+      return TPS_OK;
+    }
     case 3: src = s.d_pass; cap = (size_t)ctx->max_pass * sizeof(uint32_t); break;
     default: return fail(ctx, TPS_EINVAL, "unknown debug array %d", what);
   }

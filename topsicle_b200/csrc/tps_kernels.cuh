@@ -1,7 +1,7 @@
 /*
  * tps_kernels.cuh -- sm_100a kernels of the per-read telomere scan.
  *
- *   K1  tps_pack_kernel         ASCII -> 2-bit codes (+ invalid-group flags, sparse exact masks)
+ *   K1  tps_pack_tma_kernel     ASCII -> 2-bit codes + invalid-group flags (tps_pack_kernel: register-staged twin)
  *   K2  tps_trc_kernel<K>       per read: head/tail greedy counts, TRC decision, pass list
  *   K3  tps_window_kernel<K>    per (passing read, tile): window counts c_w (+ raw counts)
  *   K4  tps_changepoint_kernel  per passing read: exact single change point
@@ -39,7 +39,7 @@ struct TpsPatTable {
 struct TpsPacked {
   const uint32_t *codes; /* 1 word / 16 bases */
   const uint32_t *flags; /* 1 bit / 16 bases */
-  const uint16_t *masks; /* exact validity, defined where flag bit set */
+  const uint8_t *bases;  /* the ASCII batch itself: exact validity of a flagged group is recomputed from it */
 };
 
 /* counters[]: [0] n_pass, [1] K3 work cursor, [2,3] rawcount cursor (u64), [4] overflow flags,
@@ -80,11 +80,16 @@ __device__ __forceinline__ uint4 tps_ldg_stream(const uint4 *p) {
 
 #define TPS_K1_THREADS 256
 
-/* Exact validity of a flagged tile: every lane stores its group's 16-bit mask, so the tile's
- * 64 bytes of masks are written as two full 32-byte sectors (sparse 2-byte stores by the bad
- * lanes alone cost more than they save: partial-sector writes). */
-__device__ __forceinline__ void tps_store_tile_masks(const uint4 &v, uint16_t *__restrict__ mp) {
-  *mp = (uint16_t)tps_exact_mask16_simd(v.x, v.y, v.z, v.w);
+/* Validity of 16-base group g (bit i = base 16g + i is one of ACGTacgt).  K1 only flags groups that hold
+ * another byte (N, IUPAC codes, anything); the few consumers that meet a flagged group -- K2 and K3 touch
+ * the read ends and the regions of TRC-pass reads, ~0.5 % of the batch -- rebuild the exact mask from the
+ * 16 ASCII bytes, which are still resident.  Keeping that out of K1 removes a fifth of its instructions. */
+__device__ __forceinline__ uint32_t tps_group_valid(const uint32_t *__restrict__ flags, const uint8_t *__restrict__ bases,
+                                                    uint64_t g) {
+  const uint32_t fw = __ldg(flags + (g >> 5));
+  if (!((fw >> (g & 31)) & 1u)) return 0xFFFFu;
+  const uint4 v = __ldg(reinterpret_cast<const uint4 *>(bases) + g);
+  return tps_exact_mask16_simd(v.x, v.y, v.z, v.w);
 }
 
 #ifdef TPS_TUNING
@@ -92,7 +97,7 @@ __device__ __forceinline__ void tps_store_tile_masks(const uint4 &v, uint16_t *_
 template <int U, int V>
 __global__ void __launch_bounds__(TPS_K1_THREADS)
 tps_pack_probe(const uint4 *__restrict__ bases, uint32_t *__restrict__ codes, uint32_t *__restrict__ flags,
-               uint16_t *__restrict__ masks, uint64_t n_tiles) {
+               uint64_t n_tiles) {
   const uint32_t lane = threadIdx.x & 31u;
   const uint64_t warp = (uint64_t)blockIdx.x * (TPS_K1_THREADS / 32) + (threadIdx.x >> 5);
   const uint64_t stride = (uint64_t)gridDim.x * (TPS_K1_THREADS / 32) * U;
@@ -118,7 +123,7 @@ tps_pack_probe(const uint4 *__restrict__ bases, uint32_t *__restrict__ codes, ui
       } else if (V == 5) { /* codes + per-lane bad OR-ed into one store, no ballot */
         uint32_t bad;
         cp[u * 32] = tps_pack16(v[u].x, v[u].y, v[u].z, v[u].w, &bad);
-        if (bad) masks[g0 + u * 32] = 1;
+        if (bad) flags[t0 + u] = 1;
       } else {
         cp[u * 32] = v[u].x ^ v[u].y ^ v[u].z ^ v[u].w;
       }
@@ -135,7 +140,7 @@ tps_pack_probe(const uint4 *__restrict__ bases, uint32_t *__restrict__ codes, ui
 template <int U, int MINB = 4>
 __global__ void __launch_bounds__(TPS_K1_THREADS, MINB)
 tps_pack_kernel(const uint4 *__restrict__ bases, uint32_t *__restrict__ codes,
-                uint32_t *__restrict__ flags, uint16_t *__restrict__ masks, uint64_t n_tiles) {
+                uint32_t *__restrict__ flags, uint64_t n_tiles) {
   static_assert(U % 4 == 0, "U must be a multiple of 4 (vector flag stores)");
   const uint32_t lane = threadIdx.x & 31u;
   const uint64_t warp = (uint64_t)blockIdx.x * (TPS_K1_THREADS / 32) + (threadIdx.x >> 5);
@@ -160,10 +165,6 @@ tps_pack_kernel(const uint4 *__restrict__ bases, uint32_t *__restrict__ codes,
 #pragma unroll
       for (int u = 0; u < U; u += 4) fp[u / 4] = make_uint4(fl[u], fl[u + 1], fl[u + 2], fl[u + 3]);
     }
-    uint16_t *mp = masks + g0;
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-      if (fl[u] != 0u) tps_store_tile_masks(v[u], mp + u * 32); /* warp-uniform, ~20 % of tiles at 0.05 % N */
   }
   const uint64_t tt = n_main + warp; /* at most U-1 trailing tiles, one warp each */
   if (tt < n_tiles) {
@@ -173,7 +174,6 @@ tps_pack_kernel(const uint4 *__restrict__ bases, uint32_t *__restrict__ codes,
     codes[g] = tps_pack16(v.x, v.y, v.z, v.w, &bad);
     const uint32_t f = __ballot_sync(TPS_FULL, bad != 0u);
     if (lane == 0) flags[tt] = f;
-    if (f != 0u) tps_store_tile_masks(v, masks + g);
   }
 }
 
@@ -222,7 +222,7 @@ __device__ __forceinline__ void tps_bulk_g2s(uint32_t dst, const void *src, uint
 template <int U>
 __global__ void __launch_bounds__(TPS_K1T_THREADS)
 tps_pack_tma_kernel(const uint4 *__restrict__ bases, uint32_t *__restrict__ codes, uint32_t *__restrict__ flags,
-                    uint16_t *__restrict__ masks, uint64_t n_tiles, uint32_t n_stages) {
+                    uint64_t n_tiles, uint32_t n_stages) {
   extern __shared__ __align__(128) uint8_t k1t_smem[];
   uint64_t *bars = reinterpret_cast<uint64_t *>(k1t_smem + (size_t)n_stages * TPS_K1T_STAGE_BYTES(U));
   const uint32_t full0 = tps_smem_addr(bars), empty0 = full0 + 8u * n_stages;
@@ -268,13 +268,11 @@ tps_pack_tma_kernel(const uint4 *__restrict__ bases, uint32_t *__restrict__ code
     if (t0 + U <= n_tiles) {
       uint32_t fl[U];
       uint32_t *cp = codes + g0;
-      uint16_t *mp = masks + g0;
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         uint32_t bad;
         cp[u * 32] = tps_pack16(v[u].x, v[u].y, v[u].z, v[u].w, &bad);
         fl[u] = __ballot_sync(TPS_FULL, bad != 0u);
-        if (fl[u] != 0u) tps_store_tile_masks(v[u], mp + u * 32); /* warp-uniform, ~20 % of tiles at 0.05 % N */
       }
       if (lane == 0) { /* t0 is a multiple of U: the flag words of the warp's tiles go out as one vector */
         if constexpr (U == 4) *reinterpret_cast<uint4 *>(flags + t0) = make_uint4(fl[0], fl[1], fl[2], fl[3]);
@@ -288,11 +286,17 @@ tps_pack_tma_kernel(const uint4 *__restrict__ bases, uint32_t *__restrict__ code
           codes[g0 + u * 32] = tps_pack16(v[u].x, v[u].y, v[u].z, v[u].w, &bad);
           const uint32_t f = __ballot_sync(TPS_FULL, bad != 0u);
           if (lane == 0) flags[t0 + u] = f;
-          if (f != 0u) tps_store_tile_masks(v[u], masks + g0 + u * 32);
         }
       }
     }
   }
+}
+
+/* Test hook: the validity mask K2/K3 would see for every group of the batch. */
+__global__ void tps_debug_valid_kernel(const uint32_t *__restrict__ flags, const uint8_t *__restrict__ bases,
+                                       uint16_t *__restrict__ out, uint64_t n_groups) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < n_groups) out[g] = (uint16_t)tps_group_valid(flags, bases, g);
 }
 
 /* ----------------------------------------------------------------- staging (K2 and K3) */
@@ -315,8 +319,7 @@ __device__ __forceinline__ void tps_stage_linear(const TpsPacked &pk, uint64_t g
     } else {
       const uint64_t g = gfirst + (i - 2);
       uint32_t y = tps_linear_planes(__ldg(pk.codes + g));
-      uint32_t fw = __ldg(pk.flags + (g >> 5));
-      uint32_t v = ((fw >> (g & 31)) & 1u) ? (uint32_t)__ldg(pk.masks + g) : 0xFFFFu;
+      uint32_t v = tps_group_valid(pk.flags, pk.bases, g);
       l0[i] = (uint16_t)(y & 0xFFFFu);
       l1[i] = (uint16_t)(y >> 16);
       lv[i] = (uint16_t)v;
@@ -549,8 +552,7 @@ __device__ __forceinline__ void tps_trc_end_reg(const TpsScanArgs &a, const TpsP
     if (gi < ng) {
       const uint64_t g = gfirst + gi;
       const uint32_t y = tps_linear_planes(__ldg(a.pk.codes + g));
-      const uint32_t fw = __ldg(a.pk.flags + (g >> 5));
-      const uint32_t v = ((fw >> (g & 31)) & 1u) ? (uint32_t)__ldg(a.pk.masks + g) : 0xFFFFu;
+      const uint32_t v = tps_group_valid(a.pk.flags, a.pk.bases, g);
       L0 |= (y & 0xFFFFu) << (16u * h);
       L1 |= (y >> 16) << (16u * h);
       LV |= v << (16u * h);

@@ -32,6 +32,16 @@ ALG_BYTES_PER_BASE = 1.25  # K1: 1 B ASCII read + 0.25 B 2-bit code written (SUR
 # the dominant kernel: bulk-copy (TMA) staged pack kernel unless the register-staged one is forced
 K1_KERNEL = "tps_pack_kernel" if os.environ.get("TPS_K1_TMA") == "0" else "tps_pack_tma_kernel"
 
+# stdout carries exactly ONE JSON line: libraries that print to fd 1 (NCCL's version banner under torchrun)
+# are sent to stderr for the whole run, the line itself goes to the saved descriptor.
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line):
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
 
 def parse_args():
     ap = argparse.ArgumentParser()
@@ -169,7 +179,7 @@ def reference_arm(a):
             "reads_per_s": reads * a.steps / t,
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
@@ -438,7 +448,7 @@ def main():
                 "clocks": clocks,
                 "generate_s": t_gen,
                 "host_placement": {"cpus_local_to_gpu0": near, "bound": bool(near and world > 1)}}
-        print(json.dumps(line))
+        emit(line)
     ctx.close()
     for hb in host_bases + host_off:
         hb.free()

@@ -372,3 +372,66 @@ def test_span_batch_equals_back_to_back(eng, edge_records, demo_records):
     with _ctx(eng, p4, **kw) as a:
         with pytest.raises(eng.TpsError):
             a.submit_spans(buf[:100], starts, lens, len(seqs))     # last read ends beyond the uploaded bytes
+
+
+# ------------------------------------------------------------- kernel / stream variants
+VARIANTS = [
+    {},                                                     # bulk-copy K1, pack / tail streams (defaults)
+    {"TPS_K1_TMA": "0"},                                    # register-staged K1
+    {"TPS_SPLIT_STREAMS": "0"},                             # whole batch on its slot's stream
+    {"TPS_K1_STAGES": "2", "TPS_K1_STAGE_KB": "8", "TPS_K1_CTAS_PER_SM": "1"},
+    {"TPS_K1_STAGES": "6", "TPS_K1_CTAS_PER_SM": "3"},
+    {"TPS_K2_SMEM_PATH": "1"},                              # shared-memory staged K2
+]
+
+
+def test_kernel_and_stream_variants_agree(eng, monkeypatch):
+    """Every tuning knob (read at tps_create) must give bit-identical codes, flags, rows and raw counts:
+    the knobs select how the bytes move, never what is computed."""
+    rng = np.random.default_rng(77)
+    B = np.frombuffer(b"ACGT", dtype=np.uint8)
+    lens = rng.integers(1, 9000, 700)
+    lens[::50] = rng.integers(16384 * 3, 16384 * 5, len(lens[::50]))  # several 16-KiB chunks per read
+    offsets = np.zeros(len(lens) + 1, np.uint64)
+    offsets[1:] = np.cumsum(lens)
+    n = int(offsets[-1])
+    bases = B[rng.integers(0, 4, n)].copy()
+    tel = np.frombuffer((b"CCCTAA" * (n // 6 + 1))[:n], dtype=np.uint8)
+    for i in range(0, len(lens), 7):                        # telomeric heads, some with errors
+        a, e = int(offsets[i]), int(offsets[i]) + min(int(lens[i]), 3000)
+        bases[a:e] = tel[:e - a]
+    bases[rng.random(n) < 0.002] = ord("N")
+    bases[rng.random(n) < 0.0005] = ord("r")
+    pats = orc.patterns_to_search("CCCTAA", 5)              # two self-overlapping literals
+    ref = None
+    for env in VARIANTS:
+        for k in ("TPS_K1_TMA", "TPS_SPLIT_STREAMS", "TPS_K1_STAGES", "TPS_K1_STAGE_KB", "TPS_K1_CTAS_PER_SM",
+                  "TPS_K2_SMEM_PATH"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        with _ctx(eng, pats, len_telopattern=6, min_seq_length=500, cutoff=0.4, slide=6, want_rawcount=True,
+                  rawcount_capacity=1 << 26, max_batch_bases=n + 4096, n_slots=3) as ctx:
+            bids = [ctx.submit(bases, offsets) for _ in range(3)]      # three batches in flight on three slots
+            got = [_rows_without_offsets(eng, ctx.wait(b)[0]) for b in bids]
+            rows, raw = ctx.scan(bases, offsets)
+            ng = n // 16
+            codes = ctx.debug_copy(0, ng * 4).tobytes()
+            flags = ctx.debug_copy(1, (n // 512) * 4).tobytes()
+            passing = np.nonzero(rows["status"] == eng.ST_PASS)[0]
+            # raw-count offsets come from an atomic cursor: compare the tables per read, not the layout
+            tables = [ctx.rawcount_table(rows, raw, int(i)).tobytes() for i in passing[:40]]
+        cur = (codes, flags, _rows_without_offsets(eng, rows), tables)
+        assert got[0] == got[1] == got[2] == cur[2], env
+        if ref is None:
+            ref = cur
+            assert len(passing) > 20
+        else:
+            for a_, b_ in zip(cur, ref):
+                assert a_ == b_, env
+
+
+def _rows_without_offsets(eng, rows):
+    r = rows.copy()
+    r["rawcount_offset"] = 0
+    return r.tobytes()

@@ -134,6 +134,22 @@ int tps_submit(tps_ctx *ctx, const uint8_t *bases, const uint64_t *offsets, uint
  * lengths of all reads before it, see csrc/tps_fastx.c).  Same lifetime rules as tps_submit. */
 int tps_submit_spans(tps_ctx *ctx, const uint8_t *bases, uint64_t n_span, const uint64_t *starts,
                      const uint32_t *lengths, uint32_t n_reads, uint64_t batch_id);
+/* Ends-first scanning (optional, for inputs whose reads are mostly NOT telomeric): step 1 only looks at the
+ * first and last `no_bp` bases of a read (allsteps.py:176-177) and steps 2/3 only at `[trimfirst,
+ * min(L, maxlengthtelo))` of one end of the TRC-pass reads (allsteps.py:263-271), so the interior of long
+ * reads never has to cross PCIe.
+ *   tps_submit_ends: read i is uploaded as its head followed by its tail, `lengths[i]` = min(L, 2*no_bp)
+ *   bytes (the whole read when L <= 2*no_bp), `true_lengths[i]` = L.  Runs K1 + K2 only; the rows carry
+ *   the real length and status FILTERED / BELOW / PASS (n_windows, bkp, telo_length unset).
+ *   tps_submit_regions: read i is the first (tails[i] = TPS_TAIL_FORWARD) or last (TPS_TAIL_REVERSE)
+ *   min(L, maxlengthtelo) bases of a read that passed step 1 with that tail.  Runs K1..K4 with the tail
+ *   forced per read and the length filter off; n_windows, bkp, telo_length, status PASS / BADSEG and the raw
+ *   counts equal those of a whole-read scan; the step-1 fields of these rows (match_count, head_max,
+ *   tail_max, best_pattern) describe the uploaded region only -- keep those of the ends batch.  Same span-batch layout and lifetime rules as tps_submit_spans. */
+int tps_submit_ends(tps_ctx *ctx, const uint8_t *bases, uint64_t n_span, const uint64_t *starts,
+                    const uint32_t *lengths, const uint32_t *true_lengths, uint32_t n_reads, uint64_t batch_id);
+int tps_submit_regions(tps_ctx *ctx, const uint8_t *bases, uint64_t n_span, const uint64_t *starts,
+                       const uint32_t *lengths, const uint8_t *tails, uint32_t n_reads, uint64_t batch_id);
 /* Scan, under the parameters of `ctx`, the batch that `owner` has in flight as `batch_id`, without a
  * second upload or a second K1: ctx's K2..K4 are enqueued on the owner's stream and read the owner's
  * packed reads.  Same device; collect with tps_wait(ctx, batch_id, ...).  This is how several

@@ -435,3 +435,54 @@ def _rows_without_offsets(eng, rows):
     r = rows.copy()
     r["rawcount_offset"] = 0
     return r.tobytes()
+
+
+# ------------------------------------------------------------------------- ends-first protocol
+def _random_reads(seed, n=260, lmax=30000):
+    rng = np.random.default_rng(seed)
+    B = np.array(list("ACGT"))
+    reads = []
+    for i in range(n):
+        L = int(rng.integers(1, lmax if i % 4 else 2500))   # many reads shorter than 2 * no_bp
+        s = B[rng.integers(0, 4, L)]
+        if i % 3 == 0 and L > 300:
+            tl = int(rng.integers(100, L))
+            tel = np.array(list(("CCCTAA" * (tl // 6 + 2))[int(rng.integers(0, 6)):][:tl]))
+            err = rng.random(tl) < 0.03
+            tel[err] = B[rng.integers(0, 4, int(err.sum()))]
+            if i % 2:
+                s[:tl] = tel
+            else:
+                s[L - tl:] = np.array(list("".join(tel)[::-1].translate(str.maketrans("ACGT", "TGCA"))))
+        if i % 7 == 0:
+            s[rng.random(L) < 0.01] = "N"
+        reads.append("".join(s))
+    return reads
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(motif="CCCTAA", k=4, W=100, slide=6, trim=100, maxlen=20000, minlen=500, cutoff=0.3, no_bp=1000),
+    dict(motif="CCCTAA", k=5, W=50, slide=3, trim=17, maxlen=2500, minlen=0, cutoff=0.2, no_bp=1000),
+    dict(motif="CCCTAAA", k=5, W=100, slide=7, trim=100, maxlen=700, minlen=9000, cutoff=0.4, no_bp=1000),
+    dict(motif="CCCTAA", k=6, W=80, slide=6, trim=0, maxlen=20000, minlen=100, cutoff=0.1, no_bp=300),
+])
+def test_ends_first_equals_whole_read_scan(eng, demo_records, cfg):
+    """tps_submit_ends + tps_submit_regions (head/tail upload, then the regions of the TRC-pass reads) give the
+    rows and raw-count tables of the whole-read scan, field by field."""
+    reads = _random_reads(31) + [s for _, s in demo_records]
+    pats = orc.patterns_to_search(cfg["motif"], cfg["k"])
+    with _ctx(eng, pats, len_telopattern=len(cfg["motif"]), min_seq_length=cfg["minlen"], cutoff=cfg["cutoff"],
+              window_size=cfg["W"], slide=cfg["slide"], trimfirst=cfg["trim"], maxlengthtelo=cfg["maxlen"],
+              no_bp=cfg["no_bp"], want_rawcount=True, rawcount_capacity=1 << 27, max_batch_bases=1 << 25) as ctx:
+        full, raw = ctx.scan_reads(reads)
+        got, tables = ctx.scan_reads_ends_first(reads)
+        assert (full["status"] >= eng.ST_PASS).sum() > 15
+        for f in ("length", "status", "tail", "best_pattern", "match_count", "head_max", "tail_max", "n_windows",
+                  "bkp", "telo_length"):
+            assert np.array_equal(full[f], got[f]), f
+        for i in np.nonzero(full["status"] >= eng.ST_PASS)[0]:
+            want = ctx.rawcount_table(full, raw, int(i))
+            if want is None:
+                assert tables[i] is None or tables[i].size == 0
+            else:
+                assert np.array_equal(want, tables[i]), i

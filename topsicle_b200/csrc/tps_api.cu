@@ -31,6 +31,9 @@ struct Slot {
   uint64_t *d_off = nullptr;
   uint32_t *d_len = nullptr;        /* read lengths of a span batch */
   bool has_lens = false;
+  uint32_t *d_true_len = nullptr;   /* ends batch: real read lengths */
+  uint8_t *d_tails = nullptr;       /* region batch: per-read forced tail */
+  bool ends = false, regions = false; /* kind of the batch in flight */
   tps_row *d_rows = nullptr;
   uint32_t *d_pass = nullptr;
   uint32_t *d_counters = nullptr;
@@ -186,7 +189,7 @@ void tps_destroy(tps_ctx *ctx) {
     Slot &s = ctx->slots[i];
     if (s.stream) cudaStreamSynchronize(s.stream);
     cudaFree(s.d_bases); cudaFree(s.d_codes); cudaFree(s.d_flags);
-    cudaFree(s.d_off); cudaFree(s.d_len); cudaFree(s.d_rows); cudaFree(s.d_pass); cudaFree(s.d_counters);
+    cudaFree(s.d_off); cudaFree(s.d_len); cudaFree(s.d_true_len); cudaFree(s.d_tails); cudaFree(s.d_rows); cudaFree(s.d_pass); cudaFree(s.d_counters);
     cudaFree(s.d_raw); cudaFree(s.d_cw);
     if (s.h_rows) cudaFreeHost(s.h_rows);
     if (s.h_counters) cudaFreeHost(s.h_counters);
@@ -398,6 +401,8 @@ int tps_create(tps_ctx **out, int device, const tps_params *params) {
     TPS_CC(cudaMalloc(&s.d_flags, ctx->cap_tiles * sizeof(uint32_t)));
     TPS_CC(cudaMalloc(&s.d_off, ((uint64_t)p.max_batch_reads + 1) * sizeof(uint64_t)));
     TPS_CC(cudaMalloc(&s.d_len, (uint64_t)p.max_batch_reads * sizeof(uint32_t)));
+    TPS_CC(cudaMalloc(&s.d_true_len, (uint64_t)p.max_batch_reads * sizeof(uint32_t)));
+    TPS_CC(cudaMalloc(&s.d_tails, (uint64_t)p.max_batch_reads));
     TPS_CC(cudaMalloc(&s.d_rows, (uint64_t)p.max_batch_reads * sizeof(tps_row)));
     TPS_CC(cudaMalloc(&s.d_pass, (uint64_t)ctx->max_pass * sizeof(uint32_t)));
     TPS_CC(cudaMalloc(&s.d_counters, 8 * sizeof(uint32_t)));
@@ -422,7 +427,8 @@ namespace {
  * context: only K2..K4 run, reading them. */
 int enqueue_scan(tps_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t *d_bases, const uint64_t *d_off,
                  uint32_t n_reads, uint64_t n_bases, tps_row *d_rows, bool timed, const Slot *packed_by = nullptr,
-                 const uint32_t *d_len = nullptr, tps_ctx *stream_owner = nullptr) {
+                 const uint32_t *d_len = nullptr, tps_ctx *stream_owner = nullptr,
+                 const uint32_t *d_true_len = nullptr, const uint8_t *d_tails = nullptr) {
   const tps_params &p = ctx->p;
   cudaEvent_t *ev = ctx->ev[ctx->scan_seq % TPS_TIMING_RING];
   /* split mode: `st` (the slot's stream) orders the batch against its copies; K1 goes to the context's
@@ -471,6 +477,8 @@ int enqueue_scan(tps_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t *d_bases,
   s.last_bases = d_bases;
   a.offsets = d_off;
   a.lens = d_len;
+  a.true_lens = d_true_len; /* ends batch: step 1 only, the windows need bases that were not uploaded */
+  a.force_tails = d_tails;
   a.n_reads = n_reads;
   a.rows = d_rows;
   a.pass_list = s.d_pass;
@@ -483,7 +491,7 @@ int enqueue_scan(tps_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t *d_bases,
   a.trimfirst = p.trimfirst;
   a.maxlengthtelo = p.maxlengthtelo;
   a.want_rawcount = p.want_rawcount;
-  a.flags = p.flags;
+  a.flags = p.flags | (d_true_len ? TPS_FLAG_STEP1_ONLY : 0u);
   a.raw = s.d_raw;
   a.raw_capacity = p.want_rawcount ? p.rawcount_capacity : 0;
   a.cw = s.d_cw;
@@ -501,7 +509,7 @@ int enqueue_scan(tps_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t *d_bases,
     ctx->launches++;
   }
   if (timed) TPS_CUDA(ctx, cudaEventRecord(ev[2], sh));
-  if (n_reads && !(p.flags & TPS_FLAG_STEP1_ONLY)) {
+  if (n_reads && !(a.flags & TPS_FLAG_STEP1_ONLY)) {
     a.lin_words = ctx->k3_lin_words;
     a.tile_words = ctx->k3_tile_words;
     ctx->k3_fn<<<ctx->k3_grid, TPS_K3_THREADS, ctx->k3_smem, sh>>>(a, ctx->pt);
@@ -525,7 +533,8 @@ int enqueue_scan(tps_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t *d_bases,
 extern "C" {
 
 static int submit_common(tps_ctx *ctx, const uint8_t *bases, uint64_t n_bases, const uint64_t *starts,
-                         const uint32_t *lengths, uint32_t n_reads, uint64_t batch_id) {
+                         const uint32_t *lengths, uint32_t n_reads, uint64_t batch_id,
+                         const uint32_t *true_lens = nullptr, const uint8_t *tails = nullptr) {
   const tps_params &p = ctx->p;
   if (n_reads > p.max_batch_reads) return fail(ctx, TPS_ECAPACITY, "batch has %u reads, capacity %u", n_reads, p.max_batch_reads);
   if (n_bases > p.max_batch_bases) return fail(ctx, TPS_ECAPACITY, "batch has %llu bases, capacity %llu",
@@ -544,10 +553,16 @@ static int submit_common(tps_ctx *ctx, const uint8_t *bases, uint64_t n_bases, c
                                 cudaMemcpyHostToDevice, st));
   if (lengths && n_reads)
     TPS_CUDA(ctx, cudaMemcpyAsync(s.d_len, lengths, (uint64_t)n_reads * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  if (true_lens && n_reads)
+    TPS_CUDA(ctx, cudaMemcpyAsync(s.d_true_len, true_lens, (uint64_t)n_reads * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  if (tails && n_reads) TPS_CUDA(ctx, cudaMemcpyAsync(s.d_tails, tails, n_reads, cudaMemcpyHostToDevice, st));
   if (n_bases) TPS_CUDA(ctx, cudaMemcpyAsync(s.d_bases, bases, n_bases, cudaMemcpyHostToDevice, st));
   s.has_lens = lengths != nullptr;
+  s.ends = true_lens != nullptr;
+  s.regions = tails != nullptr;
   int rc = enqueue_scan(ctx, s, st, s.d_bases, s.d_off, n_reads, n_bases, s.d_rows, false, nullptr,
-                        lengths ? s.d_len : nullptr);
+                        lengths ? s.d_len : nullptr, nullptr, true_lens ? s.d_true_len : nullptr,
+                        tails ? s.d_tails : nullptr);
   if (rc) return rc;
   if (n_reads)
     TPS_CUDA(ctx, cudaMemcpyAsync(s.h_rows, s.d_rows, (uint64_t)n_reads * sizeof(tps_row), cudaMemcpyDeviceToHost, st));
@@ -575,6 +590,33 @@ int tps_submit_spans(tps_ctx *ctx, const uint8_t *bases, uint64_t n_span, const 
   return submit_common(ctx, bases, n_span, n_reads ? starts : &zero, n_reads ? lengths : nullptr, n_reads, batch_id);
 }
 
+int tps_submit_ends(tps_ctx *ctx, const uint8_t *bases, uint64_t n_span, const uint64_t *starts,
+                    const uint32_t *lengths, const uint32_t *true_lengths, uint32_t n_reads, uint64_t batch_id) {
+  if (!ctx || (n_reads && (!starts || !lengths || !true_lengths)) || (!bases && n_span))
+    return fail(ctx, TPS_EINVAL, "null argument");
+  if (n_reads && starts[n_reads - 1] + lengths[n_reads - 1] > n_span)
+    return fail(ctx, TPS_EINVAL, "last read ends beyond the %llu uploaded bytes", (unsigned long long)n_span);
+  static const uint64_t zero = 0;
+  static const uint32_t zero32 = 0;
+  return submit_common(ctx, bases, n_span, n_reads ? starts : &zero, n_reads ? lengths : nullptr, n_reads, batch_id,
+                       n_reads ? true_lengths : &zero32, nullptr);
+}
+
+int tps_submit_regions(tps_ctx *ctx, const uint8_t *bases, uint64_t n_span, const uint64_t *starts,
+                       const uint32_t *lengths, const uint8_t *tails, uint32_t n_reads, uint64_t batch_id) {
+  if (!ctx || (n_reads && (!starts || !lengths || !tails)) || (!bases && n_span))
+    return fail(ctx, TPS_EINVAL, "null argument");
+  if (ctx->p.flags & TPS_FLAG_STEP1_ONLY) return fail(ctx, TPS_EINVAL, "region batches need a context that runs steps 2/3");
+  if (n_reads && starts[n_reads - 1] + lengths[n_reads - 1] > n_span)
+    return fail(ctx, TPS_EINVAL, "last read ends beyond the %llu uploaded bytes", (unsigned long long)n_span);
+  for (uint32_t i = 0; i < n_reads; ++i)
+    if (tails[i] > TPS_TAIL_REVERSE) return fail(ctx, TPS_EINVAL, "tails[%u] = %u is not a TPS_TAIL_* value", i, tails[i]);
+  static const uint64_t zero = 0;
+  static const uint8_t zero8 = 0;
+  return submit_common(ctx, bases, n_span, n_reads ? starts : &zero, n_reads ? lengths : nullptr, n_reads, batch_id,
+                       nullptr, n_reads ? tails : &zero8);
+}
+
 int tps_submit_shared(tps_ctx *ctx, tps_ctx *owner, uint64_t batch_id) {
   if (!ctx || !owner || ctx == owner) return fail(ctx, TPS_EINVAL, "tps_submit_shared needs two distinct contexts");
   if (ctx->device != owner->device) return fail(ctx, TPS_EINVAL, "contexts are on different devices");
@@ -593,8 +635,11 @@ int tps_submit_shared(tps_ctx *ctx, tps_ctx *owner, uint64_t batch_id) {
   TPS_CUDA(ctx, cudaSetDevice(ctx->device));
   Slot &s = *sl;
   cudaStream_t st = so->stream; /* owner's stream: ordered after its H2D + K1 and before its slot is reused */
+  if (so->regions) return fail(ctx, TPS_EINVAL, "a region batch belongs to one context (its reads were chosen by that context's step 1)");
+  s.ends = so->ends;
+  s.regions = false;
   int rc = enqueue_scan(ctx, s, st, so->d_bases, so->d_off, so->n_reads, 0, s.d_rows, false, so,
-                        so->has_lens ? so->d_len : nullptr, owner);
+                        so->has_lens ? so->d_len : nullptr, owner, so->ends ? so->d_true_len : nullptr, nullptr);
   if (rc) return rc;
   if (so->n_reads)
     TPS_CUDA(ctx, cudaMemcpyAsync(s.h_rows, s.d_rows, (uint64_t)so->n_reads * sizeof(tps_row), cudaMemcpyDeviceToHost, st));

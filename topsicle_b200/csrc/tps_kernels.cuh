@@ -51,6 +51,8 @@ struct TpsScanArgs {
   TpsPacked pk;
   const uint64_t *offsets; /* read starts; without `lens`, offsets[r+1] ends read r (back-to-back batch) */
   const uint32_t *lens;    /* read lengths of a span batch (reads separated by gaps), or null */
+  const uint32_t *true_lens;   /* ends batch: the read's real length L (the batch holds head + tail only), or null */
+  const uint8_t *force_tails;  /* region batch: per-read TPS_TAIL_* chosen by an earlier step-1 scan, or null */
   uint32_t n_reads;
   tps_row *rows;
   uint32_t *pass_list;
@@ -484,14 +486,17 @@ tps_trc_kernel(const TpsScanArgs a, const TpsPatTable pt) {
   if (r >= a.n_reads) return;
   const uint64_t off = a.offsets[r];
   const uint32_t L = a.lens ? a.lens[r] : (uint32_t)(a.offsets[r + 1] - off);
+  /* ends batch: the slice geometry comes from the uploaded head + tail (L bases), the length filter, the row
+   * and the window count from the read's real length */
+  const uint32_t Lt = a.true_lens ? a.true_lens[r] : L;
   tps_row row;
-  row.length = L;
+  row.length = Lt;
   row.status = TPS_ST_FILTERED;
   row.tail = 0; row.best_pattern = 0; row.reserved0 = 0;
   row.match_count = 0; row.head_max = 0; row.tail_max = 0; row.reserved1 = 0;
   row.n_windows = 0; row.bkp = -1; row.telo_length = -1; row.reserved2 = 0;
   row.rawcount_offset = ~0ull;
-  if (L > a.min_seq_length) { /* strict, allsteps.py:175 */
+  if (Lt > a.min_seq_length || a.force_tails) { /* strict, allsteps.py:175; region batches passed it already */
     const uint32_t n = L < a.no_bp ? L : a.no_bp;
     uint32_t ms, ps, me, pe;
     tps_trc_end<K>(a, pt, pm, off, n, false, lin, mrows, cnts, lane, ms, ps);         /* seq[:no_bp] */
@@ -499,15 +504,17 @@ tps_trc_kernel(const TpsScanArgs a, const TpsPatTable pt) {
     bool fwd = ms > me; /* tie -> reverse, allsteps.py:193-198 */
     if (a.flags & TPS_FLAG_FORCE_FORWARD) fwd = true; /* caller-chosen tail, allsteps.py:294-297 */
     if (a.flags & TPS_FLAG_FORCE_REVERSE) fwd = false;
+    if (a.force_tails) fwd = a.force_tails[r] == TPS_TAIL_FORWARD;
     const uint32_t cnt = fwd ? ms : me;
     row.tail = fwd ? TPS_TAIL_FORWARD : TPS_TAIL_REVERSE;
     row.best_pattern = (uint8_t)(fwd ? ps : pe);
     row.match_count = (uint16_t)cnt;
     row.head_max = (uint16_t)ms;
     row.tail_max = (uint16_t)me;
-    row.status = cnt >= a.count_threshold ? TPS_ST_PASS : TPS_ST_BELOW;
+    /* a region batch holds reads that passed step 1 on their whole ends; its own count may see fewer bases */
+    row.status = (cnt >= a.count_threshold || a.force_tails) ? TPS_ST_PASS : TPS_ST_BELOW;
     if (row.status == TPS_ST_PASS && lane == 0 && !(a.flags & TPS_FLAG_STEP1_ONLY)) {
-      const uint32_t M = L < a.maxlengthtelo ? L : a.maxlengthtelo;
+      const uint32_t M = Lt < a.maxlengthtelo ? Lt : a.maxlengthtelo;
       const uint32_t nreg = M > a.trimfirst ? M - a.trimfirst : 0u;
       const uint32_t nW = nreg >= a.W ? (nreg - a.W) / a.slide + 1u : 0u;
       row.n_windows = nW;
@@ -639,14 +646,17 @@ tps_trc_reg_kernel(const TpsScanArgs a, const TpsPatTable pt) {
   if (r >= a.n_reads) return;
   const uint64_t off = a.offsets[r];
   const uint32_t L = a.lens ? a.lens[r] : (uint32_t)(a.offsets[r + 1] - off);
+  /* ends batch: the slice geometry comes from the uploaded head + tail (L bases), the length filter, the row
+   * and the window count from the read's real length */
+  const uint32_t Lt = a.true_lens ? a.true_lens[r] : L;
   tps_row row;
-  row.length = L;
+  row.length = Lt;
   row.status = TPS_ST_FILTERED;
   row.tail = 0; row.best_pattern = 0; row.reserved0 = 0;
   row.match_count = 0; row.head_max = 0; row.tail_max = 0; row.reserved1 = 0;
   row.n_windows = 0; row.bkp = -1; row.telo_length = -1; row.reserved2 = 0;
   row.rawcount_offset = ~0ull;
-  if (L > a.min_seq_length) { /* strict, allsteps.py:175 */
+  if (Lt > a.min_seq_length || a.force_tails) { /* strict, allsteps.py:175; region batches passed it already */
     const uint32_t n = L < a.no_bp ? L : a.no_bp;
     uint32_t ms, ps, me, pe;
     tps_trc_end_reg<K>(a, pt, pm, off, n, false, mrows, lane, ms, ps);         /* seq[:no_bp] */
@@ -654,15 +664,17 @@ tps_trc_reg_kernel(const TpsScanArgs a, const TpsPatTable pt) {
     bool fwd = ms > me; /* tie -> reverse, allsteps.py:193-198 */
     if (a.flags & TPS_FLAG_FORCE_FORWARD) fwd = true;
     if (a.flags & TPS_FLAG_FORCE_REVERSE) fwd = false;
+    if (a.force_tails) fwd = a.force_tails[r] == TPS_TAIL_FORWARD;
     const uint32_t cnt = fwd ? ms : me;
     row.tail = fwd ? TPS_TAIL_FORWARD : TPS_TAIL_REVERSE;
     row.best_pattern = (uint8_t)(fwd ? ps : pe);
     row.match_count = (uint16_t)cnt;
     row.head_max = (uint16_t)ms;
     row.tail_max = (uint16_t)me;
-    row.status = cnt >= a.count_threshold ? TPS_ST_PASS : TPS_ST_BELOW;
+    /* a region batch holds reads that passed step 1 on their whole ends; its own count may see fewer bases */
+    row.status = (cnt >= a.count_threshold || a.force_tails) ? TPS_ST_PASS : TPS_ST_BELOW;
     if (row.status == TPS_ST_PASS && lane == 0 && !(a.flags & TPS_FLAG_STEP1_ONLY)) {
-      const uint32_t M = L < a.maxlengthtelo ? L : a.maxlengthtelo;
+      const uint32_t M = Lt < a.maxlengthtelo ? Lt : a.maxlengthtelo;
       const uint32_t nreg = M > a.trimfirst ? M - a.trimfirst : 0u;
       const uint32_t nW = nreg >= a.W ? (nreg - a.W) / a.slide + 1u : 0u;
       row.n_windows = nW;

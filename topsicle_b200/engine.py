@@ -93,6 +93,10 @@ def load_library() -> C.CDLL:
     lib.tps_submit.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint64]
     lib.tps_submit_spans.restype = C.c_int
     lib.tps_submit_spans.argtypes = [vp, vp, C.c_uint64, vp, vp, C.c_uint32, C.c_uint64]
+    lib.tps_submit_ends.restype = C.c_int
+    lib.tps_submit_ends.argtypes = [vp, vp, C.c_uint64, vp, vp, vp, C.c_uint32, C.c_uint64]
+    lib.tps_submit_regions.restype = C.c_int
+    lib.tps_submit_regions.argtypes = [vp, vp, C.c_uint64, vp, vp, vp, C.c_uint32, C.c_uint64]
     lib.tps_submit_shared.restype = C.c_int
     lib.tps_submit_shared.argtypes = [vp, vp, C.c_uint64]
     lib.tps_wait.restype = C.c_int
@@ -272,6 +276,34 @@ class ScanContext:
         self._inflight[bid] = (bases, (starts, lens), n_reads)  # keep buffers alive
         return bid
 
+    def submit_ends(self, bases: np.ndarray, starts: np.ndarray, lens: np.ndarray, true_lens: np.ndarray,
+                    n_reads: int) -> int:
+        """Submit an ends batch (step 1 only): read i is uploaded as head + tail, bases[starts[i] : starts[i] +
+        lens[i]] with lens[i] = min(L, 2 * no_bp); true_lens[i] = L."""
+        assert bases.dtype == np.uint8 and starts.dtype == np.uint64 and lens.dtype == np.uint32
+        assert true_lens.dtype == np.uint32
+        assert bases.flags.c_contiguous and starts.flags.c_contiguous and lens.flags.c_contiguous
+        assert true_lens.flags.c_contiguous
+        bid = next(_batch_ids)
+        self._check(self.lib.tps_submit_ends(self._h, bases.ctypes.data, bases.size, starts.ctypes.data,
+                                             lens.ctypes.data, true_lens.ctypes.data, n_reads, bid))
+        self._inflight[bid] = (bases, (starts, lens, true_lens), n_reads)
+        return bid
+
+    def submit_regions(self, bases: np.ndarray, starts: np.ndarray, lens: np.ndarray, tails: np.ndarray,
+                       n_reads: int) -> int:
+        """Submit a region batch (steps 2/3 of reads that passed step 1 elsewhere): read i is the first
+        (tails[i] = 0) or last (tails[i] = 1) min(L, maxlengthtelo) bases of the read."""
+        assert bases.dtype == np.uint8 and starts.dtype == np.uint64 and lens.dtype == np.uint32
+        assert tails.dtype == np.uint8
+        assert bases.flags.c_contiguous and starts.flags.c_contiguous and lens.flags.c_contiguous
+        assert tails.flags.c_contiguous
+        bid = next(_batch_ids)
+        self._check(self.lib.tps_submit_regions(self._h, bases.ctypes.data, bases.size, starts.ctypes.data,
+                                                lens.ctypes.data, tails.ctypes.data, n_reads, bid))
+        self._inflight[bid] = (bases, (starts, lens, tails), n_reads)
+        return bid
+
     def submit_shared(self, owner: "ScanContext", bid: int) -> int:
         """Scan the batch `owner` has in flight as `bid` under this context's parameters, reusing the
         owner's upload and packed reads (no second H2D / K1)."""
@@ -313,6 +345,42 @@ class ScanContext:
     def scan_reads(self, seqs: Iterable):
         bases, offsets = pack_reads(seqs)
         return self.scan(bases, offsets)
+
+    def scan_reads_ends_first(self, seqs: Iterable):
+        """The ends-first protocol on in-memory reads: step 1 on head + tail of every read (tps_submit_ends),
+        steps 2/3 on the first / last min(L, maxlengthtelo) bases of the TRC-pass reads (tps_submit_regions),
+        rows merged.  Returns (rows, tables) with tables[i] = counts[w][p] of read i or None; equal to
+        scan_reads() field by field (raw-count offsets aside).  pipeline.Scanner(ends_first=True) does the same
+        from a file without ever copying the interior of a read."""
+        bufs = [s.encode("ascii", "replace") if isinstance(s, str) else bytes(s) for s in seqs]
+        h = int(self.params.no_bp)
+        minis = [b if len(b) <= 2 * h else b[:h] + b[len(b) - h:] for b in bufs]
+        bases, offsets = pack_reads(minis)
+        lens = np.diff(offsets).astype(np.uint32)
+        true_lens = np.array([len(b) for b in bufs], dtype=np.uint32)
+        rows, _ = self.wait(self.submit_ends(bases, np.ascontiguousarray(offsets[:-1]), lens, true_lens, len(bufs)))
+        tables = [None] * len(bufs)
+        idx = np.nonzero(rows["status"] == ST_PASS)[0]
+        if len(idx) == 0 or (self.params.flags & 1):       # TPS_FLAG_STEP1_ONLY
+            return rows, tables
+        m = int(self.params.maxlengthtelo)
+        regs = []
+        for i in idx:
+            b = bufs[i]
+            k = min(len(b), m)
+            regs.append(b[:k] if rows["tail"][i] == 0 else b[len(b) - k:])
+        rb, ro = pack_reads(regs)
+        tails = np.ascontiguousarray(rows["tail"][idx].astype(np.uint8))
+        rows2, raw2 = self.wait(self.submit_regions(rb, np.ascontiguousarray(ro[:-1]), np.diff(ro).astype(np.uint32),
+                                                    tails, len(regs)))
+        rows = rows.copy()
+        for j, i in enumerate(idx):
+            for f in ("status", "n_windows", "bkp", "telo_length"):
+                rows[f][i] = rows2[f][j]
+            tables[i] = self.rawcount_table(rows2, raw2, j)
+            if tables[i] is not None:
+                tables[i] = tables[i].copy()
+        return rows, tables
 
     def rawcount_table(self, rows, raw, i) -> np.ndarray:
         """counts[w][p] (uint8) of read i, or None."""

@@ -54,12 +54,32 @@ class OracleContext:
         self._pending[bid] = (b"".join(parts), off)
         return bid
 
+    def _submit_parts(self, bases, starts, lens, n_reads, kind, extra):
+        bid = next(engine._batch_ids)
+        assert n_reads <= self.max_batch_reads and bases.size <= self.max_batch_bases
+        parts = [bases[int(starts[i]):int(starts[i]) + int(lens[i])].tobytes() for i in range(n_reads)]
+        off = np.zeros(n_reads + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([len(p) for p in parts], dtype=np.uint64)
+        self._pending[bid] = (b"".join(parts), off, kind, np.array(extra[:n_reads]))
+        return bid
+
+    def submit_ends(self, bases, starts, lens, true_lens, n_reads):
+        """tps_submit_ends: head + tail of every read, real lengths aside; step 1 only."""
+        return self._submit_parts(bases, starts, lens, n_reads, "ends", true_lens)
+
+    def submit_regions(self, bases, starts, lens, tails, n_reads):
+        """tps_submit_regions: regions of reads that passed step 1, tail forced per read."""
+        assert not self.cfg.step1_only
+        return self._submit_parts(bases, starts, lens, n_reads, "regions", tails)
+
     def submit_shared(self, owner, bid):
         self._pending[bid] = owner._pending[bid]
         return bid
 
     def wait(self, bid, raw_view=False):
-        buf, off = self._pending.pop(bid)
+        buf, off, *mode = self._pending.pop(bid)
+        kind, extra = mode if mode else (None, None)
+        assert kind != "regions" or len(mode) == 2
         cfg = self.cfg
         n = len(off) - 1
         rows = np.zeros(n, dtype=engine.ROW_DTYPE)
@@ -69,23 +89,27 @@ class OracleContext:
         raw_parts, raw_at, n_pass = [], 0, 0
         for i in range(n):
             seq = buf[int(off[i]):int(off[i + 1])].decode("latin-1")
-            rows["length"][i] = len(seq)
-            if not len(seq) > cfg.min_seq_length:
+            true_len = int(extra[i]) if kind == "ends" else len(seq)
+            rows["length"][i] = true_len
+            if kind != "regions" and not true_len > cfg.min_seq_length:
                 continue
             tail, bi, cnt, ms, me, hc, tc = orc.trc_read(seq, self.patterns, cfg.len_telopattern, cfg.no_bp)
-            if cfg.force_tail:
-                tail = cfg.force_tail
+            forced = cfg.force_tail
+            if kind == "regions":
+                forced = "forward" if int(extra[i]) == 0 else "reverse"
+            if forced:
+                tail = forced
                 cs = hc if tail == "forward" else tc
                 cnt = max(cs)
                 bi = cs.index(cnt)
             rows["tail"][i] = 0 if tail == "forward" else 1
             rows["best_pattern"][i] = bi
             rows["match_count"][i], rows["head_max"][i], rows["tail_max"][i] = cnt, ms, me
-            if cnt < self.thr:
+            if cnt < self.thr and kind != "regions":
                 rows["status"][i] = engine.ST_BELOW
                 continue
             rows["status"][i] = engine.ST_PASS
-            if cfg.step1_only:
+            if cfg.step1_only or kind == "ends":
                 continue
             n_pass += 1
             if n_pass > self.max_pass:

@@ -113,3 +113,31 @@ def test_directory_of_files_scanned_concurrently(tmp_path, monkeypatch):
     sub_c = open(out / "c_trc_over_0.7.fasta").read()
     assert [ln[1:] for ln in sub_c.split("\n") if ln.startswith(">")] == [r[3] for r in want["c"]]
     assert all(len(ln) <= 60 for ln in sub_c.split("\n"))
+
+
+@pytest.mark.parametrize("case", golden_cases(), ids=lambda c: c["name"])
+def test_cli_ends_first_matches_reference_outputs(case, tmp_path, monkeypatch):
+    """--ends-first (head + tail upload, then the regions of the TRC-pass reads): the same bytes out."""
+    fake_engine.install(monkeypatch)
+    run_case(case, tmp_path, extra_argv=["--ends-first"])
+
+
+def test_ends_first_small_batches_split_regions(tmp_path, monkeypatch):
+    """Tiny batches, two stand-in devices, region batches cut by max_pass_reads: same reads, same order."""
+    fake_engine.install(monkeypatch)
+    from topsicle_b200 import pipeline
+    from topsicle_b200.patterns import patterns_to_search
+    cfgs = [pipeline.ScanConfig(patterns=patterns_to_search("CCCTAA", k), len_telopattern=6, phrase=k, slide=6,
+                                cutoff=0.4, want_rawcount=(k == 5)) for k in (4, 5)]
+    path = os.path.join(GOLD, "demo.fastq.gz")
+    _, want = pipeline.collect_file(path, cfgs)
+    _, got = pipeline.collect_file(path, cfgs, ends_first=True, max_pass_reads=3, max_batch_reads=7, devices=(0, 1),
+                                   ends_raw_bytes=200_000)
+    for w, g in zip(want, got):
+        assert len(w) > 10
+        assert [(p.index, p.read_id, p.tail, p.count, p.status, p.n_windows, p.telo_length, p.length) for p in g] == \
+               [(p.index, p.read_id, p.tail, p.count, p.status, p.n_windows, p.telo_length, p.length) for p in w]
+        for a, b in zip(w, g):
+            assert (a.counts is None) == (b.counts is None)
+            if a.counts is not None:
+                assert np.array_equal(a.counts, b.counts)

@@ -184,3 +184,43 @@ def test_one_pass_equals_two_pass_on_awkward_fastq(tmp_path):
     bad.write_bytes(b"@a\nACGT\n+\n!!!!\n@b\nACGT\n+\n!!!\n")
     with pytest.raises(fastx.FastxError):
         read_all_spans(str(bad))
+
+
+@pytest.mark.parametrize("end_len", [1000, 37, 50000])
+@pytest.mark.parametrize("suffix", [".fastq.gz", ".fastq", ".fasta"])
+def test_next_ends_head_tail_and_regions(tmp_path, end_len, suffix):
+    """The ends-first reader: head + tail of every read back to back, real lengths aside, and the full
+    sequence / the step-2 region still reachable through the record index (plain, gzip, multi-line FASTA)."""
+    import gzip
+    from oracle import topsicle_oracle as orc
+    src = os.path.join(GOLD, "demo.fastq.gz")
+    recs = list(orc.read_fastx(src))
+    path = str(tmp_path / ("x" + suffix))
+    if suffix == ".fastq.gz":
+        path = src
+    elif suffix == ".fastq":
+        open(path, "wb").write(gzip.open(src, "rb").read())
+    else:
+        with open(path, "w") as fh:
+            for rid, s in recs:
+                fh.write(f">{rid} desc\n" + "".join(s[j:j + 70] + "\n" for j in range(0, len(s), 70)))
+    bases = np.empty(1 << 22, np.uint8)
+    starts, lens, tl = np.empty(64, np.uint64), np.empty(64, np.uint32), np.empty(64, np.uint32)
+    got = []
+    with fastx.FastxFile(path, threads=3) as fx:
+        while True:
+            b = fx.next_ends(bases, starts, lens, tl, end_len, raw_cap=250_000)
+            if b is None:
+                break
+            assert b.n_bases == int(tl[:b.n_reads].sum())
+            for i in range(b.n_reads):
+                a = int(starts[i])
+                got.append((b.read_id(i), int(tl[i]), bases[a:a + int(lens[i])].tobytes(), b.sequence(i),
+                            b.region(i, 0, 20000), b.region(i, 1, 777)))
+            b.release()
+    assert len(got) == len(recs)
+    for (rid, s), g in zip(recs, got):
+        s = s.encode()
+        assert g[0] == rid and g[1] == len(s)
+        assert g[2] == (s if len(s) <= 2 * end_len else s[:end_len] + s[-end_len:])
+        assert g[3] == s and g[4] == s[:20000] and g[5] == s[-777:]

@@ -18,6 +18,19 @@ def test_cli_matches_reference_outputs(case, tmp_path):
     run_case(case, tmp_path)
 
 
+@pytest.mark.parametrize("case", golden_cases(), ids=lambda c: c["name"])
+def test_cli_ends_first_matches_reference_outputs(case, tmp_path):
+    """--ends-first on the real kernels: tps_submit_ends + tps_submit_regions, same bytes out."""
+    run_case(case, tmp_path, extra_argv=["--ends-first"])
+
+
+def test_cli_ends_first_small_batches(tmp_path, monkeypatch):
+    monkeypatch.setenv("TOPSICLE_BATCH_READS", "5")
+    monkeypatch.setenv("TOPSICLE_ENDS_FIRST", "1")
+    case = [c for c in golden_cases() if c["name"] == "CCCTAA_sweep_456_cut04_07"][0]
+    run_case(case, tmp_path)
+
+
 def test_cli_small_batches(tmp_path, monkeypatch):
     monkeypatch.setenv("TOPSICLE_BATCH_READS", "5")
     case = [c for c in golden_cases() if c["name"] == "CCCTAA_sweep_456_cut04_07"][0]

@@ -80,3 +80,20 @@ def test_cli_on_synthetic_file(synth_file, tmp_path):
     assert open(out / "telolengths_all.csv", newline="").read() == orc.csv_text("reads", 4, rows)
     sub = open(out / "reads_trc_over_0.5.fastq").read().split("\n")
     assert [ln[1:] for ln in sub[0::4] if ln] == [r["id"] for r in rows]
+
+
+def test_ends_first_many_batches_three_phrases_two_workers(synth_file):
+    """Ends-first mode on the real kernels: head + tail batches cut by file text, three phrases from one upload,
+    region batches cut by a small pass capacity, raw counts -- every field equals the oracle's."""
+    path, recs = synth_file
+    cfgs = _cfgs([4, 5, 6], cutoff=0.4)
+    stats, per = pipeline.collect_file(path, cfgs, devices=[0, 0], max_batch_bases=6 << 20, max_batch_reads=512,
+                                       depth=3, ends_first=True, ends_raw_bytes=6 << 20, max_pass_reads=16)
+    assert stats.n_reads == 2500 and stats.n_batches > 8
+    assert stats.n_bases == sum(len(s) for _, s in recs)
+    n = [_check(per[i], recs, k, 0.4) for i, k in enumerate([4, 5, 6])]
+    assert n[0] > 60 and n[0] >= n[2]
+    cfgs = _cfgs([4], cutoff=0.6, want_rawcount=True, window_size=50, slide=3)
+    stats, per = pipeline.collect_file(path, cfgs, devices=[0], max_batch_bases=16 << 20, max_batch_reads=1024,
+                                       max_pass_reads=8, rawcount_capacity=6617 * 12 * 3, ends_first=True)
+    assert _check(per[0], recs, 4, 0.6, W=50, s=3, counts=True) > 40

@@ -567,24 +567,10 @@ void tps_fastx_set_two_pass(tps_fastx *fx, int on) {
   if (fx) fx->slow_only = on;
 }
 
-/* Next batch: at most reads_cap records and bases_cap bases, in file order.
- *   bases_out[offsets_out[i] .. offsets_out[i+1]) = bases of record i; recs_out[i] indexes its text
- *   relative to *raw_base, which stays valid until tps_fastx_release(*raw_owner) (gz input) or
- *   tps_fastx_close (plain input, *raw_owner == NULL).
- * *n_reads == 0 means end of file. */
-int tps_fastx_next(tps_fastx *fx, uint64_t bases_cap, uint32_t reads_cap, uint8_t *bases_out,
-                   uint64_t *offsets_out, tps_fastx_rec *recs_out, uint32_t *n_reads,
-                   const uint8_t **raw_base, void **raw_owner) {
-  if (!fx || !bases_out || !offsets_out || !recs_out || !n_reads || !raw_base || !raw_owner)
-    return fx_fail(fx, TPS_FX_EINVAL, "null argument");
-  *n_reads = 0;
-  *raw_base = NULL;
-  *raw_owner = NULL;
-  offsets_out[0] = 0;
-  if (reads_cap == 0 || bases_cap == 0) return fx_fail(fx, TPS_FX_EINVAL, "zero capacity");
-  /* raw bytes that can hold a full batch: FASTQ carries the quality line too */
-  uint64_t want = (fx->format == TPS_FX_FASTQ ? 2 : 1) * bases_cap + bases_cap / 32 + (uint64_t)reads_cap * 128 + 4096;
-  if (want > fx->window_bytes) want = fx->window_bytes;
+/* Acquire the next window of raw text (a view of the mapping, or a freshly inflated chunk) and index its
+ * records.  Returns 0 with *rv filled, 1 at end of file, <0 on error.  `want` = raw bytes to look at. */
+static int acquire_indexed(tps_fastx *fx, uint64_t want, const uint8_t **w_out, uint8_t **chunk_out, uint64_t *win_out,
+                           int *final_out, rec_vec *rv_out) {
   const uint8_t *w = NULL;
   uint8_t *chunk = NULL;
   uint64_t win = 0;
@@ -593,13 +579,13 @@ int tps_fastx_next(tps_fastx *fx, uint64_t bases_cap, uint32_t reads_cap, uint8_
   memset(&rv, 0, sizeof(rv));
   for (;;) {
     if (!fx->is_gz) {
-      if (fx->pos >= fx->map_len) return TPS_FX_OK;
+      if (fx->pos >= fx->map_len) return 1;
       w = fx->map + fx->pos;
       win = fx->map_len - fx->pos;
       if (win > want) win = want;
       final = fx->pos + win == fx->map_len;
     } else {
-      if (fx->carry_len == 0 && fx->gz_eof) return TPS_FX_OK;
+      if (fx->carry_len == 0 && fx->gz_eof) return 1;
       uint64_t cap = fx->carry_len > want ? fx->carry_len : want;
       if (!chunk) {
         chunk = (uint8_t *)malloc(cap + 1);
@@ -644,6 +630,42 @@ int tps_fastx_next(tps_fastx *fx, uint64_t bases_cap, uint32_t reads_cap, uint8_
       return fx_fail(fx, TPS_FX_ECAPACITY, "record larger than 1 TiB");
     }
     want *= 2;
+  }
+  *w_out = w;
+  *chunk_out = chunk;
+  *win_out = win;
+  *final_out = final;
+  *rv_out = rv;
+  return 0;
+}
+
+/* Next batch: at most reads_cap records and bases_cap bases, in file order.
+ *   bases_out[offsets_out[i] .. offsets_out[i+1]) = bases of record i; recs_out[i] indexes its text
+ *   relative to *raw_base, which stays valid until tps_fastx_release(*raw_owner) (gz input) or
+ *   tps_fastx_close (plain input, *raw_owner == NULL).
+ * *n_reads == 0 means end of file. */
+int tps_fastx_next(tps_fastx *fx, uint64_t bases_cap, uint32_t reads_cap, uint8_t *bases_out,
+                   uint64_t *offsets_out, tps_fastx_rec *recs_out, uint32_t *n_reads,
+                   const uint8_t **raw_base, void **raw_owner) {
+  if (!fx || !bases_out || !offsets_out || !recs_out || !n_reads || !raw_base || !raw_owner)
+    return fx_fail(fx, TPS_FX_EINVAL, "null argument");
+  *n_reads = 0;
+  *raw_base = NULL;
+  *raw_owner = NULL;
+  offsets_out[0] = 0;
+  if (reads_cap == 0 || bases_cap == 0) return fx_fail(fx, TPS_FX_EINVAL, "zero capacity");
+  /* raw bytes that can hold a full batch: FASTQ carries the quality line too */
+  uint64_t want = (fx->format == TPS_FX_FASTQ ? 2 : 1) * bases_cap + bases_cap / 32 + (uint64_t)reads_cap * 128 + 4096;
+  if (want > fx->window_bytes) want = fx->window_bytes;
+  const uint8_t *w = NULL;
+  uint8_t *chunk = NULL;
+  uint64_t win = 0;
+  int final = 0;
+  rec_vec rv;
+  {
+    int rc = acquire_indexed(fx, want, &w, &chunk, &win, &final, &rv);
+    if (rc == 1) return TPS_FX_OK; /* end of file */
+    if (rc) return rc;
   }
   /* longest prefix within the caps */
   uint32_t n = 0;
@@ -698,6 +720,123 @@ int tps_fastx_next(tps_fastx *fx, uint64_t bases_cap, uint32_t reads_cap, uint8_
   }
   fx->n_records += n;
   *n_reads = n;
+  return TPS_FX_OK;
+}
+
+/* ------------------------------------------------------------------ ends batches (ends-first scanning)
+ * Step 1 of the scan only reads the first and the last `end_len` bases of a read (allsteps.py:176-177), so
+ * for inputs that are mostly not telomeric the interior of the reads need not be copied, uploaded or packed
+ * at all: the index pass finds the record boundaries (one memchr over the sequence line, the quality line is
+ * jumped over), then every record contributes head + tail (the whole read when L <= 2 * end_len), packed back
+ * to back.  true_lens_out[i] = L.  The records' text stays addressable through recs_out / *raw_base, which is
+ * where the caller takes the regions of the TRC-pass reads from (tps_submit_regions).
+ * At most `raw_cap` bytes of file text, `reads_cap` records and `bases_cap` uploaded bases per batch. */
+static void gather_ends(const uint8_t *w, const tps_fastx_rec *r, uint32_t end_len, uint8_t *dst) {
+  const uint32_t L = r->seq_len;
+  if (!(r->flags & 1u)) {
+    if (L <= 2u * end_len) {
+      memcpy(dst, w + r->seq_off, L);
+    } else {
+      memcpy(dst, w + r->seq_off, end_len);
+      memcpy(dst + end_len, w + r->seq_off + (L - end_len), end_len);
+    }
+    return;
+  }
+  /* multi-line / blank-carrying sequence: filter it once, then take the ends */
+  uint8_t *tmp = (uint8_t *)malloc(L ? L : 1);
+  if (!tmp) { /* cannot happen for sane L; leave the slot as N so that nothing matches */
+    memset(dst, 'N', L <= 2u * end_len ? L : 2u * end_len);
+    return;
+  }
+  gather_seq(w, r, tmp);
+  if (L <= 2u * end_len) {
+    memcpy(dst, tmp, L);
+  } else {
+    memcpy(dst, tmp, end_len);
+    memcpy(dst + end_len, tmp + (L - end_len), end_len);
+  }
+  free(tmp);
+}
+
+int tps_fastx_next_ends(tps_fastx *fx, uint64_t raw_cap, uint64_t bases_cap, uint32_t reads_cap, uint32_t end_len,
+                        uint8_t *bases_out, uint64_t *starts_out, uint32_t *lens_out, uint32_t *true_lens_out,
+                        tps_fastx_rec *recs_out, uint32_t *n_reads, uint64_t *span_out, uint64_t *true_bases_out,
+                        const uint8_t **raw_base, void **raw_owner) {
+  if (!fx || !bases_out || !starts_out || !lens_out || !true_lens_out || !recs_out || !n_reads || !span_out ||
+      !true_bases_out || !raw_base || !raw_owner)
+    return fx_fail(fx, TPS_FX_EINVAL, "null argument");
+  *n_reads = 0;
+  *span_out = 0;
+  *true_bases_out = 0;
+  *raw_base = NULL;
+  *raw_owner = NULL;
+  if (reads_cap == 0 || bases_cap == 0 || end_len == 0) return fx_fail(fx, TPS_FX_EINVAL, "zero capacity");
+  uint64_t want = raw_cap < 4096 ? 4096 : raw_cap;
+  if (want > fx->window_bytes) want = fx->window_bytes;
+  const uint8_t *w = NULL;
+  uint8_t *chunk = NULL;
+  uint64_t win = 0;
+  int final = 0;
+  rec_vec rv;
+  {
+    int rc = acquire_indexed(fx, want, &w, &chunk, &win, &final, &rv);
+    if (rc == 1) return TPS_FX_OK; /* end of file */
+    if (rc) return rc;
+  }
+  (void)final;
+  uint32_t n = 0;
+  uint64_t nb = 0, tb = 0;
+  while (n < rv.n && n < reads_cap) {
+    const uint32_t L = rv.v[n].seq_len;
+    const uint32_t m = L <= 2u * end_len ? L : 2u * end_len;
+    if (nb + m > bases_cap) break;
+    starts_out[n] = nb;
+    lens_out[n] = m;
+    true_lens_out[n] = L;
+    nb += m;
+    tb += L;
+    ++n;
+  }
+  if (n == 0 && rv.n > 0) {
+    free(rv.v);
+    free(chunk);
+    return fx_fail(fx, TPS_FX_ECAPACITY, "the batch capacity of %llu bases cannot hold the ends of one read",
+                   (unsigned long long)bases_cap);
+  }
+  uint64_t consumed;
+  if (n == rv.n) consumed = rv.end;
+  else consumed = rv.v[n].title_off - 1;
+  if (n) memcpy(recs_out, rv.v, (size_t)n * sizeof(tps_fastx_rec));
+  int T = fx->threads;
+#pragma omp parallel for num_threads(T) schedule(dynamic, 256) if (n > 4096)
+  for (int64_t i = 0; i < (int64_t)n; ++i) gather_ends(w, &rv.v[i], end_len, bases_out + starts_out[i]);
+  free(rv.v);
+  if (!fx->is_gz) {
+    *raw_base = w;
+    fx->pos += consumed;
+    if (n == 0) fx->pos = fx->map_len;
+  } else {
+    uint64_t left = win - consumed;
+    if (n == 0) left = 0;
+    uint8_t *nc = (uint8_t *)realloc(fx->carry, left ? left : 1);
+    if (!nc) {
+      free(chunk);
+      return fx_fail(fx, TPS_FX_ENOMEM, "out of memory");
+    }
+    fx->carry = nc;
+    memcpy(fx->carry, chunk + consumed, left);
+    fx->carry_len = left;
+    if (n) {
+      *raw_base = chunk;
+      *raw_owner = chunk;
+    } else {
+      free(chunk);
+    }
+  }
+  fx->n_records += n;
+  *n_reads = n;
+  *span_out = nb;
+  *true_bases_out = tb;
   return TPS_FX_OK;
 }
 

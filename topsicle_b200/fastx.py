@@ -61,6 +61,10 @@ def host_library() -> C.CDLL:
         lib.tps_fastx_next_spans.restype = C.c_int
         lib.tps_fastx_next_spans.argtypes = [vp, C.c_uint64, C.c_uint32, vp, vp, vp, vp, C.POINTER(C.c_uint32),
                                              C.POINTER(C.c_uint64), C.POINTER(vp), C.POINTER(vp)]
+        lib.tps_fastx_next_ends.restype = C.c_int
+        lib.tps_fastx_next_ends.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, vp, vp, vp, vp, vp,
+                                            C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                            C.POINTER(vp), C.POINTER(vp)]
         lib.tps_fastx_set_two_pass.restype = None
         lib.tps_fastx_set_two_pass.argtypes = [vp, C.c_int]
         lib.tps_fastx_find_id.restype = C.c_uint32
@@ -146,6 +150,38 @@ class Batch:
         self._raw = None
 
 
+class EndsBatch(Batch):
+    """A batch of the ends-first reader: `bases` holds head + tail of every read (the whole read when it is no
+    longer than 2 * end_len), `true_lens[i]` its real length; the full sequence is read from the raw text."""
+
+    def __init__(self, *a, true_lens=None, true_bases=0, end_len=0, **kw):
+        super().__init__(*a, **kw)
+        self.true_lens = true_lens
+        self.true_bases = int(true_bases)
+        self.end_len = end_len
+
+    @property
+    def n_bases(self) -> int:          # bases of the reads themselves (what was scanned), not what was uploaded
+        return self.true_bases
+
+    def sequence(self, i) -> bytes:
+        r = self.recs[i]
+        if not (int(r["flags"]) & 1):
+            return self._text(r["seq_off"], r["seq_len"])
+        raw = self._text(r["seq_off"], r["seq_raw_len"])
+        return raw.translate(None, b" \r\n\t\x0b\x0c")
+
+    def region(self, i, tail: int, maxlengthtelo: int) -> bytes:
+        """The bases steps 2/3 look at: first (tail 0) or last (tail 1) min(L, maxlengthtelo) bases."""
+        r = self.recs[i]
+        L = int(r["seq_len"])
+        k = min(L, int(maxlengthtelo))
+        if not (int(r["flags"]) & 1):
+            return self._text(int(r["seq_off"]) + (0 if tail == 0 else L - k), k)
+        s = self.sequence(i)
+        return s[:k] if tail == 0 else s[L - k:]
+
+
 class FastxFile:
     """An open FASTQ / FASTA file (gzip if the name ends in `.gz`, as the reference decides)."""
 
@@ -211,6 +247,35 @@ class FastxFile:
             return None
         b = Batch(self._lib, n.value, bases, starts, recs[:n.value], raw.value, owner.value, self.reads_delivered,
                   self.format, lens=lens, span=span.value)
+        self.reads_delivered += n.value
+        return b
+
+    def next_ends(self, bases: np.ndarray, starts: np.ndarray, lens: np.ndarray, true_lens: np.ndarray, end_len: int,
+                  raw_cap: int = 1 << 30, max_reads: int | None = None, max_bases: int | None = None,
+                  recs: np.ndarray | None = None) -> EndsBatch | None:
+        """Next batch of the ends-first reader (`tps_submit_ends`): read i contributes its first and last
+        `end_len` bases, packed back to back; at most `raw_cap` bytes of file text per batch."""
+        assert bases.dtype == np.uint8 and starts.dtype == np.uint64 and lens.dtype == np.uint32
+        assert true_lens.dtype == np.uint32
+        reads_cap = min(len(starts), len(lens), len(true_lens), max_reads if max_reads is not None else 1 << 31)
+        bases_cap = min(bases.size, max_bases if max_bases is not None else 1 << 62)
+        if recs is None:
+            recs = np.empty(reads_cap, dtype=REC_DTYPE)
+        else:
+            reads_cap = min(reads_cap, len(recs))
+        n, span, tb = C.c_uint32(0), C.c_uint64(0), C.c_uint64(0)
+        raw, owner = C.c_void_p(), C.c_void_p()
+        rc = self._lib.tps_fastx_next_ends(self._h, raw_cap, bases_cap, reads_cap, end_len, bases.ctypes.data,
+                                           starts.ctypes.data, lens.ctypes.data, true_lens.ctypes.data,
+                                           recs.ctypes.data, C.byref(n), C.byref(span), C.byref(tb), C.byref(raw),
+                                           C.byref(owner))
+        if rc != 0:
+            raise FastxError(rc, self._lib.tps_fastx_last_error(self._h).decode())
+        if n.value == 0:
+            return None
+        b = EndsBatch(self._lib, n.value, bases, starts, recs[:n.value], raw.value, owner.value, self.reads_delivered,
+                      self.format, lens=lens, span=span.value, true_lens=true_lens, true_bases=tb.value,
+                      end_len=end_len)
         self.reads_delivered += n.value
         return b
 

@@ -253,7 +253,9 @@ def analysis_run(args):
     scanner = pipeline.Scanner(scan_configs(args, telo_phrases, patterns, sliding_val), devices=devices,
                                threads=args.threads or 0,
                                max_batch_bases=int(os.environ.get("TOPSICLE_BATCH_BASES", auto_bases)),
-                               max_batch_reads=int(os.environ.get("TOPSICLE_BATCH_READS", 1 << 17)))
+                               max_batch_reads=int(os.environ.get("TOPSICLE_BATCH_READS", 1 << 17)),
+                               ends_first=bool(getattr(args, "ends_first", False)
+                                               or os.environ.get("TOPSICLE_ENDS_FIRST", "0") not in ("", "0")))
     writers = []
     try:
         if args.read_check:
@@ -366,6 +368,10 @@ def build_parser():
                    help="Override telolengths_all.csv file but keep subset fastq")
     p.add_argument("--threads", "-t", metavar="INT", type=int,
                    help="Number of CPU cores to use (by default, all available cores)", default=None)
+    p.add_argument("--ends-first", dest="ends_first", action="store_true",
+                   help="B200 only, optional: upload just the first/last 1000 bases of every read, then the "
+                        "telomere regions of the reads that pass TRC (same outputs; about a tenth of the bytes "
+                        "cross PCIe; also TOPSICLE_ENDS_FIRST=1)")
     p.add_argument("--devices", nargs="+", metavar="INT", type=int,
                    help="(B200 build) CUDA devices to scan on; default: all visible devices")
     return p

@@ -14,6 +14,12 @@ collective).  Several phrases (`--telophrase 4 5 6`) are scanned from ONE parse 
 Results are handed to the caller's sink strictly in file order, whatever order the devices
 finish in, so CSV rows, `rawcount_{phrase}_{i}.csv` numbering and the subset file come out
 exactly as the reference writes them.
+
+Ends-first mode (`Scanner(ends_first=True)`, CLI `--ends-first`): step 1 only looks at the first and last
+`no_bp` bases of a read and steps 2/3 only at one end of the TRC-pass reads, so the reader copies just
+head + tail of every read (`tps_fastx_next_ends`), the device runs K1 + K2 on those (`tps_submit_ends`),
+and the regions of the few TRC-pass reads are taken from the file text afterwards and scanned as a second,
+small batch (`tps_submit_regions`).  Same rows, same files; about a tenth of the bytes cross PCIe.
 """
 from __future__ import annotations
 
@@ -74,6 +80,7 @@ class BatchResult:
     n_bases: int
     n_scanned: int                     # reads with L > minSeqLength
     passes: list = field(default_factory=list)   # per config: list[PassRead]
+    n_uploaded: int = 0                # bases that crossed PCIe for this batch (ends-first: ends + regions)
 
 
 @dataclass
@@ -82,6 +89,7 @@ class FileStats:
     n_bases: int = 0
     n_scanned: int = 0
     n_batches: int = 0
+    n_uploaded: int = 0                # bases that crossed PCIe (== n_bases unless ends-first)
     format_name: str = ""
     timing: dict = field(default_factory=dict)   # seconds: open, parse (reader thread), submit, wait, harvest, close
 
@@ -108,12 +116,14 @@ class _Slot:
         self.bases = engine.PinnedBuffer(max_bases)
         self.offsets = engine.PinnedBuffer((max_reads + 1) * 8)     # read starts (uint64)
         self.lens = engine.PinnedBuffer(max_reads * 4)              # read lengths (uint32)
+        self.true_lens = engine.PinnedBuffer(max_reads * 4)         # ends batches: real read lengths (uint32)
         self.recs = np.empty(max_reads, dtype=fastx.REC_DTYPE)
 
     def free(self):
         self.bases.free()
         self.offsets.free()
         self.lens.free()
+        self.true_lens.free()
 
 
 def make_context(cfg: ScanConfig, device: int, max_batch_reads: int, max_batch_bases: int, n_slots: int,
@@ -132,8 +142,9 @@ def windows_per_read(cfg: ScanConfig) -> int:
     return (reg - cfg.window_size) // cfg.slide + 1 if reg >= cfg.window_size else 0
 
 
-def harvest(cfg: ScanConfig, ctx, batch, rows, raw, want_records: bool, keep=None) -> list:  # noqa: D401
-    """TRC-pass reads of one finished batch, in read order."""
+def harvest(cfg: ScanConfig, ctx, batch, rows, raw, want_records: bool, keep=None, tables=None) -> list:  # noqa: D401
+    """TRC-pass reads of one finished batch, in read order.  `tables` (ends-first mode) maps a read index to
+    its raw-count table instead of `raw` + the rows' offsets."""
     out = []
     idx = np.nonzero(rows["status"] >= engine.ST_PASS)[0]
     if len(idx) == 0:
@@ -149,7 +160,9 @@ def harvest(cfg: ScanConfig, ctx, batch, rows, raw, want_records: bool, keep=Non
         pr = PassRead(index=batch.first_read + i, read_id=rid, literal=ctx.patterns[bp],
                       tail=engine.TAIL_NAMES[tl], count=cnt, trc=cnt / ratio, status=st,
                       n_windows=nw, telo_length=telo, length=length)
-        if cfg.want_rawcount and raw is not None:
+        if cfg.want_rawcount and tables is not None:
+            pr.counts = tables.get(i)
+        elif cfg.want_rawcount and raw is not None:
             tab = ctx.rawcount_table(rows, raw, i)
             pr.counts = None if tab is None else tab.copy()
         if want_records:
@@ -163,30 +176,117 @@ class _DeviceWorker:
     packs each batch; the others scan the same device-resident batch (tps_submit_shared)."""
 
     def __init__(self, device, cfgs, max_batch_reads, max_batch_bases, depth, max_pass_reads, rawcount_capacity,
-                 context_factory):
+                 context_factory, ends_first=False):
         self.device = device
         self.cfgs = cfgs
         self.max_batch_reads = max_batch_reads
         self.max_batch_bases = max_batch_bases
+        self.max_pass_reads = max_pass_reads
         self.ctxs = []
+        # ends-first: every context also scans its own region batches (the TRC-pass reads differ per phrase)
+        self.region_cap = 0
+        if ends_first:
+            longest = max(max(1, c.maxlengthtelo) for c in cfgs)
+            self.region_cap = int(min(max_batch_bases, max(1 << 20, max_pass_reads * longest)))
         for k, c in enumerate(cfgs):
-            # followers never upload: they need no base / code buffers of their own
-            self.ctxs.append(context_factory(c, device, max_batch_reads, max_batch_bases if k == 0 else 1, depth,
+            # followers never upload whole batches: they need no base / code buffers beyond the region batches
+            self.ctxs.append(context_factory(c, device, max_batch_reads,
+                                             max_batch_bases if k == 0 else max(1, self.region_cap), depth,
                                              max_pass_reads, rawcount_capacity if c.want_rawcount else 0))
+        self.reg = None
         with numa.near_device(device):      # pinned staging on the GPU's own NUMA node
             self.slots = [_Slot(max_batch_bases, max_batch_reads) for _ in range(depth)]
+            if ends_first:
+                self.reg = _Slot(self.region_cap, max_pass_reads)
+                self.reg_tails = engine.PinnedBuffer(max_pass_reads)
 
     def close(self):
         for c in self.ctxs:
             c.close()
         for s in self.slots:
             s.free()
+        if self.reg is not None:
+            self.reg.free()
+            self.reg_tails.free()
+            self.reg = None
 
-    def submit(self, bases, starts, lens, n_reads):
-        bid = self.ctxs[0].submit_spans(bases, starts, lens, n_reads)
+    def submit(self, bases, starts, lens, n_reads, true_lens=None):
+        if true_lens is not None:
+            bid = self.ctxs[0].submit_ends(bases, starts, lens, true_lens, n_reads)
+        else:
+            bid = self.ctxs[0].submit_spans(bases, starts, lens, n_reads)
         for c in self.ctxs[1:]:
             c.submit_shared(self.ctxs[0], bid)
         return bid
+
+    # -- ends-first mode: steps 2/3 of the TRC-pass reads of an ends batch
+    def _scan_regions(self, ci, batch, rows, idx, tables):
+        """Scan the regions of reads `idx` (TRC-pass under config ci) and merge status / n_windows / bkp /
+        telo_length into `rows`; raw-count tables go to `tables[i]`.  Groups are cut to the context's
+        capacities and halved again if the raw-count buffer overflows."""
+        cfg, ctx = self.cfgs[ci], self.ctxs[ci]
+        reg = self.reg
+        rb = reg.bases.array
+        rstarts = reg.offsets.array.view(np.uint64)
+        rlens = reg.lens.array.view(np.uint32)
+        rtails = self.reg_tails.array
+        tails = rows["tail"]
+        pending = [list(map(int, idx))]
+        while pending:
+            group = pending.pop(0)
+            n, at, used = 0, 0, []
+            for i in group:                       # longest prefix that fits one region batch
+                r = batch.region(i, int(tails[i]), cfg.maxlengthtelo)
+                if n >= self.max_pass_reads or at + len(r) > self.region_cap:
+                    break
+                rb[at:at + len(r)] = np.frombuffer(r, dtype=np.uint8)
+                rstarts[n], rlens[n], rtails[n] = at, len(r), tails[i]
+                at += len(r)
+                n += 1
+                used.append(i)
+            if n == 0:
+                raise engine.TpsError(-4, f"a region of {len(r)} bases does not fit the batch capacity "
+                                          f"of {self.region_cap}")
+            if n < len(group):
+                pending.insert(0, group[n:])
+            try:
+                bid = ctx.submit_regions(rb[:at], rstarts[:n], rlens[:n], rtails[:n], n)
+                self._region_bases += at
+                rows2, raw2 = ctx.wait(bid, True)
+            except engine.TpsError as e:
+                if e.code != -4 or n <= 1:
+                    raise
+                pending.insert(0, used[n // 2:])
+                pending.insert(0, used[:n // 2])
+                continue
+            for f in ("status", "n_windows", "bkp", "telo_length"):
+                rows[f][used] = rows2[f][:n]
+            if cfg.want_rawcount and raw2 is not None:
+                for j, i in enumerate(used):
+                    tab = ctx.rawcount_table(rows2, raw2, j)
+                    tables[i] = None if tab is None else tab.copy()
+
+    def finish_ends(self, item, records_cfg, keep):
+        slot, batch, bid, seq = item
+        res = BatchResult(seq=seq, first_read=batch.first_read, n_reads=batch.n_reads, n_bases=batch.n_bases,
+                          n_scanned=0, n_uploaded=int(batch.span))
+        self._region_bases = 0
+        waited = [ctx.wait(bid)[0] for ctx in self.ctxs]      # step-1 rows under every config
+        for ci, (cfg, ctx) in enumerate(zip(self.cfgs, self.ctxs)):
+            rows = waited[ci]
+            tables = {}
+            idx = np.nonzero(rows["status"] == engine.ST_PASS)[0]
+            if len(idx) and keep is not None:
+                idx = np.array([i for i in idx if batch.read_id(int(i)) in keep], dtype=np.int64)
+            if len(idx) and not cfg.step1_only:
+                self._scan_regions(ci, batch, rows, idx, tables)
+            res.passes.append(harvest(cfg, ctx, batch, rows, None, records_cfg == ci, keep,
+                                      tables=tables if cfg.want_rawcount else None))
+            if ci == 0:
+                res.n_scanned = int((rows["status"] != engine.ST_FILTERED).sum())
+        res.n_uploaded += self._region_bases
+        batch.release()
+        return res
 
     def _scan_sub(self, ci, bases, starts, lens, lo, hi):
         """Synchronous scan of reads [lo, hi) of a batch under config ci, splitting again on capacity
@@ -216,9 +316,11 @@ class _DeviceWorker:
                     + self._scan_sub(ci, bases, starts, lens, mid, hi))
 
     def finish(self, item, records_cfg, keep):
+        if isinstance(item[1], fastx.EndsBatch):
+            return self.finish_ends(item, records_cfg, keep)
         slot, batch, bid, seq = item
         res = BatchResult(seq=seq, first_read=batch.first_read, n_reads=batch.n_reads, n_bases=batch.n_bases,
-                          n_scanned=0)
+                          n_scanned=0, n_uploaded=int(batch.span))
         n = batch.n_reads
         waited = []
         for ctx in self.ctxs:                      # release every context's slot before any re-scan
@@ -269,8 +371,12 @@ class Scanner:
 
     def __init__(self, cfgs: Sequence[ScanConfig], *, devices: Sequence[int] = (0,), threads: int = 0,
                  max_batch_bases: int = 1 << 28, max_batch_reads: int = 1 << 17, depth: int = 3,
-                 max_pass_reads: int = 0, rawcount_capacity: int = 0, context_factory=None):
+                 max_pass_reads: int = 0, rawcount_capacity: int = 0, context_factory=None,
+                 ends_first: bool = False, ends_raw_bytes: int = 1 << 28):
         context_factory = context_factory or make_context
+        self.ends_first = bool(ends_first)
+        self.ends_raw_bytes = int(ends_raw_bytes)        # file text per ends batch
+        self.end_len = max(int(c.no_bp) for c in cfgs)   # head / tail bases every config needs
         if not max_pass_reads:
             max_pass_reads = max(1024, max_batch_reads // 8)
         if not rawcount_capacity and any(c.want_rawcount for c in cfgs):
@@ -282,7 +388,8 @@ class Scanner:
         try:
             for d in devices:
                 self.workers.append(_DeviceWorker(d, self.cfgs, max_batch_reads, max_batch_bases, depth,
-                                                  max_pass_reads, rawcount_capacity, context_factory))
+                                                  max_pass_reads, rawcount_capacity, context_factory,
+                                                  ends_first=self.ends_first))
         except BaseException:
             self.close()
             raise
@@ -350,6 +457,7 @@ class Scanner:
             """Called by a worker after it finished one batch of `job`."""
             job.ordered.put(res)
             with lock:
+                job.stats.n_uploaded += res.n_uploaded
                 job.n_delivered += 1
                 done = job.eof and job.n_delivered == job.stats.n_batches
             if done:
@@ -373,9 +481,16 @@ class Scanner:
                             free.put(None)      # let the other readers see the stop signal too
                             return
                         t = time.perf_counter()
-                        batch = job.fx.next_spans(slot.bases.array, slot.offsets.array.view(np.uint64),
-                                                  slot.lens.array.view(np.uint32), max_reads=w0.max_batch_reads,
-                                                  max_span=w0.max_batch_bases, recs=slot.recs)
+                        if self.ends_first:
+                            batch = job.fx.next_ends(slot.bases.array, slot.offsets.array.view(np.uint64),
+                                                     slot.lens.array.view(np.uint32),
+                                                     slot.true_lens.array.view(np.uint32), self.end_len,
+                                                     raw_cap=self.ends_raw_bytes, max_reads=w0.max_batch_reads,
+                                                     max_bases=w0.max_batch_bases, recs=slot.recs)
+                        else:
+                            batch = job.fx.next_spans(slot.bases.array, slot.offsets.array.view(np.uint64),
+                                                      slot.lens.array.view(np.uint32), max_reads=w0.max_batch_reads,
+                                                      max_span=w0.max_batch_bases, recs=slot.recs)
                         job.stats.timing["parse"] += time.perf_counter() - t
                         if batch is None:
                             free.put(slot)
@@ -416,7 +531,8 @@ class Scanner:
                     job, slot, batch, seq = got
                     t = time.perf_counter()
                     bid = w.submit(slot.bases.array[:batch.span], batch.offsets[:batch.n_reads],
-                                   batch.lens[:batch.n_reads], batch.n_reads)
+                                   batch.lens[:batch.n_reads], batch.n_reads,
+                                   batch.true_lens[:batch.n_reads] if isinstance(batch, fastx.EndsBatch) else None)
                     job.stats.timing["submit"] += time.perf_counter() - t
                     inflight.append((job, (slot, batch, bid, seq)))
                 while inflight and not errors:

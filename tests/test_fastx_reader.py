@@ -224,3 +224,60 @@ def test_next_ends_head_tail_and_regions(tmp_path, end_len, suffix):
         assert g[0] == rid and g[1] == len(s)
         assert g[2] == (s if len(s) <= 2 * end_len else s[:end_len] + s[-end_len:])
         assert g[3] == s and g[4] == s[:20000] and g[5] == s[-777:]
+
+
+def _write_bgzf(path, data, block=0xff00):
+    """bgzip's format: gzip members of <= 64 KiB with the 'BC' extra field (compressed block size - 1),
+    closed by the empty end-of-file block."""
+    import struct
+    import zlib
+    with open(path, "wb") as fh:
+        for a in list(range(0, len(data), block)) + [None]:
+            chunk = b"" if a is None else data[a:a + block]
+            co = zlib.compressobj(6, zlib.DEFLATED, -15)
+            body = co.compress(chunk) + co.flush()
+            bsize = 12 + 6 + len(body) + 8
+            fh.write(b"\x1f\x8b\x08\x04" + b"\0\0\0\0" + b"\0\xff" + struct.pack("<H", 6) +
+                     b"BC" + struct.pack("<HH", 2, bsize - 1) + body +
+                     struct.pack("<II", zlib.crc32(chunk) & 0xffffffff, len(chunk)))
+
+
+@pytest.mark.parametrize("threads", [1, 4])
+def test_bgzf_blocks_inflated_in_parallel(tmp_path, threads):
+    """A BGZF (.gz) file gives the same records as the plain-gzip file, through every reader entry point;
+    Python's gzip (what the reference uses) reads it too; a corrupt block is an error, not a short file."""
+    src = os.path.join(GOLD, "demo.fastq.gz")
+    text = gzip.open(src, "rb").read() * 3              # ~5 MB, 80 blocks
+    path = str(tmp_path / "demo3.fastq.gz")
+    _write_bgzf(path, text)
+    assert gzip.open(path, "rb").read() == text
+    want = [(rid, s) for _ in range(3) for rid, s in orc.read_fastx(src)]
+    bases = np.empty(1 << 23, np.uint8)
+    offsets = np.empty(4096, np.uint64)
+    starts, lens, tl = np.empty(4096, np.uint64), np.empty(4096, np.uint32), np.empty(4096, np.uint32)
+    for mode in ("next", "spans", "ends"):
+        got = []
+        with fastx.FastxFile(path, threads=threads) as fx:
+            assert fx.format_name == "fastq"
+            fx.set_window(700_000)
+            while True:
+                if mode == "next":
+                    b = fx.next_batch(bases, offsets, max_bases=400_000)
+                elif mode == "spans":
+                    b = fx.next_spans(bases, starts, lens, max_span=300_000)
+                else:
+                    b = fx.next_ends(bases, starts, lens, tl, 1000, raw_cap=500_000)
+                if b is None:
+                    break
+                for i in range(b.n_reads):
+                    got.append((b.read_id(i), b.sequence(i).decode()))
+                b.release()
+        assert got == want, mode
+    raw = bytearray(open(path, "rb").read())
+    raw[len(raw) // 2] ^= 0x55
+    bad = str(tmp_path / "bad.fastq.gz")
+    open(bad, "wb").write(bytes(raw))
+    with pytest.raises(fastx.FastxError):
+        with fastx.FastxFile(bad, threads=threads) as fx:
+            while fx.next_batch(bases, offsets) is not None:
+                pass

@@ -19,8 +19,8 @@
  *
  * Plain files are mmap-ed and indexed by several threads (a window is cut into segments,
  * every segment finds its first record start on its own; the pieces must chain exactly or
- * the window is re-indexed sequentially).  `.gz` files are inflated with zlib by the calling
- * thread into chunk buffers that the batch then owns.
+ * the window is re-indexed sequentially).  `.gz` files are inflated with zlib into chunk buffers
+ * that the batch then owns: plain gzip by the calling thread, BGZF (bgzip) by all parser threads.
  */
 #define _GNU_SOURCE
 #include <errno.h>
@@ -79,6 +79,10 @@ typedef struct tps_fastx {
   uint8_t *carry;
   uint64_t carry_len;
   int gz_eof;
+  /* BGZF (bgzip) input: independent <= 64 KiB deflate blocks, inflated by all parser threads */
+  int is_bgzf;
+  const uint8_t *zmap;
+  uint64_t zlen, zpos;
   uint64_t window_bytes;
   int threads;
   int slow_only;      /* never use the one-pass FASTQ reader (tests / tuning) */
@@ -459,6 +463,109 @@ static int index_window(tps_fastx *fx, const uint8_t *w, uint64_t win_end, int f
 }
 
 /* ------------------------------------------------------------------------------ public API */
+/* ------------------------------------------------------------------ gzip input
+ * Plain gzip is one sequential deflate stream: zlib inflates it on the reader thread (gzread).  BGZF
+ * (bgzip, the block-gzip of htslib) is a series of gzip members of <= 64 KiB whose compressed size is in
+ * an extra header field, so the block boundaries are known without inflating and every parser thread
+ * inflates its own blocks.  Python's gzip module -- what the reference opens `.gz` files with,
+ * allsteps.py:141-143 -- reads both the same way. */
+static int bgzf_header(const uint8_t *p, uint64_t avail, uint32_t *bsize, uint32_t *hdr) {
+  if (avail < 18 || p[0] != 0x1f || p[1] != 0x8b || p[2] != 8 || !(p[3] & 4)) return 0;
+  const uint32_t xlen = (uint32_t)p[10] | ((uint32_t)p[11] << 8);
+  if (12ull + xlen > avail) return 0;
+  uint32_t at = 12, end = 12 + xlen;
+  while (at + 4 <= end) {
+    const uint32_t slen = (uint32_t)p[at + 2] | ((uint32_t)p[at + 3] << 8);
+    if (p[at] == 'B' && p[at + 1] == 'C' && slen == 2 && at + 6 <= end) {
+      *bsize = ((uint32_t)p[at + 4] | ((uint32_t)p[at + 5] << 8)) + 1u;
+      *hdr = end;
+      return *bsize >= end + 8u && *bsize <= avail && !(p[3] & ~4); /* no name / comment / hcrc fields */
+    }
+    at += 4 + slen;
+  }
+  return 0;
+}
+
+typedef struct bgzf_blk {
+  uint64_t zoff, out;
+  uint32_t zsize, hdr, isize;
+} bgzf_blk;
+
+/* Append inflated text to chunk[*win .. cap): as much as fits.  Sets fx->gz_eof at the end of the input.
+ * Returns 0, or <0 after fx_fail. */
+static int gz_fill(tps_fastx *fx, uint8_t *chunk, uint64_t *win, uint64_t cap) {
+  if (!fx->is_bgzf) {
+    while (*win < cap && !fx->gz_eof) {
+      uint64_t ask = cap - *win;
+      if (ask > (1u << 30)) ask = 1u << 30;
+      int n = gzread(fx->gz, chunk + *win, (unsigned)ask);
+      if (n < 0) return fx_fail(fx, TPS_FX_EIO, "gzip read error");
+      if (n == 0) fx->gz_eof = 1;
+      *win += (uint64_t)n;
+    }
+    return TPS_FX_OK;
+  }
+  bgzf_blk *blk = NULL;
+  size_t nb = 0, capb = 0;
+  uint64_t out = *win, z = fx->zpos;
+  while (z < fx->zlen) {
+    uint32_t bsize = 0, hdr = 0;
+    if (!bgzf_header(fx->zmap + z, fx->zlen - z, &bsize, &hdr)) {
+      free(blk);
+      return fx_fail(fx, TPS_FX_EIO, "corrupt BGZF block header at compressed offset %llu", (unsigned long long)z);
+    }
+    const uint8_t *t = fx->zmap + z + bsize - 4;
+    const uint32_t isize = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
+    if (out + isize > cap) break;
+    if (nb == capb) {
+      capb = capb ? capb * 2 : 4096;
+      bgzf_blk *nv = (bgzf_blk *)realloc(blk, capb * sizeof(*nv));
+      if (!nv) {
+        free(blk);
+        return fx_fail(fx, TPS_FX_ENOMEM, "out of memory");
+      }
+      blk = nv;
+    }
+    blk[nb].zoff = z; blk[nb].out = out; blk[nb].zsize = bsize; blk[nb].hdr = hdr; blk[nb].isize = isize;
+    ++nb;
+    out += isize;
+    z += bsize;
+  }
+  int bad = 0;
+#pragma omp parallel for num_threads(fx->threads) schedule(dynamic, 8) if (nb > 16)
+  for (int64_t i = 0; i < (int64_t)nb; ++i) {
+    const bgzf_blk *b = &blk[i];
+    if (b->isize == 0) continue; /* the empty end-of-file block */
+    z_stream zs;
+    memset(&zs, 0, sizeof(zs));
+    int ok = inflateInit2(&zs, -15) == Z_OK;
+    if (ok) {
+      zs.next_in = (Bytef *)(fx->zmap + b->zoff + b->hdr);
+      zs.avail_in = b->zsize - b->hdr - 8u;
+      zs.next_out = chunk + b->out;
+      zs.avail_out = b->isize;
+      ok = inflate(&zs, Z_FINISH) == Z_STREAM_END && zs.total_out == b->isize;
+      inflateEnd(&zs);
+    }
+    if (ok) {
+      const uint8_t *t = fx->zmap + b->zoff + b->zsize - 8;
+      const uint32_t want = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
+      ok = (uint32_t)crc32(crc32(0L, Z_NULL, 0), chunk + b->out, b->isize) == want;
+    }
+    if (!ok) {
+#pragma omp atomic write
+      bad = 1;
+    }
+  }
+  free(blk);
+  if (bad) return fx_fail(fx, TPS_FX_EIO, "corrupt BGZF block (inflate / CRC) near compressed offset %llu",
+                          (unsigned long long)fx->zpos);
+  fx->zpos = z;
+  *win = out;
+  if (z >= fx->zlen) fx->gz_eof = 1;
+  return TPS_FX_OK;
+}
+
 int tps_fastx_open(tps_fastx **out, const char *path, int threads) {
   if (!out || !path) return fx_fail(NULL, TPS_FX_EINVAL, "null argument");
   *out = NULL;
@@ -471,6 +578,41 @@ int tps_fastx_open(tps_fastx **out, const char *path, int threads) {
   fx->is_gz = pl >= 3 && strcmp(path + pl - 3, ".gz") == 0; /* by suffix, allsteps.py:37,141 */
   uint8_t first = 0;
   if (fx->is_gz) {
+    /* BGZF?  Map the compressed file and look at the first block header */
+    int zfd = open(path, O_RDONLY);
+    struct stat zst;
+    if (zfd >= 0 && fstat(zfd, &zst) == 0 && zst.st_size >= 28) {
+      void *zm = mmap(NULL, (size_t)zst.st_size, PROT_READ, MAP_PRIVATE, zfd, 0);
+      uint32_t bs = 0, hd = 0;
+      if (zm != MAP_FAILED && bgzf_header((const uint8_t *)zm, (uint64_t)zst.st_size, &bs, &hd)) {
+        fx->is_bgzf = 1;
+        fx->zmap = (const uint8_t *)zm;
+        fx->zlen = (uint64_t)zst.st_size;
+        fx->fd = zfd;
+        zfd = -1;
+      } else if (zm != MAP_FAILED) {
+        munmap(zm, (size_t)zst.st_size);
+      }
+    }
+    if (zfd >= 0) close(zfd);
+  }
+  if (fx->is_bgzf) {
+    fx->carry = (uint8_t *)malloc(1u << 17);
+    uint64_t got = 0;
+    if (!fx->carry || gz_fill(fx, fx->carry, &got, 1u << 17)) {
+      int rc = fx->carry ? TPS_FX_EIO : TPS_FX_ENOMEM;
+      snprintf(g_open_err, sizeof(g_open_err), "%s", fx->carry ? fx->err : "out of memory");
+      munmap((void *)fx->zmap, fx->zlen);
+      close(fx->fd);
+      free(fx->carry);
+      free(fx);
+      return rc;
+    }
+    fx->carry_len = got;
+    uint64_t i = 0; /* check_file_type: first line, stripped (allsteps.py:40) */
+    while (i < fx->carry_len && is_ws(fx->carry[i]) && fx->carry[i] != '\n') ++i;
+    first = i < fx->carry_len ? fx->carry[i] : 0;
+  } else if (fx->is_gz) {
     fx->gz = gzopen(path, "rb");
     if (!fx->gz) {
       int rc = fx_fail(NULL, TPS_FX_EIO, "cannot open %s: %s", path, strerror(errno));
@@ -524,6 +666,7 @@ int tps_fastx_open(tps_fastx **out, const char *path, int threads) {
                      path);
     if (fx->gz) gzclose(fx->gz);
     if (fx->map) munmap((void *)fx->map, fx->map_len);
+    if (fx->zmap) munmap((void *)fx->zmap, fx->zlen);
     if (fx->fd >= 0) close(fx->fd);
     free(fx->carry);
     free(fx);
@@ -552,6 +695,7 @@ static void unmap_parallel(const uint8_t *map, uint64_t len, int threads) {
 void tps_fastx_close(tps_fastx *fx) {
   if (!fx) return;
   if (fx->gz) gzclose(fx->gz);
+  if (fx->zmap) munmap((void *)fx->zmap, fx->zlen);
   if (fx->map) unmap_parallel(fx->map, fx->map_len, fx->threads);
   if (fx->fd >= 0) close(fx->fd);
   free(fx->carry);
@@ -600,16 +744,12 @@ static int acquire_indexed(tps_fastx *fx, uint64_t want, const uint8_t **w_out, 
         }
         chunk = nc;
       }
-      while (win < cap && !fx->gz_eof) {
-        uint64_t ask = cap - win;
-        if (ask > (1u << 30)) ask = 1u << 30;
-        int n = gzread(fx->gz, chunk + win, (unsigned)ask);
-        if (n < 0) {
+      {
+        int frc = gz_fill(fx, chunk, &win, cap);
+        if (frc) {
           free(chunk);
-          return fx_fail(fx, TPS_FX_EIO, "gzip read error");
+          return frc;
         }
-        if (n == 0) fx->gz_eof = 1;
-        win += (uint64_t)n;
       }
       w = chunk;
       final = fx->gz_eof;
@@ -1011,16 +1151,12 @@ int tps_fastx_next_spans(tps_fastx *fx, uint64_t span_cap, uint32_t reads_cap, u
     if (!chunk) return fx_fail(fx, TPS_FX_ENOMEM, "out of memory for a %llu-byte chunk", (unsigned long long)want);
     memcpy(chunk, fx->carry, fx->carry_len);
     win = fx->carry_len;
-    while (win < want && !fx->gz_eof) {
-      uint64_t ask = want - win;
-      if (ask > (1u << 30)) ask = 1u << 30;
-      int n = gzread(fx->gz, chunk + win, (unsigned)ask);
-      if (n < 0) {
+    {
+      int frc = gz_fill(fx, chunk, &win, want);
+      if (frc) {
         free(chunk);
-        return fx_fail(fx, TPS_FX_EIO, "gzip read error");
+        return frc;
       }
-      if (n == 0) fx->gz_eof = 1;
-      win += (uint64_t)n;
     }
     w = chunk;
     final = fx->gz_eof;

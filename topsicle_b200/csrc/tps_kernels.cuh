@@ -556,14 +556,27 @@ __device__ __forceinline__ void tps_trc_end_reg(const TpsScanArgs &a, const TpsP
 #pragma unroll
   for (uint32_t h = 0; h < 2u; ++h) {
     const uint32_t gi = 2u * lane + h;
-    if (gi < ng) {
-      const uint64_t g = gfirst + gi;
-      const uint32_t y = tps_linear_planes(__ldg(a.pk.codes + g));
-      const uint32_t v = tps_group_valid(a.pk.flags, a.pk.bases, g);
-      L0 |= (y & 0xFFFFu) << (16u * h);
-      L1 |= (y >> 16) << (16u * h);
-      LV |= v << (16u * h);
+    const bool in = gi < ng;
+    const uint64_t g = gfirst + gi;
+    uint32_t y = 0u, v = in ? 0xFFFFu : 0u;
+    bool flagged = false;
+    if (in) {
+      y = tps_linear_planes(__ldg(a.pk.codes + g));
+      flagged = (__ldg(a.pk.flags + (g >> 5)) >> (g & 31)) & 1u;
     }
+    /* exact validity of the (rare) flagged groups, one group at a time by the whole warp: 16 lanes test one
+     * ASCII byte each and a ballot is the mask -- a dozen instructions instead of the 65 of the per-lane
+     * bit-sliced formula that every lane would execute for the sake of one */
+    for (uint32_t fb = __ballot_sync(TPS_FULL, flagged); fb; fb &= fb - 1u) {
+      const uint32_t src = (uint32_t)__ffs((int)fb) - 1u;
+      const uint64_t gg = gfirst + 2u * src + h;
+      const uint32_t c = lane < 16u ? (uint32_t)__ldg(a.pk.bases + 16u * gg + lane) : 0x41u;
+      const uint32_t m = __ballot_sync(TPS_FULL, tps_byte_is_acgt(c) != 0) & 0xFFFFu;
+      if (lane == src) v = m;
+    }
+    L0 |= (y & 0xFFFFu) << (16u * h);
+    L1 |= (y >> 16) << (16u * h);
+    LV |= v << (16u * h);
   }
   /* oriented word `lane`: positions 32*lane .. 32*lane+31 of the (reversed) slice */
   uint32_t a0, a1, av;

@@ -382,6 +382,7 @@ VARIANTS = [
     {"TPS_K1_STAGES": "2", "TPS_K1_STAGE_KB": "8", "TPS_K1_CTAS_PER_SM": "1"},
     {"TPS_K1_STAGES": "6", "TPS_K1_CTAS_PER_SM": "3"},
     {"TPS_K2_SMEM_PATH": "1"},                              # shared-memory staged K2
+    {"TPS_K2_NO_PAIRS": "1"},                               # literal-by-literal match instead of complement pairs
 ]
 
 
@@ -406,7 +407,7 @@ def test_kernel_and_stream_variants_agree(eng, monkeypatch):
     ref = None
     for env in VARIANTS:
         for k in ("TPS_K1_TMA", "TPS_SPLIT_STREAMS", "TPS_K1_STAGES", "TPS_K1_STAGE_KB", "TPS_K1_CTAS_PER_SM",
-                  "TPS_K2_SMEM_PATH"):
+                  "TPS_K2_SMEM_PATH", "TPS_K2_NO_PAIRS"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)

@@ -139,6 +139,13 @@ int build_pattern_table(const tps_params *p, TpsPatTable *pt) {
       pt->bordered_mask |= 1ull << i;
     }
   }
+  /* second half = base-wise complements of the first half (code ^ 2: same plane 0, inverted plane 1)? */
+  pt->paired = p->n_patterns >= 2 && p->n_patterns % 2 == 0 && !getenv("TPS_K2_NO_PAIRS");
+  const uint32_t half = p->n_patterns / 2;
+  for (uint32_t i = 0; pt->paired && i < half; ++i) {
+    const uint32_t k = pt->len[i], km = k >= 32 ? 0xFFFFFFFFu : ((1u << k) - 1u);
+    if (pt->len[i + half] != k || pt->lo[i + half] != pt->lo[i] || pt->hi[i + half] != ((~pt->hi[i]) & km)) pt->paired = 0;
+  }
   return TPS_OK;
 }
 

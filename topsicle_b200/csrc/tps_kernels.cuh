@@ -34,6 +34,9 @@ struct TpsPatTable {
   uint32_t n;
   uint32_t n_bordered;
   uint64_t bordered_mask; /* bit p = literal p overlaps itself */
+  uint32_t paired;        /* n even and literal p + n/2 is the base-wise complement of literal p (what
+                             patterns_to_search builds, allsteps.py:104-120): code ^ 2, i.e. the same plane-0
+                             bits and inverted plane-1 bits, so the two share half of the match */
 };
 
 struct TpsPacked {
@@ -414,6 +417,25 @@ __device__ __forceinline__ uint32_t tps_win_match(const TpsWin<K> &w, const uint
   }
 }
 
+/* Match words of literal p and of its complement p + n/2 (TpsPatTable.paired): the plane-0 comparison is
+ * shared, the plane-1 comparison of the complement is the inverted one -- 14 LOP3 for the pair instead of 18. */
+template <int K>
+__device__ __forceinline__ void tps_win_match_pair(const TpsWin<K> &w, const uint2 *pm, uint32_t p, uint32_t &M,
+                                                   uint32_t &Mc) {
+  static_assert(K > 0, "paired matching needs a common literal length");
+  const uint2 *c = pm + p * K;
+  uint32_t tx = 0u, ty = 0u, tyc = 0u;
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    const uint2 m = c[j];
+    tx |= w.X[j] ^ m.x;
+    ty |= w.Y[j] ^ m.y;
+    tyc |= ~(w.Y[j] ^ m.y);
+  }
+  M = w.V & ~tx & ~ty;
+  Mc = w.V & ~tx & ~tyc;
+}
+
 /* ------------------------------------------------------------------------------------ K2 */
 #define TPS_K2_WARPS 4
 
@@ -616,11 +638,28 @@ __device__ __forceinline__ void tps_trc_end_reg(const TpsScanArgs &a, const TpsP
   tps_win_init<K>(win, a0, b0, a1, b1, av, bv);
   const uint32_t nq = (n + 31u) >> 5;
   uint32_t mine = 0u; /* count of literal `lane` */
+  bool done = false;
+  if constexpr (K > 0) {
+    if (pt.paired) { /* literal p and its complement p + U together: shared plane-0 compare, one REDUX for both */
+      const uint32_t U = pt.n >> 1;
+#pragma unroll 2
+      for (uint32_t p = 0; p < U; ++p) {
+        uint32_t M, Mc;
+        tps_win_match_pair<K>(win, pm, p, M, Mc);
+        const uint32_t c = __reduce_add_sync(TPS_FULL, tps_popc32(M) | (tps_popc32(Mc) << 16));
+        if (lane == p) mine = c & 0xFFFFu;
+        if (lane == p + U) mine = c >> 16;
+      }
+      done = true;
+    }
+  }
+  if (!done) {
 #pragma unroll 4
-  for (uint32_t p = 0; p < pt.n; ++p) { /* branch-free: occurrences of every literal */
-    const uint32_t M = tps_win_match<K>(win, pm, pt, p);
-    const uint32_t c = __reduce_add_sync(TPS_FULL, tps_popc32(M));
-    if (lane == p) mine = c;
+    for (uint32_t p = 0; p < pt.n; ++p) { /* branch-free: occurrences of every literal */
+      const uint32_t M = tps_win_match<K>(win, pm, pt, p);
+      const uint32_t c = __reduce_add_sync(TPS_FULL, tps_popc32(M));
+      if (lane == p) mine = c;
+    }
   }
   if (pt.n_bordered) { /* self-overlapping literals: occurrences != greedy count, redo those exactly */
     for (uint64_t bm = pt.bordered_mask; bm; bm &= bm - 1) {

@@ -153,6 +153,8 @@ def harvest(cfg: ScanConfig, ctx, batch, rows, raw, want_records: bool, keep=Non
     cols = [sel[f].tolist() for f in ("match_count", "best_pattern", "tail", "status", "n_windows", "telo_length",
                                       "length")]
     ratio = cfg.no_bp / cfg.len_telopattern            # allsteps.py:178
+    if cfg.want_rawcount and tables is None and raw is not None:
+        raw = np.array(raw, copy=True)     # ONE copy out of the context's landing buffer; the tables are views of it
     for i, cnt, bp, tl, st, nw, telo, length in zip(idx.tolist(), *cols):
         rid = batch.read_id(i)
         if keep is not None and rid not in keep:
@@ -163,8 +165,7 @@ def harvest(cfg: ScanConfig, ctx, batch, rows, raw, want_records: bool, keep=Non
         if cfg.want_rawcount and tables is not None:
             pr.counts = tables.get(i)
         elif cfg.want_rawcount and raw is not None:
-            tab = ctx.rawcount_table(rows, raw, i)
-            pr.counts = None if tab is None else tab.copy()
+            pr.counts = ctx.rawcount_table(rows, raw, i)
         if want_records:
             pr.record = batch.record_text(i)
         out.append(pr)
@@ -262,9 +263,9 @@ class _DeviceWorker:
             for f in ("status", "n_windows", "bkp", "telo_length"):
                 rows[f][used] = rows2[f][:n]
             if cfg.want_rawcount and raw2 is not None:
+                raw2 = np.array(raw2, copy=True)     # one copy out of the landing buffer, tables are views
                 for j, i in enumerate(used):
-                    tab = ctx.rawcount_table(rows2, raw2, j)
-                    tables[i] = None if tab is None else tab.copy()
+                    tables[i] = ctx.rawcount_table(rows2, raw2, j)
 
     def finish_ends(self, item, records_cfg, keep):
         slot, batch, bid, seq = item

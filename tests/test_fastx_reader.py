@@ -281,3 +281,25 @@ def test_bgzf_blocks_inflated_in_parallel(tmp_path, threads):
         with fastx.FastxFile(bad, threads=threads) as fx:
             while fx.next_batch(bases, offsets) is not None:
                 pass
+
+
+def test_record_text_fast_path_equals_general_form(tmp_path):
+    """record_text slices the raw text when the record already has SeqIO.write's shape, and rebuilds it when the
+    '+' line repeats the title, the title has trailing blanks or the lines end in CRLF."""
+    recs = [("r1 desc", "ACGTNNacgt", "IIIIIIIIII"), ("r2", "TTAGGG" * 5, "#" * 30), ("r3  ", "AC", "!!")]
+    variants = {
+        "plain": "".join(f"@{t}\n{s}\n+\n{q}\n" for t, s, q in recs),
+        "plus_title": "".join(f"@{t}\n{s}\n+{t}\n{q}\n" for t, s, q in recs),
+        "crlf": "".join(f"@{t}\r\n{s}\r\n+\r\n{q}\r\n" for t, s, q in recs),
+        "no_final_newline": "".join(f"@{t}\n{s}\n+\n{q}\n" for t, s, q in recs)[:-1],
+    }
+    want = ["@{}\n{}\n+\n{}\n".format(t.rstrip(), s, q).encode() for t, s, q in recs]
+    for name, text in variants.items():
+        path = str(tmp_path / f"{name}.fastq")
+        open(path, "w", newline="").write(text)
+        bases, offsets = np.empty(4096, np.uint8), np.empty(16, np.uint64)
+        with fastx.FastxFile(path, threads=1) as fx:
+            b = fx.next_batch(bases, offsets)
+            got = [b.record_text(i) for i in range(b.n_reads)]
+            b.release()
+        assert got == want, name

@@ -127,7 +127,13 @@ class Batch:
     def record_text(self, i) -> bytes:
         """The record as `SeqIO.write(record, handle, fmt)` emits it (main.py:86): FASTQ
         `@title\\nseq\\n+\\nqual\\n`; FASTA `>title\\n` + sequence wrapped at 60 columns."""
-        title = self._text(self.recs[i]["title_off"], self.recs[i]["title_len"])
+        title_off, seq_off, qual_off, title_len, _, _, seq_len, seq_raw_len, flags = self.recs[i].item()
+        if (self.format == FASTQ and not (flags & 1) and seq_raw_len == seq_len
+                and seq_off == title_off + title_len + 1 and qual_off == seq_off + seq_len + 3):
+            # the record already has SeqIO.write's shape in the file (bare '+' line, nothing stripped):
+            # one slice of the raw text instead of four copies
+            return self._text(title_off - 1, qual_off + seq_len - title_off + 1) + b"\n"
+        title = self._text(title_off, title_len)
         seq = self.sequence(i)
         if self.format == FASTQ:
             return b"@" + title + b"\n" + seq + b"\n+\n" + self.quality(i) + b"\n"

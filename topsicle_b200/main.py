@@ -256,6 +256,7 @@ def analysis_run(args):
                                max_batch_reads=int(os.environ.get("TOPSICLE_BATCH_READS", 1 << 17)),
                                ends_first=bool(getattr(args, "ends_first", False)
                                                or os.environ.get("TOPSICLE_ENDS_FIRST", "0") not in ("", "0")))
+    t_created = time.time()
     writers = []
     try:
         if args.read_check:
@@ -270,6 +271,7 @@ def analysis_run(args):
         for st in scanner.scan_files(jobs):
             total_bases += st.n_bases
             total_reads += st.n_reads
+        t_scanned = time.time()
         for w in writers:
             for k, telo_phrase in enumerate(telo_phrases):
                 for telolen, trc_val in w.results[k]:
@@ -281,6 +283,9 @@ def analysis_run(args):
         for w in writers:
             w.close()
         scanner.close()
+    if os.environ.get("TOPSICLE_TIMING"):
+        print(f"[timing] contexts + pinned staging {t_created - t0:.3f} s, scan {t_scanned - t_created:.3f} s, "
+              f"teardown {time.time() - t_scanned:.3f} s", file=sys.stderr)
     # the CSV is phrase-major (the reference's outer loop is over telo_phrases, main.py:206-235): rows of
     # the first phrase were appended as they were found, those of the other phrases follow here
     with open(output_csv, mode="a", newline="") as file:

@@ -177,7 +177,7 @@ class _DeviceWorker:
     packs each batch; the others scan the same device-resident batch (tps_submit_shared)."""
 
     def __init__(self, device, cfgs, max_batch_reads, max_batch_bases, depth, max_pass_reads, rawcount_capacity,
-                 context_factory, ends_first=False):
+                 context_factory, ends_first=False, ends_raw_bytes=1 << 28):
         self.device = device
         self.cfgs = cfgs
         self.max_batch_reads = max_batch_reads
@@ -189,23 +189,74 @@ class _DeviceWorker:
         if ends_first:
             longest = max(max(1, c.maxlengthtelo) for c in cfgs)
             self.region_cap = int(min(max_batch_bases, max(1 << 20, max_pass_reads * longest)))
-        for k, c in enumerate(cfgs):
-            # followers never upload whole batches: they need no base / code buffers beyond the region batches
-            self.ctxs.append(context_factory(c, device, max_batch_reads,
-                                             max_batch_bases if k == 0 else max(1, self.region_cap), depth,
-                                             max_pass_reads, rawcount_capacity if c.want_rawcount else 0))
-        self.reg = None
-        with numa.near_device(device):      # pinned staging on the GPU's own NUMA node
-            self.slots = [_Slot(max_batch_bases, max_batch_reads) for _ in range(depth)]
-            if ends_first:
-                self.reg = _Slot(self.region_cap, max_pass_reads)
-                self.reg_tails = engine.PinnedBuffer(max_pass_reads)
+        # page-locking the batch slots is slow (about 1.4 GB/s on a cloud VM: 0.5 s for 3 x 256 MiB, more than
+        # scanning a 10 GB file takes), so a helper thread does it while the contexts are created and the
+        # first batches are parsed; the scan takes the slots as they appear
+        self.depth = depth
+        self.slot_bases = max_batch_bases
+        if ends_first:      # head + tail of a batch's reads never exceed half of its file text
+            self.slot_bases = int(min(max_batch_bases, max(1 << 20, ends_raw_bytes // 2 + (1 << 20))))
+            self.region_cap = int(min(self.region_cap, 64 << 20))
+        self.slots = []
+        self._slot_cv = threading.Condition()
+        self._slot_error = None
+        self._slot_thread = threading.Thread(target=self._alloc_slots, name=f"tps-pin{device}", daemon=True)
+        self._slot_thread.start()
+        t0 = time.perf_counter()
+        try:
+            for k, c in enumerate(cfgs):
+                # followers never upload whole batches: they need no base / code buffers beyond the region batches
+                self.ctxs.append(context_factory(c, device, max_batch_reads,
+                                                 max_batch_bases if k == 0 else max(1, self.region_cap), depth,
+                                                 max_pass_reads, rawcount_capacity if c.want_rawcount else 0))
+        except BaseException:
+            self._slot_thread.join()
+            raise
+        self.reg = None                      # ends-first: region staging, page-locked at its first use
+        if os.environ.get("TOPSICLE_TIMING"):
+            print(f"[timing] device {device}: {len(cfgs)} context(s) {time.perf_counter() - t0:.3f} s",
+                  file=sys.stderr)
+
+    def _alloc_slots(self):
+        try:
+            t0 = time.perf_counter()
+            with numa.near_device(self.device):      # pinned staging on the GPU's own NUMA node
+                for _ in range(self.depth):
+                    s = _Slot(self.slot_bases, self.max_batch_reads)
+                    with self._slot_cv:
+                        self.slots.append(s)
+                        self._slot_cv.notify_all()
+            if os.environ.get("TOPSICLE_TIMING"):
+                print(f"[timing] device {self.device}: {self.depth} pinned slots of {self.slot_bases >> 20} MiB in "
+                      f"{time.perf_counter() - t0:.3f} s (background)", file=sys.stderr)
+        except BaseException as e:  # noqa: BLE001 - handed to whoever waits for a slot
+            with self._slot_cv:
+                self._slot_error = e
+                self._slot_cv.notify_all()
+
+    def slot(self, i):
+        """Slot i, waiting for the helper thread to page-lock it if need be."""
+        with self._slot_cv:
+            while len(self.slots) <= i and self._slot_error is None:
+                self._slot_cv.wait()
+            if len(self.slots) <= i:
+                raise self._slot_error
+            return self.slots[i]
+
+    def _region_staging(self):
+        if self.reg is None:
+            with numa.near_device(self.device):
+                self.reg = _Slot(self.region_cap, self.max_pass_reads)
+                self.reg_tails = engine.PinnedBuffer(self.max_pass_reads)
+        return self.reg
 
     def close(self):
+        self._slot_thread.join()
         for c in self.ctxs:
             c.close()
         for s in self.slots:
             s.free()
+        self.slots = []
         if self.reg is not None:
             self.reg.free()
             self.reg_tails.free()
@@ -226,7 +277,7 @@ class _DeviceWorker:
         telo_length into `rows`; raw-count tables go to `tables[i]`.  Groups are cut to the context's
         capacities and halved again if the raw-count buffer overflows."""
         cfg, ctx = self.cfgs[ci], self.ctxs[ci]
-        reg = self.reg
+        reg = self._region_staging()
         rb = reg.bases.array
         rstarts = reg.offsets.array.view(np.uint64)
         rlens = reg.lens.array.view(np.uint32)
@@ -386,14 +437,31 @@ class Scanner:
         self.cfgs = list(cfgs)
         self.threads = threads
         self.workers = []
-        try:
-            for d in devices:
-                self.workers.append(_DeviceWorker(d, self.cfgs, max_batch_reads, max_batch_bases, depth,
-                                                  max_pass_reads, rawcount_capacity, context_factory,
-                                                  ends_first=self.ends_first))
-        except BaseException:
+        devices = list(devices)
+        made = [None] * len(devices)
+        failed = []
+
+        def make(i, d):      # CUDA context creation + device allocations take ~0.4 s per GPU: all devices at once
+            try:
+                made[i] = _DeviceWorker(d, self.cfgs, max_batch_reads, max_batch_bases, depth, max_pass_reads,
+                                        rawcount_capacity, context_factory, ends_first=self.ends_first,
+                                        ends_raw_bytes=self.ends_raw_bytes)
+            except BaseException as e:  # noqa: BLE001 - re-raised below
+                failed.append(e)
+
+        if len(devices) > 1:
+            ts = [threading.Thread(target=make, args=(i, d), name=f"tps-init{d}") for i, d in enumerate(devices)]
+            for t in ts:
+                t.start()
+            for t in ts:
+                t.join()
+        else:
+            for i, d in enumerate(devices):
+                make(i, d)
+        self.workers = [w for w in made if w is not None]
+        if failed:
             self.close()
-            raise
+            raise failed[0]
 
     def close(self):
         for w in self.workers:
@@ -434,9 +502,17 @@ class Scanner:
         errors = []
         ready = queue.Queue()
         free = queue.Queue()
-        for w in self.workers:
-            for slot in w.slots:
-                free.put(slot)
+        def feed_slots():        # slots reach the readers as the helper threads finish page-locking them
+            try:
+                for i in range(max(w.depth for w in self.workers)):
+                    for w in self.workers:
+                        if i < w.depth:
+                            free.put(w.slot(i))
+            except BaseException as e:  # noqa: BLE001
+                errors.append(e)
+                free.put(None)
+
+        feeder = threading.Thread(target=feed_slots, name="tps-slots")
         w0 = self.workers[0]
         todo = queue.Queue()
         for j in jobs:
@@ -511,7 +587,7 @@ class Scanner:
 
         def work_loop(w: _DeviceWorker):
             inflight = []
-            depth = len(w.slots)
+            depth = w.depth
 
             def finish_oldest():
                 job, item = inflight.pop(0)
@@ -549,7 +625,7 @@ class Scanner:
         rthreads = [threading.Thread(target=read_loop, name=f"tps-reader{i}") for i in range(readers)]
         wthreads = [threading.Thread(target=work_loop, args=(w,), name=f"tps-dev{w.device}") for w in self.workers]
         try:
-            for t in rthreads + wthreads:
+            for t in [feeder] + rthreads + wthreads:
                 t.start()
             for t in rthreads:
                 t.join()
@@ -557,6 +633,7 @@ class Scanner:
                 ready.put(None)
             for t in wthreads:
                 t.join()
+            feeder.join()
             if errors:
                 raise errors[0]
         finally:

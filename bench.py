@@ -23,6 +23,9 @@ import time
 REPO = os.path.dirname(os.path.abspath(__file__))
 if REPO not in sys.path:
     sys.path.insert(0, REPO)
+# before anything loads libgomp (torch does): the FASTQ parser's OpenMP team shares the host cores with the
+# Python threads and the other ranks, so idle team members sleep instead of spinning
+os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
 
 import numpy as np  # noqa: E402
 

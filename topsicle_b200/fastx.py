@@ -41,6 +41,9 @@ def host_library() -> C.CDLL:
     if _lib is None:
         if not os.path.exists(HOST_LIB_PATH):
             raise RuntimeError(f"{HOST_LIB_PATH} not found: run __graft_entry__.build()")
+        # the parser's OpenMP team shares the cores with the Python reader / worker threads (and, under
+        # torchrun, with the other ranks): idle team members must sleep, not spin (read by libgomp when it loads)
+        os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
         lib = C.CDLL(HOST_LIB_PATH)
         vp = C.c_void_p
         lib.tps_fastx_open.restype = C.c_int

@@ -120,7 +120,8 @@ def patternTRC_count(filepath, telopattern, read_length=0, kmer=4, no_bp=1000, c
         return []
     cfg = pipeline.ScanConfig(patterns=literals, len_telopattern=len(telopattern), phrase=kmer, cutoff=cutoff,
                               min_seq_length=read_length, no_bp=no_bp, step1_only=True)
-    _, per_cfg = pipeline.collect_file(filepath, [cfg], devices=_devices())
+    # step 1 reads nothing but the first / last `no_bp` bases of a read: the ends-first reader uploads just those
+    _, per_cfg = pipeline.collect_file(filepath, [cfg], devices=_devices(), ends_first=True)
     return [[p.read_id, p.literal, p.tail, p.trc] for p in per_cfg[0]]
 
 

@@ -303,3 +303,49 @@ def test_record_text_fast_path_equals_general_form(tmp_path):
             got = [b.record_text(i) for i in range(b.n_reads)]
             b.release()
         assert got == want, name
+
+
+def test_next_ends_on_awkward_fastq(tmp_path):
+    """The ends-first reader on the same awkward input (CRLF, blank lines, trailing blanks, a record larger than
+    the batch's text window, no final newline): ends, real lengths, full sequences and regions, for several
+    thread counts, window sizes and tiny read / base capacities; plain and gzip."""
+    rng = np.random.default_rng(23)
+    p = tmp_path / "awk.fastq"
+    want = []
+    with open(p, "wb") as fh:
+        for i in range(1200):
+            L = int(rng.integers(0, 3000)) if i != 500 else 300000
+            seq = bytes(rng.choice(np.frombuffer(b"ACGTNacgt", np.uint8), L))
+            qual = bytes(rng.choice(np.frombuffer(b"@+I!5", np.uint8), L))
+            eol = b"\r\n" if i % 7 == 0 else b"\n"
+            pad = b"      " if i % 97 == 0 else b""
+            fh.write(b"@r%d some text%s%s%s%s+%s%s%s" % (i, eol, seq, pad, eol, eol, qual, eol if i < 1199 else b""))
+            if i % 50 == 0:
+                fh.write(b"\n")
+            want.append((f"r{i}", seq))
+    gz = tmp_path / "awk.fastq.gz"
+    with open(p, "rb") as src, gzip.open(gz, "wb", compresslevel=1) as dst:
+        dst.write(src.read())
+    H = 400
+    for path, threads, raw_cap, max_reads, max_bases in [(p, 1, 1 << 30, 4096, 1 << 22), (p, 8, 200_000, 4096, 1 << 22),
+                                                        (p, 3, 50_000, 7, 1 << 22), (p, 4, 1 << 20, 4096, 3000),
+                                                        (gz, 4, 300_000, 100, 1 << 22)]:
+        bases = np.empty(1 << 22, np.uint8)
+        starts, lens, tl = np.empty(4096, np.uint64), np.empty(4096, np.uint32), np.empty(4096, np.uint32)
+        got = []
+        with fastx.FastxFile(str(path), threads=threads) as fx:
+            while True:
+                b = fx.next_ends(bases, starts, lens, tl, H, raw_cap=raw_cap, max_reads=max_reads, max_bases=max_bases)
+                if b is None:
+                    break
+                assert b.n_reads <= max_reads and b.span <= max_bases
+                for i in range(b.n_reads):
+                    a = int(starts[i])
+                    got.append((b.read_id(i), int(tl[i]), bases[a:a + int(lens[i])].tobytes(), b.sequence(i),
+                                b.region(i, 0, 1000), b.region(i, 1, 1000)))
+                b.release()
+        assert len(got) == len(want), (threads, raw_cap)
+        for (rid, s), g in zip(want, got):
+            assert g[0] == rid and g[1] == len(s), rid
+            assert g[2] == (s if len(s) <= 2 * H else s[:H] + s[-H:]), rid
+            assert g[3] == s and g[4] == s[:1000] and g[5] == s[-1000:], rid

@@ -361,13 +361,13 @@ int tps_create(tps_ctx **out, int device, const tps_params *params) {
     ctx->k1_tma = !(e && atoi(e) == 0);
     if (ctx->k1_tma) {
       const char *se = getenv("TPS_K1_STAGES");
-      int stages = se ? atoi(se) : 4;
+      int stages = se ? atoi(se) : 2;
       if (stages < 2) stages = 2;
       if (stages > 12) stages = 12;
       ctx->k1t_stages = (uint32_t)stages;
       if (const char *ke = getenv("TPS_K1_STAGE_KB")) ctx->k1t_unroll = atoi(ke) <= 8 ? 2u : 4u;
       ctx->k1t_smem = ctx->k1t_stages * (TPS_K1T_STAGE_BYTES(ctx->k1t_unroll) + 16u);
-      int want_per_sm = 2; /* 2 CTAs x 4 stages x 16 KiB in flight per SM measured best (profiles/README.md) */
+      int want_per_sm = 3; /* 3 CTAs x 2 stages x 16 KiB = 96 KiB in flight per SM measured best (profiles/README.md) */
       if (const char *ce = getenv("TPS_K1_CTAS_PER_SM")) want_per_sm = atoi(ce);
       if (want_per_sm < 1) want_per_sm = 1;
       if (want_per_sm > 6) want_per_sm = 6;

@@ -169,8 +169,10 @@ int tps_wait(tps_ctx *ctx, uint64_t batch_id, tps_row *rows_out, uint32_t *n_pas
  * *rawcount_elems = count elements the batch produced. */
 int tps_batch_info(tps_ctx *ctx, uint64_t batch_id, uint32_t *n_pass_out, uint64_t *rawcount_elems);
 
-/* Scan a batch already resident in DEVICE memory (d_bases must be readable up to
- * n_bases rounded up to a multiple of 2048 bytes); rows are written to d_rows_out (device).
+/* Scan a batch already resident in DEVICE memory (d_bases must be 16-byte aligned, readable up to
+ * n_bases rounded up to a multiple of 2048 bytes, and unchanged until the scan has finished: K1 reads it
+ * through the bulk-copy engine, K2 / K3 re-read the ASCII bytes of groups that hold a non-ACGT byte);
+ * rows are written to d_rows_out (device).
  * Enqueued on the context's stream 0; returns without synchronising. */
 int tps_scan_device(tps_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_offsets,
                     uint32_t n_reads, uint64_t n_bases, tps_row *d_rows_out);

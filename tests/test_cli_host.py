@@ -60,10 +60,12 @@ def test_pass_capacity_overflow_is_split_not_lost(tmp_path, monkeypatch):
                                                                       for p in big[0]]
 
 
-def test_read_check_only_that_read(tmp_path, monkeypatch):
+@pytest.mark.parametrize("ends_first", ["0", "1"])
+def test_read_check_only_that_read(tmp_path, monkeypatch, ends_first):
     """--read_check: one CSV row, but the subset file still holds every TRC-pass read (main.py:64-87
     runs before the read_check branch)."""
     fake_engine.install(monkeypatch)
+    monkeypatch.setenv("TOPSICLE_ENDS_FIRST", ends_first)
     import hashlib
     from topsicle_b200 import main as tmain
     case = golden_cases()[0]
@@ -78,10 +80,12 @@ def test_read_check_only_that_read(tmp_path, monkeypatch):
     assert sub == case["files"]["demo.fastq_trc_over_0.7.fastq"]
 
 
-def test_directory_of_files_scanned_concurrently(tmp_path, monkeypatch):
+@pytest.mark.parametrize("ends_first", ["0", "1"])
+def test_directory_of_files_scanned_concurrently(tmp_path, monkeypatch, ends_first):
     """--inputDir with several files (.fastq.gz, .fastq, .fasta): files are read concurrently, every
     file's rows stay in file order, subset files are per file with the reference's naming rule."""
     fake_engine.install(monkeypatch)
+    monkeypatch.setenv("TOPSICLE_ENDS_FIRST", ends_first)
     import gzip
     import shutil
     from oracle import topsicle_oracle as orc

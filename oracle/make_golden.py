@@ -12,6 +12,7 @@ Outputs (committed, small):
   tests/golden/demo_cli.json          CLI known answers (CSV text, md5s, log summary lines)
   tests/golden/demo_step1.json        patternTRC_count rows for every read (cutoff -1)
   tests/golden/demo_rawcount.npz      rawCountPattern count tables for a few demo reads
+  tests/golden/demo_heatmap.json      patterns_vs_match_heatmap CSV md5s (overview_plot.py --recfindingpattern --rawcount)
   tests/golden/edge.fastq / edge.fasta   crafted edge-case reads
   tests/golden/edge.json              reference function outputs on them
 
@@ -164,6 +165,52 @@ def demo_rawcount():
 
 
 # ------------------------------------------------------------------ crafted edge-case reads
+def demo_heatmap():
+    """`patterns_vs_match_heatmap(...).to_csv(index=False)` of the unmodified reference (descriptive_plot.py:233-313,
+    overview_plot.py:98-108).  The first case is the reference's own golden
+    Topsicle_demo/result_justone/heatmap_rawcount_1.csv: the reads of the demo with TRC > 0.7 (phrase 5)."""
+    import contextlib
+    import importlib
+    import io
+    importlib.import_module("Topsicle.descriptive_plot")
+    dp = sys.modules["Topsicle.descriptive_plot"]
+    from Topsicle.allsteps import patternTRC_count
+    from Bio import SeqIO
+    import gzip
+    gold_md5 = md5(os.path.join(REF, "Topsicle_demo", "result_justone", "heatmap_rawcount_1.csv"))
+    out = []
+    edge_fq = os.path.join(GOLD, "edge.fastq")
+    cases = [("CCCTAAA", 5, 9000, "subset", DEMO_IN), ("CCCTAA", 4, 9000, "all", DEMO_IN),
+             ("CCCTAA", 6, 9000, "all", DEMO_IN), ("AAACCCT", 4, 20000, "all", DEMO_IN),
+             ("TTTAGGG", 6, 0, "all", DEMO_IN), ("CCCTAA", 4, 0, "all", edge_fq), ("CCCTAAA", 5, 150, "all", edge_fq)]
+    for pat, k, minlen, mode, src in cases:
+        path = src
+        tmp = None
+        if mode == "subset":      # overview_plot.py:63-84: reads with TRC > 0.7 written to a temp file first
+            with contextlib.redirect_stdout(io.StringIO()):
+                keep = {r[0] for r in patternTRC_count(src, telopattern=pat, read_length=minlen, kmer=k, no_bp=1000,
+                                                       cutoff=0.7)}
+            tmp = tempfile.mktemp(suffix=".fastq")
+            with gzip.open(src, "rt") as ih, open(tmp, "w") as oh:
+                for rec in SeqIO.parse(ih, "fastq"):
+                    if rec.id in keep:
+                        SeqIO.write(rec, oh, "fastq")
+            path = tmp
+        with contextlib.redirect_stdout(io.StringIO()):
+            df = dp.patterns_vs_match_heatmap(path, pat, k, minlen)
+        txt = df.to_csv(index=False)
+        if tmp:
+            os.remove(tmp)
+        e = dict(pattern=pat, telophrase=k, minSeqLength=minlen, input=os.path.basename(src), mode=mode,
+                 rows=len(df), md5=hashlib.md5(txt.encode()).hexdigest())
+        if mode == "subset":
+            assert e["md5"] == gold_md5 == "28ad064f247aa236af6f0fedddc63ed4", e
+            e["reference_golden"] = "Topsicle_demo/result_justone/heatmap_rawcount_1.csv"
+        out.append(e)
+        print(f"  heatmap {pat} k={k} {e['input']} {mode}: {e['rows']} rows, md5 {e['md5']}")
+    return out
+
+
 def build_edge_reads():
     rng = np.random.default_rng(20261017)
     B = np.array(list("ACGT"))
@@ -281,6 +328,9 @@ def edge_cases(fastq_path, fasta_path):
 
 def main():
     os.makedirs(GOLD, exist_ok=True)
+    if "--heatmap" in sys.argv:      # only the overview heat-map fixtures (the others are left as committed)
+        json.dump(demo_heatmap(), open(os.path.join(GOLD, "demo_heatmap.json"), "w"), indent=1)
+        return
     print("[1] reference golden check")
     ref_check = check_reference_golden()
     shutil.copy(DEMO_IN, os.path.join(GOLD, "demo.fastq.gz"))
@@ -307,6 +357,8 @@ def main():
             for i in range(0, len(s), 70):
                 f.write(s[i:i + 70] + "\n")
     json.dump(edge_cases(fq, fa), open(os.path.join(GOLD, "edge.json"), "w"), indent=0)
+    print("[6] overview heat map")
+    json.dump(demo_heatmap(), open(os.path.join(GOLD, "demo_heatmap.json"), "w"), indent=1)
     print("done")
 
 

@@ -9,5 +9,14 @@ def set_style(*a, **k):
     return None
 
 
+class _Nothing:
+    def __getattr__(self, name):
+        return lambda *a, **k: _Nothing()
+
+
+def heatmap(*a, **k):
+    return _Nothing()
+
+
 def __getattr__(name):
     return lambda *a, **k: None

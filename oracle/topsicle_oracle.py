@@ -228,6 +228,38 @@ def csv_text(file_stem: str, phrase: int, rows) -> str:
 
 
 # --------------------------------------------------------------------------- input
+# ------------------------------------------------------------------ overview heat map (descriptive_plot.py)
+def heatmap_matches(records, telopattern: str, telophrase: int, min_seq_length: int):
+    """descriptive_plot.py:233-313 `patterns_vs_match_heatmap`, the data half: for every read longer than
+    min_seq_length, every origin k-mer (NOT its complement) followed by `len(telopattern) - telophrase` more
+    characters, leftmost non-overlapping (`re.finditer(pattern(.{finding}))`), in `seq[100:2000]` and in the
+    complement of `reversed(seq)[100:2000]`.  Returns (forward_rows, reverse_rows) of (pattern, match, name)
+    in the order the reference appends them: read-major, pattern-minor, by position."""
+    pats = pattern_scramble_telo(telopattern, telophrase)
+    finding = int(len(telopattern) - telophrase)
+    trans = str.maketrans("ACGT", "TGCA")
+    fwd, rev = [], []
+    for name, seq in records:
+        if not len(seq) > min_seq_length:
+            continue
+        s1 = seq[100:2000].upper()
+        s2 = seq[::-1][100:2000].upper().translate(trans)
+        for pat in pats:
+            rx = re.compile(rf"{re.escape(pat)}(.{{{finding}}})")
+            fwd += [(pat, m.group(1), name) for m in rx.finditer(s1)]
+            rev += [(pat, m.group(1), name) for m in rx.finditer(s2)]
+    return fwd, rev
+
+
+def heatmap_csv_text(fwd, rev) -> str:
+    """`allstrands.to_csv(index=False)` of the reference (overview_plot.py:104-108): forward rows, then reverse
+    rows; the read id column holds a one-element list."""
+    out = ["Pattern,Match,read id\n"]
+    for pat, match, name in list(fwd) + list(rev):
+        out.append(f"{pat},{match},['{name}']\n")
+    return "".join(out)
+
+
 def read_fastx(path: str):
     """allsteps.py:36-50,127-149 -- (id, seq) records; id = title up to first whitespace.
 

@@ -142,3 +142,20 @@ def test_demo_cli_csv(demo_records, exact):
         text = body[0] + "".join(b.split("\r\n", 1)[1] for b in body[1:])
         assert text == case["csv"], case["name"]
         assert hashlib.md5(text.encode()).hexdigest() == case["csv_md5"]
+
+
+def test_heatmap_oracle_matches_reference_csv():
+    """oracle.heatmap_matches / heatmap_csv_text == `patterns_vs_match_heatmap(...).to_csv(index=False)` of the
+    unmodified reference, including its own golden Topsicle_demo/result_justone/heatmap_rawcount_1.csv."""
+    import hashlib
+    for case in load_json("demo_heatmap.json"):
+        src = "demo.fastq.gz" if case["input"].endswith(".gz") else case["input"]
+        recs = list(orc.read_fastx(os.path.join(GOLD, src)))
+        if case["mode"] == "subset":       # overview_plot.py:63-84
+            keep = {r[0] for r in orc.pattern_trc_count(recs, case["pattern"], read_length=case["minSeqLength"],
+                                                        kmer=case["telophrase"], no_bp=1000, cutoff=0.7)}
+            recs = [(i, s) for i, s in recs if i in keep]
+        fwd, rev = orc.heatmap_matches(recs, case["pattern"], case["telophrase"], case["minSeqLength"])
+        txt = orc.heatmap_csv_text(fwd, rev)
+        assert len(fwd) + len(rev) == case["rows"], case
+        assert hashlib.md5(txt.encode()).hexdigest() == case["md5"], case

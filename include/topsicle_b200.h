@@ -195,6 +195,19 @@ int tps_get_timeline(tps_ctx *ctx, uint32_t back, uint32_t base_back, float ms[T
 /* Number of kernels this context has launched so far. */
 uint64_t tps_kernel_launches(const tps_ctx *ctx);
 
+/* Overview heat map (the `next` row f4 of SURVEY 8): the data half of
+ * Topsicle/descriptive_plot.py:233-313 `patterns_vs_match_heatmap`, i.e. what `overview_plot.py
+ * --recfindingpattern --rawcount` writes to heatmap_rawcount_{i}.csv.  For every read longer than
+ * min_seq_length and every k-mer of `patterns` (n_patterns x k upper-case ACGT characters, the ORIGIN k-mers of
+ * pattern_scramble_telo, no complements): the leftmost non-overlapping matches of `kmer(.{match_len - k})` in
+ * `seq[skip:upto]` (strand 0) and in the complement of `reversed(seq)[skip:upto]` (strand 1).
+ * sel_out[((read * 2 + strand) * n_patterns + p) * W + w], W = ceil((upto - skip) / 32): bit b of word w set
+ * <=> a match starts at position 32 w + b of that slice.  Synchronous, stateless (own buffers, K1 + one
+ * warp per (read, strand)); reads are back to back in `bases` as for tps_submit.  Errors: tps_last_error(NULL). */
+int tps_follow_scan(int device, const uint8_t *bases, const uint64_t *offsets, uint32_t n_reads, const char *patterns,
+                    uint32_t n_patterns, uint32_t k, uint32_t match_len, uint32_t min_seq_length, uint32_t skip,
+                    uint32_t upto, uint32_t *sel_out, uint64_t sel_words);
+
 /* Test hooks: copy internal device arrays of slot 0 to the host after a scan.
  * what: 0 = 2-bit code words (uint32 per 16 bases), 1 = invalid-group flag words
  * (uint32 per 512 bases), 2 = validity masks as K2/K3 see them (uint16 per 16 bases: 0xFFFF for an

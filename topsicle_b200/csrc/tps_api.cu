@@ -758,6 +758,102 @@ int tps_get_timeline(tps_ctx *ctx, uint32_t back, uint32_t base_back, float ms[T
   return TPS_OK;
 }
 
+int tps_follow_scan(int device, const uint8_t *bases, const uint64_t *offsets, uint32_t n_reads, const char *patterns,
+                    uint32_t n_patterns, uint32_t k, uint32_t match_len, uint32_t min_seq_length, uint32_t skip,
+                    uint32_t upto, uint32_t *sel_out, uint64_t sel_words) {
+  if (!offsets || !patterns || !sel_out || (!bases && n_reads)) return fail(nullptr, TPS_EINVAL, "null argument");
+  if (n_patterns < 1 || n_patterns > 16) return fail(nullptr, TPS_EINVAL, "the follower scan takes 1..16 k-mers");
+  if (k < 1 || k > 8) return fail(nullptr, TPS_EINVAL, "the follower scan takes k-mers of 1..8 bases");
+  if (match_len < k || match_len > 64) return fail(nullptr, TPS_EINVAL, "match_len must be in k..64");
+  if (upto <= skip || upto - skip > 65536) return fail(nullptr, TPS_EINVAL, "need skip < upto <= skip + 65536");
+  if (offsets[0] != 0) return fail(nullptr, TPS_EINVAL, "offsets[0] must be 0");
+  const uint32_t wpr = (upto - skip + 31) / 32;
+  if (sel_words < (uint64_t)n_reads * 2 * n_patterns * wpr)
+    return fail(nullptr, TPS_ECAPACITY, "sel_out holds %llu words, %llu needed", (unsigned long long)sel_words,
+                (unsigned long long)((uint64_t)n_reads * 2 * n_patterns * wpr));
+  if (n_reads == 0) return TPS_OK;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(nullptr, TPS_ENODEVICE, "no CUDA device visible; topsicle_b200 has no CPU fallback");
+  }
+  if (device < 0 || device >= ndev) return fail(nullptr, TPS_EINVAL, "device %d out of range (0..%d)", device, ndev - 1);
+  tps_params pp;
+  memset(&pp, 0, sizeof(pp));
+  pp.n_patterns = n_patterns;
+  for (uint32_t i = 0; i < n_patterns; ++i) {
+    pp.pattern_len[i] = (uint8_t)k;
+    memcpy(pp.patterns[i], patterns + (size_t)i * k, k);
+  }
+  TpsPatTable pt;
+  int rc = build_pattern_table(&pp, &pt);
+  if (rc) return rc;
+  const uint64_t n_bases = offsets[n_reads];
+  const uint64_t n_tiles = (n_bases + 511) / 512;
+  const uint64_t cap_pad = ((n_bases + 2047) / 2048) * 2048 + 2048;
+  uint8_t *d_bases = nullptr;
+  uint32_t *d_codes = nullptr, *d_flags = nullptr, *d_sel = nullptr;
+  uint64_t *d_off = nullptr;
+  const uint64_t sel_bytes = (uint64_t)n_reads * 2 * n_patterns * wpr * sizeof(uint32_t);
+  cudaError_t e = cudaSetDevice(device);
+  if (e == cudaSuccess) e = cudaMalloc(&d_bases, cap_pad);
+  if (e == cudaSuccess) e = cudaMemset(d_bases, 'N', cap_pad);
+  if (e == cudaSuccess) e = cudaMalloc(&d_codes, (n_tiles + 1) * 32 * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&d_flags, (n_tiles + 4) * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&d_off, ((uint64_t)n_reads + 1) * sizeof(uint64_t));
+  if (e == cudaSuccess) e = cudaMalloc(&d_sel, sel_bytes);
+  if (e == cudaSuccess) e = cudaMemcpy(d_bases, bases, n_bases, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_off, offsets, ((uint64_t)n_reads + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && n_tiles) {
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e == cudaSuccess) {
+      const uint32_t stages = 2, smem1 = stages * (TPS_K1T_STAGE_BYTES(4) + 16u);
+      const uint64_t want = (n_tiles + TPS_K1T_STAGE_TILES(4) - 1) / TPS_K1T_STAGE_TILES(4);
+      const uint64_t cap = (uint64_t)prop.multiProcessorCount * 3;
+      tps_pack_tma_kernel<4><<<(int)(want < cap ? want : cap), TPS_K1T_THREADS, smem1>>>(
+          reinterpret_cast<const uint4 *>(d_bases), d_codes, d_flags, n_tiles, stages);
+      TpsFollowArgs a;
+      memset(&a, 0, sizeof(a));
+      a.pk.codes = d_codes;
+      a.pk.flags = d_flags;
+      a.pk.bases = d_bases;
+      a.offsets = d_off;
+      a.n_reads = n_reads;
+      a.min_seq_length = min_seq_length;
+      a.skip = skip;
+      a.upto = upto;
+      a.match_len = match_len;
+      a.lin_words = lin_words_for(upto - skip);
+      a.words_per_row = wpr;
+      a.sel = d_sel;
+      const uint32_t smem5 = (4 * n_patterns * k + TPS_K5_WARPS * (3 * a.lin_words + n_patterns * wpr)) * 4;
+      void (*fn)(const TpsFollowArgs, const TpsPatTable) = nullptr;
+      switch (k) {
+#define TPS_PICK5(KK) case KK: fn = tps_follow_kernel<KK>; break;
+        TPS_PICK5(1) TPS_PICK5(2) TPS_PICK5(3) TPS_PICK5(4) TPS_PICK5(5) TPS_PICK5(6) TPS_PICK5(7) TPS_PICK5(8)
+#undef TPS_PICK5
+      }
+      if (smem5 > (uint32_t)prop.sharedMemPerBlockOptin) {
+        e = cudaErrorInvalidValue;
+      } else {
+        if (smem5 > 48 * 1024) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5);
+        if (e == cudaSuccess) {
+          fn<<<(2 * n_reads + TPS_K5_WARPS - 1) / TPS_K5_WARPS, TPS_K5_WARPS * 32, smem5>>>(a, pt);
+          e = cudaGetLastError();
+        }
+      }
+    }
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(sel_out, d_sel, sel_bytes, cudaMemcpyDeviceToHost);
+  cudaFree(d_bases); cudaFree(d_codes); cudaFree(d_flags); cudaFree(d_off); cudaFree(d_sel);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(nullptr, e == cudaErrorMemoryAllocation ? TPS_ENOMEM : TPS_ECUDA, "tps_follow_scan: %s", cudaGetErrorString(e));
+  }
+  return TPS_OK;
+}
+
 uint64_t tps_kernel_launches(const tps_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 int tps_debug_copy(tps_ctx *ctx, int what, void *dst, size_t bytes) {

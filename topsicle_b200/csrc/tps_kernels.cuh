@@ -1052,3 +1052,97 @@ tps_changepoint_kernel(const TpsScanArgs a) {
     }
   }
 }
+
+/* ------------------------------------------------------------------------------------ K5
+ * Overview heat map (descriptive_plot.py:233-313 `patterns_vs_match_heatmap`): for every read longer than
+ * min_seq_length and every ORIGIN k-mer (no complements), the leftmost non-overlapping matches of
+ * `pattern(.{finding})` -- the k-mer followed by `finding` more characters of any kind, match length
+ * match_len = k + finding = len(telopattern) -- in `seq[skip:upto]` (strand 0) and in the complement of
+ * `reversed(seq)[skip:upto]` (strand 1: the reversed slice is matched against the complemented k-mers).
+ * One warp per (read, strand); output = one bit per selected match start, sel[read][strand][pattern][word].
+ * The host turns the bits into the reference's (Pattern, Match, read id) rows.
+ *
+ * dynamic shared memory (words): pm[2 * U * K] | pmc[2 * U * K] | per warp: lin[3 * lin_words] | rows[U * words_per_row] */
+#define TPS_K5_WARPS 4
+
+struct TpsFollowArgs {
+  TpsPacked pk;
+  const uint64_t *offsets; /* n_reads + 1 */
+  uint32_t n_reads;
+  uint32_t min_seq_length, skip, upto, match_len;
+  uint32_t lin_words, words_per_row;
+  uint32_t *sel; /* [n_reads][2][U][words_per_row] */
+};
+
+template <int K>
+__global__ void __launch_bounds__(TPS_K5_WARPS * 32)
+tps_follow_kernel(const TpsFollowArgs a, const TpsPatTable pt) {
+  static_assert(K > 0, "the follower scan needs a common k-mer length");
+  extern __shared__ __align__(16) uint32_t smem[];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  const uint32_t U = pt.n, wpr = a.words_per_row, lw = a.lin_words;
+  uint2 *pm = reinterpret_cast<uint2 *>(smem);
+  uint2 *pmc = pm + U * K;
+  tps_build_pattern_masks(pm, pt, K, threadIdx.x, TPS_K5_WARPS * 32);
+  for (uint32_t i = threadIdx.x; i < U * K; i += TPS_K5_WARPS * 32) { /* complement: code ^ 2 = plane 1 inverted */
+    const uint32_t p = i / K, j = i - p * K;
+    pmc[i] = make_uint2(0u - ((pt.lo[p] >> j) & 1u), ~(0u - ((pt.hi[p] >> j) & 1u)));
+  }
+  __syncthreads();
+  uint32_t *lin = smem + 4u * U * K + warp * (3u * lw + U * wpr);
+  uint32_t *rows = lin + 3u * lw;
+  const uint32_t idx = blockIdx.x * TPS_K5_WARPS + warp;
+  if (idx >= 2u * a.n_reads) return;
+  const uint32_t r = idx >> 1, strand = idx & 1u;
+  const uint64_t off = a.offsets[r];
+  const uint32_t L = (uint32_t)(a.offsets[r + 1] - off);
+  uint32_t *out = a.sel + ((size_t)idx * U) * wpr;
+  const uint32_t hi = L < a.upto ? L : a.upto;
+  const uint32_t n = (L > a.min_seq_length && hi > a.skip) ? hi - a.skip : 0u; /* len(seq[skip:upto]) */
+  if (n < a.match_len) { /* filtered read, or a slice too short for a single match */
+    for (uint32_t i = lane; i < U * wpr; i += 32u) out[i] = 0u;
+    return;
+  }
+  /* strand 0: read[skip, hi); strand 1: reversed read -> the slice read[L - hi, L - skip) reversed */
+  const bool rev = strand != 0u;
+  const uint64_t g0 = rev ? off + (L - hi) : off + a.skip;
+  const uint32_t phase = (uint32_t)(g0 & 15u);
+  tps_stage_linear(a.pk, g0, n, lin, lw, lane, 32u);
+  for (uint32_t i = lane; i < U * wpr; i += 32u) rows[i] = 0u;
+  __syncwarp();
+  const uint32_t nq = (n + 31u) >> 5;
+  const uint32_t last = n - a.match_len; /* last admissible match start */
+  for (uint32_t qc = 0; qc < nq; qc += 32u) {
+    const uint32_t q = qc + lane;
+    uint32_t a0, a1, av, b0, b1, bv;
+    tps_oriented_word(lin, lw, phase, n, rev, q, a0, a1, av);
+    tps_oriented_word(lin, lw, phase, n, rev, q + 1u, b0, b1, bv);
+    TpsWin<K> win;
+    tps_win_init<K>(win, a0, b0, a1, b1, av, bv);
+    if (q < nq && q < wpr) {
+      /* starts beyond `last` have no room for the `finding` characters behind the k-mer */
+      const uint32_t lim = last >= 32u * q ? last - 32u * q : 0u;
+      const uint32_t room = last < 32u * q ? 0u : (lim >= 31u ? TPS_FULL : ((2u << lim) - 1u));
+      for (uint32_t p = 0; p < U; ++p) rows[p * wpr + q] = tps_win_match<K>(win, rev ? pmc : pm, pt, p) & room;
+    }
+  }
+  __syncwarp();
+  if (lane < U) { /* leftmost non-overlapping selection, in place: a match consumes match_len positions */
+    uint32_t *row = rows + lane * wpr;
+    uint32_t pos = 0u;
+    for (uint32_t wi = 0; wi < nq && wi < wpr; ++wi) {
+      uint32_t w = row[wi], keep = 0u;
+      const uint32_t base = 32u * wi;
+      if (pos > base) w &= pos - base >= 32u ? 0u : (TPS_FULL << (pos - base));
+      while (w) {
+        const uint32_t b = (uint32_t)__ffs((int)w) - 1u;
+        keep |= 1u << b;
+        pos = base + b + a.match_len;
+        w &= pos - base >= 32u ? 0u : (TPS_FULL << (pos - base));
+      }
+      row[wi] = keep;
+    }
+  }
+  __syncwarp();
+  for (uint32_t i = lane; i < U * wpr; i += 32u) out[i] = rows[i];
+}

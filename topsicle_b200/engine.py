@@ -97,6 +97,9 @@ def load_library() -> C.CDLL:
     lib.tps_submit_ends.argtypes = [vp, vp, C.c_uint64, vp, vp, vp, C.c_uint32, C.c_uint64]
     lib.tps_submit_regions.restype = C.c_int
     lib.tps_submit_regions.argtypes = [vp, vp, C.c_uint64, vp, vp, vp, C.c_uint32, C.c_uint64]
+    lib.tps_follow_scan.restype = C.c_int
+    lib.tps_follow_scan.argtypes = [C.c_int, vp, vp, C.c_uint32, C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32,
+                                    C.c_uint32, C.c_uint32, C.c_uint32, vp, C.c_uint64]
     lib.tps_submit_shared.restype = C.c_int
     lib.tps_submit_shared.argtypes = [vp, vp, C.c_uint64]
     lib.tps_wait.restype = C.c_int
@@ -152,6 +155,29 @@ def pack_reads(seqs: Iterable) -> tuple[np.ndarray, np.ndarray]:
         offsets[1:] = np.cumsum([len(b) for b in bufs], dtype=np.uint64)
     bases = np.frombuffer(b"".join(bufs), dtype=np.uint8)
     return bases, offsets
+
+
+def follow_scan(seqs: Iterable, kmers: Sequence[str], match_len: int, min_seq_length: int, skip: int = 100,
+                upto: int = 2000, device: int = 0) -> np.ndarray:
+    """Match starts of `kmer(.{match_len - k})`, leftmost non-overlapping, in `seq[skip:upto]` (strand 0) and in the
+    complement of `reversed(seq)[skip:upto]` (strand 1) of every read longer than min_seq_length
+    (descriptive_plot.py:233-313).  Returns bool[n_reads][2][n_kmers][upto - skip]."""
+    lib = load_library()
+    bases, offsets = pack_reads(seqs)
+    n = len(offsets) - 1
+    k = len(kmers[0])
+    if any(len(m) != k for m in kmers):
+        raise ValueError("the k-mers of a follower scan share one length")
+    wpr = (upto - skip + 31) // 32
+    sel = np.zeros((n, 2, len(kmers), wpr), dtype=np.uint32)
+    if n:
+        bases = np.ascontiguousarray(bases)
+        rc = lib.tps_follow_scan(device, bases.ctypes.data, offsets.ctypes.data, n, "".join(kmers).upper().encode(),
+                                 len(kmers), k, match_len, min_seq_length, skip, upto, sel.ctypes.data, sel.size)
+        if rc != 0:
+            raise TpsError(rc, lib.tps_last_error(None).decode())
+    bits = np.unpackbits(sel.view(np.uint8), axis=-1, bitorder="little")
+    return bits[..., :upto - skip].astype(bool)
 
 
 class PinnedBuffer:

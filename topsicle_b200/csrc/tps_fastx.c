@@ -1345,3 +1345,18 @@ uint32_t tps_fastx_find_id(const uint8_t *raw_base, const tps_fastx_rec *recs, u
   }
   return found;
 }
+
+/* The ids of records idx[0..n) joined by '\n' into out (capacity cap bytes): one call instead of one string copy
+ * per TRC-pass read.  Returns the bytes written, or -1 if cap is too small. */
+int64_t tps_fastx_join_ids(const uint8_t *raw_base, const tps_fastx_rec *recs, const uint32_t *idx, uint32_t n,
+                           uint8_t *out, uint64_t cap) {
+  uint64_t at = 0;
+  for (uint32_t j = 0; j < n; ++j) {
+    const tps_fastx_rec *r = &recs[idx[j]];
+    if (at + r->id_len + 1 > cap) return -1;
+    memcpy(out + at, raw_base + r->title_off + r->id_off, r->id_len);
+    at += r->id_len;
+    out[at++] = '\n';
+  }
+  return (int64_t)at;
+}

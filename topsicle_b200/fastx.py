@@ -72,6 +72,8 @@ def host_library() -> C.CDLL:
         lib.tps_fastx_set_two_pass.argtypes = [vp, C.c_int]
         lib.tps_fastx_find_id.restype = C.c_uint32
         lib.tps_fastx_find_id.argtypes = [vp, vp, C.c_uint32, C.c_char_p, C.c_uint32, vp, C.c_uint32]
+        lib.tps_fastx_join_ids.restype = C.c_int64
+        lib.tps_fastx_join_ids.argtypes = [vp, vp, vp, C.c_uint32, vp, C.c_uint64]
         lib.tps_format_rawcount.restype = C.c_int64
         lib.tps_format_rawcount.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_char_p,
                                             C.POINTER(C.c_char_p), vp, C.c_uint64]
@@ -118,6 +120,19 @@ class Batch:
     def read_id(self, i) -> str:
         r = self.recs[i].item()   # (title_off, seq_off, qual_off, title_len, id_off, id_len, ...)
         return C.string_at(self._raw + r[0] + r[4], r[5]).decode("utf-8", "replace")
+
+    def read_ids(self, indices) -> list:
+        """Ids of several reads in one call (the harvest of a batch asks for all its TRC-pass reads at once)."""
+        idx = np.ascontiguousarray(indices, dtype=np.uint32)
+        if idx.size == 0:
+            return []
+        recs = np.ascontiguousarray(self.recs)
+        cap = int(recs["id_len"][idx].sum(dtype=np.uint64)) + idx.size
+        out = np.empty(cap, dtype=np.uint8)
+        n = self._lib.tps_fastx_join_ids(self._raw, recs.ctypes.data, idx.ctypes.data, idx.size, out.ctypes.data, cap)
+        if n < 0:
+            raise FastxError(-4, "id buffer too small")
+        return out[:n - 1].tobytes().decode("utf-8", "replace").split("\n")
 
     def sequence(self, i) -> bytes:
         a, b = self.bounds(i)

@@ -155,8 +155,8 @@ def harvest(cfg: ScanConfig, ctx, batch, rows, raw, want_records: bool, keep=Non
     ratio = cfg.no_bp / cfg.len_telopattern            # allsteps.py:178
     if cfg.want_rawcount and tables is None and raw is not None:
         raw = np.array(raw, copy=True)     # ONE copy out of the context's landing buffer; the tables are views of it
-    for i, cnt, bp, tl, st, nw, telo, length in zip(idx.tolist(), *cols):
-        rid = batch.read_id(i)
+    ids = batch.read_ids(idx)              # one C call for the ids of all TRC-pass reads of the batch
+    for i, rid, cnt, bp, tl, st, nw, telo, length in zip(idx.tolist(), ids, *cols):
         if keep is not None and rid not in keep:
             continue
         pr = PassRead(index=batch.first_read + i, read_id=rid, literal=ctx.patterns[bp],
@@ -412,6 +412,9 @@ class _BatchView:
 
     def read_id(self, i):
         return self.b.read_id(self.lo + i)
+
+    def read_ids(self, indices):
+        return self.b.read_ids(np.asarray(indices, dtype=np.int64) + self.lo)
 
     def record_text(self, i):
         return self.b.record_text(self.lo + i)

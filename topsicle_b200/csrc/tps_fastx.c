@@ -1360,3 +1360,40 @@ int64_t tps_fastx_join_ids(const uint8_t *raw_base, const tps_fastx_rec *recs, c
   }
   return (int64_t)at;
 }
+
+/* Region batch of the ends-first mode: for records idx[0..n) (TRC-pass reads of an ends batch) copy the first
+ * (tails[j] == 0) or last (tails[j] == 1) min(L, maxlen) bases back to back into dst (capacity cap bytes), fill
+ * starts / lens.  Returns how many records were placed (a prefix: the first one that does not fit stops it). */
+uint32_t tps_fastx_gather_regions(const uint8_t *raw_base, const tps_fastx_rec *recs, const uint32_t *idx,
+                                  const uint8_t *tails, uint32_t n, uint32_t maxlen, uint64_t cap, uint8_t *dst,
+                                  uint64_t *starts, uint32_t *lens) {
+  uint64_t at = 0;
+  uint32_t placed = 0;
+  for (; placed < n; ++placed) {
+    const tps_fastx_rec *r = &recs[idx[placed]];
+    const uint32_t L = r->seq_len, k = L < maxlen ? L : maxlen;
+    if (at + k > cap) break;
+    starts[placed] = at;
+    lens[placed] = k;
+    at += k;
+  }
+#pragma omp parallel for schedule(dynamic, 16) if (placed > 64)
+  for (int64_t j = 0; j < (int64_t)placed; ++j) {
+    const tps_fastx_rec *r = &recs[idx[j]];
+    const uint32_t L = r->seq_len, k = lens[j];
+    const uint32_t from = tails[j] ? L - k : 0u;
+    if (!(r->flags & 1u)) {
+      memcpy(dst + starts[j], raw_base + r->seq_off + from, k);
+    } else { /* multi-line / blank-carrying sequence: filter it, then slice */
+      uint8_t *tmp = (uint8_t *)malloc(L ? L : 1);
+      if (tmp) {
+        gather_seq(raw_base, r, tmp);
+        memcpy(dst + starts[j], tmp + from, k);
+        free(tmp);
+      } else {
+        memset(dst + starts[j], 'N', k);
+      }
+    }
+  }
+  return placed;
+}

@@ -72,6 +72,8 @@ def host_library() -> C.CDLL:
         lib.tps_fastx_set_two_pass.argtypes = [vp, C.c_int]
         lib.tps_fastx_find_id.restype = C.c_uint32
         lib.tps_fastx_find_id.argtypes = [vp, vp, C.c_uint32, C.c_char_p, C.c_uint32, vp, C.c_uint32]
+        lib.tps_fastx_gather_regions.restype = C.c_uint32
+        lib.tps_fastx_gather_regions.argtypes = [vp, vp, vp, vp, C.c_uint32, C.c_uint32, C.c_uint64, vp, vp, vp]
         lib.tps_fastx_join_ids.restype = C.c_int64
         lib.tps_fastx_join_ids.argtypes = [vp, vp, vp, C.c_uint32, vp, C.c_uint64]
         lib.tps_format_rawcount.restype = C.c_int64
@@ -194,6 +196,19 @@ class EndsBatch(Batch):
             return self._text(r["seq_off"], r["seq_len"])
         raw = self._text(r["seq_off"], r["seq_raw_len"])
         return raw.translate(None, b" \r\n\t\x0b\x0c")
+
+    def gather_regions(self, indices, tails, maxlengthtelo: int, dst: np.ndarray, starts: np.ndarray,
+                       lens: np.ndarray) -> int:
+        """Copy the regions (see `region`) of reads `indices` back to back into `dst`, filling `starts` / `lens`;
+        returns how many fitted (a prefix).  One C call (threads) instead of two copies per read in Python."""
+        idx = np.ascontiguousarray(indices, dtype=np.uint32)
+        tl = np.ascontiguousarray(tails, dtype=np.uint8)
+        assert dst.dtype == np.uint8 and starts.dtype == np.uint64 and lens.dtype == np.uint32
+        assert len(starts) >= idx.size and len(lens) >= idx.size and tl.size == idx.size
+        recs = np.ascontiguousarray(self.recs)
+        return int(self._lib.tps_fastx_gather_regions(self._raw, recs.ctypes.data, idx.ctypes.data, tl.ctypes.data,
+                                                      idx.size, int(maxlengthtelo), dst.size, dst.ctypes.data,
+                                                      starts.ctypes.data, lens.ctypes.data))
 
     def region(self, i, tail: int, maxlengthtelo: int) -> bytes:
         """The bases steps 2/3 look at: first (tail 0) or last (tail 1) min(L, maxlengthtelo) bases."""

@@ -286,25 +286,22 @@ class _DeviceWorker:
         pending = [list(map(int, idx))]
         while pending:
             group = pending.pop(0)
-            n, at, used = 0, 0, []
-            for i in group:                       # longest prefix that fits one region batch
-                r = batch.region(i, int(tails[i]), cfg.maxlengthtelo)
-                if n >= self.max_pass_reads or at + len(r) > self.region_cap:
-                    break
-                rb[at:at + len(r)] = np.frombuffer(r, dtype=np.uint8)
-                rstarts[n], rlens[n], rtails[n] = at, len(r), tails[i]
-                at += len(r)
-                n += 1
-                used.append(i)
+            cut = group[:self.max_pass_reads]
+            gt = tails[cut].astype(np.uint8)
+            # longest prefix that fits one region batch, copied by the reader library (one call, threads)
+            n = batch.gather_regions(cut, gt, cfg.maxlengthtelo, rb[:self.region_cap], rstarts, rlens)
             if n == 0:
-                raise engine.TpsError(-4, f"a region of {len(r)} bases does not fit the batch capacity "
+                raise engine.TpsError(-4, f"the region of read {cut[0]} does not fit the batch capacity "
                                           f"of {self.region_cap}")
+            used = cut[:n]
+            rtails[:n] = gt[:n]
+            at = int(rstarts[n - 1]) + int(rlens[n - 1])
             if n < len(group):
                 pending.insert(0, group[n:])
             try:
                 bid = ctx.submit_regions(rb[:at], rstarts[:n], rlens[:n], rtails[:n], n)
-                self._region_bases += at
                 rows2, raw2 = ctx.wait(bid, True)
+                self._region_bases += at
             except engine.TpsError as e:
                 if e.code != -4 or n <= 1:
                     raise

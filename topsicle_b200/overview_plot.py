@@ -51,18 +51,18 @@ def plot_running(args):
 
 
 def build_parser():
-    p = argparse.ArgumentParser(description="Command line input handling for run_analysis function")
-    p.add_argument("--inputDir", type=str, help="Path to the input folder directory")
-    p.add_argument("--outputDir", type=str, help="Path to the output folder directory")
+    """Same flags, types and defaults as the reference's overview_plot.py:122-134."""
+    p = argparse.ArgumentParser(description="Overview outputs of the telomere scan (B200 build: CSV data only)")
+    p.add_argument("--inputDir", type=str, help="input file or directory of FASTQ / FASTA(.gz) files")
+    p.add_argument("--outputDir", type=str, help="directory for the outputs")
     p.add_argument("--pattern", metavar="CHAR", type=str, required=True,
-                   help="Required, Telomere repeat sequence (in 5' to 3' orientation). For e.g., in human use CCCTAA")
-    p.add_argument("--minSeqLength", type=int, default=9000, help="Minimum of long read sequence, default = 9kbp")
+                   help="telomere repeat, 5' to 3' (e.g. CCCTAA for human)")
+    p.add_argument("--minSeqLength", type=int, default=9000, help="skip reads no longer than this (default 9000)")
     p.add_argument("--telophrase", nargs="+", type=int,
-                   help="Length of telomere k-mer to search. By default will use telomere k-mer length minus 2")
+                   help="k-mer length(s) to search; default: len(pattern) - 2")
     p.add_argument("--recfindingpattern", action="store_true",
-                   help="Optional, use this to plot the heatmap of patterns vs match")
-    p.add_argument("--rawcount", action="store_true",
-                   help="Optional, save raw count results to CSV for flexibility of plotting")
+                   help="compute the k-mer vs following-characters table (the reference's heat map)")
+    p.add_argument("--rawcount", action="store_true", help="write that table to heatmap_rawcount_{i}.csv")
     return p
 
 

@@ -85,3 +85,11 @@ def test_overview_plot_cli_writes_the_reference_csv(tmp_path):
                         "--recfindingpattern", "--rawcount"])
     got = hashlib.md5(open(out / "heatmap_rawcount_1.csv", "rb").read()).hexdigest()
     assert got == load_json("demo_heatmap.json")[0]["md5"] == "28ad064f247aa236af6f0fedddc63ed4"
+
+
+def test_heatmap_empty_inputs():
+    from topsicle_b200 import descriptive, engine
+    assert descriptive.heatmap_rows([], "CCCTAA", 4, 0) == ([], [])
+    assert descriptive.heatmap_rows([("a", ""), ("b", "")], "CCCTAA", 4, 0) == ([], [])
+    sel = engine.follow_scan(["", "ACGT"], ["CCCT"], 6, 0)
+    assert sel.shape == (2, 2, 1, 1900) and not sel.any()

@@ -802,6 +802,7 @@ int tps_follow_scan(int device, const uint8_t *bases, const uint64_t *offsets, u
   if (e == cudaSuccess) e = cudaMalloc(&d_flags, (n_tiles + 4) * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMalloc(&d_off, ((uint64_t)n_reads + 1) * sizeof(uint64_t));
   if (e == cudaSuccess) e = cudaMalloc(&d_sel, sel_bytes);
+  if (e == cudaSuccess) e = cudaMemset(d_sel, 0, sel_bytes); /* a batch of empty reads launches nothing */
   if (e == cudaSuccess) e = cudaMemcpy(d_bases, bases, n_bases, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(d_off, offsets, ((uint64_t)n_reads + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice);
   if (e == cudaSuccess && n_tiles) {

@@ -436,6 +436,53 @@ __device__ __forceinline__ void tps_win_match_pair(const TpsWin<K> &w, const uin
   Mc = w.V & ~tx & ~tyc;
 }
 
+/* ---- step-1 row logic shared by the K2 kernels ------------------------------------------------------- */
+__device__ __forceinline__ void tps_row_init(tps_row &row, uint32_t true_len) {
+  row.length = true_len;
+  row.status = TPS_ST_FILTERED;
+  row.tail = 0; row.best_pattern = 0; row.reserved0 = 0;
+  row.match_count = 0; row.head_max = 0; row.tail_max = 0; row.reserved1 = 0;
+  row.n_windows = 0; row.bkp = -1; row.telo_length = -1; row.reserved2 = 0;
+  row.rawcount_offset = ~0ull;
+}
+
+/* Tail decision, cutoff test and (lane 0) the append to the pass list, from the first-max counts of the two
+ * ends: ms / ps of seq[:no_bp], me / pe of the reversed seq[-no_bp:] (allsteps.py:190-198). */
+__device__ __forceinline__ void tps_trc_decide(const TpsScanArgs &a, uint32_t n_patterns, uint32_t r, uint32_t Lt,
+                                               uint32_t lane, uint32_t ms, uint32_t ps, uint32_t me, uint32_t pe,
+                                               tps_row &row) {
+  bool fwd = ms > me; /* tie -> reverse, allsteps.py:193-198 */
+  if (a.flags & TPS_FLAG_FORCE_FORWARD) fwd = true; /* caller-chosen tail, allsteps.py:294-297 */
+  if (a.flags & TPS_FLAG_FORCE_REVERSE) fwd = false;
+  if (a.force_tails) fwd = a.force_tails[r] == TPS_TAIL_FORWARD;
+  const uint32_t cnt = fwd ? ms : me;
+  row.tail = fwd ? TPS_TAIL_FORWARD : TPS_TAIL_REVERSE;
+  row.best_pattern = (uint8_t)(fwd ? ps : pe);
+  row.match_count = (uint16_t)cnt;
+  row.head_max = (uint16_t)ms;
+  row.tail_max = (uint16_t)me;
+  /* a region batch holds reads that passed step 1 on their whole ends; its own count may see fewer bases */
+  row.status = (cnt >= a.count_threshold || a.force_tails) ? TPS_ST_PASS : TPS_ST_BELOW;
+  if (row.status == TPS_ST_PASS && lane == 0 && !(a.flags & TPS_FLAG_STEP1_ONLY)) {
+    const uint32_t M = Lt < a.maxlengthtelo ? Lt : a.maxlengthtelo;
+    const uint32_t nreg = M > a.trimfirst ? M - a.trimfirst : 0u;
+    const uint32_t nW = nreg >= a.W ? (nreg - a.W) / a.slide + 1u : 0u;
+    row.n_windows = nW;
+    const uint32_t slot = atomicAdd(a.counters + 0, 1u);
+    if (slot < a.max_pass) {
+      a.pass_list[slot] = r;
+      if (a.want_rawcount && nW) {
+        const unsigned long long elems = (unsigned long long)nW * n_patterns;
+        const unsigned long long at = atomicAdd(reinterpret_cast<unsigned long long *>(a.counters + 2), elems);
+        if (at + elems <= a.raw_capacity) row.rawcount_offset = at;
+        else atomicOr(a.counters + 4, TPS_OVF_RAWCOUNT);
+      }
+    } else {
+      atomicOr(a.counters + 4, TPS_OVF_PASS);
+    }
+  }
+}
+
 /* ------------------------------------------------------------------------------------ K2 */
 #define TPS_K2_WARPS 4
 
@@ -512,48 +559,13 @@ tps_trc_kernel(const TpsScanArgs a, const TpsPatTable pt) {
    * and the window count from the read's real length */
   const uint32_t Lt = a.true_lens ? a.true_lens[r] : L;
   tps_row row;
-  row.length = Lt;
-  row.status = TPS_ST_FILTERED;
-  row.tail = 0; row.best_pattern = 0; row.reserved0 = 0;
-  row.match_count = 0; row.head_max = 0; row.tail_max = 0; row.reserved1 = 0;
-  row.n_windows = 0; row.bkp = -1; row.telo_length = -1; row.reserved2 = 0;
-  row.rawcount_offset = ~0ull;
+  tps_row_init(row, Lt);
   if (Lt > a.min_seq_length || a.force_tails) { /* strict, allsteps.py:175; region batches passed it already */
     const uint32_t n = L < a.no_bp ? L : a.no_bp;
     uint32_t ms, ps, me, pe;
     tps_trc_end<K>(a, pt, pm, off, n, false, lin, mrows, cnts, lane, ms, ps);         /* seq[:no_bp] */
     tps_trc_end<K>(a, pt, pm, off + L - n, n, true, lin, mrows, cnts, lane, me, pe);  /* seq[-no_bp:][::-1] */
-    bool fwd = ms > me; /* tie -> reverse, allsteps.py:193-198 */
-    if (a.flags & TPS_FLAG_FORCE_FORWARD) fwd = true; /* caller-chosen tail, allsteps.py:294-297 */
-    if (a.flags & TPS_FLAG_FORCE_REVERSE) fwd = false;
-    if (a.force_tails) fwd = a.force_tails[r] == TPS_TAIL_FORWARD;
-    const uint32_t cnt = fwd ? ms : me;
-    row.tail = fwd ? TPS_TAIL_FORWARD : TPS_TAIL_REVERSE;
-    row.best_pattern = (uint8_t)(fwd ? ps : pe);
-    row.match_count = (uint16_t)cnt;
-    row.head_max = (uint16_t)ms;
-    row.tail_max = (uint16_t)me;
-    /* a region batch holds reads that passed step 1 on their whole ends; its own count may see fewer bases */
-    row.status = (cnt >= a.count_threshold || a.force_tails) ? TPS_ST_PASS : TPS_ST_BELOW;
-    if (row.status == TPS_ST_PASS && lane == 0 && !(a.flags & TPS_FLAG_STEP1_ONLY)) {
-      const uint32_t M = Lt < a.maxlengthtelo ? Lt : a.maxlengthtelo;
-      const uint32_t nreg = M > a.trimfirst ? M - a.trimfirst : 0u;
-      const uint32_t nW = nreg >= a.W ? (nreg - a.W) / a.slide + 1u : 0u;
-      row.n_windows = nW;
-      const uint32_t slot = atomicAdd(a.counters + 0, 1u);
-      if (slot < a.max_pass) {
-        a.pass_list[slot] = r;
-        if (a.want_rawcount && nW) {
-          const unsigned long long elems = (unsigned long long)nW * pt.n;
-          const unsigned long long at =
-              atomicAdd(reinterpret_cast<unsigned long long *>(a.counters + 2), elems);
-          if (at + elems <= a.raw_capacity) row.rawcount_offset = at;
-          else atomicOr(a.counters + 4, TPS_OVF_RAWCOUNT);
-        }
-      } else {
-        atomicOr(a.counters + 4, TPS_OVF_PASS);
-      }
-    }
+    tps_trc_decide(a, pt.n, r, Lt, lane, ms, ps, me, pe, row);
   }
   if (lane == 0) a.rows[r] = row;
 }
@@ -702,48 +714,13 @@ tps_trc_reg_kernel(const TpsScanArgs a, const TpsPatTable pt) {
    * and the window count from the read's real length */
   const uint32_t Lt = a.true_lens ? a.true_lens[r] : L;
   tps_row row;
-  row.length = Lt;
-  row.status = TPS_ST_FILTERED;
-  row.tail = 0; row.best_pattern = 0; row.reserved0 = 0;
-  row.match_count = 0; row.head_max = 0; row.tail_max = 0; row.reserved1 = 0;
-  row.n_windows = 0; row.bkp = -1; row.telo_length = -1; row.reserved2 = 0;
-  row.rawcount_offset = ~0ull;
+  tps_row_init(row, Lt);
   if (Lt > a.min_seq_length || a.force_tails) { /* strict, allsteps.py:175; region batches passed it already */
     const uint32_t n = L < a.no_bp ? L : a.no_bp;
     uint32_t ms, ps, me, pe;
     tps_trc_end_reg<K>(a, pt, pm, off, n, false, mrows, lane, ms, ps);         /* seq[:no_bp] */
     tps_trc_end_reg<K>(a, pt, pm, off + L - n, n, true, mrows, lane, me, pe);  /* seq[-no_bp:][::-1] */
-    bool fwd = ms > me; /* tie -> reverse, allsteps.py:193-198 */
-    if (a.flags & TPS_FLAG_FORCE_FORWARD) fwd = true;
-    if (a.flags & TPS_FLAG_FORCE_REVERSE) fwd = false;
-    if (a.force_tails) fwd = a.force_tails[r] == TPS_TAIL_FORWARD;
-    const uint32_t cnt = fwd ? ms : me;
-    row.tail = fwd ? TPS_TAIL_FORWARD : TPS_TAIL_REVERSE;
-    row.best_pattern = (uint8_t)(fwd ? ps : pe);
-    row.match_count = (uint16_t)cnt;
-    row.head_max = (uint16_t)ms;
-    row.tail_max = (uint16_t)me;
-    /* a region batch holds reads that passed step 1 on their whole ends; its own count may see fewer bases */
-    row.status = (cnt >= a.count_threshold || a.force_tails) ? TPS_ST_PASS : TPS_ST_BELOW;
-    if (row.status == TPS_ST_PASS && lane == 0 && !(a.flags & TPS_FLAG_STEP1_ONLY)) {
-      const uint32_t M = Lt < a.maxlengthtelo ? Lt : a.maxlengthtelo;
-      const uint32_t nreg = M > a.trimfirst ? M - a.trimfirst : 0u;
-      const uint32_t nW = nreg >= a.W ? (nreg - a.W) / a.slide + 1u : 0u;
-      row.n_windows = nW;
-      const uint32_t slot = atomicAdd(a.counters + 0, 1u);
-      if (slot < a.max_pass) {
-        a.pass_list[slot] = r;
-        if (a.want_rawcount && nW) {
-          const unsigned long long elems = (unsigned long long)nW * pt.n;
-          const unsigned long long at =
-              atomicAdd(reinterpret_cast<unsigned long long *>(a.counters + 2), elems);
-          if (at + elems <= a.raw_capacity) row.rawcount_offset = at;
-          else atomicOr(a.counters + 4, TPS_OVF_RAWCOUNT);
-        }
-      } else {
-        atomicOr(a.counters + 4, TPS_OVF_PASS);
-      }
-    }
+    tps_trc_decide(a, pt.n, r, Lt, lane, ms, ps, me, pe, row);
   }
   if (lane == 0) a.rows[r] = row;
 }

@@ -429,13 +429,36 @@ int tps_create(tps_ctx **out, int device, const tps_params *params) {
 
 namespace {
 
-/* Enqueue K1..K4 for one batch on `st`.  d_bases/d_off may be slot- or caller-owned.  With
- * `packed_by` the batch was already packed (K1) into that slot's code/flag/mask buffers by another
- * context: only K2..K4 run, reading them. */
-int enqueue_scan(tps_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t *d_bases, const uint64_t *d_off,
-                 uint32_t n_reads, uint64_t n_bases, tps_row *d_rows, bool timed, const Slot *packed_by = nullptr,
-                 const uint32_t *d_len = nullptr, tps_ctx *stream_owner = nullptr,
-                 const uint32_t *d_true_len = nullptr, const uint8_t *d_tails = nullptr) {
+/* What enqueue_scan works on.  d_bases / d_off may be slot- or caller-owned.  With `packed_by` the batch was
+ * already packed (K1) into that slot's code / flag buffers by another context: only K2..K4 run, reading them,
+ * on the streams of `stream_owner`. */
+struct ScanJob {
+  const uint8_t *d_bases = nullptr;
+  const uint64_t *d_off = nullptr;
+  uint32_t n_reads = 0;
+  uint64_t n_bases = 0;
+  tps_row *d_rows = nullptr;
+  bool timed = false;                  /* record the CUDA-event ring (device-resident scans) */
+  const Slot *packed_by = nullptr;
+  const uint32_t *d_len = nullptr;     /* span batch: read lengths */
+  tps_ctx *stream_owner = nullptr;
+  const uint32_t *d_true_len = nullptr; /* ends batch: real read lengths (step 1 only) */
+  const uint8_t *d_tails = nullptr;     /* region batch: per-read forced tail */
+};
+
+/* Enqueue K1..K4 for one batch; `st` is the slot's stream (copies, ordering). */
+int enqueue_scan(tps_ctx *ctx, Slot &s, cudaStream_t st, const ScanJob &job) {
+  const uint8_t *d_bases = job.d_bases;
+  const uint64_t *d_off = job.d_off;
+  const uint32_t n_reads = job.n_reads;
+  const uint64_t n_bases = job.n_bases;
+  tps_row *d_rows = job.d_rows;
+  const bool timed = job.timed;
+  const Slot *packed_by = job.packed_by;
+  const uint32_t *d_len = job.d_len;
+  tps_ctx *stream_owner = job.stream_owner;
+  const uint32_t *d_true_len = job.d_true_len;
+  const uint8_t *d_tails = job.d_tails;
   const tps_params &p = ctx->p;
   cudaEvent_t *ev = ctx->ev[ctx->scan_seq % TPS_TIMING_RING];
   /* split mode: `st` (the slot's stream) orders the batch against its copies; K1 goes to the context's
@@ -567,9 +590,16 @@ static int submit_common(tps_ctx *ctx, const uint8_t *bases, uint64_t n_bases, c
   s.has_lens = lengths != nullptr;
   s.ends = true_lens != nullptr;
   s.regions = tails != nullptr;
-  int rc = enqueue_scan(ctx, s, st, s.d_bases, s.d_off, n_reads, n_bases, s.d_rows, false, nullptr,
-                        lengths ? s.d_len : nullptr, nullptr, true_lens ? s.d_true_len : nullptr,
-                        tails ? s.d_tails : nullptr);
+  ScanJob job;
+  job.d_bases = s.d_bases;
+  job.d_off = s.d_off;
+  job.n_reads = n_reads;
+  job.n_bases = n_bases;
+  job.d_rows = s.d_rows;
+  job.d_len = lengths ? s.d_len : nullptr;
+  job.d_true_len = true_lens ? s.d_true_len : nullptr;
+  job.d_tails = tails ? s.d_tails : nullptr;
+  int rc = enqueue_scan(ctx, s, st, job);
   if (rc) return rc;
   if (n_reads)
     TPS_CUDA(ctx, cudaMemcpyAsync(s.h_rows, s.d_rows, (uint64_t)n_reads * sizeof(tps_row), cudaMemcpyDeviceToHost, st));
@@ -645,8 +675,16 @@ int tps_submit_shared(tps_ctx *ctx, tps_ctx *owner, uint64_t batch_id) {
   if (so->regions) return fail(ctx, TPS_EINVAL, "a region batch belongs to one context (its reads were chosen by that context's step 1)");
   s.ends = so->ends;
   s.regions = false;
-  int rc = enqueue_scan(ctx, s, st, so->d_bases, so->d_off, so->n_reads, 0, s.d_rows, false, so,
-                        so->has_lens ? so->d_len : nullptr, owner, so->ends ? so->d_true_len : nullptr, nullptr);
+  ScanJob job;
+  job.d_bases = so->d_bases;
+  job.d_off = so->d_off;
+  job.n_reads = so->n_reads;
+  job.d_rows = s.d_rows;
+  job.packed_by = so;
+  job.d_len = so->has_lens ? so->d_len : nullptr;
+  job.stream_owner = owner;
+  job.d_true_len = so->ends ? so->d_true_len : nullptr;
+  int rc = enqueue_scan(ctx, s, st, job);
   if (rc) return rc;
   if (so->n_reads)
     TPS_CUDA(ctx, cudaMemcpyAsync(s.h_rows, s.d_rows, (uint64_t)so->n_reads * sizeof(tps_row), cudaMemcpyDeviceToHost, st));
@@ -724,7 +762,14 @@ int tps_scan_device_slot(tps_ctx *ctx, uint32_t slot, const uint8_t *d_bases, co
   TPS_CUDA(ctx, cudaSetDevice(ctx->device));
   Slot &s = ctx->slots[slot];
   if (s.busy) return fail(ctx, TPS_ESTATE, "slot %u busy with a submitted batch", slot);
-  return enqueue_scan(ctx, s, s.stream, d_bases, d_offsets, n_reads, n_bases, d_rows_out, true);
+  ScanJob job;
+  job.d_bases = d_bases;
+  job.d_off = d_offsets;
+  job.n_reads = n_reads;
+  job.n_bases = n_bases;
+  job.d_rows = d_rows_out;
+  job.timed = true;
+  return enqueue_scan(ctx, s, s.stream, job);
 }
 
 int tps_sync(tps_ctx *ctx) {

@@ -349,3 +349,36 @@ def test_next_ends_on_awkward_fastq(tmp_path):
             assert g[0] == rid and g[1] == len(s), rid
             assert g[2] == (s if len(s) <= 2 * H else s[:H] + s[-H:]), rid
             assert g[3] == s and g[4] == s[:1000] and g[5] == s[-1000:], rid
+
+
+def test_records_text_equals_record_text(tmp_path):
+    """The batched SeqIO.write text (one C call) equals the per-record form on FASTQ (plain / CRLF / '+title' /
+    trailing blanks), multi-line FASTA and gzip, through whole-read and ends batches."""
+    rng = np.random.default_rng(5)
+    fq, fa = tmp_path / "a.fastq", tmp_path / "a.fasta"
+    with open(fq, "wb") as f1, open(fa, "wb") as f2:
+        for i in range(300):
+            L = int(rng.integers(0, 400))
+            seq = bytes(rng.choice(np.frombuffer(b"ACGTNacgt", np.uint8), L))
+            qual = bytes(rng.choice(np.frombuffer(b"@+I!5", np.uint8), L))
+            eol = b"\r\n" if i % 5 == 0 else b"\n"
+            plus = b"+r%d" % i if i % 4 == 0 else b"+"
+            pad = b"   " if i % 9 == 0 else b""
+            f1.write(b"@r%d some text%s%s%s%s%s%s%s%s" % (i, pad, eol, seq, eol, plus, eol, qual, eol))
+            f2.write(b">r%d t%s\n" % (i, pad) + b"".join(seq[j:j + 70] + b"\n" for j in range(0, L, 70)))
+    gz = tmp_path / "a.fastq.gz"
+    with open(fq, "rb") as src, gzip.open(gz, "wb") as dst:
+        dst.write(src.read())
+    bases, offsets = np.empty(1 << 20, np.uint8), np.empty(4096, np.uint64)
+    starts, lens, tl = np.empty(4096, np.uint64), np.empty(4096, np.uint32), np.empty(4096, np.uint32)
+    for path in (fq, fa, gz):
+        for mode in ("next", "ends"):
+            with fastx.FastxFile(str(path), threads=2) as fx:
+                b = fx.next_batch(bases, offsets) if mode == "next" else fx.next_ends(bases, starts, lens, tl, 50)
+                want = [b.record_text(i) for i in range(b.n_reads)]
+                got = [bytes(t) for t in b.records_text(range(b.n_reads))]
+                some = [bytes(t) for t in b.records_text([7, 3, 299])]
+                ids = b.read_ids([7, 3, 299])
+                b.release()
+            assert b.n_reads == 300 and got == want, (path, mode)
+            assert some == [want[7], want[3], want[299]] and ids == ["r7", "r3", "r299"]

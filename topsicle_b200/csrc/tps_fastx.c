@@ -1397,3 +1397,50 @@ uint32_t tps_fastx_gather_regions(const uint8_t *raw_base, const tps_fastx_rec *
   }
   return placed;
 }
+
+/* SeqIO.write text (main.py:86) of records idx[0..n), back to back in out: FASTQ `@title\nseq\n+\nqual\n`, FASTA
+ * `>title\n` + the sequence wrapped at 60 columns.  ends[j] = end offset of record j's text.  Returns the bytes
+ * written, or -1 if cap is too small.  One call (threads) for all TRC-pass reads of a batch. */
+int64_t tps_fastx_records_text(const uint8_t *raw_base, const tps_fastx_rec *recs, const uint32_t *idx, uint32_t n,
+                               int format, uint8_t *out, uint64_t cap, uint64_t *ends) {
+  uint64_t at = 0;
+  for (uint32_t j = 0; j < n; ++j) {
+    const tps_fastx_rec *r = &recs[idx[j]];
+    const uint64_t L = r->seq_len;
+    at += format == TPS_FX_FASTQ ? 1 + (uint64_t)r->title_len + 1 + L + 3 + L + 1
+                                 : 1 + (uint64_t)r->title_len + 1 + L + (L + 59) / 60;
+    ends[j] = at;
+  }
+  if (at > cap) return -1;
+#pragma omp parallel for schedule(dynamic, 8) if (n > 32)
+  for (int64_t j = 0; j < (int64_t)n; ++j) {
+    const tps_fastx_rec *r = &recs[idx[j]];
+    const uint32_t L = r->seq_len;
+    uint8_t *o = out + (j ? ends[j - 1] : 0);
+    *o++ = format == TPS_FX_FASTQ ? '@' : '>';
+    memcpy(o, raw_base + r->title_off, r->title_len);
+    o += r->title_len;
+    *o++ = '\n';
+    if (format == TPS_FX_FASTQ) {
+      gather_seq(raw_base, r, o);
+      o += L;
+      memcpy(o, "\n+\n", 3);
+      o += 3;
+      memcpy(o, raw_base + r->qual_off, L);
+      o += L;
+      *o++ = '\n';
+    } else {
+      uint8_t *tmp = (uint8_t *)malloc(L ? L : 1);
+      if (!tmp) continue; /* cannot happen for sane L */
+      gather_seq(raw_base, r, tmp);
+      for (uint32_t a = 0; a < L; a += 60) {
+        const uint32_t k = L - a < 60 ? L - a : 60;
+        memcpy(o, tmp + a, k);
+        o += k;
+        *o++ = '\n';
+      }
+      free(tmp);
+    }
+  }
+  return (int64_t)at;
+}

@@ -74,6 +74,8 @@ def host_library() -> C.CDLL:
         lib.tps_fastx_find_id.argtypes = [vp, vp, C.c_uint32, C.c_char_p, C.c_uint32, vp, C.c_uint32]
         lib.tps_fastx_gather_regions.restype = C.c_uint32
         lib.tps_fastx_gather_regions.argtypes = [vp, vp, vp, vp, C.c_uint32, C.c_uint32, C.c_uint64, vp, vp, vp]
+        lib.tps_fastx_records_text.restype = C.c_int64
+        lib.tps_fastx_records_text.argtypes = [vp, vp, vp, C.c_uint32, C.c_int, vp, C.c_uint64, vp]
         lib.tps_fastx_join_ids.restype = C.c_int64
         lib.tps_fastx_join_ids.argtypes = [vp, vp, vp, C.c_uint32, vp, C.c_uint64]
         lib.tps_format_rawcount.restype = C.c_int64
@@ -159,6 +161,26 @@ class Batch:
             return b"@" + title + b"\n" + seq + b"\n+\n" + self.quality(i) + b"\n"
         lines = [seq[j:j + 60] for j in range(0, len(seq), 60)]
         return b">" + title + b"\n" + b"".join(ln + b"\n" for ln in lines)
+
+    def records_text(self, indices) -> list:
+        """`record_text` of several reads in one call: a list of memoryviews into one buffer (what the subset file
+        writer needs for all TRC-pass reads of a batch)."""
+        idx = np.ascontiguousarray(indices, dtype=np.uint32)
+        if idx.size == 0:
+            return []
+        recs = np.ascontiguousarray(self.recs)
+        sel = recs[idx]
+        L = sel["seq_len"].astype(np.uint64)
+        cap = int((sel["title_len"].astype(np.uint64) + 2 * L + L // 60 + 8).sum())
+        out = np.empty(cap, dtype=np.uint8)
+        ends = np.empty(idx.size, dtype=np.uint64)
+        n = self._lib.tps_fastx_records_text(self._raw, recs.ctypes.data, idx.ctypes.data, idx.size, self.format,
+                                             out.ctypes.data, cap, ends.ctypes.data)
+        if n < 0:
+            raise FastxError(-4, "record text buffer too small")
+        view = memoryview(out)
+        cuts = [0] + ends.tolist()
+        return [view[cuts[j]:cuts[j + 1]] for j in range(idx.size)]
 
     def find_id(self, read_id: str) -> list:
         """Indices of the records whose id equals `read_id` (the reference's `seq.id != read` test)."""

@@ -69,7 +69,7 @@ class PassRead:
     telo_length: int      # trimfirst + slide * bkp, -1 if BADSEG
     length: int
     counts: np.ndarray | None = None   # uint8 [n_windows][n_patterns] when want_rawcount
-    record: bytes | None = None        # SeqIO.write text when want_records
+    record: bytes | memoryview | None = None   # SeqIO.write text when want_records
 
 
 @dataclass
@@ -166,9 +166,11 @@ def harvest(cfg: ScanConfig, ctx, batch, rows, raw, want_records: bool, keep=Non
             pr.counts = tables.get(i)
         elif cfg.want_rawcount and raw is not None:
             pr.counts = ctx.rawcount_table(rows, raw, i)
-        if want_records:
-            pr.record = batch.record_text(i)
         out.append(pr)
+    if want_records and out:               # SeqIO.write text of every kept read: one C call, views of one buffer
+        first = batch.first_read
+        for pr, text in zip(out, batch.records_text([pr.index - first for pr in out])):
+            pr.record = text
     return out
 
 
@@ -415,6 +417,9 @@ class _BatchView:
 
     def record_text(self, i):
         return self.b.record_text(self.lo + i)
+
+    def records_text(self, indices):
+        return self.b.records_text(np.asarray(indices, dtype=np.int64) + self.lo)
 
 
 class Scanner:

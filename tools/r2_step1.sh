@@ -1,0 +1,8 @@
+#!/bin/bash
+timeout 900 python -m pytest tests/test_gpu_window_bp.py -x -q 2>&1 | tail -15
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_random_sweep.py -x -q 2>&1 | tail -5
+for c in 5 3 2 4; do
+  python bench.py --config $c --no-cpu-baseline --no-e2e --no-parse --steps 20 --warmup 3 > gpurun_out/r2b_c$c.json 2> gpurun_out/r2b_c$c.err || tail -5 gpurun_out/r2b_c$c.err
+  python -c "
+import json;d=json.load(open('gpurun_out/r2b_c$c.json'));print($c, d['value'], d['device_ms_per_step'], d['roofline']['pipelined_scan_frac'], d['trc_pass_reads_per_step'])"
+done

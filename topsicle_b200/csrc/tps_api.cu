@@ -39,6 +39,8 @@ struct Slot {
   uint32_t *d_counters = nullptr;
   uint8_t *d_raw = nullptr;
   uint32_t *d_cw = nullptr;         /* c_w rows of passing reads */
+  uint32_t *d_tile_done = nullptr;  /* bit-parallel K3: finished tiles per passing read */
+  TpsTile *d_items = nullptr;       /* bit-parallel K3: tile records listed by K2 */
   tps_row *h_rows = nullptr;        /* pinned */
   uint32_t *h_counters = nullptr;   /* pinned */
   uint64_t batch_id = 0;
@@ -56,6 +58,12 @@ struct tps_ctx {
   uint32_t k2_lin_words = 0, k2_nq_max = 0, k2_smem = 0;
   uint32_t k3_lin_words = 0, k3_tile_words = 0, k3_tile_bases = 0, k3_tiles_max = 0, k3_smem = 0, k3_grid = 0;
   uint32_t k4_grid = 0;
+  /* bit-parallel K3 with the change point fused (tps_window_bp_kernel): the default whenever the literals are
+   * distinct strings of one length K <= 8, W - K >= 32, W <= 2048 and no raw-count tables are wanted */
+  bool k3_bitpar = false;
+  void (*k3n_fn)(const TpsScanArgs, const TpsPatTable) = nullptr;
+  uint32_t k3n_lin_words = 0, k3n_stride = 0, k3n_tile_bases = 0, k3n_tiles_max = 0, k3n_smem = 0, k3n_grid = 0, k3n_nz = 0;
+  uint32_t k3n_cp_cap = 0, cw16_stride = 0;
   uint32_t cw_stride = 0, max_pass = 0;
   int kt = 0; /* template K of the K2/K3 instantiation in use (0 = generic) */
   void (*k2_fn)(const TpsScanArgs, const TpsPatTable) = nullptr;
@@ -162,7 +170,7 @@ extern "C" {
 int tps_abi_version(void) { return TPS_ABI_VERSION; }
 
 const char *tps_build_info(void) {
-  return "topsicle_b200 sm_100a; kernels: tps_pack_tma_kernel, tps_pack_kernel, tps_trc_reg_kernel<K>, tps_trc_kernel<K>, tps_window_kernel<K>, tps_changepoint_kernel; " __DATE__;
+  return "topsicle_b200 sm_100a; kernels: tps_pack_tma_kernel, tps_pack_kernel, tps_trc_reg_kernel<K>, tps_trc_kernel<K>, tps_window_bp_kernel<K>, tps_window_kernel<K>, tps_changepoint_kernel; " __DATE__;
 }
 
 const char *tps_last_error(const tps_ctx *ctx) { return ctx ? ctx->err : g_create_error; }
@@ -197,7 +205,7 @@ void tps_destroy(tps_ctx *ctx) {
     if (s.stream) cudaStreamSynchronize(s.stream);
     cudaFree(s.d_bases); cudaFree(s.d_codes); cudaFree(s.d_flags);
     cudaFree(s.d_off); cudaFree(s.d_len); cudaFree(s.d_true_len); cudaFree(s.d_tails); cudaFree(s.d_rows); cudaFree(s.d_pass); cudaFree(s.d_counters);
-    cudaFree(s.d_raw); cudaFree(s.d_cw);
+    cudaFree(s.d_raw); cudaFree(s.d_cw); cudaFree(s.d_tile_done); cudaFree(s.d_items);
     if (s.h_rows) cudaFreeHost(s.h_rows);
     if (s.h_counters) cudaFreeHost(s.h_counters);
     if (s.done) cudaEventDestroy(s.done);
@@ -279,7 +287,7 @@ int tps_create(tps_ctx **out, int device, const tps_params *params) {
   for (uint32_t i = 0; i < pt.n; ++i) kmax = pt.len[i] > kmax ? pt.len[i] : kmax;
   ctx->kt = (kmin == kmax && kmax <= 8) ? (int)kmax : 0;
   switch (ctx->kt) {
-#define TPS_PICK(KK) case KK: ctx->k2_fn = tps_trc_kernel<KK>; ctx->k2r_fn = tps_trc_reg_kernel<KK>; ctx->k3_fn = tps_window_kernel<KK>; break;
+#define TPS_PICK(KK) case KK: ctx->k2_fn = tps_trc_kernel<KK>; ctx->k2r_fn = tps_trc_reg_kernel<KK>; ctx->k3_fn = tps_window_kernel<KK>; ctx->k3n_fn = tps_window_bp_kernel<KK>; break;
     TPS_PICK(1) TPS_PICK(2) TPS_PICK(3) TPS_PICK(4) TPS_PICK(5) TPS_PICK(6) TPS_PICK(7) TPS_PICK(8)
 #undef TPS_PICK
     default: ctx->k2_fn = tps_trc_kernel<0>; ctx->k2r_fn = tps_trc_reg_kernel<0>; ctx->k3_fn = tps_window_kernel<0>; break;
@@ -301,15 +309,44 @@ int tps_create(tps_ctx **out, int device, const tps_params *params) {
   if (ctx->k3_tiles_max == 0) ctx->k3_tiles_max = 1;
   ctx->k3_smem = (pm_words + 3 * ctx->k3_lin_words + 3 * ctx->k3_tile_words + 3 + 2 * pt.n * ctx->k3_tile_words +
                   pt.n_bordered * ctx->k3_tile_words) * 4;
+  {
+    /* bit-parallel K3: needs distinct literals of one length (at most one literal matches at a position) */
+    bool distinct = true;
+    for (uint32_t i = 0; i < pt.n && distinct; ++i)
+      for (uint32_t j = i + 1; j < pt.n && distinct; ++j)
+        distinct = !(pt.len[i] == pt.len[j] && pt.lo[i] == pt.lo[j] && pt.hi[i] == pt.hi[j]);
+    const char *e = getenv("TPS_K3_BITPAR"); /* 0 = tps_window_kernel + tps_changepoint_kernel (A/B, and the fallback) */
+    ctx->k3_bitpar = ctx->kt > 0 && distinct && !p.want_rawcount && p.window_size >= (uint32_t)ctx->kt + 32u &&
+                     p.window_size <= 2048u && (uint64_t)cnt_max * pt.n <= 65535u /* c_w as uint16 */ &&
+                     !(e && atoi(e) == 0);
+    if (ctx->k3_bitpar) {
+      const uint32_t D = p.window_size - (uint32_t)ctx->kt;
+      ctx->k3n_tile_bases = (32u * TPS_K3N_THREADS - p.window_size) & ~31u;
+      ctx->k3n_lin_words = lin_words_for(32u * TPS_K3N_THREADS);
+      ctx->k3n_stride = TPS_K3N_THREADS + (D >> 5) + 2u;
+      ctx->k3n_tiles_max = (uint32_t)((reg_max + ctx->k3n_tile_bases - 1) / ctx->k3n_tile_bases);
+      if (ctx->k3n_tiles_max == 0) ctx->k3n_tiles_max = 1;
+      ctx->k3n_nz = 1;
+      while ((1u << ctx->k3n_nz) <= pt.n) ctx->k3n_nz++;
+      const uint32_t head_words = 2 * TPS_K3N_RAW_WORDS + pm_words + 3; /* prefetch buffers, literal masks, alignment */
+      ctx->k3n_smem = (head_words + 3 * ctx->k3n_lin_words + 3 * (TPS_K3N_THREADS + 1) + 3 + 4 * TPS_K3N_THREADS +
+                       (ctx->k3n_nz > 4 ? 4 * TPS_K3N_THREADS : 0) + 2 * TPS_K3N_THREADS +
+                       (pt.n_bordered ? 2 * TPS_K3N_THREADS : 0) + 2 * ((pt.n + 3u) & ~3u) * ctx->k3n_stride +
+                       pt.n_bordered * (TPS_K3N_THREADS + 1)) * 4;
+      ctx->k3n_cp_cap = ((ctx->k3n_smem - head_words * 4) / 2) & ~7u; /* c_w row of a read staged as uint16 */
+      ctx->cw16_stride = (uint32_t)(((nw_max ? nw_max : 1) + 7) & ~7ull);
+    }
+  }
   ctx->cw_stride = (uint32_t)(nw_max ? nw_max : 1);
   ctx->max_pass = p.max_pass_reads ? p.max_pass_reads : p.max_batch_reads;
   if (ctx->max_pass > p.max_batch_reads) ctx->max_pass = p.max_batch_reads;
-  if ((uint64_t)ctx->max_pass * ctx->k3_tiles_max > 0xFFFFFFF0ull) {
+  if ((uint64_t)ctx->max_pass * (ctx->k3_tiles_max > ctx->k3n_tiles_max ? ctx->k3_tiles_max : ctx->k3n_tiles_max) > 0xFFFFFFF0ull) {
     int c_ = fail(nullptr, TPS_EINVAL, "max_pass_reads * tiles per read overflows the work counter");
     tps_destroy(ctx);
     return c_;
   }
   const uint32_t smem_limit = (uint32_t)prop.sharedMemPerBlockOptin;
+  if (ctx->k3_bitpar && ctx->k3n_smem > smem_limit) ctx->k3_bitpar = false; /* very many literals: the plain kernel */
   if (ctx->k2_smem > smem_limit || ctx->k3_smem > smem_limit) {
     int c_ = fail(nullptr, TPS_EINVAL, "parameters need %u / %u bytes of shared memory (limit %u)", ctx->k2_smem,
                   ctx->k3_smem, smem_limit);
@@ -320,6 +357,12 @@ int tps_create(tps_ctx **out, int device, const tps_params *params) {
   TPS_CC(cudaFuncSetAttribute(ctx->k3_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->k3_smem));
   if (ctx->k2r_smem > 48 * 1024)
     TPS_CC(cudaFuncSetAttribute(ctx->k2r_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->k2r_smem));
+  if (ctx->k3_bitpar) {
+    int occn = 0;
+    TPS_CC(cudaFuncSetAttribute(ctx->k3n_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->k3n_smem));
+    TPS_CC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occn, ctx->k3n_fn, TPS_K3N_THREADS, ctx->k3n_smem));
+    ctx->k3n_grid = (uint32_t)(ctx->n_sms * (occn > 0 ? occn : 1));
+  }
   int occ1 = 0, occ3 = 0, occ4 = 0;
   {
     const char *e = getenv("TPS_K1_UNROLL"); /* tuning knob: 2, 4 (default) or 8 tiles in flight per warp */
@@ -404,8 +447,10 @@ int tps_create(tps_ctx **out, int device, const tps_params *params) {
     TPS_CC(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
     TPS_CC(cudaMalloc(&s.d_bases, cap_pad));
     TPS_CC(cudaMemset(s.d_bases, 'N', cap_pad));
-    TPS_CC(cudaMalloc(&s.d_codes, ctx->cap_tiles * 32 * sizeof(uint32_t)));
-    TPS_CC(cudaMalloc(&s.d_flags, ctx->cap_tiles * sizeof(uint32_t)));
+    /* + 64 bytes: the bit-parallel K3 prefetches code / flag words in aligned 16-byte chunks */
+    TPS_CC(cudaMalloc(&s.d_codes, ctx->cap_tiles * 32 * sizeof(uint32_t) + 64));
+    TPS_CC(cudaMalloc(&s.d_flags, ctx->cap_tiles * sizeof(uint32_t) + 64));
+    TPS_CC(cudaMemset(s.d_flags, 0, ctx->cap_tiles * sizeof(uint32_t) + 64));
     TPS_CC(cudaMalloc(&s.d_off, ((uint64_t)p.max_batch_reads + 1) * sizeof(uint64_t)));
     TPS_CC(cudaMalloc(&s.d_len, (uint64_t)p.max_batch_reads * sizeof(uint32_t)));
     TPS_CC(cudaMalloc(&s.d_true_len, (uint64_t)p.max_batch_reads * sizeof(uint32_t)));
@@ -414,7 +459,13 @@ int tps_create(tps_ctx **out, int device, const tps_params *params) {
     TPS_CC(cudaMalloc(&s.d_pass, (uint64_t)ctx->max_pass * sizeof(uint32_t)));
     TPS_CC(cudaMalloc(&s.d_counters, 8 * sizeof(uint32_t)));
     if (p.want_rawcount) TPS_CC(cudaMalloc(&s.d_raw, p.rawcount_capacity ? p.rawcount_capacity : 1));
-    TPS_CC(cudaMalloc(&s.d_cw, (uint64_t)ctx->max_pass * ctx->cw_stride * sizeof(uint32_t)));
+    if (ctx->k3_bitpar) { /* c_w rows as uint16 */
+      TPS_CC(cudaMalloc(&s.d_cw, (uint64_t)ctx->max_pass * ctx->cw16_stride * sizeof(uint16_t)));
+      TPS_CC(cudaMalloc(&s.d_tile_done, (uint64_t)ctx->max_pass * sizeof(uint32_t)));
+      TPS_CC(cudaMalloc(&s.d_items, (uint64_t)ctx->max_pass * ctx->k3n_tiles_max * sizeof(TpsTile)));
+    } else {
+      TPS_CC(cudaMalloc(&s.d_cw, (uint64_t)ctx->max_pass * ctx->cw_stride * sizeof(uint32_t)));
+    }
     TPS_CC(cudaHostAlloc(&s.h_rows, (uint64_t)p.max_batch_reads * sizeof(tps_row), cudaHostAllocDefault));
     TPS_CC(cudaHostAlloc(&s.h_counters, 8 * sizeof(uint32_t), cudaHostAllocDefault));
   }
@@ -530,6 +581,13 @@ int enqueue_scan(tps_ctx *ctx, Slot &s, cudaStream_t st, const ScanJob &job) {
   a.tile_bases = ctx->k3_tile_bases;
   a.tiles_max = ctx->k3_tiles_max;
   a.nq_max = ctx->k2_nq_max;
+  a.tile_done = s.d_tile_done;
+  a.items = ctx->k3_bitpar ? s.d_items : nullptr;
+  a.bp_tile_bases = ctx->k3n_tile_bases;
+  a.nz = ctx->k3n_nz;
+  a.cw16 = reinterpret_cast<uint16_t *>(s.d_cw);
+  a.cw16_stride = ctx->cw16_stride;
+  a.cp_cap = ctx->k3n_cp_cap;
   if (n_reads) {
     a.lin_words = ctx->k2_lin_words;
     if (ctx->k2_reg)
@@ -540,11 +598,18 @@ int enqueue_scan(tps_ctx *ctx, Slot &s, cudaStream_t st, const ScanJob &job) {
   }
   if (timed) TPS_CUDA(ctx, cudaEventRecord(ev[2], sh));
   if (n_reads && !(a.flags & TPS_FLAG_STEP1_ONLY)) {
-    a.lin_words = ctx->k3_lin_words;
-    a.tile_words = ctx->k3_tile_words;
-    ctx->k3_fn<<<ctx->k3_grid, TPS_K3_THREADS, ctx->k3_smem, sh>>>(a, ctx->pt);
-    tps_changepoint_kernel<<<ctx->k4_grid, TPS_K4_THREADS, 0, sh>>>(a);
-    ctx->launches += 2;
+    if (ctx->k3_bitpar) { /* window counts and change points in one launch */
+      a.lin_words = ctx->k3n_lin_words;
+      a.tile_words = ctx->k3n_stride;
+      ctx->k3n_fn<<<ctx->k3n_grid, TPS_K3N_THREADS, ctx->k3n_smem, sh>>>(a, ctx->pt);
+      ctx->launches += 1;
+    } else {
+      a.lin_words = ctx->k3_lin_words;
+      a.tile_words = ctx->k3_tile_words;
+      ctx->k3_fn<<<ctx->k3_grid, TPS_K3_THREADS, ctx->k3_smem, sh>>>(a, ctx->pt);
+      tps_changepoint_kernel<<<ctx->k4_grid, TPS_K4_THREADS, 0, sh>>>(a);
+      ctx->launches += 2;
+    }
   }
   if (timed) {
     TPS_CUDA(ctx, cudaEventRecord(ev[3], sh));
@@ -925,6 +990,18 @@ int tps_debug_copy(tps_ctx *ctx, int what, void *dst, size_t bytes) {
       return TPS_OK;
     }
     case 3: src = s.d_pass; cap = (size_t)ctx->max_pass * sizeof(uint32_t); break;
+    case 4:
+      src = s.d_cw;
+      cap = ctx->k3_bitpar ? (size_t)ctx->max_pass * ctx->cw16_stride * sizeof(uint16_t)
+                           : (size_t)ctx->max_pass * ctx->cw_stride * sizeof(uint32_t);
+      break;
+    case 5: { /* geometry: c_w row stride (elements), which K3 is in use, pass capacity, tile size of that K3 */
+      const uint32_t info[4] = {ctx->k3_bitpar ? ctx->cw16_stride : ctx->cw_stride, ctx->k3_bitpar ? 1u : 0u, ctx->max_pass,
+                                ctx->k3_bitpar ? ctx->k3n_tile_bases : ctx->k3_tile_bases};
+      if (bytes > sizeof(info)) return fail(ctx, TPS_EINVAL, "debug info is %zu bytes", sizeof(info));
+      memcpy(dst, info, bytes);
+      return TPS_OK;
+    }
     default: return fail(ctx, TPS_EINVAL, "unknown debug array %d", what);
   }
   if (bytes > cap) return fail(ctx, TPS_EINVAL, "debug copy of %zu bytes exceeds array size %zu", bytes, cap);

@@ -46,7 +46,7 @@ struct TpsPacked {
 };
 
 /* counters[]: [0] n_pass, [1] K3 work cursor, [2,3] rawcount cursor (u64), [4] overflow flags,
- * [5] K4 work cursor */
+ * [5] K4 work cursor, [6] tile items of the bit-parallel K3 */
 #define TPS_OVF_RAWCOUNT 1u
 #define TPS_OVF_PASS 2u
 
@@ -72,6 +72,27 @@ struct TpsScanArgs {
   uint32_t tile_bases; /* K3: window-start positions per tile */
   uint32_t tiles_max;  /* K3: tiles per read at the longest region */
   uint32_t nq_max;     /* K2: ceil(no_bp/32) */
+  /* bit-parallel K3 (tps_window_bp_kernel): K2 appends one TpsTile record per tile of every TRC-pass read with
+   * at least 7 windows to `items` (counters[6] = number of records) and zeroes the read's entry of
+   * `tile_done`, the tiles finished so far; c_w is kept as uint16 at cw16 + slot * cw16_stride */
+  uint32_t *tile_done;
+  struct TpsTile *items;
+  uint32_t bp_tile_bases; /* window-start positions per tile (a multiple of 32) */
+  uint32_t nz;            /* count planes, 2^nz > P */
+  uint16_t *cw16;
+  uint32_t cw16_stride;   /* a multiple of 8: rows start on 16-byte boundaries */
+  uint32_t cp_cap;        /* windows of one read that fit the kernel's shared-memory scratch as uint16 */
+};
+
+/* One work item of the bit-parallel K3: everything a CTA needs to stage and count one tile, worked out once by
+ * K2 (which knows the read's start, length and orientation) so that the tile loop starts with one 32-byte load. */
+struct __align__(16) TpsTile {
+  uint64_t g0;     /* first base of the staged slice in the batch */
+  uint32_t tn;     /* staged oriented positions (tile + W-base halo, clipped to the region) */
+  uint32_t tb0;    /* oriented position of the tile's first window-start position */
+  uint32_t wlo, whi; /* windows whose start lies in the tile */
+  uint32_t pi_rev; /* pass-list slot | reverse << 31 */
+  uint32_t ntiles; /* tiles of this read */
 };
 
 /* ------------------------------------------------------------------------------------ K1 */
@@ -448,9 +469,9 @@ __device__ __forceinline__ void tps_row_init(tps_row &row, uint32_t true_len) {
 
 /* Tail decision, cutoff test and (lane 0) the append to the pass list, from the first-max counts of the two
  * ends: ms / ps of seq[:no_bp], me / pe of the reversed seq[-no_bp:] (allsteps.py:190-198). */
-__device__ __forceinline__ void tps_trc_decide(const TpsScanArgs &a, uint32_t n_patterns, uint32_t r, uint32_t Lt,
-                                               uint32_t lane, uint32_t ms, uint32_t ps, uint32_t me, uint32_t pe,
-                                               tps_row &row) {
+__device__ __forceinline__ void tps_trc_decide(const TpsScanArgs &a, uint32_t n_patterns, uint32_t r, uint64_t off,
+                                               uint32_t L, uint32_t Lt, uint32_t lane, uint32_t ms, uint32_t ps,
+                                               uint32_t me, uint32_t pe, tps_row &row) {
   bool fwd = ms > me; /* tie -> reverse, allsteps.py:193-198 */
   if (a.flags & TPS_FLAG_FORCE_FORWARD) fwd = true; /* caller-chosen tail, allsteps.py:294-297 */
   if (a.flags & TPS_FLAG_FORCE_REVERSE) fwd = false;
@@ -468,9 +489,31 @@ __device__ __forceinline__ void tps_trc_decide(const TpsScanArgs &a, uint32_t n_
     const uint32_t nreg = M > a.trimfirst ? M - a.trimfirst : 0u;
     const uint32_t nW = nreg >= a.W ? (nreg - a.W) / a.slide + 1u : 0u;
     row.n_windows = nW;
+    if (nW < 7u) row.status = TPS_ST_BADSEG; /* ruptures' sanity_check: jump 5, min_size 2, one breakpoint need n >= 7 */
     const uint32_t slot = atomicAdd(a.counters + 0, 1u);
     if (slot < a.max_pass) {
       a.pass_list[slot] = r;
+      if (a.items && nW >= 7u) { /* the tiles of this read's region (balanced), as consecutive work items */
+        const uint32_t nt0 = (nreg + a.bp_tile_bases - 1u) / a.bp_tile_bases;
+        const uint32_t tsize = ((nreg + nt0 - 1u) / nt0 + 31u) & ~31u; /* <= bp_tile_bases */
+        uint32_t nt = 0; /* tiles that hold a window start: 1 .. nt0, always a prefix */
+        while (nt < nt0 && (nt * tsize + a.slide - 1u) / a.slide < nW) ++nt;
+        uint32_t at = atomicAdd(a.counters + 6, nt);
+        for (uint32_t ti = 0; ti < nt; ++ti, ++at) {
+          TpsTile tl;
+          tl.tb0 = ti * tsize;
+          tl.tn = tsize + a.W < nreg - tl.tb0 ? tsize + a.W : nreg - tl.tb0; /* a window reaches W-2 past its start */
+          /* forward: read bases [off+t+tb0, +tn); reverse: region position j is read index L-1-(t+j) */
+          tl.g0 = fwd ? off + a.trimfirst + tl.tb0 : off + L - a.trimfirst - tl.tb0 - tl.tn;
+          tl.wlo = (tl.tb0 + a.slide - 1u) / a.slide;
+          tl.whi = (tl.tb0 + tsize + a.slide - 1u) / a.slide;
+          if (tl.whi > nW) tl.whi = nW;
+          tl.pi_rev = slot | (fwd ? 0u : 0x80000000u);
+          tl.ntiles = nt;
+          a.items[at] = tl;
+        }
+        a.tile_done[slot] = 0u;
+      }
       if (a.want_rawcount && nW) {
         const unsigned long long elems = (unsigned long long)nW * n_patterns;
         const unsigned long long at = atomicAdd(reinterpret_cast<unsigned long long *>(a.counters + 2), elems);
@@ -565,7 +608,7 @@ tps_trc_kernel(const TpsScanArgs a, const TpsPatTable pt) {
     uint32_t ms, ps, me, pe;
     tps_trc_end<K>(a, pt, pm, off, n, false, lin, mrows, cnts, lane, ms, ps);         /* seq[:no_bp] */
     tps_trc_end<K>(a, pt, pm, off + L - n, n, true, lin, mrows, cnts, lane, me, pe);  /* seq[-no_bp:][::-1] */
-    tps_trc_decide(a, pt.n, r, Lt, lane, ms, ps, me, pe, row);
+    tps_trc_decide(a, pt.n, r, off, L, Lt, lane, ms, ps, me, pe, row);
   }
   if (lane == 0) a.rows[r] = row;
 }
@@ -720,7 +763,7 @@ tps_trc_reg_kernel(const TpsScanArgs a, const TpsPatTable pt) {
     uint32_t ms, ps, me, pe;
     tps_trc_end_reg<K>(a, pt, pm, off, n, false, mrows, lane, ms, ps);         /* seq[:no_bp] */
     tps_trc_end_reg<K>(a, pt, pm, off + L - n, n, true, mrows, lane, me, pe);  /* seq[-no_bp:][::-1] */
-    tps_trc_decide(a, pt.n, r, Lt, lane, ms, ps, me, pe, row);
+    tps_trc_decide(a, pt.n, r, off, L, Lt, lane, ms, ps, me, pe, row);
   }
   if (lane == 0) a.rows[r] = row;
 }
@@ -929,19 +972,145 @@ tps_window_kernel(const TpsScanArgs a, const TpsPatTable pt) {
 /* ------------------------------------------------------------------------------------ K4 */
 #define TPS_K4_THREADS 128
 
-/* One CTA per passing read: single change point of c_w, the exact form of ruptures
+/* Single change point of c_w[0..n) by one CTA of TPS_K4_THREADS threads, the exact form of ruptures
  * Binseg(model="l2", jump=5, min_size=2).predict(n_bkps=1):
  * argmax over b in {5,10,...}, 2 <= b <= n-2 of (n*S_b - b*T)^2 / (b*(n-b)), ties -> larger b.
- * Thread i of a 640-window chunk owns the candidate b = chunk + 5i and the five windows behind it;
- * S_b comes from a block-wide exclusive scan of those group sums, the argmax from the exact
- * 128-bit comparator (warp shuffles, then one shared-memory round across the four warps). */
+ * Every thread owns one run of `chunk` consecutive windows (chunk a multiple of 5, so every candidate's S_b is a
+ * running sum inside one thread):
+ *   pass 1  sums the run; one block-wide exclusive scan turns the run sums into S at the run starts and T;
+ *   pass 2  walks the run's candidates with a float32 SCREEN of the gain (relative error < 1e-6) and keeps the
+ *           thread's largest; a block-wide max gives G;
+ *   pass 3  only threads whose screen value reaches G * (1 - 1e-4) walk their run again and put every candidate
+ *           above that bar through the exact comparator (float64 cross-multiplication, 128-bit integers for
+ *           ties and near-ties); their winners go to a short shared list that thread 0 reduces.
+ * Any candidate that can be the exact argmax passes the screen, so the result is the exact one; the screen only
+ * spares the other ~99 % of the candidates the 64-bit arithmetic.  A constant signal (every gain 0) sends every
+ * candidate to pass 3, which is the old cost.  c_w comes through a reader (global rows are read with
+ * ld.global.cg: in the fused kernel other CTAs wrote them).  Result valid in thread 0. */
+struct TpsCpShared {
+  uint64_t wsum[TPS_K4_THREADS / 32];
+  float wmax[TPS_K4_THREADS / 32];
+  uint32_t n_cand;
+  tps_cand cand[TPS_K4_THREADS];
+};
+
+/* c_w readers: uint32 in global memory (tps_window_kernel's rows), uint16 in global memory (rows of the
+ * bit-parallel kernel that do not fit its scratch) or uint16 staged in shared memory */
+struct TpsCwGlobal32 {
+  const uint32_t *p;
+  __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return __ldcg(p + i); }
+};
+struct TpsCwGlobal16 {
+  const uint16_t *p;
+  __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return __ldcg(p + i); }
+};
+struct TpsCwShared16 {
+  const uint16_t *p;
+  __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return p[i]; }
+};
+template <class RD>
+__device__ __forceinline__ uint32_t tps_cw5(const RD &cw, uint32_t i) {
+  return cw(i) + cw(i + 1u) + cw(i + 2u) + cw(i + 3u) + cw(i + 4u);
+}
+
+__device__ __forceinline__ float tps_gain_screen(uint32_t n, uint64_t S, uint64_t T, uint32_t b) {
+  const float d = (float)((int64_t)((uint64_t)n * S) - (int64_t)((uint64_t)b * T));
+  return d * d * __frcp_rn((float)b * (float)(n - b));
+}
+
+template <class RD>
+__device__ __forceinline__ int32_t tps_changepoint_block(const RD cw, uint32_t n, TpsCpShared &sh, uint32_t tid) {
+  constexpr uint32_t NWARP = TPS_K4_THREADS / 32;
+  const uint32_t lane = tid & 31u, warp = tid >> 5;
+  const uint32_t chunk = 5u * ((n + 5u * TPS_K4_THREADS - 1u) / (5u * TPS_K4_THREADS));
+  const uint32_t w0 = tid * chunk < n ? tid * chunk : n;
+  const uint32_t w1 = n - w0 < chunk ? n : w0 + chunk;
+  uint64_t sum = 0;
+  {
+    uint32_t w = w0;
+    for (; w + 5u <= w1; w += 5u) sum += tps_cw5(cw, w);
+    for (; w < w1; ++w) sum += cw(w);
+  }
+  uint64_t inc = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint64_t up = __shfl_up_sync(TPS_FULL, inc, o);
+    if ((int)lane >= o) inc += up;
+  }
+  if (lane == 31u) sh.wsum[warp] = inc;
+  if (tid == 0) sh.n_cand = 0u;
+  __syncthreads();
+  uint64_t S0 = inc - sum, T = 0; /* S0 = sum_{w < w0} c_w */
+#pragma unroll
+  for (uint32_t i = 0; i < NWARP; ++i) {
+    if (i < warp) S0 += sh.wsum[i];
+    T += sh.wsum[i];
+  }
+  /* pass 2: float32 screen */
+  float gmax = -1.0f;
+  {
+    uint64_t S = S0;
+    for (uint32_t b = w0; b < w1; b += 5u) {
+      if (b >= 2u && n - b >= 2u) gmax = fmaxf(gmax, tps_gain_screen(n, S, T, b));
+      if (b + 5u <= w1) S += tps_cw5(cw, b);
+    }
+  }
+  float G = gmax;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) G = fmaxf(G, __shfl_xor_sync(TPS_FULL, G, o));
+  if (lane == 0) sh.wmax[warp] = G;
+  __syncthreads();
+#pragma unroll
+  for (uint32_t i = 0; i < NWARP; ++i) G = fmaxf(G, sh.wmax[i]);
+  const float bar = G * (1.0f - 1e-4f); /* G >= 0 whenever a candidate exists */
+  /* pass 3: exact comparison of the candidates at the top */
+  if (gmax >= bar && gmax >= 0.0f) {
+    tps_cand best;
+    best.b = -1; best.d = 0; best.den = 1; best.num_f = 0.0; best.den_f = 1.0;
+    uint64_t S = S0;
+    for (uint32_t b = w0; b < w1; b += 5u) {
+      if (b >= 2u && n - b >= 2u && tps_gain_screen(n, S, T, b) >= bar) {
+        const tps_cand c = tps_make_cand(n, S, T, b);
+        if (tps_cand_better(&best, &c)) best = c;
+      }
+      if (b + 5u <= w1) S += tps_cw5(cw, b);
+    }
+    if (best.b >= 0) sh.cand[atomicAdd(&sh.n_cand, 1u)] = best;
+  }
+  __syncthreads();
+  int32_t best_b = -1;
+  if (tid == 0) {
+    const uint32_t nc = sh.n_cand;
+    if (nc) {
+      tps_cand best = sh.cand[0];
+      for (uint32_t i = 1; i < nc; ++i) {
+        const tps_cand oth = sh.cand[i];
+        if (tps_cand_better(&best, &oth)) best = oth;
+      }
+      best_b = best.b;
+    }
+  }
+  return best_b;
+}
+
+/* Thread 0 stores the change point of read r (x[bkp] = trimfirst + slide * b, allsteps.py:304,312), or marks the
+ * read TPS_ST_BADSEG: ruptures' sanity_check needs n >= 7 for jump 5, min_size 2, one breakpoint. */
+__device__ __forceinline__ void tps_store_changepoint(const TpsScanArgs &a, uint32_t r, int32_t best_b) {
+  tps_row *row = a.rows + r;
+  if (best_b >= 0) {
+    row->bkp = best_b;
+    row->telo_length = (int32_t)(a.trimfirst + a.slide * (uint32_t)best_b);
+  } else {
+    row->status = TPS_ST_BADSEG;
+  }
+}
+
+/* Stand-alone K4 (behind tps_window_kernel): persistent CTAs, one passing read at a time. */
 __global__ void __launch_bounds__(TPS_K4_THREADS)
 tps_changepoint_kernel(const TpsScanArgs a) {
-  __shared__ uint64_t s_warp[TPS_K4_THREADS / 32];
-  __shared__ tps_cand s_cand[TPS_K4_THREADS / 32];
+  __shared__ TpsCpShared s_cp;
   __shared__ uint32_t s_pi;
-  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-  constexpr uint32_t NWARP = TPS_K4_THREADS / 32;
+  const uint32_t tid = threadIdx.x;
   uint32_t n_pass = a.counters[0];
   if (n_pass > a.max_pass) n_pass = a.max_pass;
   for (;;) {
@@ -952,82 +1121,410 @@ tps_changepoint_kernel(const TpsScanArgs a) {
     if (pi >= n_pass) break;
     const uint32_t r = a.pass_list[pi];
     const uint32_t nW = a.rows[r].n_windows;
-    const uint32_t *cw = a.cw + (size_t)pi * a.cw_stride;
     int32_t best_b = -1;
-    if (nW >= 7u) { /* ruptures sanity_check: n >= 7 for jump 5, min_size 2, one breakpoint */
-      /* T = sum of all c_w */
-      uint64_t T = 0;
-      for (uint32_t w = tid; w < nW; w += TPS_K4_THREADS) T += cw[w];
+    if (nW >= 7u) best_b = tps_changepoint_block(TpsCwGlobal32{a.cw + (size_t)pi * a.cw_stride}, nW, s_cp, tid);
+    if (tid == 0) tps_store_changepoint(a, r, best_b);
+  }
+}
+
+/* ------------------------------------------------------------------- K3 + K4, bit-parallel (default)
+ * tps_window_bp_kernel<K>: the window counts of step 2 without a per-(window, literal) loop, and the change
+ * point of a read by the CTA that finishes its last tile.
+ *
+ *   c_w = sum_p max(cnt_p(w), 1) = occ_U(w) + #{p : cnt_p(w) == 0}         (allsteps.py:279-291, `... or 1`)
+ *
+ * The literals of one scan are distinct strings of one length K, so at most one of them matches at a position:
+ * the sum of the occurrence counts is the number of set bits of the UNION row U = OR_p m_p inside the window's
+ * D = W - K start positions, one prefix-popcount difference per window instead of P.  Whether literal p occurs in
+ * a window at all is bit j of the dilated row R_p[j] = OR_{d<D} m_p[j+d]; with S = "bits at or below the highest
+ * set bit" and Pf = "bits above the lowest set bit" of a match word (one FLO / one negate each),
+ * x32[q] = S[q] | Pf[q+1] is the 32-dilation, and R[q] = x32[q] | .. | x32[q+a-1] | funnel(x32[q+a-1], x32[q+a], r)
+ * for D = 32a + r.  The P rows R_p are added bit-sliced (carry-save adders, 2 LOP3 each) into `nz` count planes,
+ * 32 positions per instruction; a window reads its count of present literals off the planes at its start bit.
+ * Self-overlapping literals (greedy != occurrences): CF marks starts that have another start of the same literal
+ * less than K ahead; a window without such a start inside is exact as it stands, the few others redo those
+ * literals with the greedy walk.
+ *
+ * Work item = (passing read, tile), listed by K2 (no empty items); the next item is fetched while the current
+ * one is processed.  A tile is <= 32 * TPS_K3N_THREADS oriented positions incl. the W-base halo, one 32-position
+ * word per thread; the tiles of a read are balanced.  The CTA that completes a read's last tile (per-read
+ * counter) runs tps_changepoint_block on the read's c_w: no second launch, and the change points overlap the
+ * window counting of other reads.
+ *
+ * dynamic shared memory (words): pm[2PK] | lin[3*lin_words] | ori[3*(NT+1)] | pad to 16 B | Z[NT] uint4 |
+ * Zhi[NT] uint4 (nz > 4) | UP[NT] uint2 | CP[NT] uint2 (bordered) | SP[P4][sp_stride] uint2 {S, Pf}, P4 = P rounded
+ * up to a multiple of 4 | brows[n_bordered][NT+1] */
+#define TPS_K3N_THREADS 128
+
+#define TPS_CSA(h, l, x, y, z)                       \
+  do {                                               \
+    const uint32_t x_ = (x), y_ = (y), z_ = (z);     \
+    (h) = (x_ & y_) | (x_ & z_) | (y_ & z_);         \
+    (l) = x_ ^ y_ ^ z_;                              \
+  } while (0)
+
+__device__ __forceinline__ uint32_t tps_block_excl_scan(uint32_t v, uint32_t *wt, uint32_t tid) {
+  const uint32_t lane = tid & 31u, warp = tid >> 5;
+  uint32_t inc = v;
 #pragma unroll
-      for (int o = 16; o; o >>= 1) T += __shfl_xor_sync(TPS_FULL, T, o);
-      if (lane == 0) s_warp[warp] = T;
-      __syncthreads();
-      T = 0;
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t up = __shfl_up_sync(TPS_FULL, inc, o);
+    if ((int)lane >= o) inc += up;
+  }
+  if (lane == 31u) wt[warp] = inc;
+  __syncthreads();
+  uint32_t before = inc - v;
 #pragma unroll
-      for (uint32_t i = 0; i < NWARP; ++i) T += s_warp[i];
-      __syncthreads();
-      tps_cand best;
-      best.b = -1; best.d = 0; best.den = 1; best.num_f = 0.0; best.den_f = 1.0;
-      uint64_t carry = 0; /* sum of c_w over the windows before this chunk */
-      for (uint32_t base = 0; base < nW; base += 5u * TPS_K4_THREADS) {
-        const uint32_t b = base + 5u * tid;
-        uint64_t g = 0;
-#pragma unroll
-        for (uint32_t i = 0; i < 5u; ++i)
-          if (b + i < nW) g += cw[b + i];
-        uint64_t inc = g;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const uint64_t up = __shfl_up_sync(TPS_FULL, inc, o);
-          if ((int)lane >= o) inc += up;
-        }
-        if (lane == 31u) s_warp[warp] = inc;
-        __syncthreads();
-        uint64_t before = carry, chunk = 0;
-#pragma unroll
-        for (uint32_t i = 0; i < NWARP; ++i) {
-          if (i < warp) before += s_warp[i];
-          chunk += s_warp[i];
-        }
-        __syncthreads();
-        const uint64_t S_b = before + inc - g; /* exclusive prefix = sum_{w<b} c_w */
-        if (b >= 2u && b < nW && nW - b >= 2u) {
-          const tps_cand c = tps_make_cand(nW, S_b, T, b);
-          if (tps_cand_better(&best, &c)) best = c;
-        }
-        carry += chunk;
-      }
-      /* warp argmax with the exact comparator (ties -> larger b) */
-#pragma unroll
-      for (int o = 16; o; o >>= 1) {
-        tps_cand oth;
-        oth.d = __shfl_xor_sync(TPS_FULL, best.d, o);
-        oth.den = __shfl_xor_sync(TPS_FULL, best.den, o);
-        oth.num_f = __shfl_xor_sync(TPS_FULL, best.num_f, o);
-        oth.den_f = __shfl_xor_sync(TPS_FULL, best.den_f, o);
-        oth.b = __shfl_xor_sync(TPS_FULL, best.b, o);
-        if (tps_cand_better(&best, &oth)) best = oth;
-      }
-      if (lane == 0) s_cand[warp] = best;
-      __syncthreads();
-      if (tid == 0) {
-        for (uint32_t i = 1; i < NWARP; ++i) {
-          const tps_cand oth = s_cand[i];
-          if (tps_cand_better(&best, &oth)) best = oth;
-        }
-        best_b = best.b;
-      }
+  for (uint32_t i = 0; i < TPS_K3N_THREADS / 32; ++i)
+    if (i < warp) before += wt[i];
+  return before;
+}
+
+/* R[q] of one literal from its {S, Pf} slots q, q+1, ...: MODE 1: D = 32 + dr (dr > 0), MODE 2: D = 32 da,
+ * MODE 3: D = 96, MODE 0: any D >= 32 */
+template <int MODE>
+__device__ __forceinline__ uint32_t tps_dilate(const uint2 *__restrict__ sp, uint32_t da, uint32_t dr) {
+  if constexpr (MODE == 1) {
+    const uint2 s0 = sp[0], s1 = sp[1], s2 = sp[2];
+    const uint32_t x0 = s0.x | s1.y, x1 = s1.x | s2.y;
+    return x0 | __funnelshift_r(x0, x1, dr);
+  } else if constexpr (MODE == 3) {
+    const uint2 s0 = sp[0], s1 = sp[1], s2 = sp[2], s3 = sp[3];
+    return (s0.x | s1.x | s1.y) | (s2.x | s2.y | s3.y);
+  } else if constexpr (MODE == 2) {
+    uint2 v = sp[0];
+    uint32_t acc = v.x;
+    for (uint32_t j = 1; j < da; ++j) {
+      v = sp[j];
+      acc |= v.x | v.y;
     }
-    if (tid == 0) {
-      tps_row *row = a.rows + r;
-      if (best_b >= 0) {
-        row->bkp = best_b;
-        row->telo_length = (int32_t)(a.trimfirst + a.slide * (uint32_t)best_b); /* x[bkp], allsteps.py:304,312 */
-      } else {
-        row->status = TPS_ST_BADSEG;
-      }
+    return acc | sp[da].y;
+  } else {
+    uint2 s0 = sp[0], s1 = sp[1];
+    uint32_t xi = s0.x | s1.y, acc = xi;
+    for (uint32_t j = 1; j < da; ++j) {
+      s0 = s1;
+      s1 = sp[j + 1u];
+      xi = s0.x | s1.y;
+      acc |= xi;
+    }
+    if (dr) {
+      s0 = s1;
+      s1 = sp[da + 1u];
+      acc |= __funnelshift_r(xi, s0.x | s1.y, dr);
+    }
+    return acc;
+  }
+}
+
+/* count planes of word q: the P presence rows added bit-sliced, four at a time; plane i is stored rotated left
+ * by i so that a window's count is four rotates and three bit-selects */
+template <int MODE>
+__device__ __forceinline__ void tps_presence_planes(const uint2 *__restrict__ sp, uint32_t P4, uint32_t stride,
+                                                    uint32_t da, uint32_t dr, uint32_t nz, uint4 *zlo, uint4 *zhi) {
+  uint32_t c1 = 0u, c2 = 0u, c4 = 0u, c8 = 0u, c16 = 0u, c32 = 0u, c64 = 0u;
+  for (uint32_t pb = 0; pb < P4; pb += 4u) {
+    const uint32_t r0 = tps_dilate<MODE>(sp, da, dr);
+    const uint32_t r1 = tps_dilate<MODE>(sp + stride, da, dr);
+    const uint32_t r2 = tps_dilate<MODE>(sp + 2u * stride, da, dr);
+    const uint32_t r3 = tps_dilate<MODE>(sp + 3u * stride, da, dr);
+    sp += 4u * stride;
+    uint32_t ta, tb, fa;
+    TPS_CSA(ta, c1, c1, r0, r1);
+    TPS_CSA(tb, c1, c1, r2, r3);
+    TPS_CSA(fa, c2, c2, ta, tb);
+    uint32_t cy = c4 & fa; /* ripple the fours */
+    c4 ^= fa;
+    if (nz > 4u) {
+      uint32_t t = c8 & cy;
+      c8 ^= cy;
+      cy = c16 & t; c16 ^= t;
+      t = c32 & cy; c32 ^= cy;
+      c64 ^= t;
+    } else {
+      c8 ^= cy;
     }
   }
+  *zlo = make_uint4(c1, __funnelshift_l(c2, c2, 1), __funnelshift_l(c4, c4, 2), __funnelshift_l(c8, c8, 3));
+  if (nz > 4u) *zhi = make_uint4(__funnelshift_l(c16, c16, 4), __funnelshift_l(c32, c32, 5), __funnelshift_l(c64, c64, 6), 0u);
+}
+
+__device__ __forceinline__ void tps_cp_async16(void *smem_dst, const void *gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tps_smem_addr(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void tps_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+/* raw code / flag words of one tile, prefetched into shared memory one tile ahead */
+#define TPS_K3N_RAW_CODE_WORDS 272 /* 258 groups of a 4096-position slice at any phase + alignment to 16 bytes */
+#define TPS_K3N_RAW_FLAG_WORDS 16
+#define TPS_K3N_RAW_WORDS (TPS_K3N_RAW_CODE_WORDS + TPS_K3N_RAW_FLAG_WORDS)
+
+/* issue the asynchronous copies of the code and flag words that cover bases [g0, g0 + n) */
+__device__ __forceinline__ void tps_prefetch_codes(const TpsPacked &pk, uint64_t g0, uint32_t n, uint32_t *raw,
+                                                   uint32_t tid) {
+  const uint64_t gfirst = g0 >> 4, glast = (g0 + n + 15u) >> 4; /* groups [gfirst, glast) */
+  const uint64_t w0 = gfirst & ~3ull;                            /* code words, 16-byte aligned */
+  const uint32_t nchunk = (uint32_t)((glast - w0 + 3u) >> 2);
+  if (tid < nchunk) tps_cp_async16(raw + 4u * tid, pk.codes + w0 + 4u * tid);
+  const uint64_t f0 = (gfirst >> 5) & ~3ull; /* flag words */
+  const uint32_t nf = (uint32_t)((((glast + 31u) >> 5) - f0 + 3u) >> 2);
+  if (tid >= 96u && tid - 96u < nf) tps_cp_async16(raw + TPS_K3N_RAW_CODE_WORDS + 4u * (tid - 96u), pk.flags + f0 + 4u * (tid - 96u));
+}
+
+/* tps_stage_linear from the prefetched words */
+__device__ __forceinline__ void tps_stage_linear_raw(const uint32_t *raw, const uint8_t *__restrict__ bases, uint64_t g0,
+                                                     uint32_t n, uint32_t *lin, uint32_t lw, uint32_t tid,
+                                                     uint32_t nthreads) {
+  uint16_t *l0 = reinterpret_cast<uint16_t *>(lin);
+  uint16_t *l1 = reinterpret_cast<uint16_t *>(lin + lw);
+  uint16_t *lv = reinterpret_cast<uint16_t *>(lin + 2 * lw);
+  const uint64_t gfirst = g0 >> 4;
+  const uint32_t ng = n ? (uint32_t)(((g0 + n + 15) >> 4) - gfirst) : 0u;
+  const uint32_t cskew = (uint32_t)(gfirst & 3ull);
+  const uint64_t f0 = (gfirst >> 5) & ~3ull;
+  for (uint32_t i = tid; i < 2 * lw; i += nthreads) {
+    if (i < 2 || i >= 2 + ng) {
+      l0[i] = 0;
+      l1[i] = 0;
+      lv[i] = 0;
+    } else {
+      const uint64_t g = gfirst + (i - 2);
+      const uint32_t y = tps_linear_planes(raw[cskew + (i - 2)]);
+      uint32_t v = 0xFFFFu;
+      if ((raw[TPS_K3N_RAW_CODE_WORDS + (uint32_t)((g >> 5) - f0)] >> (g & 31)) & 1u) { /* rare: N, IUPAC */
+        const uint4 b = __ldg(reinterpret_cast<const uint4 *>(bases) + g);
+        v = tps_exact_mask16_simd(b.x, b.y, b.z, b.w);
+      }
+      l0[i] = (uint16_t)(y & 0xFFFFu);
+      l1[i] = (uint16_t)(y >> 16);
+      lv[i] = (uint16_t)v;
+    }
+  }
+}
+
+template <int K>
+__global__ void __launch_bounds__(TPS_K3N_THREADS)
+tps_window_bp_kernel(const TpsScanArgs a, const TpsPatTable pt) {
+  static_assert(K > 0, "the bit-parallel window kernel needs a common literal length");
+  constexpr uint32_t NT = TPS_K3N_THREADS;
+  extern __shared__ __align__(16) uint32_t smem[];
+  /* software pipeline over work items: at the top of iteration k the records of items k and k+1, the code words
+   * of item k and the index of item k+2 are in shared memory; the iteration issues the copies of the code words
+   * of item k+1 and of the record of item k+2 (cp.async) and the atomic for the index of item k+3, and collects
+   * them at its end -- the tile loop never waits for global memory */
+  __shared__ TpsTile s_rec[3];
+  __shared__ uint32_t s_idx[4];
+  __shared__ uint32_t s_cp_pi, s_cp_go, s_pend_pi, s_pend_target;
+  __shared__ uint32_t s_wt[2][NT / 32];
+  __shared__ TpsCpShared s_cp;
+  const uint32_t tid = threadIdx.x, q = threadIdx.x;
+  const uint32_t P = pt.n, P4 = (P + 3u) & ~3u, lw = a.lin_words, stride = a.tile_words, nb = pt.n_bordered;
+  const uint32_t W = a.W, s = a.slide;
+  const uint32_t D = W - (uint32_t)K, da = D >> 5, dr = D & 31u, nz = a.nz;
+  const uint32_t mode = (da == 1u && dr) ? 1u : (dr ? 0u : (da == 3u ? 3u : 2u));
+  uint32_t *raw = smem; /* two buffers of TPS_K3N_RAW_WORDS */
+  uint2 *pm = reinterpret_cast<uint2 *>(smem + 2u * TPS_K3N_RAW_WORDS);
+  uint32_t *scratch = smem + 2u * TPS_K3N_RAW_WORDS + 2u * P * K; /* everything behind is free between tiles */
+  scratch += (4u - ((uint32_t)(scratch - smem) & 3u)) & 3u;
+  uint32_t *lin = scratch;
+  uint32_t *ori = lin + 3u * lw;
+  uint32_t *al = ori + 3u * (NT + 1u);
+  al += (4u - ((uint32_t)(al - smem) & 3u)) & 3u;
+  uint4 *Z = reinterpret_cast<uint4 *>(al);
+  uint4 *Zhi = Z + NT;
+  uint2 *UP = reinterpret_cast<uint2 *>(Zhi + (nz > 4u ? NT : 0u));
+  uint2 *CP = UP + NT;
+  uint2 *SP = CP + (nb ? NT : 0u);
+  uint32_t *brows = reinterpret_cast<uint32_t *>(SP + (size_t)P4 * stride);
+  tps_build_pattern_masks(pm, pt, K, tid, NT);
+  const uint32_t n_items = a.counters[6];
+
+  /* words that must read zero: the pad word behind the oriented planes, the slots of SP behind the tile and of
+   * the rows that pad P to a multiple of 4, the pad word of the plain rows.  The change point of a read borrows
+   * the scratch, so this is redone after every one of them. */
+  auto clear_scratch = [&]() {
+    if (tid < 3u) ori[tid * (NT + 1u) + NT] = 0u;
+    for (uint32_t i = tid; i < P4 * stride; i += NT) SP[i] = make_uint2(0u, 0u);
+    for (uint32_t i = tid; i < nb * (NT + 1u); i += NT) brows[i] = 0u;
+  };
+  /* change point of the read in pass-list slot pi (all of its tiles are done and visible) */
+  auto change_point = [&](uint32_t pi) {
+    const uint32_t r = a.pass_list[pi];
+    const uint32_t nW = a.rows[r].n_windows;
+    const uint16_t *cw = a.cw16 + (size_t)pi * a.cw16_stride;
+    int32_t best_b;
+    if (nW <= a.cp_cap) { /* stage the row: one round trip, then shared memory only */
+      uint16_t *sc = reinterpret_cast<uint16_t *>(scratch);
+      for (uint32_t i = tid; i < (nW + 7u) >> 3; i += NT) tps_cp_async16(sc + 8u * i, cw + 8u * i);
+      tps_cp_async_wait_all();
+      __syncthreads();
+      best_b = tps_changepoint_block(TpsCwShared16{sc}, nW, s_cp, tid);
+      __syncthreads();
+      clear_scratch();
+    } else {
+      best_b = tps_changepoint_block(TpsCwGlobal16{cw}, nW, s_cp, tid);
+    }
+    if (tid == 0) tps_store_changepoint(a, r, best_b);
+  };
+
+  clear_scratch();
+  if (tid == 0) {
+    const uint32_t base = atomicAdd(a.counters + 1, 3u);
+    s_idx[0] = base; s_idx[1] = base + 1u; s_idx[2] = base + 2u;
+    if (base < n_items) s_rec[0] = a.items[base];
+    if (base + 1u < n_items) s_rec[1] = a.items[base + 1u];
+  }
+  __syncthreads();
+  if (s_idx[0] < n_items) tps_prefetch_codes(a.pk, s_rec[0].g0, s_rec[0].tn, raw, tid);
+  tps_cp_async_wait_all();
+  __syncthreads();
+  uint32_t pend_old = 0u;  /* thread 0: result of the completion atomic of the previous tile */
+  bool has_pend = false;
+
+  for (uint32_t k = 0;; ++k) {
+    if (s_idx[k & 3u] >= n_items) break;
+    const TpsTile rec = s_rec[k % 3u];
+    uint32_t *rawk = raw + (k & 1u) * TPS_K3N_RAW_WORDS;
+    /* prefetches for the next iterations */
+    if (s_idx[(k + 1u) & 3u] < n_items) {
+      const TpsTile &nx = s_rec[(k + 1u) % 3u];
+      tps_prefetch_codes(a.pk, nx.g0, nx.tn, raw + ((k + 1u) & 1u) * TPS_K3N_RAW_WORDS, tid);
+    }
+    uint32_t next_idx = 0u;
+    if (tid == 0) {
+      const uint32_t i2 = s_idx[(k + 2u) & 3u];
+      if (i2 < n_items) {
+        tps_cp_async16(&s_rec[(k + 2u) % 3u], a.items + i2);
+        tps_cp_async16(reinterpret_cast<uint8_t *>(&s_rec[(k + 2u) % 3u]) + 16, reinterpret_cast<const uint8_t *>(a.items + i2) + 16);
+      }
+      next_idx = atomicAdd(a.counters + 1, 1u);
+    }
+    const uint32_t pi = rec.pi_rev & 0x7FFFFFFFu, tb0 = rec.tb0, tn = rec.tn;
+    const bool rev = rec.pi_rev >> 31;
+    uint16_t *cw = a.cw16 + (size_t)pi * a.cw16_stride;
+    {
+      const uint32_t phase = (uint32_t)(rec.g0 & 15u);
+      tps_stage_linear_raw(rawk, a.pk.bases, rec.g0, tn, lin, lw, tid, NT);
+      __syncthreads();
+      {
+        uint32_t p0, p1, v;
+        tps_oriented_word(lin, lw, phase, tn, rev, q, p0, p1, v);
+        ori[q] = p0;
+        ori[(NT + 1u) + q] = p1;
+        ori[2u * (NT + 1u) + q] = v;
+      }
+      __syncthreads();
+      /* (1) match words of word q: union, {S, Pf} halves of the 32-dilation, plain rows of bordered literals */
+      uint32_t U = 0u;
+      {
+        TpsWin<K> win;
+        tps_win_init<K>(win, ori[q], ori[q + 1u], ori[(NT + 1u) + q], ori[(NT + 1u) + q + 1u], ori[2u * (NT + 1u) + q],
+                        ori[2u * (NT + 1u) + q + 1u]);
+        auto halves = [](uint32_t m) { /* bits at or below the highest match | bits above the lowest match */
+          return make_uint2(__funnelshift_rc(TPS_FULL, 0u, (uint32_t)__clz((int)m)), (m | (0u - m)) << 1);
+        };
+        uint2 *sp = SP + q;
+        if (pt.paired) {
+          const uint32_t H = P >> 1;
+          uint2 *spc = sp + (size_t)H * stride;
+          for (uint32_t p = 0; p < H; ++p, sp += stride, spc += stride) {
+            uint32_t m, mc;
+            tps_win_match_pair<K>(win, pm, p, m, mc);
+            U |= m | mc;
+            *sp = halves(m);
+            *spc = halves(mc);
+          }
+        } else {
+          for (uint32_t p = 0; p < P; ++p, sp += stride) {
+            const uint32_t m = tps_win_match<K>(win, pm, pt, p);
+            U |= m;
+            *sp = halves(m);
+          }
+        }
+        for (uint64_t bm = pt.bordered_mask; bm; bm &= bm - 1) { /* uniform; none for most pattern sets */
+          const uint32_t p = (uint32_t)__ffsll((long long)bm) - 1u;
+          brows[pt.brow[p] * (NT + 1u) + q] = tps_win_match<K>(win, pm, pt, p);
+        }
+      }
+      {
+        const uint32_t before = tps_block_excl_scan(tps_popc32(U), s_wt[0], tid); /* barrier inside */
+        UP[q] = make_uint2(U, before);
+      }
+      /* (2) presence rows R_p of word q, added bit-sliced into the count planes */
+      switch (mode) {
+        case 1: tps_presence_planes<1>(SP + q, P4, stride, da, dr, nz, Z + q, Zhi + q); break;
+        case 2: tps_presence_planes<2>(SP + q, P4, stride, da, dr, nz, Z + q, Zhi + q); break;
+        case 3: tps_presence_planes<3>(SP + q, P4, stride, da, dr, nz, Z + q, Zhi + q); break;
+        default: tps_presence_planes<0>(SP + q, P4, stride, da, dr, nz, Z + q, Zhi + q); break;
+      }
+      if (nb) { /* starts of a self-overlapping literal with another start of it less than K ahead */
+        uint32_t CF = 0u;
+        for (uint32_t bi = 0; bi < nb; ++bi) {
+          const uint32_t m0 = brows[bi * (NT + 1u) + q], m1 = brows[bi * (NT + 1u) + q + 1u];
+#pragma unroll
+          for (int d = 1; d < K; ++d) CF |= m0 & __funnelshift_r(m0, m1, d);
+        }
+        const uint32_t before = tps_block_excl_scan(tps_popc32(CF), s_wt[1], tid);
+        CP[q] = make_uint2(CF, before);
+      }
+      __syncthreads();
+      /* (3) windows */
+      for (uint32_t w = rec.wlo + tid; w < rec.whi; w += NT) {
+        const uint32_t ls = w * s - tb0, e = ls + D; /* start positions [ls, e) */
+        const uint32_t q0 = ls >> 5, qe = e >> 5, b0 = ls & 31u;
+        const uint32_t m0 = (1u << b0) - 1u, me = (1u << (e & 31u)) - 1u;
+        const uint2 u0 = UP[q0], ue = UP[qe];
+        uint32_t c = ue.y + tps_popc32(ue.x & me) - u0.y - tps_popc32(u0.x & m0); /* occurrences of all literals */
+        const uint4 z = Z[q0];
+        const uint32_t r0 = __funnelshift_r(z.x, z.x, b0), r1 = __funnelshift_r(z.y, z.y, b0),
+                       r2 = __funnelshift_r(z.z, z.z, b0), r3 = __funnelshift_r(z.w, z.w, b0);
+        uint32_t present = (r0 & 1u) | (r1 & ~1u);
+        present = (present & 3u) | (r2 & ~3u);
+        present = ((present & 7u) | (r3 & ~7u)) & 15u;
+        if (nz > 4u) {
+          const uint4 zh = Zhi[q0];
+          present |= (__funnelshift_r(zh.x, zh.x, b0) & 16u) | (__funnelshift_r(zh.y, zh.y, b0) & 32u) |
+                     (__funnelshift_r(zh.z, zh.z, b0) & 64u);
+        }
+        c += P - present; /* absent literals count 1 each */
+        if (nb) {
+          const uint2 f0 = CP[q0], fe = CP[qe];
+          if (fe.y + tps_popc32(fe.x & me) - f0.y - tps_popc32(f0.x & m0)) {
+            for (uint64_t bm = pt.bordered_mask; bm; bm &= bm - 1) {
+              const uint32_t p = (uint32_t)__ffsll((long long)bm) - 1u;
+              const uint32_t *row = brows + pt.brow[p] * (NT + 1u);
+              uint32_t occ = tps_range_popcount(row, (int32_t)ls, (int32_t)e - 1);
+              uint32_t g = tps_greedy_count(row, (int32_t)ls, (int32_t)e - 1, (uint32_t)K);
+              occ = occ ? occ : 1u;
+              g = g ? g : 1u;
+              c = c - occ + g;
+            }
+          }
+        }
+        cw[w] = (uint16_t)c;
+      }
+    }
+    /* completion: the atomic that counts this tile is issued now and looked at one tile later, when its answer
+     * has long arrived; the CTA that completed a read's last tile finds its change point */
+    __syncthreads();
+    if (tid == 0) {
+      s_cp_go = has_pend && pend_old == s_pend_target - 1u;
+      s_cp_pi = s_pend_pi;
+      __threadfence(); /* cumulative: the barrier ordered the CTA's c_w stores before it */
+      pend_old = atomicAdd(a.tile_done + pi, 1u);
+      has_pend = true;
+      s_pend_pi = pi;
+      s_pend_target = rec.ntiles;
+      s_idx[(k + 3u) & 3u] = next_idx;
+    }
+    tps_cp_async_wait_all();
+    __syncthreads();
+    if (s_cp_go) change_point(s_cp_pi);
+  }
+  __syncthreads();
+  if (tid == 0) s_cp_go = has_pend && pend_old == s_pend_target - 1u;
+  __syncthreads();
+  if (s_cp_go) change_point(s_pend_pi);
 }
 
 /* ------------------------------------------------------------------------------------ K5

@@ -441,6 +441,21 @@ class ScanContext:
     def kernel_launches(self) -> int:
         return int(self.lib.tps_kernel_launches(self._h))
 
+    def debug_info(self) -> dict:
+        v = self.debug_copy(5, 16).view(np.uint32)
+        return dict(cw_stride=int(v[0]), k3_bitpar=bool(v[1]), max_pass=int(v[2]), k3_tile_bases=int(v[3]))
+
+    def window_sums(self, rows) -> dict:
+        """Test hook: {read index: c_w[0..n_windows)} of the TRC-pass reads of the last batch scanned on slot 0."""
+        n_pass = int((rows["status"] >= ST_PASS).sum())
+        if n_pass == 0:
+            return {}
+        info = self.debug_info()
+        stride, dt = info["cw_stride"], (np.uint16 if info["k3_bitpar"] else np.uint32)
+        plist = self.debug_copy(3, n_pass * 4).view(np.uint32)
+        cw = self.debug_copy(4, n_pass * stride * np.dtype(dt).itemsize).view(dt).reshape(n_pass, stride)
+        return {int(r): cw[i, :int(rows["n_windows"][r])].copy() for i, r in enumerate(plist)}
+
     def debug_copy(self, what: int, nbytes: int) -> np.ndarray:
         out = np.empty(nbytes, dtype=np.uint8)
         self._check(self.lib.tps_debug_copy(self._h, what, out.ctypes.data, nbytes))

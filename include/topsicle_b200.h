@@ -212,9 +212,10 @@ int tps_follow_scan(int device, const uint8_t *bases, const uint64_t *offsets, u
  * what: 0 = 2-bit code words (uint32 per 16 bases), 1 = invalid-group flag words
  * (uint32 per 512 bases), 2 = validity masks as K2/K3 see them (uint16 per 16 bases: 0xFFFF for an
  * unflagged group, else rebuilt from the group's ASCII bytes), 3 = pass list (uint32 read indices, unordered),
- * 4 = window sums c_w (row i = pass-list entry i; uint16 elements under the bit-parallel window kernel, else
- * uint32; row stride in elements from 5), 5 = uint32[4] {c_w row stride, 1 if the bit-parallel window kernel is
- * in use, pass-list capacity, window-start positions per tile}. */
+ * 4 = window sums (row i = pass-list entry i, row stride in elements from 5): uint32 c_w per window under the
+ * plain window kernel; under the bit-parallel kernel uint16 sums of c_w over the groups of five windows
+ * [5j, 5j+5), which is all the change point reads, 5 = uint32[4] {row stride of 4, 1 if the bit-parallel window
+ * kernel is in use, pass-list capacity, window-start positions per tile}. */
 int tps_debug_copy(tps_ctx *ctx, int what, void *dst, size_t bytes);
 
 #ifdef __cplusplus

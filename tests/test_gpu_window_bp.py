@@ -1,6 +1,7 @@
 """GPU tier: the bit-parallel window kernel (tps_window_bp_kernel, the default K3 with the change point fused)
 against the oracle and against the plain per-literal kernel (tps_window_kernel + tps_changepoint_kernel,
-TPS_K3_BITPAR=0): window sums c_w, n_windows, status, bkp and telo_length must be bit-identical.
+TPS_K3_BITPAR=0): the sums of c_w over the groups of five windows (what the change point reads), n_windows,
+status, bkp and telo_length must be bit-identical; TPS_K3_NO_GROUPS=1 (every window on its own) likewise.
 Reference semantics: /root/reference/Topsicle/allsteps.py:207-225, 279-291 (W-1 text, `or 1`, sum over all P),
 :304-315 + ruptures 1.1.9 Binseg."""
 import numpy as np
@@ -21,11 +22,15 @@ CFGS = [("CCCTAA", 4, 100, 6, 100, 20000), ("TTAGGG", 4, 50, 3, 100, 20000), ("C
         ("ACACAC", 4, 100, 2, 0, 3000), ("AAAAAA", 3, 64, 1, 5, 2500), ("TTTTAGGG", 8, 100, 8, 100, 20000)]
 
 
-def _scan(engine, pats, motif, reads, W, s, t, M, bitpar, monkeypatch, **kw):
+def _scan(engine, pats, motif, reads, W, s, t, M, bitpar, monkeypatch, no_groups=False, **kw):
     if bitpar:
         monkeypatch.delenv("TPS_K3_BITPAR", raising=False)
     else:
         monkeypatch.setenv("TPS_K3_BITPAR", "0")
+    if no_groups:
+        monkeypatch.setenv("TPS_K3_NO_GROUPS", "1")
+    else:
+        monkeypatch.delenv("TPS_K3_NO_GROUPS", raising=False)
     with engine.ScanContext(pats, len_telopattern=len(motif), min_seq_length=0, count_threshold_override=0,
                             window_size=W, slide=s, trimfirst=t, maxlengthtelo=M, max_batch_reads=1024,
                             max_batch_bases=1 << 24, **kw) as ctx:
@@ -46,9 +51,11 @@ def test_window_sums_equal_oracle_and_plain_kernel(cfg, edge_records, demo_recor
             [motif * 4000, (motif * 4000)[::-1], "ACGT" * 6000, "A" * 25000, "N" * 3000 + motif * 500]
     rows, cws, launches = _scan(engine, pats, motif, reads, W, s, t, M, True, monkeypatch)
     rows0, cws0, launches0 = _scan(engine, pats, motif, reads, W, s, t, M, False, monkeypatch)
+    rows1, cws1, _ = _scan(engine, pats, motif, reads, W, s, t, M, True, monkeypatch, no_groups=True)
     assert launches == 3 and launches0 == 4      # K1, K2, fused K3+K4  vs  K1, K2, K3, K4
-    assert rows.tobytes() == rows0.tobytes()
-    assert set(cws) == set(cws0)
+    assert rows.tobytes() == rows0.tobytes() == rows1.tobytes()
+    assert set(cws) == set(cws0) == set(cws1)
+    assert all(np.array_equal(cws[i], cws1[i]) for i in cws)
     n_cp = 0
     for i, seq in enumerate(reads):
         row = rows[i]
@@ -62,8 +69,8 @@ def test_window_sums_equal_oracle_and_plain_kernel(cfg, edge_records, demo_recor
             assert row["status"] == engine.ST_BADSEG and row["telo_length"] == -1
             continue
         c_w = counts.sum(axis=1)
-        assert np.array_equal(cws[i].astype(np.int64), c_w), (cfg, i)
-        assert np.array_equal(cws0[i].astype(np.int64), c_w), (cfg, i)
+        assert np.array_equal(cws[i], engine.group_sums(c_w)), (cfg, i)
+        assert np.array_equal(cws0[i], engine.group_sums(c_w)), (cfg, i)
         b = orc.change_point_exact(c_w)
         assert (int(row["status"]), int(row["bkp"]), int(row["telo_length"])) == (engine.ST_PASS, b, t + s * b), (cfg, i)
         n_cp += 1
@@ -98,7 +105,7 @@ def test_random_geometry(seed, monkeypatch):
             assert row["status"] == engine.ST_BADSEG
             continue
         c_w = counts.sum(axis=1)
-        assert np.array_equal(cws[i].astype(np.int64), c_w), (seed, i)
+        assert np.array_equal(cws[i], engine.group_sums(c_w)), (seed, i)
         b = orc.change_point_exact(c_w)
         assert (int(row["bkp"]), int(row["telo_length"])) == (b, t + s * b), (seed, i)
         n += 1

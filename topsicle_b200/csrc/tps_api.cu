@@ -63,7 +63,7 @@ struct tps_ctx {
   bool k3_bitpar = false;
   void (*k3n_fn)(const TpsScanArgs, const TpsPatTable) = nullptr;
   uint32_t k3n_lin_words = 0, k3n_stride = 0, k3n_tile_bases = 0, k3n_tiles_max = 0, k3n_smem = 0, k3n_grid = 0, k3n_nz = 0;
-  uint32_t k3n_cp_cap = 0, cw16_stride = 0;
+  uint32_t k3n_cp_cap = 0, gs_stride = 0, k3n_tile_windows = 0, k3n_no_groups = 0;
   uint32_t cw_stride = 0, max_pass = 0;
   int kt = 0; /* template K of the K2/K3 instantiation in use (0 = generic) */
   void (*k2_fn)(const TpsScanArgs, const TpsPatTable) = nullptr;
@@ -317,24 +317,29 @@ int tps_create(tps_ctx **out, int device, const tps_params *params) {
         distinct = !(pt.len[i] == pt.len[j] && pt.lo[i] == pt.lo[j] && pt.hi[i] == pt.hi[j]);
     const char *e = getenv("TPS_K3_BITPAR"); /* 0 = tps_window_kernel + tps_changepoint_kernel (A/B, and the fallback) */
     ctx->k3_bitpar = ctx->kt > 0 && distinct && !p.want_rawcount && p.window_size >= (uint32_t)ctx->kt + 32u &&
-                     p.window_size <= 2048u && (uint64_t)cnt_max * pt.n <= 65535u /* c_w as uint16 */ &&
-                     !(e && atoi(e) == 0);
+                     p.window_size <= 2048u && 4ull * p.slide + p.window_size <= 32u * TPS_K3N_THREADS /* a tile holds a group */ &&
+                     5ull * cnt_max * pt.n <= 65535u /* group sums as uint16 */ && !(e && atoi(e) == 0);
     if (ctx->k3_bitpar) {
-      const uint32_t D = p.window_size - (uint32_t)ctx->kt;
-      ctx->k3n_tile_bases = (32u * TPS_K3N_THREADS - p.window_size) & ~31u;
-      ctx->k3n_lin_words = lin_words_for(32u * TPS_K3N_THREADS);
-      ctx->k3n_stride = TPS_K3N_THREADS + (D >> 5) + 2u;
-      ctx->k3n_tiles_max = (uint32_t)((reg_max + ctx->k3n_tile_bases - 1) / ctx->k3n_tile_bases);
+      const uint32_t D = p.window_size - (uint32_t)ctx->kt, NT = TPS_K3N_THREADS;
+      /* a tile stages (windows - 1) * slide + W <= 32 NT positions; whole groups of five windows */
+      ctx->k3n_tile_windows = (uint32_t)(((32ull * NT - p.window_size) / p.slide + 1) / 5 * 5);
+      ctx->k3n_tile_bases = ctx->k3n_tile_windows * p.slide;
+      ctx->k3n_lin_words = lin_words_for(32u * NT);
+      ctx->k3n_stride = NT + (D >> 5) + 2u;
+      ctx->k3n_tiles_max = (uint32_t)(((nw_max + 4) / 5 + ctx->k3n_tile_windows / 5 - 1) / (ctx->k3n_tile_windows / 5));
       if (ctx->k3n_tiles_max == 0) ctx->k3n_tiles_max = 1;
       ctx->k3n_nz = 1;
       while ((1u << ctx->k3n_nz) <= pt.n) ctx->k3n_nz++;
       const uint32_t head_words = 2 * TPS_K3N_RAW_WORDS + pm_words + 3; /* prefetch buffers, literal masks, alignment */
-      ctx->k3n_smem = (head_words + 3 * ctx->k3n_lin_words + 3 * (TPS_K3N_THREADS + 1) + 3 + 4 * TPS_K3N_THREADS +
-                       (ctx->k3n_nz > 4 ? 4 * TPS_K3N_THREADS : 0) + 2 * TPS_K3N_THREADS +
-                       (pt.n_bordered ? 2 * TPS_K3N_THREADS : 0) + 2 * ((pt.n + 3u) & ~3u) * ctx->k3n_stride +
-                       pt.n_bordered * (TPS_K3N_THREADS + 1)) * 4;
-      ctx->k3n_cp_cap = ((ctx->k3n_smem - head_words * 4) / 2) & ~7u; /* c_w row of a read staged as uint16 */
-      ctx->cw16_stride = (uint32_t)(((nw_max ? nw_max : 1) + 7) & ~7ull);
+      /* lin | ori | alignment | Z | Zhi | UP | CP: free between tiles (the change point stages a read's group sums here) */
+      const uint32_t free_words = 3 * ctx->k3n_lin_words + 3 * (NT + 1) + 3 + 4 * (NT + 1) + (ctx->k3n_nz > 4 ? 4 * (NT + 1) : 0) +
+                                  2 * (NT + 2) + (pt.n_bordered ? 2 * (NT + 2) : 0);
+      ctx->k3n_smem = (head_words + free_words + 2 * ((pt.n + 3u) & ~3u) * ctx->k3n_stride + pt.n_bordered * (NT + 1)) * 4;
+      ctx->k3n_cp_cap = (free_words * 2 - 16) & ~7u;
+      ctx->gs_stride = (uint32_t)(((nw_max + 4) / 5 + 7) & ~7ull);
+      if (ctx->gs_stride == 0) ctx->gs_stride = 8;
+      const char *ng = getenv("TPS_K3_NO_GROUPS"); /* 1 = no five-window fast path (A/B) */
+      ctx->k3n_no_groups = ng && atoi(ng) != 0;
     }
   }
   ctx->cw_stride = (uint32_t)(nw_max ? nw_max : 1);
@@ -460,7 +465,7 @@ int tps_create(tps_ctx **out, int device, const tps_params *params) {
     TPS_CC(cudaMalloc(&s.d_counters, 8 * sizeof(uint32_t)));
     if (p.want_rawcount) TPS_CC(cudaMalloc(&s.d_raw, p.rawcount_capacity ? p.rawcount_capacity : 1));
     if (ctx->k3_bitpar) { /* c_w rows as uint16 */
-      TPS_CC(cudaMalloc(&s.d_cw, (uint64_t)ctx->max_pass * ctx->cw16_stride * sizeof(uint16_t)));
+      TPS_CC(cudaMalloc(&s.d_cw, (uint64_t)ctx->max_pass * ctx->gs_stride * sizeof(uint16_t)));
       TPS_CC(cudaMalloc(&s.d_tile_done, (uint64_t)ctx->max_pass * sizeof(uint32_t)));
       TPS_CC(cudaMalloc(&s.d_items, (uint64_t)ctx->max_pass * ctx->k3n_tiles_max * sizeof(TpsTile)));
     } else {
@@ -585,9 +590,11 @@ int enqueue_scan(tps_ctx *ctx, Slot &s, cudaStream_t st, const ScanJob &job) {
   a.items = ctx->k3_bitpar ? s.d_items : nullptr;
   a.bp_tile_bases = ctx->k3n_tile_bases;
   a.nz = ctx->k3n_nz;
-  a.cw16 = reinterpret_cast<uint16_t *>(s.d_cw);
-  a.cw16_stride = ctx->cw16_stride;
+  a.gs = reinterpret_cast<uint16_t *>(s.d_cw);
+  a.gs_stride = ctx->gs_stride;
   a.cp_cap = ctx->k3n_cp_cap;
+  a.bp_tile_windows = ctx->k3n_tile_windows;
+  a.no_groups = ctx->k3n_no_groups;
   if (n_reads) {
     a.lin_words = ctx->k2_lin_words;
     if (ctx->k2_reg)
@@ -992,11 +999,11 @@ int tps_debug_copy(tps_ctx *ctx, int what, void *dst, size_t bytes) {
     case 3: src = s.d_pass; cap = (size_t)ctx->max_pass * sizeof(uint32_t); break;
     case 4:
       src = s.d_cw;
-      cap = ctx->k3_bitpar ? (size_t)ctx->max_pass * ctx->cw16_stride * sizeof(uint16_t)
+      cap = ctx->k3_bitpar ? (size_t)ctx->max_pass * ctx->gs_stride * sizeof(uint16_t)
                            : (size_t)ctx->max_pass * ctx->cw_stride * sizeof(uint32_t);
       break;
     case 5: { /* geometry: c_w row stride (elements), which K3 is in use, pass capacity, tile size of that K3 */
-      const uint32_t info[4] = {ctx->k3_bitpar ? ctx->cw16_stride : ctx->cw_stride, ctx->k3_bitpar ? 1u : 0u, ctx->max_pass,
+      const uint32_t info[4] = {ctx->k3_bitpar ? ctx->gs_stride : ctx->cw_stride, ctx->k3_bitpar ? 1u : 0u, ctx->max_pass,
                                 ctx->k3_bitpar ? ctx->k3n_tile_bases : ctx->k3_tile_bases};
       if (bytes > sizeof(info)) return fail(ctx, TPS_EINVAL, "debug info is %zu bytes", sizeof(info));
       memcpy(dst, info, bytes);

@@ -74,25 +74,29 @@ struct TpsScanArgs {
   uint32_t nq_max;     /* K2: ceil(no_bp/32) */
   /* bit-parallel K3 (tps_window_bp_kernel): K2 appends one TpsTile record per tile of every TRC-pass read with
    * at least 7 windows to `items` (counters[6] = number of records) and zeroes the read's entry of
-   * `tile_done`, the tiles finished so far; c_w is kept as uint16 at cw16 + slot * cw16_stride */
+   * `tile_done`, the tiles finished so far.  The kernel keeps, per read, the sums of c_w over the groups of five
+   * consecutive windows [5j, 5j+5) -- all the change point needs (its candidates are the multiples of 5) -- as
+   * uint16 at gs + slot * gs_stride */
   uint32_t *tile_done;
   struct TpsTile *items;
   uint32_t bp_tile_bases; /* window-start positions per tile (a multiple of 32) */
   uint32_t nz;            /* count planes, 2^nz > P */
-  uint16_t *cw16;
-  uint32_t cw16_stride;   /* a multiple of 8: rows start on 16-byte boundaries */
-  uint32_t cp_cap;        /* windows of one read that fit the kernel's shared-memory scratch as uint16 */
+  uint16_t *gs;
+  uint32_t gs_stride;     /* a multiple of 8: rows start on 16-byte boundaries */
+  uint32_t cp_cap;        /* group sums of one read that fit the kernel's shared-memory scratch */
+  uint32_t bp_tile_windows; /* windows per tile at most (a multiple of 5) */
+  uint32_t no_groups;     /* 1 = every window on its own (A/B of the five-window fast path) */
 };
 
 /* One work item of the bit-parallel K3: everything a CTA needs to stage and count one tile, worked out once by
  * K2 (which knows the read's start, length and orientation) so that the tile loop starts with one 32-byte load. */
 struct __align__(16) TpsTile {
   uint64_t g0;     /* first base of the staged slice in the batch */
-  uint32_t tn;     /* staged oriented positions (tile + W-base halo, clipped to the region) */
-  uint32_t tb0;    /* oriented position of the tile's first window-start position */
-  uint32_t wlo, whi; /* windows whose start lies in the tile */
+  uint32_t tn;     /* staged oriented positions: from the start of window wlo to the end of window whi - 1 */
+  uint32_t wlo, whi; /* windows of the tile; wlo is a multiple of 5, whi too except at the end of the read */
   uint32_t pi_rev; /* pass-list slot | reverse << 31 */
   uint32_t ntiles; /* tiles of this read */
+  uint32_t reserved;
 };
 
 /* ------------------------------------------------------------------------------------ K1 */
@@ -493,23 +497,22 @@ __device__ __forceinline__ void tps_trc_decide(const TpsScanArgs &a, uint32_t n_
     const uint32_t slot = atomicAdd(a.counters + 0, 1u);
     if (slot < a.max_pass) {
       a.pass_list[slot] = r;
-      if (a.items && nW >= 7u) { /* the tiles of this read's region (balanced), as consecutive work items */
-        const uint32_t nt0 = (nreg + a.bp_tile_bases - 1u) / a.bp_tile_bases;
-        const uint32_t tsize = ((nreg + nt0 - 1u) / nt0 + 31u) & ~31u; /* <= bp_tile_bases */
-        uint32_t nt = 0; /* tiles that hold a window start: 1 .. nt0, always a prefix */
-        while (nt < nt0 && (nt * tsize + a.slide - 1u) / a.slide < nW) ++nt;
+      if (a.items && nW >= 7u) { /* the tiles of this read's windows (balanced, whole groups of 5), consecutive items */
+        const uint32_t ng = (nW + 4u) / 5u, gmax = a.bp_tile_windows / 5u;
+        const uint32_t nt = (ng + gmax - 1u) / gmax;
+        const uint32_t per = (ng + nt - 1u) / nt * 5u; /* windows per tile, <= bp_tile_windows */
         uint32_t at = atomicAdd(a.counters + 6, nt);
         for (uint32_t ti = 0; ti < nt; ++ti, ++at) {
           TpsTile tl;
-          tl.tb0 = ti * tsize;
-          tl.tn = tsize + a.W < nreg - tl.tb0 ? tsize + a.W : nreg - tl.tb0; /* a window reaches W-2 past its start */
+          tl.wlo = ti * per;
+          tl.whi = tl.wlo + per < nW ? tl.wlo + per : nW;
+          const uint32_t tb0 = tl.wlo * a.slide;              /* oriented position of the first window start */
+          tl.tn = (tl.whi - tl.wlo - 1u) * a.slide + a.W;     /* the last window ends inside the region */
           /* forward: read bases [off+t+tb0, +tn); reverse: region position j is read index L-1-(t+j) */
-          tl.g0 = fwd ? off + a.trimfirst + tl.tb0 : off + L - a.trimfirst - tl.tb0 - tl.tn;
-          tl.wlo = (tl.tb0 + a.slide - 1u) / a.slide;
-          tl.whi = (tl.tb0 + tsize + a.slide - 1u) / a.slide;
-          if (tl.whi > nW) tl.whi = nW;
+          tl.g0 = fwd ? off + a.trimfirst + tb0 : off + L - a.trimfirst - tb0 - tl.tn;
           tl.pi_rev = slot | (fwd ? 0u : 0x80000000u);
           tl.ntiles = nt;
+          tl.reserved = 0u;
           a.items[at] = tl;
         }
         a.tile_done[slot] = 0u;
@@ -975,12 +978,13 @@ tps_window_kernel(const TpsScanArgs a, const TpsPatTable pt) {
 /* Single change point of c_w[0..n) by one CTA of TPS_K4_THREADS threads, the exact form of ruptures
  * Binseg(model="l2", jump=5, min_size=2).predict(n_bkps=1):
  * argmax over b in {5,10,...}, 2 <= b <= n-2 of (n*S_b - b*T)^2 / (b*(n-b)), ties -> larger b.
- * Every thread owns one run of `chunk` consecutive windows (chunk a multiple of 5, so every candidate's S_b is a
- * running sum inside one thread):
+ * c_w comes through a reader whose elements are single windows (G = 1) or the sums of the groups of five
+ * windows [5j, 5j+5) (G = 5: the candidates are the multiples of 5, so group sums are all that is needed).
+ * Every thread owns one run of consecutive groups, so every candidate's S_b is a running sum inside one thread:
  *   pass 1  sums the run; one block-wide exclusive scan turns the run sums into S at the run starts and T;
  *   pass 2  walks the run's candidates with a float32 SCREEN of the gain (relative error < 1e-6) and keeps the
- *           thread's largest; a block-wide max gives G;
- *   pass 3  only threads whose screen value reaches G * (1 - 1e-4) walk their run again and put every candidate
+ *           thread's largest; a block-wide max gives gtop;
+ *   pass 3  only threads whose screen value reaches gtop * (1 - 1e-4) walk their run again and put every candidate
  *           above that bar through the exact comparator (float64 cross-multiplication, 128-bit integers for
  *           ties and near-ties); their winners go to a short shared list that thread 0 reduces.
  * Any candidate that can be the exact argmax passes the screen, so the result is the exact one; the screen only
@@ -1008,9 +1012,12 @@ struct TpsCwShared16 {
   const uint16_t *p;
   __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return p[i]; }
 };
-template <class RD>
+/* sum of the reader elements that make up one group of five windows: five elements of one window each
+ * (G = 1) or one element that already is the group sum (G = 5) */
+template <int G, class RD>
 __device__ __forceinline__ uint32_t tps_cw5(const RD &cw, uint32_t i) {
-  return cw(i) + cw(i + 1u) + cw(i + 2u) + cw(i + 3u) + cw(i + 4u);
+  if constexpr (G == 5) return cw(i);
+  else return cw(i) + cw(i + 1u) + cw(i + 2u) + cw(i + 3u) + cw(i + 4u);
 }
 
 __device__ __forceinline__ float tps_gain_screen(uint32_t n, uint64_t S, uint64_t T, uint32_t b) {
@@ -1018,17 +1025,20 @@ __device__ __forceinline__ float tps_gain_screen(uint32_t n, uint64_t S, uint64_
   return d * d * __frcp_rn((float)b * (float)(n - b));
 }
 
-template <class RD>
+template <int G, class RD>
 __device__ __forceinline__ int32_t tps_changepoint_block(const RD cw, uint32_t n, TpsCpShared &sh, uint32_t tid) {
+  static_assert(G == 1 || G == 5, "reader elements are windows or groups of five windows");
+  constexpr uint32_t STEP = 5 / G; /* elements per candidate */
   constexpr uint32_t NWARP = TPS_K4_THREADS / 32;
   const uint32_t lane = tid & 31u, warp = tid >> 5;
-  const uint32_t chunk = 5u * ((n + 5u * TPS_K4_THREADS - 1u) / (5u * TPS_K4_THREADS));
-  const uint32_t w0 = tid * chunk < n ? tid * chunk : n;
-  const uint32_t w1 = n - w0 < chunk ? n : w0 + chunk;
+  const uint32_t n_el = (n + G - 1u) / G; /* reader elements */
+  const uint32_t chunk = STEP * ((n + 5u * TPS_K4_THREADS - 1u) / (5u * TPS_K4_THREADS)); /* elements per thread */
+  const uint32_t w0 = tid * chunk < n_el ? tid * chunk : n_el;
+  const uint32_t w1 = n_el - w0 < chunk ? n_el : w0 + chunk;
   uint64_t sum = 0;
   {
     uint32_t w = w0;
-    for (; w + 5u <= w1; w += 5u) sum += tps_cw5(cw, w);
+    for (; w + STEP <= w1; w += STEP) sum += tps_cw5<G>(cw, w);
     for (; w < w1; ++w) sum += cw(w);
   }
   uint64_t inc = sum;
@@ -1050,30 +1060,32 @@ __device__ __forceinline__ int32_t tps_changepoint_block(const RD cw, uint32_t n
   float gmax = -1.0f;
   {
     uint64_t S = S0;
-    for (uint32_t b = w0; b < w1; b += 5u) {
+    for (uint32_t e = w0; e < w1; e += STEP) {
+      const uint32_t b = e * G;
       if (b >= 2u && n - b >= 2u) gmax = fmaxf(gmax, tps_gain_screen(n, S, T, b));
-      if (b + 5u <= w1) S += tps_cw5(cw, b);
+      if (e + STEP <= w1) S += tps_cw5<G>(cw, e);
     }
   }
-  float G = gmax;
+  float gtop = gmax;
 #pragma unroll
-  for (int o = 16; o; o >>= 1) G = fmaxf(G, __shfl_xor_sync(TPS_FULL, G, o));
-  if (lane == 0) sh.wmax[warp] = G;
+  for (int o = 16; o; o >>= 1) gtop = fmaxf(gtop, __shfl_xor_sync(TPS_FULL, gtop, o));
+  if (lane == 0) sh.wmax[warp] = gtop;
   __syncthreads();
 #pragma unroll
-  for (uint32_t i = 0; i < NWARP; ++i) G = fmaxf(G, sh.wmax[i]);
-  const float bar = G * (1.0f - 1e-4f); /* G >= 0 whenever a candidate exists */
+  for (uint32_t i = 0; i < NWARP; ++i) gtop = fmaxf(gtop, sh.wmax[i]);
+  const float bar = gtop * (1.0f - 1e-4f); /* gtop >= 0 whenever a candidate exists */
   /* pass 3: exact comparison of the candidates at the top */
   if (gmax >= bar && gmax >= 0.0f) {
     tps_cand best;
     best.b = -1; best.d = 0; best.den = 1; best.num_f = 0.0; best.den_f = 1.0;
     uint64_t S = S0;
-    for (uint32_t b = w0; b < w1; b += 5u) {
+    for (uint32_t e = w0; e < w1; e += STEP) {
+      const uint32_t b = e * G;
       if (b >= 2u && n - b >= 2u && tps_gain_screen(n, S, T, b) >= bar) {
         const tps_cand c = tps_make_cand(n, S, T, b);
         if (tps_cand_better(&best, &c)) best = c;
       }
-      if (b + 5u <= w1) S += tps_cw5(cw, b);
+      if (e + STEP <= w1) S += tps_cw5<G>(cw, e);
     }
     if (best.b >= 0) sh.cand[atomicAdd(&sh.n_cand, 1u)] = best;
   }
@@ -1122,7 +1134,7 @@ tps_changepoint_kernel(const TpsScanArgs a) {
     const uint32_t r = a.pass_list[pi];
     const uint32_t nW = a.rows[r].n_windows;
     int32_t best_b = -1;
-    if (nW >= 7u) best_b = tps_changepoint_block(TpsCwGlobal32{a.cw + (size_t)pi * a.cw_stride}, nW, s_cp, tid);
+    if (nW >= 7u) best_b = tps_changepoint_block<1>(TpsCwGlobal32{a.cw + (size_t)pi * a.cw_stride}, nW, s_cp, tid);
     if (tid == 0) tps_store_changepoint(a, r, best_b);
   }
 }
@@ -1217,8 +1229,7 @@ __device__ __forceinline__ uint32_t tps_dilate(const uint2 *__restrict__ sp, uin
   }
 }
 
-/* count planes of word q: the P presence rows added bit-sliced, four at a time; plane i is stored rotated left
- * by i so that a window's count is four rotates and three bit-selects */
+/* count planes of word q: the P presence rows added bit-sliced, four at a time */
 template <int MODE>
 __device__ __forceinline__ void tps_presence_planes(const uint2 *__restrict__ sp, uint32_t P4, uint32_t stride,
                                                     uint32_t da, uint32_t dr, uint32_t nz, uint4 *zlo, uint4 *zhi) {
@@ -1245,8 +1256,8 @@ __device__ __forceinline__ void tps_presence_planes(const uint2 *__restrict__ sp
       c8 ^= cy;
     }
   }
-  *zlo = make_uint4(c1, __funnelshift_l(c2, c2, 1), __funnelshift_l(c4, c4, 2), __funnelshift_l(c8, c8, 3));
-  if (nz > 4u) *zhi = make_uint4(__funnelshift_l(c16, c16, 4), __funnelshift_l(c32, c32, 5), __funnelshift_l(c64, c64, 6), 0u);
+  *zlo = make_uint4(c1, c2, c4, c8);
+  if (nz > 4u) *zhi = make_uint4(c16, c32, c64, 0u);
 }
 
 __device__ __forceinline__ void tps_cp_async16(void *smem_dst, const void *gsrc) {
@@ -1259,47 +1270,72 @@ __device__ __forceinline__ void tps_cp_async_wait_all() { asm volatile("cp.async
 #define TPS_K3N_RAW_FLAG_WORDS 16
 #define TPS_K3N_RAW_WORDS (TPS_K3N_RAW_CODE_WORDS + TPS_K3N_RAW_FLAG_WORDS)
 
-/* issue the asynchronous copies of the code and flag words that cover bases [g0, g0 + n) */
+/* issue the asynchronous copies of the code and flag words that cover bases [g0, g0 + n): code words from the
+ * 16-byte boundary at or below group g0 / 16, flag words from the 16-byte boundary at or below its flag word */
 __device__ __forceinline__ void tps_prefetch_codes(const TpsPacked &pk, uint64_t g0, uint32_t n, uint32_t *raw,
                                                    uint32_t tid) {
-  const uint64_t gfirst = g0 >> 4, glast = (g0 + n + 15u) >> 4; /* groups [gfirst, glast) */
-  const uint64_t w0 = gfirst & ~3ull;                            /* code words, 16-byte aligned */
-  const uint32_t nchunk = (uint32_t)((glast - w0 + 3u) >> 2);
+  const uint64_t gfirst = g0 >> 4;
+  const uint32_t ng = (uint32_t)(((g0 + n + 15u) >> 4) - gfirst); /* groups */
+  const uint64_t w0 = gfirst & ~3ull;
+  const uint32_t nchunk = (ng + (uint32_t)(gfirst & 3ull) + 3u) >> 2;
   if (tid < nchunk) tps_cp_async16(raw + 4u * tid, pk.codes + w0 + 4u * tid);
-  const uint64_t f0 = (gfirst >> 5) & ~3ull; /* flag words */
-  const uint32_t nf = (uint32_t)((((glast + 31u) >> 5) - f0 + 3u) >> 2);
+  const uint64_t f0 = (gfirst >> 5) & ~3ull;
+  const uint32_t nf = ((ng + (uint32_t)(gfirst & 127ull) + 31u) >> 5) + 3u >> 2;
   if (tid >= 96u && tid - 96u < nf) tps_cp_async16(raw + TPS_K3N_RAW_CODE_WORDS + 4u * (tid - 96u), pk.flags + f0 + 4u * (tid - 96u));
 }
 
-/* tps_stage_linear from the prefetched words */
-__device__ __forceinline__ void tps_stage_linear_raw(const uint32_t *raw, const uint8_t *__restrict__ bases, uint64_t g0,
-                                                     uint32_t n, uint32_t *lin, uint32_t lw, uint32_t tid,
-                                                     uint32_t nthreads) {
-  uint16_t *l0 = reinterpret_cast<uint16_t *>(lin);
-  uint16_t *l1 = reinterpret_cast<uint16_t *>(lin + lw);
-  uint16_t *lv = reinterpret_cast<uint16_t *>(lin + 2 * lw);
-  const uint64_t gfirst = g0 >> 4;
-  const uint32_t ng = n ? (uint32_t)(((g0 + n + 15) >> 4) - gfirst) : 0u;
-  const uint32_t cskew = (uint32_t)(gfirst & 3ull);
-  const uint64_t f0 = (gfirst >> 5) & ~3ull;
-  for (uint32_t i = tid; i < 2 * lw; i += nthreads) {
-    if (i < 2 || i >= 2 + ng) {
-      l0[i] = 0;
-      l1[i] = 0;
-      lv[i] = 0;
-    } else {
-      const uint64_t g = gfirst + (i - 2);
-      const uint32_t y = tps_linear_planes(raw[cskew + (i - 2)]);
-      uint32_t v = 0xFFFFu;
-      if ((raw[TPS_K3N_RAW_CODE_WORDS + (uint32_t)((g >> 5) - f0)] >> (g & 31)) & 1u) { /* rare: N, IUPAC */
-        const uint4 b = __ldg(reinterpret_cast<const uint4 *>(bases) + g);
-        v = tps_exact_mask16_simd(b.x, b.y, b.z, b.w);
-      }
-      l0[i] = (uint16_t)(y & 0xFFFFu);
-      l1[i] = (uint16_t)(y >> 16);
-      lv[i] = (uint16_t)v;
+/* tps_stage_linear from the prefetched words: entry e of the uint16 views holds group gfirst + e - 2 */
+__device__ __forceinline__ void tps_stage_entry_raw(const uint32_t *raw, const uint8_t *__restrict__ bases, uint64_t gfirst,
+                                                    uint32_t ng, uint32_t e, uint16_t *l0, uint16_t *l1, uint16_t *lv) {
+  uint32_t y = 0u, v = 0u;
+  const uint32_t gi = e - 2u;
+  if (gi < ng) { /* e < 2 wraps around: pad */
+    y = tps_linear_planes(raw[(uint32_t)(gfirst & 3ull) + gi]);
+    v = 0xFFFFu;
+    const uint32_t fb = (uint32_t)(gfirst & 127ull) + gi; /* flag bit relative to the first prefetched flag word */
+    if ((raw[TPS_K3N_RAW_CODE_WORDS + (fb >> 5)] >> (fb & 31u)) & 1u) { /* rare: N, IUPAC */
+      const uint4 b = __ldg(reinterpret_cast<const uint4 *>(bases) + (gfirst + gi));
+      v = tps_exact_mask16_simd(b.x, b.y, b.z, b.w);
     }
   }
+  l0[e] = (uint16_t)(y & 0xFFFFu);
+  l1[e] = (uint16_t)(y >> 16);
+  lv[e] = (uint16_t)v;
+}
+
+/* one window of the bit-parallel kernel on its own: c_w from the union row, the count planes and, where a
+ * self-overlapping literal has two starts less than K apart inside the window, the greedy walk */
+template <int K>
+__device__ __forceinline__ uint32_t tps_bp_window(uint32_t ls, uint32_t D, uint32_t P, uint32_t nz, uint32_t nb,
+                                                  const TpsPatTable &pt, const uint2 *UP, const uint4 *Z, const uint4 *Zhi,
+                                                  const uint2 *CP, const uint32_t *brows, uint32_t brow_stride) {
+  const uint32_t e = ls + D; /* start positions [ls, e) */
+  const uint32_t q0 = ls >> 5, qe = e >> 5, b0 = ls & 31u;
+  const uint32_t m0 = (1u << b0) - 1u, me = (1u << (e & 31u)) - 1u;
+  const uint2 u0 = UP[q0], ue = UP[qe];
+  uint32_t c = ue.y + tps_popc32(ue.x & me) - u0.y - tps_popc32(u0.x & m0); /* occurrences of all literals */
+  const uint4 z = Z[q0];
+  uint32_t present = ((z.x >> b0) & 1u) | (((z.y >> b0) & 1u) << 1) | (((z.z >> b0) & 1u) << 2) | (((z.w >> b0) & 1u) << 3);
+  if (nz > 4u) {
+    const uint4 zh = Zhi[q0];
+    present |= (((zh.x >> b0) & 1u) << 4) | (((zh.y >> b0) & 1u) << 5) | (((zh.z >> b0) & 1u) << 6);
+  }
+  c += P - present; /* absent literals count 1 each */
+  if (nb) {
+    const uint2 f0 = CP[q0], fe = CP[qe];
+    if (fe.y + tps_popc32(fe.x & me) - f0.y - tps_popc32(f0.x & m0)) {
+      for (uint64_t bm = pt.bordered_mask; bm; bm &= bm - 1) {
+        const uint32_t p = (uint32_t)__ffsll((long long)bm) - 1u;
+        const uint32_t *row = brows + pt.brow[p] * brow_stride;
+        uint32_t occ = tps_range_popcount(row, (int32_t)ls, (int32_t)e - 1);
+        uint32_t g = tps_greedy_count(row, (int32_t)ls, (int32_t)e - 1, (uint32_t)K);
+        occ = occ ? occ : 1u;
+        g = g ? g : 1u;
+        c = c - occ + g;
+      }
+    }
+  }
+  return c;
 }
 
 template <int K>
@@ -1322,52 +1358,61 @@ tps_window_bp_kernel(const TpsScanArgs a, const TpsPatTable pt) {
   const uint32_t W = a.W, s = a.slide;
   const uint32_t D = W - (uint32_t)K, da = D >> 5, dr = D & 31u, nz = a.nz;
   const uint32_t mode = (da == 1u && dr) ? 1u : (dr ? 0u : (da == 3u ? 3u : 2u));
+  /* five-window fast path: the five starts of a group lie within 32 positions of the first */
+  const bool grouped = 4u * s < 32u && !a.no_groups;
+  const uint32_t gm = 1u | (1u << s) | (1u << (2u * s)) | (1u << (3u * s)) | (1u << (4u * s)); /* the five starts */
+  const uint32_t lm1 = (1u << s) - 1u, lm2 = (1u << (2u * s)) - 1u, lm3 = (1u << (3u * s)) - 1u, lm4 = (1u << (4u * s)) - 1u;
   uint32_t *raw = smem; /* two buffers of TPS_K3N_RAW_WORDS */
   uint2 *pm = reinterpret_cast<uint2 *>(smem + 2u * TPS_K3N_RAW_WORDS);
-  uint32_t *scratch = smem + 2u * TPS_K3N_RAW_WORDS + 2u * P * K; /* everything behind is free between tiles */
+  uint32_t *scratch = smem + 2u * TPS_K3N_RAW_WORDS + 2u * P * K; /* free between tiles up to SP */
   scratch += (4u - ((uint32_t)(scratch - smem) & 3u)) & 3u;
   uint32_t *lin = scratch;
   uint32_t *ori = lin + 3u * lw;
   uint32_t *al = ori + 3u * (NT + 1u);
   al += (4u - ((uint32_t)(al - smem) & 3u)) & 3u;
-  uint4 *Z = reinterpret_cast<uint4 *>(al);
-  uint4 *Zhi = Z + NT;
-  uint2 *UP = reinterpret_cast<uint2 *>(Zhi + (nz > 4u ? NT : 0u));
-  uint2 *CP = UP + NT;
-  uint2 *SP = CP + (nb ? NT : 0u);
+  uint4 *Z = reinterpret_cast<uint4 *>(al);            /* NT + 1 entries each: the fast path reads word q0 + 1 */
+  uint4 *Zhi = Z + (NT + 1u);
+  uint2 *UP = reinterpret_cast<uint2 *>(Zhi + (nz > 4u ? NT + 1u : 0u));
+  uint2 *CP = UP + (NT + 2u);
+  uint2 *SP = CP + (nb ? NT + 2u : 0u);
   uint32_t *brows = reinterpret_cast<uint32_t *>(SP + (size_t)P4 * stride);
   tps_build_pattern_masks(pm, pt, K, tid, NT);
   const uint32_t n_items = a.counters[6];
 
-  /* words that must read zero: the pad word behind the oriented planes, the slots of SP behind the tile and of
-   * the rows that pad P to a multiple of 4, the pad word of the plain rows.  The change point of a read borrows
-   * the scratch, so this is redone after every one of them. */
-  auto clear_scratch = [&]() {
+  /* words between `scratch` and SP that must read zero: the pad word behind the oriented planes and behind the
+   * per-word tables.  The change point of a read borrows that part of the scratch: redone after each. */
+  auto clear_pads = [&]() {
     if (tid < 3u) ori[tid * (NT + 1u) + NT] = 0u;
-    for (uint32_t i = tid; i < P4 * stride; i += NT) SP[i] = make_uint2(0u, 0u);
-    for (uint32_t i = tid; i < nb * (NT + 1u); i += NT) brows[i] = 0u;
+    if (tid == 3u) Z[NT] = make_uint4(0u, 0u, 0u, 0u);
+    if (tid == 4u && nz > 4u) Zhi[NT] = make_uint4(0u, 0u, 0u, 0u);
+    if (tid == 5u) UP[NT] = make_uint2(0u, 0u);
+    if (tid == 6u && nb) CP[NT] = make_uint2(0u, 0u);
   };
   /* change point of the read in pass-list slot pi (all of its tiles are done and visible) */
   auto change_point = [&](uint32_t pi) {
     const uint32_t r = a.pass_list[pi];
-    const uint32_t nW = a.rows[r].n_windows;
-    const uint16_t *cw = a.cw16 + (size_t)pi * a.cw16_stride;
+    const uint32_t nW = a.rows[r].n_windows, ng = (nW + 4u) / 5u;
+    const uint16_t *gs = a.gs + (size_t)pi * a.gs_stride;
     int32_t best_b;
-    if (nW <= a.cp_cap) { /* stage the row: one round trip, then shared memory only */
+    if (ng <= a.cp_cap) { /* stage the row: one round trip, then shared memory only */
       uint16_t *sc = reinterpret_cast<uint16_t *>(scratch);
-      for (uint32_t i = tid; i < (nW + 7u) >> 3; i += NT) tps_cp_async16(sc + 8u * i, cw + 8u * i);
+      for (uint32_t i = tid; i < (ng + 7u) >> 3; i += NT) tps_cp_async16(sc + 8u * i, gs + 8u * i);
       tps_cp_async_wait_all();
       __syncthreads();
-      best_b = tps_changepoint_block(TpsCwShared16{sc}, nW, s_cp, tid);
+      best_b = tps_changepoint_block<5>(TpsCwShared16{sc}, nW, s_cp, tid);
       __syncthreads();
-      clear_scratch();
+      clear_pads();
     } else {
-      best_b = tps_changepoint_block(TpsCwGlobal16{cw}, nW, s_cp, tid);
+      best_b = tps_changepoint_block<5>(TpsCwGlobal16{gs}, nW, s_cp, tid);
     }
     if (tid == 0) tps_store_changepoint(a, r, best_b);
   };
 
-  clear_scratch();
+  /* words that stay zero for the whole kernel: the slots of SP behind the tile and of the rows that pad P to a
+   * multiple of 4, the pad word of the plain rows */
+  for (uint32_t i = tid; i < P4 * stride; i += NT) SP[i] = make_uint2(0u, 0u);
+  for (uint32_t i = tid; i < nb * (NT + 1u); i += NT) brows[i] = 0u;
+  clear_pads();
   if (tid == 0) {
     const uint32_t base = atomicAdd(a.counters + 1, 3u);
     s_idx[0] = base; s_idx[1] = base + 1u; s_idx[2] = base + 2u;
@@ -1399,12 +1444,19 @@ tps_window_bp_kernel(const TpsScanArgs a, const TpsPatTable pt) {
       }
       next_idx = atomicAdd(a.counters + 1, 1u);
     }
-    const uint32_t pi = rec.pi_rev & 0x7FFFFFFFu, tb0 = rec.tb0, tn = rec.tn;
+    const uint32_t pi = rec.pi_rev & 0x7FFFFFFFu, tn = rec.tn;
     const bool rev = rec.pi_rev >> 31;
-    uint16_t *cw = a.cw16 + (size_t)pi * a.cw16_stride;
     {
       const uint32_t phase = (uint32_t)(rec.g0 & 15u);
-      tps_stage_linear_raw(rawk, a.pk.bases, rec.g0, tn, lin, lw, tid, NT);
+      {
+        uint16_t *l0 = reinterpret_cast<uint16_t *>(lin), *l1 = reinterpret_cast<uint16_t *>(lin + lw),
+                 *lv = reinterpret_cast<uint16_t *>(lin + 2 * lw);
+        const uint64_t gfirst = rec.g0 >> 4;
+        const uint32_t ng = (uint32_t)(((rec.g0 + tn + 15u) >> 4) - gfirst);
+        tps_stage_entry_raw(rawk, a.pk.bases, gfirst, ng, tid, l0, l1, lv);
+        tps_stage_entry_raw(rawk, a.pk.bases, gfirst, ng, tid + NT, l0, l1, lv);
+        if (tid < 2u * lw - 2u * NT) tps_stage_entry_raw(rawk, a.pk.bases, gfirst, ng, tid + 2u * NT, l0, l1, lv);
+      }
       __syncthreads();
       {
         uint32_t p0, p1, v;
@@ -1468,40 +1520,44 @@ tps_window_bp_kernel(const TpsScanArgs a, const TpsPatTable pt) {
         CP[q] = make_uint2(CF, before);
       }
       __syncthreads();
-      /* (3) windows */
-      for (uint32_t w = rec.wlo + tid; w < rec.whi; w += NT) {
-        const uint32_t ls = w * s - tb0, e = ls + D; /* start positions [ls, e) */
-        const uint32_t q0 = ls >> 5, qe = e >> 5, b0 = ls & 31u;
-        const uint32_t m0 = (1u << b0) - 1u, me = (1u << (e & 31u)) - 1u;
-        const uint2 u0 = UP[q0], ue = UP[qe];
-        uint32_t c = ue.y + tps_popc32(ue.x & me) - u0.y - tps_popc32(u0.x & m0); /* occurrences of all literals */
-        const uint4 z = Z[q0];
-        const uint32_t r0 = __funnelshift_r(z.x, z.x, b0), r1 = __funnelshift_r(z.y, z.y, b0),
-                       r2 = __funnelshift_r(z.z, z.z, b0), r3 = __funnelshift_r(z.w, z.w, b0);
-        uint32_t present = (r0 & 1u) | (r1 & ~1u);
-        present = (present & 3u) | (r2 & ~3u);
-        present = ((present & 7u) | (r3 & ~7u)) & 15u;
-        if (nz > 4u) {
-          const uint4 zh = Zhi[q0];
-          present |= (__funnelshift_r(zh.x, zh.x, b0) & 16u) | (__funnelshift_r(zh.y, zh.y, b0) & 32u) |
-                     (__funnelshift_r(zh.z, zh.z, b0) & 64u);
+      /* (3) windows, one group of five per thread: sum_i c_(w+i) = sum_i [A(e_i) - A(ls_i)] + 5 P - sum_i present(ls_i)
+       * with A = prefix popcount of U.  The five starts ls + i s sit in one 32-bit view of the rows taken at
+       * ls (a funnel shift over words q0, q0+1), so A(ls_i) - A(ls_0) is a popcount under a constant mask, the
+       * same at the ends, and the five `present` bits of a count plane are one popcount under the mask gm */
+      const uint32_t n_groups = (rec.whi - rec.wlo + 4u) / 5u;
+      uint16_t *gs = a.gs + (size_t)pi * a.gs_stride + rec.wlo / 5u;
+      for (uint32_t gi = tid; gi < n_groups; gi += NT) {
+        const uint32_t ls = 5u * gi * s; /* tile origin = start of window wlo */
+        const uint32_t w0 = rec.wlo + 5u * gi;
+        uint32_t sum;
+        bool fast = grouped && w0 + 5u <= rec.whi;
+        if (fast && nb) { /* no two close starts of a self-overlapping literal anywhere in the five windows */
+          const uint32_t ee = ls + 4u * s + D;
+          const uint2 f0 = CP[ls >> 5], fe = CP[ee >> 5];
+          fast = fe.y + tps_popc32(fe.x & ((1u << (ee & 31u)) - 1u)) == f0.y + tps_popc32(f0.x & ((1u << (ls & 31u)) - 1u));
         }
-        c += P - present; /* absent literals count 1 each */
-        if (nb) {
-          const uint2 f0 = CP[q0], fe = CP[qe];
-          if (fe.y + tps_popc32(fe.x & me) - f0.y - tps_popc32(f0.x & m0)) {
-            for (uint64_t bm = pt.bordered_mask; bm; bm &= bm - 1) {
-              const uint32_t p = (uint32_t)__ffsll((long long)bm) - 1u;
-              const uint32_t *row = brows + pt.brow[p] * (NT + 1u);
-              uint32_t occ = tps_range_popcount(row, (int32_t)ls, (int32_t)e - 1);
-              uint32_t g = tps_greedy_count(row, (int32_t)ls, (int32_t)e - 1, (uint32_t)K);
-              occ = occ ? occ : 1u;
-              g = g ? g : 1u;
-              c = c - occ + g;
-            }
+        if (fast) {
+          const uint32_t q0 = ls >> 5, b0 = ls & 31u, e = ls + D, qe = e >> 5, be = e & 31u;
+          const uint2 u0 = UP[q0], ue = UP[qe];
+          const uint32_t ua = __funnelshift_r(u0.x, UP[q0 + 1u].x, b0), va = __funnelshift_r(ue.x, UP[qe + 1u].x, be);
+          const uint32_t a0 = u0.y + tps_popc32(u0.x & ((1u << b0) - 1u)), ae = ue.y + tps_popc32(ue.x & ((1u << be) - 1u));
+          sum = 5u * (ae - a0 + P) + (tps_popc32(va & lm1) + tps_popc32(va & lm2) + tps_popc32(va & lm3) + tps_popc32(va & lm4)) -
+                (tps_popc32(ua & lm1) + tps_popc32(ua & lm2) + tps_popc32(ua & lm3) + tps_popc32(ua & lm4));
+          const uint4 z0 = Z[q0], z1 = Z[q0 + 1u];
+          uint32_t present = tps_popc32(__funnelshift_r(z0.x, z1.x, b0) & gm) + 2u * tps_popc32(__funnelshift_r(z0.y, z1.y, b0) & gm) +
+                             4u * tps_popc32(__funnelshift_r(z0.z, z1.z, b0) & gm) + 8u * tps_popc32(__funnelshift_r(z0.w, z1.w, b0) & gm);
+          if (nz > 4u) {
+            const uint4 h0 = Zhi[q0], h1 = Zhi[q0 + 1u];
+            present += 16u * tps_popc32(__funnelshift_r(h0.x, h1.x, b0) & gm) + 32u * tps_popc32(__funnelshift_r(h0.y, h1.y, b0) & gm) +
+                       64u * tps_popc32(__funnelshift_r(h0.z, h1.z, b0) & gm);
           }
+          sum -= present;
+        } else {
+          sum = 0u;
+          for (uint32_t i = 0; i < 5u && w0 + i < rec.whi; ++i)
+            sum += tps_bp_window<K>(ls + i * s, D, P, nz, nb, pt, UP, Z, Zhi, CP, brows, NT + 1u);
         }
-        cw[w] = (uint16_t)c;
+        gs[gi] = (uint16_t)sum;
       }
     }
     /* completion: the atomic that counts this tile is issued now and looked at one tile later, when its answer
@@ -1510,7 +1566,7 @@ tps_window_bp_kernel(const TpsScanArgs a, const TpsPatTable pt) {
     if (tid == 0) {
       s_cp_go = has_pend && pend_old == s_pend_target - 1u;
       s_cp_pi = s_pend_pi;
-      __threadfence(); /* cumulative: the barrier ordered the CTA's c_w stores before it */
+      __threadfence(); /* cumulative: the barrier ordered the CTA's stores before it */
       pend_old = atomicAdd(a.tile_done + pi, 1u);
       has_pend = true;
       s_pend_pi = pi;

@@ -180,6 +180,13 @@ def follow_scan(seqs: Iterable, kmers: Sequence[str], match_len: int, min_seq_le
     return bits[..., :upto - skip].astype(bool)
 
 
+def group_sums(c_w) -> np.ndarray:
+    """Sums of c_w over the groups of five consecutive windows [5j, 5j+5) (the last group may be shorter)."""
+    c = np.asarray(c_w, dtype=np.int64)
+    pad = (-len(c)) % 5
+    return np.concatenate([c, np.zeros(pad, np.int64)]).reshape(-1, 5).sum(axis=1)
+
+
 class PinnedBuffer:
     """Page-locked host memory from the library, exposed as a numpy uint8 array."""
 
@@ -446,7 +453,9 @@ class ScanContext:
         return dict(cw_stride=int(v[0]), k3_bitpar=bool(v[1]), max_pass=int(v[2]), k3_tile_bases=int(v[3]))
 
     def window_sums(self, rows) -> dict:
-        """Test hook: {read index: c_w[0..n_windows)} of the TRC-pass reads of the last batch scanned on slot 0."""
+        """Test hook: {read index: sums of c_w over the groups of five windows [5j, 5j+5)} of the TRC-pass reads
+        of the last batch scanned on slot 0 (the bit-parallel kernel keeps exactly these; the plain kernel's
+        per-window c_w are summed here)."""
         n_pass = int((rows["status"] >= ST_PASS).sum())
         if n_pass == 0:
             return {}
@@ -454,7 +463,14 @@ class ScanContext:
         stride, dt = info["cw_stride"], (np.uint16 if info["k3_bitpar"] else np.uint32)
         plist = self.debug_copy(3, n_pass * 4).view(np.uint32)
         cw = self.debug_copy(4, n_pass * stride * np.dtype(dt).itemsize).view(dt).reshape(n_pass, stride)
-        return {int(r): cw[i, :int(rows["n_windows"][r])].copy() for i, r in enumerate(plist)}
+        out = {}
+        for i, r in enumerate(plist):
+            nw = int(rows["n_windows"][r])
+            if info["k3_bitpar"]:
+                out[int(r)] = cw[i, :(nw + 4) // 5].astype(np.int64)
+            else:
+                out[int(r)] = group_sums(cw[i, :nw])
+        return out
 
     def debug_copy(self, what: int, nbytes: int) -> np.ndarray:
         out = np.empty(nbytes, dtype=np.uint8)

@@ -213,9 +213,10 @@ int tps_follow_scan(int device, const uint8_t *bases, const uint64_t *offsets, u
  * (uint32 per 512 bases), 2 = validity masks as K2/K3 see them (uint16 per 16 bases: 0xFFFF for an
  * unflagged group, else rebuilt from the group's ASCII bytes), 3 = pass list (uint32 read indices, unordered),
  * 4 = window sums (row i = pass-list entry i, row stride in elements from 5): uint32 c_w per window under the
- * plain window kernel; under the bit-parallel kernel uint16 sums of c_w over the groups of five windows
- * [5j, 5j+5), which is all the change point reads, 5 = uint32[4] {row stride of 4, 1 if the bit-parallel window
- * kernel is in use, pass-list capacity, window-start positions per tile}. */
+ * plain window kernel; under the bit-parallel kernel, which keeps them in shared memory, uint16 sums of c_w over
+ * the groups of five windows [5j, 5j+5) -- what its change point reads -- and only if the context was created with
+ * TPS_K3_DEBUG_GS=1 in the environment (else TPS_ESTATE), 5 = uint32[4] {row stride of 4, 1 if the bit-parallel
+ * window kernel is in use, pass-list capacity, window-start positions per tile}. */
 int tps_debug_copy(tps_ctx *ctx, int what, void *dst, size_t bytes);
 
 #ifdef __cplusplus

@@ -31,6 +31,7 @@ def _scan(engine, pats, motif, reads, W, s, t, M, bitpar, monkeypatch, no_groups
         monkeypatch.setenv("TPS_K3_NO_GROUPS", "1")
     else:
         monkeypatch.delenv("TPS_K3_NO_GROUPS", raising=False)
+    monkeypatch.setenv("TPS_K3_DEBUG_GS", "1")     # the bit-parallel kernel also writes its group sums out
     with engine.ScanContext(pats, len_telopattern=len(motif), min_seq_length=0, count_threshold_override=0,
                             window_size=W, slide=s, trimfirst=t, maxlengthtelo=M, max_batch_reads=1024,
                             max_batch_bases=1 << 24, **kw) as ctx:

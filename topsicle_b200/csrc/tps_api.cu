@@ -39,8 +39,7 @@ struct Slot {
   uint32_t *d_counters = nullptr;
   uint8_t *d_raw = nullptr;
   uint32_t *d_cw = nullptr;         /* c_w rows of passing reads */
-  uint32_t *d_tile_done = nullptr;  /* bit-parallel K3: finished tiles per passing read */
-  TpsTile *d_items = nullptr;       /* bit-parallel K3: tile records listed by K2 */
+  TpsReadItem *d_items = nullptr;   /* bit-parallel K3: one record per TRC-pass read, listed by K2 */
   tps_row *h_rows = nullptr;        /* pinned */
   uint32_t *h_counters = nullptr;   /* pinned */
   uint64_t batch_id = 0;
@@ -63,7 +62,8 @@ struct tps_ctx {
   bool k3_bitpar = false;
   void (*k3n_fn)(const TpsScanArgs, const TpsPatTable) = nullptr;
   uint32_t k3n_lin_words = 0, k3n_stride = 0, k3n_tile_bases = 0, k3n_tiles_max = 0, k3n_smem = 0, k3n_grid = 0, k3n_nz = 0;
-  uint32_t k3n_cp_cap = 0, gs_stride = 0, k3n_tile_windows = 0, k3n_no_groups = 0;
+  uint32_t k3n_gs_cap = 0, k3n_tile_windows = 0, k3n_no_groups = 0;
+  bool k3n_debug_gs = false; /* TPS_K3_DEBUG_GS=1: the group sums of every read are also written to d_cw (tests) */
   uint32_t cw_stride = 0, max_pass = 0;
   int kt = 0; /* template K of the K2/K3 instantiation in use (0 = generic) */
   void (*k2_fn)(const TpsScanArgs, const TpsPatTable) = nullptr;
@@ -205,7 +205,7 @@ void tps_destroy(tps_ctx *ctx) {
     if (s.stream) cudaStreamSynchronize(s.stream);
     cudaFree(s.d_bases); cudaFree(s.d_codes); cudaFree(s.d_flags);
     cudaFree(s.d_off); cudaFree(s.d_len); cudaFree(s.d_true_len); cudaFree(s.d_tails); cudaFree(s.d_rows); cudaFree(s.d_pass); cudaFree(s.d_counters);
-    cudaFree(s.d_raw); cudaFree(s.d_cw); cudaFree(s.d_tile_done); cudaFree(s.d_items);
+    cudaFree(s.d_raw); cudaFree(s.d_cw); cudaFree(s.d_items);
     if (s.h_rows) cudaFreeHost(s.h_rows);
     if (s.h_counters) cudaFreeHost(s.h_counters);
     if (s.done) cudaEventDestroy(s.done);
@@ -318,7 +318,8 @@ int tps_create(tps_ctx **out, int device, const tps_params *params) {
     const char *e = getenv("TPS_K3_BITPAR"); /* 0 = tps_window_kernel + tps_changepoint_kernel (A/B, and the fallback) */
     ctx->k3_bitpar = ctx->kt > 0 && distinct && !p.want_rawcount && p.window_size >= (uint32_t)ctx->kt + 32u &&
                      p.window_size <= 2048u && 4ull * p.slide + p.window_size <= 32u * TPS_K3N_THREADS /* a tile holds a group */ &&
-                     5ull * cnt_max * pt.n <= 65535u /* group sums as uint16 */ && !(e && atoi(e) == 0);
+                     5ull * cnt_max * pt.n <= 65535u /* group sums as uint16 */ &&
+                     nw_max / 5 * 2 <= 32768 /* ... of a whole read in shared memory */ && !(e && atoi(e) == 0);
     if (ctx->k3_bitpar) {
       const uint32_t D = p.window_size - (uint32_t)ctx->kt, NT = TPS_K3N_THREADS;
       /* a tile stages (windows - 1) * slide + W <= 32 NT positions; whole groups of five windows */
@@ -330,16 +331,16 @@ int tps_create(tps_ctx **out, int device, const tps_params *params) {
       if (ctx->k3n_tiles_max == 0) ctx->k3n_tiles_max = 1;
       ctx->k3n_nz = 1;
       while ((1u << ctx->k3n_nz) <= pt.n) ctx->k3n_nz++;
-      const uint32_t head_words = 2 * TPS_K3N_RAW_WORDS + pm_words + 3; /* prefetch buffers, literal masks, alignment */
-      /* lin | ori | alignment | Z | Zhi | UP | CP: free between tiles (the change point stages a read's group sums here) */
-      const uint32_t free_words = 3 * ctx->k3n_lin_words + 3 * (NT + 1) + 3 + 4 * (NT + 1) + (ctx->k3n_nz > 4 ? 4 * (NT + 1) : 0) +
-                                  2 * (NT + 2) + (pt.n_bordered ? 2 * (NT + 2) : 0);
-      ctx->k3n_smem = (head_words + free_words + 2 * ((pt.n + 3u) & ~3u) * ctx->k3n_stride + pt.n_bordered * (NT + 1)) * 4;
-      ctx->k3n_cp_cap = (free_words * 2 - 16) & ~7u;
-      ctx->gs_stride = (uint32_t)(((nw_max + 4) / 5 + 7) & ~7ull);
-      if (ctx->gs_stride == 0) ctx->gs_stride = 8;
+      ctx->k3n_gs_cap = (uint32_t)(((nw_max + 4) / 5 + 7) & ~7ull); /* group sums of the longest read, in shared memory */
+      if (ctx->k3n_gs_cap == 0) ctx->k3n_gs_cap = 8;
+      /* raw[2] | pm | lin | ori | alignment | Z | Zhi | UP | CP | SP | brows | gsum */
+      ctx->k3n_smem = (2 * TPS_K3N_RAW_WORDS + pm_words + 3 * ctx->k3n_lin_words + 3 * (NT + 1) + 3 + 4 * (NT + 1) +
+                       (ctx->k3n_nz > 4 ? 4 * (NT + 1) : 0) + 2 * (NT + 2) + (pt.n_bordered ? 2 * (NT + 2) : 0) +
+                       2 * ((pt.n + 3u) & ~3u) * ctx->k3n_stride + pt.n_bordered * (NT + 1) + ctx->k3n_gs_cap / 2) * 4;
       const char *ng = getenv("TPS_K3_NO_GROUPS"); /* 1 = no five-window fast path (A/B) */
       ctx->k3n_no_groups = ng && atoi(ng) != 0;
+      const char *dg = getenv("TPS_K3_DEBUG_GS");
+      ctx->k3n_debug_gs = dg && atoi(dg) != 0;
     }
   }
   ctx->cw_stride = (uint32_t)(nw_max ? nw_max : 1);
@@ -464,10 +465,9 @@ int tps_create(tps_ctx **out, int device, const tps_params *params) {
     TPS_CC(cudaMalloc(&s.d_pass, (uint64_t)ctx->max_pass * sizeof(uint32_t)));
     TPS_CC(cudaMalloc(&s.d_counters, 8 * sizeof(uint32_t)));
     if (p.want_rawcount) TPS_CC(cudaMalloc(&s.d_raw, p.rawcount_capacity ? p.rawcount_capacity : 1));
-    if (ctx->k3_bitpar) { /* c_w rows as uint16 */
-      TPS_CC(cudaMalloc(&s.d_cw, (uint64_t)ctx->max_pass * ctx->gs_stride * sizeof(uint16_t)));
-      TPS_CC(cudaMalloc(&s.d_tile_done, (uint64_t)ctx->max_pass * sizeof(uint32_t)));
-      TPS_CC(cudaMalloc(&s.d_items, (uint64_t)ctx->max_pass * ctx->k3n_tiles_max * sizeof(TpsTile)));
+    if (ctx->k3_bitpar) { /* c_w never leaves the SM: group sums in shared memory */
+      TPS_CC(cudaMalloc(&s.d_items, (uint64_t)ctx->max_pass * sizeof(TpsReadItem)));
+      if (ctx->k3n_debug_gs) TPS_CC(cudaMalloc(&s.d_cw, (uint64_t)ctx->max_pass * ctx->k3n_gs_cap * sizeof(uint16_t)));
     } else {
       TPS_CC(cudaMalloc(&s.d_cw, (uint64_t)ctx->max_pass * ctx->cw_stride * sizeof(uint32_t)));
     }
@@ -586,15 +586,12 @@ int enqueue_scan(tps_ctx *ctx, Slot &s, cudaStream_t st, const ScanJob &job) {
   a.tile_bases = ctx->k3_tile_bases;
   a.tiles_max = ctx->k3_tiles_max;
   a.nq_max = ctx->k2_nq_max;
-  a.tile_done = s.d_tile_done;
   a.items = ctx->k3_bitpar ? s.d_items : nullptr;
-  a.bp_tile_bases = ctx->k3n_tile_bases;
   a.nz = ctx->k3n_nz;
-  a.gs = reinterpret_cast<uint16_t *>(s.d_cw);
-  a.gs_stride = ctx->gs_stride;
-  a.cp_cap = ctx->k3n_cp_cap;
   a.bp_tile_windows = ctx->k3n_tile_windows;
+  a.gs_cap = ctx->k3n_gs_cap;
   a.no_groups = ctx->k3n_no_groups;
+  a.gs_debug = ctx->k3_bitpar && ctx->k3n_debug_gs ? reinterpret_cast<uint16_t *>(s.d_cw) : nullptr;
   if (n_reads) {
     a.lin_words = ctx->k2_lin_words;
     if (ctx->k2_reg)
@@ -998,12 +995,14 @@ int tps_debug_copy(tps_ctx *ctx, int what, void *dst, size_t bytes) {
     }
     case 3: src = s.d_pass; cap = (size_t)ctx->max_pass * sizeof(uint32_t); break;
     case 4:
+      if (ctx->k3_bitpar && !ctx->k3n_debug_gs)
+        return fail(ctx, TPS_ESTATE, "the bit-parallel window kernel keeps its window sums in shared memory (set TPS_K3_DEBUG_GS=1)");
       src = s.d_cw;
-      cap = ctx->k3_bitpar ? (size_t)ctx->max_pass * ctx->gs_stride * sizeof(uint16_t)
+      cap = ctx->k3_bitpar ? (size_t)ctx->max_pass * ctx->k3n_gs_cap * sizeof(uint16_t)
                            : (size_t)ctx->max_pass * ctx->cw_stride * sizeof(uint32_t);
       break;
     case 5: { /* geometry: c_w row stride (elements), which K3 is in use, pass capacity, tile size of that K3 */
-      const uint32_t info[4] = {ctx->k3_bitpar ? ctx->gs_stride : ctx->cw_stride, ctx->k3_bitpar ? 1u : 0u, ctx->max_pass,
+      const uint32_t info[4] = {ctx->k3_bitpar ? ctx->k3n_gs_cap : ctx->cw_stride, ctx->k3_bitpar ? 1u : 0u, ctx->max_pass,
                                 ctx->k3_bitpar ? ctx->k3n_tile_bases : ctx->k3_tile_bases};
       if (bytes > sizeof(info)) return fail(ctx, TPS_EINVAL, "debug info is %zu bytes", sizeof(info));
       memcpy(dst, info, bytes);

@@ -46,7 +46,7 @@ struct TpsPacked {
 };
 
 /* counters[]: [0] n_pass, [1] K3 work cursor, [2,3] rawcount cursor (u64), [4] overflow flags,
- * [5] K4 work cursor, [6] tile items of the bit-parallel K3 */
+ * [5] K4 work cursor, [6] read items of the bit-parallel K3 */
 #define TPS_OVF_RAWCOUNT 1u
 #define TPS_OVF_PASS 2u
 
@@ -72,32 +72,27 @@ struct TpsScanArgs {
   uint32_t tile_bases; /* K3: window-start positions per tile */
   uint32_t tiles_max;  /* K3: tiles per read at the longest region */
   uint32_t nq_max;     /* K2: ceil(no_bp/32) */
-  /* bit-parallel K3 (tps_window_bp_kernel): K2 appends one TpsTile record per tile of every TRC-pass read with
-   * at least 7 windows to `items` (counters[6] = number of records) and zeroes the read's entry of
-   * `tile_done`, the tiles finished so far.  The kernel keeps, per read, the sums of c_w over the groups of five
-   * consecutive windows [5j, 5j+5) -- all the change point needs (its candidates are the multiples of 5) -- as
-   * uint16 at gs + slot * gs_stride */
-  uint32_t *tile_done;
-  struct TpsTile *items;
-  uint32_t bp_tile_bases; /* window-start positions per tile (a multiple of 32) */
-  uint32_t nz;            /* count planes, 2^nz > P */
-  uint16_t *gs;
-  uint32_t gs_stride;     /* a multiple of 8: rows start on 16-byte boundaries */
-  uint32_t cp_cap;        /* group sums of one read that fit the kernel's shared-memory scratch */
+  /* bit-parallel K3 (tps_window_bp_kernel): K2 appends one TpsReadItem per TRC-pass read with at least 7
+   * windows to `items` (counters[6] = number of records) */
+  struct TpsReadItem *items;
+  uint32_t nz;              /* count planes, 2^nz > P */
   uint32_t bp_tile_windows; /* windows per tile at most (a multiple of 5) */
-  uint32_t no_groups;     /* 1 = every window on its own (A/B of the five-window fast path) */
+  uint32_t gs_cap;          /* uint16 group sums per read the kernel's shared memory holds */
+  uint32_t no_groups;       /* 1 = every window on its own (A/B of the five-window fast path) */
+  uint16_t *gs_debug;       /* test hook (TPS_K3_DEBUG_GS=1): group sums also go to gs_debug + slot * gs_cap, else null */
 };
 
-/* One work item of the bit-parallel K3: everything a CTA needs to stage and count one tile, worked out once by
- * K2 (which knows the read's start, length and orientation) so that the tile loop starts with one 32-byte load. */
-struct __align__(16) TpsTile {
-  uint64_t g0;     /* first base of the staged slice in the batch */
-  uint32_t tn;     /* staged oriented positions: from the start of window wlo to the end of window whi - 1 */
-  uint32_t wlo, whi; /* windows of the tile; wlo is a multiple of 5, whi too except at the end of the read */
-  uint32_t pi_rev; /* pass-list slot | reverse << 31 */
-  uint32_t ntiles; /* tiles of this read */
-  uint32_t reserved;
+/* One work item of the bit-parallel K3 = one TRC-pass read: what a CTA needs to walk its tiles, worked out once
+ * by K2 (which has the read's start, length and orientation at hand) so that a read starts with one 32-byte load. */
+struct __align__(16) TpsReadItem {
+  uint64_t g_edge; /* forward: batch index of region position 0; reverse: one past the batch index of region position 0 */
+  uint32_t n_windows;
+  uint32_t read;   /* row index */
+  uint32_t rev;    /* 1 = reverse tail: region position j is batch index g_edge - 1 - j */
+  uint32_t slot;   /* pass-list slot */
+  uint32_t reserved[2];
 };
+
 
 /* ------------------------------------------------------------------------------------ K1 */
 __device__ __forceinline__ uint4 tps_ldg_stream(const uint4 *p) {
@@ -497,25 +492,15 @@ __device__ __forceinline__ void tps_trc_decide(const TpsScanArgs &a, uint32_t n_
     const uint32_t slot = atomicAdd(a.counters + 0, 1u);
     if (slot < a.max_pass) {
       a.pass_list[slot] = r;
-      if (a.items && nW >= 7u) { /* the tiles of this read's windows (balanced, whole groups of 5), consecutive items */
-        const uint32_t ng = (nW + 4u) / 5u, gmax = a.bp_tile_windows / 5u;
-        const uint32_t nt = (ng + gmax - 1u) / gmax;
-        const uint32_t per = (ng + nt - 1u) / nt * 5u; /* windows per tile, <= bp_tile_windows */
-        uint32_t at = atomicAdd(a.counters + 6, nt);
-        for (uint32_t ti = 0; ti < nt; ++ti, ++at) {
-          TpsTile tl;
-          tl.wlo = ti * per;
-          tl.whi = tl.wlo + per < nW ? tl.wlo + per : nW;
-          const uint32_t tb0 = tl.wlo * a.slide;              /* oriented position of the first window start */
-          tl.tn = (tl.whi - tl.wlo - 1u) * a.slide + a.W;     /* the last window ends inside the region */
-          /* forward: read bases [off+t+tb0, +tn); reverse: region position j is read index L-1-(t+j) */
-          tl.g0 = fwd ? off + a.trimfirst + tb0 : off + L - a.trimfirst - tb0 - tl.tn;
-          tl.pi_rev = slot | (fwd ? 0u : 0x80000000u);
-          tl.ntiles = nt;
-          tl.reserved = 0u;
-          a.items[at] = tl;
-        }
-        a.tile_done[slot] = 0u;
+      if (a.items && nW >= 7u) { /* one work item per read for the bit-parallel K3 */
+        TpsReadItem it;
+        it.g_edge = fwd ? off + a.trimfirst : off + L - a.trimfirst;
+        it.n_windows = nW;
+        it.read = r;
+        it.rev = fwd ? 0u : 1u;
+        it.slot = slot;
+        it.reserved[0] = it.reserved[1] = 0u;
+        a.items[atomicAdd(a.counters + 6, 1u)] = it;
       }
       if (a.want_rawcount && nW) {
         const unsigned long long elems = (unsigned long long)nW * n_patterns;
@@ -1157,15 +1142,17 @@ tps_changepoint_kernel(const TpsScanArgs a) {
  * less than K ahead; a window without such a start inside is exact as it stands, the few others redo those
  * literals with the greedy walk.
  *
- * Work item = (passing read, tile), listed by K2 (no empty items); the next item is fetched while the current
- * one is processed.  A tile is <= 32 * TPS_K3N_THREADS oriented positions incl. the W-base halo, one 32-position
- * word per thread; the tiles of a read are balanced.  The CTA that completes a read's last tile (per-read
- * counter) runs tps_changepoint_block on the read's c_w: no second launch, and the change points overlap the
- * window counting of other reads.
+ * Work item = one passing read, listed by K2: a CTA walks the read's tiles one after the other (a tile is
+ * <= 32 * TPS_K3N_THREADS oriented positions from the start of its first window to the end of its last, one
+ * 32-position word per thread; tiles are balanced and hold whole groups of five windows), keeps the sums of c_w
+ * over the groups of five windows [5j, 5j+5) -- all the change point reads: its candidates are the multiples of
+ * 5 -- in shared memory and finishes with tps_changepoint_block: no second launch, no trip through global memory
+ * between the window counts and the change point, and the change points overlap the window counting of the
+ * CTA's neighbours.  The code words of the next tile and the record of the next read are prefetched (cp.async).
  *
- * dynamic shared memory (words): pm[2PK] | lin[3*lin_words] | ori[3*(NT+1)] | pad to 16 B | Z[NT] uint4 |
- * Zhi[NT] uint4 (nz > 4) | UP[NT] uint2 | CP[NT] uint2 (bordered) | SP[P4][sp_stride] uint2 {S, Pf}, P4 = P rounded
- * up to a multiple of 4 | brows[n_bordered][NT+1] */
+ * dynamic shared memory (words): raw[2][TPS_K3N_RAW_WORDS] | pm[2PK] | lin[3*lin_words] | ori[3*(NT+1)] | pad to
+ * 16 B | Z[NT+1] uint4 | Zhi[NT+1] uint4 (nz > 4) | UP[NT+2] uint2 | CP[NT+2] uint2 (bordered) | SP[P4][sp_stride]
+ * uint2 {S, Pf}, P4 = P rounded up to a multiple of 4 | brows[n_bordered][NT+1] | gsum[gs_cap] uint16 */
 #define TPS_K3N_THREADS 128
 
 #define TPS_CSA(h, l, x, y, z)                       \
@@ -1344,13 +1331,12 @@ tps_window_bp_kernel(const TpsScanArgs a, const TpsPatTable pt) {
   static_assert(K > 0, "the bit-parallel window kernel needs a common literal length");
   constexpr uint32_t NT = TPS_K3N_THREADS;
   extern __shared__ __align__(16) uint32_t smem[];
-  /* software pipeline over work items: at the top of iteration k the records of items k and k+1, the code words
-   * of item k and the index of item k+2 are in shared memory; the iteration issues the copies of the code words
-   * of item k+1 and of the record of item k+2 (cp.async) and the atomic for the index of item k+3, and collects
-   * them at its end -- the tile loop never waits for global memory */
-  __shared__ TpsTile s_rec[3];
-  __shared__ uint32_t s_idx[4];
-  __shared__ uint32_t s_cp_pi, s_cp_go, s_pend_pi, s_pend_target;
+  /* software pipeline: while read i is processed its CTA holds the record of read i+1 (cp.async, issued at the
+   * start of read i) and the index of read i+2 (atomic, issued at the start of read i, stored at its end); every
+   * tile issues the copy of the next tile's code words -- the next tile of the read or tile 0 of read i+1 -- and
+   * collects it at its end.  No step of the loop waits for global memory. */
+  __shared__ TpsReadItem s_item[2];
+  __shared__ uint32_t s_idx[3];
   __shared__ uint32_t s_wt[2][NT / 32];
   __shared__ TpsCpShared s_cp;
   const uint32_t tid = threadIdx.x, q = threadIdx.x;
@@ -1364,9 +1350,7 @@ tps_window_bp_kernel(const TpsScanArgs a, const TpsPatTable pt) {
   const uint32_t lm1 = (1u << s) - 1u, lm2 = (1u << (2u * s)) - 1u, lm3 = (1u << (3u * s)) - 1u, lm4 = (1u << (4u * s)) - 1u;
   uint32_t *raw = smem; /* two buffers of TPS_K3N_RAW_WORDS */
   uint2 *pm = reinterpret_cast<uint2 *>(smem + 2u * TPS_K3N_RAW_WORDS);
-  uint32_t *scratch = smem + 2u * TPS_K3N_RAW_WORDS + 2u * P * K; /* free between tiles up to SP */
-  scratch += (4u - ((uint32_t)(scratch - smem) & 3u)) & 3u;
-  uint32_t *lin = scratch;
+  uint32_t *lin = smem + 2u * TPS_K3N_RAW_WORDS + 2u * P * K;
   uint32_t *ori = lin + 3u * lw;
   uint32_t *al = ori + 3u * (NT + 1u);
   al += (4u - ((uint32_t)(al - smem) & 3u)) & 3u;
@@ -1376,83 +1360,91 @@ tps_window_bp_kernel(const TpsScanArgs a, const TpsPatTable pt) {
   uint2 *CP = UP + (NT + 2u);
   uint2 *SP = CP + (nb ? NT + 2u : 0u);
   uint32_t *brows = reinterpret_cast<uint32_t *>(SP + (size_t)P4 * stride);
+  uint16_t *gsum = reinterpret_cast<uint16_t *>(brows + nb * (NT + 1u)); /* group sums of the read in hand */
   tps_build_pattern_masks(pm, pt, K, tid, NT);
   const uint32_t n_items = a.counters[6];
-
-  /* words between `scratch` and SP that must read zero: the pad word behind the oriented planes and behind the
-   * per-word tables.  The change point of a read borrows that part of the scratch: redone after each. */
-  auto clear_pads = [&]() {
-    if (tid < 3u) ori[tid * (NT + 1u) + NT] = 0u;
-    if (tid == 3u) Z[NT] = make_uint4(0u, 0u, 0u, 0u);
-    if (tid == 4u && nz > 4u) Zhi[NT] = make_uint4(0u, 0u, 0u, 0u);
-    if (tid == 5u) UP[NT] = make_uint2(0u, 0u);
-    if (tid == 6u && nb) CP[NT] = make_uint2(0u, 0u);
-  };
-  /* change point of the read in pass-list slot pi (all of its tiles are done and visible) */
-  auto change_point = [&](uint32_t pi) {
-    const uint32_t r = a.pass_list[pi];
-    const uint32_t nW = a.rows[r].n_windows, ng = (nW + 4u) / 5u;
-    const uint16_t *gs = a.gs + (size_t)pi * a.gs_stride;
-    int32_t best_b;
-    if (ng <= a.cp_cap) { /* stage the row: one round trip, then shared memory only */
-      uint16_t *sc = reinterpret_cast<uint16_t *>(scratch);
-      for (uint32_t i = tid; i < (ng + 7u) >> 3; i += NT) tps_cp_async16(sc + 8u * i, gs + 8u * i);
-      tps_cp_async_wait_all();
-      __syncthreads();
-      best_b = tps_changepoint_block<5>(TpsCwShared16{sc}, nW, s_cp, tid);
-      __syncthreads();
-      clear_pads();
-    } else {
-      best_b = tps_changepoint_block<5>(TpsCwGlobal16{gs}, nW, s_cp, tid);
-    }
-    if (tid == 0) tps_store_changepoint(a, r, best_b);
-  };
-
-  /* words that stay zero for the whole kernel: the slots of SP behind the tile and of the rows that pad P to a
-   * multiple of 4, the pad word of the plain rows */
+  /* words that stay zero for the whole kernel: the pad word behind the oriented planes and the per-word tables,
+   * the slots of SP behind the tile and of the rows that pad P to a multiple of 4, the pad word of the plain rows */
+  if (tid < 3u) ori[tid * (NT + 1u) + NT] = 0u;
+  if (tid == 3u) Z[NT] = make_uint4(0u, 0u, 0u, 0u);
+  if (tid == 4u && nz > 4u) Zhi[NT] = make_uint4(0u, 0u, 0u, 0u);
+  if (tid == 5u) UP[NT] = make_uint2(0u, 0u);
+  if (tid == 6u && nb) CP[NT] = make_uint2(0u, 0u);
   for (uint32_t i = tid; i < P4 * stride; i += NT) SP[i] = make_uint2(0u, 0u);
   for (uint32_t i = tid; i < nb * (NT + 1u); i += NT) brows[i] = 0u;
-  clear_pads();
+
+  /* tile t of a read with n_windows windows: windows [t * per, min(n_windows, (t + 1) * per)), balanced, whole
+   * groups of five; staged positions from the start of its first window to the end of its last */
+  const uint32_t gmax = a.bp_tile_windows / 5u;
+  auto tiles_of = [&](uint32_t nW, uint32_t &per) {
+    const uint32_t ng = (nW + 4u) / 5u, nt = (ng + gmax - 1u) / gmax;
+    per = (ng + nt - 1u) / nt * 5u;
+    return nt;
+  };
+  auto prefetch_tile = [&](const TpsReadItem &it, uint32_t per, uint32_t t, uint32_t *buf) {
+    const uint32_t wlo = t * per, whi = wlo + per < it.n_windows ? wlo + per : it.n_windows;
+    const uint32_t tb0 = wlo * s, tn = (whi - wlo - 1u) * s + W;
+    const uint64_t g0 = it.rev ? it.g_edge - tb0 - tn : it.g_edge + tb0;
+    tps_prefetch_codes(a.pk, g0, tn, buf, tid);
+  };
+
   if (tid == 0) {
-    const uint32_t base = atomicAdd(a.counters + 1, 3u);
-    s_idx[0] = base; s_idx[1] = base + 1u; s_idx[2] = base + 2u;
-    if (base < n_items) s_rec[0] = a.items[base];
-    if (base + 1u < n_items) s_rec[1] = a.items[base + 1u];
+    const uint32_t base = atomicAdd(a.counters + 1, 2u);
+    s_idx[0] = base; s_idx[1] = base + 1u;
+    if (base < n_items) s_item[0] = a.items[base];
   }
   __syncthreads();
-  if (s_idx[0] < n_items) tps_prefetch_codes(a.pk, s_rec[0].g0, s_rec[0].tn, raw, tid);
+  if (s_idx[0] < n_items) {
+    uint32_t per0;
+    tiles_of(s_item[0].n_windows, per0);
+    prefetch_tile(s_item[0], per0, 0u, raw);
+  }
   tps_cp_async_wait_all();
   __syncthreads();
-  uint32_t pend_old = 0u;  /* thread 0: result of the completion atomic of the previous tile */
-  bool has_pend = false;
+  uint32_t buf = 0u; /* raw buffer that holds the tile in hand */
 
-  for (uint32_t k = 0;; ++k) {
-    if (s_idx[k & 3u] >= n_items) break;
-    const TpsTile rec = s_rec[k % 3u];
-    uint32_t *rawk = raw + (k & 1u) * TPS_K3N_RAW_WORDS;
-    /* prefetches for the next iterations */
-    if (s_idx[(k + 1u) & 3u] < n_items) {
-      const TpsTile &nx = s_rec[(k + 1u) % 3u];
-      tps_prefetch_codes(a.pk, nx.g0, nx.tn, raw + ((k + 1u) & 1u) * TPS_K3N_RAW_WORDS, tid);
-    }
-    uint32_t next_idx = 0u;
-    if (tid == 0) {
-      const uint32_t i2 = s_idx[(k + 2u) & 3u];
-      if (i2 < n_items) {
-        tps_cp_async16(&s_rec[(k + 2u) % 3u], a.items + i2);
-        tps_cp_async16(reinterpret_cast<uint8_t *>(&s_rec[(k + 2u) % 3u]) + 16, reinterpret_cast<const uint8_t *>(a.items + i2) + 16);
+  for (uint32_t i = 0;; ++i) {
+    if (s_idx[i % 3u] >= n_items) break;
+    const TpsReadItem it = s_item[i & 1u];
+    const uint32_t idx_next = s_idx[(i + 1u) % 3u];
+    uint32_t idx_next2 = 0u;
+    if (tid == 0) { /* record of read i+1, index of read i+2 */
+      if (idx_next < n_items) {
+        tps_cp_async16(&s_item[(i + 1u) & 1u], a.items + idx_next);
+        tps_cp_async16(reinterpret_cast<uint8_t *>(&s_item[(i + 1u) & 1u]) + 16, reinterpret_cast<const uint8_t *>(a.items + idx_next) + 16);
       }
-      next_idx = atomicAdd(a.counters + 1, 1u);
+      idx_next2 = atomicAdd(a.counters + 1, 1u);
     }
-    const uint32_t pi = rec.pi_rev & 0x7FFFFFFFu, tn = rec.tn;
-    const bool rev = rec.pi_rev >> 31;
-    {
-      const uint32_t phase = (uint32_t)(rec.g0 & 15u);
+    const uint32_t nW = it.n_windows;
+    uint32_t per;
+    const uint32_t ntiles = tiles_of(nW, per);
+    const bool rev = it.rev != 0u;
+
+    for (uint32_t t = 0; t < ntiles; ++t, buf ^= 1u) {
+      const uint32_t wlo = t * per, whi = wlo + per < nW ? wlo + per : nW;
+      const uint32_t tb0 = wlo * s, tn = (whi - wlo - 1u) * s + W;
+      const uint64_t g0 = rev ? it.g_edge - tb0 - tn : it.g_edge + tb0;
+      const uint32_t *rawk = raw + buf * TPS_K3N_RAW_WORDS;
+      /* code words of the next tile: of this read, or tile 0 of the next read (its record arrived during an
+       * earlier tile; a one-tile read waits for it here) */
+      if (t + 1u < ntiles) {
+        prefetch_tile(it, per, t + 1u, raw + (buf ^ 1u) * TPS_K3N_RAW_WORDS);
+      } else if (idx_next < n_items) {
+        if (ntiles == 1u) {
+          tps_cp_async_wait_all();
+          __syncthreads();
+        }
+        const TpsReadItem &nx = s_item[(i + 1u) & 1u];
+        uint32_t pern;
+        tiles_of(nx.n_windows, pern);
+        prefetch_tile(nx, pern, 0u, raw + (buf ^ 1u) * TPS_K3N_RAW_WORDS);
+      }
+      const uint32_t phase = (uint32_t)(g0 & 15u);
       {
         uint16_t *l0 = reinterpret_cast<uint16_t *>(lin), *l1 = reinterpret_cast<uint16_t *>(lin + lw),
                  *lv = reinterpret_cast<uint16_t *>(lin + 2 * lw);
-        const uint64_t gfirst = rec.g0 >> 4;
-        const uint32_t ng = (uint32_t)(((rec.g0 + tn + 15u) >> 4) - gfirst);
+        const uint64_t gfirst = g0 >> 4;
+        const uint32_t ng = (uint32_t)(((g0 + tn + 15u) >> 4) - gfirst);
         tps_stage_entry_raw(rawk, a.pk.bases, gfirst, ng, tid, l0, l1, lv);
         tps_stage_entry_raw(rawk, a.pk.bases, gfirst, ng, tid + NT, l0, l1, lv);
         if (tid < 2u * lw - 2u * NT) tps_stage_entry_raw(rawk, a.pk.bases, gfirst, ng, tid + 2u * NT, l0, l1, lv);
@@ -1524,13 +1516,13 @@ tps_window_bp_kernel(const TpsScanArgs a, const TpsPatTable pt) {
        * with A = prefix popcount of U.  The five starts ls + i s sit in one 32-bit view of the rows taken at
        * ls (a funnel shift over words q0, q0+1), so A(ls_i) - A(ls_0) is a popcount under a constant mask, the
        * same at the ends, and the five `present` bits of a count plane are one popcount under the mask gm */
-      const uint32_t n_groups = (rec.whi - rec.wlo + 4u) / 5u;
-      uint16_t *gs = a.gs + (size_t)pi * a.gs_stride + rec.wlo / 5u;
+      const uint32_t n_groups = (whi - wlo + 4u) / 5u;
+      uint16_t *gs = gsum + wlo / 5u;
       for (uint32_t gi = tid; gi < n_groups; gi += NT) {
         const uint32_t ls = 5u * gi * s; /* tile origin = start of window wlo */
-        const uint32_t w0 = rec.wlo + 5u * gi;
+        const uint32_t w0 = wlo + 5u * gi;
         uint32_t sum;
-        bool fast = grouped && w0 + 5u <= rec.whi;
+        bool fast = grouped && w0 + 5u <= whi;
         if (fast && nb) { /* no two close starts of a self-overlapping literal anywhere in the five windows */
           const uint32_t ee = ls + 4u * s + D;
           const uint2 f0 = CP[ls >> 5], fe = CP[ee >> 5];
@@ -1554,33 +1546,26 @@ tps_window_bp_kernel(const TpsScanArgs a, const TpsPatTable pt) {
           sum -= present;
         } else {
           sum = 0u;
-          for (uint32_t i = 0; i < 5u && w0 + i < rec.whi; ++i)
-            sum += tps_bp_window<K>(ls + i * s, D, P, nz, nb, pt, UP, Z, Zhi, CP, brows, NT + 1u);
+          for (uint32_t j = 0; j < 5u && w0 + j < whi; ++j)
+            sum += tps_bp_window<K>(ls + j * s, D, P, nz, nb, pt, UP, Z, Zhi, CP, brows, NT + 1u);
         }
         gs[gi] = (uint16_t)sum;
       }
+      tps_cp_async_wait_all();
+      __syncthreads();
     }
-    /* completion: the atomic that counts this tile is issued now and looked at one tile later, when its answer
-     * has long arrived; the CTA that completed a read's last tile finds its change point */
-    __syncthreads();
-    if (tid == 0) {
-      s_cp_go = has_pend && pend_old == s_pend_target - 1u;
-      s_cp_pi = s_pend_pi;
-      __threadfence(); /* cumulative: the barrier ordered the CTA's stores before it */
-      pend_old = atomicAdd(a.tile_done + pi, 1u);
-      has_pend = true;
-      s_pend_pi = pi;
-      s_pend_target = rec.ntiles;
-      s_idx[(k + 3u) & 3u] = next_idx;
+    if (a.gs_debug) /* test hook */
+      for (uint32_t j = tid; j < (nW + 4u) / 5u; j += NT) a.gs_debug[(size_t)it.slot * a.gs_cap + j] = gsum[j];
+    /* the read's change point, straight from its group sums in shared memory */
+    {
+      const int32_t best_b = tps_changepoint_block<5>(TpsCwShared16{gsum}, nW, s_cp, tid);
+      if (tid == 0) {
+        tps_store_changepoint(a, it.read, best_b);
+        s_idx[(i + 2u) % 3u] = idx_next2;
+      }
     }
-    tps_cp_async_wait_all();
     __syncthreads();
-    if (s_cp_go) change_point(s_cp_pi);
   }
-  __syncthreads();
-  if (tid == 0) s_cp_go = has_pend && pend_old == s_pend_target - 1u;
-  __syncthreads();
-  if (s_cp_go) change_point(s_pend_pi);
 }
 
 /* ------------------------------------------------------------------------------------ K5

@@ -454,8 +454,9 @@ class ScanContext:
 
     def window_sums(self, rows) -> dict:
         """Test hook: {read index: sums of c_w over the groups of five windows [5j, 5j+5)} of the TRC-pass reads
-        of the last batch scanned on slot 0 (the bit-parallel kernel keeps exactly these; the plain kernel's
-        per-window c_w are summed here)."""
+        of the last batch scanned on slot 0.  The bit-parallel kernel keeps exactly these (in shared memory; it
+        writes them out only if the context was created under TPS_K3_DEBUG_GS=1); the plain kernel's per-window
+        c_w are summed here."""
         n_pass = int((rows["status"] >= ST_PASS).sum())
         if n_pass == 0:
             return {}
@@ -466,10 +467,9 @@ class ScanContext:
         out = {}
         for i, r in enumerate(plist):
             nw = int(rows["n_windows"][r])
-            if info["k3_bitpar"]:
-                out[int(r)] = cw[i, :(nw + 4) // 5].astype(np.int64)
-            else:
-                out[int(r)] = group_sums(cw[i, :nw])
+            if nw < 7:
+                continue
+            out[int(r)] = cw[i, :(nw + 4) // 5].astype(np.int64) if info["k3_bitpar"] else group_sums(cw[i, :nw])
         return out
 
     def debug_copy(self, what: int, nbytes: int) -> np.ndarray:

@@ -145,3 +145,78 @@ def test_ends_first_small_batches_split_regions(tmp_path, monkeypatch):
             assert (a.counts is None) == (b.counts is None)
             if a.counts is not None:
                 assert np.array_equal(a.counts, b.counts)
+
+
+@pytest.mark.parametrize("ends_first", ["0", "1"])
+def test_directory_with_bad_files_goes_on(tmp_path, monkeypatch, ends_first):
+    """One unreadable file of --inputDir ends THAT file, not the run: the reference walks every file of the
+    directory (main.py:224-229) and only logs a parse error (allsteps.py:137-149), keeping the reads parsed before
+    a bad record and processing the other files.  A stray text file, an empty file and a FASTQ with a truncated
+    record next to two good inputs: both good files give their 17 rows, the reads before the bad record count."""
+    import gzip
+    import shutil
+    fake_engine.install(monkeypatch)
+    monkeypatch.setenv("TOPSICLE_ENDS_FIRST", ends_first)
+    from topsicle_b200 import main as tmain
+    ind, out = tmp_path / "in", tmp_path / "out"
+    ind.mkdir()
+    demo = os.path.join(GOLD, "demo.fastq.gz")
+    shutil.copy(demo, ind / "a.fastq.gz")
+    shutil.copy(demo, ind / "b.fastq.gz")
+    (ind / "notes.txt").write_text("these are not reads\n")
+    (ind / "empty.fastq").write_text("")
+    text = gzip.open(demo, "rt").read().split("\n")
+    # 30 good records, then one whose quality line is shorter than its sequence line, then more good ones
+    bad = text[:4 * 30] + [text[120], text[121], "+", text[123][:10]] + text[124:4 * 40] + [""]
+    (ind / "trunc.fastq").write_text("\n".join(bad))
+    if hasattr(tmain.tprint, "logfile"):
+        del tmain.tprint.logfile
+    tmain.main(["--inputDir", str(ind), "--outputDir", str(out), "--pattern", "CCCTAAA", "--slide", "6", "--threads", "2"])
+    rows = [r.split(",") for r in open(out / "telolengths_all.csv", newline="").read().split("\r\n")[1:] if r]
+    by_file = {}
+    for r in rows:
+        by_file.setdefault(r[0], []).append(r)
+    assert len(by_file["a.fastq"]) == 17 and len(by_file["b.fastq"]) == 17
+    assert [r[3:] for r in by_file["a.fastq"]] == [r[3:] for r in by_file["b.fastq"]]
+    ids30 = {ln.split()[0][1:] for ln in text[:120:4]}
+    assert {r[3] for r in by_file.get("trunc", [])} == {r[3] for r in by_file["a.fastq"] if r[3] in ids30}
+    log = open(out / "topsicle_run.log").read()
+    for name in ("notes.txt", "trunc.fastq"):
+        assert f"Error occurred while parsing file {ind / name}" in log
+    assert "All telomere found" in log
+
+
+def test_reader_error_does_not_hang(tmp_path, monkeypatch):
+    """A reader thread that dies (not a parse error: those end only their file) must wake the other readers
+    that wait for a free slot; scan_files raises instead of hanging in join()."""
+    import threading
+    fake_engine.install(monkeypatch)
+    from topsicle_b200 import fastx, pipeline
+    from topsicle_b200.patterns import patterns_to_search
+    cfg = pipeline.ScanConfig(patterns=patterns_to_search("CCCTAAA", 5), len_telopattern=7, phrase=5, slide=6)
+    demo = os.path.join(GOLD, "demo.fastq.gz")
+    real = fastx.FastxFile.next_spans
+    calls = {"n": 0}
+
+    def flaky(self, *a, **kw):
+        calls["n"] += 1
+        if calls["n"] == 3:
+            raise MemoryError("simulated reader failure")
+        return real(self, *a, **kw)
+
+    monkeypatch.setattr(fastx.FastxFile, "next_spans", flaky)
+    jobs = [pipeline.FileJob(demo, lambda res: None) for _ in range(4)]
+    done = {}
+
+    def run():
+        try:
+            with pipeline.Scanner([cfg], devices=[0], depth=1, max_batch_reads=8, max_batch_bases=1 << 22) as sc:
+                sc.scan_files(jobs, readers=4)
+        except BaseException as e:  # noqa: BLE001
+            done["error"] = e
+
+    t = threading.Thread(target=run, daemon=True)
+    t.start()
+    t.join(60)
+    assert not t.is_alive(), "scan_files hung after a reader error"
+    assert isinstance(done.get("error"), MemoryError)

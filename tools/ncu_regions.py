@@ -9,11 +9,13 @@ MARKS = [("stage_fn", "tps_stage_linear(const TpsPacked"), ("oriented_fn", "tps_
          ("match_fn", "per-position matching"), ("rowlogic", "step-1 row logic"), ("cp", "#define TPS_K4_THREADS 128"),
          ("k4_kernel", "Stand-alone K4"), ("scan", "tps_block_excl_scan(uint32_t v"), ("dilate", "tps_dilate(const uint2"),
          ("planes", "tps_presence_planes(const uint2"), ("prefetch", "tps_cp_async16(void"),
-         ("stage_raw", "tps_stage_linear_raw(const uint32_t"), ("kernel_setup", "tps_window_bp_kernel(const TpsScanArgs a"),
-         ("cp_call", "auto change_point = "), ("prologue", "clear_scratch();\n  if (tid == 0) {"),
-         ("item", "for (uint32_t k = 0;; ++k) {"), ("stagecall", "tps_stage_linear_raw(rawk"),
+         ("kernel_setup", "tps_window_bp_kernel(const TpsScanArgs a"),
+         ("stage_raw", "tps_stage_entry_raw(const uint32_t"), ("bp_window_fn", "tps_bp_window(uint32_t ls"),
+         ("prologue", "auto tiles_of = "), ("read_loop", "for (uint32_t i = 0;; ++i) {"),
+         ("tile_top", "for (uint32_t t = 0; t < ntiles; ++t, buf ^= 1u) {"), ("stagecall", "const uint32_t phase = (uint32_t)(g0 & 15u);"),
          ("pass1", "(1) match words of word q"), ("pass2", "(2) presence rows R_p of word q"),
-         ("windows", "/* (3) windows */"), ("completion", "/* completion: the atomic"), ("end", "K5")]
+         ("windows", "/* (3) windows, one group of five"), ("tile_end", "tps_cp_async_wait_all();\n      __syncthreads();\n    }"),
+         ("cp_call", "/* the read's change point, straight"), ("end", "K5")]
 
 
 def main():

@@ -444,6 +444,12 @@ static int index_window(tps_fastx *fx, const uint8_t *w, uint64_t win_end, int f
     memset(out, 0, sizeof(*out)); /* fall through to the sequential index (also reports errors) */
   }
   index_fn(w, 0, win_end, win_end, final, out);
+  if (out->status == TPS_FX_EFORMAT && out->n > 0) {
+    /* the records before the malformed one are delivered as they are (the reference keeps what it parsed
+     * before a bad record, allsteps.py:137-149); the next window starts at the bad record and reports it */
+    out->status = 0;
+    return TPS_FX_OK;
+  }
   if (out->status == TPS_FX_EFORMAT) {
     free(out->v);
     out->v = NULL;

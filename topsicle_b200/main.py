@@ -90,7 +90,10 @@ class _FileWriter:
         # every phrase (last one stays), with FASTA input the first phrase's file is reused (main.py:64-66)
         is_fastq_name = name.endswith(".fastq") or name.endswith(".fq")
         self.records_cfg = None if self.subset_exists else (len(cfgs) - 1 if is_fastq_name else 0)
-        self.subset_handle = None if self.subset_exists else open(self.subset, "wb")
+        # opened at the file's first batch, not here: a directory may hold more files than `ulimit -n`, and an
+        # aborted run must not leave truncated subsets of files it never reached (main.py:82 opens per file)
+        self.subset_handle = None
+        self._closed = False
         self.rows = [[] for _ in cfgs]          # per phrase: CSV rows (held: the CSV is phrase-major)
         self.results = [[] for _ in cfgs]       # per phrase: (telolen, trc)
         self.image_num = [1 for _ in cfgs]
@@ -105,7 +108,7 @@ class _FileWriter:
             cfg, phrase = self.cfgs[k], self.phrases[k]
             for p in passes:
                 if self.records_cfg == k and p.record is not None:
-                    self.subset_handle.write(p.record)
+                    self._subset().write(p.record)
                 if args.read_check and p.read_id != args.read_check:
                     continue
                 if p.status != engine.ST_PASS:
@@ -139,7 +142,18 @@ class _FileWriter:
             with _csv_lock, open(self.csv_path, mode="a", newline="") as file:   # files are scanned concurrently
                 csv.writer(file).writerows(new_first)
 
-    def close(self):
+    def _subset(self):
+        if self.subset_handle is None:
+            self.subset_handle = open(self.subset, "wb")
+        return self.subset_handle
+
+    def close(self, create=True):
+        """`create`: the file was processed: the subset exists afterwards even if no read passed (main.py:82)."""
+        if self._closed:
+            return
+        self._closed = True
+        if self.subset_handle is None and create and not self.subset_exists:
+            self._subset()
         if self.subset_handle is not None:
             self.subset_handle.close()
             self.subset_handle = None
@@ -172,7 +186,10 @@ def file_job(args, seq_loc, telo_phrases, scanner, sliding_val):
         if not w.subset_exists:
             tprint(f"Temporary fasta file with TRC more than {min_cutoff}:", w.subset)
 
-    return w, pipeline.FileJob(seq_loc, w, records_cfg=w.records_cfg, on_done=on_done)
+    def on_error(e):     # allsteps.py:147-149: the error is logged, the reads parsed before it are kept
+        tprint(f"Error occurred while parsing file {seq_loc}: {e}")
+
+    return w, pipeline.FileJob(seq_loc, w, records_cfg=w.records_cfg, on_done=on_done, on_error=on_error)
 
 
 def analysis_run(args):
@@ -281,7 +298,7 @@ def analysis_run(args):
                     csv_rows[k].extend(w.rows[k])
     finally:
         for w in writers:
-            w.close()
+            w.close(create=False)     # files the run never reached leave no empty subset behind
         scanner.close()
     if os.environ.get("TOPSICLE_TIMING"):
         print(f"[timing] contexts + pinned staging {t_created - t0:.3f} s, scan {t_scanned - t_created:.3f} s, "

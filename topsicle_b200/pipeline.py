@@ -485,8 +485,13 @@ class Scanner:
 
         `sink(BatchResult)` is called in file order; BatchResult.passes[k] holds the TRC-pass reads
         under cfgs[k].  `records_cfg=k` attaches the SeqIO.write text of the reads passing cfgs[k].
-        `keep_ids` restricts the harvest to those read ids."""
-        return self.scan_files([FileJob(path, sink, records_cfg=records_cfg, keep_ids=keep_ids)], readers=1)[0]
+        `keep_ids` restricts the harvest to those read ids.  A parse error is raised (scan_files, which walks
+        many files, hands it to the job's on_error instead and goes on)."""
+        job = FileJob(path, sink, records_cfg=records_cfg, keep_ids=keep_ids)
+        stats = self.scan_files([job], readers=1)[0]
+        if job.error is not None:
+            raise job.error
+        return stats
 
     def scan_files(self, jobs: Sequence["FileJob"], *, readers: int = 0) -> list:
         """Scan several files concurrently (the reference's unit of parallelism is the input file,
@@ -545,6 +550,14 @@ class Scanner:
             if done:
                 finalize(job)
 
+        def parse_failed(job, e):
+            """An unreadable file or record ends THAT file, not the run: the reference walks every file of the
+            directory, logs the parse error and keeps the reads parsed before it (allsteps.py:137-149,
+            main.py:224-235)."""
+            job.error = e
+            if job.on_error is not None:
+                job.on_error(e)
+
         def read_loop():
             try:
                 while not errors:
@@ -553,26 +566,36 @@ class Scanner:
                     except queue.Empty:
                         return
                     t = time.perf_counter()
-                    job.fx = fastx.FastxFile(job.path, threads=fx_threads)
+                    try:
+                        job.fx = fastx.FastxFile(job.path, threads=fx_threads)
+                    except (fastx.FastxError, OSError) as e:
+                        parse_failed(job, e)
                     job.stats.timing["open"] = time.perf_counter() - t
-                    job.stats.format_name = job.fx.format_name
                     seq = 0
-                    while not errors:
+                    if job.fx is not None:
+                        job.stats.format_name = job.fx.format_name
+                    while job.fx is not None and not errors:
                         slot = free.get()
                         if slot is None:
                             free.put(None)      # let the other readers see the stop signal too
                             return
                         t = time.perf_counter()
-                        if self.ends_first:
-                            batch = job.fx.next_ends(slot.bases.array, slot.offsets.array.view(np.uint64),
-                                                     slot.lens.array.view(np.uint32),
-                                                     slot.true_lens.array.view(np.uint32), self.end_len,
-                                                     raw_cap=self.ends_raw_bytes, max_reads=w0.max_batch_reads,
-                                                     max_bases=w0.max_batch_bases, recs=slot.recs)
-                        else:
-                            batch = job.fx.next_spans(slot.bases.array, slot.offsets.array.view(np.uint64),
-                                                      slot.lens.array.view(np.uint32), max_reads=w0.max_batch_reads,
-                                                      max_span=w0.max_batch_bases, recs=slot.recs)
+                        try:
+                            if self.ends_first:
+                                batch = job.fx.next_ends(slot.bases.array, slot.offsets.array.view(np.uint64),
+                                                         slot.lens.array.view(np.uint32),
+                                                         slot.true_lens.array.view(np.uint32), self.end_len,
+                                                         raw_cap=self.ends_raw_bytes, max_reads=w0.max_batch_reads,
+                                                         max_bases=w0.max_batch_bases, recs=slot.recs)
+                            else:
+                                batch = job.fx.next_spans(slot.bases.array, slot.offsets.array.view(np.uint64),
+                                                          slot.lens.array.view(np.uint32),
+                                                          max_reads=w0.max_batch_reads, max_span=w0.max_batch_bases,
+                                                          recs=slot.recs)
+                        except fastx.FastxError as e:
+                            free.put(slot)
+                            parse_failed(job, e)
+                            break
                         job.stats.timing["parse"] += time.perf_counter() - t
                         if batch is None:
                             free.put(slot)
@@ -589,6 +612,7 @@ class Scanner:
                         finalize(job)
             except BaseException as e:  # noqa: BLE001 - reported to the caller below
                 errors.append(e)
+                free.put(None)   # wake the readers that wait for a slot: the workers stop returning them
 
         def work_loop(w: _DeviceWorker):
             inflight = []
@@ -654,12 +678,14 @@ class FileJob:
     """One input file of a `Scanner.scan_files` call."""
 
     def __init__(self, path: str, sink: Callable[[BatchResult], None], *, records_cfg: int | None = None,
-                 keep_ids=None, on_done: Callable[[FileStats], None] | None = None):
+                 keep_ids=None, on_done: Callable[[FileStats], None] | None = None,
+                 on_error: Callable[[Exception], None] | None = None):
         self.path = path
         self.sink = sink
         self.records_cfg = records_cfg
         self.keep_ids = keep_ids
         self.on_done = on_done
+        self.on_error = on_error     # parse error of this file (the scan goes on with the other files)
         self._reset()
 
     def _reset(self):
@@ -670,6 +696,7 @@ class FileJob:
         self.fx = None
         self.eof = False
         self.n_delivered = 0
+        self.error = None            # the FastxError / OSError that ended this file early, if any
 
 
 def scan_file(path: str, cfgs: Sequence[ScanConfig], sink: Callable[[BatchResult], None], *,

@@ -15,6 +15,7 @@ Outputs (committed, small):
   tests/golden/demo_heatmap.json      patterns_vs_match_heatmap CSV md5s (overview_plot.py --recfindingpattern --rawcount)
   tests/golden/edge.fastq / edge.fasta   crafted edge-case reads
   tests/golden/edge.json              reference function outputs on them
+  tests/golden/cli_parser.json        the reference CLI's argparse table (main.py:319-334) and --help text
 
 Usage:  python oracle/make_golden.py
 """
@@ -326,8 +327,50 @@ def edge_cases(fastq_path, fasta_path):
     return out
 
 
+def cli_parser_spec():
+    """The reference's argparse table (main.py:319-334), captured from the unmodified Topsicle.main.main(): every
+    option with its strings, dest, nargs, default, type, required flag, metavar and help text, plus the parser's
+    description and the text of `topsicle --help`."""
+    import argparse
+    import Topsicle.main as tmain
+    seen = {}
+
+    class Stop(Exception):
+        pass
+
+    def capture(self, *a, **kw):
+        seen["parser"] = self
+        raise Stop()
+
+    old_parse, old_argv = argparse.ArgumentParser.parse_args, sys.argv
+    argparse.ArgumentParser.parse_args = capture
+    sys.argv = ["topsicle"]
+    try:
+        tmain.main()
+    except Stop:
+        pass
+    finally:
+        argparse.ArgumentParser.parse_args = old_parse
+        sys.argv = old_argv
+    parser = seen["parser"]
+    parser.prog = "topsicle"
+    opts = []
+    for act in parser._actions:
+        if isinstance(act, argparse._HelpAction):
+            continue
+        opts.append(dict(option_strings=list(act.option_strings), dest=act.dest, nargs=act.nargs, default=act.default,
+                         type=getattr(act.type, "__name__", None), required=bool(act.required),
+                         metavar=act.metavar, help=act.help, action=type(act).__name__))
+    os.environ["COLUMNS"] = "100"
+    return dict(description=parser.description, formatter=parser.formatter_class.__name__, options=opts,
+                help_text=parser.format_help())
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
+    if "--cli-parser" in sys.argv:   # only the argparse table of the reference CLI
+        json.dump(cli_parser_spec(), open(os.path.join(GOLD, "cli_parser.json"), "w"), indent=1)
+        return
     if "--heatmap" in sys.argv:      # only the overview heat-map fixtures (the others are left as committed)
         json.dump(demo_heatmap(), open(os.path.join(GOLD, "demo_heatmap.json"), "w"), indent=1)
         return
@@ -359,6 +402,8 @@ def main():
     json.dump(edge_cases(fq, fa), open(os.path.join(GOLD, "edge.json"), "w"), indent=0)
     print("[6] overview heat map")
     json.dump(demo_heatmap(), open(os.path.join(GOLD, "demo_heatmap.json"), "w"), indent=1)
+    print("[7] CLI argparse table")
+    json.dump(cli_parser_spec(), open(os.path.join(GOLD, "cli_parser.json"), "w"), indent=1)
     print("done")
 
 

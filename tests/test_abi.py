@@ -10,8 +10,8 @@ from tests.conftest import REPO
 from topsicle_b200 import engine, fastx
 
 
-def declared_functions():
-    text = open(os.path.join(REPO, "include", "topsicle_b200.h")).read()
+def declared_functions(header="topsicle_b200.h"):
+    text = open(os.path.join(REPO, "include", header)).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     names = re.findall(r"^\s*(?:const\s+)?[A-Za-z_][\w\s\*]*?\b(tps_\w+)\s*\(", text, flags=re.M)
     return sorted(set(names))
@@ -67,11 +67,37 @@ def test_no_cpu_fallback():
     assert b"ABI mismatch" in lib.tps_last_error(None)
 
 
-def test_host_library_symbols():
+def test_host_library_exports_every_declared_symbol():
+    """include/topsicle_host.h is the ABI of libtps_host.so (reader, formatters, workload generator)."""
     lib = fastx.host_library()
-    for name in ("tps_fastx_open", "tps_fastx_next", "tps_fastx_release", "tps_fastx_close", "tps_fastx_find_id",
-                 "tps_format_rawcount", "tps_synth_fill", "tps_synth_lengths"):
-        assert getattr(lib, name) is not None
+    names = declared_functions("topsicle_host.h")
+    for must in ("tps_fastx_open", "tps_fastx_next", "tps_fastx_next_spans", "tps_fastx_next_ends", "tps_fastx_release",
+                 "tps_fastx_close", "tps_fastx_find_id", "tps_fastx_join_ids", "tps_fastx_gather_regions",
+                 "tps_fastx_records_text", "tps_format_rawcount", "tps_synth_fill", "tps_synth_lengths",
+                 "tps_host_threads"):
+        assert must in names, must
+    for name in names:
+        assert getattr(lib, name) is not None, name
+    # and nothing is exported that the header does not declare
+    import subprocess
+    out = subprocess.check_output(["nm", "-D", "--defined-only", fastx.HOST_LIB_PATH], text=True)
+    exported = sorted(ln.split()[-1] for ln in out.splitlines() if " T tps_" in ln)
+    assert exported == names
+
+
+def test_host_struct_layout_matches_header(tmp_path):
+    import subprocess
+    from topsicle_b200 import synth
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "topsicle_host.h"\n'
+                   'int main(void){printf("%zu %zu %zu %zu %zu\\n", sizeof(tps_fastx_rec), offsetof(tps_fastx_rec, seq_len),'
+                   'sizeof(tps_synth_cfg), offsetof(tps_synth_cfg, f_telo), offsetof(tps_synth_cfg, motif));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(REPO, "include"), "-o", str(exe), str(src)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    S = synth.SynthCfg
+    assert got == [fastx.REC_DTYPE.itemsize, fastx.REC_DTYPE.fields["seq_len"][1], C.sizeof(S), S.f_telo.offset,
+                   S.motif.offset]
 
 
 def test_product_never_imports_the_oracle():

@@ -220,3 +220,43 @@ def test_reader_error_does_not_hang(tmp_path, monkeypatch):
     t.join(60)
     assert not t.is_alive(), "scan_files hung after a reader error"
     assert isinstance(done.get("error"), MemoryError)
+
+
+def test_parser_equals_reference():
+    """Flag names, dest, nargs, defaults, types, required flags, metavars and help sentences of the `topsicle` CLI
+    equal those of the reference's parser (main.py:319-334; tests/golden/cli_parser.json is captured from the
+    unmodified Topsicle.main by oracle/make_golden.py), and so does the `--help` text of the shared flags."""
+    import argparse
+    from tests.conftest import load_json
+    from topsicle_b200 import main as tmain
+    want = load_json("cli_parser.json")
+    p = tmain.build_parser()
+    assert p.description == want["description"] and p.formatter_class.__name__ == want["formatter"]
+    got = {a.dest: a for a in p._actions if not isinstance(a, argparse._HelpAction)}
+    for o in want["options"]:
+        a = got.pop(o["dest"])
+        assert (list(a.option_strings), a.nargs, a.default, getattr(a.type, "__name__", None), bool(a.required),
+                a.metavar, a.help, type(a).__name__) == (o["option_strings"], o["nargs"], o["default"], o["type"],
+                                                        o["required"], o["metavar"], o["help"], o["action"]), o["dest"]
+    assert sorted(got) == ["devices", "ends_first"]          # what this build adds; both optional
+    assert all(not a.required for a in got.values())
+    os.environ["COLUMNS"] = "100"
+    assert tmain.build_parser(reference_only=True).format_help() == want["help_text"]
+
+
+def test_console_script_and_package_exports():
+    """`topsicle = topsicle_b200.main:main` (reference: setup.py:17-21) and the star-exports of the package
+    (reference: Topsicle/__init__.py:1)."""
+    import tomllib
+    from tests.conftest import REPO
+    meta = tomllib.load(open(os.path.join(REPO, "pyproject.toml"), "rb"))
+    assert meta["project"]["scripts"] == {"topsicle": "topsicle_b200.main:main"}
+    import topsicle_b200
+    from topsicle_b200 import main as tmain
+    assert callable(tmain.main)
+    ns = {}
+    exec("from topsicle_b200 import *", ns)
+    for name in ("check_file_type", "pattern_scramble_telo", "patterns_to_search", "unzip_file", "patternTRC_count",
+                 "seq_cut_windows", "bound_detect", "rawCountPattern", "fit_quadratic_and_find_vertex", "plot_patterns"):
+        assert callable(ns[name]), name
+    assert topsicle_b200.patternTRC_count is ns["patternTRC_count"]

@@ -38,27 +38,7 @@
 #include <omp.h>
 #endif
 
-#define TPS_FX_FASTQ 1
-#define TPS_FX_FASTA 2
-
-#define TPS_FX_OK 0
-#define TPS_FX_EIO (-1)
-#define TPS_FX_EFORMAT (-2)
-#define TPS_FX_ENOMEM (-3)
-#define TPS_FX_ECAPACITY (-4)
-#define TPS_FX_EINVAL (-5)
-
-typedef struct tps_fastx_rec { /* 48 bytes; offsets are relative to the batch's raw base */
-  uint64_t title_off;   /* first title byte (after '@' / '>') */
-  uint64_t seq_off;     /* first byte of the first sequence line */
-  uint64_t qual_off;    /* FASTQ: first byte of the quality line; FASTA: 0 */
-  uint32_t title_len;   /* right-stripped */
-  uint32_t id_off;      /* id = title[id_off : id_off + id_len] */
-  uint32_t id_len;
-  uint32_t seq_len;     /* bases after stripping */
-  uint32_t seq_raw_len; /* raw bytes spanned by the sequence lines (FASTA: incl. newlines) */
-  uint32_t flags;       /* bit 0: sequence needs the filtered copy (multi-line or inner blanks) */
-} tps_fastx_rec;
+#include "../../include/topsicle_host.h"
 
 typedef struct rec_vec {
   tps_fastx_rec *v;

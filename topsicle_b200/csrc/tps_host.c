@@ -22,21 +22,7 @@
 #include <omp.h>
 #endif
 
-typedef struct tps_synth_cfg {
-  uint64_t seed;
-  uint32_t len_kind;      /* 0 fixed(len_a); 1 lognormal(mu=len_a, sigma=len_b) clipped [len_min,len_max];
-                             2 len_a + Exp(mean len_b) capped len_max */
-  double len_a, len_b;
-  uint32_t len_min, len_max;
-  double f_telo;          /* fraction of telomeric reads */
-  uint32_t telo_min, telo_max;
-  double sub_rate, ins_rate, del_rate;
-  double n_rate;          /* per-base probability of 'N' */
-  double near_frac;       /* fraction of near-threshold reads */
-  double lower_frac;      /* fraction of reads with a 500-base lower-case stretch */
-  uint32_t motif_len;
-  char motif[32];
-} tps_synth_cfg;
+#include "../../include/topsicle_host.h"
 
 typedef struct { uint64_t s[4]; } rng_t;
 

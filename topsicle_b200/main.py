@@ -358,38 +358,55 @@ def analysis_run(args):
     return tprint("All telomere found, have a nice day.")
 
 
-def build_parser():
-    p = argparse.ArgumentParser(description="Topsicle - Telomere length estimation from long reads",
+# The reference's flag table (main.py:319-334) as data: (option strings, metavar, type, default, nargs, help).
+# A drop-in keeps names, types, defaults and help sentences to the letter -- `tests/test_cli_host.py::
+# test_parser_equals_reference` compares every field and the `--help` text with the reference's own parser
+# (tests/golden/cli_parser.json, captured from the unmodified Topsicle.main) -- so the sentences, typos included,
+# are the reference's.  type None = a store_true switch; required = the three the reference requires.
+_REQ = ("inputDir", "outputDir", "pattern")
+_REFERENCE_FLAGS = (
+    (("--inputDir", "-i"), "FILE/FOLDER", str, None, None, "Required, Path to the input file or directory"),
+    (("--outputDir", "-o"), "FOLDER", str, None, None, "Required, Path to the output directory"),
+    (("--pattern",), "CHAR", str, None, None,
+     "Required, Telomere repeat sequence (in 5' to 3' orientation). For e.g., in human use CCCTAA"),
+    (("--minSeqLength",), "INT", int, 9000, None, "Minimum length of a long read sequence that will be analyzed"),
+    (("--rawcountpattern",), None, None, False, None, "Output raw count of the k-mer for each window"),
+    (("--telophrase",), "INT", int, None, "+",
+     "Length of telomere k-mer to search. By default will use telomere k-mer length minus 2"),
+    (("--cutoff",), "FLOAT", float, 0.7, "+", "TRC statistics threshold"),
+    (("--windowSize",), "INT", int, 100, None, "Sliding window size"),
+    (("--slide",), "INT", int, None, None, "Window sliding step. Default is telomere k-mer length"),
+    (("--trimfirst",), "INT", int, 100, None, "Length of intial number of base pairs to trim"),
+    (("--maxlengthtelo",), "INT", int, 20000, None, "Longest possible length of telomere for any given read"),
+    (("--plot",), None, None, False, None,
+     "Optional, generate plot showing for each telomere read the abundance across the sequencing reead and the "
+     "changepoint"),
+    (("--rangecp",), "INT", int, None, None,
+     "Optional, set range of changepoint plot for visualization, default is maxlengthtelo"),
+    (("--read_check",), "STR", str, None, None, "Optional, get telomere of a specific read"),
+    (("--override", "-ov"), None, None, False, None, "Override telolengths_all.csv file but keep subset fastq"),
+    (("--threads", "-t"), "INT", int, None, None, "Number of CPU cores to use (by default, all available cores)"),
+)
+
+
+def build_parser(reference_only: bool = False):
+    """The `topsicle` argument parser: the reference's flags, then (unless `reference_only`) the two this build adds."""
+    p = argparse.ArgumentParser(prog="topsicle", description="Topsicle - Telomere length estimation from long reads",
                                 formatter_class=argparse.ArgumentDefaultsHelpFormatter)
-    p.add_argument("--inputDir", "-i", type=str, metavar="FILE/FOLDER",
-                   help="Required, Path to the input file or directory", required=True)
-    p.add_argument("--outputDir", "-o", type=str, metavar="FOLDER", help="Required, Path to the output directory",
-                   required=True)
-    p.add_argument("--pattern", metavar="CHAR", type=str,
-                   help="Required, Telomere repeat sequence (in 5' to 3' orientation). For e.g., in human use CCCTAA",
-                   required=True)
-    p.add_argument("--minSeqLength", metavar="INT", type=int,
-                   help="Minimum length of a long read sequence that will be analyzed", default=9000)
-    p.add_argument("--rawcountpattern", action="store_true", help="Output raw count of the k-mer for each window")
-    p.add_argument("--telophrase", nargs="+", metavar="INT", type=int,
-                   help="Length of telomere k-mer to search. By default will use telomere k-mer length minus 2")
-    p.add_argument("--cutoff", nargs="+", metavar="FLOAT", type=float, help="TRC statistics threshold", default=0.7)
-    p.add_argument("--windowSize", metavar="INT", type=int, help="Sliding window size", default=100)
-    p.add_argument("--slide", metavar="INT", type=int, help="Window sliding step. Default is telomere k-mer length")
-    p.add_argument("--trimfirst", metavar="INT", type=int, help="Length of intial number of base pairs to trim",
-                   default=100)
-    p.add_argument("--maxlengthtelo", metavar="INT", type=int,
-                   help="Longest possible length of telomere for any given read", default=20000)
-    p.add_argument("--plot", action="store_true",
-                   help="Optional, generate plot showing for each telomere read the abundance across the sequencing "
-                        "reead and the changepoint")
-    p.add_argument("--rangecp", metavar="INT", type=int,
-                   help="Optional, set range of changepoint plot for visualization, default is maxlengthtelo")
-    p.add_argument("--read_check", metavar="STR", type=str, help="Optional, get telomere of a specific read")
-    p.add_argument("--override", "-ov", action="store_true",
-                   help="Override telolengths_all.csv file but keep subset fastq")
-    p.add_argument("--threads", "-t", metavar="INT", type=int,
-                   help="Number of CPU cores to use (by default, all available cores)", default=None)
+    for names, metavar, typ, default, nargs, text in _REFERENCE_FLAGS:
+        if typ is None:
+            p.add_argument(*names, action="store_true", help=text)
+            continue
+        kw = dict(type=typ, metavar=metavar, help=text)
+        if nargs:
+            kw["nargs"] = nargs
+        if names[0].lstrip("-") in _REQ:
+            kw["required"] = True
+        else:
+            kw["default"] = default
+        p.add_argument(*names, **kw)
+    if reference_only:
+        return p
     p.add_argument("--ends-first", dest="ends_first", action="store_true",
                    help="B200 only, optional: upload just the first/last 1000 bases of every read, then the "
                         "telomere regions of the reads that pass TRC (same outputs; about a tenth of the bytes "

@@ -179,9 +179,10 @@ class _DeviceWorker:
     packs each batch; the others scan the same device-resident batch (tps_submit_shared)."""
 
     def __init__(self, device, cfgs, max_batch_reads, max_batch_bases, depth, max_pass_reads, rawcount_capacity,
-                 context_factory, ends_first=False, ends_raw_bytes=1 << 28):
+                 context_factory, ends_first=False, ends_raw_bytes=1 << 28, leaders=(0,)):
         self.device = device
         self.cfgs = cfgs
+        self.leaders = set(leaders)     # configs whose context can upload and pack a batch (full-size buffers)
         self.max_batch_reads = max_batch_reads
         self.max_batch_bases = max_batch_bases
         self.max_pass_reads = max_pass_reads
@@ -209,7 +210,7 @@ class _DeviceWorker:
             for k, c in enumerate(cfgs):
                 # followers never upload whole batches: they need no base / code buffers beyond the region batches
                 self.ctxs.append(context_factory(c, device, max_batch_reads,
-                                                 max_batch_bases if k == 0 else max(1, self.region_cap), depth,
+                                                 max_batch_bases if k in self.leaders else max(1, self.region_cap), depth,
                                                  max_pass_reads, rawcount_capacity if c.want_rawcount else 0))
         except BaseException:
             self._slot_thread.join()
@@ -264,13 +265,17 @@ class _DeviceWorker:
             self.reg_tails.free()
             self.reg = None
 
-    def submit(self, bases, starts, lens, n_reads, true_lens=None):
+    def submit(self, bases, starts, lens, n_reads, true_lens=None, group=None):
+        """Upload and scan one batch under the configs `group` (default: all): the first uploads and packs,
+        the others scan the same device-resident batch."""
+        group = group if group is not None else range(len(self.ctxs))
+        lead = self.ctxs[group[0]]
         if true_lens is not None:
-            bid = self.ctxs[0].submit_ends(bases, starts, lens, true_lens, n_reads)
+            bid = lead.submit_ends(bases, starts, lens, true_lens, n_reads)
         else:
-            bid = self.ctxs[0].submit_spans(bases, starts, lens, n_reads)
-        for c in self.ctxs[1:]:
-            c.submit_shared(self.ctxs[0], bid)
+            bid = lead.submit_spans(bases, starts, lens, n_reads)
+        for k in group[1:]:
+            self.ctxs[k].submit_shared(lead, bid)
         return bid
 
     # -- ends-first mode: steps 2/3 of the TRC-pass reads of an ends batch
@@ -317,14 +322,15 @@ class _DeviceWorker:
                 for j, i in enumerate(used):
                     tables[i] = ctx.rawcount_table(rows2, raw2, j)
 
-    def finish_ends(self, item, records_cfg, keep):
+    def finish_ends(self, item, records_cfg, keep, group):
         slot, batch, bid, seq = item
         res = BatchResult(seq=seq, first_read=batch.first_read, n_reads=batch.n_reads, n_bases=batch.n_bases,
                           n_scanned=0, n_uploaded=int(batch.span))
         self._region_bases = 0
-        waited = [ctx.wait(bid)[0] for ctx in self.ctxs]      # step-1 rows under every config
-        for ci, (cfg, ctx) in enumerate(zip(self.cfgs, self.ctxs)):
-            rows = waited[ci]
+        waited = [self.ctxs[k].wait(bid)[0] for k in group]      # step-1 rows under every config of the job
+        for gi, ci in enumerate(group):
+            cfg, ctx = self.cfgs[ci], self.ctxs[ci]
+            rows = waited[gi]
             tables = {}
             idx = np.nonzero(rows["status"] == engine.ST_PASS)[0]
             if len(idx) and keep is not None:
@@ -333,27 +339,28 @@ class _DeviceWorker:
                 self._scan_regions(ci, batch, rows, idx, tables)
             res.passes.append(harvest(cfg, ctx, batch, rows, None, records_cfg == ci, keep,
                                       tables=tables if cfg.want_rawcount else None))
-            if ci == 0:
+            if gi == 0:
                 res.n_scanned = int((rows["status"] != engine.ST_FILTERED).sum())
         res.n_uploaded += self._region_bases
         batch.release()
         return res
 
-    def _scan_sub(self, ci, bases, starts, lens, lo, hi):
-        """Synchronous scan of reads [lo, hi) of a batch under config ci, splitting again on capacity
-        overflow (more TRC-pass reads or raw counts than the context's per-batch capacity)."""
+    def _scan_sub(self, ci, bases, starts, lens, lo, hi, lead=0):
+        """Synchronous scan of reads [lo, hi) of a batch under config ci (uploaded by the context of config
+        `lead`), splitting again on capacity overflow (more TRC-pass reads or raw counts than the context's
+        per-batch capacity)."""
         base0 = int(starts[lo])
         sub_starts = (starts[lo:hi] - starts[lo]).astype(np.uint64)
         sub_lens = np.ascontiguousarray(lens[lo:hi])
         sub_bases = np.ascontiguousarray(bases[base0:int(starts[hi - 1]) + int(lens[hi - 1])])
         try:
-            bid = self.ctxs[0].submit_spans(sub_bases, sub_starts, sub_lens, hi - lo)
-            if ci == 0:
-                rows, raw = self.ctxs[0].wait(bid)
+            bid = self.ctxs[lead].submit_spans(sub_bases, sub_starts, sub_lens, hi - lo)
+            if ci == lead:
+                rows, raw = self.ctxs[lead].wait(bid)
             else:
-                self.ctxs[ci].submit_shared(self.ctxs[0], bid)
+                self.ctxs[ci].submit_shared(self.ctxs[lead], bid)
                 try:
-                    self.ctxs[0].wait(bid)
+                    self.ctxs[lead].wait(bid)
                 except engine.TpsError as e:       # the leader's own overflow is irrelevant here
                     if e.code != -4:
                         raise
@@ -363,31 +370,34 @@ class _DeviceWorker:
             if e.code != -4 or hi - lo <= 1:
                 raise
             mid = (lo + hi) // 2
-            return (self._scan_sub(ci, bases, starts, lens, lo, mid)
-                    + self._scan_sub(ci, bases, starts, lens, mid, hi))
+            return (self._scan_sub(ci, bases, starts, lens, lo, mid, lead)
+                    + self._scan_sub(ci, bases, starts, lens, mid, hi, lead))
 
-    def finish(self, item, records_cfg, keep):
+    def finish(self, item, records_cfg, keep, group=None):
+        """Results of one submitted batch: BatchResult.passes[j] = TRC-pass reads under config group[j]."""
+        group = list(group) if group is not None else list(range(len(self.ctxs)))
         if isinstance(item[1], fastx.EndsBatch):
-            return self.finish_ends(item, records_cfg, keep)
+            return self.finish_ends(item, records_cfg, keep, group)
         slot, batch, bid, seq = item
         res = BatchResult(seq=seq, first_read=batch.first_read, n_reads=batch.n_reads, n_bases=batch.n_bases,
                           n_scanned=0, n_uploaded=int(batch.span))
         n = batch.n_reads
         waited = []
-        for ctx in self.ctxs:                      # release every context's slot before any re-scan
+        for k in group:                            # release every context's slot before any re-scan
             try:
-                waited.append(ctx.wait(bid, True))  # tables are copied out per read by harvest()
+                waited.append(self.ctxs[k].wait(bid, True))  # tables are copied out per read by harvest()
             except engine.TpsError as e:
                 if e.code != -4 or n <= 1:
                     raise
                 waited.append(None)
-        for ci, (cfg, ctx) in enumerate(zip(self.cfgs, self.ctxs)):
-            if waited[ci] is not None:
-                parts = [(0, n, *waited[ci])]
+        for gi, ci in enumerate(group):
+            cfg, ctx = self.cfgs[ci], self.ctxs[ci]
+            if waited[gi] is not None:
+                parts = [(0, n, *waited[gi])]
             else:
                 mid = n // 2
-                parts = (self._scan_sub(ci, slot.bases.array, batch.offsets, batch.lens, 0, mid)
-                         + self._scan_sub(ci, slot.bases.array, batch.offsets, batch.lens, mid, n))
+                parts = (self._scan_sub(ci, slot.bases.array, batch.offsets, batch.lens, 0, mid, group[0])
+                         + self._scan_sub(ci, slot.bases.array, batch.offsets, batch.lens, mid, n, group[0]))
             passes = []
             scanned = 0
             for lo, hi, rows, raw in parts:
@@ -395,7 +405,7 @@ class _DeviceWorker:
                 view = _BatchView(batch, lo)
                 passes += harvest(cfg, ctx, view, rows, raw, records_cfg == ci, keep)
             res.passes.append(passes)
-            if ci == 0:
+            if gi == 0:
                 res.n_scanned = scanned
         batch.release()
         return res
@@ -429,7 +439,10 @@ class Scanner:
     def __init__(self, cfgs: Sequence[ScanConfig], *, devices: Sequence[int] = (0,), threads: int = 0,
                  max_batch_bases: int = 1 << 28, max_batch_reads: int = 1 << 17, depth: int = 3,
                  max_pass_reads: int = 0, rawcount_capacity: int = 0, context_factory=None,
-                 ends_first: bool = False, ends_raw_bytes: int = 1 << 28):
+                 ends_first: bool = False, ends_raw_bytes: int = 1 << 28, leaders: Sequence[int] = (0,)):
+        """`leaders`: the configs that may come first in a FileJob's `cfg_ids` (their contexts get full-size
+        upload buffers).  The CLI scans every file under all telophrases of one pattern, so config 0 leads; a mixed
+        batch of files with different `--pattern`s (one config per pattern) makes every config a leader."""
         context_factory = context_factory or make_context
         self.ends_first = bool(ends_first)
         self.ends_raw_bytes = int(ends_raw_bytes)        # file text per ends batch
@@ -450,7 +463,7 @@ class Scanner:
             try:
                 made[i] = _DeviceWorker(d, self.cfgs, max_batch_reads, max_batch_bases, depth, max_pass_reads,
                                         rawcount_capacity, context_factory, ends_first=self.ends_first,
-                                        ends_raw_bytes=self.ends_raw_bytes)
+                                        ends_raw_bytes=self.ends_raw_bytes, leaders=leaders)
             except BaseException as e:  # noqa: BLE001 - re-raised below
                 failed.append(e)
 
@@ -503,6 +516,10 @@ class Scanner:
         Threads: the C parser is itself multi-threaded on plain files; `.gz` files are inflated by one
         thread each, which is why several readers matter for directories of compressed files."""
         jobs = list(jobs)
+        for j in jobs:
+            if j.cfg_ids is not None and (not j.cfg_ids or j.cfg_ids[0] not in self.workers[0].leaders):
+                raise ValueError(f"{j.path}: cfg_ids {j.cfg_ids} must start with one of the Scanner's leaders "
+                                 f"{sorted(self.workers[0].leaders)}")
         n_workers = len(self.workers)
         n_threads = self.threads or len(os.sched_getaffinity(0))
         if readers <= 0:
@@ -621,7 +638,7 @@ class Scanner:
             def finish_oldest():
                 job, item = inflight.pop(0)
                 t = time.perf_counter()
-                res = w.finish(item, job.records_cfg, job.keep_ids)
+                res = w.finish(item, job.records_cfg, job.keep_ids, job.cfg_ids)
                 job.stats.timing["finish"] += time.perf_counter() - t
                 free.put(item[0])
                 delivered(job, res)
@@ -638,7 +655,8 @@ class Scanner:
                     t = time.perf_counter()
                     bid = w.submit(slot.bases.array[:batch.span], batch.offsets[:batch.n_reads],
                                    batch.lens[:batch.n_reads], batch.n_reads,
-                                   batch.true_lens[:batch.n_reads] if isinstance(batch, fastx.EndsBatch) else None)
+                                   batch.true_lens[:batch.n_reads] if isinstance(batch, fastx.EndsBatch) else None,
+                                   job.cfg_ids)
                     job.stats.timing["submit"] += time.perf_counter() - t
                     inflight.append((job, (slot, batch, bid, seq)))
                 while inflight and not errors:
@@ -679,8 +697,10 @@ class FileJob:
 
     def __init__(self, path: str, sink: Callable[[BatchResult], None], *, records_cfg: int | None = None,
                  keep_ids=None, on_done: Callable[[FileStats], None] | None = None,
-                 on_error: Callable[[Exception], None] | None = None):
+                 on_error: Callable[[Exception], None] | None = None, cfg_ids: Sequence[int] | None = None):
         self.path = path
+        # the Scanner's configs this file is scanned under (default: all); BatchResult.passes follows this order
+        self.cfg_ids = list(cfg_ids) if cfg_ids is not None else None
         self.sink = sink
         self.records_cfg = records_cfg
         self.keep_ids = keep_ids

@@ -334,7 +334,7 @@ int tps_create(tps_ctx **out, int device, const tps_params *params) {
       ctx->k3n_gs_cap = (uint32_t)(((nw_max + 4) / 5 + 7) & ~7ull); /* group sums of the longest read, in shared memory */
       if (ctx->k3n_gs_cap == 0) ctx->k3n_gs_cap = 8;
       /* raw[2] | pm | lin | ori | alignment | Z | Zhi | UP | CP | SP | brows | gsum */
-      ctx->k3n_smem = (2 * TPS_K3N_RAW_WORDS + pm_words + 3 + 3 * ctx->k3n_lin_words + 3 * (NT + 1) + 3 + 4 * (NT + 1) +
+      ctx->k3n_smem = (2 * TPS_K3N_RAW_WORDS + pm_words + 3 * ctx->k3n_lin_words + 3 * (NT + 1) + 3 + 4 * (NT + 1) +
                        (ctx->k3n_nz > 4 ? 4 * (NT + 1) : 0) + 2 * (NT + 2) + (pt.n_bordered ? 2 * (NT + 2) : 0) +
                        2 * ((pt.n + 3u) & ~3u) * ctx->k3n_stride + pt.n_bordered * (NT + 1) + ctx->k3n_gs_cap / 2) * 4;
       const char *ng = getenv("TPS_K3_NO_GROUPS"); /* 1 = no five-window fast path (A/B) */

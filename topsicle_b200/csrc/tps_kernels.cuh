@@ -1325,11 +1325,8 @@ __device__ __forceinline__ uint32_t tps_bp_window(uint32_t ls, uint32_t D, uint3
   return c;
 }
 
-#ifndef TPS_K3N_MINB
-#define TPS_K3N_MINB 9 /* resident CTAs per SM the register allocation is held to */
-#endif
 template <int K>
-__global__ void __launch_bounds__(TPS_K3N_THREADS, TPS_K3N_MINB)
+__global__ void __launch_bounds__(TPS_K3N_THREADS)
 tps_window_bp_kernel(const TpsScanArgs a, const TpsPatTable pt) {
   static_assert(K > 0, "the bit-parallel window kernel needs a common literal length");
   constexpr uint32_t NT = TPS_K3N_THREADS;
@@ -1341,6 +1338,7 @@ tps_window_bp_kernel(const TpsScanArgs a, const TpsPatTable pt) {
   __shared__ TpsReadItem s_item[2];
   __shared__ uint32_t s_idx[3];
   __shared__ uint32_t s_wt[2][NT / 32];
+  __shared__ TpsCpShared s_cp;
   const uint32_t tid = threadIdx.x, q = threadIdx.x;
   const uint32_t P = pt.n, P4 = (P + 3u) & ~3u, lw = a.lin_words, stride = a.tile_words, nb = pt.n_bordered;
   const uint32_t W = a.W, s = a.slide;
@@ -1353,12 +1351,6 @@ tps_window_bp_kernel(const TpsScanArgs a, const TpsPatTable pt) {
   uint32_t *raw = smem; /* two buffers of TPS_K3N_RAW_WORDS */
   uint2 *pm = reinterpret_cast<uint2 *>(smem + 2u * TPS_K3N_RAW_WORDS);
   uint32_t *lin = smem + 2u * TPS_K3N_RAW_WORDS + 2u * P * K;
-  lin += (4u - ((uint32_t)(lin - smem) & 3u)) & 3u;
-  /* the change point's scratch lies over lin | ori | Z | UP, which are free between a read's last tile and the
-   * next read's first (static_assert below: it fits before SP for any geometry) */
-  TpsCpShared &s_cp = *reinterpret_cast<TpsCpShared *>(lin);
-  static_assert(sizeof(TpsCpShared) <= (3u * 130u + 3u * (NT + 1u) + 4u * (NT + 1u) + 2u * (NT + 2u)) * 4u,
-                "change-point scratch must fit over lin | ori | Z | UP");
   uint32_t *ori = lin + 3u * lw;
   uint32_t *al = ori + 3u * (NT + 1u);
   al += (4u - ((uint32_t)(al - smem) & 3u)) & 3u;
@@ -1371,17 +1363,13 @@ tps_window_bp_kernel(const TpsScanArgs a, const TpsPatTable pt) {
   uint16_t *gsum = reinterpret_cast<uint16_t *>(brows + nb * (NT + 1u)); /* group sums of the read in hand */
   tps_build_pattern_masks(pm, pt, K, tid, NT);
   const uint32_t n_items = a.counters[6];
-  /* words that must read zero: the pad word behind the oriented planes and the per-word tables (the change
-   * point's scratch lies over them: redone after each), and for the whole kernel the slots of SP behind the tile
-   * and of the rows that pad P to a multiple of 4 and the pad word of the plain rows */
-  auto clear_pads = [&]() {
-    if (tid < 3u) ori[tid * (NT + 1u) + NT] = 0u;
-    if (tid == 3u) Z[NT] = make_uint4(0u, 0u, 0u, 0u);
-    if (tid == 4u && nz > 4u) Zhi[NT] = make_uint4(0u, 0u, 0u, 0u);
-    if (tid == 5u) UP[NT] = make_uint2(0u, 0u);
-    if (tid == 6u && nb) CP[NT] = make_uint2(0u, 0u);
-  };
-  clear_pads();
+  /* words that stay zero for the whole kernel: the pad word behind the oriented planes and the per-word tables,
+   * the slots of SP behind the tile and of the rows that pad P to a multiple of 4, the pad word of the plain rows */
+  if (tid < 3u) ori[tid * (NT + 1u) + NT] = 0u;
+  if (tid == 3u) Z[NT] = make_uint4(0u, 0u, 0u, 0u);
+  if (tid == 4u && nz > 4u) Zhi[NT] = make_uint4(0u, 0u, 0u, 0u);
+  if (tid == 5u) UP[NT] = make_uint2(0u, 0u);
+  if (tid == 6u && nb) CP[NT] = make_uint2(0u, 0u);
   for (uint32_t i = tid; i < P4 * stride; i += NT) SP[i] = make_uint2(0u, 0u);
   for (uint32_t i = tid; i < nb * (NT + 1u); i += NT) brows[i] = 0u;
 
@@ -1577,7 +1565,6 @@ tps_window_bp_kernel(const TpsScanArgs a, const TpsPatTable pt) {
       }
     }
     __syncthreads();
-    clear_pads(); /* two barriers of the next tile lie between this and the first read of a pad */
   }
 }
 

@@ -49,7 +49,7 @@ def emit(line):
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=16)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", type=int, default=2, help="BASELINE.json config number (2..5)")
@@ -65,9 +65,9 @@ def parse_args():
     return ap.parse_args()
 
 
-def scan_kwargs(spec):
+def scan_kwargs(spec, motif=None):
     cli = spec["cli"]
-    pattern = cli["pattern"]
+    pattern = motif or cli["pattern"]
     phrases = cli.get("telophrase") or [len(pattern) - 2]
     cut = cli.get("cutoff", 0.7)
     return dict(pattern=pattern, phrase=phrases[0], cutoff=min(cut) if isinstance(cut, list) else cut,
@@ -145,17 +145,26 @@ def hbm_peak():
 
 
 def ncu_traffic_per_base():
-    """dram bytes per base of the pack kernel (K1) from the committed ncu --set full capture."""
+    """(dram bytes per base of the pack kernel K1, where that figure comes from): the committed
+    ncu --set full capture of the same command, not a live measurement."""
     try:
         with open(os.path.join(REPO, "profiles", "k1_traffic.json")) as fh:
-            return float(json.load(fh)["dram_bytes_per_base"])
+            d = json.load(fh)
+            return float(d["dram_bytes_per_base"]), ("profiles/k1_traffic.json (ncu --set full, dram__bytes_read.sum + "
+                                                     f"dram__bytes_write.sum per base; captured {d.get('captured', 'round 1')})")
     except Exception:
-        return None
+        return None, None
 
 
-def run_cpu_baseline(config, reads, steps=1, warmup=0, first_read=0):
+def run_cpu_baseline(config, reads, steps=1, warmup=0, first_read=0, motif=None, phrase=0, raw=False):
     cmd = [sys.executable, os.path.join(REPO, "oracle", "cpu_baseline.py"), "--config", str(config),
            "--reads", str(reads), "--steps", str(steps), "--warmup", str(warmup), "--first-read", str(first_read)]
+    if motif:
+        cmd += ["--motif", motif]
+    if phrase:
+        cmd += ["--phrase", str(phrase)]
+    if raw:
+        cmd.append("--raw")
     out = subprocess.run(cmd, check=True, capture_output=True, text=True).stdout.strip().splitlines()[-1]
     return json.loads(out)
 
@@ -169,7 +178,12 @@ def reference_arm(a):
     from topsicle_b200 import synth
     spec = synth.CONFIGS[a.config]
     cores = len(os.sched_getaffinity(0))
-    reads = a.cpu_sample_reads or min(4000 * cores, 100000)
+    # the repo arm's batch (same `config`) unless K + W passes over it would not end within a few minutes on
+    # these cores (the port does ~900 reads/s/core on config 2); then a bounded sample, and the line says so
+    reads = a.cpu_sample_reads or a.reads_per_step or default_reads_per_step(spec)
+    budget = int(240.0 / max(1, a.steps + a.warmup) * 900 * cores)
+    if not a.cpu_sample_reads and reads > budget:
+        reads = max(1024, budget // 1024 * 1024)
     r = run_cpu_baseline(a.config, reads, steps=a.steps, warmup=a.warmup)
     t = sum(r["seconds"])
     value = r["bases"] * a.steps / t / 1e9
@@ -206,24 +220,45 @@ def main():
     dev = torch.device("cuda", local_rank)
 
     spec = synth.CONFIGS[a.config]
-    kw = scan_kwargs(spec)
+    # pattern sets of the workload: one, or (config 5) one per species sub-batch -- the reference takes one
+    # --pattern per invocation (main.py:321), so every sub-batch is scanned under its own pattern set
+    motifs = list(spec.get("sub_batches") or [spec["cli"]["pattern"]])
+    nm = len(motifs)
+    kws = [scan_kwargs(spec, m) for m in motifs]
+    kw = kws[0]
+    phrases_all = spec["cli"].get("telophrase") or [kw["phrase"]]
+    want_raw_cfg = bool(spec["cli"].get("rawcountpattern"))
     reads_per_step = a.reads_per_step or default_reads_per_step(spec)
-    nb = max(1, a.distinct_batches)
+    nb = (max(1, a.distinct_batches, nm) + nm - 1) // nm * nm     # batch b holds reads of sub-batch b % nm
 
-    # CPU baseline first (separate process, no CUDA in it), rank 0 at N=1 only
+    def ctx_kwargs(k):
+        return dict(len_telopattern=len(k["pattern"]), cutoff=k["cutoff"], min_seq_length=k["min_len"], window_size=k["W"],
+                    slide=k["slide"], trimfirst=k["trim"], maxlengthtelo=k["maxlen"], device=local_rank)
+
+    # CPU baseline first (separate process, no CUDA in it), rank 0 at N=1 only: the timed sample is the first
+    # pattern set / telophrase; the other pattern sets and telophrases get a smaller untimed sample, for parity
     cpu = None
-    cpu_rows, cpu_sample_reads = None, 0
+    cpu_runs = {}      # (motif index, phrase) -> (sample reads, port output)
     if world == 1 and not a.no_cpu_baseline:
         cores = len(os.sched_getaffinity(0))
-        sample_reads = a.cpu_sample_reads or min(10000 * cores, 200000)
-        r = run_cpu_baseline(a.config, sample_reads)
-        cpu_rows, cpu_sample_reads = r.get("pass_rows"), sample_reads
+        reg = max(0, kw["maxlen"] - kw["trim"])
+        nw = (reg - kw["W"]) // kw["slide"] + 1 if reg >= kw["W"] else 0
+        per_read = 1.0 / 900 + spec["f_telo"] * 0.2 * nw / 3301          # seconds per read and core of the port
+        sample_reads = a.cpu_sample_reads or int(min(reads_per_step, 200000, max(2048, 25.0 * cores / per_read)))
+        r = run_cpu_baseline(a.config, sample_reads, motif=motifs[0] if nm > 1 else None, raw=want_raw_cfg)
+        cpu_runs[(0, kw["phrase"])] = (sample_reads, r)
         cpu = {"value": r["gbases_per_s"][0], "unit": UNIT, "cores": r["cores"], "kind": "port",
                "reads_per_s": r["reads_per_s"][0],
                "sample": f"first {sample_reads} reads ({r['bases'] / 1e9:.3f} Gbases, {r['n_pass']} TRC-pass) of the "
                          f"workload, {r['seconds'][0]:.1f} s; in-memory reads (parsing not charged)"}
+        extra = max(2048, sample_reads // 4)
+        for mi in range(nm):
+            for ph in (phrases_all if nm == 1 else [kws[mi]["phrase"]]):
+                if (mi, ph) not in cpu_runs:
+                    cpu_runs[(mi, ph)] = (extra, run_cpu_baseline(a.config, extra, motif=motifs[mi] if nm > 1 else None,
+                                                                  phrase=ph, raw=want_raw_cfg))
 
-    # ---- synthetic batches: rank r owns reads [r*nb*R + b*R, ...) -> pinned host + device copies
+    # ---- synthetic batches: rank r owns reads [r*nb/nm*R + ...) of every sub-batch -> pinned host + device copies
     # host placement: this rank's pinned buffers and parser threads on the CPUs local to its GPU
     from topsicle_b200 import numa
     cores_before = len(os.sched_getaffinity(0))
@@ -231,13 +266,15 @@ def main():
     if near and world > 1:
         os.sched_setaffinity(0, near)
     t_gen = time.perf_counter()
-    host_bases, host_off, dev_bases, dev_off, nbases = [], [], [], [], []
+    host_bases, host_off, dev_bases, dev_off, nbases, first_reads = [], [], [], [], [], []
     for b in range(nb):
-        first = (rank * nb + b) * reads_per_step
-        off = synth.read_lengths(spec, first, reads_per_step)
+        mi = b % nm
+        first = (rank * (nb // nm) + b // nm) * reads_per_step
+        mot = motifs[mi] if nm > 1 else None
+        off = synth.read_lengths(spec, first, reads_per_step, mot)
         n = int(off[-1])
         hb = engine.PinnedBuffer(n)
-        synth.fill_reads(spec, first, off, hb.array)
+        synth.fill_reads(spec, first, off, hb.array, motif=mot)
         ho = engine.PinnedBuffer(off.nbytes)
         ho.array.view(np.uint64)[:] = off
         pad = (n + 2047) // 2048 * 2048
@@ -245,16 +282,14 @@ def main():
         db[:n].copy_(torch.from_numpy(hb.array[:n]))
         do = torch.from_numpy(off.view(np.int64)).to(dev)
         host_bases.append(hb); host_off.append(ho); dev_bases.append(db); dev_off.append(do); nbases.append(n)
+        first_reads.append(first)
     t_gen = time.perf_counter() - t_gen
     max_bases = max(nbases)
     n_streams = max(1, min(a.streams, 3))
-    d_rows_s = [torch.empty(reads_per_step * 40, dtype=torch.uint8, device=dev) for _ in range(n_streams)]
-    d_rows = d_rows_s[0]
+    d_rows_s = [torch.empty(reads_per_step * 40, dtype=torch.uint8, device=dev) for _ in range(n_streams * nm)]
 
-    pats = patterns_to_search(kw["pattern"], kw["phrase"])
-    ctx = engine.ScanContext(pats, len_telopattern=len(kw["pattern"]), cutoff=kw["cutoff"], min_seq_length=kw["min_len"],
-                             window_size=kw["W"], slide=kw["slide"], trimfirst=kw["trim"], maxlengthtelo=kw["maxlen"],
-                             device=local_rank, n_slots=3, max_batch_reads=reads_per_step, max_batch_bases=max_bases)
+    ctxs = [engine.ScanContext(patterns_to_search(k["pattern"], k["phrase"]), n_slots=3, max_batch_reads=reads_per_step,
+                               max_batch_bases=max_bases, **ctx_kwargs(k)) for k in kws]
 
     def barrier():
         torch.cuda.synchronize()
@@ -279,37 +314,38 @@ def main():
     # ---- kernel-only: batch resident in HBM; every step's input (1.5 GB) is larger than the 126 MB L2
     def step_device(i):
         b = i % nb
-        sl = i % n_streams
-        ctx.scan_device(dev_bases[b].data_ptr(), dev_off[b].data_ptr(), reads_per_step, nbases[b],
-                        d_rows_s[sl].data_ptr(), slot=sl)
+        mi = b % nm
+        sl = (i // nm) % n_streams
+        ctxs[mi].scan_device(dev_bases[b].data_ptr(), dev_off[b].data_ptr(), reads_per_step, nbases[b],
+                             d_rows_s[mi * n_streams + sl].data_ptr(), slot=sl)
+        return mi * n_streams + sl
 
     for i in range(a.warmup):
         step_device(i)
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
-    launches0 = ctx.kernel_launches()
+    launches0 = sum(c.kernel_launches() for c in ctxs)
     t0 = time.perf_counter()
+    last_buf = 0
     for i in range(a.steps):
-        step_device(i)
+        last_buf = step_device(i)
     barrier()
     t1 = time.perf_counter()
-    launches = ctx.kernel_launches() - launches0
-    rows_dev = np.frombuffer(d_rows_s[(a.steps - 1) % n_streams].cpu().numpy().tobytes(),
-                             dtype=engine.ROW_DTYPE).copy()
+    launches = sum(c.kernel_launches() for c in ctxs) - launches0
+    rows_dev = np.frombuffer(d_rows_s[last_buf].cpu().numpy().tobytes(), dtype=engine.ROW_DTYPE).copy()
     # device-side (CUDA event) times per kernel, from the library's event ring.  With several streams
     # the kernels of consecutive batches overlap and per-kernel event times are not attributable, so the
     # per-kernel figures (and the K1 roofline) come from an extra single-stream pass over the same batches.
-    n_attr = min(a.steps, 256)
-    if n_streams > 1:
-        n_attr = min(a.steps, 16)
-        barrier()
-        for i in range(n_attr):
-            b = i % nb
-            ctx.scan_device(dev_bases[b].data_ptr(), dev_off[b].data_ptr(), reads_per_step, nbases[b],
-                            d_rows_s[0].data_ptr(), slot=0)
-        barrier()
-    ring = [ctx.timings(back) for back in range(n_attr)]
+    n_attr = max(nm, min(a.steps, 16) // nm * nm)
+    barrier()
+    for i in range(n_attr):
+        b = i % nb
+        ctxs[b % nm].scan_device(dev_bases[b].data_ptr(), dev_off[b].data_ptr(), reads_per_step, nbases[b],
+                                 d_rows_s[(b % nm) * n_streams].data_ptr(), slot=0)
+        ctxs[b % nm].sync()
+    barrier()
+    ring = [c.timings(back) for c in ctxs for back in range(n_attr // nm)]
     k1_ms = statistics.mean(t["k1_pack"] for t in ring)
     k2_ms = statistics.mean(t["k2_trc"] for t in ring)
     k3_ms = statistics.mean(t["k3_windows_cp"] for t in ring)
@@ -321,29 +357,42 @@ def main():
     value = total_bases / wall / 1e9
 
     # ---- parity at bench size: the CPU port's rows (float64 ruptures, as the reference computes them) for the
-    # sampled reads that lie in batch 0 against the GPU rows of the same reads
-    parity = None
-    if cpu_rows is not None and rank == 0:
-        ctx.scan_device(dev_bases[0].data_ptr(), dev_off[0].data_ptr(), reads_per_step, nbases[0],
-                        d_rows_s[0].data_ptr(), slot=0)
-        ctx.sync()
-        rows0 = np.frombuffer(d_rows_s[0].cpu().numpy().tobytes(), dtype=engine.ROW_DTYPE)
-        n_cmp = min(reads_per_step, cpu_sample_reads)
-        want = {gi: (tail, trc, telo) for gi, tail, trc, telo in cpu_rows if gi < n_cmp}
-        got = {int(i): (engine.TAIL_NAMES[int(rows0["tail"][i])],
-                        engine.trc_value(int(rows0["match_count"][i]), len(kw["pattern"])),
-                        int(rows0["telo_length"][i]))
-               for i in np.nonzero(rows0["status"][:n_cmp] >= engine.ST_PASS)[0]}
-        same_set = set(want) == set(got)
-        both = sorted(set(want) & set(got))
-        diffs = [abs(want[i][2] - got[i][2]) for i in both]
-        parity = {"reads_compared": int(n_cmp), "trc_pass_cpu": len(want), "trc_pass_gpu": len(got),
-                  "pass_sets_identical": same_set,
-                  "tail_and_trc_identical": all(want[i][:2] == got[i][:2] for i in both),
-                  "telo_length_exact": sum(1 for d in diffs if d == 0), "telo_length_max_abs_diff": max(diffs, default=0),
-                  "note": "CPU side = float64 numpy.var argmax (ruptures restatement); GPU side = exact rational argmax"}
+    # sampled reads against the GPU rows of the same reads: every pattern set, every telophrase, and (config 3) the
+    # md5 of every TRC-pass read's raw-count table
+    parity_all = []
+    if cpu_runs and rank == 0:
+        import hashlib
+        for (mi, ph), (n_cmp, r) in sorted(cpu_runs.items()):
+            k = dict(kws[mi], phrase=ph)
+            n_cmp = min(n_cmp, reads_per_step)
+            off = host_off[mi].array.view(np.uint64)[:n_cmp + 1]
+            hb = host_bases[mi].array[:int(off[-1])]
+            with engine.ScanContext(patterns_to_search(k["pattern"], ph), n_slots=1, max_batch_reads=n_cmp,
+                                    max_batch_bases=int(off[-1]) + 4096, want_rawcount=want_raw_cfg,
+                                    max_pass_reads=min(n_cmp, 16384), **ctx_kwargs(k)) as pc:
+                rows0, raw0 = pc.scan(hb, np.ascontiguousarray(off))
+                want = {gi: (tail, trc, telo, dig) for gi, tail, trc, telo, dig in r["pass_rows"] if gi < n_cmp}
+                got = {}
+                for i in np.nonzero(rows0["status"] >= engine.ST_PASS)[0]:
+                    dig = None
+                    if want_raw_cfg:
+                        tab = pc.rawcount_table(rows0, raw0, int(i))
+                        dig = hashlib.md5(tab.tobytes()).hexdigest() if tab is not None else None
+                    got[int(i)] = (engine.TAIL_NAMES[int(rows0["tail"][i])],
+                                   engine.trc_value(int(rows0["match_count"][i]), len(k["pattern"])),
+                                   int(rows0["telo_length"][i]), dig)
+            both = sorted(set(want) & set(got))
+            diffs = [abs(want[i][2] - got[i][2]) for i in both]
+            parity_all.append({
+                "pattern": k["pattern"], "telophrase": ph, "reads_compared": int(n_cmp), "trc_pass_cpu": len(want),
+                "trc_pass_gpu": len(got), "pass_sets_identical": set(want) == set(got),
+                "tail_and_trc_identical": all(want[i][:2] == got[i][:2] for i in both),
+                "telo_length_exact": sum(1 for d in diffs if d == 0), "telo_length_max_abs_diff": max(diffs, default=0),
+                "rawcount_tables_identical": (sum(1 for i in both if want[i][3] == got[i][3]) if want_raw_cfg else None),
+                "note": "CPU side = float64 numpy.var argmax (ruptures restatement); GPU side = exact rational argmax"})
+    parity = parity_all[0] if parity_all else None
 
-    # ---- end to end: pinned host buffers -> tps_submit / tps_wait (3 slots in flight)
+    # ---- end to end: pinned host buffers -> tps_submit / tps_wait (3 slots in flight per pattern set)
     e2e = None
     if not a.no_e2e:
         depth = 3
@@ -352,12 +401,14 @@ def main():
             pending, last = [], None
             for i in range(nsteps):
                 b = i % nb
-                bid = ctx.submit(host_bases[b].array[:nbases[b]], host_off[b].array.view(np.uint64))
-                pending.append(bid)
+                c = ctxs[b % nm]
+                pending.append((c, c.submit(host_bases[b].array[:nbases[b]], host_off[b].array.view(np.uint64))))
                 if len(pending) >= depth:
-                    last = ctx.wait(pending.pop(0))
+                    c0, bid = pending.pop(0)
+                    last = c0.wait(bid)
             while pending:
-                last = ctx.wait(pending.pop(0))
+                c0, bid = pending.pop(0)
+                last = c0.wait(bid)
             return last
 
         run_e2e(max(a.warmup, 1))
@@ -376,89 +427,100 @@ def main():
                "ms_per_step": e_wall / a.steps * 1e3, "slots_in_flight": depth}
     clocks = sampler.stop(t0, time.perf_counter())
 
-    # ---- end to end from a FASTQ file: C reader (host threads) -> pinned batches -> H2D -> kernels -> D2H
-    # -> harvest of the TRC-pass reads, through the same Scanner the `topsicle` CLI uses
+    # ---- end to end from FASTQ files: C reader (host threads) -> pinned batches -> H2D -> kernels -> D2H
+    # -> harvest of the TRC-pass reads, through the same Scanner the `topsicle` CLI uses.  One file per pattern
+    # set, each scanned under its own set (config 5); every telophrase + raw-count tables from one pass (config 3)
     e2e_file = None
     if not a.no_parse:
         from topsicle_b200 import pipeline
-        ctx.close()
+        for c in ctxs:
+            c.close()
         shm = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else "/tmp"
-        path = os.path.join(shm, f"tps_bench_{os.getpid()}_r{rank}.fastq")
+        paths = [os.path.join(shm, f"tps_bench_{os.getpid()}_r{rank}_{mi}.fastq") for mi in range(nm)]
         try:
-            synth.write_fastq(path, host_bases[0].array[:nbases[0]], host_off[0].array.view(np.uint64),
-                              prefix=f"syn{a.config}", first_read=rank * nb * reads_per_step)
-            fsize = os.path.getsize(path)
-            # every telophrase of the configuration (config 3: 4 5 6 + raw count tables) from one pass
-            phrases = spec["cli"].get("telophrase") or [kw["phrase"]]
-            cfgs = [pipeline.ScanConfig(patterns=patterns_to_search(kw["pattern"], k), len_telopattern=len(kw["pattern"]),
-                                        phrase=k, cutoff=kw["cutoff"], min_seq_length=kw["min_len"],
-                                        window_size=kw["W"], slide=kw["slide"], trimfirst=kw["trim"],
-                                        maxlengthtelo=kw["maxlen"],
-                                        want_rawcount=bool(spec["cli"].get("rawcountpattern")))
-                    for k in phrases]
-            got = []
+            for mi, path in enumerate(paths):
+                synth.write_fastq(path, host_bases[mi].array[:nbases[mi]], host_off[mi].array.view(np.uint64),
+                                  prefix=f"syn{a.config}", first_read=first_reads[mi])
+            fsize = sum(os.path.getsize(p) for p in paths)
+            if nm == 1:
+                cfgs = [pipeline.ScanConfig(patterns=patterns_to_search(kw["pattern"], k), len_telopattern=len(kw["pattern"]),
+                                            phrase=k, cutoff=kw["cutoff"], min_seq_length=kw["min_len"],
+                                            window_size=kw["W"], slide=kw["slide"], trimfirst=kw["trim"],
+                                            maxlengthtelo=kw["maxlen"], want_rawcount=want_raw_cfg)
+                        for k in phrases_all]
+                groups, leaders = [None], (0,)
+            else:
+                cfgs = [pipeline.ScanConfig(patterns=patterns_to_search(k["pattern"], k["phrase"]),
+                                            len_telopattern=len(k["pattern"]), phrase=k["phrase"], cutoff=k["cutoff"],
+                                            min_seq_length=k["min_len"], window_size=k["W"], slide=k["slide"],
+                                            trimfirst=k["trim"], maxlengthtelo=k["maxlen"]) for k in kws]
+                groups, leaders = [[mi] for mi in range(nm)], tuple(range(nm))
             # ranks share the host cores (a rank bound to its GPU's CPUs already has its share)
             host_threads = max(1, cores_before // world)
-            with pipeline.Scanner(cfgs, devices=[local_rank], max_batch_bases=1 << 28, max_batch_reads=1 << 17,
-                                  depth=3, threads=host_threads) as sc:
-                sc.scan_file(path, lambda res: None)           # warm-up pass (page cache, first launches)
-                barrier()
-                t4 = time.perf_counter()
-                for _ in range(a.parse_passes):
-                    got.clear()
-                    st = sc.scan_file(path, lambda res: got.extend(res.passes[0]))
-                barrier()
-                t5 = time.perf_counter()
-            p_wall = max_over_ranks(t5 - t4)
-            p_bases = sum_over_ranks(float(st.n_bases * a.parse_passes))
-            assert st.n_reads == reads_per_step and st.n_bases == nbases[0]
-            # the same file through the ends-first mode (reported separately: the interior of the reads is
+
+            def timed_passes(ends_first):
+                got = [[] for _ in paths]
+                with pipeline.Scanner(cfgs, devices=[local_rank], max_batch_bases=1 << 28, max_batch_reads=1 << 17,
+                                      depth=3, threads=host_threads, ends_first=ends_first, leaders=leaders) as sc:
+                    def jobs():
+                        return [pipeline.FileJob(p, (lambda res, j=j: got[j].extend(res.passes[0])), cfg_ids=groups[j])
+                                for j, p in enumerate(paths)]
+                    sc.scan_files(jobs(), readers=1)           # warm-up pass (page cache, first launches)
+                    barrier()
+                    ta = time.perf_counter()
+                    for _ in range(a.parse_passes):
+                        for g in got:
+                            g.clear()
+                        stats = sc.scan_files(jobs(), readers=1)
+                    barrier()
+                    tb = time.perf_counter()
+                return got, stats, max_over_ranks(tb - ta)
+
+            got, stats, p_wall = timed_passes(False)
+            n_bases_pass = sum(st.n_bases for st in stats)
+            p_bases = sum_over_ranks(float(n_bases_pass * a.parse_passes))
+            assert sum(st.n_reads for st in stats) == reads_per_step * nm and n_bases_pass == sum(nbases[:nm])
+            # the same files through the ends-first mode (reported separately: the interior of the reads is
             # neither copied nor uploaded nor packed; B_alg' = the bytes actually touched)
-            got_full = [(p.index, p.tail, p.count, p.telo_length) for p in got]
-            got2 = []
-            with pipeline.Scanner(cfgs, devices=[local_rank], max_batch_bases=1 << 28, max_batch_reads=1 << 17,
-                                  depth=3, threads=host_threads, ends_first=True) as sc:
-                sc.scan_file(path, lambda res: None)
-                barrier()
-                t6 = time.perf_counter()
-                for _ in range(a.parse_passes):
-                    got2.clear()
-                    st2 = sc.scan_file(path, lambda res: got2.extend(res.passes[0]))
-                barrier()
-                t7 = time.perf_counter()
-            q_wall = max_over_ranks(t7 - t6)
+            got2, stats2, q_wall = timed_passes(True)
+            key = lambda gs: [[(p.index, p.tail, p.count, p.telo_length) for p in g] for g in gs]  # noqa: E731
+            timing = lambda sts: {k: round(sum(st.timing[k] for st in sts), 4) for k in sts[0].timing}  # noqa: E731
             e2e_ends = {"value": p_bases / q_wall / 1e9, "unit": UNIT, "ms_per_pass": q_wall / a.parse_passes * 1e3,
-                        "uploaded_bases_per_pass": int(st2.n_uploaded), "bases_per_pass": int(st2.n_bases),
-                        "uploaded_fraction": st2.n_uploaded / max(1, st2.n_bases),
-                        "rows_identical_to_whole_read_scan":
-                            [(p.index, p.tail, p.count, p.telo_length) for p in got2] == got_full,
-                        "host_seconds_last_pass": {k: round(v, 4) for k, v in st2.timing.items()},
-                        "what": "same file, Scanner(ends_first=True): head + tail of every read uploaded and "
+                        "uploaded_bases_per_pass": int(sum(st.n_uploaded for st in stats2)),
+                        "bases_per_pass": int(n_bases_pass),
+                        "uploaded_fraction": sum(st.n_uploaded for st in stats2) / max(1, n_bases_pass),
+                        "rows_identical_to_whole_read_scan": key(got2) == key(got),
+                        "host_seconds_last_pass": timing(stats2),
+                        "what": "same files, Scanner(ends_first=True): head + tail of every read uploaded and "
                                 "scanned (K1 + K2), then the regions of the TRC-pass reads (K1..K4); reported "
                                 "separately from e2e_from_fastq because the interior of the reads is never touched"}
-            e2e_file = {"value": p_bases / p_wall / 1e9, "unit": UNIT, "file_bytes": fsize, "passes": a.parse_passes,
-                        "ms_per_pass": p_wall / a.parse_passes * 1e3, "host_threads_per_rank": host_threads,
-                        "trc_pass_reads": len(got), "telophrases": phrases,
-                        "rawcount_tables": bool(spec["cli"].get("rawcountpattern")), "host_seconds_last_pass": {k: round(v, 4) for k, v in st.timing.items()},
+            e2e_file = {"value": p_bases / p_wall / 1e9, "unit": UNIT, "file_bytes": fsize, "files": len(paths),
+                        "passes": a.parse_passes, "ms_per_pass": p_wall / a.parse_passes * 1e3,
+                        "host_threads_per_rank": host_threads, "trc_pass_reads": sum(len(g) for g in got),
+                        "patterns": motifs, "telophrases": phrases_all if nm == 1 else [k["phrase"] for k in kws],
+                        "rawcount_tables": want_raw_cfg, "host_seconds_last_pass": timing(stats),
                         "what": "uncompressed FASTQ in page cache -> telomere rows (parse + PCIe + kernels + harvest)",
                         "ends_first": e2e_ends}
         finally:
-            if os.path.exists(path):
-                os.remove(path)
+            for path in paths:
+                if os.path.exists(path):
+                    os.remove(path)
 
     n_pass = int((rows_dev["status"] >= engine.ST_PASS).sum())
     peak, peak_src = hbm_peak()
     alg_bytes = ALG_BYTES_PER_BASE * bases_attr
     achieved = alg_bytes / (k1_ms * 1e-3) / 1e9
-    tpb = ncu_traffic_per_base()
+    tpb, tpb_src = ncu_traffic_per_base()
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": wall / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u8", "data": "synthetic (synth-v1, per-read xoshiro streams; see topsicle_b200/synth.py)",
                 "config": {"workload": spec["name"], "reads_per_step": reads_per_step,
                            "bases_per_step": int(bases_timed / a.steps), "distinct_batches": nb, "streams": n_streams,
-                           "pattern": kw["pattern"], "telophrase": kw["phrase"], "cutoff": kw["cutoff"],
-                           "minSeqLength": kw["min_len"], "windowSize": kw["W"], "slide": kw["slide"],
+                           "pattern": kw["pattern"] if nm == 1 else motifs,
+                           "telophrase": kw["phrase"] if nm == 1 else [k["phrase"] for k in kws], "cutoff": kw["cutoff"],
+                           "minSeqLength": kw["min_len"], "windowSize": kw["W"],
+                           "slide": kw["slide"] if nm == 1 else [k["slide"] for k in kws],
                            "trimfirst": kw["trim"], "maxlengthtelo": kw["maxlen"],
                            "l2_policy": "each step reads a batch (>1 GB) far larger than the 126 MB L2",
                            "parallelism": f"reads sharded over {world} GPU(s), no collective"},
@@ -469,15 +531,17 @@ def main():
                 "roofline": {"bound": "hbm", "kernel": K1_KERNEL, "achieved": achieved, "peak": peak,
                              "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                              "algorithmic_bytes_per_base": ALG_BYTES_PER_BASE,
-                             "traffic": (tpb * bases_timed / a.steps) if tpb else None,
+                             "traffic": (tpb * bases_timed / a.steps) if tpb else None, "traffic_source": tpb_src,
                              "whole_scan_frac": alg_bytes / (dev_ms * 1e-3) / 1e9 / peak,
                              "pipelined_scan_frac": ALG_BYTES_PER_BASE * value / peak / world},
-                "cpu_baseline": cpu, "parity_sample": parity, "e2e": e2e, "e2e_from_fastq": e2e_file, "gpu_launches": int(launches),
+                "cpu_baseline": cpu, "parity_sample": parity, "parity_all": parity_all or None, "e2e": e2e,
+                "e2e_from_fastq": e2e_file, "gpu_launches": int(launches),
                 "clocks": clocks,
                 "generate_s": t_gen,
                 "host_placement": {"cpus_local_to_gpu0": near, "bound": bool(near and world > 1)}}
         emit(line)
-    ctx.close()
+    for c in ctxs:
+        c.close()
     for hb in host_bases + host_off:
         hb.free()
     if world > 1:

@@ -46,10 +46,12 @@ def _windows(s, window_size, step):
 
 
 def scan_shard(args):
-    """Reference-style scan of a list of (index, read string) -> (n_scanned, n_pass, [(index, tail, count, telo)])."""
+    """Reference-style scan of a list of (index, read string) -> (n_scanned, n_pass, [(index, tail, count, telo,
+    md5 of the chosen tail's uint8 count table [window][literal] or None)])."""
+    import hashlib
     import ruptures as rpt  # restated 1.1.9 (oracle/shims)
     from oracle.topsicle_oracle import patterns_to_search
-    seqs, pattern, phrase, cutoff, min_len, W, slide, trim, maxlen = args
+    seqs, pattern, phrase, cutoff, min_len, W, slide, trim, maxlen, want_raw = args
     literals = patterns_to_search(pattern, phrase)
     compiled = [re.compile(p) for p in literals]
     ratio = 1000 / len(pattern)
@@ -78,20 +80,27 @@ def scan_shard(args):
         s_fwd = seq[trim:m].upper()
         s_rev = seq[::-1].upper()[trim:m]
         mean_s, mean_e = [], []
+        tab_s, tab_e = [], []
         for start, cut in _windows(s_fwd, W, slide):
             c = [len([mm.start() for mm in pat.finditer(cut)]) or 1 for pat in compiled]
             mean_s.append((start, sum(c) / len(c)))
+            tab_s.append(c)
         for start, cut in _windows(s_rev, W, slide):
             c = [len([mm.start() for mm in pat.finditer(cut)]) or 1 for pat in compiled]
             mean_e.append((start, sum(c) / len(c)))
+            tab_e.append(c)
         mean = mean_s if tail == "forward" else mean_e
+        digest = None
+        if want_raw:     # rawCountPattern's table of the chosen tail (allsteps.py:401-416), as the kernels return it
+            tab = tab_s if tail == "forward" else tab_e
+            digest = hashlib.md5(np.asarray(tab, dtype=np.uint8).tobytes()).hexdigest()
         x = [a + trim for a, _ in mean]
         y = [b for _, b in mean]
         if len(y) < 7:
-            telo.append((gi, tail, trc, -1))
+            telo.append((gi, tail, trc, -1, digest))
             continue
         res = rpt.Binseg(model="l2").fit(np.array(y)).predict(pen=4, n_bkps=1)
-        telo.append((gi, tail, trc, int(x[res[0]])))
+        telo.append((gi, tail, trc, int(x[res[0]]), digest))
     return n_scanned, len(passing), telo
 
 
@@ -111,7 +120,7 @@ def time_sample(seqs, scan_kw, cores, steps=1, warmup=0):
     import multiprocessing as mp
     shards = deal_shards(seqs, cores)
     argl = [(sh, scan_kw["pattern"], scan_kw["phrase"], scan_kw["cutoff"], scan_kw["min_len"], scan_kw["W"],
-             scan_kw["slide"], scan_kw["trim"], scan_kw["maxlen"]) for sh in shards]
+             scan_kw["slide"], scan_kw["trim"], scan_kw["maxlen"], scan_kw.get("want_raw", False)) for sh in shards]
     times, last = [], None
     ctx = mp.get_context("fork")
     with ctx.Pool(processes=cores) as pool:
@@ -134,18 +143,24 @@ def main():
     ap.add_argument("--steps", type=int, default=1)
     ap.add_argument("--warmup", type=int, default=0)
     ap.add_argument("--cores", type=int, default=0)
+    ap.add_argument("--motif", default="", help="pattern of this sub-batch (config 5: TTAGGG / TTTAGGG / AAACCCT)")
+    ap.add_argument("--phrase", type=int, default=0, help="telophrase (default: the configuration's first)")
+    ap.add_argument("--raw", action="store_true", help="also return the md5 of every TRC-pass read's count table")
     a = ap.parse_args()
     from topsicle_b200 import synth
     spec = synth.CONFIGS[a.config]
-    cli = spec["cli"]
-    bases, off, _ = synth.generate(spec, a.first_read, a.reads)
+    cli = dict(spec["cli"])
+    if a.motif:
+        cli["pattern"] = a.motif
+    bases, off, _ = synth.generate(spec, a.first_read, a.reads, motif=a.motif or None)
     buf = bases.tobytes().decode("ascii")
     seqs = [buf[int(off[i]):int(off[i + 1])] for i in range(a.reads)]
     cores = a.cores or len(os.sched_getaffinity(0))
     pattern = cli["pattern"]
     phrases = cli.get("telophrase") or [len(pattern) - 2]
     cut = cli.get("cutoff", 0.7)
-    kw = dict(pattern=pattern, phrase=phrases[0], cutoff=min(cut) if isinstance(cut, list) else cut,
+    kw = dict(pattern=pattern, phrase=a.phrase or phrases[0], want_raw=a.raw,
+              cutoff=min(cut) if isinstance(cut, list) else cut,
               min_len=cli.get("minSeqLength", 9000), W=cli.get("windowSize", 100),
               slide=cli.get("slide") or len(pattern), trim=cli.get("trimfirst", 100),
               maxlen=cli.get("maxlengthtelo", 20000))
@@ -154,7 +169,8 @@ def main():
     print(json.dumps(dict(config=a.config, reads=a.reads, bases=n_bases, cores=cores, n_pass=n_pass,
                           seconds=times, gbases_per_s=[n_bases / t / 1e9 for t in times],
                           reads_per_s=[a.reads / t for t in times],
-                          pass_rows=[[gi + a.first_read, tail, trc, telo] for gi, tail, trc, telo in rows])))
+                          pattern=pattern, phrase=kw["phrase"],
+                          pass_rows=[[gi + a.first_read, tail, trc, telo, dig] for gi, tail, trc, telo, dig in rows])))
 
 
 if __name__ == "__main__":

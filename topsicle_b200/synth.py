@@ -62,9 +62,13 @@ CONFIGS = {
             seed=2004, total_reads=1_333_000, len_kind=2, len_a=100_000.0, len_b=50_000.0, len_min=100_000,
             len_max=1_000_000, f_telo=0.005, telo_min=2000, telo_max=18000, motif="CCCTAA", **ONT,
             cli=dict(pattern="CCCTAA", maxlengthtelo=20000)),
-    5: dict(name="config5: mixed species, LogNormal N50 20 kb, --windowSize 50 --slide 3",
-            seed=2005, total_reads=1_000_000, len_kind=1, len_a=math.log(20000.0) - 0.49, len_b=0.7,
+    # three sub-batches of 1 M reads, one per species: the reference takes one --pattern per invocation
+    # (main.py:321), so each sub-batch is scanned under its own pattern set
+    5: dict(name="config5: mixed species (TTAGGG, TTTAGGG, AAACCCT sub-batches), LogNormal N50 20 kb, "
+                 "--windowSize 50 --slide 3",
+            seed=2005, total_reads=3_000_000, len_kind=1, len_a=math.log(20000.0) - 0.49, len_b=0.7,
             len_min=1000, len_max=250_000, f_telo=0.05, telo_min=2000, telo_max=12000, motif="TTAGGG", **ONT,
+            sub_batches=["TTAGGG", "TTTAGGG", "AAACCCT"],
             cli=dict(pattern="TTAGGG", windowSize=50, slide=3)),
 }
 
@@ -85,9 +89,9 @@ def make_cfg(spec: dict, motif: str | None = None) -> SynthCfg:
     return c
 
 
-def read_lengths(spec: dict, first_read: int, n_reads: int) -> np.ndarray:
+def read_lengths(spec: dict, first_read: int, n_reads: int, motif: str | None = None) -> np.ndarray:
     """offsets[n_reads+1] (uint64) of reads first_read .. first_read+n_reads-1 laid back to back."""
-    cfg = make_cfg(spec)
+    cfg = make_cfg(spec, motif)
     off = np.zeros(n_reads + 1, dtype=np.uint64)
     rc = host_library().tps_synth_lengths(C.byref(cfg), first_read, n_reads, off.ctypes.data)
     assert rc == 0
@@ -107,10 +111,10 @@ def fill_reads(spec: dict, first_read: int, offsets: np.ndarray, out: np.ndarray
     return kinds
 
 
-def generate(spec: dict, first_read: int, n_reads: int, threads: int = 0):
-    off = read_lengths(spec, first_read, n_reads)
+def generate(spec: dict, first_read: int, n_reads: int, threads: int = 0, motif: str | None = None):
+    off = read_lengths(spec, first_read, n_reads, motif)
     bases = np.empty(int(off[-1]), dtype=np.uint8)
-    kinds = fill_reads(spec, first_read, off, bases, threads)
+    kinds = fill_reads(spec, first_read, off, bases, threads, motif)
     return bases, off, kinds
 
 

@@ -463,7 +463,8 @@ def main():
                 with pipeline.Scanner(cfgs, devices=[local_rank], max_batch_bases=1 << 28, max_batch_reads=1 << 17,
                                       depth=3, threads=host_threads, ends_first=ends_first, leaders=leaders) as sc:
                     def jobs():
-                        return [pipeline.FileJob(p, (lambda res, j=j: got[j].extend(res.passes[0])), cfg_ids=groups[j])
+                        # the sink keeps the batch's columnar result (PassBatch); rows are compared after the clock stops
+                        return [pipeline.FileJob(p, (lambda res, j=j: got[j].append(res.passes[0])), cfg_ids=groups[j])
                                 for j, p in enumerate(paths)]
                     sc.scan_files(jobs(), readers=1)           # warm-up pass (page cache, first launches)
                     barrier()
@@ -483,7 +484,7 @@ def main():
             # the same files through the ends-first mode (reported separately: the interior of the reads is
             # neither copied nor uploaded nor packed; B_alg' = the bytes actually touched)
             got2, stats2, q_wall = timed_passes(True)
-            key = lambda gs: [[(p.index, p.tail, p.count, p.telo_length) for p in g] for g in gs]  # noqa: E731
+            key = lambda gs: [[(p.index, p.tail, p.count, p.telo_length) for pb in g for p in pb] for g in gs]  # noqa: E731
             timing = lambda sts: {k: round(sum(st.timing[k] for st in sts), 4) for k in sts[0].timing}  # noqa: E731
             e2e_ends = {"value": p_bases / q_wall / 1e9, "unit": UNIT, "ms_per_pass": q_wall / a.parse_passes * 1e3,
                         "uploaded_bases_per_pass": int(sum(st.n_uploaded for st in stats2)),
@@ -496,7 +497,7 @@ def main():
                                 "separately from e2e_from_fastq because the interior of the reads is never touched"}
             e2e_file = {"value": p_bases / p_wall / 1e9, "unit": UNIT, "file_bytes": fsize, "files": len(paths),
                         "passes": a.parse_passes, "ms_per_pass": p_wall / a.parse_passes * 1e3,
-                        "host_threads_per_rank": host_threads, "trc_pass_reads": sum(len(g) for g in got),
+                        "host_threads_per_rank": host_threads, "trc_pass_reads": sum(len(pb) for g in got for pb in g),
                         "patterns": motifs, "telophrases": phrases_all if nm == 1 else [k["phrase"] for k in kws],
                         "rawcount_tables": want_raw_cfg, "host_seconds_last_pass": timing(stats),
                         "what": "uncompressed FASTQ in page cache -> telomere rows (parse + PCIe + kernels + harvest)",

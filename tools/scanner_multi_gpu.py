@@ -72,14 +72,14 @@ def main():
         print(json.dumps({"generated": n_files, "reads_per_file": reads_per_file, "gbases": round(total_bases / 1e9, 2),
                           "fastq_gb": round(sum(os.path.getsize(p) for p, _ in files) / 1e9, 1),
                           "seconds": round(time.perf_counter() - t0, 1)}), flush=True)
-        key = lambda ps: [(p.index, p.read_id, p.tail, p.count, p.telo_length) for p in ps]  # noqa: E731
+        key = lambda pbs: [(p.index, p.read_id, p.tail, p.count, p.telo_length) for pb in pbs for p in pb]  # noqa: E731
 
         def run(devices, ends_first, use_files):
             got = {p: [] for p, _ in use_files}
             with pipeline.Scanner(cfgs, devices=devices, leaders=tuple(range(nm)), ends_first=ends_first,
                                   threads=len(os.sched_getaffinity(0))) as sc:
                 def jobs():
-                    return [pipeline.FileJob(p, (lambda res, p=p: got[p].extend(res.passes[0])), cfg_ids=[mi])
+                    return [pipeline.FileJob(p, (lambda res, p=p: got[p].append(res.passes[0])), cfg_ids=[mi])
                             for p, mi in use_files]
                 sc.scan_files(jobs())                    # warm-up: page cache, first launches
                 t = time.perf_counter()
@@ -104,7 +104,7 @@ def main():
                 print(json.dumps({"config": a.config, "workload": spec["name"], "gpus": n, "files": len(use),
                                   "patterns": motifs, "ends_first": ends_first, "gbases_per_pass": round(nbases / 1e9, 2),
                                   "seconds_per_pass": round(dt, 4), "gbases_per_s": round(nbases / dt / 1e9, 2),
-                                  "trc_pass_reads": sum(len(g) for g in got.values()),
+                                  "trc_pass_reads": sum(len(pb) for g in got.values() for pb in g),
                                   "uploaded_fraction": round(sum(st.n_uploaded for st in stats) / max(1, nbases), 4),
                                   "rows_identical_to_first_run": same,
                                   "host_threads": len(os.sched_getaffinity(0))}), flush=True)
@@ -115,7 +115,7 @@ def main():
                 with pipeline.Scanner([cfgs[mi]], devices=[0]) as sc:
                     for p, _ in mine:
                         rows = []
-                        sc.scan_file(p, lambda res: rows.extend(res.passes[0]))
+                        sc.scan_file(p, lambda res: rows.append(res.passes[0]))
                         ok = ok and key(rows) == ref_rows[p]
             print(json.dumps({"config": a.config, "per_pattern_rows_identical_to_single_pattern_runs": ok}), flush=True)
     finally:

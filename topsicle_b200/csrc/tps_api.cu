@@ -12,6 +12,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
 #include <new>
 
 #include "tps_kernels.cuh"
@@ -92,6 +93,47 @@ struct tps_ctx {
 };
 
 namespace {
+
+/* The pack / tail stream pair is one per DEVICE, shared by every context of the process on that device
+ * (reference-counted): the contexts of several pattern sets or telophrases then queue their K1s on one stream --
+ * never two persistent HBM-bound pack kernels resident at once -- and their K2..K4 on the other. */
+struct DevStreams {
+  cudaStream_t pack = nullptr, tail = nullptr;
+  int refs = 0;
+};
+std::mutex g_dev_mutex;
+DevStreams g_dev_streams[64];
+
+int acquire_dev_streams(int device, cudaStream_t *pack, cudaStream_t *tail) {
+  std::lock_guard<std::mutex> lk(g_dev_mutex);
+  DevStreams &d = g_dev_streams[device & 63];
+  if (d.refs == 0) {
+    int pr_lo = 0, pr_hi = 0;
+    if (cudaDeviceGetStreamPriorityRange(&pr_lo, &pr_hi) != cudaSuccess) return -1;
+    if (cudaStreamCreateWithPriority(&d.pack, cudaStreamNonBlocking, pr_lo) != cudaSuccess) return -1;
+    if (cudaStreamCreateWithPriority(&d.tail, cudaStreamNonBlocking, pr_hi) != cudaSuccess) {
+      cudaStreamDestroy(d.pack);
+      d.pack = nullptr;
+      return -1;
+    }
+  }
+  ++d.refs;
+  *pack = d.pack;
+  *tail = d.tail;
+  return 0;
+}
+
+void release_dev_streams(int device) {
+  std::lock_guard<std::mutex> lk(g_dev_mutex);
+  DevStreams &d = g_dev_streams[device & 63];
+  if (d.refs > 0 && --d.refs == 0) {
+    cudaStreamSynchronize(d.pack);
+    cudaStreamSynchronize(d.tail);
+    cudaStreamDestroy(d.pack);
+    cudaStreamDestroy(d.tail);
+    d.pack = d.tail = nullptr;
+  }
+}
 
 int fail(tps_ctx *ctx, int code, const char *fmt, ...) {
   char *dst = ctx ? ctx->err : g_create_error;
@@ -214,8 +256,12 @@ void tps_destroy(tps_ctx *ctx) {
     if (s.e_tail) cudaEventDestroy(s.e_tail);
     if (s.stream) cudaStreamDestroy(s.stream);
   }
-  if (ctx->pack_stream) { cudaStreamSynchronize(ctx->pack_stream); cudaStreamDestroy(ctx->pack_stream); }
-  if (ctx->tail_stream) { cudaStreamSynchronize(ctx->tail_stream); cudaStreamDestroy(ctx->tail_stream); }
+  if (ctx->pack_stream) { /* shared with the other contexts of this device: drained, then released */
+    cudaStreamSynchronize(ctx->pack_stream);
+    cudaStreamSynchronize(ctx->tail_stream);
+    release_dev_streams(ctx->device);
+    ctx->pack_stream = ctx->tail_stream = nullptr;
+  }
   for (int r = 0; r < TPS_TIMING_RING; ++r)
     for (int i = 0; i < 4; ++i)
       if (ctx->ev[r][i]) cudaEventDestroy(ctx->ev[r][i]);
@@ -435,11 +481,10 @@ int tps_create(tps_ctx **out, int device, const tps_params *params) {
   {
     const char *e = getenv("TPS_SPLIT_STREAMS"); /* 0 = everything of a batch on its slot's stream */
     ctx->split = !(e && atoi(e) == 0);
-    if (ctx->split) {
-      int pr_lo = 0, pr_hi = 0;
-      TPS_CC(cudaDeviceGetStreamPriorityRange(&pr_lo, &pr_hi));
-      TPS_CC(cudaStreamCreateWithPriority(&ctx->pack_stream, cudaStreamNonBlocking, pr_lo));
-      TPS_CC(cudaStreamCreateWithPriority(&ctx->tail_stream, cudaStreamNonBlocking, pr_hi));
+    if (ctx->split && acquire_dev_streams(device, &ctx->pack_stream, &ctx->tail_stream) != 0) {
+      int c_ = fail(nullptr, TPS_ECUDA, "cannot create the pack / tail streams: %s", cudaGetErrorString(cudaGetLastError()));
+      tps_destroy(ctx);
+      return c_;
     }
   }
   ctx->cap_tiles = (p.max_batch_bases + 511) / 512;

@@ -72,6 +72,61 @@ class PassRead:
     record: bytes | memoryview | None = None   # SeqIO.write text when want_records
 
 
+class PassBatch:
+    """The TRC-pass reads of one batch under one config, as columns: what a device hands back is arrays, and a
+    batch of a telomere-enriched library holds thousands of passing reads, so the rows stay arrays until somebody
+    asks for one read.  Behaves as a sequence of PassRead (len, iteration, indexing) built on demand; the
+    raw-count tables (`table(j)`, `PassRead.counts`) are views of one array per batch.
+
+    Columns (numpy, length n): index (position of the read in its file), count, literal_idx, tail_code, status,
+    n_windows, telo_length, length; `ids` (list of str), `trc` (float64 = count / (no_bp / len(pattern)),
+    allsteps.py:178-186), `records` (SeqIO.write text per read when asked for, else None)."""
+
+    __slots__ = ("cfg", "patterns", "index", "ids", "count", "literal_idx", "tail_code", "status", "n_windows",
+                 "telo_length", "length", "trc", "records", "_raw", "_raw_off", "_tables")
+
+    def __init__(self, cfg, patterns, index, ids, sel, raw=None, raw_off=None, tables=None, records=None):
+        self.cfg, self.patterns = cfg, patterns
+        self.index, self.ids = index, ids
+        self.count = sel["match_count"]
+        self.literal_idx = sel["best_pattern"]
+        self.tail_code = sel["tail"]
+        self.status = sel["status"]
+        self.n_windows = sel["n_windows"]
+        self.telo_length = sel["telo_length"]
+        self.length = sel["length"]
+        self.trc = self.count / (cfg.no_bp / cfg.len_telopattern)
+        self.records = records
+        self._raw, self._raw_off, self._tables = raw, raw_off, tables
+
+    def __len__(self):
+        return len(self.index)
+
+    def table(self, j):
+        """uint8 counts[n_windows][n_patterns] of the j-th passing read, or None."""
+        if self._tables is not None:
+            return self._tables[j]
+        if self._raw is None or int(self._raw_off[j]) == engine.NO_RAWCOUNT:
+            return None
+        nw, npat, off = int(self.n_windows[j]), len(self.patterns), int(self._raw_off[j])
+        return self._raw[off:off + nw * npat].reshape(nw, npat)
+
+    def __getitem__(self, j):
+        if isinstance(j, slice):
+            return [self[i] for i in range(*j.indices(len(self)))]
+        if j < 0:
+            j += len(self)
+        return PassRead(index=int(self.index[j]), read_id=self.ids[j], literal=self.patterns[int(self.literal_idx[j])],
+                        tail=engine.TAIL_NAMES[int(self.tail_code[j])], count=int(self.count[j]), trc=float(self.trc[j]),
+                        status=int(self.status[j]), n_windows=int(self.n_windows[j]),
+                        telo_length=int(self.telo_length[j]), length=int(self.length[j]),
+                        counts=self.table(j) if self.cfg.want_rawcount else None,
+                        record=self.records[j] if self.records is not None else None)
+
+    def __iter__(self):
+        return (self[j] for j in range(len(self)))
+
+
 @dataclass
 class BatchResult:
     seq: int
@@ -79,7 +134,7 @@ class BatchResult:
     n_reads: int
     n_bases: int
     n_scanned: int                     # reads with L > minSeqLength
-    passes: list = field(default_factory=list)   # per config: list[PassRead]
+    passes: list = field(default_factory=list)   # per config of the job: PassBatch (a sequence of PassRead)
     n_uploaded: int = 0                # bases that crossed PCIe for this batch (ends-first: ends + regions)
 
 
@@ -142,36 +197,27 @@ def windows_per_read(cfg: ScanConfig) -> int:
     return (reg - cfg.window_size) // cfg.slide + 1 if reg >= cfg.window_size else 0
 
 
-def harvest(cfg: ScanConfig, ctx, batch, rows, raw, want_records: bool, keep=None, tables=None) -> list:  # noqa: D401
-    """TRC-pass reads of one finished batch, in read order.  `tables` (ends-first mode) maps a read index to
-    its raw-count table instead of `raw` + the rows' offsets."""
-    out = []
+def harvest(cfg: ScanConfig, ctx, batch, rows, raw, want_records: bool, keep=None, tables=None) -> PassBatch:
+    """TRC-pass reads of one finished batch, in read order, as one PassBatch (no per-read Python work: a handful of
+    array operations and two C calls per batch).  `tables` (ends-first mode) maps a read index to its raw-count table
+    instead of `raw` + the rows' offsets."""
     idx = np.nonzero(rows["status"] >= engine.ST_PASS)[0]
-    if len(idx) == 0:
-        return out
+    ids = batch.read_ids(idx) if len(idx) else []   # one C call for the ids of all TRC-pass reads of the batch
+    if keep is not None and len(idx):
+        sel_keep = np.fromiter((rid in keep for rid in ids), dtype=bool, count=len(ids))
+        idx = idx[sel_keep]
+        ids = [rid for rid, k in zip(ids, sel_keep) if k]
     sel = rows[idx]
-    cols = [sel[f].tolist() for f in ("match_count", "best_pattern", "tail", "status", "n_windows", "telo_length",
-                                      "length")]
-    ratio = cfg.no_bp / cfg.len_telopattern            # allsteps.py:178
-    if cfg.want_rawcount and tables is None and raw is not None:
-        raw = np.array(raw, copy=True)     # ONE copy out of the context's landing buffer; the tables are views of it
-    ids = batch.read_ids(idx)              # one C call for the ids of all TRC-pass reads of the batch
-    for i, rid, cnt, bp, tl, st, nw, telo, length in zip(idx.tolist(), ids, *cols):
-        if keep is not None and rid not in keep:
-            continue
-        pr = PassRead(index=batch.first_read + i, read_id=rid, literal=ctx.patterns[bp],
-                      tail=engine.TAIL_NAMES[tl], count=cnt, trc=cnt / ratio, status=st,
-                      n_windows=nw, telo_length=telo, length=length)
-        if cfg.want_rawcount and tables is not None:
-            pr.counts = tables.get(i)
-        elif cfg.want_rawcount and raw is not None:
-            pr.counts = ctx.rawcount_table(rows, raw, i)
-        out.append(pr)
-    if want_records and out:               # SeqIO.write text of every kept read: one C call, views of one buffer
-        first = batch.first_read
-        for pr, text in zip(out, batch.records_text([pr.index - first for pr in out])):
-            pr.record = text
-    return out
+    raw_copy = raw_off = tabs = None
+    if cfg.want_rawcount and tables is not None:
+        tabs = [tables.get(int(i)) for i in idx]
+    elif cfg.want_rawcount and raw is not None:
+        raw_copy = np.array(raw, copy=True)  # ONE copy out of the context's landing buffer; the tables are views of it
+        raw_off = sel["rawcount_offset"]
+    records = None
+    if want_records and len(idx):          # SeqIO.write text of every kept read: one C call, views of one buffer
+        records = batch.records_text(idx)
+    return PassBatch(cfg, ctx.patterns, batch.first_read + idx, ids, sel, raw_copy, raw_off, tabs, records)
 
 
 class _DeviceWorker:
@@ -403,8 +449,9 @@ class _DeviceWorker:
             for lo, hi, rows, raw in parts:
                 scanned += int((rows["status"] != engine.ST_FILTERED).sum())
                 view = _BatchView(batch, lo)
-                passes += harvest(cfg, ctx, view, rows, raw, records_cfg == ci, keep)
-            res.passes.append(passes)
+                passes.append(harvest(cfg, ctx, view, rows, raw, records_cfg == ci, keep))
+            # one part unless the batch overflowed a capacity and was re-scanned in halves (then: plain list)
+            res.passes.append(passes[0] if len(passes) == 1 else [p for part in passes for p in part])
             if gi == 0:
                 res.n_scanned = scanned
         batch.release()

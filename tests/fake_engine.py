@@ -76,6 +76,10 @@ class OracleContext:
         self._pending[bid] = owner._pending[bid]
         return bid
 
+    def wait_leased(self, bid):
+        rows, raw = self.wait(bid)
+        return rows, raw, None
+
     def wait(self, bid, raw_view=False):
         buf, off, *mode = self._pending.pop(bid)
         kind, extra = mode if mode else (None, None)

@@ -211,6 +211,28 @@ class PinnedBuffer:
             pass
 
 
+class RawLease:
+    """A page-locked landing buffer that holds the raw-count tables of one finished batch, on loan from its
+    context's pool: the tables are handed out as views of it (no second copy of tens of megabytes per batch) and
+    stay valid until `release()`."""
+
+    __slots__ = ("_ctx", "_buf")
+
+    def __init__(self, ctx, buf):
+        self._ctx, self._buf = ctx, buf
+
+    def release(self):
+        if self._buf is not None:
+            self._ctx._raw_pool.append(self._buf)
+            self._buf = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
 class ScanContext:
     """One GPU scan context == the arguments of one process_file call (main.py:52-150)."""
 
@@ -263,12 +285,16 @@ class ScanContext:
             raise TpsError(rc, self.lib.tps_last_error(None).decode())
         self._inflight = {}
         self._raw_pin = None
+        self._raw_pool = []          # free landing buffers of wait_leased()
 
     # -- lifetime
     def close(self):
         if getattr(self, "_raw_pin", None) is not None:
             self._raw_pin.free()
             self._raw_pin = None
+        for b in getattr(self, "_raw_pool", []):
+            b.free()
+        self._raw_pool = []
         if getattr(self, "_h", None) and self._h.value:
             self.lib.tps_destroy(self._h)
             self._h = C.c_void_p()
@@ -370,6 +396,36 @@ class ScanContext:
         finally:
             del self._inflight[bid]
         return rows, raw
+
+    def wait_leased(self, bid: int):
+        """wait() for pipelines: (rows, raw tables as a view of a leased landing buffer or None, RawLease or None).
+        The view is valid until the lease is released; leases of several finished batches may be out at once."""
+        if not self.want_rawcount:
+            rows, _ = self.wait(bid)
+            return rows, None, None
+        bases, offsets, n_reads = self._inflight[bid]
+        rows = np.empty(n_reads, dtype=ROW_DTYPE)
+        n_pass = C.c_uint32(0)
+        elems = C.c_uint64(0)
+        buf = None
+        try:
+            self._check(self.lib.tps_batch_info(self._h, bid, C.byref(n_pass), C.byref(elems)))
+            need = min(int(elems.value), int(self.params.rawcount_capacity))
+            fit = [b for b in self._raw_pool if b.nbytes >= need]
+            if fit:
+                buf = min(fit, key=lambda b: b.nbytes)
+                self._raw_pool.remove(buf)
+            else:
+                buf = PinnedBuffer(max(need * 5 // 4, 1 << 22))
+            raw = buf.array[:need]
+            self._check(self.lib.tps_wait(self._h, bid, rows.ctypes.data, C.byref(n_pass), raw.ctypes.data, raw.size,
+                                          C.byref(elems)))
+            lease, buf = RawLease(self, buf), None
+            return rows, raw[:elems.value], lease
+        finally:
+            if buf is not None:
+                self._raw_pool.append(buf)
+            del self._inflight[bid]
 
     def scan(self, bases: np.ndarray, offsets: np.ndarray):
         """Synchronous scan of one host batch -> (rows, rawcounts or None)."""

@@ -83,9 +83,9 @@ class PassBatch:
     allsteps.py:178-186), `records` (SeqIO.write text per read when asked for, else None)."""
 
     __slots__ = ("cfg", "patterns", "index", "ids", "count", "literal_idx", "tail_code", "status", "n_windows",
-                 "telo_length", "length", "trc", "records", "_raw", "_raw_off", "_tables")
+                 "telo_length", "length", "trc", "records", "_raw", "_raw_off", "_tables", "_leases")
 
-    def __init__(self, cfg, patterns, index, ids, sel, raw=None, raw_off=None, tables=None, records=None):
+    def __init__(self, cfg, patterns, index, ids, sel, raw=None, raw_off=None, tables=None, records=None, leases=()):
         self.cfg, self.patterns = cfg, patterns
         self.index, self.ids = index, ids
         self.count = sel["match_count"]
@@ -98,9 +98,19 @@ class PassBatch:
         self.trc = self.count / (cfg.no_bp / cfg.len_telopattern)
         self.records = records
         self._raw, self._raw_off, self._tables = raw, raw_off, tables
+        self._leases = list(leases)
 
     def __len__(self):
         return len(self.index)
+
+    def release(self):
+        """Give the page-locked landing buffers behind the raw-count tables back to their contexts.  The pipeline
+        calls this when the sink has returned: a sink that keeps tables beyond its call copies them."""
+        for ls in self._leases:
+            ls.release()
+        self._leases = []
+        if self._raw is not None or self._tables is not None:
+            self._raw = self._tables = None
 
     def table(self, j):
         """uint8 counts[n_windows][n_patterns] of the j-th passing read, or None."""
@@ -137,6 +147,11 @@ class BatchResult:
     passes: list = field(default_factory=list)   # per config of the job: PassBatch (a sequence of PassRead)
     n_uploaded: int = 0                # bases that crossed PCIe for this batch (ends-first: ends + regions)
 
+    def release(self):
+        for p in self.passes:
+            if hasattr(p, "release"):
+                p.release()
+
 
 @dataclass
 class FileStats:
@@ -162,7 +177,11 @@ class _OrderedSink:
         with self.lock:
             self.held[res.seq] = res
             while self.next_seq in self.held:
-                self.fn(self.held.pop(self.next_seq))
+                res = self.held.pop(self.next_seq)
+                try:
+                    self.fn(res)
+                finally:
+                    res.release()      # the raw-count tables were views of leased landing buffers
                 self.next_seq += 1
 
 
@@ -197,7 +216,8 @@ def windows_per_read(cfg: ScanConfig) -> int:
     return (reg - cfg.window_size) // cfg.slide + 1 if reg >= cfg.window_size else 0
 
 
-def harvest(cfg: ScanConfig, ctx, batch, rows, raw, want_records: bool, keep=None, tables=None) -> PassBatch:
+def harvest(cfg: ScanConfig, ctx, batch, rows, raw, want_records: bool, keep=None, tables=None,
+            leases=()) -> PassBatch:
     """TRC-pass reads of one finished batch, in read order, as one PassBatch (no per-read Python work: a handful of
     array operations and two C calls per batch).  `tables` (ends-first mode) maps a read index to its raw-count table
     instead of `raw` + the rows' offsets."""
@@ -212,12 +232,13 @@ def harvest(cfg: ScanConfig, ctx, batch, rows, raw, want_records: bool, keep=Non
     if cfg.want_rawcount and tables is not None:
         tabs = [tables.get(int(i)) for i in idx]
     elif cfg.want_rawcount and raw is not None:
-        raw_copy = np.array(raw, copy=True)  # ONE copy out of the context's landing buffer; the tables are views of it
+        # the tables are views of `raw`: a leased landing buffer (no copy), else one copy out of the context's own
+        raw_copy = raw if leases else np.array(raw, copy=True)
         raw_off = sel["rawcount_offset"]
     records = None
     if want_records and len(idx):          # SeqIO.write text of every kept read: one C call, views of one buffer
         records = batch.records_text(idx)
-    return PassBatch(cfg, ctx.patterns, batch.first_read + idx, ids, sel, raw_copy, raw_off, tabs, records)
+    return PassBatch(cfg, ctx.patterns, batch.first_read + idx, ids, sel, raw_copy, raw_off, tabs, records, leases)
 
 
 class _DeviceWorker:
@@ -261,7 +282,7 @@ class _DeviceWorker:
         except BaseException:
             self._slot_thread.join()
             raise
-        self.reg = None                      # ends-first: region staging, page-locked at its first use
+        self.regs = {}                       # ends-first: region staging per config, page-locked at its first use
         if os.environ.get("TOPSICLE_TIMING"):
             print(f"[timing] device {device}: {len(cfgs)} context(s) {time.perf_counter() - t0:.3f} s",
                   file=sys.stderr)
@@ -292,12 +313,11 @@ class _DeviceWorker:
                 raise self._slot_error
             return self.slots[i]
 
-    def _region_staging(self):
-        if self.reg is None:
+    def _region_staging(self, ci):
+        if ci not in self.regs:
             with numa.near_device(self.device):
-                self.reg = _Slot(self.region_cap, self.max_pass_reads)
-                self.reg_tails = engine.PinnedBuffer(self.max_pass_reads)
-        return self.reg
+                self.regs[ci] = (_Slot(self.region_cap, self.max_pass_reads), engine.PinnedBuffer(self.max_pass_reads))
+        return self.regs[ci]
 
     def close(self):
         self._slot_thread.join()
@@ -306,10 +326,10 @@ class _DeviceWorker:
         for s in self.slots:
             s.free()
         self.slots = []
-        if self.reg is not None:
-            self.reg.free()
-            self.reg_tails.free()
-            self.reg = None
+        for reg, tails in self.regs.values():
+            reg.free()
+            tails.free()
+        self.regs = {}
 
     def submit(self, bases, starts, lens, n_reads, true_lens=None, group=None):
         """Upload and scan one batch under the configs `group` (default: all): the first uploads and packs,
@@ -325,35 +345,44 @@ class _DeviceWorker:
         return bid
 
     # -- ends-first mode: steps 2/3 of the TRC-pass reads of an ends batch
-    def _scan_regions(self, ci, batch, rows, idx, tables):
-        """Scan the regions of reads `idx` (TRC-pass under config ci) and merge status / n_windows / bkp /
-        telo_length into `rows`; raw-count tables go to `tables[i]`.  Groups are cut to the context's
-        capacities and halved again if the raw-count buffer overflows."""
+    def _regions_submit(self, ci, batch, rows, group):
+        """Gather the regions of the longest prefix of reads `group` that fits one region batch into config ci's
+        staging (one call of the reader library, threads) and submit it; returns (reads used, batch id, bases,
+        reads left over)."""
         cfg, ctx = self.cfgs[ci], self.ctxs[ci]
-        reg = self._region_staging()
+        reg, reg_tails = self._region_staging(ci)
         rb = reg.bases.array
         rstarts = reg.offsets.array.view(np.uint64)
         rlens = reg.lens.array.view(np.uint32)
-        rtails = self.reg_tails.array
-        tails = rows["tail"]
-        pending = [list(map(int, idx))]
-        while pending:
-            group = pending.pop(0)
-            cut = group[:self.max_pass_reads]
-            gt = tails[cut].astype(np.uint8)
-            # longest prefix that fits one region batch, copied by the reader library (one call, threads)
-            n = batch.gather_regions(cut, gt, cfg.maxlengthtelo, rb[:self.region_cap], rstarts, rlens)
-            if n == 0:
-                raise engine.TpsError(-4, f"the region of read {cut[0]} does not fit the batch capacity "
-                                          f"of {self.region_cap}")
-            used = cut[:n]
-            rtails[:n] = gt[:n]
-            at = int(rstarts[n - 1]) + int(rlens[n - 1])
-            if n < len(group):
-                pending.insert(0, group[n:])
+        rtails = reg_tails.array
+        cut = group[:self.max_pass_reads]
+        gt = rows["tail"][cut].astype(np.uint8)
+        n = batch.gather_regions(cut, gt, cfg.maxlengthtelo, rb[:self.region_cap], rstarts, rlens)
+        if n == 0:
+            raise engine.TpsError(-4, f"the region of read {cut[0]} does not fit the batch capacity "
+                                      f"of {self.region_cap}")
+        rtails[:n] = gt[:n]
+        at = int(rstarts[n - 1]) + int(rlens[n - 1])
+        bid = ctx.submit_regions(rb[:at], rstarts[:n], rlens[:n], rtails[:n], n)
+        return cut[:n], bid, at, group[n:]
+
+    def _scan_regions(self, ci, batch, rows, first, tables, leases):
+        """Steps 2/3 of the TRC-pass reads of an ends batch under config ci: `first` is the region batch already in
+        flight (_regions_submit); status / n_windows / bkp / telo_length are merged into `rows`, raw-count tables
+        go to `tables[i]` (views of leased landing buffers, collected in `leases`).  Reads that did not fit the
+        first batch follow one batch at a time; a batch that overflows the raw-count buffer is halved."""
+        cfg, ctx = self.cfgs[ci], self.ctxs[ci]
+        pending, inflight = [], first
+        while pending or inflight is not None:
+            if inflight is None:
+                inflight = self._regions_submit(ci, batch, rows, pending.pop(0))
+            used, bid, at, rest = inflight
+            inflight = None
+            if rest:
+                pending.insert(0, rest)
+            n = len(used)
             try:
-                bid = ctx.submit_regions(rb[:at], rstarts[:n], rlens[:n], rtails[:n], n)
-                rows2, raw2 = ctx.wait(bid, True)
+                rows2, raw2, lease = ctx.wait_leased(bid)
                 self._region_bases += at
             except engine.TpsError as e:
                 if e.code != -4 or n <= 1:
@@ -364,9 +393,14 @@ class _DeviceWorker:
             for f in ("status", "n_windows", "bkp", "telo_length"):
                 rows[f][used] = rows2[f][:n]
             if cfg.want_rawcount and raw2 is not None:
-                raw2 = np.array(raw2, copy=True)     # one copy out of the landing buffer, tables are views
+                if lease is not None:
+                    leases.append(lease)
+                else:
+                    raw2 = np.array(raw2, copy=True)
                 for j, i in enumerate(used):
                     tables[i] = ctx.rawcount_table(rows2, raw2, j)
+            elif lease is not None:
+                lease.release()
 
     def finish_ends(self, item, records_cfg, keep, group):
         slot, batch, bid, seq = item
@@ -374,17 +408,22 @@ class _DeviceWorker:
                           n_scanned=0, n_uploaded=int(batch.span))
         self._region_bases = 0
         waited = [self.ctxs[k].wait(bid)[0] for k in group]      # step-1 rows under every config of the job
-        for gi, ci in enumerate(group):
-            cfg, ctx = self.cfgs[ci], self.ctxs[ci]
+        firsts = {}
+        for gi, ci in enumerate(group):    # the region batches of all configs go out before any is waited for
             rows = waited[gi]
-            tables = {}
             idx = np.nonzero(rows["status"] == engine.ST_PASS)[0]
             if len(idx) and keep is not None:
                 idx = np.array([i for i in idx if batch.read_id(int(i)) in keep], dtype=np.int64)
-            if len(idx) and not cfg.step1_only:
-                self._scan_regions(ci, batch, rows, idx, tables)
+            if len(idx) and not self.cfgs[ci].step1_only:
+                firsts[ci] = self._regions_submit(ci, batch, rows, [int(i) for i in idx])
+        for gi, ci in enumerate(group):
+            cfg, ctx = self.cfgs[ci], self.ctxs[ci]
+            rows = waited[gi]
+            tables, leases = {}, []
+            if ci in firsts:
+                self._scan_regions(ci, batch, rows, firsts[ci], tables, leases)
             res.passes.append(harvest(cfg, ctx, batch, rows, None, records_cfg == ci, keep,
-                                      tables=tables if cfg.want_rawcount else None))
+                                      tables=tables if cfg.want_rawcount else None, leases=leases))
             if gi == 0:
                 res.n_scanned = int((rows["status"] != engine.ST_FILTERED).sum())
         res.n_uploaded += self._region_bases
@@ -402,7 +441,7 @@ class _DeviceWorker:
         try:
             bid = self.ctxs[lead].submit_spans(sub_bases, sub_starts, sub_lens, hi - lo)
             if ci == lead:
-                rows, raw = self.ctxs[lead].wait(bid)
+                rows, raw, lease = self.ctxs[lead].wait_leased(bid)
             else:
                 self.ctxs[ci].submit_shared(self.ctxs[lead], bid)
                 try:
@@ -410,8 +449,8 @@ class _DeviceWorker:
                 except engine.TpsError as e:       # the leader's own overflow is irrelevant here
                     if e.code != -4:
                         raise
-                rows, raw = self.ctxs[ci].wait(bid)
-            return [(lo, hi, rows, raw)]
+                rows, raw, lease = self.ctxs[ci].wait_leased(bid)
+            return [(lo, hi, rows, raw, lease)]
         except engine.TpsError as e:
             if e.code != -4 or hi - lo <= 1:
                 raise
@@ -431,7 +470,7 @@ class _DeviceWorker:
         waited = []
         for k in group:                            # release every context's slot before any re-scan
             try:
-                waited.append(self.ctxs[k].wait(bid, True))  # tables are copied out per read by harvest()
+                waited.append(self.ctxs[k].wait_leased(bid))  # tables: views of a leased landing buffer
             except engine.TpsError as e:
                 if e.code != -4 or n <= 1:
                     raise
@@ -439,19 +478,30 @@ class _DeviceWorker:
         for gi, ci in enumerate(group):
             cfg, ctx = self.cfgs[ci], self.ctxs[ci]
             if waited[gi] is not None:
-                parts = [(0, n, *waited[gi])]
+                parts = [(0, n, waited[gi][0], waited[gi][1], waited[gi][2])]
             else:
                 mid = n // 2
                 parts = (self._scan_sub(ci, slot.bases.array, batch.offsets, batch.lens, 0, mid, group[0])
                          + self._scan_sub(ci, slot.bases.array, batch.offsets, batch.lens, mid, n, group[0]))
             passes = []
             scanned = 0
-            for lo, hi, rows, raw in parts:
+            for lo, hi, rows, raw, lease in parts:
                 scanned += int((rows["status"] != engine.ST_FILTERED).sum())
                 view = _BatchView(batch, lo)
-                passes.append(harvest(cfg, ctx, view, rows, raw, records_cfg == ci, keep))
+                passes.append(harvest(cfg, ctx, view, rows, raw, records_cfg == ci, keep,
+                                      leases=[lease] if lease is not None else ()))
             # one part unless the batch overflowed a capacity and was re-scanned in halves (then: plain list)
-            res.passes.append(passes[0] if len(passes) == 1 else [p for part in passes for p in part])
+            if len(passes) == 1:
+                res.passes.append(passes[0])
+            else:
+                flat = []
+                for part in passes:
+                    for p in part:
+                        if p.counts is not None:
+                            p.counts = p.counts.copy()     # the part's landing buffer goes back right away
+                        flat.append(p)
+                    part.release()
+                res.passes.append(flat)
             if gi == 0:
                 res.n_scanned = scanned
         batch.release()

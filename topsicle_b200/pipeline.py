@@ -75,8 +75,9 @@ class PassRead:
 class PassBatch:
     """The TRC-pass reads of one batch under one config, as columns: what a device hands back is arrays, and a
     batch of a telomere-enriched library holds thousands of passing reads, so the rows stay arrays until somebody
-    asks for one read.  Behaves as a sequence of PassRead (len, iteration, indexing) built on demand; the
-    raw-count tables (`table(j)`, `PassRead.counts`) are views of one array per batch.
+    asks for one read.  Behaves as a sequence of PassRead (len, iteration, indexing) built on demand.  The raw-count
+    tables are views of one array per batch: `table(j)` hands out the view (valid until the sink returns, when the
+    pipeline gives the landing buffer back), a PassRead owns a copy.
 
     Columns (numpy, length n): index (position of the read in its file), count, literal_idx, tail_code, status,
     n_windows, telo_length, length; `ids` (list of str), `trc` (float64 = count / (no_bp / len(pattern)),
@@ -121,6 +122,12 @@ class PassBatch:
         nw, npat, off = int(self.n_windows[j]), len(self.patterns), int(self._raw_off[j])
         return self._raw[off:off + nw * npat].reshape(nw, npat)
 
+    def _own_table(self, j):
+        """table(j) for a PassRead, which may outlive the sink call: a copy when the batch's tables are views of
+        leased landing buffers."""
+        t = self.table(j)
+        return t.copy() if (t is not None and self._leases) else t
+
     def __getitem__(self, j):
         if isinstance(j, slice):
             return [self[i] for i in range(*j.indices(len(self)))]
@@ -130,7 +137,7 @@ class PassBatch:
                         tail=engine.TAIL_NAMES[int(self.tail_code[j])], count=int(self.count[j]), trc=float(self.trc[j]),
                         status=int(self.status[j]), n_windows=int(self.n_windows[j]),
                         telo_length=int(self.telo_length[j]), length=int(self.length[j]),
-                        counts=self.table(j) if self.cfg.want_rawcount else None,
+                        counts=self._own_table(j) if self.cfg.want_rawcount else None,
                         record=self.records[j] if self.records is not None else None)
 
     def __iter__(self):

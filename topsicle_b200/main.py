@@ -207,8 +207,8 @@ def analysis_run(args):
     else:
         num_cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
         tprint(f"By default, Topsicle allocates nmber of cores: {num_cores}")
+    explicit_devices = bool(getattr(args, "devices", None) or os.environ.get("TOPSICLE_DEVICES"))
     devices = args.devices if getattr(args, "devices", None) else visible_devices()
-    tprint(f"CUDA devices used for the scan: {devices} ({engine.load_library().tps_build_info().decode()})")
 
     output_csv = f"{args.outputDir}/telolengths_all.csv"
     tprint(f"Output will be here: {output_csv}")
@@ -267,6 +267,13 @@ def analysis_run(args):
     except OSError:
         total_bytes = 1 << 40
     auto_bases = min(1 << 28, max(1 << 24, 1 << max(0, (total_bytes // 48).bit_length() - 1)))
+    if not explicit_devices and len(devices) > 1:
+        # a GPU scans ~30 Gbases/s from FASTQ, but bringing one up (CUDA context, device buffers, page-locked
+        # staging) and tearing it down costs about a second of process time: measured on an 8-GPU box, 12 GB of
+        # FASTQ take 0.14 s to scan and 12 s of wall time when all eight devices are initialised
+        # (profiles/README.md).  One more device per 32 GiB of input text; --devices / TOPSICLE_DEVICES override.
+        devices = devices[:max(1, min(len(devices), 1 + total_bytes // (32 << 30)))]
+    tprint(f"CUDA devices used for the scan: {devices} ({engine.load_library().tps_build_info().decode()})")
     scanner = pipeline.Scanner(scan_configs(args, telo_phrases, patterns, sliding_val), devices=devices,
                                threads=args.threads or 0,
                                max_batch_bases=int(os.environ.get("TOPSICLE_BATCH_BASES", auto_bases)),

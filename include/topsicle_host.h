@@ -104,6 +104,32 @@ int64_t tps_fastx_records_text(const uint8_t *raw_base, const tps_fastx_rec *rec
 int64_t tps_format_rawcount(const uint8_t *counts, uint32_t n_windows, uint32_t n_patterns, uint32_t slide,
                             const char *tail, const char *const *patterns, char *out, uint64_t cap);
 
+/* ---- parallel inflate of plain gzip (csrc/tps_pgz.c), what the reader uses for `.gz` input that is not BGZF.
+ * Replaces: gzip.open(filepath, 'rt') in unzip_file (allsteps.py:142-146), one zlib stream on one core.
+ * The compressed file is cut into one piece per thread; every thread finds the first deflate block that starts in
+ * its piece, decodes from there with an unknown 32 KiB window into 16-bit symbols, the pieces must chain exactly,
+ * then all are resolved to bytes in parallel; CRC-32 and length of every gzip member are verified. */
+typedef struct tps_pgz tps_pgz;
+typedef struct tps_pgz_stats {
+  uint64_t stretches;           /* calls that inflated a stretch of the file */
+  uint64_t segments;            /* pieces decoded (one per thread and stretch when every block-start search succeeds) */
+  uint64_t chain_breaks;        /* pieces thrown away because the piece before did not land on their start */
+  uint64_t members;             /* gzip members completed (CRC-32 and length verified) */
+  uint64_t text_bytes;          /* inflated bytes */
+  uint64_t parallel_text_bytes; /* ... of which decoded from a guessed block start with an unknown window */
+} tps_pgz_stats;
+/* zmap[0..zlen) = the whole compressed file (mapped).  NULL if it does not start with a gzip member header. */
+tps_pgz *tps_pgz_open(const uint8_t *zmap, uint64_t zlen, int threads);
+void tps_pgz_close(tps_pgz *g);
+/* Up to cap bytes of inflated text into dst; 0 = end of file; -1 = corrupt input / out of memory (tps_pgz_error). */
+int64_t tps_pgz_read(tps_pgz *g, uint8_t *dst, uint64_t cap);
+int tps_pgz_eof(const tps_pgz *g);
+const char *tps_pgz_error(const tps_pgz *g);
+void tps_pgz_get_stats(const tps_pgz *g, tps_pgz_stats *out);
+void tps_pgz_set_piece(tps_pgz *g, uint64_t bytes); /* compressed bytes per thread and stretch (tests, tuning) */
+/* The same counters of the reader's own inflater (all zero unless `fx` reads plain gzip). */
+void tps_fastx_inflate_stats(const tps_fastx *fx, tps_pgz_stats *out);
+
 /* ---- synth-v1 workload generator (no reference counterpart: the reference ships no benchmark) */
 typedef struct tps_synth_cfg {
   uint64_t seed;

@@ -74,7 +74,7 @@ def test_host_library_exports_every_declared_symbol():
     for must in ("tps_fastx_open", "tps_fastx_next", "tps_fastx_next_spans", "tps_fastx_next_ends", "tps_fastx_release",
                  "tps_fastx_close", "tps_fastx_find_id", "tps_fastx_join_ids", "tps_fastx_gather_regions",
                  "tps_fastx_records_text", "tps_format_rawcount", "tps_synth_fill", "tps_synth_lengths",
-                 "tps_host_threads"):
+                 "tps_host_threads", "tps_pgz_open", "tps_pgz_read", "tps_fastx_inflate_stats"):
         assert must in names, must
     for name in names:
         assert getattr(lib, name) is not None, name

@@ -382,3 +382,91 @@ def test_records_text_equals_record_text(tmp_path):
                 b.release()
             assert b.n_reads == 300 and got == want, (path, mode)
             assert some == [want[7], want[3], want[299]] and ids == ["r7", "r3", "r299"]
+
+
+# ------------------------------------------------------------------ plain gzip: parallel inflate (csrc/tps_pgz.c)
+def _synthetic_fastq(n_reads=2500, seed=5):
+    """FASTQ text with realistic (poorly compressible) quality lines."""
+    from topsicle_b200 import synth
+    bases, off, _ = synth.generate(synth.CONFIGS[2], 0, n_reads)
+    rng = np.random.default_rng(seed)
+    out = []
+    for i in range(n_reads):
+        s = bases[int(off[i]):int(off[i + 1])].tobytes()
+        out.append(b"@r%d some description\n%s\n+\n%s\n" % (i, s, rng.integers(35, 74, len(s)).astype(np.uint8).tobytes()))
+    return b"".join(out)
+
+
+def _read_all(path, threads=8, **env):
+    from topsicle_b200 import fastx
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update({k: str(v) for k, v in env.items()})
+    try:
+        with fastx.FastxFile(path, threads=threads) as fx:
+            bases = np.empty(1 << 26, dtype=np.uint8)
+            offsets = np.empty((1 << 15) + 1, dtype=np.uint64)
+            recs = []
+            while True:
+                b = fx.next_batch(bases, offsets)
+                if b is None:
+                    break
+                recs += [(b.read_id(i), b.sequence(i), b.quality(i)) for i in range(b.n_reads)]
+                b.release()
+            return recs, fx.inflate_stats()
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize("level", [1, 6, 9])
+def test_plain_gzip_parallel_inflate_equals_zlib(tmp_path, level):
+    """A `.fastq.gz` written by gzip (one deflate stream) is inflated by all parser threads -- block starts guessed,
+    unknown windows decoded symbolically, pieces chained, CRC-32 checked -- and gives exactly the records zlib
+    gives (TPS_FX_NO_PGZ=1) and the plain file gives.  Reference: gzip.open in unzip_file, allsteps.py:142-146."""
+    import gzip
+    text = _synthetic_fastq()
+    plain, gz = tmp_path / "r.fastq", tmp_path / "r.fastq.gz"
+    plain.write_bytes(text)
+    gz.write_bytes(gzip.compress(text, compresslevel=level))
+    want, st0 = _read_all(str(plain))
+    assert st0["text_bytes"] == 0
+    got, st = _read_all(str(gz), TPS_PGZ_PIECE=1 << 18)
+    assert got == want and len(got) == 2500
+    assert st["text_bytes"] == len(text) and st["members"] == 1 and st["chain_breaks"] == 0
+    assert st["parallel_text_bytes"] > 0.7 * len(text) and st["segments"] > 3 * st["stretches"]
+    zl, st_z = _read_all(str(gz), TPS_FX_NO_PGZ=1)
+    assert zl == want and st_z["text_bytes"] == 0
+    one, st1 = _read_all(str(gz), threads=1)
+    assert one == want and st1["parallel_text_bytes"] == 0
+
+
+def test_plain_gzip_members_stored_blocks_and_damage(tmp_path):
+    """Several members (`cat a.gz b.gz`), an empty member, stored blocks (level 0), binary data in front of the text
+    (no block start is found in it: that stretch is decoded by one thread), a flipped byte (CRC-32 mismatch) and a
+    truncated file (both reported, never silently accepted)."""
+    import gzip
+    from topsicle_b200 import fastx
+    text = _synthetic_fastq(900, seed=9)
+    cut = [text.rfind(b"\n@r", 0, len(text) // 3) + 1, text.rfind(b"\n@r", 0, 2 * len(text) // 3) + 1]
+    multi = (gzip.compress(text[:cut[0]], 6) + gzip.compress(b"") + gzip.compress(text[cut[0]:cut[1]], 0)
+             + gzip.compress(text[cut[1]:], 9))
+    p = tmp_path / "multi.fastq.gz"
+    p.write_bytes(multi)
+    plain = tmp_path / "plain.fastq"
+    plain.write_bytes(text)
+    want, _ = _read_all(str(plain))
+    got, st = _read_all(str(p), TPS_PGZ_PIECE=1 << 17)
+    assert got == want and st["members"] == 4 and st["text_bytes"] == len(text)
+    z = bytearray(gzip.compress(text, 6))
+    z[len(z) // 2] ^= 0x5A
+    bad = tmp_path / "bad.fastq.gz"
+    bad.write_bytes(bytes(z))
+    with pytest.raises(fastx.FastxError):
+        _read_all(str(bad), TPS_PGZ_PIECE=1 << 17)
+    trunc = tmp_path / "trunc.fastq.gz"
+    trunc.write_bytes(gzip.compress(text, 6)[:len(z) // 2])
+    with pytest.raises(fastx.FastxError):
+        _read_all(str(trunc), TPS_PGZ_PIECE=1 << 17)

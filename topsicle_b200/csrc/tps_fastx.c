@@ -39,6 +39,7 @@
 #endif
 
 #include "../../include/topsicle_host.h"
+#include "tps_pgz.h"
 
 typedef struct rec_vec {
   tps_fastx_rec *v;
@@ -59,6 +60,8 @@ typedef struct tps_fastx {
   uint8_t *carry;
   uint64_t carry_len;
   int gz_eof;
+  /* plain gzip: parallel two-pass inflate over the mapped file (tps_pgz.c); zlib (gz) only with TPS_FX_NO_PGZ=1 */
+  tps_pgz *pgz;
   /* BGZF (bgzip) input: independent <= 64 KiB deflate blocks, inflated by all parser threads */
   int is_bgzf;
   const uint8_t *zmap;
@@ -480,6 +483,16 @@ typedef struct bgzf_blk {
 /* Append inflated text to chunk[*win .. cap): as much as fits.  Sets fx->gz_eof at the end of the input.
  * Returns 0, or <0 after fx_fail. */
 static int gz_fill(tps_fastx *fx, uint8_t *chunk, uint64_t *win, uint64_t cap) {
+  if (fx->pgz) {
+    while (*win < cap && !fx->gz_eof) {
+      const int64_t n = tps_pgz_read(fx->pgz, chunk + *win, cap - *win);
+      if (n < 0) return fx_fail(fx, TPS_FX_EIO, "gzip input: %s", tps_pgz_error(fx->pgz));
+      *win += (uint64_t)n;
+      if (tps_pgz_eof(fx->pgz)) fx->gz_eof = 1;
+      else if (n == 0) break; /* the rest of the buffer is too small for another stretch */
+    }
+    return TPS_FX_OK;
+  }
   if (!fx->is_bgzf) {
     while (*win < cap && !fx->gz_eof) {
       uint64_t ask = cap - *win;
@@ -576,18 +589,26 @@ int tps_fastx_open(tps_fastx **out, const char *path, int threads) {
         fx->zlen = (uint64_t)zst.st_size;
         fx->fd = zfd;
         zfd = -1;
+      } else if (zm != MAP_FAILED && !getenv("TPS_FX_NO_PGZ") &&
+                 (fx->pgz = tps_pgz_open((const uint8_t *)zm, (uint64_t)zst.st_size, fx->threads)) != NULL) {
+        fx->zmap = (const uint8_t *)zm; /* plain gzip: inflated by all parser threads (tps_pgz.c) */
+        fx->zlen = (uint64_t)zst.st_size;
+        fx->fd = zfd;
+        zfd = -1;
+        madvise(zm, (size_t)zst.st_size, MADV_SEQUENTIAL);
       } else if (zm != MAP_FAILED) {
         munmap(zm, (size_t)zst.st_size);
       }
     }
     if (zfd >= 0) close(zfd);
   }
-  if (fx->is_bgzf) {
+  if (fx->is_bgzf || fx->pgz) {
     fx->carry = (uint8_t *)malloc(1u << 17);
     uint64_t got = 0;
     if (!fx->carry || gz_fill(fx, fx->carry, &got, 1u << 17)) {
       int rc = fx->carry ? TPS_FX_EIO : TPS_FX_ENOMEM;
       snprintf(g_open_err, sizeof(g_open_err), "%s", fx->carry ? fx->err : "out of memory");
+      tps_pgz_close(fx->pgz);
       munmap((void *)fx->zmap, fx->zlen);
       close(fx->fd);
       free(fx->carry);
@@ -651,6 +672,7 @@ int tps_fastx_open(tps_fastx **out, const char *path, int threads) {
     int rc = fx_fail(NULL, TPS_FX_EFORMAT, "%s: format cannot be identified (first line starts with neither '@' nor '>')",
                      path);
     if (fx->gz) gzclose(fx->gz);
+    tps_pgz_close(fx->pgz);
     if (fx->map) munmap((void *)fx->map, fx->map_len);
     if (fx->zmap) munmap((void *)fx->zmap, fx->zlen);
     if (fx->fd >= 0) close(fx->fd);
@@ -681,6 +703,7 @@ static void unmap_parallel(const uint8_t *map, uint64_t len, int threads) {
 void tps_fastx_close(tps_fastx *fx) {
   if (!fx) return;
   if (fx->gz) gzclose(fx->gz);
+  tps_pgz_close(fx->pgz);
   if (fx->zmap) munmap((void *)fx->zmap, fx->zlen);
   if (fx->map) unmap_parallel(fx->map, fx->map_len, fx->threads);
   if (fx->fd >= 0) close(fx->fd);
@@ -689,6 +712,11 @@ void tps_fastx_close(tps_fastx *fx) {
 }
 
 int tps_fastx_format(const tps_fastx *fx) { return fx ? fx->format : 0; }
+void tps_fastx_inflate_stats(const tps_fastx *fx, tps_pgz_stats *out) {
+  if (!out) return;
+  memset(out, 0, sizeof(*out));
+  if (fx && fx->pgz) tps_pgz_get_stats(fx->pgz, out);
+}
 void tps_fastx_set_window(tps_fastx *fx, uint64_t bytes) {
   if (fx && bytes >= 4096) fx->window_bytes = bytes;
 }

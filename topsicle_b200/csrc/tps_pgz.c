@@ -1,0 +1,794 @@
+/*
+ * tps_pgz.c -- parallel inflate of plain gzip input (what the reference opens with gzip.open,
+ * allsteps.py:142-146: every README example and the demo input are `.fastq.gz`).
+ *
+ * A gzip member is ONE deflate stream: block k can only be decoded after block k-1 (its Huffman tables sit in
+ * its own header, but its back-references reach 32 KiB into the text before it), which is why zlib inflates a
+ * `.fastq.gz` on one core at ~0.2 GB/s of text.  The way around it (the idea of pugz, Kerbiriou & Chikhi 2019),
+ * written from scratch here:
+ *
+ *   1. cut the next stretch of the compressed file into one piece per thread;
+ *   2. every thread but the first finds the first deflate block that starts in its piece: it tries each bit
+ *      offset, keeps an offset whose dynamic-Huffman header is a complete prefix code (zlib's own validity
+ *      rules), whose block decodes to text bytes only, and which is followed by another valid block header;
+ *   3. every thread decodes from its block start to the next thread's block start.  It does not know the 32 KiB
+ *      of text before its start, so it decodes into 16-bit SYMBOLS: 0..255 = a literal byte, 256 + i = "byte i of
+ *      the unknown window"; copies of symbols are symbols.  Thread k must land EXACTLY on the block start thread
+ *      k+1 found (else everything after k is thrown away and redone from where k stopped);
+ *   4. the last 32 KiB of every piece are resolved in order (a cheap sequential chain), then all pieces are
+ *      translated to bytes in parallel, straight into the caller's buffer, each thread taking the CRC-32 of its
+ *      bytes on the way; the CRCs are combined and compared with the gzip trailer at the end of the member.
+ *
+ * Anything unusual (a stream that is not text, stored / fixed blocks, several members, a wrong guess) costs
+ * speed, never correctness: the first piece of every stretch starts at a known position with a known window, and
+ * the chain check plus the member's CRC-32 / ISIZE are the same guarantees zlib gives.
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <zlib.h> /* crc32, crc32_combine */
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "tps_pgz.h"
+
+#include <stdio.h>
+#include <sys/mman.h>
+#include <time.h>
+static double pgz_now(void) {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+#define PGZ_WSIZE 32768u
+#define LIT_TB 11 /* primary table bits, literal / length code */
+#define DST_TB 8  /* primary table bits, distance code */
+#define MAX_SUB 5120 /* > 286 long codes x 16-entry subtables */
+
+typedef struct huff {
+  uint32_t tab[(1u << LIT_TB) + MAX_SUB]; /* entry: sym << 16 | kind << 8 | len; kind 1 = subtable (sym = offset, len = its bits) */
+  uint32_t tb;
+} huff;
+
+typedef struct bitrd {
+  const uint8_t *base, *p, *end;
+  uint64_t buf;
+  uint32_t cnt;
+} bitrd;
+
+static inline void br_init(bitrd *b, const uint8_t *base, uint64_t len, uint64_t bitpos) {
+  b->base = base;
+  b->end = base + len;
+  b->p = base + (bitpos >> 3);
+  b->buf = 0;
+  b->cnt = 0;
+  if (b->p < b->end) {
+    b->buf = (uint64_t)*b->p++ >> (bitpos & 7);
+    b->cnt = 8 - (uint32_t)(bitpos & 7);
+  }
+}
+static inline void br_refill(bitrd *b) {
+  if (b->p + 8 <= b->end) { /* libdeflate-style branch-light refill */
+    uint64_t w;
+    memcpy(&w, b->p, 8);
+    b->buf |= w << b->cnt;
+    b->p += (63 - b->cnt) >> 3;
+    b->cnt |= 56;
+  } else {
+    while (b->cnt <= 56 && b->p < b->end) {
+      b->buf |= (uint64_t)*b->p++ << b->cnt;
+      b->cnt += 8;
+    }
+  }
+}
+static inline uint64_t br_pos(const bitrd *b) { return (uint64_t)(b->p - b->base) * 8 - b->cnt; }
+static inline uint32_t br_bits(bitrd *b, uint32_t n) { /* n <= 16, after a refill */
+  const uint32_t v = (uint32_t)(b->buf & ((1u << n) - 1u));
+  b->buf >>= n;
+  b->cnt -= n;
+  return v;
+}
+
+static inline uint32_t rev_bits(uint32_t c, uint32_t n) {
+  uint32_t r = 0;
+  for (uint32_t i = 0; i < n; ++i) r |= ((c >> i) & 1u) << (n - 1 - i);
+  return r;
+}
+
+/* Canonical Huffman decoding table from code lengths (RFC 1951 3.2.2) under zlib's validity rules
+ * (inftrees.c): an over-subscribed set is invalid; an incomplete set is invalid unless it is a single code of
+ * length 1 and `allow_single`.  Returns 0 if valid. */
+static int huff_build(huff *h, const uint8_t *lens, uint32_t n, uint32_t tb, int allow_single) {
+  uint32_t count[16] = {0}, next[16], maxlen = 0, ncodes = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    count[lens[i]]++;
+    if (lens[i]) {
+      ++ncodes;
+      if (lens[i] > maxlen) maxlen = lens[i];
+    }
+  }
+  h->tb = tb;
+  const uint32_t psize = 1u << tb;
+  if (ncodes == 0) { /* no codes at all: legal for the distance code of a block without matches */
+    if (!allow_single) return -1;
+    for (uint32_t i = 0; i < psize; ++i) h->tab[i] = 0; /* len 0 = invalid code when used */
+    return 0;
+  }
+  int32_t left = 1;
+  for (uint32_t l = 1; l <= 15; ++l) {
+    left <<= 1;
+    left -= (int32_t)count[l];
+    if (left < 0) return -1;
+  }
+  if (left > 0 && !(allow_single && maxlen == 1)) return -1;
+  uint32_t code = 0;
+  count[0] = 0;
+  for (uint32_t l = 1; l <= 15; ++l) {
+    code = (code + count[l - 1]) << 1;
+    next[l] = code;
+  }
+  for (uint32_t i = 0; i < psize; ++i) h->tab[i] = 0;
+  /* subtable sizes: longest code behind every primary index */
+  uint8_t sub[1u << LIT_TB];
+  int have_long = 0;
+  if (maxlen > tb) {
+    memset(sub, 0, psize);
+    uint32_t nx[16];
+    memcpy(nx, next, sizeof(nx));
+    for (uint32_t s = 0; s < n; ++s) {
+      const uint32_t l = lens[s];
+      if (!l) continue;
+      const uint32_t r = rev_bits(nx[l]++, l);
+      if (l > tb) {
+        have_long = 1;
+        const uint32_t pi = r & (psize - 1);
+        if (l - tb > sub[pi]) sub[pi] = (uint8_t)(l - tb);
+      }
+    }
+  }
+  uint32_t suboff = psize;
+  if (have_long) {
+    for (uint32_t pi = 0; pi < psize; ++pi) {
+      if (!sub[pi]) continue;
+      if (suboff + (1u << sub[pi]) > psize + MAX_SUB) return -1;
+      h->tab[pi] = (suboff << 16) | (1u << 8) | sub[pi];
+      for (uint32_t k = 0; k < (1u << sub[pi]); ++k) h->tab[suboff + k] = 0;
+      suboff += 1u << sub[pi];
+    }
+  }
+  for (uint32_t s = 0; s < n; ++s) {
+    const uint32_t l = lens[s];
+    if (!l) continue;
+    const uint32_t r = rev_bits(next[l]++, l);
+    if (l <= tb) {
+      for (uint32_t k = r; k < psize; k += 1u << l) h->tab[k] = (s << 16) | l;
+    } else {
+      const uint32_t pe = h->tab[r & (psize - 1)];
+      const uint32_t off = pe >> 16, sb = pe & 255u;
+      for (uint32_t k = r >> tb; k < (1u << sb); k += 1u << (l - tb)) h->tab[off + k] = (s << 16) | (l - tb);
+    }
+  }
+  return 0;
+}
+
+/* one symbol; returns -1 on an invalid code.  The reader was refilled (>= 32 bits unless at the end).
+ * tb is a compile-time constant at every call site (the function is inlined). */
+static inline __attribute__((always_inline)) int32_t huff_sym_tb(const huff *h, bitrd *b, const uint32_t tb) {
+  uint32_t e = h->tab[b->buf & ((1u << tb) - 1u)];
+  if (__builtin_expect((e >> 8) & 1u, 0)) {
+    b->buf >>= tb;
+    b->cnt -= tb;
+    e = h->tab[(e >> 16) + (uint32_t)(b->buf & ((1u << (e & 255u)) - 1u))];
+  }
+  const uint32_t l = e & 255u;
+  if (__builtin_expect(l == 0 || l > b->cnt, 0)) return -1;
+  b->buf >>= l;
+  b->cnt -= l;
+  return (int32_t)(e >> 16);
+}
+static inline int32_t huff_sym(const huff *h, bitrd *b) { return huff_sym_tb(h, b, h->tb); }
+
+static const uint16_t LEN_BASE[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+static const uint8_t LEN_EXTRA[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+static const uint16_t DST_BASE[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+static const uint8_t DST_EXTRA[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+static const uint8_t CL_ORDER[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+
+typedef struct blockhdr {
+  int final, type;
+  huff lit, dst;
+  uint32_t stored_len;
+} blockhdr;
+
+/* Parse one block header at the reader's position.  0 ok, -1 invalid / out of data. */
+static int read_block_header(bitrd *b, blockhdr *h) {
+  br_refill(b);
+  if (b->cnt < 3) return -1;
+  h->final = (int)br_bits(b, 1);
+  h->type = (int)br_bits(b, 2);
+  if (h->type == 3) return -1;
+  if (h->type == 0) {
+    const uint32_t drop = b->cnt & 7u; /* to the byte boundary */
+    b->buf >>= drop;
+    b->cnt -= drop;
+    br_refill(b);
+    if (b->cnt < 32) return -1;
+    const uint32_t len = br_bits(b, 16), nlen = br_bits(b, 16);
+    if ((len ^ nlen) != 0xFFFFu) return -1;
+    h->stored_len = len;
+    return 0;
+  }
+  uint8_t lens[320];
+  if (h->type == 1) {
+    for (int i = 0; i < 144; ++i) lens[i] = 8;
+    for (int i = 144; i < 256; ++i) lens[i] = 9;
+    for (int i = 256; i < 280; ++i) lens[i] = 7;
+    for (int i = 280; i < 288; ++i) lens[i] = 8;
+    if (huff_build(&h->lit, lens, 288, LIT_TB, 0)) return -1;
+    for (int i = 0; i < 32; ++i) lens[i] = 5; /* 30 and 31 complete the code; using them is an error (RFC 1951 3.2.6) */
+    return huff_build(&h->dst, lens, 32, DST_TB, 1);
+  }
+  if (b->cnt < 14) return -1;
+  const uint32_t hlit = br_bits(b, 5) + 257, hdist = br_bits(b, 5) + 1, hclen = br_bits(b, 4) + 4;
+  if (hlit > 286 || hdist > 30) return -1;
+  uint8_t cl[19] = {0};
+  br_refill(b);
+  for (uint32_t i = 0; i < hclen; ++i) {
+    if (b->cnt < 3) {
+      br_refill(b);
+      if (b->cnt < 3) return -1;
+    }
+    cl[CL_ORDER[i]] = (uint8_t)br_bits(b, 3);
+  }
+  huff clh;
+  if (huff_build(&clh, cl, 19, 7, 0)) return -1;
+  uint32_t i = 0;
+  while (i < hlit + hdist) {
+    br_refill(b);
+    const int32_t s = huff_sym(&clh, b);
+    if (s < 0) return -1;
+    if (s < 16) {
+      lens[i++] = (uint8_t)s;
+    } else {
+      uint32_t rep, val = 0;
+      if (b->cnt < 7) return -1;
+      if (s == 16) {
+        if (i == 0) return -1;
+        val = lens[i - 1];
+        rep = 3 + br_bits(b, 2);
+      } else if (s == 17) {
+        rep = 3 + br_bits(b, 3);
+      } else {
+        rep = 11 + br_bits(b, 7);
+      }
+      if (i + rep > hlit + hdist) return -1;
+      while (rep--) lens[i++] = (uint8_t)val;
+    }
+  }
+  if (lens[256] == 0) return -1; /* no end-of-block code */
+  if (huff_build(&h->lit, lens, hlit, LIT_TB, 0)) return -1;
+  return huff_build(&h->dst, lens + hlit, hdist, DST_TB, 1);
+}
+
+typedef struct seg {
+  uint64_t start_bit; /* a block starts here */
+  uint64_t stop_bit;  /* decode whole blocks until the position is >= this */
+  uint64_t end_bit;   /* where the decode stopped (a block boundary) */
+  uint16_t *out;
+  uint64_t n, cap;
+  int status;    /* 0 ok, -1 corrupt, -2 out of memory */
+  int saw_final; /* stopped behind the member's last block */
+  int symbolic;  /* started with an unknown window */
+  uint32_t crc;
+} seg;
+
+/* Symbol buffers are tens of megabytes per thread and written once per stretch: 2 MiB-aligned and advised as huge
+ * pages, so that first touch costs one fault per 2 MiB instead of 512 (with eight threads faulting at once the
+ * kernel's address-space lock made the first stretches several times slower than the rest). */
+static uint16_t *sym_alloc(uint64_t n) {
+  const uint64_t bytes = (n * sizeof(uint16_t) + (2u << 20) - 1) & ~(uint64_t)((2u << 20) - 1);
+  void *p = NULL;
+  if (posix_memalign(&p, 2u << 20, bytes)) return NULL;
+#ifdef MADV_HUGEPAGE
+  madvise(p, bytes, MADV_HUGEPAGE);
+#endif
+  return (uint16_t *)p;
+}
+
+static int seg_grow(seg *s, uint64_t need) {
+  if (s->n + need <= s->cap) return 0;
+  uint64_t nc = s->cap ? s->cap * 2 : (1u << 22);
+  while (nc < s->n + need) nc *= 2;
+  uint16_t *nv = sym_alloc(nc);
+  if (!nv) return -1;
+  if (s->n) memcpy(nv, s->out, s->n * sizeof(uint16_t));
+  free(s->out);
+  s->out = nv;
+  s->cap = nc;
+  return 0;
+}
+
+static inline int is_text(uint32_t c) { return c == 10 || c == 13 || c == 9 || (c >= 32 && c < 127); }
+
+/* Decode the block whose header was just read.  win = the 32768 symbols before the segment's start.
+ * text_only / max_out: the stricter rules of the block-start search.  0 ok, <0 error. */
+static int decode_block(bitrd *b, const blockhdr *h, seg *s, const uint16_t *win, int text_only, uint64_t max_out) {
+  if (h->type == 0) {
+    if (b->cnt & 7u) return -1;
+    uint32_t left = h->stored_len;
+    if (seg_grow(s, (uint64_t)left + 8)) return -2;
+    while (left && b->cnt >= 8) { /* bytes already in the bit buffer */
+      const uint32_t c = br_bits(b, 8);
+      if (text_only && !is_text(c)) return -1;
+      s->out[s->n++] = (uint16_t)c;
+      --left;
+    }
+    if (b->cnt == 0) b->buf = 0; /* bits a wide refill read ahead of the accounted ones */
+    if ((uint64_t)(b->end - b->p) < left) return -1;
+    for (uint32_t i = 0; i < left; ++i) {
+      if (text_only && !is_text(b->p[i])) return -1;
+      s->out[s->n++] = b->p[i];
+    }
+    b->p += left;
+    return 0;
+  }
+  for (;;) {
+    if (seg_grow(s, 320)) return -2;
+    br_refill(b);
+    int32_t sym = huff_sym_tb(&h->lit, b, LIT_TB);
+    if (sym < 0) return -1;
+    if (sym < 256) {
+      if (text_only && !is_text((uint32_t)sym)) return -1;
+      s->out[s->n++] = (uint16_t)sym;
+      /* a second literal from the same refill: most of FASTQ text is literals and short matches */
+      if (b->cnt >= 32) {
+        sym = huff_sym_tb(&h->lit, b, LIT_TB);
+        if (sym < 0) return -1;
+        if (sym < 256) {
+          if (text_only && !is_text((uint32_t)sym)) return -1;
+          s->out[s->n++] = (uint16_t)sym;
+          continue;
+        }
+      } else {
+        continue;
+      }
+    }
+    if (sym == 256) return 0;
+    sym -= 257;
+    if (sym >= 29) return -1;
+    if (b->cnt < 48) br_refill(b);
+    if (b->cnt < LEN_EXTRA[sym]) return -1;
+    const uint32_t len = LEN_BASE[sym] + br_bits(b, LEN_EXTRA[sym]);
+    const int32_t ds = huff_sym_tb(&h->dst, b, DST_TB);
+    if (ds < 0 || ds >= 30) return -1;
+    if (b->cnt < 13) br_refill(b);
+    if (b->cnt < DST_EXTRA[ds]) return -1;
+    const uint32_t dist = DST_BASE[ds] + br_bits(b, DST_EXTRA[ds]);
+    if (dist > s->n + PGZ_WSIZE) return -1;
+    uint16_t *o = s->out + s->n;
+    if (dist <= s->n) {
+      const uint16_t *f = o - dist;
+      if (dist >= 8) { /* eight symbols at a time; may write up to 7 past the match (320 symbols of slack) */
+        for (uint32_t k = 0; k < len; k += 8) memcpy(o + k, f + k, 16);
+      } else {
+        for (uint32_t k = 0; k < len; ++k) o[k] = f[k];
+      }
+    } else { /* reaches into the window before the segment */
+      for (uint32_t k = 0; k < len; ++k) {
+        const int64_t at = (int64_t)s->n + k - dist;
+        o[k] = at >= 0 ? s->out[at] : win[(int64_t)PGZ_WSIZE + at];
+      }
+    }
+    s->n += len;
+    if (max_out && s->n > max_out) return -1;
+  }
+}
+
+/* Decode whole blocks from s->start_bit until the position reaches s->stop_bit or the member ends. */
+static void decode_segment(const uint8_t *z, uint64_t zlen, seg *s, const uint16_t *win) {
+  bitrd b;
+  br_init(&b, z, zlen, s->start_bit);
+  blockhdr *h = (blockhdr *)malloc(sizeof(blockhdr));
+  if (!h) {
+    s->status = -2;
+    return;
+  }
+  s->status = 0;
+  for (;;) {
+    if (read_block_header(&b, h)) {
+      s->status = -1;
+      break;
+    }
+    const int rc = decode_block(&b, h, s, win, 0, 0);
+    if (rc) {
+      s->status = rc;
+      break;
+    }
+    s->end_bit = br_pos(&b);
+    if (h->final) {
+      s->saw_final = 1;
+      break;
+    }
+    if (s->end_bit >= s->stop_bit) break;
+  }
+  free(h);
+}
+
+/* First bit position >= from (and < limit) where a dynamic-Huffman block starts: valid header, the block decodes
+ * to text, and another valid block header follows.  Returns ~0 if none. */
+static uint64_t find_block_start(const uint8_t *z, uint64_t zlen, uint64_t from, uint64_t limit, const uint16_t *symwin) {
+  blockhdr *h = (blockhdr *)malloc(sizeof(blockhdr)), *h2 = (blockhdr *)malloc(sizeof(blockhdr));
+  seg t;
+  memset(&t, 0, sizeof(t));
+  uint64_t found = ~0ull;
+  if (h && h2) {
+    for (uint64_t pos = from; pos < limit; ++pos) {
+      /* cheap pre-filter on the first 17 header bits: BFINAL 0, BTYPE 2, HLIT <= 29, HDIST <= 29 */
+      const uint64_t byte = pos >> 3;
+      if (byte + 4 > zlen) break;
+      uint32_t w = (uint32_t)z[byte] | ((uint32_t)z[byte + 1] << 8) | ((uint32_t)z[byte + 2] << 16) | ((uint32_t)z[byte + 3] << 24);
+      w >>= pos & 7;
+      if ((w & 7u) != 4u) continue;          /* BFINAL = 0, BTYPE = 10b */
+      if (((w >> 3) & 31u) > 29u) continue;  /* HLIT */
+      if (((w >> 8) & 31u) > 29u) continue;  /* HDIST */
+      bitrd b;
+      br_init(&b, z, zlen, pos);
+      if (read_block_header(&b, h)) continue;
+      t.n = 0;
+      if (decode_block(&b, h, &t, symwin, 1, 1u << 22)) continue;
+      if (t.n < 1024) continue; /* a real block of a FASTQ stream holds tens of kilobytes */
+      if (read_block_header(&b, h2)) continue;
+      found = pos;
+      break;
+    }
+  }
+  free(t.out);
+  free(h);
+  free(h2);
+  return found;
+}
+
+struct tps_pgz {
+  const uint8_t *z;
+  uint64_t zlen;
+  int threads;
+  uint64_t pos_bit;          /* next block of the current member */
+  int in_member;
+  int eof;
+  uint8_t window[PGZ_WSIZE]; /* last text of the current member (shorter at its start: wlen) */
+  uint32_t wlen;
+  uint32_t crc;
+  uint64_t isize;
+  uint16_t *bufs[256];       /* symbol buffers of the pieces, kept from stretch to stretch */
+  uint64_t bufcap[256];
+  uint8_t *q;                /* text produced but not yet handed out */
+  uint64_t q_len, q_off;
+  double ratio;              /* text bytes per compressed byte so far */
+  uint64_t piece;            /* compressed bytes per thread and stretch */
+  tps_pgz_stats st;
+  char err[160];
+};
+
+static int pgz_fail(tps_pgz *g, const char *msg) {
+  strncpy(g->err, msg, sizeof(g->err) - 1);
+  return -1;
+}
+
+/* gzip member header at byte offset `at` (RFC 1952); returns the offset of the deflate data or 0. */
+static uint64_t gzip_header(const uint8_t *z, uint64_t zlen, uint64_t at) {
+  if (at + 18 > zlen || z[at] != 0x1f || z[at + 1] != 0x8b || z[at + 2] != 8) return 0;
+  const uint8_t flg = z[at + 3];
+  if (flg & 0xE0) return 0;
+  uint64_t p = at + 10;
+  if (flg & 4) {
+    if (p + 2 > zlen) return 0;
+    p += 2 + ((uint64_t)z[p] | ((uint64_t)z[p + 1] << 8));
+  }
+  if (flg & 8) {
+    while (p < zlen && z[p]) ++p;
+    ++p;
+  }
+  if (flg & 16) {
+    while (p < zlen && z[p]) ++p;
+    ++p;
+  }
+  if (flg & 2) p += 2;
+  return p < zlen ? p : 0;
+}
+
+tps_pgz *tps_pgz_open(const uint8_t *zmap, uint64_t zlen, int threads) {
+  const uint64_t d = gzip_header(zmap, zlen, 0);
+  if (!d) return NULL;
+  tps_pgz *g = (tps_pgz *)calloc(1, sizeof(*g));
+  if (!g) return NULL;
+  g->z = zmap;
+  g->zlen = zlen;
+  g->threads = threads > 0 ? (threads > 256 ? 256 : threads) : 1;
+  g->pos_bit = d * 8;
+  g->in_member = 1;
+  g->crc = (uint32_t)crc32(0L, Z_NULL, 0);
+  g->ratio = 4.5;
+  g->piece = 4u << 20;
+  const char *e = getenv("TPS_PGZ_PIECE"); /* compressed bytes per thread and stretch (tests, tuning) */
+  if (e && atoll(e) >= (1 << 16)) g->piece = (uint64_t)atoll(e);
+  return g;
+}
+
+void tps_pgz_close(tps_pgz *g) {
+  if (!g) return;
+  for (int i = 0; i < 256; ++i) free(g->bufs[i]);
+  free(g->q);
+  free(g);
+}
+
+const char *tps_pgz_error(const tps_pgz *g) { return g ? g->err : "out of memory"; }
+void tps_pgz_get_stats(const tps_pgz *g, tps_pgz_stats *out) {
+  if (g && out) *out = g->st;
+}
+void tps_pgz_set_piece(tps_pgz *g, uint64_t bytes) {
+  if (g && bytes >= (1u << 16)) g->piece = bytes;
+}
+
+/* The member ended at pos_bit: check its trailer, move to the next member or to the end of the file. */
+static int end_member(tps_pgz *g) {
+  uint64_t p = (g->pos_bit + 7) >> 3;
+  if (p + 8 > g->zlen) return pgz_fail(g, "gzip trailer missing (truncated file)");
+  const uint32_t crc = (uint32_t)g->z[p] | ((uint32_t)g->z[p + 1] << 8) | ((uint32_t)g->z[p + 2] << 16) | ((uint32_t)g->z[p + 3] << 24);
+  const uint32_t isz = (uint32_t)g->z[p + 4] | ((uint32_t)g->z[p + 5] << 8) | ((uint32_t)g->z[p + 6] << 16) | ((uint32_t)g->z[p + 7] << 24);
+  if (crc != g->crc || isz != (uint32_t)g->isize) return pgz_fail(g, "gzip CRC-32 / length check failed (corrupt file)");
+  p += 8;
+  g->st.members++;
+  while (p < g->zlen && g->z[p] == 0) ++p; /* zero padding between / behind members */
+  if (p >= g->zlen) {
+    g->eof = 1;
+    g->in_member = 0;
+    return 0;
+  }
+  const uint64_t d = gzip_header(g->z, g->zlen, p);
+  if (!d) return pgz_fail(g, "data behind the gzip member is not another member");
+  g->pos_bit = d * 8;
+  g->wlen = 0;
+  g->crc = (uint32_t)crc32(0L, Z_NULL, 0);
+  g->isize = 0;
+  return 0;
+}
+
+/* Inflate the next stretch of the member; the text goes to dst (at most cap bytes) or, if the stretch turns out
+ * larger, to the internal queue.  Returns the bytes written to dst, -1 on error. */
+static int64_t next_stretch(tps_pgz *g, uint8_t *dst, uint64_t cap) {
+  const double t_in = pgz_now();
+  int T = g->threads;
+  /* size the stretch so that its text most likely fits the caller's buffer */
+  uint64_t piece = g->piece;
+  const uint64_t want_comp = (uint64_t)((double)cap / g->ratio * 0.85);
+  if ((uint64_t)T * piece > want_comp) {
+    piece = want_comp / (uint64_t)T;
+    if (piece < (1u << 18)) {
+      piece = 1u << 18;
+      T = (int)(want_comp / piece);
+      if (T < 1) T = 1;
+    }
+  }
+  const uint64_t start_byte = g->pos_bit >> 3;
+  if (start_byte + (uint64_t)T * piece > g->zlen) {
+    const uint64_t left = g->zlen - start_byte;
+    if (left < (uint64_t)T * (1u << 18)) T = (int)(left >> 18) > 0 ? (int)(left >> 18) : 1;
+    piece = left / (uint64_t)T + 1;
+  }
+  seg *sg = (seg *)calloc((size_t)T, sizeof(seg));
+  uint16_t *symwin = (uint16_t *)malloc(PGZ_WSIZE * sizeof(uint16_t));
+  uint16_t *win0 = (uint16_t *)malloc(PGZ_WSIZE * sizeof(uint16_t));
+  if (!sg || !symwin || !win0) {
+    free(sg); free(symwin); free(win0);
+    return pgz_fail(g, "out of memory");
+  }
+  for (uint32_t i = 0; i < PGZ_WSIZE; ++i) symwin[i] = (uint16_t)(256u + i);
+  for (uint32_t i = 0; i < PGZ_WSIZE; ++i) win0[i] = i >= PGZ_WSIZE - g->wlen ? g->window[i - (PGZ_WSIZE - g->wlen)] : 0;
+  const int dbg = getenv("TPS_PGZ_DEBUG") != NULL;
+  const double t_a = pgz_now();
+  /* 2. block starts */
+  uint64_t *starts = (uint64_t *)malloc(((size_t)T + 1) * sizeof(uint64_t));
+  starts[0] = g->pos_bit;
+#pragma omp parallel for num_threads(T) schedule(static, 1)
+  for (int i = 1; i < T; ++i) {
+    const uint64_t from = (start_byte + (uint64_t)i * piece) * 8, lim = (start_byte + (uint64_t)(i + 1) * piece) * 8;
+    starts[i] = find_block_start(g->z, g->zlen, from, lim < g->zlen * 8 ? lim : g->zlen * 8, symwin);
+  }
+  int ns = 1; /* pieces that found a start, in order */
+  for (int i = 1; i < T; ++i)
+    if (starts[i] != ~0ull && starts[i] > starts[ns - 1]) starts[ns++] = starts[i];
+  const uint64_t stretch_end = (start_byte + (uint64_t)T * piece) * 8;
+  for (int i = 0; i < ns; ++i) {
+    sg[i].out = g->bufs[i];
+    sg[i].cap = g->bufcap[i];
+    g->bufs[i] = NULL;
+    const uint64_t expect = (uint64_t)((double)piece * g->ratio * 1.5) + (1u << 20); /* no doubling on the way */
+    if (sg[i].cap < expect) { /* with headroom: the running ratio moves a little from stretch to stretch */
+      const uint64_t want = (expect + expect / 2 + (1u << 23) - 1) & ~(uint64_t)((1u << 23) - 1);
+      free(sg[i].out);
+      sg[i].out = sym_alloc(want);
+      sg[i].cap = sg[i].out ? want : 0;
+    }
+    sg[i].start_bit = starts[i];
+    sg[i].stop_bit = i + 1 < ns ? starts[i + 1] : stretch_end;
+    sg[i].symbolic = i > 0;
+  }
+  const double t_b = pgz_now();
+  /* 3. decode */
+#pragma omp parallel for num_threads(ns) schedule(static, 1)
+  for (int i = 0; i < ns; ++i) decode_segment(g->z, g->zlen, &sg[i], i ? symwin : win0);
+  const double t_c = pgz_now();
+  /* the chain: segment i must stop exactly where segment i+1 started */
+  int good = 0;
+  for (int i = 0; i < ns; ++i) {
+    if (sg[i].status) break;
+    good = i + 1;
+    if (sg[i].saw_final) break;
+    if (i + 1 < ns && sg[i].end_bit != sg[i + 1].start_bit) {
+      g->st.chain_breaks++;
+      break;
+    }
+  }
+  int64_t ret = -1;
+  if (good == 0) {
+    pgz_fail(g, sg[0].status == -2 ? "out of memory" : "corrupt deflate stream");
+  } else {
+    /* 4. windows in order, then everything to bytes in parallel */
+    uint8_t *wins = (uint8_t *)malloc((size_t)good * PGZ_WSIZE);
+    uint32_t *wlens = (uint32_t *)malloc((size_t)good * sizeof(uint32_t));
+    uint64_t total = 0;
+    for (int i = 0; i < good; ++i) total += sg[i].n;
+    uint8_t *target = dst;
+    int to_queue = 0;
+    if (total > cap) { /* the estimate was too small: keep the text, hand it out piecewise */
+      free(g->q);
+      g->q = (uint8_t *)malloc(total ? total : 1);
+      g->q_len = total;
+      g->q_off = 0;
+      target = g->q;
+      to_queue = 1;
+    }
+    if (!wins || !wlens || !target) {
+      pgz_fail(g, "out of memory");
+    } else {
+      /* window before segment i = last 32 KiB of the text up to its start */
+      memcpy(wins, g->window, g->wlen);
+      wlens[0] = g->wlen;
+      for (int i = 1; i < good; ++i) {
+        const seg *p = &sg[i - 1];
+        const uint8_t *pw = wins + (size_t)(i - 1) * PGZ_WSIZE;
+        uint8_t *w = wins + (size_t)i * PGZ_WSIZE;
+        const uint32_t pwl = wlens[i - 1];
+        const uint64_t take = p->n < PGZ_WSIZE ? p->n : PGZ_WSIZE;
+        const uint32_t keep = take < PGZ_WSIZE ? (uint32_t)((PGZ_WSIZE - take) < pwl ? (PGZ_WSIZE - take) : pwl) : 0;
+        memcpy(w, pw + (pwl - keep), keep);
+        for (uint64_t k = 0; k < take; ++k) {
+          const uint16_t v = p->out[p->n - take + k];
+          /* symbol 256 + j = byte j of the 32 KiB window, whose last pwl bytes are known (a valid stream never
+           * reaches further back than the member's start) */
+          w[keep + k] = v < 256 ? (uint8_t)v : (v - 256u >= PGZ_WSIZE - pwl ? pw[v - 256u - (PGZ_WSIZE - pwl)] : 0);
+        }
+        wlens[i] = keep + (uint32_t)take;
+      }
+      uint64_t *offs = (uint64_t *)malloc(((size_t)good + 1) * sizeof(uint64_t));
+      offs[0] = 0;
+      for (int i = 0; i < good; ++i) offs[i + 1] = offs[i] + sg[i].n;
+      int bad_ref = 0;
+#pragma omp parallel for num_threads(good) schedule(static, 1)
+      for (int i = 0; i < good; ++i) {
+        const seg *s = &sg[i];
+        uint8_t *o = target + offs[i];
+        if (!s->symbolic) {
+          for (uint64_t k = 0; k < s->n; ++k) o[k] = (uint8_t)s->out[k];
+        } else {
+          const uint8_t *w = wins + (size_t)i * PGZ_WSIZE;
+          const uint32_t wl = wlens[i], miss = PGZ_WSIZE - wl;
+          uint64_t k = 0;
+          while (k < s->n) {
+            /* past the first stretch of a piece nearly everything is resolved: whole runs of 32 narrow at once */
+            if (k + 32 <= s->n) {
+              uint16_t any = 0;
+              for (int j = 0; j < 32; ++j) any |= s->out[k + j];
+              if (any < 256) {
+                for (int j = 0; j < 32; ++j) o[k + j] = (uint8_t)s->out[k + j];
+                k += 32;
+                continue;
+              }
+            }
+            const uint64_t ke = k + 32 <= s->n ? k + 32 : s->n;
+            for (; k < ke; ++k) {
+              const uint16_t v = s->out[k];
+              if (v < 256) o[k] = (uint8_t)v;
+              else if (v - 256u >= miss) o[k] = w[v - 256u - miss];
+              else {
+                o[k] = 0;
+                bad_ref = 1; /* a reference before the start of the member: corrupt */
+              }
+            }
+          }
+        }
+        uint64_t done = 0;
+        uint32_t c = (uint32_t)crc32(0L, Z_NULL, 0);
+        while (done < s->n) {
+          const uint64_t step = s->n - done > (1u << 30) ? (1u << 30) : s->n - done;
+          c = (uint32_t)crc32(c, o + done, (uInt)step);
+          done += step;
+        }
+        sg[i].crc = c;
+      }
+      if (dbg)
+        fprintf(stderr, "[pgz] stretch: %d pieces of %.2f MB, %d starts, %d good; setup %.4f s, search %.4f s, decode %.4f s, resolve+crc %.4f s, %.1f MB text\n",
+                T, piece / 1e6, ns, good, t_a - t_in, t_b - t_a, t_c - t_b, pgz_now() - t_c, total / 1e6);
+      if (bad_ref) {
+        pgz_fail(g, "corrupt deflate stream (reference before the start of the member)");
+      } else {
+        for (int i = 0; i < good; ++i) g->crc = (uint32_t)crc32_combine(g->crc, sg[i].crc, (z_off_t)sg[i].n);
+        g->isize += total;
+        /* new window */
+        const seg *l = &sg[good - 1];
+        if (total >= PGZ_WSIZE) {
+          memcpy(g->window, target + total - PGZ_WSIZE, PGZ_WSIZE);
+          g->wlen = PGZ_WSIZE;
+        } else {
+          const uint32_t keep = (uint32_t)((PGZ_WSIZE - total) < g->wlen ? (PGZ_WSIZE - total) : g->wlen);
+          memmove(g->window, g->window + (g->wlen - keep), keep);
+          memcpy(g->window + keep, target, total);
+          g->wlen = keep + (uint32_t)total;
+        }
+        g->pos_bit = l->end_bit;
+        g->st.stretches++;
+        g->st.segments += (uint64_t)good;
+        g->st.text_bytes += total;
+        if (good > 1) g->st.parallel_text_bytes += total - sg[0].n;
+        const uint64_t comp = (l->end_bit >> 3) - start_byte;
+        if (comp > (1u << 16)) g->ratio = 0.5 * g->ratio + 0.5 * ((double)total / (double)comp);
+        if (g->ratio < 1.0) g->ratio = 1.0;
+        ret = 0;
+        if (l->saw_final && end_member(g)) ret = -1;
+        if (ret == 0) ret = to_queue ? 0 : (int64_t)total;
+      }
+      free(offs);
+    }
+    free(wins);
+    free(wlens);
+  }
+  for (int i = 0; i < T; ++i) { /* keep the symbol buffers: fresh ones cost a page fault per 4 KiB */
+    g->bufs[i] = sg[i].out;
+    g->bufcap[i] = sg[i].cap;
+  }
+  free(sg);
+  free(symwin);
+  free(win0);
+  free(starts);
+  return ret;
+}
+
+int64_t tps_pgz_read(tps_pgz *g, uint8_t *dst, uint64_t cap) {
+  if (!g || !dst) return -1;
+  uint64_t got = 0;
+  while (got < cap) {
+    if (g->q_off < g->q_len) {
+      uint64_t n = g->q_len - g->q_off;
+      if (n > cap - got) n = cap - got;
+      memcpy(dst + got, g->q + g->q_off, n);
+      g->q_off += n;
+      got += n;
+      if (g->q_off == g->q_len) {
+        free(g->q);
+        g->q = NULL;
+        g->q_len = g->q_off = 0;
+      }
+      continue;
+    }
+    if (g->eof) break;
+    if (cap - got < (1u << 20) && got) break; /* not worth a stretch: the caller comes back */
+    const int64_t n = next_stretch(g, dst + got, cap - got);
+    if (n < 0) return -1;
+    got += (uint64_t)n;
+  }
+  return (int64_t)got;
+}
+
+int tps_pgz_eof(const tps_pgz *g) { return g && g->eof && g->q_off >= g->q_len; }

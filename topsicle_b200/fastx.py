@@ -70,6 +70,8 @@ def host_library() -> C.CDLL:
                                             C.POINTER(vp), C.POINTER(vp)]
         lib.tps_fastx_set_two_pass.restype = None
         lib.tps_fastx_set_two_pass.argtypes = [vp, C.c_int]
+        lib.tps_fastx_inflate_stats.restype = None
+        lib.tps_fastx_inflate_stats.argtypes = [vp, vp]
         lib.tps_fastx_find_id.restype = C.c_uint32
         lib.tps_fastx_find_id.argtypes = [vp, vp, C.c_uint32, C.c_char_p, C.c_uint32, vp, C.c_uint32]
         lib.tps_fastx_gather_regions.restype = C.c_uint32
@@ -339,6 +341,14 @@ class FastxFile:
                       end_len=end_len)
         self.reads_delivered += n.value
         return b
+
+    def inflate_stats(self) -> dict:
+        """Counters of the parallel gzip inflater (all zero unless the file is plain gzip): stretches, segments,
+        chain_breaks, members, text_bytes, parallel_text_bytes."""
+        out = (C.c_uint64 * 6)()
+        self._lib.tps_fastx_inflate_stats(self._h, out)
+        return dict(zip(("stretches", "segments", "chain_breaks", "members", "text_bytes", "parallel_text_bytes"),
+                        (int(x) for x in out)))
 
     def set_two_pass(self, on: bool = True):
         """Force the index-then-gather reader (the one-pass FASTQ reader's validating fallback)."""

@@ -483,13 +483,12 @@ typedef struct bgzf_blk {
 /* Append inflated text to chunk[*win .. cap): as much as fits.  Sets fx->gz_eof at the end of the input.
  * Returns 0, or <0 after fx_fail. */
 static int gz_fill(tps_fastx *fx, uint8_t *chunk, uint64_t *win, uint64_t cap) {
-  if (fx->pgz) {
-    while (*win < cap && !fx->gz_eof) {
+  if (fx->pgz) { /* may stop short of cap: the inflater only runs stretches that keep every thread busy */
+    if (*win < cap && !fx->gz_eof) {
       const int64_t n = tps_pgz_read(fx->pgz, chunk + *win, cap - *win);
       if (n < 0) return fx_fail(fx, TPS_FX_EIO, "gzip input: %s", tps_pgz_error(fx->pgz));
       *win += (uint64_t)n;
       if (tps_pgz_eof(fx->pgz)) fx->gz_eof = 1;
-      else if (n == 0) break; /* the rest of the buffer is too small for another stretch */
     }
     return TPS_FX_OK;
   }

@@ -314,7 +314,8 @@ static inline int is_text(uint32_t c) { return c == 10 || c == 13 || c == 9 || (
 
 /* Decode the block whose header was just read.  win = the 32768 symbols before the segment's start.
  * text_only / max_out: the stricter rules of the block-start search.  0 ok, <0 error. */
-static int decode_block(bitrd *b, const blockhdr *h, seg *s, const uint16_t *win, int text_only, uint64_t max_out) {
+static inline __attribute__((always_inline)) int decode_block_impl(bitrd *b, const blockhdr *h, seg *s, const uint16_t *win,
+                                                                  const int text_only, const uint64_t max_out) {
   if (h->type == 0) {
     if (b->cnt & 7u) return -1;
     uint32_t left = h->stored_len;
@@ -335,15 +336,21 @@ static int decode_block(bitrd *b, const blockhdr *h, seg *s, const uint16_t *win
     return 0;
   }
   for (;;) {
-    if (seg_grow(s, 320)) return -2;
+    if (__builtin_expect(s->n + 320 > s->cap, 0) && seg_grow(s, 320)) return -2;
     br_refill(b);
     int32_t sym = huff_sym_tb(&h->lit, b, LIT_TB);
     if (sym < 0) return -1;
     if (sym < 256) {
       if (text_only && !is_text((uint32_t)sym)) return -1;
       s->out[s->n++] = (uint16_t)sym;
-      /* a second literal from the same refill: most of FASTQ text is literals and short matches */
-      if (b->cnt >= 32) {
+      /* up to two more literals from the same refill (3 x 15 bits < 56): most of FASTQ text -- the quality
+       * lines above all -- is literals and short matches */
+      if (b->cnt < 48) continue;
+      sym = huff_sym_tb(&h->lit, b, LIT_TB);
+      if (sym < 0) return -1;
+      if (sym < 256) {
+        if (text_only && !is_text((uint32_t)sym)) return -1;
+        s->out[s->n++] = (uint16_t)sym;
         sym = huff_sym_tb(&h->lit, b, LIT_TB);
         if (sym < 0) return -1;
         if (sym < 256) {
@@ -351,8 +358,6 @@ static int decode_block(bitrd *b, const blockhdr *h, seg *s, const uint16_t *win
           s->out[s->n++] = (uint16_t)sym;
           continue;
         }
-      } else {
-        continue;
       }
     }
     if (sym == 256) return 0;
@@ -386,6 +391,13 @@ static int decode_block(bitrd *b, const blockhdr *h, seg *s, const uint16_t *win
   }
 }
 
+static int decode_block(bitrd *b, const blockhdr *h, seg *s, const uint16_t *win) {
+  return decode_block_impl(b, h, s, win, 0, 0);
+}
+static int decode_block_text(bitrd *b, const blockhdr *h, seg *s, const uint16_t *win, uint64_t max_out) {
+  return decode_block_impl(b, h, s, win, 1, max_out);
+}
+
 /* Decode whole blocks from s->start_bit until the position reaches s->stop_bit or the member ends. */
 static void decode_segment(const uint8_t *z, uint64_t zlen, seg *s, const uint16_t *win) {
   bitrd b;
@@ -401,7 +413,7 @@ static void decode_segment(const uint8_t *z, uint64_t zlen, seg *s, const uint16
       s->status = -1;
       break;
     }
-    const int rc = decode_block(&b, h, s, win, 0, 0);
+    const int rc = decode_block(&b, h, s, win);
     if (rc) {
       s->status = rc;
       break;
@@ -437,7 +449,7 @@ static uint64_t find_block_start(const uint8_t *z, uint64_t zlen, uint64_t from,
       br_init(&b, z, zlen, pos);
       if (read_block_header(&b, h)) continue;
       t.n = 0;
-      if (decode_block(&b, h, &t, symwin, 1, 1u << 22)) continue;
+      if (decode_block_text(&b, h, &t, symwin, 1u << 22)) continue;
       if (t.n < 1024) continue; /* a real block of a FASTQ stream holds tens of kilobytes */
       if (read_block_header(&b, h2)) continue;
       found = pos;
@@ -783,7 +795,9 @@ int64_t tps_pgz_read(tps_pgz *g, uint8_t *dst, uint64_t cap) {
       continue;
     }
     if (g->eof) break;
-    if (cap - got < (1u << 20) && got) break; /* not worth a stretch: the caller comes back */
+    /* a stretch pays when every thread gets a full piece: with less room than that left in the caller's buffer,
+     * hand back what there is (the caller comes back with a fresh buffer) */
+    if (got && (double)(cap - got) < 0.6 * (double)g->threads * (double)g->piece * g->ratio) break;
     const int64_t n = next_stretch(g, dst + got, cap - got);
     if (n < 0) return -1;
     got += (uint64_t)n;

@@ -57,6 +57,12 @@ int tps_fastx_format(const tps_fastx *fx);
 const char *tps_fastx_last_error(const tps_fastx *fx);
 /* Raw bytes examined per call (default 512 MiB) / force the validating two-pass reader (tests, tuning). */
 void tps_fastx_set_window(tps_fastx *fx, uint64_t bytes);
+/* A record with more bases than a whole batch can hold normally ends the file with TPS_FX_ECAPACITY.  With
+ * clip_bases > 0, tps_fastx_next / tps_fastx_next_spans deliver such a record as a batch of its own that holds its
+ * first and last clip_bases bases back to back (its tps_fastx_rec still describes the whole record).  The scan is
+ * unchanged by that when clip_bases >= max(maxlengthtelo, 1000) and 2 * clip_bases > minSeqLength: it looks at
+ * no other base (reference: Topsicle/allsteps.py:176-177, 266-268). */
+void tps_fastx_set_clip(tps_fastx *fx, uint64_t clip_bases);
 void tps_fastx_set_two_pass(tps_fastx *fx, int on);
 
 /* Next batch of records in file order: at most reads_cap records and bases_cap bases, bases of record i at

@@ -260,3 +260,47 @@ def test_console_script_and_package_exports():
                  "seq_cut_windows", "bound_detect", "rawCountPattern", "fit_quadratic_and_find_vertex", "plot_patterns"):
         assert callable(ns[name]), name
     assert topsicle_b200.patternTRC_count is ns["patternTRC_count"]
+
+
+@pytest.mark.parametrize("fmt", ["fasta", "fastq"])
+def test_record_longer_than_a_batch_is_scanned_by_its_ends(tmp_path, monkeypatch, fmt):
+    """A FASTA of contigs: records far longer than a whole batch (chromosomes) are delivered as their first and
+    last max(maxlengthtelo, 1000) bases, which is every base the scan looks at -- same rows and the same subset
+    records as with a batch that holds them whole (the reference reads such files like any other)."""
+    fake_engine.install(monkeypatch)
+    from topsicle_b200 import pipeline
+    from topsicle_b200.patterns import patterns_to_search
+    rng = np.random.default_rng(77)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+
+    def rand(n):
+        return bytes(rng.choice(acgt, n)).decode()
+    seqs = [("short1", "CCCTAA" * 400 + rand(9000)),
+            ("chrF", "CCCTAA" * 700 + rand(400_000)),                      # forward telomere, 404 kb
+            ("chrN", rand(350_000)),                                        # no telomere
+            ("chrR", rand(500_000) + "TTAGGG" * 900),                       # reverse telomere
+            ("short2", rand(12000) + "TTAGGG" * 300)]
+    path = tmp_path / f"contigs.{fmt}"
+    with open(path, "w") as fh:
+        for name, s in seqs:
+            if fmt == "fasta":
+                fh.write(f">{name} len={len(s)}\n")
+                fh.writelines(s[i:i + 60] + "\n" for i in range(0, len(s), 60))
+            else:
+                fh.write(f"@{name}\n{s}\n+\n{'I' * len(s)}\n")
+    cfg = pipeline.ScanConfig(patterns=patterns_to_search("CCCTAA", 4), len_telopattern=6, phrase=4, slide=6,
+                              maxlengthtelo=20000, want_rawcount=True)
+    _, whole = pipeline.collect_file(str(path), [cfg], max_batch_bases=1 << 20, records_cfg=0)
+    _, clipped = pipeline.collect_file(str(path), [cfg], max_batch_bases=100_000, records_cfg=0)
+    assert [p.read_id for p in whole[0]] == ["short1", "chrF", "chrR", "short2"]
+
+    def key(p):
+        return (p.index, p.read_id, p.tail, round(p.trc, 6), p.status, p.n_windows, p.telo_length, p.record,
+                p.counts.tobytes())
+    assert [key(p) for p in clipped[0]] == [key(p) for p in whole[0]]
+    assert [p.length for p in clipped[0]] == [len(seqs[0][1]), 40000, 40000, len(seqs[4][1])]
+    # a batch too small for the two ends: the file ends with the reader's capacity error, as before
+    from topsicle_b200 import fastx
+    with pytest.raises(fastx.FastxError) as e:
+        pipeline.collect_file(str(path), [cfg], max_batch_bases=30_000)
+    assert e.value.code == -4

@@ -1,4 +1,5 @@
-"""GPU tier: the bit-parallel window kernel (tps_window_bp_kernel, the default K3 with the change point fused)
+"""GPU tier: the bit-parallel window kernel (tps_window_bp_kernel, the default K3 with the change point fused;
+a read per CTA, or -- few passing reads -- a read's tiles dealt over 2 or 4 CTAs, TPS_K3_SPLIT=0 to forbid)
 against the oracle and against the plain per-literal kernel (tps_window_kernel + tps_changepoint_kernel,
 TPS_K3_BITPAR=0): the sums of c_w over the groups of five windows (what the change point reads), n_windows,
 status, bkp and telo_length must be bit-identical; TPS_K3_NO_GROUPS=1 (every window on its own) likewise.
@@ -22,7 +23,7 @@ CFGS = [("CCCTAA", 4, 100, 6, 100, 20000), ("TTAGGG", 4, 50, 3, 100, 20000), ("C
         ("ACACAC", 4, 100, 2, 0, 3000), ("AAAAAA", 3, 64, 1, 5, 2500), ("TTTTAGGG", 8, 100, 8, 100, 20000)]
 
 
-def _scan(engine, pats, motif, reads, W, s, t, M, bitpar, monkeypatch, no_groups=False, **kw):
+def _scan(engine, pats, motif, reads, W, s, t, M, bitpar, monkeypatch, no_groups=False, no_split=False, **kw):
     if bitpar:
         monkeypatch.delenv("TPS_K3_BITPAR", raising=False)
     else:
@@ -31,6 +32,10 @@ def _scan(engine, pats, motif, reads, W, s, t, M, bitpar, monkeypatch, no_groups
         monkeypatch.setenv("TPS_K3_NO_GROUPS", "1")
     else:
         monkeypatch.delenv("TPS_K3_NO_GROUPS", raising=False)
+    if no_split:
+        monkeypatch.setenv("TPS_K3_SPLIT", "0")
+    else:
+        monkeypatch.delenv("TPS_K3_SPLIT", raising=False)
     monkeypatch.setenv("TPS_K3_DEBUG_GS", "1")     # the bit-parallel kernel also writes its group sums out
     with engine.ScanContext(pats, len_telopattern=len(motif), min_seq_length=0, count_threshold_override=0,
                             window_size=W, slide=s, trimfirst=t, maxlengthtelo=M, max_batch_reads=1024,
@@ -53,10 +58,12 @@ def test_window_sums_equal_oracle_and_plain_kernel(cfg, edge_records, demo_recor
     rows, cws, launches = _scan(engine, pats, motif, reads, W, s, t, M, True, monkeypatch)
     rows0, cws0, launches0 = _scan(engine, pats, motif, reads, W, s, t, M, False, monkeypatch)
     rows1, cws1, _ = _scan(engine, pats, motif, reads, W, s, t, M, True, monkeypatch, no_groups=True)
+    # ~100 reads on a grid of several hundred CTAs: the scans above dealt every read's tiles over four CTAs; one CTA per read:
+    rows2, cws2, _ = _scan(engine, pats, motif, reads, W, s, t, M, True, monkeypatch, no_split=True)
     assert launches == 3 and launches0 == 4      # K1, K2, fused K3+K4  vs  K1, K2, K3, K4
-    assert rows.tobytes() == rows0.tobytes() == rows1.tobytes()
-    assert set(cws) == set(cws0) == set(cws1)
-    assert all(np.array_equal(cws[i], cws1[i]) for i in cws)
+    assert rows.tobytes() == rows0.tobytes() == rows1.tobytes() == rows2.tobytes()
+    assert set(cws) == set(cws0) == set(cws1) == set(cws2)
+    assert all(np.array_equal(cws[i], cws1[i]) and np.array_equal(cws[i], cws2[i]) for i in cws)
     n_cp = 0
     for i, seq in enumerate(reads):
         row = rows[i]

@@ -41,6 +41,8 @@ struct Slot {
   uint8_t *d_raw = nullptr;
   uint32_t *d_cw = nullptr;         /* c_w rows of passing reads */
   TpsReadItem *d_items = nullptr;   /* bit-parallel K3: one record per TRC-pass read, listed by K2 */
+  uint32_t *d_tile_done = nullptr;  /* bit-parallel K3, split mode: CTAs done per passing read */
+  uint16_t *d_gs_debug = nullptr;   /* TPS_K3_DEBUG_GS=1: copy of every read's group sums */
   tps_row *h_rows = nullptr;        /* pinned */
   uint32_t *h_counters = nullptr;   /* pinned */
   uint64_t batch_id = 0;
@@ -64,7 +66,8 @@ struct tps_ctx {
   void (*k3n_fn)(const TpsScanArgs, const TpsPatTable) = nullptr;
   uint32_t k3n_lin_words = 0, k3n_stride = 0, k3n_tile_bases = 0, k3n_tiles_max = 0, k3n_smem = 0, k3n_grid = 0, k3n_nz = 0;
   uint32_t k3n_gs_cap = 0, k3n_tile_windows = 0, k3n_no_groups = 0;
-  bool k3n_debug_gs = false; /* TPS_K3_DEBUG_GS=1: the group sums of every read are also written to d_cw (tests) */
+  bool k3n_debug_gs = false; /* TPS_K3_DEBUG_GS=1: the group sums of every read are also written out (tests) */
+  uint32_t k3n_no_split = 0;
   uint32_t cw_stride = 0, max_pass = 0;
   int kt = 0; /* template K of the K2/K3 instantiation in use (0 = generic) */
   void (*k2_fn)(const TpsScanArgs, const TpsPatTable) = nullptr;
@@ -247,7 +250,7 @@ void tps_destroy(tps_ctx *ctx) {
     if (s.stream) cudaStreamSynchronize(s.stream);
     cudaFree(s.d_bases); cudaFree(s.d_codes); cudaFree(s.d_flags);
     cudaFree(s.d_off); cudaFree(s.d_len); cudaFree(s.d_true_len); cudaFree(s.d_tails); cudaFree(s.d_rows); cudaFree(s.d_pass); cudaFree(s.d_counters);
-    cudaFree(s.d_raw); cudaFree(s.d_cw); cudaFree(s.d_items);
+    cudaFree(s.d_raw); cudaFree(s.d_cw); cudaFree(s.d_items); cudaFree(s.d_tile_done); cudaFree(s.d_gs_debug);
     if (s.h_rows) cudaFreeHost(s.h_rows);
     if (s.h_counters) cudaFreeHost(s.h_counters);
     if (s.done) cudaEventDestroy(s.done);
@@ -382,11 +385,13 @@ int tps_create(tps_ctx **out, int device, const tps_params *params) {
       /* raw[2] | pm | lin | ori | alignment | Z | Zhi | UP | CP | SP | brows | gsum */
       ctx->k3n_smem = (2 * TPS_K3N_RAW_WORDS + pm_words + 3 * ctx->k3n_lin_words + 3 * (NT + 1) + 3 + 4 * (NT + 1) +
                        (ctx->k3n_nz > 4 ? 4 * (NT + 1) : 0) + 2 * (NT + 2) + (pt.n_bordered ? 2 * (NT + 2) : 0) +
-                       2 * ((pt.n + 3u) & ~3u) * ctx->k3n_stride + pt.n_bordered * (NT + 1) + ctx->k3n_gs_cap / 2) * 4;
+                       2 * ((pt.n + 3u) & ~3u) * ctx->k3n_stride + pt.n_bordered * (NT + 1) + 4 + ctx->k3n_gs_cap / 2) * 4;
       const char *ng = getenv("TPS_K3_NO_GROUPS"); /* 1 = no five-window fast path (A/B) */
       ctx->k3n_no_groups = ng && atoi(ng) != 0;
       const char *dg = getenv("TPS_K3_DEBUG_GS");
       ctx->k3n_debug_gs = dg && atoi(dg) != 0;
+      const char *sp = getenv("TPS_K3_SPLIT"); /* 0 = a read is always one CTA's work (A/B) */
+      ctx->k3n_no_split = sp && atoi(sp) == 0;
     }
   }
   ctx->cw_stride = (uint32_t)(nw_max ? nw_max : 1);
@@ -512,7 +517,10 @@ int tps_create(tps_ctx **out, int device, const tps_params *params) {
     if (p.want_rawcount) TPS_CC(cudaMalloc(&s.d_raw, p.rawcount_capacity ? p.rawcount_capacity : 1));
     if (ctx->k3_bitpar) { /* c_w never leaves the SM: group sums in shared memory */
       TPS_CC(cudaMalloc(&s.d_items, (uint64_t)ctx->max_pass * sizeof(TpsReadItem)));
-      if (ctx->k3n_debug_gs) TPS_CC(cudaMalloc(&s.d_cw, (uint64_t)ctx->max_pass * ctx->k3n_gs_cap * sizeof(uint16_t)));
+      TPS_CC(cudaMalloc(&s.d_tile_done, (uint64_t)ctx->max_pass * sizeof(uint32_t)));
+      /* group-sum rows for the split mode (few passing reads); as uint16 a fifth of a tenth of the plain kernel's c_w */
+      TPS_CC(cudaMalloc(&s.d_cw, (uint64_t)ctx->max_pass * ctx->k3n_gs_cap * sizeof(uint16_t)));
+      if (ctx->k3n_debug_gs) TPS_CC(cudaMalloc(&s.d_gs_debug, (uint64_t)ctx->max_pass * ctx->k3n_gs_cap * sizeof(uint16_t)));
     } else {
       TPS_CC(cudaMalloc(&s.d_cw, (uint64_t)ctx->max_pass * ctx->cw_stride * sizeof(uint32_t)));
     }
@@ -636,7 +644,10 @@ int enqueue_scan(tps_ctx *ctx, Slot &s, cudaStream_t st, const ScanJob &job) {
   a.bp_tile_windows = ctx->k3n_tile_windows;
   a.gs_cap = ctx->k3n_gs_cap;
   a.no_groups = ctx->k3n_no_groups;
-  a.gs_debug = ctx->k3_bitpar && ctx->k3n_debug_gs ? reinterpret_cast<uint16_t *>(s.d_cw) : nullptr;
+  a.gs_debug = ctx->k3_bitpar && ctx->k3n_debug_gs ? s.d_gs_debug : nullptr;
+  a.gs_rows = ctx->k3_bitpar ? reinterpret_cast<uint16_t *>(s.d_cw) : nullptr;
+  a.tile_done = s.d_tile_done;
+  a.no_split = ctx->k3n_no_split;
   if (n_reads) {
     a.lin_words = ctx->k2_lin_words;
     if (ctx->k2_reg)
@@ -1042,7 +1053,7 @@ int tps_debug_copy(tps_ctx *ctx, int what, void *dst, size_t bytes) {
     case 4:
       if (ctx->k3_bitpar && !ctx->k3n_debug_gs)
         return fail(ctx, TPS_ESTATE, "the bit-parallel window kernel keeps its window sums in shared memory (set TPS_K3_DEBUG_GS=1)");
-      src = s.d_cw;
+      src = ctx->k3_bitpar ? (const void *)s.d_gs_debug : (const void *)s.d_cw;
       cap = ctx->k3_bitpar ? (size_t)ctx->max_pass * ctx->k3n_gs_cap * sizeof(uint16_t)
                            : (size_t)ctx->max_pass * ctx->cw_stride * sizeof(uint32_t);
       break;

@@ -67,6 +67,7 @@ typedef struct tps_fastx {
   const uint8_t *zmap;
   uint64_t zlen, zpos;
   uint64_t window_bytes;
+  uint64_t clip_bases; /* tps_fastx_set_clip: ends kept of a record longer than a whole batch (0 = such a record is an error) */
   int threads;
   int slow_only;      /* never use the one-pass FASTQ reader (tests / tuning) */
   uint64_t n_records; /* records delivered so far */
@@ -732,6 +733,9 @@ void tps_fastx_inflate_stats(const tps_fastx *fx, tps_pgz_stats *out) {
 void tps_fastx_set_window(tps_fastx *fx, uint64_t bytes) {
   if (fx && bytes >= 4096) fx->window_bytes = bytes;
 }
+void tps_fastx_set_clip(tps_fastx *fx, uint64_t clip_bases) {
+  if (fx) fx->clip_bases = clip_bases;
+}
 void tps_fastx_release(void *owner) { free(owner); }
 void tps_fastx_set_two_pass(tps_fastx *fx, int on) {
   if (fx) fx->slow_only = on;
@@ -807,6 +811,8 @@ static int acquire_indexed(tps_fastx *fx, uint64_t want, const uint8_t **w_out, 
   return 0;
 }
 
+static void gather_ends(const uint8_t *w, const tps_fastx_rec *r, uint32_t end_len, uint8_t *dst);
+
 /* Next batch: at most reads_cap records and bases_cap bases, in file order.
  *   bases_out[offsets_out[i] .. offsets_out[i+1]) = bases of record i; recs_out[i] indexes its text
  *   relative to *raw_base, which stays valid until tps_fastx_release(*raw_owner) (gz input) or
@@ -843,6 +849,18 @@ int tps_fastx_next(tps_fastx *fx, uint64_t bases_cap, uint32_t reads_cap, uint8_
     offsets_out[n + 1] = nb;
     ++n;
   }
+  /* A record longer than a whole batch (a chromosome in a FASTA of contigs): the scan only looks at a bounded
+   * stretch of either end (allsteps.py:176-177 the first / last 1000 bases, :266-268 at most maxlengthtelo bases
+   * from the chosen end), so with tps_fastx_set_clip the record is delivered, alone, as its first and last
+   * clip_bases bases back to back; recs_out[0] still describes the whole record. */
+  int clipped = 0;
+  if (n == 0 && rv.n > 0 && fx->clip_bases && 2 * fx->clip_bases <= bases_cap && 2 * fx->clip_bases <= 0xFFFFFFFFull &&
+      rv.v[0].seq_len > 2 * fx->clip_bases) {
+    clipped = 1;
+    n = 1;
+    nb = 2 * fx->clip_bases;
+    offsets_out[1] = nb;
+  }
   if (n == 0 && rv.n > 0) {
     uint32_t L = rv.v[0].seq_len;
     free(rv.v);
@@ -856,11 +874,15 @@ int tps_fastx_next(tps_fastx *fx, uint64_t bases_cap, uint32_t reads_cap, uint8_
   if (n) memcpy(recs_out, rv.v, (size_t)n * sizeof(tps_fastx_rec));
   int T = fx->threads;
   double t_g = dbg_now();
+  if (clipped) {
+    gather_ends(w, &rv.v[0], (uint32_t)fx->clip_bases, bases_out);
+  } else {
 #pragma omp parallel num_threads(T) if (nb > (8u << 20))
-  {
+    {
 #pragma omp for schedule(dynamic, 16)
-    for (int64_t i = 0; i < (int64_t)n; ++i) gather_seq(w, &rv.v[i], bases_out + offsets_out[i]);
-    copy_fence(); /* non-temporal stores are visible before the batch is handed to the DMA engine */
+      for (int64_t i = 0; i < (int64_t)n; ++i) gather_seq(w, &rv.v[i], bases_out + offsets_out[i]);
+      copy_fence(); /* non-temporal stores are visible before the batch is handed to the DMA engine */
+    }
   }
   if (getenv("TPS_FX_DEBUG")) fprintf(stderr, "[fastx] gather %.1f MB in %.4f s\n", nb / 1e6, dbg_now() - t_g);
   free(rv.v);

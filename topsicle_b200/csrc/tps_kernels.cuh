@@ -80,6 +80,12 @@ struct TpsScanArgs {
   uint32_t gs_cap;          /* uint16 group sums per read the kernel's shared memory holds */
   uint32_t no_groups;       /* 1 = every window on its own (A/B of the five-window fast path) */
   uint16_t *gs_debug;       /* test hook (TPS_K3_DEBUG_GS=1): group sums also go to gs_debug + slot * gs_cap, else null */
+  /* split mode (few passing reads: fewer than half as many as resident CTAs): the tiles of a read are dealt over
+   * 2 or 4 CTAs, whose group sums meet in gs_rows + slot * gs_cap; tile_done[slot] counts the CTAs that are done
+   * (zeroed by K2 at the append) and the last one finds the change point */
+  uint16_t *gs_rows;
+  uint32_t *tile_done;
+  uint32_t no_split;        /* 1 = never split (A/B) */
 };
 
 /* One work item of the bit-parallel K3 = one TRC-pass read: what a CTA needs to walk its tiles, worked out once
@@ -501,6 +507,7 @@ __device__ __forceinline__ void tps_trc_decide(const TpsScanArgs &a, uint32_t n_
         it.slot = slot;
         it.reserved[0] = it.reserved[1] = 0u;
         a.items[atomicAdd(a.counters + 6, 1u)] = it;
+        a.tile_done[slot] = 0u;
       }
       if (a.want_rawcount && nW) {
         const unsigned long long elems = (unsigned long long)nW * n_patterns;
@@ -1337,6 +1344,7 @@ tps_window_bp_kernel(const TpsScanArgs a, const TpsPatTable pt) {
    * collects it at its end.  No step of the loop waits for global memory. */
   __shared__ TpsReadItem s_item[2];
   __shared__ uint32_t s_idx[3];
+  __shared__ uint32_t s_last;
   __shared__ uint32_t s_wt[2][NT / 32];
   __shared__ TpsCpShared s_cp;
   const uint32_t tid = threadIdx.x, q = threadIdx.x;
@@ -1360,7 +1368,8 @@ tps_window_bp_kernel(const TpsScanArgs a, const TpsPatTable pt) {
   uint2 *CP = UP + (NT + 2u);
   uint2 *SP = CP + (nb ? NT + 2u : 0u);
   uint32_t *brows = reinterpret_cast<uint32_t *>(SP + (size_t)P4 * stride);
-  uint16_t *gsum = reinterpret_cast<uint16_t *>(brows + nb * (NT + 1u)); /* group sums of the read in hand */
+  /* group sums of the read in hand (16-byte aligned: the split mode fills them with cp.async) */
+  uint16_t *gsum = reinterpret_cast<uint16_t *>((reinterpret_cast<uintptr_t>(brows + nb * (NT + 1u)) + 15u) & ~(uintptr_t)15u);
   tps_build_pattern_masks(pm, pt, K, tid, NT);
   const uint32_t n_items = a.counters[6];
   /* words that stay zero for the whole kernel: the pad word behind the oriented planes and the per-word tables,
@@ -1388,30 +1397,42 @@ tps_window_bp_kernel(const TpsScanArgs a, const TpsPatTable pt) {
     tps_prefetch_codes(a.pk, g0, tn, buf, tid);
   };
 
+  /* A work unit is a read, or -- when the batch holds at most twice (once) as many passing reads as the grid has
+   * CTAs, so that whole reads would leave CTAs idle or the last ones alone at the end -- every second (fourth) tile
+   * of a read: unit u = (read u / parts, tiles t = u % parts, + parts, ...). */
+  const uint32_t parts = a.no_split ? 1u : (n_items <= gridDim.x ? 4u : (n_items <= 2u * gridDim.x ? 2u : 1u));
+  const uint32_t n_units = n_items * parts;
+  bool have = false; /* the code words of this CTA's next tile are in raw[buf] */
   if (tid == 0) {
     const uint32_t base = atomicAdd(a.counters + 1, 2u);
     s_idx[0] = base; s_idx[1] = base + 1u;
-    if (base < n_items) s_item[0] = a.items[base];
+    if (base < n_units) s_item[0] = a.items[base / parts];
   }
   __syncthreads();
-  if (s_idx[0] < n_items) {
+  if (s_idx[0] < n_units) {
     uint32_t per0;
-    tiles_of(s_item[0].n_windows, per0);
-    prefetch_tile(s_item[0], per0, 0u, raw);
+    const uint32_t nt0 = tiles_of(s_item[0].n_windows, per0), part0 = s_idx[0] % parts;
+    if (part0 < nt0) {
+      prefetch_tile(s_item[0], per0, part0, raw);
+      have = true;
+    }
   }
   tps_cp_async_wait_all();
   __syncthreads();
   uint32_t buf = 0u; /* raw buffer that holds the tile in hand */
 
   for (uint32_t i = 0;; ++i) {
-    if (s_idx[i % 3u] >= n_items) break;
+    const uint32_t unit = s_idx[i % 3u];
+    if (unit >= n_units) break;
     const TpsReadItem it = s_item[i & 1u];
+    const uint32_t part = unit % parts;
     const uint32_t idx_next = s_idx[(i + 1u) % 3u];
     uint32_t idx_next2 = 0u;
-    if (tid == 0) { /* record of read i+1, index of read i+2 */
-      if (idx_next < n_items) {
-        tps_cp_async16(&s_item[(i + 1u) & 1u], a.items + idx_next);
-        tps_cp_async16(reinterpret_cast<uint8_t *>(&s_item[(i + 1u) & 1u]) + 16, reinterpret_cast<const uint8_t *>(a.items + idx_next) + 16);
+    if (tid == 0) { /* record of unit i+1, index of unit i+2 */
+      if (idx_next < n_units) {
+        const TpsReadItem *src = a.items + idx_next / parts;
+        tps_cp_async16(&s_item[(i + 1u) & 1u], src);
+        tps_cp_async16(reinterpret_cast<uint8_t *>(&s_item[(i + 1u) & 1u]) + 16, reinterpret_cast<const uint8_t *>(src) + 16);
       }
       idx_next2 = atomicAdd(a.counters + 1, 1u);
     }
@@ -1419,25 +1440,35 @@ tps_window_bp_kernel(const TpsScanArgs a, const TpsPatTable pt) {
     uint32_t per;
     const uint32_t ntiles = tiles_of(nW, per);
     const bool rev = it.rev != 0u;
+    if (part < ntiles && !have) { /* the unit before had nothing to prefetch for (an empty unit): fetch now */
+      prefetch_tile(it, per, part, raw + buf * TPS_K3N_RAW_WORDS);
+      tps_cp_async_wait_all();
+      __syncthreads();
+    }
+    have = false;
+    uint16_t *gdst = parts == 1u ? gsum : a.gs_rows + (size_t)it.slot * a.gs_cap;
 
-    for (uint32_t t = 0; t < ntiles; ++t, buf ^= 1u) {
+    for (uint32_t t = part; t < ntiles; t += parts, buf ^= 1u) {
       const uint32_t wlo = t * per, whi = wlo + per < nW ? wlo + per : nW;
       const uint32_t tb0 = wlo * s, tn = (whi - wlo - 1u) * s + W;
       const uint64_t g0 = rev ? it.g_edge - tb0 - tn : it.g_edge + tb0;
       const uint32_t *rawk = raw + buf * TPS_K3N_RAW_WORDS;
-      /* code words of the next tile: of this read, or tile 0 of the next read (its record arrived during an
-       * earlier tile; a one-tile read waits for it here) */
-      if (t + 1u < ntiles) {
-        prefetch_tile(it, per, t + 1u, raw + (buf ^ 1u) * TPS_K3N_RAW_WORDS);
-      } else if (idx_next < n_items) {
-        if (ntiles == 1u) {
+      /* code words of the next tile: of this unit, or the first tile of the next unit (its record was asked for at
+       * the start of this unit and has arrived by the end of any tile; a unit's first tile waits for it here) */
+      if (t + parts < ntiles) {
+        prefetch_tile(it, per, t + parts, raw + (buf ^ 1u) * TPS_K3N_RAW_WORDS);
+      } else if (idx_next < n_units) {
+        if (t == part) {
           tps_cp_async_wait_all();
           __syncthreads();
         }
         const TpsReadItem &nx = s_item[(i + 1u) & 1u];
         uint32_t pern;
-        tiles_of(nx.n_windows, pern);
-        prefetch_tile(nx, pern, 0u, raw + (buf ^ 1u) * TPS_K3N_RAW_WORDS);
+        const uint32_t ntn = tiles_of(nx.n_windows, pern), partn = idx_next % parts;
+        if (partn < ntn) {
+          prefetch_tile(nx, pern, partn, raw + (buf ^ 1u) * TPS_K3N_RAW_WORDS);
+          have = true;
+        }
       }
       const uint32_t phase = (uint32_t)(g0 & 15u);
       {
@@ -1517,7 +1548,7 @@ tps_window_bp_kernel(const TpsScanArgs a, const TpsPatTable pt) {
        * ls (a funnel shift over words q0, q0+1), so A(ls_i) - A(ls_0) is a popcount under a constant mask, the
        * same at the ends, and the five `present` bits of a count plane are one popcount under the mask gm */
       const uint32_t n_groups = (whi - wlo + 4u) / 5u;
-      uint16_t *gs = gsum + wlo / 5u;
+      uint16_t *gs = gdst + wlo / 5u;
       for (uint32_t gi = tid; gi < n_groups; gi += NT) {
         const uint32_t ls = 5u * gi * s; /* tile origin = start of window wlo */
         const uint32_t w0 = wlo + 5u * gi;
@@ -1554,16 +1585,31 @@ tps_window_bp_kernel(const TpsScanArgs a, const TpsPatTable pt) {
       tps_cp_async_wait_all();
       __syncthreads();
     }
-    if (a.gs_debug) /* test hook */
-      for (uint32_t j = tid; j < (nW + 4u) / 5u; j += NT) a.gs_debug[(size_t)it.slot * a.gs_cap + j] = gsum[j];
-    /* the read's change point, straight from its group sums in shared memory */
-    {
-      const int32_t best_b = tps_changepoint_block<5>(TpsCwShared16{gsum}, nW, s_cp, tid);
+    bool mine = true; /* this CTA finds the read's change point */
+    if (parts > 1u) { /* the CTA that completes the read collects the group sums of all its parts */
+      __syncthreads();
       if (tid == 0) {
-        tps_store_changepoint(a, it.read, best_b);
-        s_idx[(i + 2u) % 3u] = idx_next2;
+        __threadfence(); /* cumulative: the barrier ordered the CTA's stores before it */
+        s_last = atomicAdd(a.tile_done + it.slot, 1u) == parts - 1u;
+      }
+      __syncthreads();
+      mine = s_last != 0u;
+      if (mine) {
+        __threadfence();
+        for (uint32_t j = tid; j < ((nW + 4u) / 5u + 7u) >> 3; j += NT) tps_cp_async16(gsum + 8u * j, gdst + 8u * j);
+        tps_cp_async_wait_all();
+        __syncthreads();
       }
     }
+    if (mine) {
+      if (a.gs_debug) /* test hook */
+        for (uint32_t j = tid; j < (nW + 4u) / 5u; j += NT) a.gs_debug[(size_t)it.slot * a.gs_cap + j] = gsum[j];
+      /* the read's change point, straight from its group sums in shared memory */
+      const int32_t best_b = tps_changepoint_block<5>(TpsCwShared16{gsum}, nW, s_cp, tid);
+      if (tid == 0) tps_store_changepoint(a, it.read, best_b);
+    }
+    if (tid == 0) s_idx[(i + 2u) % 3u] = idx_next2;
+    tps_cp_async_wait_all(); /* the record of the next unit, if no tile of this unit waited for it */
     __syncthreads();
   }
 }

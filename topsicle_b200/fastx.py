@@ -54,6 +54,8 @@ def host_library() -> C.CDLL:
         lib.tps_fastx_format.argtypes = [vp]
         lib.tps_fastx_set_window.restype = None
         lib.tps_fastx_set_window.argtypes = [vp, C.c_uint64]
+        lib.tps_fastx_set_clip.restype = None
+        lib.tps_fastx_set_clip.argtypes = [vp, C.c_uint64]
         lib.tps_fastx_release.restype = None
         lib.tps_fastx_release.argtypes = [vp]
         lib.tps_fastx_last_error.restype = C.c_char_p
@@ -262,6 +264,11 @@ class FastxFile:
 
     def set_window(self, nbytes: int):
         self._lib.tps_fastx_set_window(self._h, nbytes)
+
+    def set_clip(self, clip_bases: int):
+        """A record longer than a whole batch is delivered as its first + last `clip_bases` bases (a batch of its
+        own) instead of ending the file with error -4; see include/topsicle_host.h."""
+        self._lib.tps_fastx_set_clip(self._h, int(clip_bases))
 
     def next_batch(self, bases: np.ndarray, offsets: np.ndarray, max_reads: int | None = None,
                    max_bases: int | None = None, recs: np.ndarray | None = None) -> Batch | None:

@@ -551,6 +551,9 @@ class Scanner:
         self.ends_first = bool(ends_first)
         self.ends_raw_bytes = int(ends_raw_bytes)        # file text per ends batch
         self.end_len = max(int(c.no_bp) for c in cfgs)   # head / tail bases every config needs
+        # whole-read mode, a record longer than a batch: the ends the reader keeps of it hold every base any config
+        # looks at (step 1: no_bp; step 2: maxlengthtelo from either end) and stay longer than min_seq_length
+        self.clip_bases = max(max(int(c.no_bp), int(c.maxlengthtelo), int(c.min_seq_length) // 2 + 1) for c in cfgs)
         if not max_pass_reads:
             max_pass_reads = max(1024, max_batch_reads // 8)
         if not rawcount_capacity and any(c.want_rawcount for c in cfgs):
@@ -691,6 +694,9 @@ class Scanner:
                         job.fx = fastx.FastxFile(job.path, threads=fx_threads)
                     except (fastx.FastxError, OSError) as e:
                         parse_failed(job, e)
+                    if job.fx is not None and not self.ends_first:
+                        # a record longer than a batch (a chromosome): the scan reads a bounded stretch of either end
+                        job.fx.set_clip(self.clip_bases)
                     job.stats.timing["open"] = time.perf_counter() - t
                     seq = 0
                     if job.fx is not None:

@@ -385,7 +385,7 @@ def test_records_text_equals_record_text(tmp_path):
 
 
 # ------------------------------------------------------------------ plain gzip: parallel inflate (csrc/tps_pgz.c)
-def _synthetic_fastq(n_reads=2500, seed=5):
+def _synthetic_fastq(n_reads=1000, seed=5):
     """FASTQ text with realistic (poorly compressible) quality lines."""
     from topsicle_b200 import synth
     bases, off, _ = synth.generate(synth.CONFIGS[2], 0, n_reads)
@@ -434,13 +434,59 @@ def test_plain_gzip_parallel_inflate_equals_zlib(tmp_path, level):
     want, st0 = _read_all(str(plain))
     assert st0["text_bytes"] == 0
     got, st = _read_all(str(gz), TPS_PGZ_PIECE=1 << 18)
-    assert got == want and len(got) == 2500
+    assert got == want and len(got) == 1000
     assert st["text_bytes"] == len(text) and st["members"] == 1 and st["chain_breaks"] == 0
     assert st["parallel_text_bytes"] > 0.7 * len(text) and st["segments"] > 3 * st["stretches"]
     zl, st_z = _read_all(str(gz), TPS_FX_NO_PGZ=1)
     assert zl == want and st_z["text_bytes"] == 0
     one, st1 = _read_all(str(gz), threads=1)
     assert one == want and st1["parallel_text_bytes"] == 0
+    # the plain decoder (one symbol per table lookup) and zlib's crc32 in place of the folded one
+    slow, st_s = _read_all(str(gz), TPS_PGZ_PIECE=1 << 18, TPS_PGZ_FAST=0, TPS_PGZ_CLMUL=0)
+    assert slow == want and st_s["text_bytes"] == len(text)
+
+
+def test_plain_gzip_long_codes_and_fixed_blocks(tmp_path):
+    """Streams that leave the decoder's direct tables: a skewed 94-letter quality alphabet (literal codes longer
+    than 12 bits, the general path inside the fast loop), long repeats (length 258, distance codes with 13 extra
+    bits), repeats at distances below 8, and a file small enough for fixed-Huffman blocks."""
+    import gzip
+    rng = np.random.default_rng(41)
+    p_q = 0.82 ** np.arange(94)
+    p_q /= p_q.sum()
+    recs = []
+    for i in range(1500):
+        L = int(rng.integers(200, 9000))
+        kind = i % 5
+        if kind == 0:
+            seq = bytes(rng.choice(np.frombuffer(b"ACGT", np.uint8), L))
+        elif kind == 1:
+            seq = (b"TTAGGG" * (L // 6 + 1))[:L]
+        elif kind == 2:
+            seq = (b"A" * L)
+        elif kind == 3:
+            seq = (b"AC" * (L // 2 + 1))[:L]
+        else:
+            seq = bytes(rng.choice(np.frombuffer(b"ACGTNacgtn", np.uint8), L))
+        qual = bytes((33 + rng.choice(94, L, p=p_q)).astype(np.uint8)).replace(b"@", b"A")
+        recs.append(b"@q%d\n%s\n+\n%s\n" % (i, seq, qual))
+    text = b"".join(recs)
+    plain = tmp_path / "r.fastq"
+    plain.write_bytes(text)
+    want, _ = _read_all(str(plain))
+    for level in (1, 6, 9):
+        gz = tmp_path / f"r{level}.fastq.gz"
+        gz.write_bytes(gzip.compress(text, compresslevel=level))
+        got, st = _read_all(str(gz), TPS_PGZ_PIECE=1 << 17)
+        assert got == want and st["text_bytes"] == len(text) and st["chain_breaks"] == 0, level
+        assert st["parallel_text_bytes"] > 0.5 * len(text)
+        slow, _ = _read_all(str(gz), TPS_PGZ_PIECE=1 << 17, TPS_PGZ_FAST=0)
+        assert slow == want
+    tiny = b"@t1\nACGTACGTAC\n+\nIIIIIIIIII\n@t2\nTTAGGGTTAGGG\n+\nIIIIIIIIIIII\n"
+    tz = tmp_path / "tiny.fastq.gz"
+    tz.write_bytes(gzip.compress(tiny, 6))
+    got, _ = _read_all(str(tz))
+    assert [(r[0], r[1]) for r in got] == [("t1", b"ACGTACGTAC"), ("t2", b"TTAGGGTTAGGG")]
 
 
 def test_plain_gzip_members_stored_blocks_and_damage(tmp_path):

@@ -42,6 +42,125 @@ static double pgz_now(void) {
   return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
 }
 
+/* ---- CRC-32 (gzip polynomial) by carry-less multiplication: folds 64 bytes per step (Gopal et al., "Fast CRC
+ * computation for generic polynomials using PCLMULQDQ", Intel 2009) instead of zlib's table walk, which at about
+ * 2 GB/s per thread was a third of the time of the pass that turns symbols into bytes.  Checked against zlib on
+ * first use; zlib's crc32 is used when the CPU lacks the instruction or the check fails. */
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+#define PGZ_HAVE_CLMUL 1
+__attribute__((target("pclmul,sse4.1"))) static uint32_t crc32_clmul_raw(const uint8_t *buf, size_t len, uint32_t crc) {
+  /* len >= 64 and a multiple of 16; crc = the register (bit-inverted CRC) on both sides */
+  static const uint64_t __attribute__((aligned(16))) k1k2[2] = {0x0154442bd4ull, 0x01c6e41596ull};
+  static const uint64_t __attribute__((aligned(16))) k3k4[2] = {0x01751997d0ull, 0x00ccaa009eull};
+  static const uint64_t __attribute__((aligned(16))) k5k0[2] = {0x0163cd6124ull, 0x0000000000ull};
+  static const uint64_t __attribute__((aligned(16))) poly[2] = {0x01db710641ull, 0x01f7011641ull};
+  __m128i x0, x1, x2, x3, x4, x5, x6, x7, x8, y5, y6, y7, y8;
+  x1 = _mm_loadu_si128((const __m128i *)(buf + 0x00));
+  x2 = _mm_loadu_si128((const __m128i *)(buf + 0x10));
+  x3 = _mm_loadu_si128((const __m128i *)(buf + 0x20));
+  x4 = _mm_loadu_si128((const __m128i *)(buf + 0x30));
+  x1 = _mm_xor_si128(x1, _mm_cvtsi32_si128((int)crc));
+  x0 = _mm_load_si128((const __m128i *)k1k2);
+  buf += 64;
+  len -= 64;
+  while (len >= 64) { /* four independent 128-bit lanes, each folded over 512 bits */
+    x5 = _mm_clmulepi64_si128(x1, x0, 0x00);
+    x6 = _mm_clmulepi64_si128(x2, x0, 0x00);
+    x7 = _mm_clmulepi64_si128(x3, x0, 0x00);
+    x8 = _mm_clmulepi64_si128(x4, x0, 0x00);
+    x1 = _mm_clmulepi64_si128(x1, x0, 0x11);
+    x2 = _mm_clmulepi64_si128(x2, x0, 0x11);
+    x3 = _mm_clmulepi64_si128(x3, x0, 0x11);
+    x4 = _mm_clmulepi64_si128(x4, x0, 0x11);
+    y5 = _mm_loadu_si128((const __m128i *)(buf + 0x00));
+    y6 = _mm_loadu_si128((const __m128i *)(buf + 0x10));
+    y7 = _mm_loadu_si128((const __m128i *)(buf + 0x20));
+    y8 = _mm_loadu_si128((const __m128i *)(buf + 0x30));
+    x1 = _mm_xor_si128(_mm_xor_si128(x1, x5), y5);
+    x2 = _mm_xor_si128(_mm_xor_si128(x2, x6), y6);
+    x3 = _mm_xor_si128(_mm_xor_si128(x3, x7), y7);
+    x4 = _mm_xor_si128(_mm_xor_si128(x4, x8), y8);
+    buf += 64;
+    len -= 64;
+  }
+  x0 = _mm_load_si128((const __m128i *)k3k4); /* the four lanes into one */
+  x5 = _mm_clmulepi64_si128(x1, x0, 0x00);
+  x1 = _mm_clmulepi64_si128(x1, x0, 0x11);
+  x1 = _mm_xor_si128(_mm_xor_si128(x1, x2), x5);
+  x5 = _mm_clmulepi64_si128(x1, x0, 0x00);
+  x1 = _mm_clmulepi64_si128(x1, x0, 0x11);
+  x1 = _mm_xor_si128(_mm_xor_si128(x1, x3), x5);
+  x5 = _mm_clmulepi64_si128(x1, x0, 0x00);
+  x1 = _mm_clmulepi64_si128(x1, x0, 0x11);
+  x1 = _mm_xor_si128(_mm_xor_si128(x1, x4), x5);
+  while (len >= 16) {
+    x2 = _mm_loadu_si128((const __m128i *)buf);
+    x5 = _mm_clmulepi64_si128(x1, x0, 0x00);
+    x1 = _mm_clmulepi64_si128(x1, x0, 0x11);
+    x1 = _mm_xor_si128(_mm_xor_si128(x1, x2), x5);
+    buf += 16;
+    len -= 16;
+  }
+  x2 = _mm_clmulepi64_si128(x1, x0, 0x10); /* 128 -> 64 bits */
+  x3 = _mm_setr_epi32(~0, 0, ~0, 0);
+  x1 = _mm_srli_si128(x1, 8);
+  x1 = _mm_xor_si128(x1, x2);
+  x0 = _mm_loadl_epi64((const __m128i *)k5k0);
+  x2 = _mm_srli_si128(x1, 4);
+  x1 = _mm_and_si128(x1, x3);
+  x1 = _mm_clmulepi64_si128(x1, x0, 0x00);
+  x1 = _mm_xor_si128(x1, x2);
+  x0 = _mm_load_si128((const __m128i *)poly); /* Barrett reduction to 32 bits */
+  x2 = _mm_and_si128(x1, x3);
+  x2 = _mm_clmulepi64_si128(x2, x0, 0x10);
+  x2 = _mm_and_si128(x2, x3);
+  x2 = _mm_clmulepi64_si128(x2, x0, 0x00);
+  x1 = _mm_xor_si128(x1, x2);
+  return (uint32_t)_mm_extract_epi32(x1, 1);
+}
+#endif
+
+static int pgz_clmul_ok = -1; /* -1 not probed yet */
+
+static uint32_t pgz_crc32_zlib(uint32_t c, const uint8_t *p, uint64_t n) {
+  while (n) {
+    const uint64_t step = n > (1u << 30) ? (1u << 30) : n;
+    c = (uint32_t)crc32(c, p, (uInt)step);
+    p += step;
+    n -= step;
+  }
+  return c;
+}
+
+/* crc32(c, p, n) of zlib, faster */
+static uint32_t pgz_crc32(uint32_t c, const uint8_t *p, uint64_t n) {
+#ifdef PGZ_HAVE_CLMUL
+  if (pgz_clmul_ok < 0) { /* probe: CPU support and agreement with zlib on lengths around the folding steps */
+    const char *env = getenv("TPS_PGZ_CLMUL"); /* 0 = zlib's crc32 (A/B, tests) */
+    int ok = !(env && atoi(env) == 0) && __builtin_cpu_supports("pclmul") && __builtin_cpu_supports("sse4.1");
+    if (ok) {
+      uint8_t t[64 * 5 + 48];
+      uint32_t x = 12345u;
+      for (size_t i = 0; i < sizeof(t); ++i) {
+        x = x * 1664525u + 1013904223u;
+        t[i] = (uint8_t)(x >> 24);
+      }
+      for (size_t len = 64; len <= sizeof(t) && ok; len += 16)
+        ok = ~crc32_clmul_raw(t, len, ~0x89abcdefu) == (uint32_t)crc32(0x89abcdefu, t, (uInt)len);
+    }
+    pgz_clmul_ok = ok;
+  }
+  if (pgz_clmul_ok && n >= 64) {
+    const uint64_t body = n & ~(uint64_t)15;
+    c = ~crc32_clmul_raw(p, body, ~c);
+    p += body;
+    n -= body;
+  }
+#endif
+  return pgz_crc32_zlib(c, p, n);
+}
+
 #define PGZ_WSIZE 32768u
 #define LIT_TB 11 /* primary table bits, literal / length code */
 #define DST_TB 8  /* primary table bits, distance code */
@@ -196,11 +315,85 @@ static const uint16_t DST_BASE[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 6
 static const uint8_t DST_EXTRA[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
 static const uint8_t CL_ORDER[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
+#define FAST_TB 12  /* index bits of the literal-run table */
+#define DFAST_TB 10 /* index bits of the direct distance table */
+#define PGZ_F_LEN 0x40u
+#define PGZ_F_EOB 0x80u
+
 typedef struct blockhdr {
   int final, type;
   huff lit, dst;
   uint32_t stored_len;
+  /* Literal runs (build_fast): the next FAST_TB bits -> up to three literals whose codes fit them whole.
+   * entry: bits 0-3 code bits consumed | bits 4-5 literals (0 = not a literal run: take the general path) |
+   * bits 8-15, 16-23, 24-31 the literals.  FASTQ text is mostly literals -- bases at 2-3 bits, quality characters at
+   * 5-6 -- and a one-symbol-per-lookup decoder is bound by the lookup's latency, so two or three per lookup nearly
+   * double or triple its rate.
+   * A length code that fits is there as well: bit 6 set | bits 0-3 code bits | bits 8-10 extra bits | bits 16-24
+   * base length; the end of block: bit 7 set | bits 0-3 code bits. */
+  uint32_t fast[1u << FAST_TB];
+  /* distance codes, direct: bits 0-3 code bits (0 = code longer than DFAST_TB, unused or invalid: general path) |
+   * bits 8-11 extra bits | bits 16-30 base distance */
+  uint32_t dfast[1u << DFAST_TB];
 } blockhdr;
+
+/* The literal-run table of a block with Huffman codes; needs h->lit. */
+static void build_fast(blockhdr *h) {
+  const uint32_t *tab = h->lit.tab;
+  const uint32_t pmask = (1u << LIT_TB) - 1u;
+  for (uint32_t i = 0; i < (1u << FAST_TB); ++i) {
+    uint32_t bits = 0, n = 0, pay = 0, j = i, room = FAST_TB;
+    while (n < 3 && room) {
+      const uint32_t e = tab[j & pmask];
+      const uint32_t l = e & 255u;
+      /* the code must be fully inside the bits that are known; long codes, invalid codes, lengths and the end of
+       * block go the general way */
+      if (((e >> 8) & 1u) || l == 0 || l > room || (e >> 16) >= 256u) break;
+      pay |= (e >> 16) << (8u * n);
+      ++n;
+      bits += l;
+      room -= l;
+      j >>= l;
+    }
+    if (n) {
+      h->fast[i] = bits | (n << 4) | (pay << 8);
+      continue;
+    }
+    const uint32_t e = tab[i & pmask], l = e & 255u, sym = e >> 16;
+    uint32_t f = 0u;
+    if (!((e >> 8) & 1u) && l != 0 && l <= FAST_TB && sym >= 256u) {
+      if (sym == 256u) f = PGZ_F_EOB | l;
+      else if (sym - 257u < 29u) f = PGZ_F_LEN | l | ((uint32_t)LEN_EXTRA[sym - 257u] << 8) | ((uint32_t)LEN_BASE[sym - 257u] << 16);
+    }
+    h->fast[i] = f;
+  }
+  const uint32_t *dt = h->dst.tab;
+  for (uint32_t i = 0; i < (1u << DFAST_TB); ++i) {
+    const uint32_t e = dt[i & ((1u << DST_TB) - 1u)];
+    uint32_t l = e & 255u, sym = e >> 16, ok = 1;
+    if ((e >> 8) & 1u) { /* subtable: the code is DST_TB + its own bits long */
+      const uint32_t sb = l;
+      if (DST_TB + sb <= DFAST_TB) {
+        const uint32_t e2 = dt[sym + ((i >> DST_TB) & ((1u << sb) - 1u))];
+        l = (e2 & 255u) ? DST_TB + (e2 & 255u) : 0u;
+        sym = e2 >> 16;
+      } else {
+        /* the subtable index is only partly inside the DFAST_TB bits: the entry is right if the code it selects
+         * is short enough to lie inside them */
+        const uint32_t known = DFAST_TB - DST_TB;
+        const uint32_t e2 = dt[sym + ((i >> DST_TB) & ((1u << known) - 1u))];
+        if ((e2 & 255u) && (e2 & 255u) <= known) {
+          l = DST_TB + (e2 & 255u);
+          sym = e2 >> 16;
+        } else {
+          ok = 0;
+        }
+      }
+    }
+    h->dfast[i] = (ok && l != 0 && l <= DFAST_TB && sym < 30u)
+                      ? (l | ((uint32_t)DST_EXTRA[sym] << 8) | ((uint32_t)DST_BASE[sym] << 16)) : 0u;
+  }
+}
 
 /* Parse one block header at the reader's position.  0 ok, -1 invalid / out of data. */
 static int read_block_header(bitrd *b, blockhdr *h) {
@@ -391,8 +584,125 @@ static inline __attribute__((always_inline)) int decode_block_impl(bitrd *b, con
   }
 }
 
-static int decode_block(bitrd *b, const blockhdr *h, seg *s, const uint16_t *win) {
+/* The same decode for a Huffman block with the literal-run table, on local copies of the reader and the output
+ * cursor; hands over to decode_block_impl near the end of the input and of the symbol buffer (any symbol boundary
+ * is a valid place to continue).  0 ok, <0 error. */
+static int decode_block_fast(bitrd *b, const blockhdr *h, seg *s, const uint16_t *win) {
+  if ((uint64_t)(b->end - b->base) < 64 || s->cap < 1024) return decode_block_impl(b, h, s, win, 0, 0);
+  bitrd lb = *b;
+  const uint8_t *const safe = lb.end - 32; /* three 8-byte refills of one iteration stay inside the input */
+  uint16_t *o = s->out + s->n;
+  uint16_t *const olim = s->out + s->cap - 336;
+  const uint32_t *const fast = h->fast;
+  const uint32_t *const dfast = h->dfast;
+  int rc = 1; /* 1 = hand over */
+#define PGZ_REFILL()                 \
+  do {                               \
+    uint64_t w_;                     \
+    memcpy(&w_, lb.p, 8);            \
+    lb.buf |= w_ << lb.cnt;          \
+    lb.p += (63 - lb.cnt) >> 3;      \
+    lb.cnt |= 56;                    \
+  } while (0)
+#define PGZ_EMIT(e)                                                                                        \
+  do {                                                                                                     \
+    const uint64_t x_ = (e) >> 8;                                                                          \
+    const uint64_t v_ = (x_ & 0xFFu) | ((x_ & 0xFF00u) << 8) | ((x_ & 0xFF0000u) << 16);                   \
+    memcpy(o, &v_, 8);                                                                                     \
+    o += ((e) >> 4) & 3u;                                                                                  \
+    lb.buf >>= (e) & 15u;                                                                                  \
+    lb.cnt -= (e) & 15u;                                                                                   \
+  } while (0)
+  while (lb.p <= safe && o < olim) {
+    PGZ_REFILL();
+    /* up to three literal runs from one refill, then whatever follows still finds 20 bits */
+    uint32_t e = fast[lb.buf & ((1u << FAST_TB) - 1u)];
+    if (e & 0x30u) {
+      PGZ_EMIT(e);
+      e = fast[lb.buf & ((1u << FAST_TB) - 1u)];
+      if (e & 0x30u) {
+        PGZ_EMIT(e);
+        e = fast[lb.buf & ((1u << FAST_TB) - 1u)];
+        if (e & 0x30u) {
+          PGZ_EMIT(e);
+          e = fast[lb.buf & ((1u << FAST_TB) - 1u)];
+          if (e & 0x30u) {
+            PGZ_EMIT(e);
+            continue;
+          }
+        }
+      }
+    }
+    uint32_t len;
+    if (e & PGZ_F_LEN) { /* length code and its extra bits: <= 12 + 5 of the >= 20 bits at hand */
+      const uint32_t cb = e & 15u, xb = (e >> 8) & 7u;
+      len = (e >> 16) + ((uint32_t)(lb.buf >> cb) & ((1u << xb) - 1u));
+      lb.buf >>= cb + xb;
+      lb.cnt -= cb + xb;
+    } else if (e & PGZ_F_EOB) {
+      lb.buf >>= e & 15u;
+      lb.cnt -= e & 15u;
+      rc = 0;
+      break;
+    } else { /* a code longer than FAST_TB bits, or an invalid one */
+      int32_t sym = huff_sym_tb(&h->lit, &lb, LIT_TB);
+      if (sym < 0) { rc = -1; break; }
+      if (sym < 256) {
+        *o++ = (uint16_t)sym;
+        continue;
+      }
+      if (sym == 256) { rc = 0; break; }
+      sym -= 257;
+      if (sym >= 29) { rc = -1; break; }
+      PGZ_REFILL();
+      len = LEN_BASE[sym] + br_bits(&lb, LEN_EXTRA[sym]);
+    }
+    PGZ_REFILL();
+    uint32_t dist;
+    const uint32_t d = dfast[lb.buf & ((1u << DFAST_TB) - 1u)];
+    if (__builtin_expect(d != 0u, 1)) { /* <= 10 + 13 bits */
+      const uint32_t cb = d & 15u, xb = (d >> 8) & 15u;
+      dist = (d >> 16) + ((uint32_t)(lb.buf >> cb) & ((1u << xb) - 1u));
+      lb.buf >>= cb + xb;
+      lb.cnt -= cb + xb;
+    } else {
+      const int32_t ds = huff_sym_tb(&h->dst, &lb, DST_TB);
+      if (ds < 0 || ds >= 30) { rc = -1; break; }
+      dist = DST_BASE[ds] + br_bits(&lb, DST_EXTRA[ds]); /* <= 15 + 13 of 56 bits */
+    }
+    const uint64_t n = (uint64_t)(o - s->out);
+    if (__builtin_expect(dist <= n, 1)) {
+      const uint16_t *f = o - dist;
+      if (__builtin_expect(dist >= 8, 1)) { /* eight symbols at a time; writes up to 15 past the match (slack above) */
+        memcpy(o, f, 16);
+        memcpy(o + 8, f + 8, 16);
+        for (uint32_t k = 16; k < len; k += 8) memcpy(o + k, f + k, 16);
+      } else {
+        for (uint32_t k = 0; k < len; ++k) o[k] = f[k];
+      }
+    } else { /* reaches into the window before the segment */
+      if (dist > n + PGZ_WSIZE) { rc = -1; break; }
+      for (uint32_t k = 0; k < len; ++k) {
+        const int64_t at = (int64_t)n + k - dist;
+        o[k] = at >= 0 ? s->out[at] : win[(int64_t)PGZ_WSIZE + at];
+      }
+    }
+    o += len;
+  }
+#undef PGZ_EMIT
+#undef PGZ_REFILL
+  *b = lb;
+  s->n = (uint64_t)(o - s->out);
+  if (rc <= 0) return rc;
   return decode_block_impl(b, h, s, win, 0, 0);
+}
+
+static int pgz_fast_on = 1; /* TPS_PGZ_FAST=0 (read by tps_pgz_open): one symbol per lookup everywhere (A/B, tests) */
+
+static int decode_block(bitrd *b, blockhdr *h, seg *s, const uint16_t *win) {
+  if (h->type == 0 || !pgz_fast_on) return decode_block_impl(b, h, s, win, 0, 0);
+  build_fast(h);
+  return decode_block_fast(b, h, s, win);
 }
 static int decode_block_text(bitrd *b, const blockhdr *h, seg *s, const uint16_t *win, uint64_t max_out) {
   return decode_block_impl(b, h, s, win, 1, max_out);
@@ -521,6 +831,15 @@ tps_pgz *tps_pgz_open(const uint8_t *zmap, uint64_t zlen, int threads) {
   g->pos_bit = d * 8;
   g->in_member = 1;
   g->crc = (uint32_t)crc32(0L, Z_NULL, 0);
+  pgz_clmul_ok = -1; /* probed here, on one thread, under this open's environment */
+  (void)pgz_crc32(0u, zmap, 0);
+  {
+    const char *f = getenv("TPS_PGZ_FAST");
+    pgz_fast_on = !(f && atoi(f) == 0);
+  }
+  if (getenv("TPS_PGZ_DEBUG"))
+    fprintf(stderr, "[pgz] open: %d threads, literal-run tables %s, crc32 by %s\n", g->threads, pgz_fast_on ? "on" : "off",
+            pgz_clmul_ok ? "pclmulqdq" : "zlib");
   g->ratio = 4.5;
   g->piece = 4u << 20;
   const char *e = getenv("TPS_PGZ_PIECE"); /* compressed bytes per thread and stretch (tests, tuning) */
@@ -692,41 +1011,36 @@ static int64_t next_stretch(tps_pgz *g, uint8_t *dst, uint64_t cap) {
       for (int i = 0; i < good; ++i) {
         const seg *s = &sg[i];
         uint8_t *o = target + offs[i];
-        if (!s->symbolic) {
-          for (uint64_t k = 0; k < s->n; ++k) o[k] = (uint8_t)s->out[k];
-        } else {
-          const uint8_t *w = wins + (size_t)i * PGZ_WSIZE;
-          const uint32_t wl = wlens[i], miss = PGZ_WSIZE - wl;
-          uint64_t k = 0;
-          while (k < s->n) {
-            /* past the first stretch of a piece nearly everything is resolved: whole runs of 32 narrow at once */
-            if (k + 32 <= s->n) {
+        const uint8_t *w = wins + (size_t)i * PGZ_WSIZE;
+        const uint32_t wl = wlens[i], miss = PGZ_WSIZE - wl;
+        uint32_t c = (uint32_t)crc32(0L, Z_NULL, 0);
+        /* a chunk of symbols to bytes, then its CRC while the bytes are still in the cache */
+        for (uint64_t k0 = 0; k0 < s->n; k0 += 1u << 15) {
+          const uint64_t k1 = k0 + (1u << 15) < s->n ? k0 + (1u << 15) : s->n;
+          uint64_t k = k0;
+          while (k < k1) {
+            /* past the first stretch of a piece nearly everything is resolved: whole runs of 64 narrow at once */
+            if (k + 64 <= k1) {
               uint16_t any = 0;
-              for (int j = 0; j < 32; ++j) any |= s->out[k + j];
+              for (int j = 0; j < 64; ++j) any |= s->out[k + j];
               if (any < 256) {
-                for (int j = 0; j < 32; ++j) o[k + j] = (uint8_t)s->out[k + j];
-                k += 32;
+                for (int j = 0; j < 64; ++j) o[k + j] = (uint8_t)s->out[k + j];
+                k += 64;
                 continue;
               }
             }
-            const uint64_t ke = k + 32 <= s->n ? k + 32 : s->n;
+            const uint64_t ke = k + 64 <= k1 ? k + 64 : k1;
             for (; k < ke; ++k) {
               const uint16_t v = s->out[k];
               if (v < 256) o[k] = (uint8_t)v;
-              else if (v - 256u >= miss) o[k] = w[v - 256u - miss];
+              else if (s->symbolic && v - 256u >= miss) o[k] = w[v - 256u - miss];
               else {
                 o[k] = 0;
                 bad_ref = 1; /* a reference before the start of the member: corrupt */
               }
             }
           }
-        }
-        uint64_t done = 0;
-        uint32_t c = (uint32_t)crc32(0L, Z_NULL, 0);
-        while (done < s->n) {
-          const uint64_t step = s->n - done > (1u << 30) ? (1u << 30) : s->n - done;
-          c = (uint32_t)crc32(c, o + done, (uInt)step);
-          done += step;
+          c = pgz_crc32(c, o + k0, k1 - k0);
         }
         sg[i].crc = c;
       }

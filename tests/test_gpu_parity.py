@@ -9,6 +9,7 @@ import pytest
 
 from oracle import topsicle_oracle as orc
 from tests.conftest import GOLD, load_json
+from tests.test_gpu_random_sweep import make_reads
 
 pytestmark = pytest.mark.gpu
 
@@ -430,6 +431,41 @@ def test_kernel_and_stream_variants_agree(eng, monkeypatch):
         else:
             for a_, b_ in zip(cur, ref):
                 assert a_ == b_, env
+
+
+@pytest.mark.parametrize("motif,k", [("CCCTAA", 4), ("TTAGGG", 4), ("CCCTAA", 3), ("CCCTAAA", 5), ("TTTAGGG", 5),
+                                     ("AAACCCT", 5), ("TTTAGGG", 6), ("TTTTAGGG", 6), ("CCCTAAAA", 8), ("CCTAA", 3)])
+def test_k2_with_literals_in_the_instructions_equals_table_k2(eng, edge_records, demo_records, monkeypatch, motif, k):
+    """Complement-paired literal sets of 5..8 literals without self-overlap run tps_trc_const_kernel<K, U> (masks as
+    constant operands, unrolled); TPS_K2_CONST=0 keeps tps_trc_reg_kernel<K>.  Same rows, whole reads and ends
+    batches, and both equal the oracle's step 1 (allsteps.py:175-198)."""
+    pats = orc.patterns_to_search(motif, k)
+    rng = np.random.default_rng(len(motif) * 31 + k)
+    reads = [sq for _, sq in edge_records] + [sq for _, sq in demo_records[:30]] + make_reads(rng, motif, 120, 20000)
+    out = []
+    for const in (True, False):
+        if const:
+            monkeypatch.delenv("TPS_K2_CONST", raising=False)
+        else:
+            monkeypatch.setenv("TPS_K2_CONST", "0")
+        with _ctx(eng, pats, len_telopattern=len(motif), min_seq_length=0, cutoff=0.3, slide=len(motif)) as ctx:
+            bordered = any(p[:i] == p[-i:] for p in pats for i in range(1, len(p)))
+            eligible = not bordered and 5 <= len(pats) // 2 <= 8 and 3 <= k <= 8
+            assert ctx.debug_info()["k2_kernel"] == ("const" if const and eligible else "reg")
+            rows, _ = ctx.scan_reads(reads)
+            out.append(rows)
+    assert out[0].tobytes() == out[1].tobytes()
+    n_pass = 0
+    for i, seq in enumerate(reads):
+        if len(seq) == 0:
+            continue
+        tail, bi, cnt, ms, me, _, _ = orc.trc_read(seq, pats, len(motif), 1000)
+        row = out[0][i]
+        got = (eng.TAIL_NAMES[row["tail"]], int(row["best_pattern"]), int(row["match_count"]), int(row["head_max"]),
+               int(row["tail_max"]))
+        assert got == (tail, bi, cnt, ms, me), (motif, k, i)
+        n_pass += row["status"] >= eng.ST_PASS
+    assert n_pass > 10
 
 
 def _rows_without_offsets(eng, rows):

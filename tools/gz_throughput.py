@@ -29,7 +29,7 @@ def read_file(path, threads, env=None):
     old = {k: os.environ.get(k) for k in (env or {})}
     os.environ.update(env or {})
     try:
-        h = hashlib.md5()
+        h, hl = hashlib.md5(), hashlib.md5()
         t0 = time.perf_counter()
         n_reads = n_bases = 0
         with fastx.FastxFile(path, threads=threads) as fx:
@@ -53,11 +53,12 @@ def read_file(path, threads, env=None):
                 b = fx.next_batch(bases, offsets)
                 if b is None:
                     break
+                # independent of where the reader cut its batches: all bases back to back, all read lengths
                 h.update(bases[:int(offsets[b.n_reads])].tobytes())
-                h.update(offsets[:b.n_reads + 1].tobytes())
+                hl.update(np.diff(offsets[:b.n_reads + 1]).astype(np.uint64).tobytes())
                 b.release()
         return dict(seconds=round(dt, 3), reads=n_reads, gbases=round(n_bases / 1e9, 3),
-                    gbases_per_s=round(n_bases / dt / 1e9, 3), md5=h.hexdigest(), inflate=st)
+                    gbases_per_s=round(n_bases / dt / 1e9, 3), md5=h.hexdigest() + hl.hexdigest(), inflate=st)
     finally:
         for k, v in old.items():
             if v is None:

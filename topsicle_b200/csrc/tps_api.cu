@@ -72,6 +72,10 @@ struct tps_ctx {
   int kt = 0; /* template K of the K2/K3 instantiation in use (0 = generic) */
   void (*k2_fn)(const TpsScanArgs, const TpsPatTable) = nullptr;
   void (*k2r_fn)(const TpsScanArgs, const TpsPatTable) = nullptr; /* register-staged K2 (no_bp <= 1000, P <= 32) */
+  /* K2 with the literal set in the instruction stream (constant-bank masks, unrolled): complement-paired sets of
+   * 5..8 literals of one length 3..8 without self-overlap -- every default CLI run */
+  void (*k2c_fn)(const TpsScanArgs, const TpsPairMasks) = nullptr;
+  TpsPairMasks k2c_masks;
   bool k2_reg = false;
   uint32_t k2r_smem = 0;
   void (*k3_fn)(const TpsScanArgs, const TpsPatTable) = nullptr;
@@ -348,6 +352,28 @@ int tps_create(tps_ctx **out, int device, const tps_params *params) {
   ctx->k2_smem = (pm_words + TPS_K2_WARPS * (3 * ctx->k2_lin_words + pt.n_bordered * ctx->k2_nq_max + TPS_MAX_PATTERNS)) * 4;
   ctx->k2_reg = p.no_bp <= 1000 && pt.n <= 32 && !getenv("TPS_K2_SMEM_PATH");
   ctx->k2r_smem = (pm_words + TPS_K2R_WARPS * pt.n_bordered * 32) * 4;
+  {
+    const char *e = getenv("TPS_K2_CONST"); /* 0 = always the table-driven K2 (A/B, tests) */
+    const uint32_t U = pt.n / 2;
+    if (ctx->k2_reg && pt.paired && pt.n_bordered == 0 && !(e && atoi(e) == 0)) {
+#define TPS_PICK_U(KK, UU) case UU: ctx->k2c_fn = tps_trc_const_kernel<KK, UU>; break;
+#define TPS_PICK_K(KK) case KK: switch (U) { TPS_PICK_U(KK, 5) TPS_PICK_U(KK, 6) TPS_PICK_U(KK, 7) TPS_PICK_U(KK, 8) default: break; } break;
+      switch (ctx->kt) {
+        TPS_PICK_K(3) TPS_PICK_K(4) TPS_PICK_K(5) TPS_PICK_K(6) TPS_PICK_K(7) TPS_PICK_K(8)
+        default: break;
+      }
+#undef TPS_PICK_K
+#undef TPS_PICK_U
+    }
+    if (ctx->k2c_fn) {
+      memset(&ctx->k2c_masks, 0, sizeof(ctx->k2c_masks));
+      for (uint32_t q = 0; q < U; ++q)
+        for (int j = 0; j < ctx->kt; ++j) {
+          ctx->k2c_masks.x[q][j] = 0u - ((pt.lo[q] >> j) & 1u);
+          ctx->k2c_masks.y[q][j] = 0u - ((pt.hi[q] >> j) & 1u);
+        }
+    }
+  }
   /* K3 geometry: a tile stages tile_bases + W positions; keep that <= 4096 (128 words) when W allows */
   const uint32_t w32 = (p.window_size + 31) / 32 * 32;
   ctx->k3_tile_bases = w32 + 1024 <= 4096 ? 4096 - w32 : 1024;
@@ -650,7 +676,9 @@ int enqueue_scan(tps_ctx *ctx, Slot &s, cudaStream_t st, const ScanJob &job) {
   a.no_split = ctx->k3n_no_split;
   if (n_reads) {
     a.lin_words = ctx->k2_lin_words;
-    if (ctx->k2_reg)
+    if (ctx->k2c_fn)
+      ctx->k2c_fn<<<(n_reads + TPS_K2R_WARPS - 1) / TPS_K2R_WARPS, TPS_K2R_WARPS * 32, 0, sh>>>(a, ctx->k2c_masks);
+    else if (ctx->k2_reg)
       ctx->k2r_fn<<<(n_reads + TPS_K2R_WARPS - 1) / TPS_K2R_WARPS, TPS_K2R_WARPS * 32, ctx->k2r_smem, sh>>>(a, ctx->pt);
     else
       ctx->k2_fn<<<(n_reads + TPS_K2_WARPS - 1) / TPS_K2_WARPS, TPS_K2_WARPS * 32, ctx->k2_smem, sh>>>(a, ctx->pt);
@@ -1057,9 +1085,11 @@ int tps_debug_copy(tps_ctx *ctx, int what, void *dst, size_t bytes) {
       cap = ctx->k3_bitpar ? (size_t)ctx->max_pass * ctx->k3n_gs_cap * sizeof(uint16_t)
                            : (size_t)ctx->max_pass * ctx->cw_stride * sizeof(uint32_t);
       break;
-    case 5: { /* geometry: c_w row stride (elements), which K3 is in use, pass capacity, tile size of that K3 */
-      const uint32_t info[4] = {ctx->k3_bitpar ? ctx->k3n_gs_cap : ctx->cw_stride, ctx->k3_bitpar ? 1u : 0u, ctx->max_pass,
-                                ctx->k3_bitpar ? ctx->k3n_tile_bases : ctx->k3_tile_bases};
+    case 5: { /* geometry: c_w row stride (elements), which K3 is in use, pass capacity, tile size of that K3,
+               * which K2 is in use (0 shared-memory staged, 1 register staged, 2 literal set in the instructions) */
+      const uint32_t info[5] = {ctx->k3_bitpar ? ctx->k3n_gs_cap : ctx->cw_stride, ctx->k3_bitpar ? 1u : 0u, ctx->max_pass,
+                                ctx->k3_bitpar ? ctx->k3n_tile_bases : ctx->k3_tile_bases,
+                                ctx->k2c_fn ? 2u : (ctx->k2_reg ? 1u : 0u)};
       if (bytes > sizeof(info)) return fail(ctx, TPS_EINVAL, "debug info is %zu bytes", sizeof(info));
       memcpy(dst, info, bytes);
       return TPS_OK;

@@ -99,25 +99,19 @@ TPS_HD uint32_t tps_exact_mask16(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t
 TPS_HD uint32_t tps_code_at(uint32_t u, uint32_t g) { return (u >> (8 * (g & 3) + 2 * (g >> 2))) & 3u; }
 
 /* code word -> linear bit planes: low 16 bits = plane0 (code bit 0) of bases 0..15 in order,
- * high 16 bits = plane1 (code bit 1). */
-TPS_HD uint32_t tps_linear_planes(uint32_t u) {
-  uint32_t x0 = u & 0x55555555u, x1 = (u >> 1) & 0x55555555u;
-  /* compress the 4 even bits of every byte into its low nibble: nibble bit i <- bit 2i */
-  x0 = (x0 | (x0 >> 1)) & 0x33333333u;
-  x1 = (x1 | (x1 >> 1)) & 0x33333333u;
-  x0 = (x0 | (x0 >> 2)) & 0x0F0F0F0Fu;
-  x1 = (x1 | (x1 >> 2)) & 0x0F0F0F0Fu;
-  /* gather the 4 nibbles into 16 bits: bit 4m+i */
-  x0 = (x0 | (x0 >> 4)) & 0x00FF00FFu;
-  x1 = (x1 | (x1 >> 4)) & 0x00FF00FFu;
-  x0 = (x0 | (x0 >> 8)) & 0x0000FFFFu;
-  x1 = (x1 | (x1 >> 8)) & 0x0000FFFFu;
-  uint32_t y = x0 | (x1 << 16);
-  /* 4x4 bit-matrix transpose in each half: bit 4m+i -> bit 4i+m */
-  uint32_t t = (y ^ (y >> 3)) & 0x0A0A0A0Au;
-  y ^= t ^ (t << 3);
-  t = (y ^ (y >> 6)) & 0x00CC00CCu;
-  y ^= t ^ (t << 6);
+ * high 16 bits = plane1 (code bit 1).  Bit 8m + 2i + pl of the code word (base 4i + m, plane pl) goes to bit
+ * 16 pl + 4i + m: a permutation of the five INDEX bits [m1 m0 i1 i0 pl] -> [pl i1 i0 m1 m0], done as four
+ * exchanges of two index bits (delta swaps: positions 4<->0, 3<->2, 2<->1, 1<->0), 16 instructions instead of the
+ * 28 of compressing each plane and transposing it. */
+TPS_HD uint32_t tps_linear_planes(uint32_t y) {
+  uint32_t t = (y ^ (y >> 15)) & 0x0000AAAAu;
+  y ^= t ^ (t << 15);
+  t = (y ^ (y >> 4)) & 0x00F000F0u;
+  y ^= t ^ (t << 4);
+  t = (y ^ (y >> 2)) & 0x0C0C0C0Cu;
+  y ^= t ^ (t << 2);
+  t = (y ^ (y >> 1)) & 0x22222222u;
+  y ^= t ^ (t << 1);
   return y;
 }
 

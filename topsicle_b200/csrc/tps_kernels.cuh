@@ -472,6 +472,18 @@ __device__ __forceinline__ void tps_row_init(tps_row &row, uint32_t true_len) {
   row.rawcount_offset = ~0ull;
 }
 
+/* The 40-byte row as five 64-bit stores (rows are 8-byte aligned). */
+__device__ __forceinline__ void tps_store_row(tps_row *dst, const tps_row &row) {
+  uint2 *d = reinterpret_cast<uint2 *>(dst);
+  d[0] = make_uint2(row.length, (uint32_t)row.status | ((uint32_t)row.tail << 8) | ((uint32_t)row.best_pattern << 16) |
+                                    ((uint32_t)row.reserved0 << 24));
+  d[1] = make_uint2((uint32_t)row.match_count | ((uint32_t)row.head_max << 16),
+                    (uint32_t)row.tail_max | ((uint32_t)row.reserved1 << 16));
+  d[2] = make_uint2(row.n_windows, (uint32_t)row.bkp);
+  d[3] = make_uint2((uint32_t)row.telo_length, row.reserved2);
+  d[4] = make_uint2((uint32_t)row.rawcount_offset, (uint32_t)(row.rawcount_offset >> 32));
+}
+
 /* Tail decision, cutoff test and (lane 0) the append to the pass list, from the first-max counts of the two
  * ends: ms / ps of seq[:no_bp], me / pe of the reversed seq[-no_bp:] (allsteps.py:190-198). */
 __device__ __forceinline__ void tps_trc_decide(const TpsScanArgs &a, uint32_t n_patterns, uint32_t r, uint64_t off,
@@ -617,9 +629,8 @@ tps_trc_kernel(const TpsScanArgs a, const TpsPatTable pt) {
  * REDUX.MAX over (count << 8 | 255 - index).  Only self-overlapping literals still write their
  * match row to shared memory for the greedy walk. */
 template <int K>
-__device__ __forceinline__ void tps_trc_end_reg(const TpsScanArgs &a, const TpsPatTable &pt, const uint2 *pm,
-                                                uint64_t g0, uint32_t n, bool rev, uint32_t *mrows,
-                                                uint32_t lane, uint32_t &best, uint32_t &bestp) {
+__device__ __forceinline__ void tps_trc_stage_reg(const TpsScanArgs &a, uint64_t g0, uint32_t n, bool rev, uint32_t lane,
+                                                  TpsWin<K> &win) {
   const uint32_t phase = (uint32_t)(g0 & 15u);
   const uint64_t gfirst = g0 >> 4;
   const uint32_t ng = n ? (uint32_t)(((g0 + n + 15) >> 4) - gfirst) : 0u; /* <= 64 */
@@ -684,8 +695,15 @@ __device__ __forceinline__ void tps_trc_end_reg(const TpsScanArgs &a, const TpsP
   uint32_t b0 = __shfl_down_sync(TPS_FULL, a0, 1), b1 = __shfl_down_sync(TPS_FULL, a1, 1),
            bv = __shfl_down_sync(TPS_FULL, av, 1);
   if (lane == 31u) b0 = b1 = bv = 0u;
-  TpsWin<K> win;
   tps_win_init<K>(win, a0, b0, a1, b1, av, bv);
+}
+
+template <int K>
+__device__ __forceinline__ void tps_trc_end_reg(const TpsScanArgs &a, const TpsPatTable &pt, const uint2 *pm,
+                                                uint64_t g0, uint32_t n, bool rev, uint32_t *mrows,
+                                                uint32_t lane, uint32_t &best, uint32_t &bestp) {
+  TpsWin<K> win;
+  tps_trc_stage_reg<K>(a, g0, n, rev, lane, win);
   const uint32_t nq = (n + 31u) >> 5;
   uint32_t mine = 0u; /* count of literal `lane` */
   bool done = false;
@@ -760,7 +778,67 @@ tps_trc_reg_kernel(const TpsScanArgs a, const TpsPatTable pt) {
     tps_trc_end_reg<K>(a, pt, pm, off + L - n, n, true, mrows, lane, me, pe);  /* seq[-no_bp:][::-1] */
     tps_trc_decide(a, pt.n, r, off, L, Lt, lane, ms, ps, me, pe, row);
   }
-  if (lane == 0) a.rows[r] = row;
+  if (lane == 0) tps_store_row(a.rows + r, row);
+}
+
+/* K2 for the literal sets every CLI run builds (patterns_to_search: the U distinct k-mers of pattern + pattern and
+ * their base-wise complements, allsteps.py:104-120) when none overlaps itself: U and K are template parameters, the
+ * pair loop is unrolled and the 0 / ~0 plane masks of the literals are kernel parameters, i.e. constant-bank operands
+ * of the LOP3s -- no mask table in shared memory, no block barrier, no loop or select instructions.  The counts of
+ * a pair come out of one REDUX as a warp-uniform value, so the first maximum in literal order (allsteps.py:190-191)
+ * is a running max over (count << 8 | 255 - index). */
+#define TPS_K2C_MAXU 8
+struct TpsPairMasks {
+  uint32_t x[TPS_K2C_MAXU][8], y[TPS_K2C_MAXU][8]; /* [pair p][base j]: all-ones if plane 0 / 1 of literal p's base j is 1 */
+};
+
+template <int K, int U>
+__device__ __forceinline__ void tps_trc_end_const(const TpsScanArgs &a, const TpsPairMasks &pm, uint64_t g0, uint32_t n,
+                                                  bool rev, uint32_t lane, uint32_t &best, uint32_t &bestp) {
+  TpsWin<K> win;
+  tps_trc_stage_reg<K>(a, g0, n, rev, lane, win);
+  /* 16-bit keys count << 4 | 15 - index (count <= 1000 / 3, index < 16), the pair's two side by side: the sum over
+   * the lanes is linear in the counts, the tie-breakers are added behind it, the running maximum is one packed
+   * 16x2 max per pair */
+  uint32_t key2 = 0u;
+#pragma unroll
+  for (int p = 0; p < U; ++p) {
+    uint32_t tx = 0u, ty = 0u, tyc = 0u;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      tx |= win.X[j] ^ pm.x[p][j];
+      ty |= win.Y[j] ^ pm.y[p][j];
+      tyc |= ~(win.Y[j] ^ pm.y[p][j]);
+    }
+    const uint32_t M = win.V & ~tx & ~ty, Mc = win.V & ~tx & ~tyc;
+    const uint32_t c = __reduce_add_sync(TPS_FULL, tps_popc32(M) * 16u + tps_popc32(Mc) * (16u << 16));
+    key2 = __vmaxu2(key2, c + ((15u - (uint32_t)p) | ((15u - (uint32_t)(p + U)) << 16)));
+  }
+  const uint32_t klo = key2 & 0xFFFFu, khi = key2 >> 16;
+  const uint32_t key = klo > khi ? klo : khi;
+  best = key >> 4;
+  bestp = best ? 15u - (key & 15u) : 0u;
+}
+
+template <int K, int U>
+__global__ void __launch_bounds__(TPS_K2R_WARPS * 32)
+tps_trc_const_kernel(const TpsScanArgs a, const TpsPairMasks pm) {
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  const uint32_t r = blockIdx.x * TPS_K2R_WARPS + warp;
+  if (r >= a.n_reads) return;
+  const uint64_t off = a.offsets[r];
+  const uint32_t L = a.lens ? a.lens[r] : (uint32_t)(a.offsets[r + 1] - off);
+  const uint32_t Lt = a.true_lens ? a.true_lens[r] : L; /* ends batch: see tps_trc_reg_kernel */
+  tps_row row;
+  tps_row_init(row, Lt);
+  if (Lt > a.min_seq_length || a.force_tails) {
+    const uint32_t n = L < a.no_bp ? L : a.no_bp;
+    uint32_t ms, ps, me, pe;
+    tps_trc_end_const<K, U>(a, pm, off, n, false, lane, ms, ps);
+    tps_trc_end_const<K, U>(a, pm, off + L - n, n, true, lane, me, pe);
+    tps_trc_decide(a, 2u * U, r, off, L, Lt, lane, ms, ps, me, pe, row);
+  }
+  if (lane == 0) tps_store_row(a.rows + r, row);
 }
 
 /* ------------------------------------------------------------------------------------ K3 */

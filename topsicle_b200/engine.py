@@ -505,8 +505,9 @@ class ScanContext:
         return int(self.lib.tps_kernel_launches(self._h))
 
     def debug_info(self) -> dict:
-        v = self.debug_copy(5, 16).view(np.uint32)
-        return dict(cw_stride=int(v[0]), k3_bitpar=bool(v[1]), max_pass=int(v[2]), k3_tile_bases=int(v[3]))
+        v = self.debug_copy(5, 20).view(np.uint32)
+        return dict(cw_stride=int(v[0]), k3_bitpar=bool(v[1]), max_pass=int(v[2]), k3_tile_bases=int(v[3]),
+                    k2_kernel=("smem", "reg", "const")[int(v[4])])
 
     def window_sums(self, rows) -> dict:
         """Test hook: {read index: sums of c_w over the groups of five windows [5j, 5j+5)} of the TRC-pass reads

@@ -749,7 +749,9 @@ __device__ __forceinline__ void tps_trc_end_reg(const TpsScanArgs &a, const TpsP
   bestp = best ? 255u - (kmax & 255u) : 0u;
 }
 
+#ifndef TPS_K2R_WARPS
 #define TPS_K2R_WARPS 8
+#endif
 
 /* dynamic shared memory (words): pm[2 * P * max(K,1)] | per warp: mrows[n_bordered * 32] */
 template <int K>

@@ -10,10 +10,11 @@ import subprocess
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(REPO, "topsicle_b200", "libtopsicle_b200.so")
-WANT = {"tps_pack_tma_kernelILi4E": "K1 tps_pack_tma_kernel<4>", "tps_trc_reg_kernelILi4E": "K2 tps_trc_reg_kernel<4>",
+WANT = {"tps_pack_tma_kernelILi4E": "K1 tps_pack_tma_kernel<4>", "tps_trc_const_kernelILi4ELi6E": "K2 tps_trc_const_kernel<4, 6>",
+        "tps_trc_reg_kernelILi4E": "K2 (table-driven) tps_trc_reg_kernel<4>",
         "tps_window_bp_kernelILi4E": "K3+K4 tps_window_bp_kernel<4>", "tps_window_kernelILi4E": "K3 (plain) tps_window_kernel<4>",
         "tps_changepoint_kernel": "K4 (stand-alone) tps_changepoint_kernel"}
-KEYS = ["UBLKCP", "SYNCS", "LDGSTS", "LDGDEPBAR", "DEPBAR", "REDUX", "CREDUX", "POPC", "FLO", "LOP3", "SHF", "LDS", "STS",
+KEYS = ["UBLKCP", "SYNCS", "LDGSTS", "LDGDEPBAR", "DEPBAR", "REDUX", "CREDUX", "VIMNMX", "LDCU", "POPC", "FLO", "LOP3", "SHF", "LDS", "STS",
         "VOTE", "ATOM", "ATOMG", "MEMBAR", "BAR", "DMUL", "DFMA", "DADD", "I2F", "MUFU"]
 
 

@@ -865,8 +865,10 @@ int tps_fastx_next(tps_fastx *fx, uint64_t bases_cap, uint32_t reads_cap, uint8_
     uint32_t L = rv.v[0].seq_len;
     free(rv.v);
     free(chunk);
-    return fx_fail(fx, TPS_FX_ECAPACITY, "read #%llu has %u bases, more than the batch capacity of %llu",
-                   (unsigned long long)(fx->n_records + 1), L, (unsigned long long)bases_cap);
+    return fx_fail(fx, TPS_FX_ECAPACITY,
+                   "read #%llu has %u bases, more than the batch capacity of %llu%s",
+                   (unsigned long long)(fx->n_records + 1), L, (unsigned long long)bases_cap,
+                   fx->clip_bases ? " (which cannot even hold its two ends: raise the batch size, TOPSICLE_BATCH_BASES)" : "");
   }
   uint64_t consumed;
   if (n == rv.n) consumed = rv.end;

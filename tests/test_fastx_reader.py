@@ -444,6 +444,11 @@ def test_plain_gzip_parallel_inflate_equals_zlib(tmp_path, level):
     # the plain decoder (one symbol per table lookup) and zlib's crc32 in place of the folded one
     slow, st_s = _read_all(str(gz), TPS_PGZ_PIECE=1 << 18, TPS_PGZ_FAST=0, TPS_PGZ_CLMUL=0)
     assert slow == want and st_s["text_bytes"] == len(text)
+    # pieces that stay symbolic to their end (no change-over to byte output), and large pieces that all change over
+    sym, st_y = _read_all(str(gz), TPS_PGZ_PIECE=1 << 18, TPS_PGZ_BYTES=0)
+    assert sym == want and st_y["text_bytes"] == len(text)
+    big, st_b = _read_all(str(gz), TPS_PGZ_PIECE=1 << 21)
+    assert big == want and st_b["text_bytes"] == len(text) and st_b["chain_breaks"] == 0
 
 
 def test_plain_gzip_long_codes_and_fixed_blocks(tmp_path):

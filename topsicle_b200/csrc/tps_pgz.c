@@ -465,32 +465,51 @@ static int read_block_header(bitrd *b, blockhdr *h) {
   return huff_build(&h->dst, lens + hlit, hdist, DST_TB, 1);
 }
 
+typedef struct obuf16 { /* symbols */
+  uint16_t *out;
+  uint64_t n, cap;
+} obuf16;
+typedef struct obuf8 { /* bytes */
+  uint8_t *out;
+  uint64_t n, cap;
+} obuf8;
+
+/* One piece of a stretch.  Its text is sym.n symbols followed by byt.n bytes: a piece that starts with an unknown
+ * window decodes to symbols until its last 32 KiB hold none that refers to the unknown window (in FASTQ text that
+ * takes a few hundred kilobytes of a piece's eight megabytes), and to bytes from the next block on -- half the
+ * store traffic, and nothing left to translate afterwards; the first piece of a stretch knows its window and
+ * decodes to bytes from the start. */
 typedef struct seg {
   uint64_t start_bit; /* a block starts here */
   uint64_t stop_bit;  /* decode whole blocks until the position is >= this */
   uint64_t end_bit;   /* where the decode stopped (a block boundary) */
-  uint16_t *out;
-  uint64_t n, cap;
+  obuf16 sym;
+  obuf8 byt;
+  uint8_t *bwin;      /* the 32 KiB before the byte phase (owned unless it is the stretch's known window) */
+  int bwin_owned;
+  uint64_t scanned;   /* symbols already searched for window references */
+  uint64_t unres_end; /* 1 + index of the last symbol that refers to the unknown window */
   int status;    /* 0 ok, -1 corrupt, -2 out of memory */
   int saw_final; /* stopped behind the member's last block */
   int symbolic;  /* started with an unknown window */
   uint32_t crc;
 } seg;
 
-/* Symbol buffers are tens of megabytes per thread and written once per stretch: 2 MiB-aligned and advised as huge
- * pages, so that first touch costs one fault per 2 MiB instead of 512 (with eight threads faulting at once the
- * kernel's address-space lock made the first stretches several times slower than the rest). */
-static uint16_t *sym_alloc(uint64_t n) {
-  const uint64_t bytes = (n * sizeof(uint16_t) + (2u << 20) - 1) & ~(uint64_t)((2u << 20) - 1);
+/* Output buffers are megabytes per thread and written once per stretch: 2 MiB-aligned and advised as huge pages, so
+ * that first touch costs one fault per 2 MiB instead of 512 (with eight threads faulting at once the kernel's
+ * address-space lock made the first stretches several times slower than the rest). */
+static void *big_alloc(uint64_t nbytes) {
+  const uint64_t bytes = (nbytes + (2u << 20) - 1) & ~(uint64_t)((2u << 20) - 1);
   void *p = NULL;
   if (posix_memalign(&p, 2u << 20, bytes)) return NULL;
 #ifdef MADV_HUGEPAGE
   madvise(p, bytes, MADV_HUGEPAGE);
 #endif
-  return (uint16_t *)p;
+  return p;
 }
+static uint16_t *sym_alloc(uint64_t n) { return (uint16_t *)big_alloc(n * sizeof(uint16_t)); }
 
-static int seg_grow(seg *s, uint64_t need) {
+static int grow_sym(obuf16 *s, uint64_t need) {
   if (s->n + need <= s->cap) return 0;
   uint64_t nc = s->cap ? s->cap * 2 : (1u << 22);
   while (nc < s->n + need) nc *= 2;
@@ -502,213 +521,54 @@ static int seg_grow(seg *s, uint64_t need) {
   s->cap = nc;
   return 0;
 }
+static int grow_byte(obuf8 *s, uint64_t need) {
+  if (s->n + need <= s->cap) return 0;
+  uint64_t nc = s->cap ? s->cap * 2 : (1u << 22);
+  while (nc < s->n + need) nc *= 2;
+  uint8_t *nv = (uint8_t *)big_alloc(nc);
+  if (!nv) return -1;
+  if (s->n) memcpy(nv, s->out, s->n);
+  free(s->out);
+  s->out = nv;
+  s->cap = nc;
+  return 0;
+}
 
 static inline int is_text(uint32_t c) { return c == 10 || c == 13 || c == 9 || (c >= 32 && c < 127); }
 
-/* Decode the block whose header was just read.  win = the 32768 symbols before the segment's start.
- * text_only / max_out: the stricter rules of the block-start search.  0 ok, <0 error. */
-static inline __attribute__((always_inline)) int decode_block_impl(bitrd *b, const blockhdr *h, seg *s, const uint16_t *win,
-                                                                  const int text_only, const uint64_t max_out) {
-  if (h->type == 0) {
-    if (b->cnt & 7u) return -1;
-    uint32_t left = h->stored_len;
-    if (seg_grow(s, (uint64_t)left + 8)) return -2;
-    while (left && b->cnt >= 8) { /* bytes already in the bit buffer */
-      const uint32_t c = br_bits(b, 8);
-      if (text_only && !is_text(c)) return -1;
-      s->out[s->n++] = (uint16_t)c;
-      --left;
-    }
-    if (b->cnt == 0) b->buf = 0; /* bits a wide refill read ahead of the accounted ones */
-    if ((uint64_t)(b->end - b->p) < left) return -1;
-    for (uint32_t i = 0; i < left; ++i) {
-      if (text_only && !is_text(b->p[i])) return -1;
-      s->out[s->n++] = b->p[i];
-    }
-    b->p += left;
-    return 0;
-  }
-  for (;;) {
-    if (__builtin_expect(s->n + 320 > s->cap, 0) && seg_grow(s, 320)) return -2;
-    br_refill(b);
-    int32_t sym = huff_sym_tb(&h->lit, b, LIT_TB);
-    if (sym < 0) return -1;
-    if (sym < 256) {
-      if (text_only && !is_text((uint32_t)sym)) return -1;
-      s->out[s->n++] = (uint16_t)sym;
-      /* up to two more literals from the same refill (3 x 15 bits < 56): most of FASTQ text -- the quality
-       * lines above all -- is literals and short matches */
-      if (b->cnt < 48) continue;
-      sym = huff_sym_tb(&h->lit, b, LIT_TB);
-      if (sym < 0) return -1;
-      if (sym < 256) {
-        if (text_only && !is_text((uint32_t)sym)) return -1;
-        s->out[s->n++] = (uint16_t)sym;
-        sym = huff_sym_tb(&h->lit, b, LIT_TB);
-        if (sym < 0) return -1;
-        if (sym < 256) {
-          if (text_only && !is_text((uint32_t)sym)) return -1;
-          s->out[s->n++] = (uint16_t)sym;
-          continue;
-        }
-      }
-    }
-    if (sym == 256) return 0;
-    sym -= 257;
-    if (sym >= 29) return -1;
-    if (b->cnt < 48) br_refill(b);
-    if (b->cnt < LEN_EXTRA[sym]) return -1;
-    const uint32_t len = LEN_BASE[sym] + br_bits(b, LEN_EXTRA[sym]);
-    const int32_t ds = huff_sym_tb(&h->dst, b, DST_TB);
-    if (ds < 0 || ds >= 30) return -1;
-    if (b->cnt < 13) br_refill(b);
-    if (b->cnt < DST_EXTRA[ds]) return -1;
-    const uint32_t dist = DST_BASE[ds] + br_bits(b, DST_EXTRA[ds]);
-    if (dist > s->n + PGZ_WSIZE) return -1;
-    uint16_t *o = s->out + s->n;
-    if (dist <= s->n) {
-      const uint16_t *f = o - dist;
-      if (dist >= 8) { /* eight symbols at a time; may write up to 7 past the match (320 symbols of slack) */
-        for (uint32_t k = 0; k < len; k += 8) memcpy(o + k, f + k, 16);
-      } else {
-        for (uint32_t k = 0; k < len; ++k) o[k] = f[k];
-      }
-    } else { /* reaches into the window before the segment */
-      for (uint32_t k = 0; k < len; ++k) {
-        const int64_t at = (int64_t)s->n + k - dist;
-        o[k] = at >= 0 ? s->out[at] : win[(int64_t)PGZ_WSIZE + at];
-      }
-    }
-    s->n += len;
-    if (max_out && s->n > max_out) return -1;
-  }
-}
-
-/* The same decode for a Huffman block with the literal-run table, on local copies of the reader and the output
- * cursor; hands over to decode_block_impl near the end of the input and of the symbol buffer (any symbol boundary
- * is a valid place to continue).  0 ok, <0 error. */
-static int decode_block_fast(bitrd *b, const blockhdr *h, seg *s, const uint16_t *win) {
-  if ((uint64_t)(b->end - b->base) < 64 || s->cap < 1024) return decode_block_impl(b, h, s, win, 0, 0);
-  bitrd lb = *b;
-  const uint8_t *const safe = lb.end - 32; /* three 8-byte refills of one iteration stay inside the input */
-  uint16_t *o = s->out + s->n;
-  uint16_t *const olim = s->out + s->cap - 336;
-  const uint32_t *const fast = h->fast;
-  const uint32_t *const dfast = h->dfast;
-  int rc = 1; /* 1 = hand over */
-#define PGZ_REFILL()                 \
-  do {                               \
-    uint64_t w_;                     \
-    memcpy(&w_, lb.p, 8);            \
-    lb.buf |= w_ << lb.cnt;          \
-    lb.p += (63 - lb.cnt) >> 3;      \
-    lb.cnt |= 56;                    \
-  } while (0)
-#define PGZ_EMIT(e)                                                                                        \
-  do {                                                                                                     \
-    const uint64_t x_ = (e) >> 8;                                                                          \
-    const uint64_t v_ = (x_ & 0xFFu) | ((x_ & 0xFF00u) << 8) | ((x_ & 0xFF0000u) << 16);                   \
-    memcpy(o, &v_, 8);                                                                                     \
-    o += ((e) >> 4) & 3u;                                                                                  \
-    lb.buf >>= (e) & 15u;                                                                                  \
-    lb.cnt -= (e) & 15u;                                                                                   \
-  } while (0)
-  while (lb.p <= safe && o < olim) {
-    PGZ_REFILL();
-    /* up to three literal runs from one refill, then whatever follows still finds 20 bits */
-    uint32_t e = fast[lb.buf & ((1u << FAST_TB) - 1u)];
-    if (e & 0x30u) {
-      PGZ_EMIT(e);
-      e = fast[lb.buf & ((1u << FAST_TB) - 1u)];
-      if (e & 0x30u) {
-        PGZ_EMIT(e);
-        e = fast[lb.buf & ((1u << FAST_TB) - 1u)];
-        if (e & 0x30u) {
-          PGZ_EMIT(e);
-          e = fast[lb.buf & ((1u << FAST_TB) - 1u)];
-          if (e & 0x30u) {
-            PGZ_EMIT(e);
-            continue;
-          }
-        }
-      }
-    }
-    uint32_t len;
-    if (e & PGZ_F_LEN) { /* length code and its extra bits: <= 12 + 5 of the >= 20 bits at hand */
-      const uint32_t cb = e & 15u, xb = (e >> 8) & 7u;
-      len = (e >> 16) + ((uint32_t)(lb.buf >> cb) & ((1u << xb) - 1u));
-      lb.buf >>= cb + xb;
-      lb.cnt -= cb + xb;
-    } else if (e & PGZ_F_EOB) {
-      lb.buf >>= e & 15u;
-      lb.cnt -= e & 15u;
-      rc = 0;
-      break;
-    } else { /* a code longer than FAST_TB bits, or an invalid one */
-      int32_t sym = huff_sym_tb(&h->lit, &lb, LIT_TB);
-      if (sym < 0) { rc = -1; break; }
-      if (sym < 256) {
-        *o++ = (uint16_t)sym;
-        continue;
-      }
-      if (sym == 256) { rc = 0; break; }
-      sym -= 257;
-      if (sym >= 29) { rc = -1; break; }
-      PGZ_REFILL();
-      len = LEN_BASE[sym] + br_bits(&lb, LEN_EXTRA[sym]);
-    }
-    PGZ_REFILL();
-    uint32_t dist;
-    const uint32_t d = dfast[lb.buf & ((1u << DFAST_TB) - 1u)];
-    if (__builtin_expect(d != 0u, 1)) { /* <= 10 + 13 bits */
-      const uint32_t cb = d & 15u, xb = (d >> 8) & 15u;
-      dist = (d >> 16) + ((uint32_t)(lb.buf >> cb) & ((1u << xb) - 1u));
-      lb.buf >>= cb + xb;
-      lb.cnt -= cb + xb;
-    } else {
-      const int32_t ds = huff_sym_tb(&h->dst, &lb, DST_TB);
-      if (ds < 0 || ds >= 30) { rc = -1; break; }
-      dist = DST_BASE[ds] + br_bits(&lb, DST_EXTRA[ds]); /* <= 15 + 13 of 56 bits */
-    }
-    const uint64_t n = (uint64_t)(o - s->out);
-    if (__builtin_expect(dist <= n, 1)) {
-      const uint16_t *f = o - dist;
-      if (__builtin_expect(dist >= 8, 1)) { /* eight symbols at a time; writes up to 15 past the match (slack above) */
-        memcpy(o, f, 16);
-        memcpy(o + 8, f + 8, 16);
-        for (uint32_t k = 16; k < len; k += 8) memcpy(o + k, f + k, 16);
-      } else {
-        for (uint32_t k = 0; k < len; ++k) o[k] = f[k];
-      }
-    } else { /* reaches into the window before the segment */
-      if (dist > n + PGZ_WSIZE) { rc = -1; break; }
-      for (uint32_t k = 0; k < len; ++k) {
-        const int64_t at = (int64_t)n + k - dist;
-        o[k] = at >= 0 ? s->out[at] : win[(int64_t)PGZ_WSIZE + at];
-      }
-    }
-    o += len;
-  }
-#undef PGZ_EMIT
-#undef PGZ_REFILL
-  *b = lb;
-  s->n = (uint64_t)(o - s->out);
-  if (rc <= 0) return rc;
-  return decode_block_impl(b, h, s, win, 0, 0);
-}
+#define PGZ_T uint16_t
+#define PGZ_OBUF obuf16
+#define PGZ_NAME(x) x##_sym
+#define PGZ_BYTES 0
+#define PGZ_CHUNK 8u
+#include "tps_pgz_decode.inc"
+#undef PGZ_T
+#undef PGZ_OBUF
+#undef PGZ_NAME
+#undef PGZ_BYTES
+#undef PGZ_CHUNK
+#define PGZ_T uint8_t
+#define PGZ_OBUF obuf8
+#define PGZ_NAME(x) x##_byte
+#define PGZ_BYTES 1
+#define PGZ_CHUNK 16u
+#include "tps_pgz_decode.inc"
+#undef PGZ_T
+#undef PGZ_OBUF
+#undef PGZ_NAME
+#undef PGZ_BYTES
+#undef PGZ_CHUNK
 
 static int pgz_fast_on = 1; /* TPS_PGZ_FAST=0 (read by tps_pgz_open): one symbol per lookup everywhere (A/B, tests) */
 
-static int decode_block(bitrd *b, blockhdr *h, seg *s, const uint16_t *win) {
-  if (h->type == 0 || !pgz_fast_on) return decode_block_impl(b, h, s, win, 0, 0);
-  build_fast(h);
-  return decode_block_fast(b, h, s, win);
-}
-static int decode_block_text(bitrd *b, const blockhdr *h, seg *s, const uint16_t *win, uint64_t max_out) {
-  return decode_block_impl(b, h, s, win, 1, max_out);
+static int pgz_bytes_on = 1; /* TPS_PGZ_BYTES=0 (read by tps_pgz_open): pieces stay symbolic to their end (A/B, tests) */
+
+static int decode_block_text(bitrd *b, const blockhdr *h, obuf16 *s, const uint16_t *win, uint64_t max_out) {
+  return decode_block_impl_sym(b, h, s, win, 1, max_out);
 }
 
-/* Decode whole blocks from s->start_bit until the position reaches s->stop_bit or the member ends. */
+/* Decode whole blocks from s->start_bit until the position reaches s->stop_bit or the member ends.
+ * win = the 32768 symbols before a symbolic piece; a piece with a known window comes with s->bwin set. */
 static void decode_segment(const uint8_t *z, uint64_t zlen, seg *s, const uint16_t *win) {
   bitrd b;
   br_init(&b, z, zlen, s->start_bit);
@@ -718,12 +578,17 @@ static void decode_segment(const uint8_t *z, uint64_t zlen, seg *s, const uint16
     return;
   }
   s->status = 0;
+  int bytes = s->bwin != NULL;
   for (;;) {
     if (read_block_header(&b, h)) {
       s->status = -1;
       break;
     }
-    const int rc = decode_block(&b, h, s, win);
+    int rc;
+    const int fast = h->type != 0 && pgz_fast_on;
+    if (fast) build_fast(h);
+    if (bytes) rc = fast ? decode_block_fast_byte(&b, h, &s->byt, s->bwin) : decode_block_impl_byte(&b, h, &s->byt, s->bwin, 0, 0);
+    else rc = fast ? decode_block_fast_sym(&b, h, &s->sym, win) : decode_block_impl_sym(&b, h, &s->sym, win, 0, 0);
     if (rc) {
       s->status = rc;
       break;
@@ -734,6 +599,24 @@ static void decode_segment(const uint8_t *z, uint64_t zlen, seg *s, const uint16
       break;
     }
     if (s->end_bit >= s->stop_bit) break;
+    if (!bytes && pgz_bytes_on) { /* do the last 32 KiB still refer to the unknown window? */
+      const uint16_t *o = s->sym.out;
+      uint64_t k = s->scanned, last = s->unres_end;
+      for (; k < s->sym.n; ++k)
+        if (o[k] >= 256u) last = k + 1;
+      s->scanned = k;
+      s->unres_end = last;
+      if (s->sym.n >= PGZ_WSIZE && s->sym.n - last >= PGZ_WSIZE) {
+        s->bwin = (uint8_t *)malloc(PGZ_WSIZE);
+        if (!s->bwin) {
+          s->status = -2;
+          break;
+        }
+        s->bwin_owned = 1;
+        for (uint32_t j = 0; j < PGZ_WSIZE; ++j) s->bwin[j] = (uint8_t)o[s->sym.n - PGZ_WSIZE + j];
+        bytes = 1;
+      }
+    }
   }
   free(h);
 }
@@ -742,7 +625,7 @@ static void decode_segment(const uint8_t *z, uint64_t zlen, seg *s, const uint16
  * to text, and another valid block header follows.  Returns ~0 if none. */
 static uint64_t find_block_start(const uint8_t *z, uint64_t zlen, uint64_t from, uint64_t limit, const uint16_t *symwin) {
   blockhdr *h = (blockhdr *)malloc(sizeof(blockhdr)), *h2 = (blockhdr *)malloc(sizeof(blockhdr));
-  seg t;
+  obuf16 t;
   memset(&t, 0, sizeof(t));
   uint64_t found = ~0ull;
   if (h && h2) {
@@ -785,6 +668,8 @@ struct tps_pgz {
   uint64_t isize;
   uint16_t *bufs[256];       /* symbol buffers of the pieces, kept from stretch to stretch */
   uint64_t bufcap[256];
+  uint8_t *bbufs[256];       /* byte buffers of the pieces, likewise */
+  uint64_t bbufcap[256];
   uint8_t *q;                /* text produced but not yet handed out */
   uint64_t q_len, q_off;
   double ratio;              /* text bytes per compressed byte so far */
@@ -836,6 +721,8 @@ tps_pgz *tps_pgz_open(const uint8_t *zmap, uint64_t zlen, int threads) {
   {
     const char *f = getenv("TPS_PGZ_FAST");
     pgz_fast_on = !(f && atoi(f) == 0);
+    f = getenv("TPS_PGZ_BYTES");
+    pgz_bytes_on = !(f && atoi(f) == 0);
   }
   if (getenv("TPS_PGZ_DEBUG"))
     fprintf(stderr, "[pgz] open: %d threads, literal-run tables %s, crc32 by %s\n", g->threads, pgz_fast_on ? "on" : "off",
@@ -850,6 +737,7 @@ tps_pgz *tps_pgz_open(const uint8_t *zmap, uint64_t zlen, int threads) {
 void tps_pgz_close(tps_pgz *g) {
   if (!g) return;
   for (int i = 0; i < 256; ++i) free(g->bufs[i]);
+  for (int i = 0; i < 256; ++i) free(g->bbufs[i]);
   free(g->q);
   free(g);
 }
@@ -910,13 +798,11 @@ static int64_t next_stretch(tps_pgz *g, uint8_t *dst, uint64_t cap) {
   }
   seg *sg = (seg *)calloc((size_t)T, sizeof(seg));
   uint16_t *symwin = (uint16_t *)malloc(PGZ_WSIZE * sizeof(uint16_t));
-  uint16_t *win0 = (uint16_t *)malloc(PGZ_WSIZE * sizeof(uint16_t));
-  if (!sg || !symwin || !win0) {
-    free(sg); free(symwin); free(win0);
+  if (!sg || !symwin) {
+    free(sg); free(symwin);
     return pgz_fail(g, "out of memory");
   }
   for (uint32_t i = 0; i < PGZ_WSIZE; ++i) symwin[i] = (uint16_t)(256u + i);
-  for (uint32_t i = 0; i < PGZ_WSIZE; ++i) win0[i] = i >= PGZ_WSIZE - g->wlen ? g->window[i - (PGZ_WSIZE - g->wlen)] : 0;
   const int dbg = getenv("TPS_PGZ_DEBUG") != NULL;
   const double t_a = pgz_now();
   /* 2. block starts */
@@ -931,25 +817,42 @@ static int64_t next_stretch(tps_pgz *g, uint8_t *dst, uint64_t cap) {
   for (int i = 1; i < T; ++i)
     if (starts[i] != ~0ull && starts[i] > starts[ns - 1]) starts[ns++] = starts[i];
   const uint64_t stretch_end = (start_byte + (uint64_t)T * piece) * 8;
+  uint8_t *bwin0 = (uint8_t *)calloc(1, PGZ_WSIZE); /* the known window of the first piece, zero-padded in front */
+  if (!bwin0) {
+    free(sg); free(symwin); free(starts);
+    return pgz_fail(g, "out of memory");
+  }
+  memcpy(bwin0 + (PGZ_WSIZE - g->wlen), g->window, g->wlen);
   for (int i = 0; i < ns; ++i) {
-    sg[i].out = g->bufs[i];
-    sg[i].cap = g->bufcap[i];
+    sg[i].sym.out = g->bufs[i];
+    sg[i].sym.cap = g->bufcap[i];
+    sg[i].byt.out = g->bbufs[i];
+    sg[i].byt.cap = g->bbufcap[i];
     g->bufs[i] = NULL;
+    g->bbufs[i] = NULL;
     const uint64_t expect = (uint64_t)((double)piece * g->ratio * 1.5) + (1u << 20); /* no doubling on the way */
-    if (sg[i].cap < expect) { /* with headroom: the running ratio moves a little from stretch to stretch */
-      const uint64_t want = (expect + expect / 2 + (1u << 23) - 1) & ~(uint64_t)((1u << 23) - 1);
-      free(sg[i].out);
-      sg[i].out = sym_alloc(want);
-      sg[i].cap = sg[i].out ? want : 0;
+    const uint64_t want = (expect + expect / 2 + (1u << 23) - 1) & ~(uint64_t)((1u << 23) - 1);
+    /* with headroom: the running ratio moves a little from stretch to stretch.  A piece that may go over to bytes
+     * touches only the front of its symbol buffer (untouched pages cost nothing) */
+    if (i > 0 && sg[i].sym.cap < expect) {
+      free(sg[i].sym.out);
+      sg[i].sym.out = sym_alloc(want);
+      sg[i].sym.cap = sg[i].sym.out ? want : 0;
+    }
+    if ((i == 0 || pgz_bytes_on) && sg[i].byt.cap < expect) {
+      free(sg[i].byt.out);
+      sg[i].byt.out = (uint8_t *)big_alloc(want);
+      sg[i].byt.cap = sg[i].byt.out ? want : 0;
     }
     sg[i].start_bit = starts[i];
     sg[i].stop_bit = i + 1 < ns ? starts[i + 1] : stretch_end;
     sg[i].symbolic = i > 0;
+    if (i == 0) sg[i].bwin = bwin0; /* bytes from the start */
   }
   const double t_b = pgz_now();
   /* 3. decode */
 #pragma omp parallel for num_threads(ns) schedule(static, 1)
-  for (int i = 0; i < ns; ++i) decode_segment(g->z, g->zlen, &sg[i], i ? symwin : win0);
+  for (int i = 0; i < ns; ++i) decode_segment(g->z, g->zlen, &sg[i], symwin);
   const double t_c = pgz_now();
   /* the chain: segment i must stop exactly where segment i+1 started */
   int good = 0;
@@ -970,7 +873,7 @@ static int64_t next_stretch(tps_pgz *g, uint8_t *dst, uint64_t cap) {
     uint8_t *wins = (uint8_t *)malloc((size_t)good * PGZ_WSIZE);
     uint32_t *wlens = (uint32_t *)malloc((size_t)good * sizeof(uint32_t));
     uint64_t total = 0;
-    for (int i = 0; i < good; ++i) total += sg[i].n;
+    for (int i = 0; i < good; ++i) total += sg[i].sym.n + sg[i].byt.n;
     uint8_t *target = dst;
     int to_queue = 0;
     if (total > cap) { /* the estimate was too small: keep the text, hand it out piecewise */
@@ -992,20 +895,24 @@ static int64_t next_stretch(tps_pgz *g, uint8_t *dst, uint64_t cap) {
         const uint8_t *pw = wins + (size_t)(i - 1) * PGZ_WSIZE;
         uint8_t *w = wins + (size_t)i * PGZ_WSIZE;
         const uint32_t pwl = wlens[i - 1];
-        const uint64_t take = p->n < PGZ_WSIZE ? p->n : PGZ_WSIZE;
+        const uint64_t plen = p->sym.n + p->byt.n;
+        const uint64_t take = plen < PGZ_WSIZE ? plen : PGZ_WSIZE;
         const uint32_t keep = take < PGZ_WSIZE ? (uint32_t)((PGZ_WSIZE - take) < pwl ? (PGZ_WSIZE - take) : pwl) : 0;
         memcpy(w, pw + (pwl - keep), keep);
-        for (uint64_t k = 0; k < take; ++k) {
-          const uint16_t v = p->out[p->n - take + k];
+        /* the last `take` elements of the piece: the end of its symbols, then its bytes */
+        const uint64_t from_bytes = p->byt.n < take ? p->byt.n : take, from_syms = take - from_bytes;
+        for (uint64_t k = 0; k < from_syms; ++k) {
+          const uint16_t v = p->sym.out[p->sym.n - from_syms + k];
           /* symbol 256 + j = byte j of the 32 KiB window, whose last pwl bytes are known (a valid stream never
            * reaches further back than the member's start) */
           w[keep + k] = v < 256 ? (uint8_t)v : (v - 256u >= PGZ_WSIZE - pwl ? pw[v - 256u - (PGZ_WSIZE - pwl)] : 0);
         }
+        memcpy(w + keep + from_syms, p->byt.out + (p->byt.n - from_bytes), from_bytes);
         wlens[i] = keep + (uint32_t)take;
       }
       uint64_t *offs = (uint64_t *)malloc(((size_t)good + 1) * sizeof(uint64_t));
       offs[0] = 0;
-      for (int i = 0; i < good; ++i) offs[i + 1] = offs[i] + sg[i].n;
+      for (int i = 0; i < good; ++i) offs[i + 1] = offs[i] + sg[i].sym.n + sg[i].byt.n;
       int bad_ref = 0;
 #pragma omp parallel for num_threads(good) schedule(static, 1)
       for (int i = 0; i < good; ++i) {
@@ -1013,25 +920,27 @@ static int64_t next_stretch(tps_pgz *g, uint8_t *dst, uint64_t cap) {
         uint8_t *o = target + offs[i];
         const uint8_t *w = wins + (size_t)i * PGZ_WSIZE;
         const uint32_t wl = wlens[i], miss = PGZ_WSIZE - wl;
+        const uint16_t *so = s->sym.out;
+        const uint64_t sn = s->sym.n;
         uint32_t c = (uint32_t)crc32(0L, Z_NULL, 0);
         /* a chunk of symbols to bytes, then its CRC while the bytes are still in the cache */
-        for (uint64_t k0 = 0; k0 < s->n; k0 += 1u << 15) {
-          const uint64_t k1 = k0 + (1u << 15) < s->n ? k0 + (1u << 15) : s->n;
+        for (uint64_t k0 = 0; k0 < sn; k0 += 1u << 15) {
+          const uint64_t k1 = k0 + (1u << 15) < sn ? k0 + (1u << 15) : sn;
           uint64_t k = k0;
           while (k < k1) {
-            /* past the first stretch of a piece nearly everything is resolved: whole runs of 64 narrow at once */
+            /* a little into a piece nearly everything is resolved: whole runs of 64 narrow at once */
             if (k + 64 <= k1) {
               uint16_t any = 0;
-              for (int j = 0; j < 64; ++j) any |= s->out[k + j];
+              for (int j = 0; j < 64; ++j) any |= so[k + j];
               if (any < 256) {
-                for (int j = 0; j < 64; ++j) o[k + j] = (uint8_t)s->out[k + j];
+                for (int j = 0; j < 64; ++j) o[k + j] = (uint8_t)so[k + j];
                 k += 64;
                 continue;
               }
             }
             const uint64_t ke = k + 64 <= k1 ? k + 64 : k1;
             for (; k < ke; ++k) {
-              const uint16_t v = s->out[k];
+              const uint16_t v = so[k];
               if (v < 256) o[k] = (uint8_t)v;
               else if (s->symbolic && v - 256u >= miss) o[k] = w[v - 256u - miss];
               else {
@@ -1042,6 +951,12 @@ static int64_t next_stretch(tps_pgz *g, uint8_t *dst, uint64_t cap) {
           }
           c = pgz_crc32(c, o + k0, k1 - k0);
         }
+        /* the piece's bytes: copied and summed chunk by chunk */
+        for (uint64_t k0 = 0; k0 < s->byt.n; k0 += 1u << 16) {
+          const uint64_t len = s->byt.n - k0 < (1u << 16) ? s->byt.n - k0 : (1u << 16);
+          memcpy(o + sn + k0, s->byt.out + k0, len);
+          c = pgz_crc32(c, o + sn + k0, len);
+        }
         sg[i].crc = c;
       }
       if (dbg)
@@ -1050,7 +965,8 @@ static int64_t next_stretch(tps_pgz *g, uint8_t *dst, uint64_t cap) {
       if (bad_ref) {
         pgz_fail(g, "corrupt deflate stream (reference before the start of the member)");
       } else {
-        for (int i = 0; i < good; ++i) g->crc = (uint32_t)crc32_combine(g->crc, sg[i].crc, (z_off_t)sg[i].n);
+        for (int i = 0; i < good; ++i)
+          g->crc = (uint32_t)crc32_combine(g->crc, sg[i].crc, (z_off_t)(sg[i].sym.n + sg[i].byt.n));
         g->isize += total;
         /* new window */
         const seg *l = &sg[good - 1];
@@ -1067,7 +983,7 @@ static int64_t next_stretch(tps_pgz *g, uint8_t *dst, uint64_t cap) {
         g->st.stretches++;
         g->st.segments += (uint64_t)good;
         g->st.text_bytes += total;
-        if (good > 1) g->st.parallel_text_bytes += total - sg[0].n;
+        if (good > 1) g->st.parallel_text_bytes += total - sg[0].sym.n - sg[0].byt.n;
         const uint64_t comp = (l->end_bit >> 3) - start_byte;
         if (comp > (1u << 16)) g->ratio = 0.5 * g->ratio + 0.5 * ((double)total / (double)comp);
         if (g->ratio < 1.0) g->ratio = 1.0;
@@ -1080,13 +996,16 @@ static int64_t next_stretch(tps_pgz *g, uint8_t *dst, uint64_t cap) {
     free(wins);
     free(wlens);
   }
-  for (int i = 0; i < T; ++i) { /* keep the symbol buffers: fresh ones cost a page fault per 4 KiB */
-    g->bufs[i] = sg[i].out;
-    g->bufcap[i] = sg[i].cap;
+  for (int i = 0; i < ns; ++i) { /* keep the buffers: fresh ones cost their page faults again */
+    g->bufs[i] = sg[i].sym.out;
+    g->bufcap[i] = sg[i].sym.cap;
+    g->bbufs[i] = sg[i].byt.out;
+    g->bbufcap[i] = sg[i].byt.cap;
+    if (sg[i].bwin_owned) free(sg[i].bwin);
   }
   free(sg);
   free(symwin);
-  free(win0);
+  free(bwin0);
   free(starts);
   return ret;
 }

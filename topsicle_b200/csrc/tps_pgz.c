@@ -638,6 +638,23 @@ static uint64_t find_block_start(const uint8_t *z, uint64_t zlen, uint64_t from,
       if ((w & 7u) != 4u) continue;          /* BFINAL = 0, BTYPE = 10b */
       if (((w >> 3) & 31u) > 29u) continue;  /* HLIT */
       if (((w >> 8) & 31u) > 29u) continue;  /* HDIST */
+      /* the HCLEN + 4 three-bit lengths of the code-length code must form a complete prefix code (zlib accepts
+       * nothing else): a Kraft sum over 57 bits read in one go turns away nearly every position that got here */
+      {
+        const uint64_t at = pos + 17;
+        if ((at >> 3) + 8 <= zlen) {
+          uint64_t v;
+          memcpy(&v, z + (at >> 3), 8);
+          v >>= at & 7;
+          const uint32_t hclen = ((w >> 13) & 15u) + 4u;
+          uint32_t kraft = 0;
+          for (uint32_t i = 0; i < hclen; ++i) {
+            const uint32_t l = (uint32_t)(v >> (3u * i)) & 7u;
+            kraft += l ? 128u >> l : 0u;
+          }
+          if (kraft != 128u) continue;
+        }
+      }
       bitrd b;
       br_init(&b, z, zlen, pos);
       if (read_block_header(&b, h)) continue;

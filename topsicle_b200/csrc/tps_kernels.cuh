@@ -1413,7 +1413,11 @@ __device__ __forceinline__ uint32_t tps_bp_window(uint32_t ls, uint32_t D, uint3
 }
 
 template <int K>
+#ifdef TPS_K3N_MINB
+__global__ void __launch_bounds__(TPS_K3N_THREADS, TPS_K3N_MINB)
+#else
 __global__ void __launch_bounds__(TPS_K3N_THREADS)
+#endif
 tps_window_bp_kernel(const TpsScanArgs a, const TpsPatTable pt) {
   static_assert(K > 0, "the bit-parallel window kernel needs a common literal length");
   constexpr uint32_t NT = TPS_K3N_THREADS;

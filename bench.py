@@ -333,6 +333,20 @@ def main():
     barrier()
     t1 = time.perf_counter()
     launches = sum(c.kernel_launches() for c in ctxs) - launches0
+    # The K steps as the DEVICE saw them: CUDA events of the library's own streams (the scans run on the slot /
+    # pack / tail streams, which torch events do not see), from the first kernel of the first timed step to the end
+    # of whichever of the last steps finished last.  The host clock around the two barriers also holds the latency
+    # of the closing barrier (a NCCL all-reduce at N > 1), which is 5-25 % of a 20-step region of 6 ms.
+    step_ctx = [(i % nb) % nm for i in range(a.steps)]
+    per_ctx = [step_ctx.count(m) for m in range(nm)]
+    dev_span = None
+    if max(per_ctx) <= 250:
+
+        def back_of(i):     # scan_device calls of step i's context issued after step i
+            return sum(1 for j in range(i + 1, a.steps) if step_ctx[j] == step_ctx[i])
+        c0 = ctxs[step_ctx[0]]
+        dev_span = max(c0.elapsed_to(back_of(0), 0, ctxs[step_ctx[i]], back_of(i), 3)
+                       for i in range(max(0, a.steps - n_streams * nm), a.steps)) * 1e-3
     rows_dev = np.frombuffer(d_rows_s[last_buf].cpu().numpy().tobytes(), dtype=engine.ROW_DTYPE).copy()
     # device-side (CUDA event) times per kernel, from the library's event ring.  With several streams
     # the kernels of consecutive batches overlap and per-kernel event times are not attributable, so the
@@ -352,7 +366,8 @@ def main():
     dev_ms = statistics.mean(t["total"] for t in ring)
     bases_timed = sum(nbases[i % nb] for i in range(a.steps))
     bases_attr = sum(nbases[i % nb] for i in range(n_attr)) / n_attr
-    wall = max_over_ranks(t1 - t0)
+    host_wall = max_over_ranks(t1 - t0)
+    wall = max_over_ranks(dev_span) if dev_span is not None else host_wall
     total_bases = sum_over_ranks(float(bases_timed))
     value = total_bases / wall / 1e9
 
@@ -537,6 +552,10 @@ def main():
                              "pipelined_scan_frac": ALG_BYTES_PER_BASE * value / peak / world},
                 "cpu_baseline": cpu, "parity_sample": parity, "parity_all": parity_all or None, "e2e": e2e,
                 "e2e_from_fastq": e2e_file, "gpu_launches": int(launches),
+                "timing": {"method": ("CUDA events on the library's streams: first kernel of the first timed step -> end "
+                                      "of the last steps, between the two barriers; max over ranks") if dev_span is not None
+                           else "host clock between the two barriers (more timed scans than the event ring holds)",
+                           "device_span_ms": wall * 1e3, "host_wall_between_barriers_ms": host_wall * 1e3},
                 "clocks": clocks,
                 "generate_s": t_gen,
                 "host_placement": {"cpus_local_to_gpu0": near, "bound": bool(near and world > 1)}}

@@ -192,6 +192,12 @@ int tps_get_timings(tps_ctx *ctx, uint32_t back, float ms[TPS_N_TIMINGS]);
 /* Timeline of overlapping scans: ms[i] = time from the start of the timed scan `base_back` calls ago to
  * event i of the scan `back` calls ago (0 = K1 start, 1 = K1 end, 2 = K2 end, 3 = K4 end). */
 int tps_get_timeline(tps_ctx *ctx, uint32_t back, uint32_t base_back, float ms[TPS_N_TIMINGS]);
+/* Device time (ms) from event `from_event` of the tps_scan_device call `from_back` calls ago of context `from` to
+ * event `to_event` of the call `to_back` calls ago of context `to` (same device; events as in tps_get_timeline):
+ * the span of a run of overlapping scans issued through several contexts, measured on the device.  Blocks until both
+ * scans have finished. */
+int tps_elapsed_between(tps_ctx *from, uint32_t from_back, uint32_t from_event, tps_ctx *to, uint32_t to_back,
+                        uint32_t to_event, float *ms);
 /* Number of kernels this context has launched so far. */
 uint64_t tps_kernel_launches(const tps_ctx *ctx);
 

@@ -20,7 +20,7 @@ def declared_functions(header="topsicle_b200.h"):
 def test_header_declares_the_expected_entry_points():
     names = declared_functions()
     for must in ("tps_create", "tps_destroy", "tps_submit", "tps_wait", "tps_batch_info", "tps_scan_device",
-                 "tps_sync", "tps_get_timings", "tps_get_timeline", "tps_last_error", "tps_alloc_pinned", "tps_free_pinned",
+                 "tps_sync", "tps_get_timings", "tps_get_timeline", "tps_elapsed_between", "tps_last_error", "tps_alloc_pinned", "tps_free_pinned",
                  "tps_abi_version", "tps_build_info", "tps_kernel_launches", "tps_debug_copy", "tps_device_count",
                  "tps_follow_scan", "tps_submit_spans", "tps_submit_ends", "tps_submit_regions", "tps_submit_shared", "tps_scan_device_slot"):
         assert must in names, must

@@ -956,6 +956,22 @@ int tps_get_timeline(tps_ctx *ctx, uint32_t back, uint32_t base_back, float ms[T
   return TPS_OK;
 }
 
+int tps_elapsed_between(tps_ctx *from, uint32_t from_back, uint32_t from_event, tps_ctx *to, uint32_t to_back,
+                        uint32_t to_event, float *ms) {
+  if (!from || !to || !ms || from_event > 3 || to_event > 3) return TPS_EINVAL;
+  if (from->device != to->device) return fail(to, TPS_EINVAL, "the two scans ran on different devices");
+  if (from_back >= TPS_TIMING_RING || from_back >= from->scan_seq || to_back >= TPS_TIMING_RING || to_back >= to->scan_seq)
+    return fail(to, TPS_ESTATE, "timed scan %u / %u steps back is not recorded (ring of %d)", from_back, to_back,
+                TPS_TIMING_RING);
+  cudaEvent_t *e0 = from->ev[(from->scan_seq - 1 - from_back) % TPS_TIMING_RING];
+  cudaEvent_t *e1 = to->ev[(to->scan_seq - 1 - to_back) % TPS_TIMING_RING];
+  TPS_CUDA(to, cudaSetDevice(to->device));
+  TPS_CUDA(to, cudaEventSynchronize(e0[3]));
+  TPS_CUDA(to, cudaEventSynchronize(e1[3]));
+  TPS_CUDA(to, cudaEventElapsedTime(ms, e0[from_event], e1[to_event]));
+  return TPS_OK;
+}
+
 int tps_follow_scan(int device, const uint8_t *bases, const uint64_t *offsets, uint32_t n_reads, const char *patterns,
                     uint32_t n_patterns, uint32_t k, uint32_t match_len, uint32_t min_seq_length, uint32_t skip,
                     uint32_t upto, uint32_t *sel_out, uint64_t sel_words) {

@@ -116,6 +116,8 @@ def load_library() -> C.CDLL:
     lib.tps_get_timings.argtypes = [vp, C.c_uint32, C.POINTER(C.c_float * 4)]
     lib.tps_get_timeline.restype = C.c_int
     lib.tps_get_timeline.argtypes = [vp, C.c_uint32, C.c_uint32, C.POINTER(C.c_float * 4)]
+    lib.tps_elapsed_between.restype = C.c_int
+    lib.tps_elapsed_between.argtypes = [vp, C.c_uint32, C.c_uint32, vp, C.c_uint32, C.c_uint32, C.POINTER(C.c_float)]
     lib.tps_kernel_launches.restype = C.c_uint64
     lib.tps_kernel_launches.argtypes = [vp]
     lib.tps_debug_copy.restype = C.c_int
@@ -500,6 +502,13 @@ class ScanContext:
         ms = (C.c_float * 4)()
         self._check(self.lib.tps_get_timeline(self._h, back, base_back, C.byref(ms)))
         return tuple(float(x) for x in ms)
+
+    def elapsed_to(self, back: int, event: int, other: "ScanContext", other_back: int, other_event: int) -> float:
+        """Device time (ms) from event `event` (0 K1 start .. 3 scan end) of this context's scan_device call `back`
+        calls ago to event `other_event` of `other`'s call `other_back` calls ago (tps_elapsed_between)."""
+        ms = C.c_float()
+        self._check(self.lib.tps_elapsed_between(self._h, back, event, other._h, other_back, other_event, C.byref(ms)))
+        return float(ms.value)
 
     def kernel_launches(self) -> int:
         return int(self.lib.tps_kernel_launches(self._h))

@@ -97,3 +97,39 @@ def test_ends_first_many_batches_three_phrases_two_workers(synth_file):
     stats, per = pipeline.collect_file(path, cfgs, devices=[0], max_batch_bases=16 << 20, max_batch_reads=1024,
                                        max_pass_reads=8, rawcount_capacity=6617 * 12 * 3, ends_first=True)
     assert _check(per[0], recs, 4, 0.6, W=50, s=3, counts=True) > 40
+
+
+def test_device_span_of_overlapping_scans_across_contexts():
+    """tps_elapsed_between: the device time from the first kernel of one context's scan to the end of another
+    context's later scan (what bench.py times its K steps with) -- ordered, consistent with the per-scan
+    timeline, and loud when a scan is not in the event ring."""
+    import torch
+    from topsicle_b200 import engine, synth
+    from topsicle_b200.patterns import patterns_to_search
+    spec = synth.CONFIGS[2]
+    n = 4000
+    off = synth.read_lengths(spec, 0, n)
+    host = np.empty(int(off[-1]), dtype=np.uint8)
+    synth.fill_reads(spec, 0, off, host)
+    dev = torch.device("cuda", 0)
+    db = torch.empty((host.size + 2047) // 2048 * 2048, dtype=torch.uint8, device=dev)
+    db[:host.size].copy_(torch.from_numpy(host))
+    do = torch.from_numpy(off.view(np.int64)).to(dev)
+    rows = [torch.empty(n * 40, dtype=torch.uint8, device=dev) for _ in range(4)]
+    kw = dict(cutoff=0.7, min_seq_length=9000, n_slots=3, max_batch_reads=n, max_batch_bases=host.size + 4096)
+    with engine.ScanContext(patterns_to_search("CCCTAA", 4), len_telopattern=6, slide=6, **kw) as a, \
+            engine.ScanContext(patterns_to_search("TTTAGGG", 5), len_telopattern=7, slide=7, **kw) as b:
+        for i in range(6):          # a, b, a, b, a, b on rotating slots
+            c = a if i % 2 == 0 else b
+            c.scan_device(db.data_ptr(), do.data_ptr(), n, host.size, rows[i % 4].data_ptr(), slot=(i // 2) % 3)
+        a.sync()
+        b.sync()
+        span = a.elapsed_to(2, 0, b, 0, 3)                    # first scan of a -> end of the last scan of b
+        assert span > 0
+        own = a.timeline(0, 2)                                # a's last scan relative to a's first
+        assert 0 < own[0] <= own[3] and a.elapsed_to(2, 0, a, 0, 3) == pytest.approx(own[3], rel=1e-3, abs=1e-3)
+        assert span >= a.elapsed_to(2, 0, b, 2, 3) > 0        # b's first scan ended earlier than its last
+        t = [c.timings(0)["total"] for c in (a, b)]
+        assert span >= max(t)
+        with pytest.raises(engine.TpsError):
+            a.elapsed_to(3, 0, b, 0, 3)                       # a has only three scans on record

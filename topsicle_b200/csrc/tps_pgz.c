@@ -14,10 +14,17 @@
  *   3. every thread decodes from its block start to the next thread's block start.  It does not know the 32 KiB
  *      of text before its start, so it decodes into 16-bit SYMBOLS: 0..255 = a literal byte, 256 + i = "byte i of
  *      the unknown window"; copies of symbols are symbols.  Thread k must land EXACTLY on the block start thread
- *      k+1 found (else everything after k is thrown away and redone from where k stopped);
- *   4. the last 32 KiB of every piece are resolved in order (a cheap sequential chain), then all pieces are
- *      translated to bytes in parallel, straight into the caller's buffer, each thread taking the CRC-32 of its
- *      bytes on the way; the CRCs are combined and compared with the gzip trailer at the end of the member.
+ *      k+1 found (else everything after k is thrown away and redone from where k stopped).  Once the last
+ *      32 KiB a piece has produced hold no symbol of the unknown window any more (in FASTQ text: a few hundred
+ *      kilobytes into a piece of eight megabytes) the piece goes over to plain BYTE output at the next block;
+ *      the first piece of a stretch knows its window and decodes to bytes from the start;
+ *   4. the last 32 KiB of every piece are resolved in order (a cheap sequential chain), then the symbolic fronts
+ *      of all pieces are translated to bytes and their byte parts copied, in parallel, straight into the caller's
+ *      buffer, each thread taking the CRC-32 of its bytes on the way (folded with PCLMULQDQ); the CRCs are
+ *      combined and compared with the gzip trailer at the end of the member.
+ *
+ * The block decoders (tps_pgz_decode.inc, compiled for symbols and for bytes) look up to three literals, or a
+ * length code with its base and extra-bit count, in one 12-bit table and distances in a direct 10-bit table.
  *
  * Anything unusual (a stream that is not text, stored / fixed blocks, several members, a wrong guess) costs
  * speed, never correctness: the first piece of every stretch starts at a known position with a known window, and

@@ -26,6 +26,7 @@
 #include <errno.h>
 #include <fcntl.h>
 #include <stdarg.h>
+#include <pthread.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -486,14 +487,86 @@ typedef struct bgzf_blk {
 /* Window buffers of compressed input are hundreds of megabytes, written once by all parser threads and freed with
  * the batch: 2 MiB-aligned and advised as huge pages, so that first touch is one fault per 2 MiB instead of 512
  * (with sixteen threads faulting at once the address-space lock made a cold window cost as much as inflating it). */
+/* Window buffers of compressed input are hundreds of megabytes, live for one batch and are handed back by
+ * tps_fastx_release; a fresh one costs its page faults again (a 512 MiB window: ~0.1 s of a batch's 0.13 s at
+ * 2 Gbases/s), so the last few are kept and reused (process-wide, by all open files). */
+#define WPOOL_LIVE 64
+#define WPOOL_KEEP 3
+static struct {
+  pthread_mutex_t mu;
+  void *live[WPOOL_LIVE];
+  uint64_t live_sz[WPOOL_LIVE];
+  void *kept[WPOOL_KEEP];
+  uint64_t kept_sz[WPOOL_KEEP];
+} wpool = {PTHREAD_MUTEX_INITIALIZER, {0}, {0}, {0}, {0}};
+
 static uint8_t *window_alloc(uint64_t bytes) {
   void *p = NULL;
   const uint64_t sz = (bytes + (2u << 20) - 1) & ~(uint64_t)((2u << 20) - 1);
+  pthread_mutex_lock(&wpool.mu);
+  for (int i = 0; i < WPOOL_KEEP && !p; ++i)
+    if (wpool.kept[i] && wpool.kept_sz[i] >= sz && wpool.kept_sz[i] <= 2 * sz) {
+      p = wpool.kept[i];
+      wpool.kept[i] = NULL;
+      for (int j = 0; j < WPOOL_LIVE; ++j)
+        if (!wpool.live[j]) {
+          wpool.live[j] = p;
+          wpool.live_sz[j] = wpool.kept_sz[i];
+          break;
+        }
+    }
+  pthread_mutex_unlock(&wpool.mu);
+  if (p) return (uint8_t *)p;
   if (posix_memalign(&p, 2u << 20, sz)) return NULL;
 #ifdef MADV_HUGEPAGE
   madvise(p, sz, MADV_HUGEPAGE);
 #endif
+  pthread_mutex_lock(&wpool.mu);
+  for (int j = 0; j < WPOOL_LIVE; ++j)
+    if (!wpool.live[j]) {
+      wpool.live[j] = p;
+      wpool.live_sz[j] = sz;
+      break;
+    }
+  pthread_mutex_unlock(&wpool.mu);
   return (uint8_t *)p;
+}
+
+/* Hands a window buffer back: kept for reuse if it is one of ours and there is room, else freed. */
+static void window_free(void *p) {
+  if (!p) return;
+  uint64_t sz = 0;
+  void *drop = p;
+  pthread_mutex_lock(&wpool.mu);
+  for (int j = 0; j < WPOOL_LIVE; ++j)
+    if (wpool.live[j] == p) {
+      sz = wpool.live_sz[j];
+      wpool.live[j] = NULL;
+      break;
+    }
+  if (sz && !getenv("TPS_FX_NO_POOL")) {
+    int at = -1;
+    for (int i = 0; i < WPOOL_KEEP; ++i)
+      if (!wpool.kept[i]) at = i;
+    if (at < 0) { /* full: the smallest one goes */
+      at = 0;
+      for (int i = 1; i < WPOOL_KEEP; ++i)
+        if (wpool.kept_sz[i] < wpool.kept_sz[at]) at = i;
+      if (wpool.kept_sz[at] < sz) {
+        drop = wpool.kept[at];
+        wpool.kept[at] = NULL;
+      } else {
+        at = -1;
+      }
+    }
+    if (at >= 0) {
+      wpool.kept[at] = p;
+      wpool.kept_sz[at] = sz;
+      if (drop == p) drop = NULL;
+    }
+  }
+  pthread_mutex_unlock(&wpool.mu);
+  free(drop);
 }
 
 static int gz_fill(tps_fastx *fx, uint8_t *chunk, uint64_t *win, uint64_t cap) {
@@ -736,7 +809,7 @@ void tps_fastx_set_window(tps_fastx *fx, uint64_t bytes) {
 void tps_fastx_set_clip(tps_fastx *fx, uint64_t clip_bases) {
   if (fx) fx->clip_bases = clip_bases;
 }
-void tps_fastx_release(void *owner) { free(owner); }
+void tps_fastx_release(void *owner) { window_free(owner); }
 void tps_fastx_set_two_pass(tps_fastx *fx, int on) {
   if (fx) fx->slow_only = on;
 }
@@ -769,17 +842,17 @@ static int acquire_indexed(tps_fastx *fx, uint64_t want, const uint8_t **w_out, 
       } else {
         uint8_t *nc = window_alloc(cap + 1);
         if (!nc) {
-          free(chunk);
+          window_free(chunk);
           return fx_fail(fx, TPS_FX_ENOMEM, "out of memory for a %llu-byte chunk", (unsigned long long)cap);
         }
         memcpy(nc, chunk, win);
-        free(chunk);
+        window_free(chunk);
         chunk = nc;
       }
       {
         int frc = gz_fill(fx, chunk, &win, cap);
         if (frc) {
-          free(chunk);
+          window_free(chunk);
           return frc;
         }
       }
@@ -790,7 +863,7 @@ static int acquire_indexed(tps_fastx *fx, uint64_t want, const uint8_t **w_out, 
     int rc = index_window(fx, w, win, final, &rv);
     if (getenv("TPS_FX_DEBUG")) fprintf(stderr, "[fastx] index %.1f MB in %.4f s, %zu records\n", win / 1e6, dbg_now() - t_ix, rv.n);
     if (rc) {
-      free(chunk);
+      window_free(chunk);
       return rc;
     }
     if (rv.n > 0 || final) break;
@@ -798,7 +871,7 @@ static int acquire_indexed(tps_fastx *fx, uint64_t want, const uint8_t **w_out, 
     free(rv.v);
     memset(&rv, 0, sizeof(rv));
     if (want >= (1ull << 40)) {
-      free(chunk);
+      window_free(chunk);
       return fx_fail(fx, TPS_FX_ECAPACITY, "record larger than 1 TiB");
     }
     want *= 2;
@@ -864,7 +937,7 @@ int tps_fastx_next(tps_fastx *fx, uint64_t bases_cap, uint32_t reads_cap, uint8_
   if (n == 0 && rv.n > 0) {
     uint32_t L = rv.v[0].seq_len;
     free(rv.v);
-    free(chunk);
+    window_free(chunk);
     return fx_fail(fx, TPS_FX_ECAPACITY,
                    "read #%llu has %u bases, more than the batch capacity of %llu%s",
                    (unsigned long long)(fx->n_records + 1), L, (unsigned long long)bases_cap,
@@ -897,7 +970,7 @@ int tps_fastx_next(tps_fastx *fx, uint64_t bases_cap, uint32_t reads_cap, uint8_
     if (n == 0) left = 0;
     uint8_t *nc = (uint8_t *)realloc(fx->carry, left ? left : 1);
     if (!nc) {
-      free(chunk);
+      window_free(chunk);
       return fx_fail(fx, TPS_FX_ENOMEM, "out of memory");
     }
     fx->carry = nc;
@@ -907,7 +980,7 @@ int tps_fastx_next(tps_fastx *fx, uint64_t bases_cap, uint32_t reads_cap, uint8_
       *raw_base = chunk;
       *raw_owner = chunk;
     } else {
-      free(chunk);
+      window_free(chunk);
     }
   }
   fx->n_records += n;
@@ -991,7 +1064,7 @@ int tps_fastx_next_ends(tps_fastx *fx, uint64_t raw_cap, uint64_t bases_cap, uin
   }
   if (n == 0 && rv.n > 0) {
     free(rv.v);
-    free(chunk);
+    window_free(chunk);
     return fx_fail(fx, TPS_FX_ECAPACITY, "the batch capacity of %llu bases cannot hold the ends of one read",
                    (unsigned long long)bases_cap);
   }
@@ -1012,7 +1085,7 @@ int tps_fastx_next_ends(tps_fastx *fx, uint64_t raw_cap, uint64_t bases_cap, uin
     if (n == 0) left = 0;
     uint8_t *nc = (uint8_t *)realloc(fx->carry, left ? left : 1);
     if (!nc) {
-      free(chunk);
+      window_free(chunk);
       return fx_fail(fx, TPS_FX_ENOMEM, "out of memory");
     }
     fx->carry = nc;
@@ -1022,7 +1095,7 @@ int tps_fastx_next_ends(tps_fastx *fx, uint64_t raw_cap, uint64_t bases_cap, uin
       *raw_base = chunk;
       *raw_owner = chunk;
     } else {
-      free(chunk);
+      window_free(chunk);
     }
   }
   fx->n_records += n;
@@ -1206,7 +1279,7 @@ int tps_fastx_next_spans(tps_fastx *fx, uint64_t span_cap, uint32_t reads_cap, u
     {
       int frc = gz_fill(fx, chunk, &win, want);
       if (frc) {
-        free(chunk);
+        window_free(chunk);
         return frc;
       }
     }
@@ -1221,7 +1294,7 @@ int tps_fastx_next_spans(tps_fastx *fx, uint64_t span_cap, uint32_t reads_cap, u
   if (!parts || !sst) {
     free(parts);
     free(sst);
-    free(chunk);
+    window_free(chunk);
     return fx_fail(fx, TPS_FX_ENOMEM, "out of memory");
   }
   double t_ix = dbg_now();
@@ -1299,7 +1372,7 @@ capped:
     uint64_t left = n ? win - consumed : 0;
     uint8_t *nc = (uint8_t *)realloc(fx->carry, left ? left : 1);
     if (!nc) {
-      free(chunk);
+      window_free(chunk);
       return fx_fail(fx, TPS_FX_ENOMEM, "out of memory");
     }
     fx->carry = nc;
@@ -1309,7 +1382,7 @@ capped:
       *raw_base = chunk;
       *raw_owner = chunk;
     } else {
-      free(chunk);
+      window_free(chunk);
     }
   }
   fx->n_records += n;

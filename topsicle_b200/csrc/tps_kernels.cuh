@@ -1236,6 +1236,9 @@ tps_changepoint_kernel(const TpsScanArgs a) {
  * 5 -- in shared memory and finishes with tps_changepoint_block: no second launch, no trip through global memory
  * between the window counts and the change point, and the change points overlap the window counting of the
  * CTA's neighbours.  The code words of the next tile and the record of the next read are prefetched (cp.async).
+ * With few passing reads (at most twice as many as CTAs) a work unit is every second or fourth tile of a read: the
+ * group sums of the parts meet in a global uint16 row per read (gs_rows), tile_done counts the finished parts, and
+ * the CTA that completes a read fetches the row and finds the change point.
  *
  * dynamic shared memory (words): raw[2][TPS_K3N_RAW_WORDS] | pm[2PK] | lin[3*lin_words] | ori[3*(NT+1)] | pad to
  * 16 B | Z[NT+1] uint4 | Zhi[NT+1] uint4 (nz > 4) | UP[NT+2] uint2 | CP[NT+2] uint2 (bordered) | SP[P4][sp_stride]

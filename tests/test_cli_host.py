@@ -304,3 +304,24 @@ def test_record_longer_than_a_batch_is_scanned_by_its_ends(tmp_path, monkeypatch
     with pytest.raises(fastx.FastxError) as e:
         pipeline.collect_file(str(path), [cfg], max_batch_bases=30_000)
     assert e.value.code == -4
+
+
+def test_recommended_cutoff_clamps():
+    """The reference's clamps on the fitted vertex (main.py:277-291): every branch, values and log wording."""
+    from topsicle_b200.main import recommended_cutoff as rc
+    assert rc(0.82, 1.1, 0.9, 0.7) == (0.82, [])                                   # inside the data: kept
+    x, notes = rc(1.4, 1.1, 0.93, 0.7)                                              # right of the data: the median
+    assert x == 0.93 and notes == ["Asymptotic TRC 1.400 is greater than max TRC, which is not expected. See plot.",
+                                   "Using median TRC value (0.930) as asymptotic TRC instead."]
+    x, notes = rc(1.4, 1.2, 1.05, 0.7)                                              # ... or 0.9 when the median is >= 1
+    assert x == 0.9 and notes[1] == "Using 0.9 as asymptotic TRC instead, since asymptotic is greater than 1.0."
+    x, notes = rc(0.35, 0.9, 0.8, 0.3)                                              # below 0.4 but above the input cutoff
+    assert x == 0.35 and notes == ["Quadratic fit suggests asymptotic TRC less than 0.4. See plot with fit line"]
+    x, notes = rc(0.2, 0.38, 0.3, 0.3)                                              # low data and below the input cutoff
+    assert x == 0.3 and len(notes) == 3
+    assert notes[1] == ("Maximum TRC value in data is 0.380, which is less than 0.4, indicating low confidence in "
+                        "telomere detection.")
+    assert notes[2] == ("Asymptotic TRC 0.200 is less than input cutoff 0.300. Topsicle declares input TRC (=0.3) as "
+                        "asymptotic TRC.")
+    x, notes = rc(0.9, 0.5, 0.35, 0.36)                                             # both clamps in a row
+    assert x == 0.36 and len(notes) == 4 and notes[3].startswith("Asymptotic TRC 0.350 is less than input cutoff 0.360")

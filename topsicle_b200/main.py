@@ -159,6 +159,33 @@ class _FileWriter:
             self.subset_handle = None
 
 
+def recommended_cutoff(vertex_x, max_trc, median_trc, inputtrc):
+    """The clamps the reference puts on the vertex of its quadratic fit before it recommends a TRC cutoff
+    (main.py:277-296), as a function -> (cutoff, log lines in the reference's wording).  A vertex to the right of
+    every data point is not believed (the median TRC stands in, or 0.9 when even that is >= 1); a vertex below 0.4
+    is reported, and one below the cutoff the run was started with is replaced by that cutoff."""
+    notes = []
+    x = vertex_x
+    if x > max_trc:
+        notes.append(f"Asymptotic TRC {x:.3f} is greater than max TRC, which is not expected. See plot.")
+        if median_trc < 1.0:
+            x = median_trc
+            notes.append(f"Using median TRC value ({median_trc:.3f}) as asymptotic TRC instead.")
+        else:
+            x = 0.9
+            notes.append("Using 0.9 as asymptotic TRC instead, since asymptotic is greater than 1.0.")
+    if x < 0.4:
+        notes.append("Quadratic fit suggests asymptotic TRC less than 0.4. See plot with fit line")
+        if max_trc < 0.4:
+            notes.append(f"Maximum TRC value in data is {max_trc:.3f}, which is less than 0.4, indicating low "
+                         "confidence in telomere detection.")
+        if x < inputtrc:
+            notes.append(f"Asymptotic TRC {x:.3f} is less than input cutoff {inputtrc:.3f}. Topsicle "
+                         f"declares input TRC (={inputtrc}) as asymptotic TRC.")
+            x = inputtrc
+    return x, notes
+
+
 def scan_configs(args, telo_phrases, patterns, sliding_val):
     """One ScanConfig per telophrase == the arguments the reference passes down (main.py:57,129-130,147-148)."""
     min_cutoff = min(args.cutoff) if isinstance(args.cutoff, (list, tuple)) else args.cutoff
@@ -334,23 +361,9 @@ def analysis_run(args):
             vertex_x, vertex_y, coeffs = fit_quadratic_and_find_vertex(
                 phrase_to_trc[phrase], phrase_to_telo[phrase], inputtrc=inputtrc, median_trc=median_trc,
                 save_path=plot_path)
-            if vertex_x > max_trc:
-                tprint(f"Asymptotic TRC {vertex_x:.3f} is greater than max TRC, which is not expected. See plot.")
-                if median_trc < 1.0:
-                    tprint(f"Using median TRC value ({median_trc:.3f}) as asymptotic TRC instead.")
-                    vertex_x = median_trc
-                else:
-                    tprint("Using 0.9 as asymptotic TRC instead, since asymptotic is greater than 1.0.")
-                    vertex_x = 0.9
-            if vertex_x < 0.4:
-                tprint("Quadratic fit suggests asymptotic TRC less than 0.4. See plot with fit line")
-                if max_trc < 0.4:
-                    tprint(f"Maximum TRC value in data is {max_trc:.3f}, which is less than 0.4, indicating low "
-                           "confidence in telomere detection.")
-                if vertex_x < inputtrc:
-                    tprint(f"Asymptotic TRC {vertex_x:.3f} is less than input cutoff {inputtrc:.3f}. Topsicle "
-                           f"declares input TRC (={inputtrc}) as asymptotic TRC.")
-                    vertex_x = inputtrc
+            vertex_x, notes = recommended_cutoff(vertex_x, max_trc, median_trc, inputtrc)
+            for note in notes:
+                tprint(note)
             tprint(f"asymptotic TRC, or recommended cutoff: {vertex_x:.3f}")
             filtered_telolen = [telo for trc, telo in zip(phrase_to_trc[phrase], phrase_to_telo[phrase])
                                 if trc >= vertex_x]

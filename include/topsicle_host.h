@@ -133,6 +133,9 @@ int tps_pgz_eof(const tps_pgz *g);
 const char *tps_pgz_error(const tps_pgz *g);
 void tps_pgz_get_stats(const tps_pgz *g, tps_pgz_stats *out);
 void tps_pgz_set_piece(tps_pgz *g, uint64_t bytes); /* compressed bytes per thread and stretch (tests, tuning) */
+/* One complete raw deflate stream with an empty window that inflates to exactly `want` <= 65536 bytes (a BGZF
+ * block): bytes to dst, their CRC-32 to *crc_out.  0 ok, -1 corrupt or of another length, -3 not applicable. */
+int tps_pgz_inflate_block(const uint8_t *z, uint64_t zlen, uint8_t *dst, uint64_t want, uint32_t *crc_out);
 /* The same counters of the reader's own inflater (all zero unless `fx` reads plain gzip). */
 void tps_fastx_inflate_stats(const tps_fastx *fx, tps_pgz_stats *out);
 

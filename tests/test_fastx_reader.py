@@ -242,10 +242,13 @@ def _write_bgzf(path, data, block=0xff00):
                      struct.pack("<II", zlib.crc32(chunk) & 0xffffffff, len(chunk)))
 
 
-@pytest.mark.parametrize("threads", [1, 4])
-def test_bgzf_blocks_inflated_in_parallel(tmp_path, threads):
+@pytest.mark.parametrize("threads", [1, 4, -4])
+def test_bgzf_blocks_inflated_in_parallel(tmp_path, threads, monkeypatch):
     """A BGZF (.gz) file gives the same records as the plain-gzip file, through every reader entry point;
     Python's gzip (what the reference uses) reads it too; a corrupt block is an error, not a short file."""
+    if threads < 0:                                     # the blocks through zlib instead of the repo's byte decoder
+        monkeypatch.setenv("TPS_FX_BGZF_ZLIB", "1")
+        threads = -threads
     src = os.path.join(GOLD, "demo.fastq.gz")
     text = gzip.open(src, "rb").read() * 3              # ~5 MB, 80 blocks
     path = str(tmp_path / "demo3.fastq.gz")

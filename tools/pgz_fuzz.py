@@ -26,6 +26,8 @@ def lib():
     L.tps_pgz_error.restype = C.c_char_p
     L.tps_pgz_error.argtypes = [C.c_void_p]
     L.tps_pgz_set_piece.argtypes = [C.c_void_p, C.c_uint64]
+    L.tps_pgz_inflate_block.restype = C.c_int
+    L.tps_pgz_inflate_block.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32)]
     return L
 
 
@@ -98,6 +100,24 @@ def main():
         if b"".join(got) != text:
             raise SystemExit(f"case {case}: MISMATCH kind {kind} n {n} members {members} {env} threads {threads} cap {cap}")
         n_par += threads > 1
+        # the single-block entry (BGZF blocks): a raw deflate stream of <= 64 KiB of the same text, and a damaged one
+        cut = text[:int(rng.integers(0, 65537))]
+        co = zlib.compressobj(int(rng.integers(0, 10)), zlib.DEFLATED, -15, int(rng.integers(1, 10)),
+                              strategies[int(rng.integers(0, 5))])
+        raw = co.compress(cut) + co.flush()
+        rb = np.frombuffer(raw, np.uint8)
+        out = np.empty(max(len(cut), 1), np.uint8)
+        crc = C.c_uint32()
+        rc = L.tps_pgz_inflate_block(rb.ctypes.data, len(raw), out.ctypes.data, len(cut), C.byref(crc))
+        if rc != 0 or out[:len(cut)].tobytes() != cut or crc.value != (zlib.crc32(cut) & 0xffffffff):
+            raise SystemExit(f"case {case}: single block rc {rc} kind {kind} len {len(cut)} {env}")
+        if len(raw) > 40:
+            bad = bytearray(raw)
+            bad[len(bad) // 2] ^= 0x41
+            bb = np.frombuffer(bytes(bad), np.uint8)
+            rc = L.tps_pgz_inflate_block(bb.ctypes.data, len(bad), out.ctypes.data, len(cut), C.byref(crc))
+            if rc == 0 and crc.value == (zlib.crc32(cut) & 0xffffffff) and out[:len(cut)].tobytes() != cut:
+                raise SystemExit(f"case {case}: damaged block accepted with the right CRC but other bytes")
     print(f"{a.cases} cases identical ({n_par} with more than one thread)")
 
 

@@ -617,25 +617,32 @@ static int gz_fill(tps_fastx *fx, uint8_t *chunk, uint64_t *win, uint64_t cap) {
     z += bsize;
   }
   int bad = 0;
+  const int bgzf_zlib = getenv("TPS_FX_BGZF_ZLIB") != NULL && atoi(getenv("TPS_FX_BGZF_ZLIB")) != 0;
 #pragma omp parallel for num_threads(fx->threads) schedule(dynamic, 8) if (nb > 16)
   for (int64_t i = 0; i < (int64_t)nb; ++i) {
     const bgzf_blk *b = &blk[i];
     if (b->isize == 0) continue; /* the empty end-of-file block */
-    z_stream zs;
-    memset(&zs, 0, sizeof(zs));
-    int ok = inflateInit2(&zs, -15) == Z_OK;
-    if (ok) {
-      zs.next_in = (Bytef *)(fx->zmap + b->zoff + b->hdr);
-      zs.avail_in = b->zsize - b->hdr - 8u;
-      zs.next_out = chunk + b->out;
-      zs.avail_out = b->isize;
-      ok = inflate(&zs, Z_FINISH) == Z_STREAM_END && zs.total_out == b->isize;
-      inflateEnd(&zs);
-    }
-    if (ok) {
-      const uint8_t *t = fx->zmap + b->zoff + b->zsize - 8;
-      const uint32_t want = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
-      ok = (uint32_t)crc32(crc32(0L, Z_NULL, 0), chunk + b->out, b->isize) == want;
+    const uint8_t *t = fx->zmap + b->zoff + b->zsize - 8;
+    const uint32_t want = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
+    /* the table-driven byte decoder of tps_pgz.c with the folded CRC-32 (about twice zlib's rate on FASTQ text);
+     * zlib when it does not apply (TPS_FX_BGZF_ZLIB=1 forces zlib: A/B, tests) */
+    uint32_t got = 0;
+    int rc = bgzf_zlib ? -3 : tps_pgz_inflate_block(fx->zmap + b->zoff + b->hdr, b->zsize - b->hdr - 8u, chunk + b->out,
+                                                    b->isize, &got);
+    int ok = rc == 0 && got == want;
+    if (rc == -3) {
+      z_stream zs;
+      memset(&zs, 0, sizeof(zs));
+      ok = inflateInit2(&zs, -15) == Z_OK;
+      if (ok) {
+        zs.next_in = (Bytef *)(fx->zmap + b->zoff + b->hdr);
+        zs.avail_in = b->zsize - b->hdr - 8u;
+        zs.next_out = chunk + b->out;
+        zs.avail_out = b->isize;
+        ok = inflate(&zs, Z_FINISH) == Z_STREAM_END && zs.total_out == b->isize;
+        inflateEnd(&zs);
+      }
+      if (ok) ok = (uint32_t)crc32(crc32(0L, Z_NULL, 0), chunk + b->out, b->isize) == want;
     }
     if (!ok) {
 #pragma omp atomic write

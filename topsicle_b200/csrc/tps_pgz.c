@@ -475,10 +475,12 @@ static int read_block_header(bitrd *b, blockhdr *h) {
 typedef struct obuf16 { /* symbols */
   uint16_t *out;
   uint64_t n, cap;
+  int fixed; /* the buffer is not ours to grow */
 } obuf16;
 typedef struct obuf8 { /* bytes */
   uint8_t *out;
   uint64_t n, cap;
+  int fixed;
 } obuf8;
 
 /* One piece of a stretch.  Its text is sym.n symbols followed by byt.n bytes: a piece that starts with an unknown
@@ -518,6 +520,7 @@ static uint16_t *sym_alloc(uint64_t n) { return (uint16_t *)big_alloc(n * sizeof
 
 static int grow_sym(obuf16 *s, uint64_t need) {
   if (s->n + need <= s->cap) return 0;
+  if (s->fixed) return -1;
   uint64_t nc = s->cap ? s->cap * 2 : (1u << 22);
   while (nc < s->n + need) nc *= 2;
   uint16_t *nv = sym_alloc(nc);
@@ -530,6 +533,7 @@ static int grow_sym(obuf16 *s, uint64_t need) {
 }
 static int grow_byte(obuf8 *s, uint64_t need) {
   if (s->n + need <= s->cap) return 0;
+  if (s->fixed) return -1;
   uint64_t nc = s->cap ? s->cap * 2 : (1u << 22);
   while (nc < s->n + need) nc *= 2;
   uint8_t *nv = (uint8_t *)big_alloc(nc);
@@ -626,6 +630,42 @@ static void decode_segment(const uint8_t *z, uint64_t zlen, seg *s, const uint16
     }
   }
   free(h);
+}
+
+/* One complete raw deflate stream that starts with an empty window and inflates to exactly `want` <= 65536 bytes (a
+ * BGZF block) -> dst, with the CRC-32 of the bytes.  Uses the byte decoders above; thread-safe (per-thread tables and
+ * scratch).  0 ok, -1 corrupt / another length, -3 not applicable (want too large, out of memory). */
+int tps_pgz_inflate_block(const uint8_t *z, uint64_t zlen, uint8_t *dst, uint64_t want, uint32_t *crc_out) {
+  static __thread blockhdr *h = NULL;
+  static __thread uint8_t *scratch = NULL;
+  static const uint8_t no_window[PGZ_WSIZE] = {0};
+  if (!z || !dst || !crc_out || want > 65536u) return -3;
+  if (!h) h = (blockhdr *)malloc(sizeof(blockhdr));
+  if (!scratch) scratch = (uint8_t *)malloc(65536u + 2048u);
+  if (!h || !scratch) return -3;
+  obuf8 o;
+  o.out = scratch;
+  o.n = 0;
+  o.cap = 65536u + 2048u;
+  o.fixed = 1;
+  bitrd b;
+  br_init(&b, z, zlen, 0);
+  for (;;) {
+    if (read_block_header(&b, h)) return -1;
+    int rc;
+    if (h->type != 0 && pgz_fast_on) {
+      build_fast(h);
+      rc = decode_block_fast_byte(&b, h, &o, no_window);
+    } else {
+      rc = decode_block_impl_byte(&b, h, &o, no_window, 0, 0);
+    }
+    if (rc || o.n > want) return -1;
+    if (h->final) break;
+  }
+  if (o.n != want) return -1;
+  memcpy(dst, scratch, want);
+  *crc_out = pgz_crc32((uint32_t)crc32(0L, Z_NULL, 0), dst, want);
+  return 0;
 }
 
 /* First bit position >= from (and < limit) where a dynamic-Huffman block starts: valid header, the block decodes
